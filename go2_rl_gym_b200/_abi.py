@@ -1,0 +1,122 @@
+"""ctypes mirror of include/go2_b200.h and the loader of the CUDA library.
+
+The product path has NO CPU fallback: `load_library()` raises if `libgo2b200.so` is missing
+(build it with `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes as C
+import os
+
+NUM_DOF, NUM_DYN, NUM_REPORT, NUM_COL = 12, 13, 19, 32
+NUM_OBS, NUM_PRIV, NUM_HEIGHT, NUM_REW, NUM_CMD = 45, 263, 187, 14, 4
+INERTIA_STRIDE = 10
+EP_STATS = NUM_REW + 12
+
+REWARD_NAMES = ["tracking_lin_vel", "tracking_ang_vel", "lin_vel_z", "ang_vel_xy", "dof_acc", "dof_power", "torques",
+                "correct_base_height", "action_rate", "action_smoothness", "collision", "dof_pos_limits",
+                "feet_regulation", "hip_to_default"]
+
+f32, i32, u32 = C.c_float, C.c_int32, C.c_uint32
+
+
+class Go2Model(C.Structure):
+    _fields_ = [("joint_origin", f32 * 3 * NUM_DOF), ("joint_axis", i32 * NUM_DOF),
+                ("q_lower", f32 * NUM_DOF), ("q_upper", f32 * NUM_DOF), ("effort", f32 * NUM_DOF),
+                ("vel_limit", f32 * NUM_DOF), ("col_pos", f32 * 3 * NUM_COL), ("col_radius", f32 * NUM_COL),
+                ("col_dyn", i32 * NUM_COL), ("col_report", i32 * NUM_COL), ("foot_offset", f32 * 3 * 4)]
+
+
+class Go2EnvConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", i32), ("env_offset", i32), ("seed_lo", u32), ("seed_hi", u32),
+        ("sim_dt", f32), ("decimation", i32), ("gravity_z", f32),
+        ("kp", f32 * NUM_DOF), ("kd", f32 * NUM_DOF), ("default_dof_pos", f32 * NUM_DOF),
+        ("action_scale", f32), ("clip_actions", f32), ("clip_obs", f32),
+        ("randomize_action_delay", i32), ("randomize_motor_strength", i32), ("randomize_motor_zero_offset", i32),
+        ("randomize_pd_gains", i32), ("push_robots", i32), ("add_noise", i32),
+        ("motor_strength_range", f32 * 2), ("motor_zero_offset_range", f32 * 2), ("kp_mult_range", f32 * 2),
+        ("kd_mult_range", f32 * 2),
+        ("push_interval", i32), ("max_push_vel_xy", f32), ("max_push_ang_vel", f32),
+        ("solver_iters", i32), ("erp", f32), ("limit_erp", f32), ("contact_offset", f32), ("max_depen_vel", f32),
+        ("bounce_threshold", f32), ("penetration_slop", f32), ("terrain_friction", f32), ("terrain_restitution", f32),
+        ("mesh_type", i32), ("hf_rows", i32), ("hf_cols", i32), ("hscale", f32), ("vscale", f32), ("border", f32),
+        ("num_levels", i32), ("num_types", i32), ("terrain_length", f32),
+        ("terrain_curriculum", i32), ("move_down_by_accumulated_xy_command", i32), ("custom_origins", i32),
+        ("resampling_time", f32), ("dynamic_resample_commands", i32), ("limit_vel_prob", f32),
+        ("limit_vel_invert_when_continuous", i32), ("limit_ang_vel_at_zero_command_prob", f32),
+        ("max_episode_length", i32), ("max_episode_length_s", f32), ("dt", f32),
+        ("reward_scales", f32 * NUM_REW), ("tracking_sigma", f32), ("base_height_target", f32),
+        ("soft_dof_limit_lo", f32 * NUM_DOF), ("soft_dof_limit_hi", f32 * NUM_DOF),
+        ("dynamic_sigma", i32), ("ds_min_lin", f32), ("ds_max_lin", f32), ("ds_min_ang", f32), ("ds_max_ang", f32),
+        ("ds_max_sigma", f32 * 9),
+        ("obs_scale_lin_vel", f32), ("obs_scale_ang_vel", f32), ("obs_scale_dof_pos", f32), ("obs_scale_dof_vel", f32),
+        ("obs_scale_height", f32), ("noise_scale_vec", f32 * NUM_OBS),
+        ("height_points", f32 * 2 * NUM_HEIGHT), ("base_height_mask", f32 * NUM_HEIGHT),
+        ("num_base_height_points", f32), ("base_init_state", f32 * 13),
+    ]
+
+
+class Go2StepParams(C.Structure):
+    _fields_ = [("common_step_counter", u32), ("reward_curriculum", f32 * NUM_REW), ("zero_command_proba", f32),
+                ("max_lin_vel", f32), ("ep_slot", i32)]
+
+
+_PTR_FIELDS = [
+    "root_states", "dof_pos", "dof_vel", "torques", "contact_forces", "feet_pos", "feet_vel",
+    "actions", "last_actions", "last_last_actions", "last_dof_vel", "obs_buf", "privileged_obs_buf", "rew_buf",
+    "reset_buf", "time_out_buf", "episode_length_buf",
+    "base_lin_vel", "base_ang_vel", "projected_gravity", "measured_heights",
+    "commands", "commands_resampling_step", "commands_xy_accumulation", "last_is_limit_vel", "env_command_ranges",
+    "terrain_levels", "terrain_types", "terrain_ids", "env_origins", "max_move_distance", "terrain_origins",
+    "height_samples",
+    "motor_strengths", "motor_zero_offsets", "p_gains_multiplier", "d_gains_multiplier", "friction_coeffs",
+    "restitutions", "body_inertia", "episode_sums", "ep_stats", "ep_accum",
+]
+
+
+class Go2EnvBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _PTR_FIELDS]
+
+
+PTR_FIELDS = tuple(_PTR_FIELDS)
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgo2b200.so")
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Load libgo2b200.so (hand-written sm_100a kernels + C ABI). Raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with: python -c 'import __graft_entry__ as g; g.build()'")
+    lib = C.CDLL(_LIB_PATH)
+    vp = C.c_void_p
+    lib.go2_env_create.argtypes = [C.POINTER(Go2EnvConfig), C.POINTER(Go2Model), C.POINTER(Go2EnvBuffers), C.POINTER(vp)]
+    lib.go2_env_create.restype = C.c_int
+    lib.go2_env_destroy.argtypes = [vp]
+    lib.go2_env_destroy.restype = None
+    lib.go2_env_step.argtypes = [vp, vp, C.POINTER(Go2StepParams), vp]
+    lib.go2_env_step.restype = C.c_int
+    lib.go2_env_step_host.argtypes = [vp, vp, C.POINTER(Go2StepParams), vp, vp, vp, vp, vp]
+    lib.go2_env_step_host.restype = C.c_int
+    lib.go2_env_reset_all.argtypes = [vp, C.POINTER(Go2StepParams), vp]
+    lib.go2_env_reset_all.restype = C.c_int
+    lib.go2_env_substeps.argtypes = [vp, vp, C.c_int, vp]
+    lib.go2_env_substeps.restype = C.c_int
+    lib.go2_last_error.restype = C.c_char_p
+    lib.go2_kernel_launch_count.restype = C.c_longlong
+    _LIB = lib
+    return lib
+
+
+def check(rc, lib=None):
+    if rc != 0:
+        lib = lib or load_library()
+        raise RuntimeError(f"libgo2b200 error {rc}: {lib.go2_last_error().decode()}")

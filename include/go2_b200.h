@@ -1,0 +1,197 @@
+/* go2_b200.h — C ABI of the B200-native Go2 environment step + PPO trainer kernels.
+ *
+ * The reference (wty-yy/go2_rl_gym) is pure Python and has no FFI of its own; its only native
+ * boundary is the Isaac Gym tensor API reached through `self.gym.*`
+ * (legged_gym/envs/base/legged_robot.py:82-92,107-109,632,705,722,769-787).  This header is the
+ * boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): plain pointers and sizes,
+ * caller-owned device memory, an int return code, no exceptions, no torch types.
+ *
+ * Every per-env quantity is its own row-major [num_envs, d] array ("structure of arrays of rows");
+ * one warp owns one env and reads each row with lanes 0..d-1, i.e. one coalesced transaction per row.
+ * The arrays are exactly the tensors the reference exposes as attributes of LeggedRobot
+ * (legged_robot.py:765-859), so the Python shell wraps them zero-copy.
+ */
+#ifndef GO2_B200_H
+#define GO2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GO2_NUM_DOF 12
+#define GO2_NUM_DYN 13       /* dynamic bodies after merging fixed joints */
+#define GO2_NUM_REPORT 19    /* rigid bodies Isaac Gym reports (dont_collapse links kept) */
+#define GO2_NUM_COL 32       /* sphere collider samples, one per lane */
+#define GO2_NUM_OBS 45       /* go2_env.py:26-32 */
+#define GO2_NUM_PRIV 263     /* go2_env.py:36-47 */
+#define GO2_NUM_HEIGHT 187   /* 17 x 11 scan, legged_robot_config.py:26-27 */
+#define GO2_NUM_REW 14       /* active reward terms of GO2Cfg (go2_config.py:178-194) */
+#define GO2_NUM_CMD 4
+#define GO2_INERTIA_STRIDE 10 /* mass, com xyz, Ixx Iyy Izz Ixy Ixz Iyz (about COM, link frame) */
+#define GO2_EP_STATS (GO2_NUM_REW + 12) /* rew means [14], terrain level mean, per-terrain-id means [9], n_reset, spare */
+
+/* order of reward terms everywhere (scales, curriculum scales, episode_sums columns) */
+enum Go2Reward {
+  GO2_REW_TRACKING_LIN_VEL = 0, GO2_REW_TRACKING_ANG_VEL, GO2_REW_LIN_VEL_Z, GO2_REW_ANG_VEL_XY,
+  GO2_REW_DOF_ACC, GO2_REW_DOF_POWER, GO2_REW_TORQUES, GO2_REW_CORRECT_BASE_HEIGHT, GO2_REW_ACTION_RATE,
+  GO2_REW_ACTION_SMOOTHNESS, GO2_REW_COLLISION, GO2_REW_DOF_POS_LIMITS, GO2_REW_FEET_REGULATION,
+  GO2_REW_HIP_TO_DEFAULT
+};
+
+/* Robot constants shared by all envs (from go2.urdf via tools/gen_go2_model.py). */
+typedef struct Go2Model {
+  float joint_origin[GO2_NUM_DOF][3]; /* joint frame origin in the parent body frame */
+  int32_t joint_axis[GO2_NUM_DOF];    /* 0=x 1=y 2=z */
+  float q_lower[GO2_NUM_DOF], q_upper[GO2_NUM_DOF];
+  float effort[GO2_NUM_DOF];          /* torque_limits, legged_robot.py:370 */
+  float vel_limit[GO2_NUM_DOF];
+  float col_pos[GO2_NUM_COL][3];      /* sphere centre in its dynamic body's frame */
+  float col_radius[GO2_NUM_COL];
+  int32_t col_dyn[GO2_NUM_COL];       /* dynamic body 0..12 */
+  int32_t col_report[GO2_NUM_COL];    /* reported body 0..18 (contact_forces row) */
+  float foot_offset[4][3];            /* *_foot link origin in the calf frame */
+} Go2Model;
+
+/* Static configuration (LeggedRobotCfg / GO2Cfg values the step needs). */
+typedef struct Go2EnvConfig {
+  int32_t num_envs;          /* envs owned by this handle (this rank's shard) */
+  int32_t env_offset;        /* global index of local env 0 (multi-GPU sharding keeps global ids for RNG) */
+  uint32_t seed_lo, seed_hi; /* Philox key */
+  /* sim / control (legged_robot_config.py:242-259, go2_config.py:77-85) */
+  float sim_dt; int32_t decimation; float gravity_z;
+  float kp[GO2_NUM_DOF], kd[GO2_NUM_DOF], default_dof_pos[GO2_NUM_DOF];
+  float action_scale, clip_actions, clip_obs;
+  /* domain randomisation switches and ranges (go2_config.py:39-75) */
+  int32_t randomize_action_delay, randomize_motor_strength, randomize_motor_zero_offset, randomize_pd_gains;
+  int32_t push_robots, add_noise;
+  float motor_strength_range[2], motor_zero_offset_range[2], kp_mult_range[2], kd_mult_range[2];
+  int32_t push_interval; float max_push_vel_xy, max_push_ang_vel;
+  /* contact / limit solver (physics spec) */
+  int32_t solver_iters; float erp, limit_erp, contact_offset, max_depen_vel, bounce_threshold, penetration_slop;
+  float terrain_friction, terrain_restitution;
+  /* terrain (legged_robot_config.py:15-41) */
+  int32_t mesh_type;         /* 0 plane, 1 heightfield (trimesh is served by the heightfield path) */
+  int32_t hf_rows, hf_cols;  /* height_samples is [hf_rows(x), hf_cols(y)] int16 */
+  float hscale, vscale, border;
+  int32_t num_levels, num_types; /* terrain.num_rows, terrain.num_cols */
+  float terrain_length;      /* cfg.terrain.terrain_length (8 m) */
+  int32_t terrain_curriculum, move_down_by_accumulated_xy_command, custom_origins;
+  /* commands (go2_config.py:97-146) */
+  float resampling_time; int32_t dynamic_resample_commands;
+  float limit_vel_prob; int32_t limit_vel_invert_when_continuous; float limit_ang_vel_at_zero_command_prob;
+  /* episode */
+  int32_t max_episode_length; float max_episode_length_s; float dt; /* dt = decimation * sim_dt */
+  /* rewards: scales already multiplied by dt (legged_robot.py:920), GO2 order (enum Go2Reward) */
+  float reward_scales[GO2_NUM_REW];
+  float tracking_sigma, base_height_target;
+  float soft_dof_limit_lo[GO2_NUM_DOF], soft_dof_limit_hi[GO2_NUM_DOF];
+  int32_t dynamic_sigma; float ds_min_lin, ds_max_lin, ds_min_ang, ds_max_ang, ds_max_sigma[9];
+  /* observations (go2_env.py:9-53) */
+  float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel, obs_scale_height;
+  float noise_scale_vec[GO2_NUM_OBS];
+  float height_points[GO2_NUM_HEIGHT][2];   /* body-frame xy of the scan grid (legged_robot.py:1172-1186) */
+  float base_height_mask[GO2_NUM_HEIGHT];   /* legged_robot.py:790-795 */
+  float num_base_height_points;
+  float base_init_state[13];                /* pos, quat xyzw, lin vel, ang vel (legged_robot.py:1000) */
+} Go2EnvConfig;
+
+/* Per-step scalars the host derives from common_step_counter (curricula), no device sync involved. */
+typedef struct Go2StepParams {
+  uint32_t common_step_counter;   /* value AFTER this step's increment (legged_robot.py:112) */
+  float reward_curriculum[GO2_NUM_REW]; /* legged_robot.py:144-168, 1.0 where no curriculum */
+  float zero_command_proba;       /* legged_robot.py:556-557 */
+  float max_lin_vel;              /* legged_robot.py:442 */
+  int32_t ep_slot;                /* row of ep_stats this step writes */
+} Go2StepParams;
+
+/* Caller-owned arrays (device pointers for the CUDA library, host pointers for the oracle). */
+typedef struct Go2EnvBuffers {
+  /* simulation state */
+  float* root_states;      /* [N,13] pos, quat xyzw, world lin vel, world ang vel */
+  float* dof_pos;          /* [N,12] */
+  float* dof_vel;          /* [N,12] */
+  float* torques;          /* [N,12] last substep, after motor strength */
+  float* contact_forces;   /* [N,19,3] world, last substep */
+  float* feet_pos;         /* [N,4,3] world (rigid_body_states[:, feet, 0:3]) */
+  float* feet_vel;         /* [N,4,3] world linear velocity */
+  /* policy interface */
+  float* actions;          /* [N,12] clipped copy of the step input */
+  float* last_actions;     /* [N,12] */
+  float* last_last_actions;/* [N,12] */
+  float* last_dof_vel;     /* [N,12] */
+  float* obs_buf;          /* [N,45] */
+  float* privileged_obs_buf;/* [N,263] */
+  float* rew_buf;          /* [N] */
+  uint8_t* reset_buf;      /* [N] */
+  uint8_t* time_out_buf;   /* [N] */
+  int32_t* episode_length_buf; /* [N] */
+  /* derived base-frame quantities (legged_robot.py:119-125) */
+  float* base_lin_vel;     /* [N,3] */
+  float* base_ang_vel;     /* [N,3] */
+  float* projected_gravity;/* [N,3] */
+  float* measured_heights; /* [N,187] */
+  /* commands */
+  float* commands;         /* [N,4] */
+  float* commands_resampling_step; /* [N] */
+  float* commands_xy_accumulation; /* [N,2] */
+  uint8_t* last_is_limit_vel;      /* [N] */
+  float* env_command_ranges;       /* [N,6] x lo/hi, y lo/hi, yaw lo/hi */
+  /* terrain curriculum */
+  int32_t* terrain_levels; /* [N] */
+  int32_t* terrain_types;  /* [N] */
+  int32_t* terrain_ids;    /* [N] 0..8 */
+  float* env_origins;      /* [N,3] */
+  float* max_move_distance;/* [N] */
+  const float* terrain_origins;   /* [num_levels,num_types,3] */
+  const int16_t* height_samples;  /* [hf_rows,hf_cols] */
+  /* per-env randomised properties */
+  float* motor_strengths;  /* [N,12] */
+  float* motor_zero_offsets;/* [N,12] */
+  float* p_gains_multiplier;/* [N,12] */
+  float* d_gains_multiplier;/* [N,12] */
+  const float* friction_coeffs; /* [N] robot shape friction */
+  const float* restitutions;    /* [N] */
+  const float* body_inertia;    /* [N,13,10] composite inertials of the dynamic bodies */
+  /* logging */
+  float* episode_sums;     /* [N,14] */
+  float* ep_stats;         /* [ep_slots, GO2_EP_STATS] */
+  float* ep_accum;         /* [GO2_EP_STATS + 2] scratch for the cross-env sums (zeroed by the step) */
+} Go2EnvBuffers;
+
+/* ---- environment (CUDA library: libgo2b200.so) ------------------------------------------------ */
+typedef struct Go2Env Go2Env;
+
+/* Replaces gym.create_sim/prepare_sim + acquire_*_tensor (legged_robot.py:292-310,769-787). 0 on success. */
+int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvBuffers* bufs, Go2Env** out);
+void go2_env_destroy(Go2Env* env);
+/* Replaces LeggedRobot.step (legged_robot.py:60-100): the fused kernel. actions: device [N,12]. */
+int go2_env_step(Go2Env* env, const float* actions, const Go2StepParams* sp, void* cuda_stream);
+/* Same, HOST buffers: H2D of actions, kernel, D2H of obs/priv/rew/reset inside the call (bench e2e). */
+int go2_env_step_host(Go2Env* env, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv,
+                      float* h_rew, uint8_t* h_reset, void* cuda_stream);
+/* Replaces reset_idx(arange(N)) at construction (base_task.py:82-86 calls reset_idx then a zero-action step). */
+int go2_env_reset_all(Go2Env* env, const Go2StepParams* sp, void* cuda_stream);
+/* One physics substep only (parity tests of the dynamics in isolation). */
+int go2_env_substep_only(Go2Env* env, int n_substeps, void* cuda_stream);
+const char* go2_last_error(void);
+int go2_kernel_launch_count(void); /* kernels launched by this library since load */
+
+/* ---- RL kernels (rsl_rl restated; see go2_rl.h section below) ---------------------------------- */
+
+/* Y[M,N] = act(X[M,K] W[N,K]^T + b[N]);  act: 0 none, 1 ELU.  Row-major fp32, leading dims given. */
+int go2_linear_forward(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy,
+                       int M, int N, int K, int act, void* stream);
+/* dX[M,K] = (dY[M,N] * act'(Y)) W[N,K];  if Yact != NULL dY is first multiplied IN PLACE by ELU'(Yact). */
+int go2_linear_backward(const float* X, int ldx, const float* W, float* dY, int ldy, const float* Yact,
+                        float* dX, int lddx, float* dW, float* db, int M, int N, int K, int accumulate, void* stream);
+/* RolloutStorage.compute_returns (rollout_storage.py:123-137). All [T,N]. stats: [3] scratch. */
+int go2_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+            float* returns, float* advantages, int T, int N, float gamma, float lam, int normalize,
+            float* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GO2_B200_H */
