@@ -184,11 +184,9 @@ class EnvArrays:
         c.randomize_motor_zero_offset = int(dr.randomize_motor_zero_offset)
         c.randomize_pd_gains = int(dr.randomize_pd_gains)
         c.push_robots, c.add_noise = int(dr.push_robots), int(cfg.noise.add_noise)
-        for k in range(2):
-            c.motor_strength_range[k] = dr.motor_strength_range[k]
-            c.motor_zero_offset_range[k] = dr.motor_zero_offset_range[k]
-            c.kp_mult_range[k] = dr.stiffness_multiplier_range[k]
-            c.kd_mult_range[k] = dr.damping_multiplier_range[k]
+        for dst, src in ((c.motor_strength_range, dr.motor_strength_range), (c.motor_zero_offset_range, dr.motor_zero_offset_range),
+                         (c.kp_mult_range, dr.stiffness_multiplier_range), (c.kd_mult_range, dr.damping_multiplier_range)):
+            dst[0], dst[1] = src[0], src[1] - src[0]   # {lower, span}; span formed in double like torch_rand_float does
         c.push_interval, c.max_push_vel_xy, c.max_push_ang_vel = self.push_interval, dr.max_push_vel_xy, dr.max_push_ang_vel
         b200 = getattr(cfg.sim, "b200", None)
         c.solver_iters = getattr(b200, "solver_iterations", 4)

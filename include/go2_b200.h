@@ -66,6 +66,8 @@ typedef struct Go2EnvConfig {
   /* domain randomisation switches and ranges (go2_config.py:39-75) */
   int32_t randomize_action_delay, randomize_motor_strength, randomize_motor_zero_offset, randomize_pd_gains;
   int32_t push_robots, add_noise;
+  /* uniform ranges are stored as {lower, upper - lower}: the span is formed in double on the host exactly as
+     torch_rand_float(lower, upper) forms it from Python floats, so device draws round like the reference's */
   float motor_strength_range[2], motor_zero_offset_range[2], kp_mult_range[2], kd_mult_range[2];
   int32_t push_interval; float max_push_vel_xy, max_push_ang_vel;
   /* contact / limit solver (physics spec) */

@@ -548,11 +548,11 @@ static void reset_env(const Go2EnvConfig& C, const Go2Model& M, const Go2EnvBuff
   for (int j = 0; j < GO2_NUM_DOF; ++j) {
     U4 r = philox4x32_10(ge, sp.common_step_counter, ST_RESET_DR, (uint32_t)j, C.seed_lo, C.seed_hi);
     size_t o = (size_t)e * GO2_NUM_DOF + j;
-    if (C.randomize_motor_strength) B.motor_strengths[o] = (C.motor_strength_range[1] - C.motor_strength_range[0]) * u01(r.x) + C.motor_strength_range[0];
-    if (C.randomize_motor_zero_offset) B.motor_zero_offsets[o] = (C.motor_zero_offset_range[1] - C.motor_zero_offset_range[0]) * u01(r.y) + C.motor_zero_offset_range[0];
+    if (C.randomize_motor_strength) B.motor_strengths[o] = C.motor_strength_range[1] * u01(r.x) + C.motor_strength_range[0];
+    if (C.randomize_motor_zero_offset) B.motor_zero_offsets[o] = C.motor_zero_offset_range[1] * u01(r.y) + C.motor_zero_offset_range[0];
     if (C.randomize_pd_gains) {
-      B.p_gains_multiplier[o] = (C.kp_mult_range[1] - C.kp_mult_range[0]) * u01(r.z) + C.kp_mult_range[0];
-      B.d_gains_multiplier[o] = (C.kd_mult_range[1] - C.kd_mult_range[0]) * u01(r.w) + C.kd_mult_range[0];
+      B.p_gains_multiplier[o] = C.kp_mult_range[1] * u01(r.z) + C.kp_mult_range[0];
+      B.d_gains_multiplier[o] = C.kd_mult_range[1] * u01(r.w) + C.kd_mult_range[0];
     }
   }
   U4 s3 = philox4x32_10(ge, sp.common_step_counter, ST_RESET_STATE, 3, C.seed_lo, C.seed_hi);
@@ -796,9 +796,11 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     if (C.push_robots && (B.episode_length_buf[e] % C.push_interval == 0)) {  // legged_robot.py:709-724
       U4 p0 = philox4x32_10(ge, sp.common_step_counter, ST_PUSH, 0, C.seed_lo, C.seed_hi);
       U4 p1 = philox4x32_10(ge, sp.common_step_counter, ST_PUSH, 1, C.seed_lo, C.seed_hi);
-      rs[7] = (2 * u01(p0.x) - 1) * C.max_push_vel_xy; rs[8] = (2 * u01(p0.y) - 1) * C.max_push_vel_xy;
-      rs[10] = (2 * u01(p0.z) - 1) * C.max_push_ang_vel; rs[11] = (2 * u01(p0.w) - 1) * C.max_push_ang_vel;
-      rs[12] = (2 * u01(p1.x) - 1) * C.max_push_ang_vel;
+      // torch_rand_float(-m, m): (m - (-m)) * u + (-m); doubling is exact in binary floating point
+      float sv = 2 * C.max_push_vel_xy, sa = 2 * C.max_push_ang_vel;
+      rs[7] = sv * u01(p0.x) - C.max_push_vel_xy; rs[8] = sv * u01(p0.y) - C.max_push_vel_xy;
+      rs[10] = sa * u01(p0.z) - C.max_push_ang_vel; rs[11] = sa * u01(p0.w) - C.max_push_ang_vel;
+      rs[12] = sa * u01(p1.x) - C.max_push_ang_vel;
     }
     // compute_observations, go2_env.py:23-53 (q, qd, actions re-read: a reset may have changed them)
     float* ob = B.obs_buf + (size_t)e * GO2_NUM_OBS; float* pv = B.privileged_obs_buf + (size_t)e * GO2_NUM_PRIV;
@@ -858,7 +860,7 @@ int go2_oracle_substeps(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBu
     float* rs = B->root_states + (size_t)e * 13;
     real pos[3] = {rs[0], rs[1], rs[2]}, quat[4] = {rs[3], rs[4], rs[5], rs[6]}, lw[3] = {rs[7], rs[8], rs[9]}, aw[3] = {rs[10], rs[11], rs[12]};
     real q[GO2_NUM_DOF], qd[GO2_NUM_DOF], tau[GO2_NUM_DOF];
-    for (int j = 0; j < GO2_NUM_DOF; ++j) { q[j] = B->dof_pos[(size_t)e * GO2_NUM_DOF + j]; qd[j] = B->dof_vel[(size_t)e * GO2_NUM_DOF + j]; tau[j] = tau_in[(size_t)e * GO2_NUM_DOF + j]; }
+    for (int j = 0; j < GO2_NUM_DOF; ++j) { q[j] = B->dof_pos[(size_t)e * GO2_NUM_DOF + j]; qd[j] = B->dof_vel[(size_t)e * GO2_NUM_DOF + j]; tau[j] = std::min(std::max(tau_in[(size_t)e * GO2_NUM_DOF + j], -M->effort[j]), M->effort[j]); }
     SubstepOut so;
     for (int s = 0; s < n; ++s)
       physics_substep(*C, *M, T, B->body_inertia + (size_t)e * GO2_NUM_DYN * GO2_INERTIA_STRIDE, B->friction_coeffs[e], B->restitutions[e], pos, quat, lw, aw, q, qd, tau, so);
@@ -866,6 +868,31 @@ int go2_oracle_substeps(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBu
     for (int i = 0; i < 4; ++i) rs[3 + i] = (float)quat[i];
     for (int j = 0; j < GO2_NUM_DOF; ++j) { B->dof_pos[(size_t)e * GO2_NUM_DOF + j] = (float)q[j]; B->dof_vel[(size_t)e * GO2_NUM_DOF + j] = (float)qd[j]; }
     for (int b = 0; b < GO2_NUM_REPORT; ++b) for (int i = 0; i < 3; ++i) B->contact_forces[((size_t)e * GO2_NUM_REPORT + b) * 3 + i] = (float)so.contact_force[b][i];
+  }
+  return 0;
+}
+
+// feet position / velocity of the current state (what refresh_rigid_body_state_tensor exposes for the 4 foot bodies)
+int go2_oracle_feet(const Go2EnvConfig* C, const Go2Model* Mp, const Go2EnvBuffers* B) {
+  const Go2Model& M = *Mp;
+  for (int e = 0; e < C->num_envs; ++e) {
+    const float* rs = B->root_states + (size_t)e * 13;
+    real pos[3] = {rs[0], rs[1], rs[2]}, quat[4] = {rs[3], rs[4], rs[5], rs[6]}, q[GO2_NUM_DOF], qd[GO2_NUM_DOF];
+    for (int j = 0; j < GO2_NUM_DOF; ++j) { q[j] = B->dof_pos[(size_t)e * GO2_NUM_DOF + j]; qd[j] = B->dof_vel[(size_t)e * GO2_NUM_DOF + j]; }
+    Kin K;
+    kinematics(M, pos, quat, q, K);
+    V3 wb = mulT(K.Rw[0], V3{rs[10], rs[11], rs[12]}), vb = mulT(K.Rw[0], V3{rs[7], rs[8], rs[9]});
+    V6 v[GO2_NUM_DYN];
+    v[0] = mk6(wb, vb);
+    for (int b = 1; b < GO2_NUM_DYN; ++b) { v[b] = mul(K.X[b], v[parent_of(M, b)]); v[b].v[M.joint_axis[b - 1]] += qd[b - 1]; }
+    for (int l = 0; l < 4; ++l) {
+      int b = 3 + 3 * l;
+      V3 r{(real)M.foot_offset[l][0], (real)M.foot_offset[l][1], (real)M.foot_offset[l][2]};
+      V3 pw = K.pw[b] + mul(K.Rw[b], r);
+      V3 vw = mul(K.Rw[b], lin(v[b]) + cross(ang(v[b]), r));
+      float* fp = B->feet_pos + ((size_t)e * 4 + l) * 3; float* fv = B->feet_vel + ((size_t)e * 4 + l) * 3;
+      fp[0] = (float)pw.x; fp[1] = (float)pw.y; fp[2] = (float)pw.z; fv[0] = (float)vw.x; fv[1] = (float)vw.y; fv[2] = (float)vw.z;
+    }
   }
   return 0;
 }

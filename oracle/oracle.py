@@ -21,6 +21,7 @@ def load(double=False):
     lib.go2_oracle_step.argtypes = [P(_abi.Go2EnvConfig), P(_abi.Go2Model), P(_abi.Go2EnvBuffers), C.c_void_p, P(_abi.Go2StepParams)]
     lib.go2_oracle_reset_all.argtypes = [P(_abi.Go2EnvConfig), P(_abi.Go2Model), P(_abi.Go2EnvBuffers), P(_abi.Go2StepParams)]
     lib.go2_oracle_substeps.argtypes = [P(_abi.Go2EnvConfig), P(_abi.Go2Model), P(_abi.Go2EnvBuffers), C.c_void_p, C.c_int]
+    lib.go2_oracle_feet.argtypes = [P(_abi.Go2EnvConfig), P(_abi.Go2Model), P(_abi.Go2EnvBuffers)]
     lib.go2_oracle_philox.argtypes = [C.c_uint32] * 6 + [P(C.c_uint32)]
     return lib
 
@@ -44,6 +45,9 @@ class OracleEnv:
         a = actions.contiguous().float()
         self.lib.go2_oracle_step(C.byref(self.A.config), C.byref(self.A.model), C.byref(self.A.buffers), a.data_ptr(), C.byref(sp))
         return sp
+
+    def feet(self):
+        self.lib.go2_oracle_feet(C.byref(self.A.config), C.byref(self.A.model), C.byref(self.A.buffers))
 
     def substeps(self, tau, n):
         t = tau.contiguous().float()

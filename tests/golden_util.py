@@ -1,0 +1,49 @@
+"""Shared helpers: rebuild the env of a golden fixture and compare per-step outputs."""
+import os
+
+import numpy as np
+import torch
+
+from go2_rl_gym_b200.envs.env_arrays import EnvArrays
+from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# tolerances: integer / flag state is bit-exact; float state within fp32 rounding of a different summation order
+EXACT = ["reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel"]
+TOL = {"default": (2e-5, 2e-5), "rew_buf": (1e-5, 1e-5), "episode_sums": (1e-4, 1e-5), "privileged_obs_buf": (1e-4, 1e-4),
+       "contact_forces": (1e-3, 1e-3), "torques": (1e-4, 1e-4), "dof_vel": (1e-4, 1e-4), "root_states": (1e-4, 1e-4),
+       "obs_buf": (1e-4, 1e-4), "feet_vel": (1e-4, 1e-4), "last_dof_vel": (1e-4, 1e-4)}
+
+
+def load_case(name, device="cpu", **kw):
+    z = np.load(os.path.join(GOLDEN, f"env_{name}.npz"))
+    N, seed, plane = int(z["meta_N"]), int(z["meta_seed"]), bool(z["meta_plane"])
+    cfg = GO2Cfg()
+    cfg.env.num_envs = N
+    cfg.terrain.mesh_type = "plane" if plane else "heightfield"
+    cfg.seed = seed
+    A = EnvArrays(cfg, device, seed=seed, **kw)
+    for k in z.files:
+        if k.startswith("s0_"):
+            A.tensors[k[3:]].copy_(torch.from_numpy(z[k]).to(A.tensors[k[3:]].dtype))
+    return z, A
+
+
+def compare_step(z, i, tensors, keys=None, skip=()):
+    bad = []
+    names = [k[len(f"out{i}_"):] for k in z.files if k.startswith(f"out{i}_")]
+    for name in names:
+        if name.startswith("ep_") or name in skip or (keys is not None and name not in keys) or name not in tensors:
+            continue
+        ref = z[f"out{i}_{name}"]
+        got = tensors[name].detach().cpu().numpy().reshape(ref.shape)
+        if name in EXACT:
+            if not np.array_equal(ref.astype(np.int64), got.astype(np.int64)):
+                bad.append((name, "exact", np.argwhere(ref.astype(np.int64) != got.astype(np.int64))[:4].tolist()))
+        else:
+            rtol, atol = TOL.get(name, TOL["default"])
+            if not np.allclose(got, ref, rtol=rtol, atol=atol):
+                err = np.abs(got - ref)
+                bad.append((name, float(err.max()), np.unravel_index(err.argmax(), err.shape)))
+    return bad
