@@ -1,0 +1,195 @@
+"""LeggedRobot — the VecEnv the runners drive, backed by ONE fused sm_100a kernel per step.
+
+Drop-in for `legged_gym.envs.base.legged_robot.LeggedRobot` / `base_task.BaseTask`
+(reference: legged_gym/envs/base/legged_robot.py:25-142, base_task.py:11-86; contract: rsl_rl/env/vec_env.py:36-59):
+same constructor signature, same public buffers (`obs_buf, privileged_obs_buf, rew_buf, reset_buf, episode_length_buf,
+time_out_buf, extras, commands, root_states, dof_pos, dof_vel, torques, contact_forces, base_lin_vel, ...`), same
+`step / reset / get_observations / get_privileged_observations / update_reward_curriculum` methods and the attributes
+train.py and the runners reach into.  Every buffer is a zero-copy torch view of the device rows
+the kernel reads and writes (include/go2_b200.h: Go2EnvBuffers).
+
+There is no CPU path: construction raises if libgo2b200.so is missing or no CUDA device is present.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ... import _abi
+from ..env_arrays import EnvArrays, EP_SLOTS, class_to_dict  # noqa: F401
+from ...utils.terrain import TERRAIN_NAMES
+
+
+class LeggedRobot:
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True,
+                 env_offset=0, num_envs_global=None):
+        self.cfg = cfg
+        self.sim_params = sim_params
+        self.physics_engine = physics_engine
+        self.sim_device = sim_device
+        self.headless = headless
+        self.height_samples = None
+        self.debug_viz = False
+        self.init_done = False
+        dev = torch.device(sim_device if str(sim_device).startswith("cuda") else "cuda:0")
+        if not torch.cuda.is_available():
+            raise RuntimeError("go2_rl_gym_b200 needs a CUDA device (B200); there is no CPU fallback for the env step")
+        self._lib = _abi.load_library()
+        self.device = str(dev)
+        torch.cuda.set_device(dev)
+        self.num_envs = cfg.env.num_envs
+        self.num_obs = cfg.env.num_observations
+        self.num_privileged_obs = cfg.env.num_privileged_obs
+        self.num_actions = cfg.env.num_actions
+        if (self.num_obs, self.num_privileged_obs, self.num_actions) != (_abi.NUM_OBS, _abi.NUM_PRIV, _abi.NUM_DOF):
+            raise NotImplementedError("the fused kernel is specialised for the Go2 45 / 263 / 12 layout (go2_env.py:23-53)")
+        A = EnvArrays(cfg, dev, num_envs=self.num_envs, env_offset=env_offset, num_envs_global=num_envs_global,
+                      seed=getattr(cfg, "seed", 1))
+        self._A = A
+        T = A.tensors
+        # ---- public buffers (same names as the reference's attributes)
+        for name in ("root_states", "dof_pos", "dof_vel", "torques", "contact_forces", "actions", "last_actions",
+                     "last_last_actions", "last_dof_vel", "obs_buf", "privileged_obs_buf", "rew_buf", "base_lin_vel",
+                     "base_ang_vel", "projected_gravity", "measured_heights", "commands", "commands_resampling_step",
+                     "commands_xy_accumulation", "terrain_levels", "terrain_types", "terrain_ids", "env_origins",
+                     "max_move_distance", "motor_strengths", "motor_zero_offsets", "p_gains_multiplier",
+                     "d_gains_multiplier", "feet_pos", "feet_vel"):
+            setattr(self, name, T[name])
+        self.reset_buf = T["reset_buf"].view(torch.bool)
+        self.time_out_buf = T["time_out_buf"].view(torch.bool)
+        self.last_is_limit_vel = T["last_is_limit_vel"].view(torch.bool)
+        self._episode_length_buf = T["episode_length_buf"]
+        self.base_quat = self.root_states[:, 3:7]
+        self.base_pos = self.root_states[:, 0:3]
+        self.friction_coeffs = T["friction_coeffs"]
+        self.episode_sums = {n: T["episode_sums"][:, k] for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales}
+        self.env_command_ranges = {"lin_vel_x": T["env_command_ranges"][:, 0:2], "lin_vel_y": T["env_command_ranges"][:, 2:4],
+                                   "ang_vel_yaw": T["env_command_ranges"][:, 4:6]}
+        self.dt = A.dt
+        self.max_episode_length_s = A.max_episode_length_s
+        self.max_episode_length = A.max_episode_length
+        self.obs_scales = cfg.normalization.obs_scales
+        self.reward_scales = A.reward_scales
+        self.command_ranges = A.command_ranges
+        self.custom_origins = A.custom_origins
+        if not A.plane:
+            self.terrain = A.terrain
+            self.height_samples = T["height_samples"]
+            self.terrain_origins = T["terrain_origins"]
+            self.max_terrain_level = cfg.terrain.num_rows
+        self.num_dof = self.num_dofs = _abi.NUM_DOF
+        self.num_bodies = _abi.NUM_REPORT
+        self.dof_names = A.model_json["dof_names"]
+        body_names = A.model_json["report_bodies"]
+        idx = lambda key: torch.tensor([i for i, n in enumerate(body_names) if key in n], dtype=torch.long, device=dev)
+        self.feet_indices = idx(cfg.asset.foot_name)
+        self.penalised_contact_indices = torch.cat([idx(k) for k in cfg.asset.penalize_contacts_on])
+        self.termination_contact_indices = torch.cat([idx(k) for k in cfg.asset.terminate_after_contacts_on])
+        self.default_dof_pos = torch.from_numpy(A.default_dof_pos_np).to(dev).unsqueeze(0)
+        self.torque_limits = torch.tensor(list(A.model.effort), device=dev)
+        self.noise_scale_vec = torch.from_numpy(A.noise_scale_vec_np).to(dev)
+        self.add_noise = cfg.noise.add_noise
+        self.common_step_counter = 0
+        self.num_steps_per_env = 24
+        self.extras = {}
+        self.reward_curriculum_configs = list(cfg.rewards.curriculum_rewards or [])
+        self.reward_curriculum_scales = {c["reward_name"]: c["start_value"] for c in self.reward_curriculum_configs}
+        self.zero_command_proba = 0.0
+        self._stream = 0  # legacy default stream: ordered with torch's current stream
+        self._ep_names = ["rew_" + n for n in _abi.REWARD_NAMES if n in A.reward_scales]
+        self._ep_cols = [k for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales]
+        # ---- library handle
+        h = ctypes.c_void_p()
+        _abi.check(self._lib.go2_env_create(ctypes.byref(A.config), ctypes.byref(A.model), ctypes.byref(A.buffers), ctypes.byref(h)), self._lib)
+        self._h = h
+        self.init_done = True
+
+    # episode_length_buf is re-ASSIGNED by the runner (on_policy_runner.py:118): keep the device row the kernel owns
+    @property
+    def episode_length_buf(self):
+        return self._episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        self._episode_length_buf.copy_(value.to(self._episode_length_buf.dtype))
+
+    def __del__(self):
+        h, lib = getattr(self, "_h", None), getattr(self, "_lib", None)
+        if h and lib:
+            lib.go2_env_destroy(h)
+            self._h = None
+
+    # ---- VecEnv contract -----------------------------------------------------------------------------------
+    def get_observations(self):
+        return self.obs_buf
+
+    def get_privileged_observations(self):
+        return self.privileged_obs_buf
+
+    def reset_idx(self, env_ids):
+        raise NotImplementedError("resets are fused into the step kernel (legged_robot.py:132-133); use reset()")
+
+    def reset(self):
+        """Reset all robots then take one zero-action step (base_task.py:82-86)."""
+        sp = self._A.step_params(self.common_step_counter)
+        _abi.check(self._lib.go2_env_reset_all(self._h, ctypes.byref(sp), self._stream), self._lib)
+        obs, privileged_obs, _, _, _ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return obs, privileged_obs
+
+    def update_reward_curriculum(self, force_update: bool = False):  # legged_robot.py:144-152
+        if self.reward_curriculum_configs and (self.common_step_counter % self.num_steps_per_env == 0 or force_update):
+            it = self.common_step_counter // self.num_steps_per_env
+            for c in self.reward_curriculum_configs:
+                self.reward_curriculum_scales[c["reward_name"]] = EnvArrays._scale(c, it)
+
+    def get_current_scale(self, config):
+        return EnvArrays._scale(config, self.common_step_counter // self.num_steps_per_env)
+
+    def step(self, actions):
+        """legged_robot.py:60-100 as one kernel: clip, action delay, 4x(PD torque + physics substep), post-physics."""
+        a = actions.to(device=self.device, dtype=torch.float32)
+        if not a.is_contiguous():
+            a = a.contiguous()
+        self.common_step_counter += 1
+        self.update_reward_curriculum()
+        slot = self.common_step_counter % EP_SLOTS
+        sp = self._A.step_params(self.common_step_counter, ep_slot=slot, reward_curriculum=self.reward_curriculum_scales)
+        self.zero_command_proba = sp.zero_command_proba
+        _abi.check(self._lib.go2_env_step(self._h, a.data_ptr(), ctypes.byref(sp), self._stream), self._lib)
+        self._last_actions_in = a  # keep the input alive until the kernel has consumed it
+        self._fill_extras(slot)
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def step_host(self, actions_np, obs_out, priv_out, rew_out, reset_out):
+        """Same step through HOST buffers (numpy, ideally pinned): H2D, kernel, D2H inside the C call (bench e2e)."""
+        self.common_step_counter += 1
+        self.update_reward_curriculum()
+        sp = self._A.step_params(self.common_step_counter, ep_slot=self.common_step_counter % EP_SLOTS,
+                                 reward_curriculum=self.reward_curriculum_scales)
+        _abi.check(self._lib.go2_env_step_host(self._h, actions_np.ctypes.data, ctypes.byref(sp), obs_out.ctypes.data,
+                                               priv_out.ctypes.data, rew_out.ctypes.data, reset_out.ctypes.data, self._stream), self._lib)
+
+    def _fill_extras(self, slot):
+        """extras["episode"] / extras["time_outs"] (legged_robot.py:229-245) as 0-d views of the row the kernel filled.
+        The row is only rewritten by a step in which some env reset; otherwise the previous dict is re-served, exactly
+        like the reference's stale `self.extras` (on_policy_runner.py:145-146)."""
+        row = self._A.tensors["ep_stats"][slot]
+        ep = {}
+        for name, col in zip(self._ep_names, self._ep_cols):
+            ep[name] = row[col]
+        ep["terrain_level_all"] = row[_abi.NUM_REW]
+        if not self._A.plane:
+            for name, cols in self._A.terrain.name2cols.items():
+                ep["terrain_level_" + name] = row[_abi.NUM_REW + 1 + TERRAIN_NAMES.index(name)]
+        if self.cfg.commands.curriculum:
+            ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+        self._ep_latest = (ep, row[_abi.NUM_REW + 11])
+        # the validity flag of the row tells the runner whether this step produced a fresh dict
+        self.extras["episode"] = ep
+        self.extras["episode_valid"] = row[_abi.NUM_REW + 11]
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf
+
+    def substeps(self, tau, n):
+        """n bare physics substeps under given joint torques (tests)."""
+        _abi.check(self._lib.go2_env_substeps(self._h, tau.contiguous().data_ptr(), int(n), self._stream), self._lib)

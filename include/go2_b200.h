@@ -175,23 +175,10 @@ int go2_env_step_host(Go2Env* env, const float* h_actions, const Go2StepParams* 
                       float* h_rew, uint8_t* h_reset, void* cuda_stream);
 /* Replaces reset_idx(arange(N)) at construction (base_task.py:82-86 calls reset_idx then a zero-action step). */
 int go2_env_reset_all(Go2Env* env, const Go2StepParams* sp, void* cuda_stream);
-/* One physics substep only (parity tests of the dynamics in isolation). */
-int go2_env_substep_only(Go2Env* env, int n_substeps, void* cuda_stream);
+/* n bare physics substeps under given joint torques tau [N,12] (parity tests of the dynamics in isolation). */
+int go2_env_substeps(Go2Env* env, const float* tau, int n_substeps, void* cuda_stream);
 const char* go2_last_error(void);
-int go2_kernel_launch_count(void); /* kernels launched by this library since load */
-
-/* ---- RL kernels (rsl_rl restated; see go2_rl.h section below) ---------------------------------- */
-
-/* Y[M,N] = act(X[M,K] W[N,K]^T + b[N]);  act: 0 none, 1 ELU.  Row-major fp32, leading dims given. */
-int go2_linear_forward(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy,
-                       int M, int N, int K, int act, void* stream);
-/* dX[M,K] = (dY[M,N] * act'(Y)) W[N,K];  if Yact != NULL dY is first multiplied IN PLACE by ELU'(Yact). */
-int go2_linear_backward(const float* X, int ldx, const float* W, float* dY, int ldy, const float* Yact,
-                        float* dX, int lddx, float* dW, float* db, int M, int N, int K, int accumulate, void* stream);
-/* RolloutStorage.compute_returns (rollout_storage.py:123-137). All [T,N]. stats: [3] scratch. */
-int go2_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
-            float* returns, float* advantages, int T, int N, float gamma, float lam, int normalize,
-            float* stats, void* stream);
+long long go2_kernel_launch_count(void); /* kernels launched by this library since load */
 
 #ifdef __cplusplus
 }
