@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import load_case, compare_step
+from golden_util import load_case, compare_step, TOL_TIGHT
 from oracle.oracle import OracleEnv
 
 
@@ -17,7 +17,7 @@ def test_oracle_matches_reference_env(name):
     n_reset = 0
     for i in range(int(z["meta_K"])):
         sp = O.step(actions[i])
-        bad = compare_step(z, i, A.tensors)
+        bad = compare_step(z, i, A.tensors, tol=TOL_TIGHT)
         assert not bad, f"step {i}: {bad}"
         n_reset += int(z[f"out{i}_reset_buf"].sum())
         ep = z[f"out{i}_ep_rew"]
