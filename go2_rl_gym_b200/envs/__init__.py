@@ -1,0 +1,9 @@
+"""Task registration (legged_gym/envs/__init__.py:9-15)."""
+from .go2.go2_env import Go2Robot
+from .go2.go2_config import GO2Cfg, GO2CfgPPO, GO2CfgCTS, GO2CfgMoECTS, GO2CfgMoENGCTS, GO2CfgMCPCTS, GO2CfgACMoECTS, GO2CfgDualMoECTS
+from .base.legged_robot import LeggedRobot
+from ..utils.task_registry import task_registry
+
+task_registry.register("go2", Go2Robot, GO2Cfg(), GO2CfgPPO())
+task_registry.register("go2_cts", Go2Robot, GO2Cfg(), GO2CfgCTS())
+task_registry.register("go2_moe_cts", Go2Robot, GO2Cfg(), GO2CfgMoECTS())

@@ -18,22 +18,8 @@ import torch
 
 from .. import _abi
 from ..utils import robot_model
+from ..utils.cfg_dict import class_to_dict  # noqa: F401
 from ..utils.terrain import Terrain, TERRAIN_NAMES
-
-
-def class_to_dict(obj):
-    if not hasattr(obj, "__dict__"):
-        return obj
-    result = {}
-    for key in dir(obj):
-        if key.startswith("_"):
-            continue
-        val = getattr(obj, key)
-        if isinstance(val, list):
-            result[key] = [class_to_dict(v) for v in val]
-        else:
-            result[key] = class_to_dict(val)
-    return result
 
 
 _U8 = ("reset_buf", "time_out_buf", "last_is_limit_vel")

@@ -1,0 +1,180 @@
+"""PPO (drop-in for rsl_rl/algorithms/ppo.py:37-187) on hand-written kernels.
+
+Same constructor and method names.  Differences a caller can observe, all deliberate and documented in DESIGN.md:
+  * act() samples with the library's Philox normal (keyed by seed / env / step) instead of torch's global generator;
+  * update() runs without any host synchronisation: the KL-adaptive learning rate (ppo.py:139-151) lives in a device scalar
+    read by the fused clip+Adam kernel; `learning_rate` on the host is refreshed once per update() for logging;
+  * with torch.distributed initialised, each optimiser step all-reduces the flat gradient (one NCCL call, scalar tail included)."""
+import torch
+import torch.distributed as dist
+
+from .. import _ops
+from ..modules import ActorCritic
+from ..storage import RolloutStorage
+
+
+class PPO:
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
+                 schedule="fixed", desired_kl=0.01, device='cpu', seed=1, env_offset=0):
+        self.device = device
+        self.desired_kl = desired_kl
+        self.schedule = schedule
+        self.learning_rate = learning_rate
+        self.actor_critic = actor_critic
+        self.storage = None
+        self.transition = RolloutStorage.Transition()
+        self.clip_param = clip_param
+        self.num_learning_epochs = num_learning_epochs
+        self.num_mini_batches = num_mini_batches
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.gamma = gamma
+        self.lam = lam
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.seed = int(seed)
+        self.env_offset = int(env_offset)
+        self._act_step = 0
+        self._opt_step = 0
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.optimizer = None  # Adam state lives in flat vectors; see optimizer_state_dict()
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        dev = self.device
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, dev)
+        T = num_transitions_per_env
+        self.mini_batch_size = (num_envs * T) // self.num_mini_batches
+        ac = self.actor_critic
+        ac.flatten_(dev, max(num_envs, self.mini_batch_size))
+        n = ac.flat_params.numel()
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self._lr = torch.full((1,), float(self.learning_rate), device=dev)
+        self._scal = torch.zeros(20, device=dev)
+        self._log = torch.zeros(4, device=dev)
+        self._scratch = torch.zeros(1025, device=dev)
+        self._dmu = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
+        self._dval = torch.empty(self.mini_batch_size, 1, device=dev)
+        self._mu_b = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
+        self._val_b = torch.empty(self.mini_batch_size, 1, device=dev)
+        self._last_values = torch.empty(num_envs, 1, device=dev)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    # ---- rollout ---------------------------------------------------------------------------------------------
+    def act(self, obs, critic_obs):
+        st, t, ac = self.storage, self.storage.step, self.actor_critic
+        if t >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        N, A = st.num_envs, st.actions.shape[-1]
+        st.observations[t].copy_(obs)
+        (st.privileged_observations if st.privileged_observations is not None else st.observations)[t].copy_(critic_obs)
+        mu = ac._actor_forward(st.observations[t])
+        ac.evaluate(critic_obs, out=st.values[t])
+        self._act_step += 1
+        _ops.call("go2_sample_actions", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
+                  _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._act_step, self.env_offset)
+        self.transition.actions = st.actions[t]
+        self.transition.values = st.values[t]
+        return st.actions[t]
+
+    def process_env_step(self, rewards, dones, infos):
+        st, t = self.storage, self.storage.step
+        tout = infos.get('time_outs') if isinstance(infos, dict) else None
+        d8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8)
+        t8 = None if tout is None else (tout.view(torch.uint8) if tout.dtype == torch.bool else tout.to(torch.uint8))
+        _ops.call("go2_process_env_step", _ops.ptr(rewards), _ops.ptr(d8), _ops.ptr(t8), _ops.ptr(st.values[t]), _ops.ptr(st.rewards[t]),
+                  _ops.ptr(st.dones[t]), st.num_envs, self.gamma)
+        st.step += 1
+        self.transition.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        self.actor_critic.evaluate(last_critic_obs, out=self._last_values)
+        self.storage.compute_returns(self._last_values, self.gamma, self.lam, reduce_stats=self._reduce_adv_stats if self.world_size > 1 else None)
+
+    def _reduce_adv_stats(self, stats):
+        dist.all_reduce(stats)
+        return self.storage.num_envs * self.storage.num_transitions_per_env * self.world_size
+
+    # ---- update ----------------------------------------------------------------------------------------------
+    def update(self, indices=None):
+        st, ac = self.storage, self.actor_critic
+        mb, A = self.mini_batch_size, st.actions.shape[-1]
+        if indices is None:
+            indices = torch.randperm(self.num_mini_batches * mb, device=self.device)
+        sh = st.shuffled(indices, {})
+        self._log.zero_()
+        inv_count = 1.0 / (mb * self.world_size)
+        adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
+        std_grad = ac._gviews["std"]
+        for epoch in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                s = slice(i * mb, (i + 1) * mb)
+                obs_b, cobs_b = sh["obs"][s], sh["critic_obs"][s]
+                ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A)
+                ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1)
+                _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
+                          _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
+                          _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dval), _ops.ptr(self._scal),
+                          mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss), inv_count)
+                ac.actor_engine.backward(self._dmu, A)
+                ac.critic_engine.backward(self._dval, 1)
+                std_grad.copy_(self._scal[4:4 + A])
+                if self.world_size > 1:
+                    # one collective per optimiser step: flat gradient + the scalar tail (KL / loss sums) ride together
+                    self._allreduce_grads()
+                _ops.call("go2_kl_adaptive_lr", _ops.ptr(self._scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
+                          _ops.ptr(self._lr), _ops.ptr(self._log))
+                self._opt_step += 1
+                _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
+                          ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), self._opt_step, 1.0, _ops.ptr(self._scratch))
+        num_updates = self.num_learning_epochs * self.num_mini_batches
+        log = self._log.tolist()          # the single host sync of update()
+        self.learning_rate = log[3]
+        st.clear()
+        return log[0] / num_updates, log[1] / num_updates
+
+    def _allreduce_grads(self):
+        if not hasattr(self, "_comm"):
+            n = self.actor_critic.flat_grads.numel()
+            self._comm = torch.empty(n + 4, device=self.device)
+        n = self.actor_critic.flat_grads.numel()
+        self._comm[:n].copy_(self.actor_critic.flat_grads)
+        self._comm[n:].copy_(self._scal[:4])
+        dist.all_reduce(self._comm)
+        self.actor_critic.flat_grads.copy_(self._comm[:n])
+        self._scal[:4].copy_(self._comm[n:])
+
+    # ---- checkpoint interop (torch.optim.Adam layout, ppo.py:67) ---------------------------------------------
+    def optimizer_state_dict(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.actor_critic.parameters()):
+            k = p.numel()
+            state[i] = {"step": torch.tensor(float(self._opt_step)), "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
+            off += k
+        group = {"lr": self.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(state)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.actor_critic.parameters()):
+            k = p.numel()
+            s = sd["state"].get(i)
+            if s is not None:
+                self.exp_avg[off:off + k].copy_(s["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(s["exp_avg_sq"].reshape(-1))
+                self._opt_step = int(float(s["step"]))
+            off += k
+        if sd.get("param_groups"):
+            self.learning_rate = float(sd["param_groups"][0]["lr"])
+            self._lr.fill_(self.learning_rate)

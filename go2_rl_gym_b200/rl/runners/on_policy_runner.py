@@ -1,0 +1,174 @@
+"""OnPolicyRunner (drop-in for rsl_rl/runners/on_policy_runner.py:60-320).
+
+Same constructor `(env, train_cfg, log_dir, device)`, `learn`, `log`, `save`, `load`, `get_inference_policy` and the same
+TensorBoard scalars / console table.  The rollout loop itself has no host synchronisation: per-step episode statistics are
+accumulated on the device and fetched once per iteration (the reference calls `.cpu()` inside the step loop, :149-150)."""
+import os
+import statistics
+import time
+from collections import deque
+from pathlib import Path
+
+import torch
+import yaml
+
+from ..algorithms import PPO
+from ..modules import ActorCritic
+from ...envs.env_arrays import class_to_dict
+
+try:
+    from torch.utils.tensorboard import SummaryWriter
+except Exception:  # tensorboard is optional on the bench box
+    SummaryWriter = None
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg, log_dir=None, device='cpu'):
+        self.cfg = train_cfg["runner"]
+        self.alg_cfg = train_cfg["algorithm"]
+        self.policy_cfg = train_cfg["policy"]
+        self.device = device
+        self.env = env
+        num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
+        actor_critic_class = {"ActorCritic": ActorCritic}[self.cfg["policy_class_name"]]
+        actor_critic = actor_critic_class(self.env.num_obs, num_critic_obs, self.env.num_actions, **self.policy_cfg)
+        alg_class = {"PPO": PPO}[self.cfg["algorithm_class_name"]]
+        seed = train_cfg.get("seed", 1)
+        self.alg = alg_class(actor_critic, device=self.device, seed=seed, env_offset=getattr(env, "_A", None).env_offset if hasattr(env, "_A") else 0,
+                             **self.alg_cfg)
+        self.num_steps_per_env = self.cfg["num_steps_per_env"]
+        self.save_interval = self.cfg["save_interval"]
+        self.alg.init_storage(self.env.num_envs, self.num_steps_per_env, [self.env.num_obs], [self.env.num_privileged_obs], [self.env.num_actions])
+        self.log_dir = log_dir
+        self.writer = None
+        self.tot_timesteps = 0
+        self.tot_time = 0
+        self.current_learning_iteration = 0
+        _, _ = self.env.reset()
+        if self.log_dir is not None and self.env.cfg.env.test is False:
+            Path(self.log_dir).mkdir(parents=True, exist_ok=True)
+            all_cfg = {"train_cfg": train_cfg, "env_cfg": class_to_dict(self.env.cfg)}
+            yaml.safe_dump(all_cfg, open(os.path.join(self.log_dir, 'config.yaml'), 'w'))
+        self.robogauge_client = None  # external evaluation service: out of scope
+        N = self.env.num_envs
+        self._cur_reward_sum = torch.zeros(N, device=self.device)
+        self._cur_episode_length = torch.zeros(N, device=self.device)
+        # per-iteration device-side episode log: [T, N] finished-episode returns / lengths (NaN where no episode ended)
+        self._done_rew = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
+        self._done_len = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
+
+    def learn(self, num_learning_iterations, init_at_random_ep_len=False):
+        if self.log_dir is not None and self.writer is None and SummaryWriter is not None:
+            self.writer = SummaryWriter(log_dir=self.log_dir, flush_secs=10)
+        if init_at_random_ep_len:
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+        obs = self.env.get_observations()
+        privileged_obs = self.env.get_privileged_observations()
+        critic_obs = privileged_obs if privileged_obs is not None else obs
+        self.alg.actor_critic.train()
+        ep_infos = []
+        rewbuffer, lenbuffer = deque(maxlen=100), deque(maxlen=100)
+        tot_iter = self.current_learning_iteration + num_learning_iterations
+        nan = float("nan")
+        it = self.current_learning_iteration
+        for it in range(self.current_learning_iteration, tot_iter):
+            start = time.time()
+            with torch.inference_mode():
+                for i in range(self.num_steps_per_env):
+                    actions = self.alg.act(obs, critic_obs)
+                    obs, privileged_obs, rewards, dones, infos = self.env.step(actions)
+                    critic_obs = privileged_obs if privileged_obs is not None else obs
+                    self.alg.process_env_step(rewards, dones, infos)
+                    if self.log_dir is not None:
+                        if 'episode' in infos:
+                            ep_infos.append(infos['episode'])
+                        self._cur_reward_sum += rewards
+                        self._cur_episode_length += 1
+                        self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
+                        self._done_len[i] = torch.where(dones, self._cur_episode_length, nan)
+                        self._cur_reward_sum *= ~dones
+                        self._cur_episode_length *= ~dones
+                if self.log_dir is not None:  # one fetch per iteration, time-major order like the reference's per-step extend
+                    dr, dl = self._done_rew.flatten(), self._done_len.flatten()
+                    keep = ~torch.isnan(dr)
+                    rewbuffer.extend(dr[keep].cpu().numpy().tolist())
+                    lenbuffer.extend(dl[keep].cpu().numpy().tolist())
+                torch.cuda.synchronize()
+                stop = time.time()
+                collection_time = stop - start
+                start = stop
+                self.alg.compute_returns(critic_obs)
+            mean_value_loss, mean_surrogate_loss = self.alg.update()
+            stop = time.time()
+            learn_time = stop - start
+            if self.log_dir is not None:
+                self.log(locals())
+                if it % self.save_interval == 0:
+                    self.save(os.path.join(self.log_dir, 'model_{}.pt'.format(it)), it, False)
+            ep_infos.clear()
+        self.current_learning_iteration += num_learning_iterations
+        if self.log_dir is not None:
+            self.save(os.path.join(self.log_dir, 'model_{}.pt'.format(self.current_learning_iteration)), it, True)
+
+    def log(self, locs, width=80, pad=35):
+        self.tot_timesteps += self.num_steps_per_env * self.env.num_envs
+        self.tot_time += locs['collection_time'] + locs['learn_time']
+        iteration_time = locs['collection_time'] + locs['learn_time']
+        ep_string = ''
+        if locs['ep_infos']:
+            for key in locs['ep_infos'][0]:
+                vals = []
+                for ep_info in locs['ep_infos']:
+                    v = ep_info[key]
+                    v = v if isinstance(v, torch.Tensor) else torch.tensor([float(v)], device=self.device)
+                    vals.append(v.reshape(-1).to(self.device))
+                value = torch.mean(torch.cat(vals))
+                if self.writer:
+                    self.writer.add_scalar('Episode/' + key, value, locs['it'])
+                ep_string += f"""{f'Mean episode {key}:':>{pad}} {value:.4f}\n"""
+        mean_std = self.alg.actor_critic.std.mean()
+        fps = int(self.num_steps_per_env * self.env.num_envs / (locs['collection_time'] + locs['learn_time']))
+        if self.writer:
+            w = self.writer
+            w.add_scalar('Loss/value_function', locs['mean_value_loss'], locs['it'])
+            w.add_scalar('Loss/surrogate', locs['mean_surrogate_loss'], locs['it'])
+            w.add_scalar('Loss/learning_rate', self.alg.learning_rate, locs['it'])
+            w.add_scalar('Policy/mean_noise_std', mean_std.item(), locs['it'])
+            w.add_scalar('Perf/total_fps', fps, locs['it'])
+            w.add_scalar('Perf/collection time', locs['collection_time'], locs['it'])
+            w.add_scalar('Perf/learning_time', locs['learn_time'], locs['it'])
+            if len(locs['rewbuffer']) > 0:
+                w.add_scalar('Train/mean_reward', statistics.mean(locs['rewbuffer']), locs['it'])
+                w.add_scalar('Train/mean_episode_length', statistics.mean(locs['lenbuffer']), locs['it'])
+                w.add_scalar('Train/mean_reward/time', statistics.mean(locs['rewbuffer']), self.tot_time)
+                w.add_scalar('Train/mean_episode_length/time', statistics.mean(locs['lenbuffer']), self.tot_time)
+        head = f" \033[1m Learning iteration {locs['it']}/{self.current_learning_iteration + locs['num_learning_iterations']} \033[0m "
+        log_string = (f"""{'#' * width}\n{head.center(width, ' ')}\n\n"""
+                      f"""{'Computation:':>{pad}} {fps:.0f} steps/s (collection: {locs['collection_time']:.3f}s, learning {locs['learn_time']:.3f}s)\n"""
+                      f"""{'Value function loss:':>{pad}} {locs['mean_value_loss']:.4f}\n"""
+                      f"""{'Surrogate loss:':>{pad}} {locs['mean_surrogate_loss']:.4f}\n"""
+                      f"""{'Mean action noise std:':>{pad}} {mean_std.item():.2f}\n""")
+        if len(locs['rewbuffer']) > 0:
+            log_string += (f"""{'Mean reward:':>{pad}} {statistics.mean(locs['rewbuffer']):.2f}\n"""
+                           f"""{'Mean episode length:':>{pad}} {statistics.mean(locs['lenbuffer']):.2f}\n""")
+        log_string += ep_string
+        log_string += (f"""{'-' * width}\n{'Total timesteps:':>{pad}} {self.tot_timesteps}\n"""
+                       f"""{'Iteration time:':>{pad}} {iteration_time:.2f}s\n{'Total time:':>{pad}} {self.tot_time:.2f}s\n"""
+                       f"""{'ETA:':>{pad}} {self.tot_time / (locs['it'] + 1) * (locs['num_learning_iterations'] - locs['it']):.1f}s\n""")
+        print(log_string)
+
+    def save(self, path, it, last_model, infos=None):
+        torch.save({'model_state_dict': self.alg.actor_critic.state_dict(), 'optimizer_state_dict': self.alg.optimizer_state_dict(),
+                    'iter': self.current_learning_iteration, 'infos': infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        loaded_dict = torch.load(path, map_location=self.device, weights_only=False)
+        self.alg.actor_critic.load_state_dict(loaded_dict['model_state_dict'])
+        if load_optimizer and loaded_dict.get('optimizer_state_dict') is not None:
+            self.alg.load_optimizer_state_dict(loaded_dict['optimizer_state_dict'])
+        self.current_learning_iteration = loaded_dict['iter']
+        return loaded_dict['infos']
+
+    def get_inference_policy(self, device=None):
+        self.alg.actor_critic.eval()
+        return self.alg.actor_critic.act_inference
