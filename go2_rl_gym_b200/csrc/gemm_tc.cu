@@ -1,0 +1,368 @@
+// gemm_tc.cu — the trainer's dense contraction on Blackwell tensor cores: C[M,N] = A[M,K] · B[N,K]^T, fp32 in HBM,
+// tf32 multiply / fp32 accumulate in TMEM (tcgen05.mma.kind::tf32), operands streamed by TMA (cp.async.bulk.tensor, 128B
+// swizzle) through an mbarrier ring, fused epilogues for the three uses of the MLP path:
+//   forward   Y  = act(X W^T + b)                     (A = X  [rows, in],  B = W   [out, in])        actor_critic.py:58-79
+//   dgrad     dX = (dZ W) * ELU'(Y_prev)              (A = dZ [rows, out], B = W^T [in, out])        autograd of the above
+//   wgrad     dW = dZ^T X  (split over the rows)      (A = dZ^T [out, rows], B = X^T [in, rows])
+// Both operands are always K-major (contraction index contiguous): the producers of activations / gradients emit the
+// transposed copy next to the row-major one (epilogue flag), which costs one extra coalesced store instead of an MN-major
+// tf32 descriptor (tf32 only allows the special 128B_BASE32B layout there).
+//
+// CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM -> registers -> global; warp w owns TMEM lanes 32*(w%4)..+31).  One 128 x BN tile per CTA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+
+#include "../../include/go2_b200.h"
+#include "common.cuh"
+
+namespace go2 {
+
+constexpr int TC_BM = 128;        // UMMA M (cta_group::1)
+constexpr int TC_BK = 32;         // floats per stage along K = one 128-byte swizzle atom
+constexpr int TC_UMMA_K = 8;      // tf32: 32 bytes of K per instruction
+constexpr int TC_THREADS = 192;
+
+enum { TC_EPI_PLAIN = 0, TC_EPI_BIAS = 1, TC_EPI_BIAS_ELU = 2, TC_EPI_MUL_ELU_GRAD = 3 };
+
+struct TcParams {
+  int M, N, K;             // logical sizes (rows of A, rows of B, contraction)
+  int kb_per_split;        // K blocks (of TC_BK) each grid.z slice handles
+  float* C; long ldc;      // row-major output (may be null)
+  float* Ct; long ldct;    // transposed output Ct[n][m] (may be null)
+  const float* bias;       // [N] or null
+  const float* aux; long ldaux;  // ELU output of the previous layer (dgrad) or null
+  int epi;
+  long split_stride;       // elements between consecutive split slices of C
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+               "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, "
+      "%29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows at 128-byte pitch, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int total_kb = (p.K + TC_BK - 1) / TC_BK;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nkb = max(0, min(p.kb_per_split, total_kb - kb0));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        mbar_expect_tx(full_bar + s, STAGE_BYTES);
+        tma_load_2d(&tmA, full_bar + s, sa, (kb0 + kb) * TC_BK, m0);
+        tma_load_2d(&tmB, full_bar + s, sa + A_BYTES, (kb0 + kb) * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(full_bar + s, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+          // advance 32 bytes of K inside the swizzle atom: +2 in the (address >> 4) field
+          umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);                       // frees the smem slot when these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full);        // accumulator complete
+      }
+      __syncwarp();
+    }
+    if (nkb == 0 && elect_one()) {                        // empty K range: nothing to wait for
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_full)) : "memory");
+    }
+  } else {
+    // ===== epilogue warps: quadrant q of the 128 TMEM lanes
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + 32 * q + lane;
+    float* Cz = p.C ? p.C + (long)blockIdx.z * p.split_stride : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), r);
+      else { for (int j = 0; j < 32; ++j) r[j] = 0; }
+      const int nb = n0 + c * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        const int n = nb + j;
+        if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) x += (n < p.N) ? __ldg(p.bias + n) : 0.0f;
+        if (p.epi == TC_EPI_BIAS_ELU) x = x > 0.0f ? x : expm1f(x);
+        v[j] = x;
+      }
+      if (p.epi == TC_EPI_MUL_ELU_GRAD && m < p.M) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int n = nb + 4 * j4;
+          if (n + 3 < p.N) {
+            const float4 y = *reinterpret_cast<const float4*>(p.aux + (long)m * p.ldaux + n);
+            v[4 * j4] *= (y.x > 0.0f ? 1.0f : y.x + 1.0f); v[4 * j4 + 1] *= (y.y > 0.0f ? 1.0f : y.y + 1.0f);
+            v[4 * j4 + 2] *= (y.z > 0.0f ? 1.0f : y.z + 1.0f); v[4 * j4 + 3] *= (y.w > 0.0f ? 1.0f : y.w + 1.0f);
+          } else {
+            for (int t = 0; t < 4; ++t) if (n + t < p.N) { float y = p.aux[(long)m * p.ldaux + n + t]; v[4 * j4 + t] *= (y > 0.0f ? 1.0f : y + 1.0f); }
+          }
+        }
+      }
+      if (Cz && m < p.M) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int n = nb + 4 * j4;
+          if (n + 3 < p.N) *reinterpret_cast<float4*>(Cz + (long)m * p.ldc + n) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          else { for (int t = 0; t < 4; ++t) if (n + t < p.N) Cz[(long)m * p.ldc + n + t] = v[4 * j4 + t]; }
+        }
+      }
+      if (p.Ct && m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const int n = nb + j; if (n < p.N) p.Ct[(long)n * p.ldct + m] = v[j]; }  // coalesced across lanes
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+  }
+}
+
+// out[i] = sum_z part[z][i] (deterministic split-K reduction); rows x cols with output leading dimension ld_out
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int Z, long ld_part, long ld_out, int cols) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long r = i / cols, c = i % cols;
+  float s = 0;
+  for (int z = 0; z < Z; ++z) s += part[(long)z * ld_part * (n / cols) + r * ld_part + c];
+  out[r * ld_out + c] = s;
+}
+
+// out[r][c] = in[c][r]  (weights W -> W^T for dgrad), tile transpose through shared memory
+__global__ void transpose_kernel(const float* __restrict__ in, long ldin, float* __restrict__ out, long ldout, int rows, int cols) {
+  __shared__ float t[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
+  for (int i = 0; i < 32; i += 8) if (r + i < rows && c < cols) t[threadIdx.y + i][threadIdx.x] = in[(long)(r + i) * ldin + c];
+  __syncthreads();
+  int oc = blockIdx.y * 32 + threadIdx.x, orow = blockIdx.x * 32 + threadIdx.y;
+  for (int i = 0; i < 32; i += 8) if (orow + i < cols && oc < rows) out[(long)(orow + i) * ldout + oc] = t[threadIdx.x][threadIdx.y + i];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)sym;
+  });
+  return fn;
+}
+// row-major [rows, cols] fp32 with leading dimension ld (elements); box = 32 floats x box_rows, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(4, "cuTensorMapEncodeTiled unavailable");
+  if (((uintptr_t)ptr & 15) || ((ld * 4) & 15)) return set_error(5, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(6, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + BN - 1) / BN, splits);
+  gemm_tf32_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tb, p);
+  count_launch();
+  return 0;
+}
+
+// C[M,N] = A[M,K] B[N,K]^T with both operands K-major; see TcParams for the epilogue
+static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams p, int splits, cudaStream_t st) {
+  const int BN = p.N > 64 ? 128 : 64;
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, A, p.M, p.K, lda, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&tb, B, p.N, p.K, ldb, BN);
+  if (rc) return rc;
+  const int total_kb = (p.K + TC_BK - 1) / TC_BK;
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  if (BN == 128) rc = launch_tc<128, 5>(ta, tb, p, splits, st);
+  else rc = launch_tc<64, 6>(ta, tb, p, splits, st);
+  if (rc) return rc;
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace go2
+
+using namespace go2;
+
+extern "C" {
+
+// Y[M,N] (and optionally Yt[N,M]) = act(X[M,K] W[N,K]^T + b)
+int go2_linear_forward_tc(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N,
+                          int K, int act, void* stream) {
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.C = Y; p.ldc = ldy; p.Ct = Yt; p.ldct = ldyt; p.bias = b; p.epi = act ? TC_EPI_BIAS_ELU : TC_EPI_BIAS;
+  return gemm_tc(X, ldx, W, ldw, p, 1, (cudaStream_t)stream);
+}
+
+// dX[M,K] (and dXt[K,M]) = (dZ[M,N] Wt[K,N]^T) * ELU'(act_in);  Wt = W^T stored [K, N]
+int go2_linear_dgrad_tc(const float* dZ, int lddz, const float* Wt, int ldwt, const float* act_in, int ldact, float* dX, int lddx, float* dXt,
+                        int lddxt, int M, int N, int K, void* stream) {
+  TcParams p{};
+  p.M = M; p.N = K; p.K = N; p.C = dX; p.ldc = lddx; p.Ct = dXt; p.ldct = lddxt; p.aux = act_in; p.ldaux = ldact;
+  p.epi = act_in ? TC_EPI_MUL_ELU_GRAD : TC_EPI_PLAIN;
+  return gemm_tc(dZ, lddz, Wt, ldwt, p, 1, (cudaStream_t)stream);
+}
+
+// dW[N,K] = dZt[N,M] Xt[K,M]^T, split over the M rows through `workspace` (deterministic)
+int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, int M, int N, int K, float* workspace,
+                        long workspace_floats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BN = K > 64 ? 128 : 64;
+  const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);
+  const int total_kb = (M + TC_BK - 1) / TC_BK;
+  int splits = max(1, min(min(total_kb / 4, 64), (296 + tiles - 1) / tiles));
+  const long ldp = (K + 3) / 4 * 4;
+  while (splits > 1 && (long)splits * N * ldp > workspace_floats) --splits;
+  if (!workspace) splits = 1;
+  TcParams p{};
+  p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN;
+  if (splits == 1 && lddw % 4 == 0) {
+    p.C = dW; p.ldc = lddw;
+    return gemm_tc(dZt, lddzt, Xt, ldxt, p, 1, st);
+  }
+  if (!workspace || (long)N * ldp > workspace_floats) return set_error(5, "go2_linear_wgrad_tc: workspace too small");
+  p.C = workspace; p.ldc = ldp; p.split_stride = (long)N * ldp;
+  int rc = gemm_tc(dZt, lddzt, Xt, ldxt, p, splits, st);
+  if (rc) return rc;
+  const long n = (long)N * K;
+  tc_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, ldp, lddw, K);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream) {
+  dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, ldin, out, ldout, rows, cols);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

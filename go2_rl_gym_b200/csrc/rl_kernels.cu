@@ -28,7 +28,7 @@ template <bool A_K_CONTIG, bool B_J_CONTIG>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, long sai, long sak, const float* __restrict__ B, long sbk,
                                                         long sbj, float* __restrict__ C, long ldc, int M, int N, int K, int k_chunk,
                                                         const float* __restrict__ bias, int epi, const float* __restrict__ aux, long ldaux,
-                                                        long split_stride) {
+                                                        long split_stride, float* __restrict__ Ct, long ldct) {
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 4], Bs[BK][BN + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
       if (epi == EPI_BIAS || epi == EPI_BIAS_ELU) v += bias[gj];
       if (epi == EPI_BIAS_ELU) v = v > 0.0f ? v : expm1f(v);
       if (epi == EPI_MUL_ELU_GRAD) { float y = aux[gi * ldaux + gj]; v *= (y > 0.0f ? 1.0f : y + 1.0f); }
-      Cz[gi * ldc + gj] = v;
+      if (C) Cz[gi * ldc + gj] = v;
+      if (Ct) Ct[gj * ldct + gi] = v;
     }
   }
 }
@@ -202,11 +203,25 @@ __global__ void adv_normalize_kernel(float* __restrict__ adv, long n, const doub
 }
 
 // mini_batch_generator gather (rollout_storage.py:173-181): dst[i, 0:w] = src[idx[i], 0:w], dst row stride ldd (zero padded)
-__global__ void gather_rows_kernel(const float* __restrict__ src, int w, const int64_t* __restrict__ idx, float* __restrict__ dst, int ldd, long n) {
+__global__ void gather_rows_kernel(const float* __restrict__ src, int w, const int64_t* __restrict__ idx, float* __restrict__ dst, int ldd, long n,
+                                   float* __restrict__ dst_t) {
+  __shared__ float tile[8][33];
   const long i = (long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (i >= n) return;
-  const long s = idx[i];
-  for (int c = threadIdx.x; c < ldd; c += blockDim.x) dst[i * ldd + c] = c < w ? src[s * w + c] : 0.0f;
+  const long s = (i < n) ? (idx ? idx[i] : i) : 0;
+  for (int c0 = 0; c0 < ldd; c0 += 32) {
+    const int c = c0 + threadIdx.x;
+    float v = (i < n && c < w) ? src[s * w + c] : 0.0f;
+    if (i < n && c < ldd && dst) dst[i * ldd + c] = v;
+    if (dst_t) {  // transposed copy dst_t[c][i] (row pitch n), staged through shared memory so both sides stay coalesced
+      tile[threadIdx.y][threadIdx.x] = v;
+      __syncthreads();
+      const int tr = threadIdx.x % 8, tc = threadIdx.y * 4 + threadIdx.x / 8;  // 8 rows i x 32 cols -> each thread one element
+      const long ii = (long)blockIdx.x * blockDim.y + tr;
+      const int cc = c0 + tc;
+      if (ii < n && cc < w) dst_t[(long)cc * n + ii] = tile[tr][tc];
+      __syncthreads();
+    }
+  }
 }
 
 // ================================================================================================ PPO loss, forward + backward
@@ -215,7 +230,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int w, const i
 struct PpoLossArgs {
   const float* mu; const float* std_param; const float* value; const float* actions; const float* old_logp; const float* adv;
   const float* target_values; const float* returns; const float* old_mu; const float* old_sigma;
-  float* dmu; float* dvalue; float* scal;
+  float* dmu; float* dmu_t; float* dvalue; float* scal;
   int M, A; float clip, value_coef, entropy_coef; int use_clipped_value_loss; float inv_count;  // 1 / (global mini-batch rows)
 };
 __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs p) {
@@ -257,7 +272,9 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs p) {
     for (int k = 0; k < p.A; ++k) {
       const float m = p.mu[(long)i * p.A + k], s = p.std_param[k], a = p.actions[(long)i * p.A + k];
       const float d = a - m;
-      p.dmu[(long)i * p.A + k] = dlp * d / (s * s);                       // d lp / d mu = (a - mu) / s^2
+      const float g = dlp * d / (s * s);                                  // d lp / d mu = (a - mu) / s^2
+      p.dmu[(long)i * p.A + k] = g;
+      if (p.dmu_t) p.dmu_t[(long)k * p.M + i] = g;
       dstd[k] = dlp * (d * d / (s * s * s) - 1.0f / s)                      // d lp / d s
                 - p.entropy_coef * p.inv_count / s;                         // - coef * d mean(entropy) / d s
     }
@@ -330,12 +347,13 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
 using namespace go2;
 
 static int launch_gemm(int a_k_contig, int b_j_contig, const float* A, long sai, long sak, const float* B, long sbk, long sbj, float* C, long ldc,
-                       int M, int N, int K, int splits, const float* bias, int epi, const float* aux, long ldaux, long split_stride, cudaStream_t st) {
+                       int M, int N, int K, int splits, const float* bias, int epi, const float* aux, long ldaux, long split_stride, cudaStream_t st,
+                       float* Ct = nullptr, long ldct = 0) {
   dim3 grid((N + 63) / 64, (M + 63) / 64, splits), block(256);
   const int k_chunk = ((K + splits - 1) / splits + 15) / 16 * 16;
-  if (a_k_contig && !b_j_contig) gemm_simt_kernel<true, false><<<grid, block, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, k_chunk, bias, epi, aux, ldaux, split_stride);
-  else if (a_k_contig && b_j_contig) gemm_simt_kernel<true, true><<<grid, block, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, k_chunk, bias, epi, aux, ldaux, split_stride);
-  else if (!a_k_contig && b_j_contig) gemm_simt_kernel<false, true><<<grid, block, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, k_chunk, bias, epi, aux, ldaux, split_stride);
+  if (a_k_contig && !b_j_contig) gemm_simt_kernel<true, false><<<grid, block, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, k_chunk, bias, epi, aux, ldaux, split_stride, Ct, ldct);
+  else if (a_k_contig && b_j_contig) gemm_simt_kernel<true, true><<<grid, block, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, k_chunk, bias, epi, aux, ldaux, split_stride, Ct, ldct);
+  else if (!a_k_contig && b_j_contig) gemm_simt_kernel<false, true><<<grid, block, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, k_chunk, bias, epi, aux, ldaux, split_stride, Ct, ldct);
   else return set_error(3, "gemm layout not instantiated");
   count_launch();
   return 0;
@@ -343,16 +361,16 @@ static int launch_gemm(int a_k_contig, int b_j_contig, const float* A, long sai,
 
 extern "C" {
 
-int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int N, int K, int act, void* stream) {
-  int rc = launch_gemm(1, 0, X, ldx, 1, W, 1, ldw, Y, ldy, M, N, K, 1, b, act ? EPI_BIAS_ELU : EPI_BIAS, nullptr, 0, 0, (cudaStream_t)stream);
+int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N, int K, int act, void* stream) {
+  int rc = launch_gemm(1, 0, X, ldx, 1, W, 1, ldw, Y, ldy, M, N, K, 1, b, act ? EPI_BIAS_ELU : EPI_BIAS, nullptr, 0, 0, (cudaStream_t)stream, Yt, ldyt);
   if (rc) return rc;
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int go2_linear_dgrad_simt(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, int M, int N, int K, void* stream) {
+int go2_linear_dgrad_simt(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream) {
   // dX[M,K] = dY[M,N] W[N,K], times ELU'(act_in) when act_in != NULL
-  int rc = launch_gemm(1, 1, dY, lddy, 1, W, ldw, 1, dX, lddx, M, K, N, 1, nullptr, act_in ? EPI_MUL_ELU_GRAD : EPI_NONE, act_in, ldact, 0, (cudaStream_t)stream);
+  int rc = launch_gemm(1, 1, dY, lddy, 1, W, ldw, 1, dX, lddx, M, K, N, 1, nullptr, act_in ? EPI_MUL_ELU_GRAD : EPI_NONE, act_in, ldact, 0, (cudaStream_t)stream, dXt, lddxt);
   if (rc) return rc;
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -377,6 +395,13 @@ int go2_linear_wgrad_simt(const float* dY, int lddy, const float* X, int ldx, fl
     count_launch();
   }
   if (db) { colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(dY, lddy, db, M, N); count_launch(); }
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int go2_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream) {
+  colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(dY, lddy, db, M, N);
+  count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -415,22 +440,22 @@ int go2_adv_normalize(float* advantages, long n, const double* stats, double glo
   return 0;
 }
 
-int go2_gather_rows(const float* src, int width, const int64_t* idx, float* dst, int ldd, long n, void* stream) {
+int go2_gather_rows(const float* src, int width, const int64_t* idx, float* dst, int ldd, float* dst_t, long n, void* stream) {
   dim3 block(32, 8);
-  gather_rows_kernel<<<(unsigned)((n + 7) / 8), block, 0, (cudaStream_t)stream>>>(src, width, idx, dst, ldd, n);
+  gather_rows_kernel<<<(unsigned)((n + 7) / 8), block, 0, (cudaStream_t)stream>>>(src, width, idx, dst, ldd, n, dst_t);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int go2_ppo_loss(const float* mu, const float* std_param, const float* value, const float* actions, const float* old_logp, const float* adv,
-                 const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dvalue,
+                 const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dmu_t, float* dvalue,
                  float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss, float inv_count,
                  void* stream) {
   if (A > 16) return set_error(1, "go2_ppo_loss: at most 16 actions");
   cudaStream_t st = (cudaStream_t)stream;
   GO2_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(float) * (4 + 16), st));
-  PpoLossArgs p{mu, std_param, value, actions, old_logp, adv, target_values, returns, old_mu, old_sigma, dmu, dvalue, scal,
+  PpoLossArgs p{mu, std_param, value, actions, old_logp, adv, target_values, returns, old_mu, old_sigma, dmu, dmu_t, dvalue, scal,
                 M, A, clip, value_coef, entropy_coef, use_clipped_value_loss, inv_count};
   ppo_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(p);
   count_launch();

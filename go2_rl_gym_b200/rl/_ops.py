@@ -9,15 +9,20 @@ from .. import _abi
 
 _vp, _i, _f, _l = C.c_void_p, C.c_int, C.c_float, C.c_long
 _SIGS = {
-    "go2_linear_forward_simt": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "go2_linear_dgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "go2_linear_forward_simt": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "go2_linear_forward_tc": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "go2_linear_dgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "go2_linear_dgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
     "go2_linear_wgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
+    "go2_linear_wgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _l, _vp],
+    "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
+    "go2_colsum": [_vp, _i, _vp, _i, _i, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
     "go2_process_env_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp],
     "go2_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp],
     "go2_adv_normalize": [_vp, _l, _vp, C.c_double, _vp],
-    "go2_gather_rows": [_vp, _i, _vp, _vp, _i, _l, _vp],
-    "go2_ppo_loss": [_vp] * 13 + [_i, _i, _f, _f, _f, _i, _f, _vp],
+    "go2_gather_rows": [_vp, _i, _vp, _vp, _i, _vp, _l, _vp],
+    "go2_ppo_loss": [_vp] * 14 + [_i, _i, _f, _f, _f, _i, _f, _vp],
     "go2_kl_adaptive_lr": [_vp, _f, _f, _vp, _vp, _vp],
     "go2_adam_clip_step": [_vp, _vp, _vp, _vp, _l, _f, _vp, _i, _f, _vp, _vp],
 }
@@ -51,46 +56,104 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-USE_TC = os.environ.get("GO2_GEMM", "tc") != "simt"
+def use_tc():
+    """GO2_GEMM=simt forces the strict-fp32 CUDA-core GEMM everywhere (numerical cross-check of the tensor-core path)."""
+    return os.environ.get("GO2_GEMM", "tc") != "simt"
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
 
 
 class MlpEngine:
-    """A chain of Linear(+ELU) layers evaluated with the library's GEMM kernels on views of a flat parameter vector.
+    """A chain of Linear(+ELU) layers on views of a flat parameter vector, evaluated by the library's GEMM kernels.
 
-    dims = [in, h1, ..., out]; ELU after every layer but the last (actor_critic.py:58-79).  `weights[l]`/`biases[l]` are
-    views into the flat parameter buffer, `gweights[l]`/`gbiases[l]` the matching views into the flat gradient buffer."""
+    dims = [in, h1, ..., out]; ELU after every layer but the last (actor_critic.py:58-79).  Tensor-core path
+    (tcgen05, tf32 multiply / fp32 accumulate): every contraction is K-major, so
+      * forward needs X [M, in] and W [out, in] with 16-byte row pitches -> the first layer uses a zero-padded copy of its
+        weight (refreshed after each optimiser step) and callers pass inputs whose leading dimension is a multiple of 4;
+      * dgrad needs W^T (refreshed with the weights) and writes dZ both row-major and transposed;
+      * wgrad contracts over the batch rows and therefore reads the TRANSPOSED activations / gradients, which the forward and
+        dgrad epilogues (and the gather / loss kernels for the two ends of the chain) emit next to the row-major copies.
+    Layers whose shapes cannot meet the TMA alignment rules (a 1-wide output in dgrad) run on the CUDA-core GEMM."""
 
-    def __init__(self, dims, weights, biases, gweights, gbiases, max_rows, device):
+    def __init__(self, dims, weights, biases, gweights, gbiases, max_rows, device, train_rows=0):
         self.dims, self.L = list(dims), len(dims) - 1
         self.W, self.b, self.gW, self.gb = weights, biases, gweights, gbiases
-        self.max_rows = max_rows
-        self.acts = [torch.empty(max_rows, d, device=device) for d in dims[1:-1]]
+        self.max_rows, self.train_rows = max_rows, train_rows
+        self.tc = use_tc()
+        dev = device
+        self.acts = [torch.empty(max_rows, d, device=dev) for d in dims[1:-1]]
+        self.actsT = [torch.empty(d, train_rows, device=dev) for d in dims[1:-1]] if (train_rows and self.tc) else None
         hmax = max(dims[1:-1]) if self.L > 1 else dims[-1]
-        self.dbuf = [torch.empty(max_rows, hmax, device=device) for _ in range(2)]
-        self.work = torch.empty(64 * max(dims[l] * dims[l + 1] for l in range(self.L)), device=device)
+        self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(2)]
+        self.dbufT = [torch.empty(hmax, max(train_rows, 1), device=dev) for _ in range(2)] if (train_rows and self.tc) else None
+        self.work = torch.empty(64 * max(_pad4(dims[l]) * dims[l + 1] for l in range(self.L)), device=dev)
+        # derived weight copies for the tensor-core path
+        self.kpad0 = _pad4(dims[0])
+        self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if (self.tc and self.kpad0 != dims[0]) else None
+        self.Wt = [None] + [torch.empty(dims[l], _pad4(dims[l + 1]), device=dev) for l in range(1, self.L)] if self.tc else None
+        self._xpad = torch.zeros(max_rows, self.kpad0, device=dev) if self.tc else None
+        self.dirty = True
 
-    def forward(self, X, ldx, M, out, ld_out, save=True):
-        """out[M, dims[-1]] = MLP(X[M, dims[0]]); keeps the hidden activations when save (needed by backward)."""
-        assert M <= self.max_rows
+    def mark_dirty(self):
+        self.dirty = True
+
+    def _refresh(self, need_wt):
+        if not self.tc or not self.dirty:
+            return
+        if self.W0p is not None:
+            self.W0p[:, :self.dims[0]].copy_(self.W[0])
+        if need_wt:
+            for l in range(1, self.L):
+                call("go2_transpose", ptr(self.W[l]), self.dims[l], ptr(self.Wt[l]), self.Wt[l].shape[1], self.dims[l + 1], self.dims[l])
+            self.dirty = False
+        elif self.W0p is None:
+            self.dirty = False
+
+    def forward(self, X, ldx, M, out, ld_out, train=False, Xt=None, ldxt=0):
+        """out[M, dims[-1]] = MLP(X[M, dims[0]]).  train=True keeps what backward() needs (Xt = X^T [in, M] for wgrad)."""
+        assert M <= self.max_rows and (not train or M <= self.train_rows)
+        self._refresh(need_wt=train)
         src, lds = X, ldx
+        if self.tc and (ldx % 4 or X.data_ptr() % 16):  # inputs straight from the env rows (ld 45 / 263): zero-padded staging copy
+            call("go2_gather_rows", ptr(X), self.dims[0], 0, ptr(self._xpad), self.kpad0, 0, M)
+            src, lds = self._xpad, self.kpad0
         for l in range(self.L):
             last = l == self.L - 1
             dst, ldd = (out, ld_out) if last else (self.acts[l], self.dims[l + 1])
-            call("go2_linear_forward_simt", ptr(src), lds, ptr(self.W[l]), self.dims[l], ptr(self.b[l]), ptr(dst), ldd, M, self.dims[l + 1],
-                 self.dims[l], 0 if last else 1)
+            dstT, lddT = (None, 0) if (last or not train or not self.tc) else (self.actsT[l], self.train_rows)
+            if self.tc:
+                W, ldw = (self.W0p, self.kpad0) if (l == 0 and self.W0p is not None) else (self.W[l], self.dims[l])
+                call("go2_linear_forward_tc", ptr(src), lds, ptr(W), ldw, ptr(self.b[l]), ptr(dst), ldd, ptr(dstT), lddT, M, self.dims[l + 1],
+                     self.dims[l], 0 if last else 1)
+            else:
+                call("go2_linear_forward_simt", ptr(src), lds, ptr(self.W[l]), self.dims[l], ptr(self.b[l]), ptr(dst), ldd, 0, 0, M,
+                     self.dims[l + 1], self.dims[l], 0 if last else 1)
             src, lds = dst, ldd
-        self._X, self._ldx, self._M = X, ldx, M
+        self._M, self._Xt, self._ldxt = M, Xt, ldxt
+        self._Xin, self._ldxin = (self._xpad, self.kpad0) if (self.tc and (ldx % 4 or X.data_ptr() % 16)) else (X, ldx)
 
-    def backward(self, dY, lddy):
-        """Accumulates nothing: overwrites gW/gb with d loss / d params for the rows of the last forward()."""
+    def backward(self, dY, lddy, dYt=None, lddyt=0):
+        """Overwrites gW/gb with d loss / d params for the rows of the last forward(train=True).
+        dY [M, out] row-major; dYt [out, M] its transpose (tensor-core wgrad); both are produced by the loss kernel."""
         M = self._M
-        d, ldd = dY, lddy
+        d, ldd, dT, lddT = dY, lddy, dYt, lddyt
         for l in range(self.L - 1, -1, -1):
-            xin, ldx = (self._X, self._ldx) if l == 0 else (self.acts[l - 1], self.dims[l])
-            call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), self.dims[l], ptr(self.gb[l]), M, self.dims[l + 1],
-                 self.dims[l], ptr(self.work), self.work.numel())
+            n_out, n_in = self.dims[l + 1], self.dims[l]
+            call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out)
+            xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in)
+            if self.tc and dT is not None and (l > 0 or self._Xt is not None):
+                xT, ldxT = (self._Xt, self._ldxt) if l == 0 else (self.actsT[l - 1], self.train_rows)
+                call("go2_linear_wgrad_tc", ptr(dT), lddT, ptr(xT), ldxT, ptr(self.gW[l]), n_in, M, n_out, n_in, ptr(self.work), self.work.numel())
+            else:
+                call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())
             if l > 0:
-                nxt = self.dbuf[l % 2]
-                call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), self.dims[l], ptr(self.acts[l - 1]), self.dims[l], ptr(nxt),
-                     self.dims[l], M, self.dims[l + 1], self.dims[l])
-                d, ldd = nxt, self.dims[l]
+                nxt, nxtT = self.dbuf[l % 2], (self.dbufT[l % 2] if self.dbufT is not None else None)
+                if self.tc and n_out % 4 == 0:
+                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,
+                         ptr(nxtT), self.train_rows, M, n_out, n_in)
+                else:
+                    call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,
+                         ptr(nxtT), self.train_rows if nxtT is not None else 0, M, n_out, n_in)
+                d, ldd, dT, lddT = nxt, n_in, nxtT, self.train_rows

@@ -48,7 +48,7 @@ class PPO:
         T = num_transitions_per_env
         self.mini_batch_size = (num_envs * T) // self.num_mini_batches
         ac = self.actor_critic
-        ac.flatten_(dev, max(num_envs, self.mini_batch_size))
+        ac.flatten_(dev, max(num_envs, self.mini_batch_size), train_rows=self.mini_batch_size)
         n = ac.flat_params.numel()
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
@@ -57,6 +57,7 @@ class PPO:
         self._log = torch.zeros(4, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
         self._dmu = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
+        self._dmu_t = torch.empty(action_shape[0], self.mini_batch_size, device=dev)
         self._dval = torch.empty(self.mini_batch_size, 1, device=dev)
         self._mu_b = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
         self._val_b = torch.empty(self.mini_batch_size, 1, device=dev)
@@ -108,9 +109,13 @@ class PPO:
     def update(self, indices=None):
         st, ac = self.storage, self.actor_critic
         mb, A = self.mini_batch_size, st.actions.shape[-1]
+        sh_w = (st.privileged_observations if st.privileged_observations is not None else st.observations).shape[-1]
         if indices is None:
             indices = torch.randperm(self.num_mini_batches * mb, device=self.device)
-        sh = st.shuffled(indices, {})
+        tc = _ops.use_tc()
+        pads = {"obs": (st.observations.shape[-1] + 3) // 4 * 4, "critic_obs": (sh_w + 3) // 4 * 4} if tc else {}
+        sh = st.shuffled(indices, pads, transposed=("obs", "critic_obs") if tc else ())
+        total = indices.numel()
         self._log.zero_()
         inv_count = 1.0 / (mb * self.world_size)
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
@@ -119,14 +124,16 @@ class PPO:
             for i in range(self.num_mini_batches):
                 s = slice(i * mb, (i + 1) * mb)
                 obs_b, cobs_b = sh["obs"][s], sh["critic_obs"][s]
-                ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A)
-                ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1)
+                obs_t = sh["obs_t"][:, s] if tc else None
+                cobs_t = sh["critic_obs_t"][:, s] if tc else None
+                ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A, train=True, Xt=obs_t, ldxt=total)
+                ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, Xt=cobs_t, ldxt=total)
                 _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
                           _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
-                          _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dval), _ops.ptr(self._scal),
+                          _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0, _ops.ptr(self._dval), _ops.ptr(self._scal),
                           mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss), inv_count)
-                ac.actor_engine.backward(self._dmu, A)
-                ac.critic_engine.backward(self._dval, 1)
+                ac.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
+                ac.critic_engine.backward(self._dval, 1, self._dval if tc else None, mb)   # [mb,1] and its transpose share storage
                 std_grad.copy_(self._scal[4:4 + A])
                 if self.world_size > 1:
                     # one collective per optimiser step: flat gradient + the scalar tail (KL / loss sums) ride together
@@ -136,6 +143,7 @@ class PPO:
                 self._opt_step += 1
                 _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
                           ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), self._opt_step, 1.0, _ops.ptr(self._scratch))
+                ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
         num_updates = self.num_learning_epochs * self.num_mini_batches
         log = self._log.tolist()          # the single host sync of update()
         self.learning_rate = log[3]

@@ -41,7 +41,7 @@ class ActorCritic(nn.Module):
         self._mean = None
 
     # ---- flat parameter storage ------------------------------------------------------------------------------
-    def flatten_(self, device, max_rows):
+    def flatten_(self, device, max_rows, train_rows=0):
         """Move to `device`, re-home every parameter inside one flat vector (parameters() order: std, actor.*, critic.*)."""
         params = list(self.parameters())
         n = sum(p.numel() for p in params)
@@ -65,7 +65,7 @@ class ActorCritic(nn.Module):
             b = [self._views[f"{seq_name}.{i}.bias"] for i in idx]
             gW = [self._gviews[f"{seq_name}.{i}.weight"] for i in idx]
             gb = [self._gviews[f"{seq_name}.{i}.bias"] for i in idx]
-            return _ops.MlpEngine(dims, W, b, gW, gb, max_rows, device)
+            return _ops.MlpEngine(dims, W, b, gW, gb, max_rows, device, train_rows=train_rows)
 
         self.actor_engine = engine("actor", self.actor_dims)
         self.critic_engine = engine("critic", self.critic_dims)
@@ -94,6 +94,7 @@ class ActorCritic(nn.Module):
             for k, p in own.items():
                 if k in state_dict:
                     p.data.copy_(state_dict[k].to(p.device))
+        self.actor_engine.mark_dirty(); self.critic_engine.mark_dirty()
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     # ---- reference API ---------------------------------------------------------------------------------------
@@ -119,7 +120,7 @@ class ActorCritic(nn.Module):
         obs = observations if observations.is_contiguous() else observations.contiguous()
         M = obs.shape[0]
         out = self._mu_buf[:M] if out is None else out
-        self.actor_engine.forward(obs, obs.shape[1], M, out, self.num_actions, save=save)
+        self.actor_engine.forward(obs, obs.shape[1], M, out, self.num_actions)
         self._mean = out
         return out
 

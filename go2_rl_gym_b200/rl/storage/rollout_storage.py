@@ -67,9 +67,10 @@ class RolloutStorage:
         done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
         return (done_indices[1:] - done_indices[:-1]).float().mean(), self.rewards.mean()
 
-    def shuffled(self, indices, pads):
+    def shuffled(self, indices, pads, transposed=()):
         """Gather every per-sample field in `indices` order (time-major flatten, rollout_storage.py:152-165).
-        pads: dict field -> padded row length. Returns dict of [T*N, ld] tensors (cached buffers)."""
+        pads: field -> padded row length; transposed: fields that also get a [width, T*N] transposed copy (key + '_t').
+        Returns dict of cached buffers."""
         n = indices.numel()
         if not hasattr(self, "_sh"):
             self._sh = {}
@@ -83,7 +84,13 @@ class RolloutStorage:
             buf = self._sh.get(k)
             if buf is None or buf.shape != (n, ld):
                 buf = self._sh[k] = torch.empty(n, ld, device=self.device)
-            _ops.call("go2_gather_rows", _ops.ptr(src), w, _ops.ptr(indices), _ops.ptr(buf), ld, n)
+            bt = None
+            if k in transposed:
+                bt = self._sh.get(k + "_t")
+                if bt is None or bt.shape != (w, n):
+                    bt = self._sh[k + "_t"] = torch.empty(w, n, device=self.device)
+                out[k + "_t"] = bt
+            _ops.call("go2_gather_rows", _ops.ptr(src), w, _ops.ptr(indices), _ops.ptr(buf), ld, _ops.ptr(bt), n)
             out[k] = buf
         return out
 

@@ -185,11 +185,21 @@ long long go2_kernel_launch_count(void); /* kernels launched by this library sin
  * All matrices row-major fp32 with explicit leading dimensions; every pointer is device memory. */
 
 /* Y[M,N] = act(X[M,K] W[N,K]^T + b[N]); act: 0 none, 1 ELU   (nn.Linear + nn.ELU, actor_critic.py:58-79) */
-int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int N, int K, int act, void* stream);
+int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N, int K, int act, void* stream);
+/* same contraction on the tensor cores (tcgen05.mma kind::tf32, TMA-fed; csrc/gemm_tc.cu); Yt (optional) receives Y^T [N,M] */
+int go2_linear_forward_tc(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N, int K, int act, void* stream);
 /* dX[M,K] = dY[M,N] W[N,K], multiplied by ELU'(act_in) when act_in (the layer input's post-activation) is given */
-int go2_linear_dgrad_simt(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, int M, int N, int K, void* stream);
+int go2_linear_dgrad_simt(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream);
+/* tensor-core dgrad: Wt = W^T stored [K,N]; dXt (optional) receives dX^T [K,M] */
+int go2_linear_dgrad_tc(const float* dZ, int lddz, const float* Wt, int ldwt, const float* act_in, int ldact, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream);
 /* dW[N,K] = dY^T X, db[N] = column sums of dY; deterministic split over the M rows through `workspace` */
 int go2_linear_wgrad_simt(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K, float* workspace, long workspace_floats, void* stream);
+/* tensor-core wgrad from the transposed copies dZt [N,M], Xt [K,M] (contraction over the M rows is then K-major for both operands) */
+int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, int M, int N, int K, float* workspace, long workspace_floats, void* stream);
+/* out[cols,rows] = in[rows,cols]^T */
+int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
+/* db[N] = column sums of dY[M,N] */
+int go2_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */
 int go2_sample_actions(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A, uint64_t seed, uint32_t step, int env_offset, void* stream);
 /* PPO.process_env_step (ppo.py:104-111): rewards += gamma V time_out; rows of the transition */
@@ -198,11 +208,12 @@ int go2_process_env_step(const float* rew, const uint8_t* dones, const uint8_t* 
 int go2_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, float* returns, float* advantages, int T, int N, float gamma, float lam, double* stats, void* stream);
 /* advantages = (adv - mean) / (std + 1e-8) with the (possibly all-reduced) stats and global count (rollout_storage.py:136-137) */
 int go2_adv_normalize(float* advantages, long n, const double* stats, double global_count, void* stream);
-/* mini-batch gather (rollout_storage.py:173-181): dst[i, :width] = src[idx[i], :width], zero padded to ldd */
-int go2_gather_rows(const float* src, int width, const int64_t* idx, float* dst, int ldd, long n, void* stream);
+/* mini-batch gather (rollout_storage.py:173-181): dst[i, :width] = src[idx[i], :width] (idx NULL = identity), zero padded to ldd;
+ * dst_t (optional) receives the transposed copy [width, n] */
+int go2_gather_rows(const float* src, int width, const int64_t* idx, float* dst, int ldd, float* dst_t, long n, void* stream);
 /* PPO losses forward + backward (ppo.py:131-171). scal[20]: sum KL, sum surrogate, sum value loss, sum entropy, d/d std[16] */
 int go2_ppo_loss(const float* mu, const float* std_param, const float* value, const float* actions, const float* old_logp, const float* adv,
-                 const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dvalue,
+                 const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dmu_t, float* dvalue,
                  float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss, float inv_count, void* stream);
 /* KL-adaptive learning rate on the device (ppo.py:139-151); log_out[4] accumulates value/surrogate loss, holds kl, lr */
 int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* lr_state, float* log_out, void* stream);

@@ -16,6 +16,10 @@ def _t(k, dev="cuda"):
     return torch.from_numpy(Z[k]).to(dev)
 
 
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
 @pytest.mark.parametrize("M,N,K,act", [(1000, 512, 45, 1), (4096, 256, 512, 1), (333, 12, 128, 0), (2048, 1, 128, 0), (24576, 512, 263, 1)])
 def test_linear_forward(M, N, K, act):
     from go2_rl_gym_b200.rl import _ops
@@ -24,9 +28,55 @@ def test_linear_forward(M, N, K, act):
     ref = torch.nn.functional.linear(X, W, b)
     ref = torch.nn.functional.elu(ref) if act else ref
     Xd, Wd, bd = X.cuda(), W.cuda(), b.cuda()
-    Y = torch.empty(M, N, device="cuda")
-    _ops.call("go2_linear_forward_simt", Xd.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Y.data_ptr(), N, M, N, K, act)
+    Y, Yt = torch.empty(M, N, device="cuda"), torch.empty(N, M, device="cuda")
+    _ops.call("go2_linear_forward_simt", Xd.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Y.data_ptr(), N, Yt.data_ptr(), M, M, N, K, act)
     assert torch.allclose(Y.cpu(), ref, rtol=1e-4, atol=1e-4)      # fp32 FMA chain vs fp32 blocked sum
+    assert torch.equal(Yt.t().contiguous(), Y)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1000, 512, 48, 1), (4096, 256, 512, 1), (333, 12, 128, 0), (2048, 1, 128, 0), (24576, 512, 264, 1),
+                                       (24576, 128, 256, 1), (130, 64, 32, 0)])
+def test_linear_forward_tensor_core(M, N, K, act):
+    """tcgen05 tf32 x tf32 -> fp32: operands are truncated to 10 mantissa bits, so the bar is 2e-3 relative (norm-wise) and
+    5e-3 * sqrt(K)-scaled absolute per element."""
+    from go2_rl_gym_b200.rl import _ops
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    X, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    ref = torch.nn.functional.linear(X, W, b)
+    ref = torch.nn.functional.elu(ref) if act else ref
+    Xd, Wd, bd = X.cuda(), W.cuda(), b.cuda()
+    Y, Yt = torch.zeros(M, N, device="cuda"), torch.zeros(N, M, device="cuda")
+    _ops.call("go2_linear_forward_tc", Xd.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Y.data_ptr(), N, Yt.data_ptr(), M, M, N, K, act)
+    torch.cuda.synchronize()
+    assert _rel(Y.cpu(), ref) < 2e-3, _rel(Y.cpu(), ref)
+    assert torch.allclose(Y.cpu(), ref, rtol=5e-3, atol=5e-3)
+    assert torch.equal(Yt.t().contiguous(), Y)
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 256, 512), (24576, 128, 256), (777 * 4, 12, 128), (24576, 512, 45), (24576, 1, 128)])
+def test_linear_backward_tensor_core(M, N, K):
+    from go2_rl_gym_b200.rl import _ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    Xact = torch.nn.functional.elu(torch.randn(M, K, generator=g))
+    W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    dY = torch.randn(M, N, generator=g)
+    dX_ref = (dY @ W) * torch.where(Xact > 0, torch.ones_like(Xact), Xact + 1)
+    dW_ref = dY.t() @ Xact
+    dYd, Xd = dY.cuda(), Xact.cuda()
+    dYt, Xt = dYd.t().contiguous(), Xd.t().contiguous()
+    dW = torch.zeros(N, K, device="cuda")
+    work = torch.empty(64 * N * ((K + 3) // 4 * 4), device="cuda")
+    _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW.data_ptr(), K, M, N, K, work.data_ptr(), work.numel())
+    torch.cuda.synchronize()
+    assert _rel(dW.cpu(), dW_ref) < 2e-3, _rel(dW.cpu(), dW_ref)
+    if N % 4 == 0 and K % 4 == 0:
+        Np = N
+        Wt = W.t().contiguous().cuda()                        # [K, N]
+        dX, dXt = torch.zeros(M, K, device="cuda"), torch.zeros(K, M, device="cuda")
+        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, Xd.data_ptr(), K, dX.data_ptr(), K, dXt.data_ptr(), M, M, N, K)
+        torch.cuda.synchronize()
+        assert _rel(dX.cpu(), dX_ref) < 2e-3, _rel(dX.cpu(), dX_ref)
+        assert torch.equal(dXt.t().contiguous(), dX)
 
 
 @pytest.mark.parametrize("M,N,K", [(1000, 512, 45), (8192, 256, 512), (24576, 128, 256), (777, 12, 128)])
@@ -42,7 +92,7 @@ def test_linear_backward(M, N, K):
     dYd, Wd, Xd = dY.cuda(), W.cuda(), Xact.cuda()
     dX, dW, db = torch.empty(M, K, device="cuda"), torch.empty(N, K, device="cuda"), torch.empty(N, device="cuda")
     work = torch.empty(64 * N * K, device="cuda")
-    _ops.call("go2_linear_dgrad_simt", dYd.data_ptr(), N, Wd.data_ptr(), K, Xd.data_ptr(), K, dX.data_ptr(), K, M, N, K)
+    _ops.call("go2_linear_dgrad_simt", dYd.data_ptr(), N, Wd.data_ptr(), K, Xd.data_ptr(), K, dX.data_ptr(), K, 0, 0, M, N, K)
     _ops.call("go2_linear_wgrad_simt", dYd.data_ptr(), N, Xd.data_ptr(), K, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
     assert torch.allclose(dX.cpu(), dX_ref, rtol=1e-4, atol=1e-4)
     scale = math.sqrt(M)
@@ -63,8 +113,13 @@ def test_gae_matches_reference_fixture():
     assert torch.allclose(st.advantages.cpu(), torch.from_numpy(Z["st_advantages"]), atol=2e-5)
 
 
-def test_ppo_update_matches_reference_fixture():
-    """Whole PPO.update (5 epochs x 4 mini-batches, adaptive LR, clip + Adam) vs the reference's result on the same data."""
+@pytest.mark.parametrize("gemm", ["simt", "tc"])
+def test_ppo_update_matches_reference_fixture(gemm, monkeypatch):
+    """Whole PPO.update (5 epochs x 4 mini-batches, adaptive LR, clip + Adam) vs the reference's result on the same data.
+    simt = strict fp32 GEMMs: parameters within 1e-3 rel / 2e-5 abs.  tc = tf32 tensor-core GEMMs (10-bit mantissa operands):
+    Adam divides by sqrt(v), which amplifies gradient rounding on near-zero gradients, so the bar is on the UPDATE as a whole:
+    || (new - old) - (ref_new - old) || <= 5 % of || ref_new - old ||, losses within 2e-3, identical learning-rate path."""
+    monkeypatch.setenv("GO2_GEMM", gemm)
     from golden.rl_cfg import CFG
     from go2_rl_gym_b200.rl.algorithms import PPO
     from go2_rl_gym_b200.rl.modules import ActorCritic
@@ -77,13 +132,22 @@ def test_ppo_update_matches_reference_fixture():
     for k in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
         getattr(st, k).copy_(_t("st_" + k))
     mvl, msl = alg.update(indices=_t("perm"))
-    assert abs(mvl - float(Z["mean_value_loss"])) < 1e-4 and abs(msl - float(Z["mean_surrogate_loss"])) < 1e-4
+    tol_l, atol_p = (1e-4, 2e-5) if gemm == "simt" else (2e-3, None)
+    assert abs(mvl - float(Z["mean_value_loss"])) < tol_l and abs(msl - float(Z["mean_surrogate_loss"])) < tol_l
     assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
+    worst, num, den = 0.0, 0.0, 0.0
     for k, v in ac.state_dict().items():
-        ref = torch.from_numpy(Z["sd1_" + k])
-        assert torch.allclose(v.cpu(), ref, rtol=1e-3, atol=2e-5), (k, float((v.cpu() - ref).abs().max()))
-    osd = alg.optimizer_state_dict()
-    assert torch.allclose(osd["state"][1]["exp_avg"].cpu(), torch.from_numpy(Z["adam_exp_avg_1"]), rtol=1e-3, atol=1e-6)
+        ref, old = torch.from_numpy(Z["sd1_" + k]), torch.from_numpy(Z["sd0_" + k])
+        worst = max(worst, float((v.cpu() - ref).abs().max()))
+        num += float(((v.cpu() - old) - (ref - old)).pow(2).sum()); den += float((ref - old).pow(2).sum())
+        if atol_p is not None:
+            assert torch.allclose(v.cpu(), ref, rtol=1e-3, atol=atol_p), (k, float((v.cpu() - ref).abs().max()))
+    rel = (num / den) ** 0.5
+    print(f"[{gemm}] after 20 optimiser steps: max |param - reference| = {worst:.2e}, relative error of the update = {rel:.3e}")
+    assert rel < (1e-3 if gemm == "simt" else 5e-2)
+    if gemm == "simt":
+        osd = alg.optimizer_state_dict()
+        assert torch.allclose(osd["state"][1]["exp_avg"].cpu(), torch.from_numpy(Z["adam_exp_avg_1"]), rtol=1e-3, atol=1e-6)
 
 
 def test_act_and_process_env_step():
@@ -101,11 +165,11 @@ def test_act_and_process_env_step():
     from oracle import rl_oracle as R
     mu = R.mlp_forward(sd, "actor", obs.cpu()); v = R.mlp_forward(sd, "critic", priv.cpu())
     st = alg.storage
-    assert torch.allclose(st.mu[0].cpu(), mu, atol=1e-4) and torch.allclose(st.values[0].cpu(), v, atol=1e-4)
+    assert torch.allclose(st.mu[0].cpu(), mu, atol=3e-3) and torch.allclose(st.values[0].cpu(), v, atol=3e-3)   # tf32 forward
     z = (a.cpu() - mu) / sd["std"]
     assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02      # Philox Box-Muller normals
     lp = R.log_prob(st.mu[0].cpu(), sd["std"], a.cpu())
-    assert torch.allclose(st.actions_log_prob[0].cpu().squeeze(-1), lp, atol=1e-4)
+    assert torch.allclose(st.actions_log_prob[0].cpu().squeeze(-1), lp, atol=1e-3)
     rew = torch.randn(N, device="cuda"); dones = torch.rand(N, device="cuda") < 0.1; touts = dones & (torch.rand(N, device="cuda") < 0.5)
     alg.process_env_step(rew, dones, {"time_outs": touts})
     exp = rew + CFG["gamma"] * st.values[0].squeeze(-1) * touts.float()
