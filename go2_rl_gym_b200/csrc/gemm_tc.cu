@@ -101,7 +101,7 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -299,8 +299,8 @@ static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams 
   if (rc) return rc;
   const int total_kb = (p.K + TC_BK - 1) / TC_BK;
   p.kb_per_split = (total_kb + splits - 1) / splits;
-  if (BN == 128) rc = launch_tc<128, 5>(ta, tb, p, splits, st);
-  else rc = launch_tc<64, 6>(ta, tb, p, splits, st);
+  if (BN == 128) rc = launch_tc<128, 3>(ta, tb, p, splits, st);   // 3 x 32 KB stages -> two CTAs per SM (epilogue of one overlaps the mainloop of the other)
+  else rc = launch_tc<64, 4>(ta, tb, p, splits, st);
   if (rc) return rc;
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -107,15 +107,23 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   out[(i / cols) * ld_out + (i % cols)] = s;
 }
 
-// db[j] = sum_m dY[m][j] : one block per 32 columns, 8 row groups, fixed-order tree
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, long ld, float* __restrict__ db, int M, int N) {
+// db[j] = sum_m dY[m][j], deterministic two-stage: grid (col blocks of 32, row chunks) -> part[chunk][j], then a fixed-order sum
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dY, long ld, float* __restrict__ part, int M, int N, int rows_per_chunk) {
   __shared__ float sm[8][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32, j = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
   float s = 0;
-  if (j < N) for (int m = ty; m < M; m += 8) s += dY[(long)m * ld + j];
+  if (j < N) for (int m = r0 + ty; m < r1; m += 8) s += dY[(long)m * ld + j];
   sm[ty][tx] = s;
   __syncthreads();
-  if (ty == 0 && j < N) { float t = 0; for (int r = 0; r < 8; ++r) t += sm[r][tx]; db[j] = t; }
+  if (ty == 0 && j < N) { float t = 0; for (int r = 0; r < 8; ++r) t += sm[r][tx]; part[(long)blockIdx.y * N + j] = t; }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ db, int N, int chunks) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float t = 0;
+  for (int c = 0; c < chunks; ++c) t += part[(long)c * N + j];
+  db[j] = t;
 }
 
 // ================================================================================================ rollout kernels
@@ -321,8 +329,14 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
   if (threadIdx.x == 0) part[blockIdx.x] = red[0];
 }
-__global__ void sumsq_final_kernel(const float* __restrict__ part, int nb, float* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { float s = 0; for (int i = 0; i < nb; ++i) s += part[i]; out[0] = s; }
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ part, int nb, float* __restrict__ out) {
+  __shared__ float red[256];
+  float s = 0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = red[0];
 }
 // clip_grad_norm_(max_norm) fused with Adam (torch defaults: beta 0.9/0.999, eps 1e-8, no weight decay)
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
@@ -394,13 +408,19 @@ int go2_linear_wgrad_simt(const float* dY, int lddy, const float* X, int ldx, fl
     splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, lddw, K);
     count_launch();
   }
-  if (db) { colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(dY, lddy, db, M, N); count_launch(); }
+  if (db) return set_error(1, "go2_linear_wgrad_simt: bias gradient moved to go2_colsum");
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int go2_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream) {
-  colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(dY, lddy, db, M, N);
+int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = max(1, min(64, M / 256));
+  const int rpc = (M + chunks - 1) / chunks;
+  dim3 grid((N + 31) / 32, chunks);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(dY, lddy, scratch, M, N, rpc);
+  count_launch();
+  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(scratch, db, N, chunks);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -476,7 +496,7 @@ int go2_adam_clip_step(float* params, const float* grads, float* exp_avg, float*
   const int nb = (int)min((long)1024, (n + 255) / 256);
   sumsq_partial_kernel<<<nb, 256, 0, st>>>(grads, n, scratch + 1);
   count_launch();
-  sumsq_final_kernel<<<1, 32, 0, st>>>(scratch + 1, nb, scratch);
+  sumsq_final_kernel<<<1, 256, 0, st>>>(scratch + 1, nb, scratch);
   count_launch();
   const double b1 = 0.9, b2 = 0.999;
   const float bc1 = (float)(1.0 - pow(b1, step)), bc2s = (float)sqrt(1.0 - pow(b2, step));

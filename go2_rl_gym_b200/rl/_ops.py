@@ -16,7 +16,7 @@ _SIGS = {
     "go2_linear_wgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_linear_wgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _l, _vp],
     "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
-    "go2_colsum": [_vp, _i, _vp, _i, _i, _vp],
+    "go2_colsum": [_vp, _i, _vp, _i, _i, _vp, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
     "go2_process_env_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp],
     "go2_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp],
@@ -141,7 +141,7 @@ class MlpEngine:
         d, ldd, dT, lddT = dY, lddy, dYt, lddyt
         for l in range(self.L - 1, -1, -1):
             n_out, n_in = self.dims[l + 1], self.dims[l]
-            call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out)
+            call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
             xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in)
             if self.tc and dT is not None and (l > 0 or self._Xt is not None):
                 xT, ldxT = (self._Xt, self._ldxt) if l == 0 else (self.actsT[l - 1], self.train_rows)

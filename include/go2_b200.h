@@ -199,7 +199,7 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
 /* out[cols,rows] = in[rows,cols]^T */
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
 /* db[N] = column sums of dY[M,N] */
-int go2_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream);
+int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */
 int go2_sample_actions(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A, uint64_t seed, uint32_t step, int env_offset, void* stream);
 /* PPO.process_env_step (ppo.py:104-111): rewards += gamma V time_out; rows of the transition */

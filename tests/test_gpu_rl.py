@@ -93,7 +93,8 @@ def test_linear_backward(M, N, K):
     dX, dW, db = torch.empty(M, K, device="cuda"), torch.empty(N, K, device="cuda"), torch.empty(N, device="cuda")
     work = torch.empty(64 * N * K, device="cuda")
     _ops.call("go2_linear_dgrad_simt", dYd.data_ptr(), N, Wd.data_ptr(), K, Xd.data_ptr(), K, dX.data_ptr(), K, 0, 0, M, N, K)
-    _ops.call("go2_linear_wgrad_simt", dYd.data_ptr(), N, Xd.data_ptr(), K, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
+    _ops.call("go2_linear_wgrad_simt", dYd.data_ptr(), N, Xd.data_ptr(), K, dW.data_ptr(), K, 0, M, N, K, work.data_ptr(), work.numel())
+    _ops.call("go2_colsum", dYd.data_ptr(), N, db.data_ptr(), M, N, work.data_ptr())
     assert torch.allclose(dX.cpu(), dX_ref, rtol=1e-4, atol=1e-4)
     scale = math.sqrt(M)
     assert torch.allclose(dW.cpu(), dW_ref, rtol=1e-4, atol=2e-4 * scale)
