@@ -86,6 +86,6 @@ def ppo_update(sd, data, indices, cfg):
             torch.nn.utils.clip_grad_norm_([params[k] for k in order], cfg["max_grad_norm"])
             opt.step()
             mvl += vloss.item(); msl += surr.item()
-            rec.append((float(vloss), float(surr), float(lr)))
+            rec.append((float(vloss.detach()), float(surr.detach()), float(lr)))
     n = cfg["num_learning_epochs"] * cfg["num_mini_batches"]
     return {k: v.detach() for k, v in params.items()}, mvl / n, msl / n, lr, rec
