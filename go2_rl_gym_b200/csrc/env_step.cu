@@ -15,7 +15,7 @@ namespace go2 {
 
 constexpr int WARPS_PER_CTA = 4;
 
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, 4)
 step_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
             const __grid_constant__ Go2StepParams sp, const float* __restrict__ actions) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];

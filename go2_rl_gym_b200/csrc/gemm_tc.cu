@@ -33,9 +33,11 @@ struct TcParams {
   float* C; long ldc;      // row-major output (may be null)
   float* Ct; long ldct;    // transposed output Ct[n][m] (may be null)
   const float* bias;       // [N] or null
-  const float* aux; long ldaux;  // ELU output of the previous layer (dgrad) or null
+  const float* aux; long ldaux;  // ELU output of the previous layer (dgrad), row-major, or null
+  const float* aux_t; long ldaux_t;  // the same activation transposed [N, M] (preferred: coalesced in the epilogue)
   int epi;
   long split_stride;       // elements between consecutive split slices of C
+  long long* dbg;          // optional [gridDim.x*gridDim.y][8] clock64 stamps (profiling aid)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -104,7 +106,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, keeps the shared address space
   constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -113,6 +115,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  long long* dbg = p.dbg ? p.dbg + (long)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int total_kb = (p.K + TC_BK - 1) / TC_BK;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = max(0, min(p.kb_per_split, total_kb - kb0));
@@ -132,6 +136,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer
@@ -171,56 +176,100 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_full)) : "memory");
     }
   } else {
-    // ===== epilogue warps: quadrant q of the 128 TMEM lanes
+    // ===== epilogue warps: quadrant q of the 128 TMEM lanes.  Thread = one output row; the transposed copy is stored straight
+    // from registers (lanes = consecutive rows -> coalesced), the row-major copy goes through a padded 32x32 shared tile so
+    // that every store instruction writes one 128-byte row segment.  ELU' (dgrad) reads the TRANSPOSED activation, also coalesced.
     const int q = warp & 3;
+    float* tile = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 36);
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + 32 * q + lane;
+    if (dbg && threadIdx.x == 64) dbg[2] = clock64();
+    const int mrow0 = m0 + 32 * q;
+    const int m = mrow0 + lane;
     float* Cz = p.C ? p.C + (long)blockIdx.z * p.split_stride : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= p.N) break;
       uint32_t r[32];
       if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), r);
       else { for (int j = 0; j < 32; ++j) r[j] = 0; }
-      const int nb = n0 + c * 32;
       float v[32];
+      float bias_lane = 0.0f;   // one coalesced load per chunk, broadcast by shuffle
+      if ((p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) && nb + lane < p.N) bias_lane = __ldg(p.bias + nb + lane);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(r[j]);
-        const int n = nb + j;
-        if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) x += (n < p.N) ? __ldg(p.bias + n) : 0.0f;
-        if (p.epi == TC_EPI_BIAS_ELU) x = x > 0.0f ? x : expm1f(x);
+        if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) x += __shfl_sync(0xffffffffu, bias_lane, j);
+        if (p.epi == TC_EPI_BIAS_ELU) x = x > 0.0f ? x : (__expf(x) - 1.0f);   // |abs err| < 2e-7: below tf32 resolution of the product
         v[j] = x;
       }
-      if (p.epi == TC_EPI_MUL_ELU_GRAD && m < p.M) {
+      if (p.epi == TC_EPI_MUL_ELU_GRAD && (m < p.M || (p.aux_t && mrow0 + 31 < p.M))) {
+        if (p.aux_t && (p.ldaux_t & 3) == 0 && mrow0 + 31 < p.M) {
+          // 128-bit loads of the transposed activation (4 columns x 128 B per instruction), redistributed through the shared tile
+          const int mc = (lane & 7) * 4;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = nb + 4 * j4;
-          if (n + 3 < p.N) {
-            const float4 y = *reinterpret_cast<const float4*>(p.aux + (long)m * p.ldaux + n);
-            v[4 * j4] *= (y.x > 0.0f ? 1.0f : y.x + 1.0f); v[4 * j4 + 1] *= (y.y > 0.0f ? 1.0f : y.y + 1.0f);
-            v[4 * j4 + 2] *= (y.z > 0.0f ? 1.0f : y.z + 1.0f); v[4 * j4 + 3] *= (y.w > 0.0f ? 1.0f : y.w + 1.0f);
-          } else {
-            for (int t = 0; t < 4; ++t) if (n + t < p.N) { float y = p.aux[(long)m * p.ldaux + n + t]; v[4 * j4 + t] *= (y > 0.0f ? 1.0f : y + 1.0f); }
+          for (int it = 0; it < 8; ++it) {
+            const int jj = it * 4 + (lane >> 3), n = nb + jj;
+            float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (n < p.N) y = __ldg(reinterpret_cast<const float4*>(p.aux_t + (long)n * p.ldaux_t + mrow0 + mc));
+            *reinterpret_cast<float4*>(tile + jj * 36 + mc) = y;
           }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float y = tile[j * 36 + lane]; v[j] *= (y > 0.0f ? 1.0f : y + 1.0f); }
+          __syncwarp();
+        } else if (p.aux_t) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const int n = nb + j; if (n < p.N) { const float y = __ldg(p.aux_t + (long)n * p.ldaux_t + m); v[j] *= (y > 0.0f ? 1.0f : y + 1.0f); } }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const int n = nb + j; if (n < p.N) { const float y = p.aux[(long)m * p.ldaux + n]; v[j] *= (y > 0.0f ? 1.0f : y + 1.0f); } }
         }
       }
-      if (Cz && m < p.M) {
+      // ---- stores: 128-bit vectors, 4 rows x 128 B per warp instruction, staged through a padded shared tile (pitch 36 floats)
+      constexpr int TP = 36;
+      const bool vec_ok = ((p.N & 3) == 0);
+      if (Cz) {
+        if (vec_ok && (p.ldc & 3) == 0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = nb + 4 * j4;
-          if (n + 3 < p.N) *reinterpret_cast<float4*>(Cz + (long)m * p.ldc + n) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-          else { for (int t = 0; t < 4; ++t) if (n + t < p.N) Cz[(long)m * p.ldc + n + t] = v[4 * j4 + t]; }
+          for (int q4 = 0; q4 < 8; ++q4) *reinterpret_cast<float4*>(tile + lane * TP + 4 * q4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+          __syncwarp();
+          const int cc = (lane & 7) * 4, n = nb + cc;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), mm = mrow0 + rr;
+            if (mm < p.M && n < p.N) *reinterpret_cast<float4*>(Cz + (long)mm * p.ldc + n) = *reinterpret_cast<const float4*>(tile + rr * TP + cc);
+          }
+          __syncwarp();
+        } else if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const int n = nb + j; if (n < p.N) Cz[(long)m * p.ldc + n] = v[j]; }
         }
       }
-      if (p.Ct && m < p.M) {
+      if (p.Ct) {
+        if ((p.ldct & 3) == 0 && mrow0 + 31 < p.M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const int n = nb + j; if (n < p.N) p.Ct[(long)n * p.ldct + m] = v[j]; }  // coalesced across lanes
+          for (int j = 0; j < 32; ++j) tile[j * TP + lane] = v[j];
+          __syncwarp();
+          const int mc = (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int jj = it * 4 + (lane >> 3), n = nb + jj;
+            if (n < p.N) *reinterpret_cast<float4*>(p.Ct + (long)n * p.ldct + mrow0 + mc) = *reinterpret_cast<const float4*>(tile + jj * TP + mc);
+          }
+          __syncwarp();
+        } else if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const int n = nb + j; if (n < p.N) p.Ct[(long)n * p.ldct + m] = v[j]; }
+        }
       }
     }
+    if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[4] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
@@ -228,13 +277,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // out[i] = sum_z part[z][i] (deterministic split-K reduction); rows x cols with output leading dimension ld_out
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int Z, long ld_part, long ld_out, int cols) {
+// cols = K (+1 when the bias gradient rides along as an extra "ones" column of X^T: that column goes to db)
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int Z, long ld_part, long ld_out, int cols,
+                                        int k_real, float* __restrict__ db) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long r = i / cols, c = i % cols;
   float s = 0;
   for (int z = 0; z < Z; ++z) s += part[(long)z * ld_part * (n / cols) + r * ld_part + c];
-  out[r * ld_out + c] = s;
+  if (c < k_real) out[r * ld_out + c] = s;
+  else if (db) db[r] = s;
 }
 
 // out[r][c] = in[c][r]  (weights W -> W^T for dgrad), tile transpose through shared memory
@@ -277,7 +329,7 @@ static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int splits, cudaStream_t st) {
-  constexpr int smem = STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+  constexpr int smem = STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256 + 4 * 32 * 36 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -299,8 +351,9 @@ static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams 
   if (rc) return rc;
   const int total_kb = (p.K + TC_BK - 1) / TC_BK;
   p.kb_per_split = (total_kb + splits - 1) / splits;
-  if (BN == 128) rc = launch_tc<128, 3>(ta, tb, p, splits, st);   // 3 x 32 KB stages -> two CTAs per SM (epilogue of one overlaps the mainloop of the other)
-  else rc = launch_tc<64, 4>(ta, tb, p, splits, st);
+  // 2 x 32 KB stages + 17 KB epilogue staging = 82 KB -> two CTAs per SM: the epilogue of one overlaps the mainloop of the other
+  if (BN == 128) rc = launch_tc<128, 2>(ta, tb, p, splits, st);
+  else rc = launch_tc<64, 3>(ta, tb, p, splits, st);
   if (rc) return rc;
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -321,18 +374,21 @@ int go2_linear_forward_tc(const float* X, int ldx, const float* W, int ldw, cons
 }
 
 // dX[M,K] (and dXt[K,M]) = (dZ[M,N] Wt[K,N]^T) * ELU'(act_in);  Wt = W^T stored [K, N]
-int go2_linear_dgrad_tc(const float* dZ, int lddz, const float* Wt, int ldwt, const float* act_in, int ldact, float* dX, int lddx, float* dXt,
-                        int lddxt, int M, int N, int K, void* stream) {
+int go2_linear_dgrad_tc(const float* dZ, int lddz, const float* Wt, int ldwt, const float* act_in, int ldact, const float* act_in_t, int ldact_t,
+                        float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream) {
   TcParams p{};
-  p.M = M; p.N = K; p.K = N; p.C = dX; p.ldc = lddx; p.Ct = dXt; p.ldct = lddxt; p.aux = act_in; p.ldaux = ldact;
-  p.epi = act_in ? TC_EPI_MUL_ELU_GRAD : TC_EPI_PLAIN;
+  p.M = M; p.N = K; p.K = N; p.C = dX; p.ldc = lddx; p.Ct = dXt; p.ldct = lddxt; p.aux = act_in; p.ldaux = ldact; p.aux_t = act_in_t; p.ldaux_t = ldact_t;
+  p.epi = (act_in || act_in_t) ? TC_EPI_MUL_ELU_GRAD : TC_EPI_PLAIN;
   return gemm_tc(dZ, lddz, Wt, ldwt, p, 1, (cudaStream_t)stream);
 }
 
 // dW[N,K] = dZt[N,M] Xt[K,M]^T, split over the M rows through `workspace` (deterministic)
-int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, int M, int N, int K, float* workspace,
+int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, float* db, int M, int N, int K, float* workspace,
                         long workspace_floats, void* stream) {
+  // db != NULL: Xt carries one extra row of ones after its K feature rows, so column K of the product is the bias gradient
   cudaStream_t st = (cudaStream_t)stream;
+  const int k_real = K;
+  if (db) K = K + 1;
   const int BN = K > 64 ? 128 : 64;
   const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);
   const int total_kb = (M + TC_BK - 1) / TC_BK;
@@ -342,7 +398,7 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
   if (!workspace) splits = 1;
   TcParams p{};
   p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN;
-  if (splits == 1 && lddw % 4 == 0) {
+  if (splits == 1 && lddw % 4 == 0 && !db) {
     p.C = dW; p.ldc = lddw;
     return gemm_tc(dZt, lddzt, Xt, ldxt, p, 1, st);
   }
@@ -351,10 +407,18 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
   int rc = gemm_tc(dZt, lddzt, Xt, ldxt, p, splits, st);
   if (rc) return rc;
   const long n = (long)N * K;
-  tc_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, ldp, lddw, K);
+  tc_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, ldp, lddw, K, k_real, db);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// profiling aid: forward GEMM with per-CTA clock64 stamps {start, setup done, accumulator ready, epilogue done, end}
+int go2_linear_forward_tc_dbg(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N,
+                              int K, int act, long long* dbg, void* stream) {
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.C = Y; p.ldc = ldy; p.Ct = Yt; p.ldct = ldyt; p.bias = b; p.epi = act ? TC_EPI_BIAS_ELU : TC_EPI_BIAS; p.dbg = dbg;
+  return gemm_tc(X, ldx, W, ldw, p, 1, (cudaStream_t)stream);
 }
 
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream) {

@@ -338,12 +338,22 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restric
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
   if (threadIdx.x == 0) out[0] = red[0];
 }
+// optimiser step counter and bias corrections live on the device (lr_state = {lr, step, 1-beta1^t, sqrt(1-beta2^t)}) so that a
+// whole update() can be replayed as a CUDA graph
+__global__ void adam_prep_kernel(float* __restrict__ lr_state, float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float t = lr_state[1] + 1.0f;
+  lr_state[1] = t;
+  lr_state[2] = (float)(1.0 - pow((double)beta1, (double)t));
+  lr_state[3] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
+}
 // clip_grad_norm_(max_norm) fused with Adam (torch defaults: beta 0.9/0.999, eps 1e-8, no weight decay)
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                                  const float* __restrict__ sumsq, float max_norm, const float* __restrict__ lr_state, float beta1, float beta2,
-                                 float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                                 float eps, float grad_scale) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const float bc1 = lr_state[2], bc2_sqrt = lr_state[3];
   const float total = sqrtf(sumsq[0]) * grad_scale;
   float coef = max_norm / (total + 1e-6f);
   coef = coef < 1.0f ? coef : 1.0f;
@@ -490,18 +500,18 @@ int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* 
   return 0;
 }
 
-int go2_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float max_grad_norm, const float* lr_state,
-                       int step, float grad_scale, float* scratch /* >= 1025 floats */, void* stream) {
+int go2_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float max_grad_norm, float* lr_state,
+                       float grad_scale, float* scratch /* >= 1025 floats */, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = (int)min((long)1024, (n + 255) / 256);
   sumsq_partial_kernel<<<nb, 256, 0, st>>>(grads, n, scratch + 1);
   count_launch();
   sumsq_final_kernel<<<1, 256, 0, st>>>(scratch + 1, nb, scratch);
   count_launch();
-  const double b1 = 0.9, b2 = 0.999;
-  const float bc1 = (float)(1.0 - pow(b1, step)), bc2s = (float)sqrt(1.0 - pow(b2, step));
+  adam_prep_kernel<<<1, 32, 0, st>>>(lr_state, 0.9f, 0.999f);
+  count_launch();
   adam_clip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, scratch, max_grad_norm, lr_state, 0.9f, 0.999f,
-                                                                1e-8f, bc1, bc2s, grad_scale);
+                                                                1e-8f, grad_scale);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -12,9 +12,9 @@ _SIGS = {
     "go2_linear_forward_simt": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "go2_linear_forward_tc": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "go2_linear_dgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
-    "go2_linear_dgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "go2_linear_dgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
     "go2_linear_wgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
-    "go2_linear_wgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _l, _vp],
+    "go2_linear_wgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
     "go2_colsum": [_vp, _i, _vp, _i, _i, _vp, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
@@ -24,7 +24,7 @@ _SIGS = {
     "go2_gather_rows": [_vp, _i, _vp, _vp, _i, _vp, _l, _vp],
     "go2_ppo_loss": [_vp] * 14 + [_i, _i, _f, _f, _f, _i, _f, _vp],
     "go2_kl_adaptive_lr": [_vp, _f, _f, _vp, _vp, _vp],
-    "go2_adam_clip_step": [_vp, _vp, _vp, _vp, _l, _f, _vp, _i, _f, _vp, _vp],
+    "go2_adam_clip_step": [_vp, _vp, _vp, _vp, _l, _f, _vp, _f, _vp, _vp],
 }
 _lib = None
 
@@ -84,32 +84,33 @@ class MlpEngine:
         self.tc = use_tc()
         dev = device
         self.acts = [torch.empty(max_rows, d, device=dev) for d in dims[1:-1]]
-        self.actsT = [torch.empty(d, train_rows, device=dev) for d in dims[1:-1]] if (train_rows and self.tc) else None
+        # transposed activations carry one extra row of ones: the bias gradient then falls out of the wgrad contraction
+        self.actsT = [torch.ones(d + 1, train_rows, device=dev) for d in dims[1:-1]] if (train_rows and self.tc) else None
         hmax = max(dims[1:-1]) if self.L > 1 else dims[-1]
         self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(2)]
         self.dbufT = [torch.empty(hmax, max(train_rows, 1), device=dev) for _ in range(2)] if (train_rows and self.tc) else None
-        self.work = torch.empty(64 * max(_pad4(dims[l]) * dims[l + 1] for l in range(self.L)), device=dev)
+        self.work = torch.empty(64 * max(_pad4(dims[l] + 1) * dims[l + 1] for l in range(self.L)), device=dev)
         # derived weight copies for the tensor-core path
         self.kpad0 = _pad4(dims[0])
         self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if (self.tc and self.kpad0 != dims[0]) else None
         self.Wt = [None] + [torch.empty(dims[l], _pad4(dims[l + 1]), device=dev) for l in range(1, self.L)] if self.tc else None
         self._xpad = torch.zeros(max_rows, self.kpad0, device=dev) if self.tc else None
-        self.dirty = True
+        self._dirty_w0, self._dirty_wt = True, True
 
     def mark_dirty(self):
-        self.dirty = True
+        self._dirty_w0, self._dirty_wt = True, True
 
     def _refresh(self, need_wt):
-        if not self.tc or not self.dirty:
+        if not self.tc:
             return
-        if self.W0p is not None:
-            self.W0p[:, :self.dims[0]].copy_(self.W[0])
-        if need_wt:
+        if self._dirty_w0:
+            if self.W0p is not None:
+                self.W0p[:, :self.dims[0]].copy_(self.W[0])
+            self._dirty_w0 = False
+        if need_wt and self._dirty_wt:
             for l in range(1, self.L):
                 call("go2_transpose", ptr(self.W[l]), self.dims[l], ptr(self.Wt[l]), self.Wt[l].shape[1], self.dims[l + 1], self.dims[l])
-            self.dirty = False
-        elif self.W0p is None:
-            self.dirty = False
+            self._dirty_wt = False
 
     def forward(self, X, ldx, M, out, ld_out, train=False, Xt=None, ldxt=0):
         """out[M, dims[-1]] = MLP(X[M, dims[0]]).  train=True keeps what backward() needs (Xt = X^T [in, M] for wgrad)."""
@@ -141,18 +142,19 @@ class MlpEngine:
         d, ldd, dT, lddT = dY, lddy, dYt, lddyt
         for l in range(self.L - 1, -1, -1):
             n_out, n_in = self.dims[l + 1], self.dims[l]
-            call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
             xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in)
             if self.tc and dT is not None and (l > 0 or self._Xt is not None):
-                xT, ldxT = (self._Xt, self._ldxt) if l == 0 else (self.actsT[l - 1], self.train_rows)
-                call("go2_linear_wgrad_tc", ptr(dT), lddT, ptr(xT), ldxT, ptr(self.gW[l]), n_in, M, n_out, n_in, ptr(self.work), self.work.numel())
+                xT, ldxT = (self._Xt, self._ldxt) if l == 0 else (self.actsT[l - 1], self.train_rows)   # both end with a row of ones
+                call("go2_linear_wgrad_tc", ptr(dT), lddT, ptr(xT), ldxT, ptr(self.gW[l]), n_in, ptr(self.gb[l]), M, n_out, n_in, ptr(self.work),
+                     self.work.numel())
             else:
+                call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
                 call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())
             if l > 0:
                 nxt, nxtT = self.dbuf[l % 2], (self.dbufT[l % 2] if self.dbufT is not None else None)
                 if self.tc and n_out % 4 == 0:
-                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,
-                         ptr(nxtT), self.train_rows, M, n_out, n_in)
+                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], 0, 0, ptr(self.actsT[l - 1]), self.train_rows,
+                         ptr(nxt), n_in, ptr(nxtT), self.train_rows, M, n_out, n_in)
                 else:
                     call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,
                          ptr(nxtT), self.train_rows if nxtT is not None else 0, M, n_out, n_in)

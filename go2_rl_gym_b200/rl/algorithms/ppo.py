@@ -5,6 +5,8 @@ Same constructor and method names.  Differences a caller can observe, all delibe
   * update() runs without any host synchronisation: the KL-adaptive learning rate (ppo.py:139-151) lives in a device scalar
     read by the fused clip+Adam kernel; `learning_rate` on the host is refreshed once per update() for logging;
   * with torch.distributed initialised, each optimiser step all-reduces the flat gradient (one NCCL call, scalar tail included)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -52,13 +54,18 @@ class PPO:
         n = ac.flat_params.numel()
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
-        self._lr = torch.full((1,), float(self.learning_rate), device=dev)
+        self._lr = torch.zeros(4, device=dev)      # {lr, optimiser step, Adam bias corrections} — device resident
+        self._lr[0] = float(self.learning_rate)
+        self._graph = None
+        self._graph_warm = 0
         self._scal = torch.zeros(20, device=dev)
         self._log = torch.zeros(4, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
         self._dmu = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
         self._dmu_t = torch.empty(action_shape[0], self.mini_batch_size, device=dev)
-        self._dval = torch.empty(self.mini_batch_size, 1, device=dev)
+        self._dval = torch.empty(self.mini_batch_size + 4, 1, device=dev)[:self.mini_batch_size]
+        # [1+1, mb] view of the value gradient for the tensor-core wgrad: row 0 = dV^T (same storage), then the engine's ones row is not needed here
+        self._dval_t = self._dval
         self._mu_b = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
         self._val_b = torch.empty(self.mini_batch_size, 1, device=dev)
         self._last_values = torch.empty(num_envs, 1, device=dev)
@@ -117,6 +124,35 @@ class PPO:
         sh = st.shuffled(indices, pads, transposed=("obs", "critic_obs") if tc else ())
         total = indices.numel()
         self._log.zero_()
+        self._sh, self._total, self._tc = sh, total, tc
+        use_graph = self.world_size == 1 and os.environ.get("GO2_GRAPH", "1") != "0"
+        if not use_graph:
+            self._update_body()
+        elif self._graph is None and self._graph_warm < 1:
+            self._update_body()                       # first call eager: allocations, cudaFuncSetAttribute, tensor maps
+            self._graph_warm += 1
+        elif self._graph is None:
+            # every launch of the 20 optimiser steps depends only on device-resident state -> capture once, replay per iteration
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._update_body()
+            self._graph = g
+            g.replay()
+        else:
+            self._graph.replay()
+        ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
+        self._opt_step += self.num_learning_epochs * self.num_mini_batches
+        num_updates = self.num_learning_epochs * self.num_mini_batches
+        log = self._log.tolist()          # the single host sync of update()
+        self.learning_rate = log[3]
+        st.clear()
+        return log[0] / num_updates, log[1] / num_updates
+
+    def _update_body(self):
+        st, ac = self.storage, self.actor_critic
+        sh, total, tc = self._sh, self._total, self._tc
+        mb, A = self.mini_batch_size, st.actions.shape[-1]
         inv_count = 1.0 / (mb * self.world_size)
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
         std_grad = ac._gviews["std"]
@@ -130,25 +166,20 @@ class PPO:
                 ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, Xt=cobs_t, ldxt=total)
                 _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
                           _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
-                          _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0, _ops.ptr(self._dval), _ops.ptr(self._scal),
-                          mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef, int(self.use_clipped_value_loss), inv_count)
+                          _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0,
+                          _ops.ptr(self._dval), _ops.ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+                          int(self.use_clipped_value_loss), inv_count)
                 ac.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
-                ac.critic_engine.backward(self._dval, 1, self._dval if tc else None, mb)   # [mb,1] and its transpose share storage
+                ac.critic_engine.backward(self._dval, 1, self._dval_t if tc else None, mb)
                 std_grad.copy_(self._scal[4:4 + A])
                 if self.world_size > 1:
                     # one collective per optimiser step: flat gradient + the scalar tail (KL / loss sums) ride together
                     self._allreduce_grads()
                 _ops.call("go2_kl_adaptive_lr", _ops.ptr(self._scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
                           _ops.ptr(self._lr), _ops.ptr(self._log))
-                self._opt_step += 1
                 _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
-                          ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), self._opt_step, 1.0, _ops.ptr(self._scratch))
+                          ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), 1.0, _ops.ptr(self._scratch))
                 ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
-        num_updates = self.num_learning_epochs * self.num_mini_batches
-        log = self._log.tolist()          # the single host sync of update()
-        self.learning_rate = log[3]
-        st.clear()
-        return log[0] / num_updates, log[1] / num_updates
 
     def _allreduce_grads(self):
         if not hasattr(self, "_comm"):
@@ -182,7 +213,8 @@ class PPO:
                 self.exp_avg[off:off + k].copy_(s["exp_avg"].reshape(-1))
                 self.exp_avg_sq[off:off + k].copy_(s["exp_avg_sq"].reshape(-1))
                 self._opt_step = int(float(s["step"]))
+                self._lr[1] = float(self._opt_step)
             off += k
         if sd.get("param_groups"):
             self.learning_rate = float(sd["param_groups"][0]["lr"])
-            self._lr.fill_(self.learning_rate)
+            self._lr[0] = self.learning_rate

@@ -87,8 +87,8 @@ class RolloutStorage:
             bt = None
             if k in transposed:
                 bt = self._sh.get(k + "_t")
-                if bt is None or bt.shape != (w, n):
-                    bt = self._sh[k + "_t"] = torch.empty(w, n, device=self.device)
+                if bt is None or bt.shape != (w + 1, n):
+                    bt = self._sh[k + "_t"] = torch.ones(w + 1, n, device=self.device)   # last row stays 1: bias-gradient column of the wgrad
                 out[k + "_t"] = bt
             _ops.call("go2_gather_rows", _ops.ptr(src), w, _ops.ptr(indices), _ops.ptr(buf), ld, _ops.ptr(bt), n)
             out[k] = buf

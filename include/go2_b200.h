@@ -190,12 +190,13 @@ int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, co
 int go2_linear_forward_tc(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N, int K, int act, void* stream);
 /* dX[M,K] = dY[M,N] W[N,K], multiplied by ELU'(act_in) when act_in (the layer input's post-activation) is given */
 int go2_linear_dgrad_simt(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream);
-/* tensor-core dgrad: Wt = W^T stored [K,N]; dXt (optional) receives dX^T [K,M] */
-int go2_linear_dgrad_tc(const float* dZ, int lddz, const float* Wt, int ldwt, const float* act_in, int ldact, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream);
+/* tensor-core dgrad: Wt = W^T stored [K,N]; act_in_t = the activation transposed [K,M] (either form may be NULL); dXt (optional) receives dX^T [K,M] */
+int go2_linear_dgrad_tc(const float* dZ, int lddz, const float* Wt, int ldwt, const float* act_in, int ldact, const float* act_in_t, int ldact_t, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream);
 /* dW[N,K] = dY^T X, db[N] = column sums of dY; deterministic split over the M rows through `workspace` */
 int go2_linear_wgrad_simt(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K, float* workspace, long workspace_floats, void* stream);
-/* tensor-core wgrad from the transposed copies dZt [N,M], Xt [K,M] (contraction over the M rows is then K-major for both operands) */
-int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, int M, int N, int K, float* workspace, long workspace_floats, void* stream);
+/* tensor-core wgrad from the transposed copies dZt [N,M], Xt [K,M] (contraction over the M rows is then K-major for both operands);
+ * db != NULL: Xt has one extra row of ones (row K) and db[N] receives the bias gradient from the same contraction */
+int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, float* db, int M, int N, int K, float* workspace, long workspace_floats, void* stream);
 /* out[cols,rows] = in[rows,cols]^T */
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
 /* db[N] = column sums of dY[M,N] */
@@ -217,8 +218,9 @@ int go2_ppo_loss(const float* mu, const float* std_param, const float* value, co
                  float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss, float inv_count, void* stream);
 /* KL-adaptive learning rate on the device (ppo.py:139-151); log_out[4] accumulates value/surrogate loss, holds kl, lr */
 int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* lr_state, float* log_out, void* stream);
-/* clip_grad_norm_ + Adam.step on a flat parameter vector (ppo.py:176-177); scratch >= 1025 floats */
-int go2_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float max_grad_norm, const float* lr_state, int step, float grad_scale, float* scratch, void* stream);
+/* clip_grad_norm_ + Adam.step on a flat parameter vector (ppo.py:176-177); lr_state[4] = {lr, step count, 1-beta1^t, sqrt(1-beta2^t)} lives on the
+ * device (the call increments the step), scratch >= 1025 floats */
+int go2_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float max_grad_norm, float* lr_state, float grad_scale, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

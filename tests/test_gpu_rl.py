@@ -63,17 +63,27 @@ def test_linear_backward_tensor_core(M, N, K):
     dX_ref = (dY @ W) * torch.where(Xact > 0, torch.ones_like(Xact), Xact + 1)
     dW_ref = dY.t() @ Xact
     dYd, Xd = dY.cuda(), Xact.cuda()
-    dYt, Xt = dYd.t().contiguous(), Xd.t().contiguous()
-    dW = torch.zeros(N, K, device="cuda")
-    work = torch.empty(64 * N * ((K + 3) // 4 * 4), device="cuda")
-    _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW.data_ptr(), K, M, N, K, work.data_ptr(), work.numel())
+    dYt = dYd.t().contiguous()
+    Xt = torch.cat([Xd.t(), torch.ones(1, M, device="cuda")], 0).contiguous()      # [K+1, M]: last row of ones -> bias gradient
+    dW, db = torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda")
+    work = torch.empty(64 * N * ((K + 4) // 4 * 4), device="cuda")
+    _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
     torch.cuda.synchronize()
     assert _rel(dW.cpu(), dW_ref) < 2e-3, _rel(dW.cpu(), dW_ref)
+    assert _rel(db.cpu(), dY.sum(0)) < 2e-3
+    dW2 = torch.zeros(N, K, device="cuda")
+    _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW2.data_ptr(), K, 0, M, N, K, work.data_ptr(), work.numel())
+    torch.cuda.synchronize()
+    assert _rel(dW2.cpu(), dW_ref) < 2e-3
     if N % 4 == 0 and K % 4 == 0:
         Np = N
         Wt = W.t().contiguous().cuda()                        # [K, N]
         dX, dXt = torch.zeros(M, K, device="cuda"), torch.zeros(K, M, device="cuda")
-        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, Xd.data_ptr(), K, dX.data_ptr(), K, dXt.data_ptr(), M, M, N, K)
+        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, 0, 0, Xt.data_ptr(), M, dX.data_ptr(), K, dXt.data_ptr(), M, M, N, K)
+        dX2 = torch.zeros(M, K, device="cuda")
+        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, Xd.data_ptr(), K, 0, 0, dX2.data_ptr(), K, 0, 0, M, N, K)
+        torch.cuda.synchronize()
+        assert torch.equal(dX2, dX)
         torch.cuda.synchronize()
         assert _rel(dX.cpu(), dX_ref) < 2e-3, _rel(dX.cpu(), dX_ref)
         assert torch.equal(dXt.t().contiguous(), dX)
