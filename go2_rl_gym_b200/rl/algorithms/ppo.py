@@ -10,7 +10,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from .. import _ops
+from .. import _ops, dist_utils
 from ..modules import ActorCritic
 from ..storage import RolloutStorage
 
@@ -109,8 +109,7 @@ class PPO:
         self.storage.compute_returns(self._last_values, self.gamma, self.lam, reduce_stats=self._reduce_adv_stats if self.world_size > 1 else None)
 
     def _reduce_adv_stats(self, stats):
-        dist.all_reduce(stats)
-        return self.storage.num_envs * self.storage.num_transitions_per_env * self.world_size
+        return dist_utils.allreduce_adv_stats(stats, self.storage.num_envs * self.storage.num_transitions_per_env)
 
     # ---- update ----------------------------------------------------------------------------------------------
     def update(self, indices=None):
@@ -182,15 +181,7 @@ class PPO:
                 ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
 
     def _allreduce_grads(self):
-        if not hasattr(self, "_comm"):
-            n = self.actor_critic.flat_grads.numel()
-            self._comm = torch.empty(n + 4, device=self.device)
-        n = self.actor_critic.flat_grads.numel()
-        self._comm[:n].copy_(self.actor_critic.flat_grads)
-        self._comm[n:].copy_(self._scal[:4])
-        dist.all_reduce(self._comm)
-        self.actor_critic.flat_grads.copy_(self._comm[:n])
-        self._scal[:4].copy_(self._comm[n:])
+        self._comm = dist_utils.allreduce_grads_and_tail(self.actor_critic.flat_grads, self._scal[:4], getattr(self, "_comm", None))
 
     # ---- checkpoint interop (torch.optim.Adam layout, ppo.py:67) ---------------------------------------------
     def optimizer_state_dict(self):
