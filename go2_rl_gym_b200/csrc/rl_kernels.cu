@@ -157,15 +157,17 @@ __global__ void sample_actions_kernel(const float* __restrict__ mu, const float*
 }
 
 // PPO.process_env_step (ppo.py:104-111): rewards += gamma * values * time_outs; store rewards and dones
+// perm (optional): storage row e holds env perm[e] (CTS stores teacher envs first, cts.py:144-152)
 __global__ void process_env_step_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ dones, const uint8_t* __restrict__ time_outs,
                                         const float* __restrict__ values, float* __restrict__ rew_out, uint8_t* __restrict__ dones_out, int N,
-                                        float gamma) {
+                                        float gamma, const int64_t* __restrict__ perm) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
-  float r = rew[e];
-  if (time_outs) r += gamma * (values[e] * (float)time_outs[e]);
+  const long src = perm ? perm[e] : e;
+  float r = rew[src];
+  if (time_outs) r += gamma * (values[e] * (float)time_outs[src]);
   rew_out[e] = r;
-  dones_out[e] = dones[e];
+  dones_out[e] = dones[src];
 }
 
 // RolloutStorage.compute_returns (rollout_storage.py:123-134): reverse scan per env; also the sums for the normalisation
@@ -240,10 +242,12 @@ struct PpoLossArgs {
   const float* target_values; const float* returns; const float* old_mu; const float* old_sigma;
   float* dmu; float* dmu_t; float* dvalue; float* scal;
   int M, A; float clip, value_coef, entropy_coef; int use_clipped_value_loss; float inv_count;  // 1 / (global mini-batch rows)
+  // CTS (cts.py / moe_cts.py:166-168): the surrogate is mean over the teacher rows [0, split) PLUS mean over the student rows [split, M)
+  int split; float inv_count_a, inv_count_b;
 };
 __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float kl = 0, surr = 0, vl = 0, ent = 0;
+  float kl = 0, surr = 0, surr_b = 0, vl = 0, ent = 0;
   float dstd[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) dstd[k] = 0;
@@ -260,12 +264,12 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs p) {
     const float A_ = p.adv[i];
     const float ratio = expf(lp - p.old_logp[i]);
     const float s1 = -A_ * ratio, s2 = -A_ * fminf(fmaxf(ratio, 1.0f - p.clip), 1.0f + p.clip);
-    surr = fmaxf(s1, s2);
+    if (i < p.split) surr = fmaxf(s1, s2); else surr_b = fmaxf(s1, s2);
     // d surr / d lp : the unclipped branch (or a tie) carries gradient -A ratio; the clipped branch only inside the clip range
     float dlp;
     if (s1 >= s2) dlp = -A_ * ratio;
     else dlp = (ratio > 1.0f - p.clip && ratio < 1.0f + p.clip) ? -A_ * ratio : 0.0f;
-    dlp *= p.inv_count;
+    dlp *= (i < p.split) ? p.inv_count_a : p.inv_count_b;
     const float v = p.value[i], tv = p.target_values[i], ret = p.returns[i];
     float dv;
     if (p.use_clipped_value_loss) {
@@ -302,11 +306,13 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs p) {
   t = block_sum(surr); if (threadIdx.x == 0) atomicAdd(p.scal + 1, t);
   t = block_sum(vl); if (threadIdx.x == 0) atomicAdd(p.scal + 2, t);
   t = block_sum(ent); if (threadIdx.x == 0) atomicAdd(p.scal + 3, t);
+  t = block_sum(surr_b); if (threadIdx.x == 0) atomicAdd(p.scal + 19, t);
   for (int k = 0; k < p.A; ++k) { t = block_sum(dstd[k]); if (threadIdx.x == 0) atomicAdd(p.scal + 4 + k, t); }
 }
 
 // KL-adaptive learning rate (ppo.py:139-151), entirely on the device: lr_state = {lr}
-__global__ void kl_lr_kernel(const float* __restrict__ scal, float count, float desired_kl, float* __restrict__ lr_state, float* __restrict__ log_out) {
+__global__ void kl_lr_kernel(const float* __restrict__ scal, float count, float desired_kl, float* __restrict__ lr_state, float* __restrict__ log_out,
+                             float count_a, float count_b) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float kl_mean = scal[0] / count;
   float lr = lr_state[0];
@@ -315,7 +321,7 @@ __global__ void kl_lr_kernel(const float* __restrict__ scal, float count, float 
     else if (kl_mean < desired_kl / 2.0f && kl_mean > 0.0f) lr = fminf(1e-2f, lr * 1.5f);
   }
   lr_state[0] = lr;
-  if (log_out) { log_out[0] += scal[2] / count; log_out[1] += scal[1] / count; log_out[2] = kl_mean; log_out[3] = lr; }
+  if (log_out) { log_out[0] += scal[2] / count; log_out[1] += scal[1] / count_a + scal[19] / count_b; log_out[2] = kl_mean; log_out[3] = lr; log_out[4] += scal[3] / count; }
 }
 
 // ================================================================================================ clip + Adam
@@ -446,8 +452,8 @@ int go2_sample_actions(const float* mu, const float* std_param, float* actions, 
 }
 
 int go2_process_env_step(const float* rew, const uint8_t* dones, const uint8_t* time_outs, const float* values, float* rew_out, uint8_t* dones_out,
-                         int N, float gamma, void* stream) {
-  process_env_step_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rew, dones, time_outs, values, rew_out, dones_out, N, gamma);
+                         int N, float gamma, const int64_t* perm, void* stream) {
+  process_env_step_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rew, dones, time_outs, values, rew_out, dones_out, N, gamma, perm);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -481,20 +487,20 @@ int go2_gather_rows(const float* src, int width, const int64_t* idx, float* dst,
 int go2_ppo_loss(const float* mu, const float* std_param, const float* value, const float* actions, const float* old_logp, const float* adv,
                  const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dmu_t, float* dvalue,
                  float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss, float inv_count,
-                 void* stream) {
+                 int split, float inv_count_a, float inv_count_b, void* stream) {
   if (A > 16) return set_error(1, "go2_ppo_loss: at most 16 actions");
   cudaStream_t st = (cudaStream_t)stream;
   GO2_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(float) * (4 + 16), st));
   PpoLossArgs p{mu, std_param, value, actions, old_logp, adv, target_values, returns, old_mu, old_sigma, dmu, dmu_t, dvalue, scal,
-                M, A, clip, value_coef, entropy_coef, use_clipped_value_loss, inv_count};
+                M, A, clip, value_coef, entropy_coef, use_clipped_value_loss, inv_count, split, inv_count_a, inv_count_b};
   ppo_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(p);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* lr_state, float* log_out, void* stream) {
-  kl_lr_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scal, count, desired_kl, lr_state, log_out);
+int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* lr_state, float* log_out, float count_a, float count_b, void* stream) {
+  kl_lr_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scal, count, desired_kl, lr_state, log_out, count_a, count_b);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

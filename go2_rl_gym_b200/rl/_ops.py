@@ -18,12 +18,21 @@ _SIGS = {
     "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
     "go2_colsum": [_vp, _i, _vp, _i, _i, _vp, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
-    "go2_process_env_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp],
+    "go2_process_env_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp],
     "go2_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp],
     "go2_adv_normalize": [_vp, _l, _vp, C.c_double, _vp],
     "go2_gather_rows": [_vp, _i, _vp, _vp, _i, _vp, _l, _vp],
-    "go2_ppo_loss": [_vp] * 14 + [_i, _i, _f, _f, _f, _i, _f, _vp],
-    "go2_kl_adaptive_lr": [_vp, _f, _f, _vp, _vp, _vp],
+    "go2_ppo_loss": [_vp] * 14 + [_i, _i, _f, _f, _f, _i, _f, _i, _f, _f, _vp],
+    "go2_kl_adaptive_lr": [_vp, _f, _f, _vp, _vp, _f, _f, _vp],
+    "go2_concat2": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _l, _vp],
+    "go2_l2norm_forward": [_vp, _i, _vp, _i, _vp, _l, _i, _vp],
+    "go2_l2norm_backward": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _l, _i, _vp],
+    "go2_moe_combine_forward": [_vp, _vp, _vp, _vp, _l, _i, _i, _vp],
+    "go2_moe_combine_backward": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _l, _i, _i, _vp],
+    "go2_latent_loss": [_vp, _vp, _vp, _vp, _l, _i, _vp],
+    "go2_cts_log": [_vp, _vp, _vp, _l, _i, _vp],
+    "go2_history_update": [_vp, _vp, _vp, _l, _i, _i, _vp],
+    "go2_gather_u8": [_vp, _vp, _vp, _l, _vp],
     "go2_adam_clip_step": [_vp, _vp, _vp, _vp, _l, _f, _vp, _f, _vp, _vp],
 }
 _lib = None
@@ -68,33 +77,36 @@ def _pad4(n):
 class MlpEngine:
     """A chain of Linear(+ELU) layers on views of a flat parameter vector, evaluated by the library's GEMM kernels.
 
-    dims = [in, h1, ..., out]; ELU after every layer but the last (actor_critic.py:58-79).  Tensor-core path
-    (tcgen05, tf32 multiply / fp32 accumulate): every contraction is K-major, so
+    dims = [in, h1, ..., out]; ELU after every layer but the last (actor_critic.py:58-79), or after the last one too when
+    last_act (the experts' backbone, modules/utils.py:81).  Tensor-core path (tcgen05, tf32 multiply / fp32 accumulate): every
+    contraction is K-major, so
       * forward needs X [M, in] and W [out, in] with 16-byte row pitches -> the first layer uses a zero-padded copy of its
         weight (refreshed after each optimiser step) and callers pass inputs whose leading dimension is a multiple of 4;
       * dgrad needs W^T (refreshed with the weights) and writes dZ both row-major and transposed;
       * wgrad contracts over the batch rows and therefore reads the TRANSPOSED activations / gradients, which the forward and
-        dgrad epilogues (and the gather / loss kernels for the two ends of the chain) emit next to the row-major copies.
+        dgrad epilogues (and the gather / concat / loss kernels for the two ends of the chain) emit next to the row-major
+        copies; each transposed activation carries one extra row of ones so the bias gradient falls out of the same GEMM.
     Layers whose shapes cannot meet the TMA alignment rules (a 1-wide output in dgrad) run on the CUDA-core GEMM."""
 
-    def __init__(self, dims, weights, biases, gweights, gbiases, max_rows, device, train_rows=0):
+    def __init__(self, dims, weights, biases, gweights, gbiases, max_rows, device, train_rows=0, last_act=False, need_dx=False):
         self.dims, self.L = list(dims), len(dims) - 1
         self.W, self.b, self.gW, self.gb = weights, biases, gweights, gbiases
-        self.max_rows, self.train_rows = max_rows, train_rows
+        self.max_rows, self.train_rows, self.last_act, self.need_dx = max_rows, train_rows, last_act, need_dx
         self.tc = use_tc()
         dev = device
-        self.acts = [torch.empty(max_rows, d, device=dev) for d in dims[1:-1]]
-        # transposed activations carry one extra row of ones: the bias gradient then falls out of the wgrad contraction
-        self.actsT = [torch.ones(d + 1, train_rows, device=dev) for d in dims[1:-1]] if (train_rows and self.tc) else None
+        hidden = dims[1:] if last_act else dims[1:-1]
+        self.acts = [torch.empty(max_rows, d, device=dev) for d in hidden]
+        self.actsT = [torch.ones(d + 1, train_rows, device=dev) for d in hidden] if (train_rows and self.tc) else None
         hmax = max(dims[1:-1]) if self.L > 1 else dims[-1]
         self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(2)]
         self.dbufT = [torch.empty(hmax, max(train_rows, 1), device=dev) for _ in range(2)] if (train_rows and self.tc) else None
         self.work = torch.empty(64 * max(_pad4(dims[l] + 1) * dims[l + 1] for l in range(self.L)), device=dev)
-        # derived weight copies for the tensor-core path
         self.kpad0 = _pad4(dims[0])
         self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if (self.tc and self.kpad0 != dims[0]) else None
-        self.Wt = [None] + [torch.empty(dims[l], _pad4(dims[l + 1]), device=dev) for l in range(1, self.L)] if self.tc else None
+        first_wt = 0 if need_dx else 1
+        self.Wt = ([None] * first_wt + [torch.zeros(dims[l], _pad4(dims[l + 1]), device=dev) for l in range(first_wt, self.L)]) if self.tc else None
         self._xpad = torch.zeros(max_rows, self.kpad0, device=dev) if self.tc else None
+        self.dx = torch.zeros(max(train_rows, 1), self.kpad0, device=dev) if need_dx else None
         self._dirty_w0, self._dirty_wt = True, True
 
     def mark_dirty(self):
@@ -108,36 +120,51 @@ class MlpEngine:
                 self.W0p[:, :self.dims[0]].copy_(self.W[0])
             self._dirty_w0 = False
         if need_wt and self._dirty_wt:
-            for l in range(1, self.L):
+            for l in range(0 if self.need_dx else 1, self.L):
                 call("go2_transpose", ptr(self.W[l]), self.dims[l], ptr(self.Wt[l]), self.Wt[l].shape[1], self.dims[l + 1], self.dims[l])
             self._dirty_wt = False
 
-    def forward(self, X, ldx, M, out, ld_out, train=False, Xt=None, ldxt=0):
-        """out[M, dims[-1]] = MLP(X[M, dims[0]]).  train=True keeps what backward() needs (Xt = X^T [in, M] for wgrad)."""
+    @property
+    def out(self):
+        """Last-layer activation buffer (last_act engines)."""
+        return self.acts[-1]
+
+    @property
+    def outT(self):
+        return self.actsT[-1]
+
+    def forward(self, X, ldx, M, out=None, ld_out=0, train=False, Xt=None, ldxt=0):
+        """out[M, dims[-1]] = MLP(X[M, dims[0]]).  train=True keeps what backward() needs (Xt = X^T [in (+ ones row), M] for wgrad).
+        last_act engines write their output (and its transpose) into self.out / self.outT."""
         assert M <= self.max_rows and (not train or M <= self.train_rows)
         self._refresh(need_wt=train)
         src, lds = X, ldx
         if self.tc and (ldx % 4 or X.data_ptr() % 16):  # inputs straight from the env rows (ld 45 / 263): zero-padded staging copy
             call("go2_gather_rows", ptr(X), self.dims[0], 0, ptr(self._xpad), self.kpad0, 0, M)
             src, lds = self._xpad, self.kpad0
+        self._Xin, self._ldxin = src, lds
         for l in range(self.L):
             last = l == self.L - 1
-            dst, ldd = (out, ld_out) if last else (self.acts[l], self.dims[l + 1])
-            dstT, lddT = (None, 0) if (last or not train or not self.tc) else (self.actsT[l], self.train_rows)
+            if last and not self.last_act:
+                dst, ldd, dstT, lddT = out, ld_out, None, 0
+            else:
+                dst, ldd = self.acts[l], self.dims[l + 1]
+                dstT, lddT = (self.actsT[l], self.train_rows) if (train and self.tc) else (None, 0)
+            act = 0 if (last and not self.last_act) else 1
             if self.tc:
                 W, ldw = (self.W0p, self.kpad0) if (l == 0 and self.W0p is not None) else (self.W[l], self.dims[l])
                 call("go2_linear_forward_tc", ptr(src), lds, ptr(W), ldw, ptr(self.b[l]), ptr(dst), ldd, ptr(dstT), lddT, M, self.dims[l + 1],
-                     self.dims[l], 0 if last else 1)
+                     self.dims[l], act)
             else:
                 call("go2_linear_forward_simt", ptr(src), lds, ptr(self.W[l]), self.dims[l], ptr(self.b[l]), ptr(dst), ldd, 0, 0, M,
-                     self.dims[l + 1], self.dims[l], 0 if last else 1)
+                     self.dims[l + 1], self.dims[l], act)
             src, lds = dst, ldd
         self._M, self._Xt, self._ldxt = M, Xt, ldxt
-        self._Xin, self._ldxin = (self._xpad, self.kpad0) if (self.tc and (ldx % 4 or X.data_ptr() % 16)) else (X, ldx)
 
     def backward(self, dY, lddy, dYt=None, lddyt=0):
         """Overwrites gW/gb with d loss / d params for the rows of the last forward(train=True).
-        dY [M, out] row-major; dYt [out, M] its transpose (tensor-core wgrad); both are produced by the loss kernel."""
+        dY [M, out] = gradient w.r.t. the LAST LINEAR's output (for last_act engines the caller has already applied ELU');
+        dYt [out, M] its transpose (tensor-core wgrad).  With need_dx the gradient w.r.t. the input lands in self.dx [M, pad4(in)]."""
         M = self._M
         d, ldd, dT, lddT = dY, lddy, dYt, lddyt
         for l in range(self.L - 1, -1, -1):
@@ -159,3 +186,8 @@ class MlpEngine:
                     call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,
                          ptr(nxtT), self.train_rows if nxtT is not None else 0, M, n_out, n_in)
                 d, ldd, dT, lddT = nxt, n_in, nxtT, self.train_rows
+            elif self.need_dx:
+                if self.tc and n_out % 4 == 0:
+                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[0]), self.Wt[0].shape[1], 0, 0, 0, 0, ptr(self.dx), self.kpad0, 0, 0, M, n_out, n_in)
+                else:
+                    call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[0]), n_in, 0, 0, ptr(self.dx), self.kpad0, 0, 0, M, n_out, n_in)

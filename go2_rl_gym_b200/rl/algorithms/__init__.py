@@ -1,1 +1,2 @@
 from .ppo import PPO
+from .cts import CTS, MoECTS

@@ -1,0 +1,285 @@
+"""CTS and MoECTS — Concurrent Teacher-Student PPO (drop-ins for rsl_rl/algorithms/cts.py:39-285 and moe_cts.py:40-234).
+
+Same constructor arguments and methods.  75 % of the envs (i % 4 != 0) act through the TEACHER encoder (privileged obs), the rest
+through the STUDENT encoder (5-frame observation history, evaluated without gradient in pass 1); transitions are stored teacher
+first.  update(): pass 1 = PPO on [latent | obs] with optimizer 1 (teacher encoder + critic + actor + std, KL-adaptive LR);
+pass 2 = latent reconstruction (+ MoE load balance) on the student rows with optimizer 2.  Everything runs on the library's
+kernels; the two Adam states are two contiguous segments of one flat vector."""
+import os
+
+import torch
+import torch.distributed as dist
+
+from .. import _ops, dist_utils
+from .._ops import call, ptr
+from ..storage.rollout_storage_cts import RolloutStorageCTS
+
+
+class CTS:
+    def __init__(self, model, num_envs, history_length, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, student_encoder_learning_rate=1e-3, max_grad_norm=1.0,
+                 use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, teacher_env_ratio=0.75, device='cpu', load_balance_coef=0.0,
+                 seed=0, env_offset=0):
+        self.device = device
+        self.desired_kl, self.schedule, self.learning_rate = desired_kl, schedule, learning_rate
+        self.student_encoder_learning_rate = student_encoder_learning_rate
+        self.history_length = history_length
+        self.model = model
+        self.storage = None
+        self.transition = RolloutStorageCTS.Transition()
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef, self.load_balance_coef = value_loss_coef, entropy_coef, load_balance_coef
+        self.gamma, self.lam, self.max_grad_norm, self.use_clipped_value_loss = gamma, lam, max_grad_norm, use_clipped_value_loss
+        self.teacher_num_envs = max(int(num_envs * teacher_env_ratio), 1)
+        self.student_num_envs = num_envs - self.teacher_num_envs
+        student_env_ratio = 1 - teacher_env_ratio
+        k = int(1 / student_env_ratio)
+        # global env ids decide the role (cts.py:93-97), so a shard of a multi-GPU run keeps the single-process assignment
+        ids = torch.arange(num_envs)
+        gids = ids + env_offset
+        self.teacher_env_idxs = ids[gids % k != 0].to(device)
+        self.student_env_idxs = ids[gids % k == 0].to(device)
+        assert len(self.teacher_env_idxs) == self.teacher_num_envs, f"{len(self.teacher_env_idxs)=} != {self.teacher_num_envs=}"
+        assert len(self.student_env_idxs) == self.student_num_envs, f"{len(self.student_env_idxs)=} != {self.student_num_envs=}"
+        self.perm = torch.cat([self.teacher_env_idxs, self.student_env_idxs]).contiguous()           # storage row -> env
+        self.inv_perm = torch.empty_like(self.perm)
+        self.inv_perm[self.perm] = torch.arange(num_envs, device=device)                             # env -> storage row
+        self.seed, self.env_offset = int(seed), int(env_offset)
+        self._act_step = 0
+        self.world_size = dist_utils.world_size()
+        self.optimizer1 = self.optimizer2 = None
+
+    # ---- set-up ------------------------------------------------------------------------------------------------------
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        dev, T = self.device, num_transitions_per_env
+        self.storage = RolloutStorageCTS(num_envs, self.teacher_num_envs, self.history_length, T, actor_obs_shape, critic_obs_shape, action_shape, dev)
+        nb = self.num_mini_batches
+        self.tm, self.sm = self.teacher_num_envs * T // nb, self.student_num_envs * T // nb
+        self.mb = self.tm + self.sm
+        m = self.model
+        m.flatten_(dev, max(num_envs, self.mb), self.mb, self.tm, self.sm)
+        A, D, N = action_shape[0], m.latent_dim, num_envs
+        z = lambda *s: torch.zeros(*s, device=dev)
+        self.exp_avg, self.exp_avg_sq = z(m.flat_params.numel()), z(m.flat_params.numel())
+        self._lr1, self._lr2 = z(4), z(4)
+        self._lr1[0], self._lr2[0] = float(self.learning_rate), float(self.student_encoder_learning_rate)
+        self._scal, self._log, self._log2 = z(20), z(5), z(2)
+        self._scratch, self._acc = z(1025), z(1)
+        rows = max(N, self.mb)
+        self._lat = z(rows, D)
+        self._lat_t = z(max(self.sm, 1), D)          # teacher latents of the student rows (pass 2 target)
+        self._xa = z(rows, (D + actor_obs_shape[0] + 3) // 4 * 4)
+        self._xc = z(rows, (D + critic_obs_shape[0] + 3) // 4 * 4)
+        self._xa_t = torch.ones(D + actor_obs_shape[0] + 1, self.mb, device=dev)
+        self._xc_t = torch.ones(D + critic_obs_shape[0] + 1, self.mb, device=dev)
+        self._mu, self._val = z(rows, A), z(rows, 1)
+        self._dmu, self._dmu_t, self._dval = z(self.mb, A), z(A, self.mb), z(self.mb + 4, 1)[:self.mb]
+        self._dlat = z(self.mb, D)
+        self._dls = z(max(self.sm, 1), D)
+        self._last_values = z(N, 1)
+        self._hist_p = z(N, self.history_length * actor_obs_shape[0])
+        self._rew_p, self._actions_env = z(N), z(N, A)
+        self._graph, self._graph_warm = None, 0
+
+    def test_mode(self):
+        self.model.eval()
+
+    def train_mode(self):
+        self.model.train()
+
+    # ---- shared forward pieces -----------------------------------------------------------------------------------------
+    def _latents(self, priv, hist, n_t, n_s, train_teacher=False, priv_t=None, ld_t=0):
+        """self._lat[0:n_t] = teacher latent of the first n_t rows, self._lat[n_t:n_t+n_s] = student latent of the rest (no grad)."""
+        m = self.model
+        if n_t:
+            m.teacher_latent(priv[:n_t], n_t, self._lat[:n_t], train=train_teacher, Xt=priv_t, ldxt=ld_t)
+        if n_s:
+            m.student.forward(hist[n_t:n_t + n_s], n_s, self._lat[n_t:n_t + n_s])
+
+    def _heads(self, obs, priv, M, train=False):
+        m, D = self.model, self.model.latent_dim
+        tc = _ops.use_tc()
+        xa_t = self._xa_t if (train and tc) else None
+        xc_t = self._xc_t if (train and tc) else None
+        call("go2_concat2", ptr(self._lat), D, D, ptr(obs), m.num_obs, obs.stride(0), ptr(self._xa), self._xa.shape[1], ptr(xa_t), M)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(priv), m.num_critic_obs, priv.stride(0), ptr(self._xc), self._xc.shape[1], ptr(xc_t), M)
+        m.actor_engine.forward(self._xa, self._xa.shape[1], M, self._mu[:M], m.num_actions, train=train, Xt=xa_t, ldxt=M)
+        m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, Xt=xc_t, ldxt=M)
+
+    # ---- rollout -------------------------------------------------------------------------------------------------------
+    def act(self, obs, privileged_obs, history):
+        st, t, m = self.storage, self.storage.step, self.model
+        if t >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        N, A = st.num_envs, st.actions.shape[-1]
+        gather = lambda src, w, dst: call("go2_gather_rows", ptr(src.contiguous()), w, ptr(self.perm), ptr(dst), w, 0, N)
+        gather(obs, obs.shape[1], st.observations[t])
+        gather(privileged_obs, privileged_obs.shape[1], st.privileged_observations[t])
+        gather(history, history.shape[1], st.history[t])
+        nt, ns = self.teacher_num_envs, self.student_num_envs
+        self._latents(st.privileged_observations[t], st.history[t], nt, ns)
+        self._heads(st.observations[t], st.privileged_observations[t], N)
+        st.values[t].copy_(self._val[:N])
+        self._act_step += 1
+        call("go2_sample_actions", ptr(self._mu), ptr(m.std.data), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
+             N, A, self.seed, self._act_step, self.env_offset)
+        call("go2_gather_rows", ptr(st.actions[t]), A, ptr(self.inv_perm), ptr(self._actions_env), A, 0, N)   # back to env order
+        return self._actions_env
+
+    def process_env_step(self, rewards, dones, infos):
+        st, t = self.storage, self.storage.step
+        tout = infos.get('time_outs') if isinstance(infos, dict) else None
+        d8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8)
+        t8 = None if tout is None else (tout.view(torch.uint8) if tout.dtype == torch.bool else tout.to(torch.uint8))
+        call("go2_process_env_step", ptr(rewards), ptr(d8), ptr(t8), ptr(st.values[t]), ptr(st.rewards[t]), ptr(st.dones[t]), st.num_envs, self.gamma,
+             ptr(self.perm))
+        st.step += 1
+        self.transition.clear()
+        self.model.reset(dones)
+
+    def compute_returns(self, last_privileged_obs, last_history):
+        N = self.storage.num_envs
+        call("go2_gather_rows", ptr(last_privileged_obs.contiguous()), last_privileged_obs.shape[1], ptr(self.perm), ptr(self._xc_p(N)), last_privileged_obs.shape[1], 0, N)
+        call("go2_gather_rows", ptr(last_history.contiguous()), last_history.shape[1], ptr(self.perm), ptr(self._hist_p), last_history.shape[1], 0, N)
+        priv_p = self._xc_p(N)
+        self._latents(priv_p, self._hist_p, self.teacher_num_envs, self.student_num_envs)
+        D, m = self.model.latent_dim, self.model
+        call("go2_concat2", ptr(self._lat), D, D, ptr(priv_p), m.num_critic_obs, priv_p.stride(0), ptr(self._xc), self._xc.shape[1], 0, N)
+        m.critic_engine.forward(self._xc, self._xc.shape[1], N, self._last_values, 1)
+        self.storage.compute_returns(self._last_values, self.gamma, self.lam,
+                                     reduce_stats=(lambda s: dist_utils.allreduce_adv_stats(s, N * self.storage.num_transitions_per_env)) if self.world_size > 1 else None)
+
+    def _xc_p(self, N):
+        if not hasattr(self, "_priv_p"):
+            self._priv_p = torch.zeros(N, self.model.num_critic_obs, device=self.device)
+        return self._priv_p
+
+    # ---- update --------------------------------------------------------------------------------------------------------
+    def update(self, teacher_perm=None, student_perm=None):
+        st, m = self.storage, self.model
+        idx, tm, sm = st.batch_indices(self.num_mini_batches, teacher_perm, student_perm)
+        tc = _ops.use_tc()
+        pads = {"critic_obs": (m.num_critic_obs + 3) // 4 * 4, "history": (st.history.shape[-1] + 3) // 4 * 4} if tc else {}
+        self._sh = st.shuffled(idx, pads, transposed=("critic_obs", "history") if tc else ())
+        self._total = idx.numel()
+        self._log.zero_(); self._log2.zero_()
+        use_graph = self.world_size == 1 and os.environ.get("GO2_GRAPH", "1") != "0"
+        if not use_graph:
+            self._update_body()
+        elif self._graph is None and self._graph_warm < 1:
+            self._update_body()
+            self._graph_warm += 1
+        elif self._graph is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._update_body()
+            self._graph = g
+            g.replay()
+        else:
+            self._graph.replay()
+        m.mark_dirty()
+        n = self.num_learning_epochs * self.num_mini_batches
+        log, log2 = self._log.tolist(), self._log2.tolist()      # the single host sync of update()
+        self.learning_rate = log[3]
+        st.clear()
+        out = (log[0] / n, log[1] / n, log[4] / n, log2[0] / n)
+        return out + (log2[1] / n,) if self._moe else out
+
+    _moe = False
+
+    def _update_body(self):
+        st, m, sh, total = self.storage, self.model, self._sh, self._total
+        tm, sm, mb, A, D = self.tm, self.sm, self.mb, st.actions.shape[-1], m.latent_dim
+        tc = _ops.use_tc()
+        adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
+        ws = self.world_size
+        n1, n2 = m.n1, m.n2
+        P, G = m.flat_params, m.flat_grads
+        # ---------------- pass 1: PPO on teacher + student rows, optimizer 1 (moe_cts.py:114-195)
+        for epoch in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                s = slice(i * mb, (i + 1) * mb)
+                obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
+                priv_t = sh["critic_obs_t"][:, i * mb:i * mb + tm] if tc else None
+                self._latents(priv_b, hist_b, tm, sm, train_teacher=True, priv_t=priv_t, ld_t=total)
+                self._heads(obs_b, priv_b, mb, train=True)
+                call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
+                     ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
+                     ptr(self._dmu_t) if tc else 0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+                     int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
+                m.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
+                m.critic_engine.backward(self._dval, 1, self._dval if tc else None, mb)
+                # d loss / d latent = first D columns of the actor's input gradient, teacher rows only (student latents carry no grad)
+                m.teacher_backward(m.actor_engine.dx, m.actor_engine.kpad0, self._lat, D, tm)
+                m._gviews["std"].copy_(self._scal[4:4 + A])
+                if ws > 1:
+                    self._comm1 = dist_utils.allreduce_grads_and_tail(G[:n1], self._scal, getattr(self, "_comm1", None))
+                call("go2_kl_adaptive_lr", ptr(self._scal), float(mb * ws), float(self.desired_kl) if adaptive else -1.0, ptr(self._lr1), ptr(self._log),
+                     float(tm * ws), float(max(sm, 1) * ws))
+                call("go2_adam_clip_step", ptr(P), ptr(G), ptr(self.exp_avg), ptr(self.exp_avg_sq), n1, self.max_grad_norm, ptr(self._lr1), 1.0,
+                     ptr(self._scratch))
+                for e in (m.teacher_engine, m.actor_engine, m.critic_engine):
+                    e.mark_dirty()
+        # ---------------- pass 2: student encoder towards the (updated) teacher latent, optimizer 2 (moe_cts.py:197-224)
+        if sm == 0:
+            return
+        for epoch in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                s = slice(i * mb + tm, (i + 1) * mb)
+                priv_b, hist_b = sh["critic_obs"][s], sh["history"][s]
+                hist_t = sh["history_t"][:, i * mb + tm:(i + 1) * mb] if tc else None
+                m.teacher_latent(priv_b, sm, self._lat_t)
+                m.student.forward(hist_b, sm, self._lat[:sm], train=True, Xt=hist_t, ldxt=total)
+                call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t), ptr(self._dls), ptr(self._acc), sm, D)
+                m.student.backward(self._dls, self.load_balance_coef)
+                call("go2_cts_log", ptr(self._acc), ptr(m.student.usage) if self._moe else 0, ptr(self._log2), sm * D, m.student.E if self._moe else 1)
+                if ws > 1:
+                    dist.all_reduce(G[n1:])
+                    G[n1:].div_(ws)
+                call("go2_adam_clip_step", ptr(P) + 4 * n1, ptr(G) + 4 * n1, ptr(self.exp_avg) + 4 * n1, ptr(self.exp_avg_sq) + 4 * n1, n2,
+                     self.max_grad_norm, ptr(self._lr2), 1.0, ptr(self._scratch))
+                for e in m.student.engines():
+                    e.mark_dirty()
+                m.student.mark_dirty()
+
+    # ---- checkpoint interop (two torch.optim.Adam state dicts, on_policy_runner_cts.py:287-294) --------------------------
+    def _opt_state(self, names, lr, lr_state):
+        named = dict(self.model.named_parameters())
+        state = {}
+        for i, k in enumerate(names):
+            p = named[k]
+            n, off = p.numel(), self.model._offsets[k]
+            state[i] = {"step": lr_state[1].detach().cpu().clone(), "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def optimizer1_state_dict(self):
+        return self._opt_state(self.model.seg1_names, self.learning_rate, self._lr1)
+
+    def optimizer2_state_dict(self):
+        return self._opt_state(self.model.seg2_names, self.student_encoder_learning_rate, self._lr2)
+
+    def load_optimizer_state_dicts(self, sd1, sd2):
+        named = dict(self.model.named_parameters())
+        for sd, names, lrs in ((sd1, self.model.seg1_names, self._lr1), (sd2, self.model.seg2_names, self._lr2)):
+            if sd is None:
+                continue
+            for i, k in enumerate(names):
+                n, off = named[k].numel(), self.model._offsets[k]
+                s = sd["state"].get(i)
+                if s is not None:
+                    self.exp_avg[off:off + n].copy_(s["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
+                    lrs[1] = float(s["step"])
+            if sd.get("param_groups"):
+                lrs[0] = float(sd["param_groups"][0]["lr"])
+        self.learning_rate = float(self._lr1[0])
+
+
+class MoECTS(CTS):
+    _moe = True
+
+    def __init__(self, model, num_envs, history_length, load_balance_coef=0.01, **kwargs):
+        super().__init__(model, num_envs, history_length, load_balance_coef=load_balance_coef, **kwargs)

@@ -59,7 +59,7 @@ class PPO:
         self._graph = None
         self._graph_warm = 0
         self._scal = torch.zeros(20, device=dev)
-        self._log = torch.zeros(4, device=dev)
+        self._log = torch.zeros(5, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
         self._dmu = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
         self._dmu_t = torch.empty(action_shape[0], self.mini_batch_size, device=dev)
@@ -99,7 +99,7 @@ class PPO:
         d8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8)
         t8 = None if tout is None else (tout.view(torch.uint8) if tout.dtype == torch.bool else tout.to(torch.uint8))
         _ops.call("go2_process_env_step", _ops.ptr(rewards), _ops.ptr(d8), _ops.ptr(t8), _ops.ptr(st.values[t]), _ops.ptr(st.rewards[t]),
-                  _ops.ptr(st.dones[t]), st.num_envs, self.gamma)
+                  _ops.ptr(st.dones[t]), st.num_envs, self.gamma, 0)
         st.step += 1
         self.transition.clear()
         self.actor_critic.reset(dones)
@@ -167,7 +167,7 @@ class PPO:
                           _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
                           _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0,
                           _ops.ptr(self._dval), _ops.ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
-                          int(self.use_clipped_value_loss), inv_count)
+                          int(self.use_clipped_value_loss), inv_count, mb, inv_count, inv_count)
                 ac.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
                 ac.critic_engine.backward(self._dval, 1, self._dval_t if tc else None, mb)
                 std_grad.copy_(self._scal[4:4 + A])
@@ -175,7 +175,7 @@ class PPO:
                     # one collective per optimiser step: flat gradient + the scalar tail (KL / loss sums) ride together
                     self._allreduce_grads()
                 _ops.call("go2_kl_adaptive_lr", _ops.ptr(self._scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
-                          _ops.ptr(self._lr), _ops.ptr(self._log))
+                          _ops.ptr(self._lr), _ops.ptr(self._log), float(mb * self.world_size), 1.0)
                 _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
                           ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), 1.0, _ops.ptr(self._scratch))
                 ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
@@ -185,27 +185,25 @@ class PPO:
 
     # ---- checkpoint interop (torch.optim.Adam layout, ppo.py:67) ---------------------------------------------
     def optimizer_state_dict(self):
-        state, off = {}, 0
-        for i, p in enumerate(self.actor_critic.parameters()):
-            k = p.numel()
+        state, offs = {}, self.actor_critic._offsets
+        for i, (name, p) in enumerate(self.actor_critic.named_parameters()):
+            k, off = p.numel(), offs[name]
             state[i] = {"step": torch.tensor(float(self._opt_step)), "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
-            off += k
         group = {"lr": self.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
                  "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(state)))}
         return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):
-        off = 0
-        for i, p in enumerate(self.actor_critic.parameters()):
-            k = p.numel()
+        offs = self.actor_critic._offsets
+        for i, (name, p) in enumerate(self.actor_critic.named_parameters()):
+            k, off = p.numel(), offs[name]
             s = sd["state"].get(i)
             if s is not None:
                 self.exp_avg[off:off + k].copy_(s["exp_avg"].reshape(-1))
                 self.exp_avg_sq[off:off + k].copy_(s["exp_avg_sq"].reshape(-1))
                 self._opt_step = int(float(s["step"]))
                 self._lr[1] = float(self._opt_step)
-            off += k
         if sd.get("param_groups"):
             self.learning_rate = float(sd["param_groups"][0]["lr"])
             self._lr[0] = self.learning_rate

@@ -43,19 +43,19 @@ class ActorCritic(nn.Module):
     # ---- flat parameter storage ------------------------------------------------------------------------------
     def flatten_(self, device, max_rows, train_rows=0):
         """Move to `device`, re-home every parameter inside one flat vector (parameters() order: std, actor.*, critic.*)."""
-        params = list(self.parameters())
-        n = sum(p.numel() for p in params)
-        flat = torch.empty(n, device=device, dtype=torch.float32)
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.parameters())     # every parameter starts 16-byte aligned (TMA operand rule)
+        flat = torch.zeros(n, device=device, dtype=torch.float32)
         grad = torch.zeros(n, device=device, dtype=torch.float32)
         off = 0
-        self._views, self._gviews = {}, {}
+        self._views, self._gviews, self._offsets = {}, {}, {}
         for name, p in self.named_parameters():
             k = p.numel()
+            self._offsets[name] = off
             flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = flat[off:off + k].view(p.shape)
             self._views[name] = p.data
             self._gviews[name] = grad[off:off + k].view(p.shape)
-            off += k
+            off += (k + 3) // 4 * 4
         self._flat, self._grad = flat, grad
         self.device = torch.device(device)
 

@@ -1,0 +1,362 @@
+"""ActorCriticCTS / ActorCriticMoECTS (drop-ins for rsl_rl/modules/actor_critic_cts.py:18-160 and
+actor_critic_moe_cts.py:20-141 + modules/utils.py:24-151).
+
+Same constructor arguments and `state_dict` keys (teacher_encoder.*, student_encoder.* / student_moe_encoder.moe.*,
+actor.*, critic.*, std), parameters re-homed in ONE flat vector split into two contiguous optimiser segments:
+  segment 1 (optimizer1, cts.py:72-79): teacher_encoder, critic, actor, std        segment 2 (optimizer2): the student encoder
+and every forward / backward evaluated by the library's kernels (GEMMs on tcgen05, the small pieces in csrc/cts_kernels.cu)."""
+import torch
+import torch.nn as nn
+
+from .. import _ops
+from .._ops import call, ptr
+
+
+class MLP(nn.Module):  # parameter container with the reference's key layout (modules/utils.py:51-67)
+    def __init__(self, dims, last_activation=False):
+        super().__init__()
+        layers = []
+        for i in range(len(dims) - 1):
+            layers.append(nn.Linear(dims[i], dims[i + 1]))
+            if i < len(dims) - 2 or last_activation:
+                layers.append(nn.ELU())
+        self.network = nn.Sequential(*layers)
+        self.dims, self.last_activation = list(dims), last_activation
+
+    def forward(self, x):
+        return self.network(x)
+
+
+class L2Norm(nn.Module):
+    def forward(self, x):
+        return torch.nn.functional.normalize(x, p=2.0, dim=-1)
+
+
+class Experts(nn.Module):
+    def __init__(self, expert_num, input_dim, backbone_hidden_dims, expert_hidden_dim, output_dim):
+        super().__init__()
+        self.expert_num, self.output_dim = expert_num, output_dim
+        self.backbone = MLP([input_dim, *backbone_hidden_dims, expert_num * expert_hidden_dim], last_activation=True)
+        self.experts = nn.Conv1d(expert_num * expert_hidden_dim, expert_num * output_dim, kernel_size=1, groups=expert_num)
+
+
+class MoE(nn.Module):
+    def __init__(self, expert_num, input_dim, hidden_dims, output_dim):
+        super().__init__()
+        self.experts = Experts(expert_num, input_dim, hidden_dims[:-1], hidden_dims[-1], output_dim)
+        self.gating_network = nn.Sequential(MLP([input_dim, *hidden_dims[:-1], expert_num]), nn.Softmax(dim=-1))
+
+
+class StudentMoEEncoder(nn.Module):
+    def __init__(self, expert_num, input_dim, hidden_dims, output_dim):
+        super().__init__()
+        self.norm_layer = L2Norm()
+        self.moe = MoE(expert_num, input_dim, hidden_dims, output_dim)
+
+
+def _seq_mlp(dims):  # ActorCriticCTS keeps plain nn.Sequential keys (actor_critic_cts.py:51-104)
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers.append(nn.ELU())
+    return layers
+
+
+def _linear_names(prefix, n_layers):
+    return [f"{prefix}.{2 * i}" for i in range(n_layers)]
+
+
+class _CTSBase(nn.Module):
+    is_recurrent = False
+
+    # ---- flat storage ---------------------------------------------------------------------------------------------
+    def _segments(self):
+        raise NotImplementedError
+
+    def flatten_(self, device, max_rows, train_rows_1, train_rows_t, train_rows_s):
+        """train_rows_1: mini-batch rows of pass 1; _t / _s: its teacher / student parts."""
+        seg1, seg2 = self._segments()
+        named = dict(self.named_parameters())
+        n1 = sum((named[k].numel() + 3) // 4 * 4 for k in seg1)     # every parameter starts 16-byte aligned (TMA operand rule);
+        n2 = sum((named[k].numel() + 3) // 4 * 4 for k in seg2)     # the padding stays zero (zero gradient -> Adam leaves it at zero)
+        flat = torch.zeros(n1 + n2, device=device)
+        grad = torch.zeros(n1 + n2, device=device)
+        self._views, self._gviews, self._offsets, off = {}, {}, {}, 0
+        for k in seg1 + seg2:
+            p = named[k]
+            n = p.numel()
+            self._offsets[k] = off
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            self._views[k] = p.data
+            self._gviews[k] = grad[off:off + n].view(p.shape)
+            off += (n + 3) // 4 * 4
+        self._flat, self._grad, self.n1, self.n2 = flat, grad, n1, n2
+        self.seg1_names, self.seg2_names = seg1, seg2
+        self.device = torch.device(device)
+        self.history = self.history.to(device)
+        self._build_engines(device, max_rows, train_rows_1, train_rows_t, train_rows_s)
+        return self
+
+    def _engine(self, names, dims, max_rows, train_rows, **kw):
+        W = [self._views[n + ".weight"] for n in names]
+        b = [self._views[n + ".bias"] for n in names]
+        gW = [self._gviews[n + ".weight"] for n in names]
+        gb = [self._gviews[n + ".bias"] for n in names]
+        return _ops.MlpEngine(dims, W, b, gW, gb, max_rows, self.device, train_rows=train_rows, **kw)
+
+    @property
+    def flat_params(self):
+        return self._flat
+
+    @property
+    def flat_grads(self):
+        return self._grad
+
+    def engines(self):
+        return [self.teacher_engine, self.actor_engine, self.critic_engine] + self.student.engines()
+
+    def mark_dirty(self):
+        for e in self.engines():
+            e.mark_dirty()
+        self.student.mark_dirty()
+
+    def load_state_dict(self, state_dict, strict=True):
+        if getattr(self, "_flat", None) is None:
+            return super().load_state_dict(state_dict, strict)
+        own = dict(self.named_parameters())
+        missing = [k for k in own if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in own]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing}, unexpected {unexpected}")
+        with torch.no_grad():
+            for k, p in own.items():
+                if k in state_dict:
+                    p.data.copy_(state_dict[k].to(p.device))
+        self.mark_dirty()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    # ---- reference API --------------------------------------------------------------------------------------------
+    def reset(self, dones=None):
+        if dones is not None:
+            self.history[dones > 0] = 0.0
+
+    def forward(self):
+        raise NotImplementedError
+
+    def teacher_latent(self, priv, M, out, train=False, Xt=None, ldxt=0):
+        """out[M, latent] = L2Norm(teacher_encoder(priv))  (actor_critic_moe_cts.py:116-117)"""
+        e = self.teacher_engine
+        e.forward(priv, priv.shape[1] if priv.dim() == 2 else 0, M, self._t_pre[:M], self.latent_dim, train=train, Xt=Xt, ldxt=ldxt)
+        call("go2_l2norm_forward", ptr(self._t_pre), self.latent_dim, ptr(out), out.stride(0), ptr(self._t_norm), M, self.latent_dim)
+
+    def teacher_backward(self, dlatent, lddl, latent, ldl, M):
+        call("go2_l2norm_backward", ptr(dlatent), lddl, ptr(latent), ldl, ptr(self._t_norm), ptr(self._t_dpre), self.latent_dim,
+             ptr(self._t_dpre_t) if self._t_dpre_t is not None else 0, M, self.latent_dim)
+        # the transposed copy is written with row pitch M (the rows of this call)
+        self.teacher_engine.backward(self._t_dpre, self.latent_dim, self._t_dpre_t, M)
+
+    def act_inference(self, obs):
+        """Student policy (actor_critic_moe_cts.py:127-132): roll the history, encode it, act on [latent | obs]."""
+        N = obs.shape[0]
+        call("go2_history_update", ptr(self.history), ptr(obs.contiguous()), 0, N, self.history_length, self.num_obs)
+        lat = self._inf_lat[:N]
+        self.student.forward(self.history.view(N, -1), N, lat)
+        xa = self._inf_xa[:N]
+        call("go2_concat2", ptr(lat), self.latent_dim, self.latent_dim, ptr(obs), self.num_obs, obs.shape[1], ptr(xa), xa.shape[1], 0, N)
+        out = self._inf_mu[:N]
+        self.actor_engine.forward(xa, xa.shape[1], N, out, self.num_actions)
+        return out.clone()
+
+
+class _StudentMLP:
+    """Plain student encoder: MLP + L2Norm (actor_critic_cts.py:73-89)."""
+
+    def __init__(self, model, names, dims, max_rows, train_rows):
+        self.m, self.D = model, dims[-1]
+        self.engine = model._engine(names, dims, max_rows, train_rows)
+        dev = model.device
+        self.pre = torch.empty(max_rows, self.D, device=dev)
+        self.norm = torch.empty(max_rows, device=dev)
+        self.dpre = torch.empty(max(train_rows, 1), self.D, device=dev)
+        self.dpre_t = torch.empty(self.D, max(train_rows, 1), device=dev) if _ops.use_tc() else None
+
+    def engines(self):
+        return [self.engine]
+
+    def mark_dirty(self):
+        pass
+
+    def forward(self, hist, M, out, train=False, Xt=None, ldxt=0):
+        self.engine.forward(hist, hist.shape[1], M, self.pre[:M], self.D, train=train, Xt=Xt, ldxt=ldxt)
+        call("go2_l2norm_forward", ptr(self.pre), self.D, ptr(out), out.stride(0), ptr(self.norm), M, self.D)
+        self._out, self._M = out, M
+
+    def backward(self, dlatent, lb_coef=0.0):
+        M = self._M
+        call("go2_l2norm_backward", ptr(dlatent), self.D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), self.D,
+             ptr(self.dpre_t), M, self.D)
+        self.engine.backward(self.dpre, self.D, self.dpre_t, M)
+        return None
+
+
+class _StudentMoE:
+    """StudentMoEEncoder (modules/utils.py:69-151): shared backbone -> 8 block-diagonal experts, softmax gate, weighted sum, L2Norm."""
+
+    def __init__(self, model, prefix, in_dim, hidden_dims, E, D, max_rows, train_rows):
+        self.m, self.E, self.D, self.H = model, E, D, hidden_dims[-1]
+        dev = model.device
+        bdims = [in_dim, *hidden_dims[:-1], E * self.H]
+        gdims = [in_dim, *hidden_dims[:-1], E]
+        nb = len(bdims) - 1
+        self.backbone = model._engine(_linear_names(prefix + ".moe.experts.backbone.network", nb), bdims, max_rows, train_rows, last_act=True)
+        self.gate = model._engine(_linear_names(prefix + ".moe.gating_network.0.network", len(gdims) - 1), gdims, max_rows, train_rows)
+        self.We = model._views[prefix + ".moe.experts.experts.weight"].view(E * D, self.H)     # Conv1d [E*D, H, 1] -> E blocks of [D, H]
+        self.be = model._views[prefix + ".moe.experts.experts.bias"]
+        self.gWe = model._gviews[prefix + ".moe.experts.experts.weight"].view(E * D, self.H)
+        self.gbe = model._gviews[prefix + ".moe.experts.experts.bias"]
+        tr = max(train_rows, 1)
+        z = lambda *s: torch.empty(*s, device=dev)
+        self.eo, self.logits, self.gates = z(max_rows, E * D), z(max_rows, E), z(max_rows, E)
+        self.pre, self.norm = z(max_rows, D), z(max_rows)
+        self.dpre, self.deo, self.deo_t = z(tr, D), z(tr, E * D), z(E * D, tr)
+        self.dlogits, self.dlogits_t = z(tr, E), z(E, tr)
+        self.dfeat, self.dfeat_t = z(tr, E * self.H), z(E * self.H, tr)
+        self.usage = torch.zeros(E, device=dev)
+        self.Wet = torch.zeros(E * self.H, D, device=dev)   # per expert W_e^T [H, D], stacked
+        self.work = torch.empty(64 * D * (self.H + 4), device=dev)
+        self._dirty = True
+        self.train_rows = train_rows
+
+    def engines(self):
+        return [self.backbone, self.gate]
+
+    def mark_dirty(self):
+        self._dirty = True
+
+    def forward(self, hist, M, out, train=False, Xt=None, ldxt=0):
+        E, D, H = self.E, self.D, self.H
+        self.backbone.forward(hist, hist.shape[1], M, train=train, Xt=Xt, ldxt=ldxt)
+        feat = self.backbone.out
+        for e in range(E):  # block-diagonal expert layer = Conv1d(groups=E, kernel 1)
+            fn = "go2_linear_forward_tc" if _ops.use_tc() else "go2_linear_forward_simt"
+            call(fn, ptr(feat) + 4 * e * H, E * H, ptr(self.We) + 4 * e * D * H, H, ptr(self.be) + 4 * e * D, ptr(self.eo) + 4 * e * D, E * D, 0, 0,
+                 M, D, H, 0)
+        self.gate.forward(hist, hist.shape[1], M, self.logits[:M], E, train=train, Xt=Xt, ldxt=ldxt)
+        call("go2_moe_combine_forward", ptr(self.logits), ptr(self.eo), ptr(self.gates), ptr(self.pre), M, E, D)
+        call("go2_l2norm_forward", ptr(self.pre), D, ptr(out), out.stride(0), ptr(self.norm), M, D)
+        self._out, self._M = out, M
+
+    def backward(self, dlatent, lb_coef=0.0):
+        E, D, H, M, tr = self.E, self.D, self.H, self._M, self.train_rows
+        tc = _ops.use_tc()
+        call("go2_l2norm_backward", ptr(dlatent), D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), D, 0, M, D)
+        call("go2_moe_combine_backward", ptr(self.dpre), ptr(self.gates), ptr(self.eo), ptr(self.usage), float(lb_coef), ptr(self.deo),
+             ptr(self.deo_t) if tc else 0, ptr(self.dlogits), ptr(self.dlogits_t) if tc else 0, M, E, D)
+        # NOTE deo_t / dlogits_t are written with row pitch M by the kernel
+        if self._dirty and tc:
+            for e in range(E):
+                call("go2_transpose", ptr(self.We) + 4 * e * D * H, H, ptr(self.Wet) + 4 * e * H * D, D, D, H)
+            self._dirty = False
+        call("go2_colsum", ptr(self.deo), E * D, ptr(self.gbe), M, E * D, ptr(self.work))
+        feat, featT = self.backbone.out, self.backbone.outT if tc else None
+        for e in range(E):
+            if tc:
+                call("go2_linear_wgrad_tc", ptr(self.deo_t) + 4 * e * D * M, M, ptr(featT) + 4 * e * H * tr, tr, ptr(self.gWe) + 4 * e * D * H, H, 0,
+                     M, D, H, ptr(self.work), self.work.numel())
+                call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, 0, 0, ptr(featT) + 4 * e * H * tr, tr,
+                     ptr(self.dfeat) + 4 * e * H, E * H, ptr(self.dfeat_t) + 4 * e * H * tr, tr, M, D, H)
+            else:
+                call("go2_linear_wgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, E * H, ptr(self.gWe) + 4 * e * D * H, H, 0,
+                     M, D, H, ptr(self.work), self.work.numel())
+                call("go2_linear_dgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(self.We) + 4 * e * D * H, H, ptr(feat) + 4 * e * H, E * H,
+                     ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
+        self.backbone.backward(self.dfeat, E * H, self.dfeat_t if tc else None, tr)
+        self.gate.backward(self.dlogits, E, self.dlogits_t if tc else None, M)
+
+
+class ActorCriticMoECTS(_CTSBase):
+    def __init__(self, num_obs, num_critic_obs, num_actions, num_envs, history_length, actor_hidden_dims=[512, 256, 128],
+                 critic_hidden_dims=[512, 256, 128], teacher_encoder_hidden_dims=[512, 256], student_encoder_hidden_dims=[512, 256, 256],
+                 expert_num=8, activation='elu', init_noise_std=1.0, latent_dim=32, norm_type='l2norm', **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        if activation != 'elu' or norm_type != 'l2norm':
+            raise NotImplementedError("fused epilogues implement ELU / L2Norm (the go2_moe_cts configuration)")
+        super().__init__()
+        self.num_obs, self.num_critic_obs, self.num_actions = num_obs, num_critic_obs, num_actions
+        self.history_length, self.latent_dim, self.expert_num = history_length, latent_dim, expert_num
+        self.register_buffer("history", torch.zeros((num_envs, history_length, num_obs)), persistent=False)
+        self.t_dims = [num_critic_obs, *teacher_encoder_hidden_dims, latent_dim]
+        self.s_hidden = list(student_encoder_hidden_dims)
+        self.a_dims = [latent_dim + num_obs, *actor_hidden_dims, num_actions]
+        self.c_dims = [latent_dim + num_critic_obs, *critic_hidden_dims, 1]
+        self.teacher_encoder = nn.Sequential(MLP(self.t_dims), L2Norm())
+        self.student_moe_encoder = StudentMoEEncoder(expert_num, num_obs * history_length, self.s_hidden, latent_dim)
+        self.actor = MLP(self.a_dims)
+        self.critic = MLP(self.c_dims)
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        self.student_prefix = "student_moe_encoder"
+
+    def _segments(self):
+        names = [k for k, _ in self.named_parameters()]
+        seg1 = [k for k in names if k.startswith("teacher_encoder.")] + [k for k in names if k.startswith("critic.")] + \
+               [k for k in names if k.startswith("actor.")] + ["std"]
+        seg2 = [k for k in names if k.startswith("student_moe_encoder.")]
+        return seg1, seg2
+
+    def _build_engines(self, dev, max_rows, tr1, trt, trs):
+        self.teacher_engine = self._engine(_linear_names("teacher_encoder.0.network", len(self.t_dims) - 1), self.t_dims, max_rows, max(trt, trs))
+        self.actor_engine = self._engine(_linear_names("actor.network", len(self.a_dims) - 1), self.a_dims, max_rows, tr1, need_dx=True)
+        self.critic_engine = self._engine(_linear_names("critic.network", len(self.c_dims) - 1), self.c_dims, max_rows, tr1)
+        self.student = _StudentMoE(self, "student_moe_encoder", self.num_obs * self.history_length, self.s_hidden, self.expert_num, self.latent_dim,
+                                   max_rows, trs)
+        self._common_buffers(dev, max_rows, max(trt, trs))
+
+    def _common_buffers(self, dev, max_rows, trt):
+        D = self.latent_dim
+        self._t_pre = torch.empty(max_rows, D, device=dev)
+        self._t_norm = torch.empty(max_rows, device=dev)
+        self._t_dpre = torch.empty(max(trt, 1), D, device=dev)
+        self._t_dpre_t = torch.empty(D, max(trt, 1), device=dev) if _ops.use_tc() else None
+        self._inf_lat = torch.empty(max_rows, D, device=dev)
+        self._inf_xa = torch.zeros(max_rows, (self.a_dims[0] + 3) // 4 * 4, device=dev)
+        self._inf_mu = torch.empty(max_rows, self.num_actions, device=dev)
+
+
+class ActorCriticCTS(_CTSBase):
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, num_envs, history_length, actor_hidden_dims=[512, 256, 128],
+                 critic_hidden_dims=[512, 256, 128], teacher_encoder_hidden_dims=[512, 256], student_encoder_hidden_dims=[512, 256],
+                 activation='elu', init_noise_std=1.0, latent_dim=32, norm_type='l2norm', **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        if activation != 'elu' or norm_type != 'l2norm':
+            raise NotImplementedError("fused epilogues implement ELU / L2Norm (the go2_cts configuration)")
+        super().__init__()
+        self.num_obs, self.num_critic_obs, self.num_actions = num_actor_obs, num_critic_obs, num_actions
+        self.history_length, self.latent_dim = history_length, latent_dim
+        self.register_buffer("history", torch.zeros((num_envs, history_length, num_actor_obs)), persistent=False)
+        self.t_dims = [num_critic_obs, *teacher_encoder_hidden_dims, latent_dim]
+        self.s_dims = [num_actor_obs * history_length, *student_encoder_hidden_dims, latent_dim]
+        self.a_dims = [latent_dim + num_actor_obs, *actor_hidden_dims, num_actions]
+        self.c_dims = [latent_dim + num_critic_obs, *critic_hidden_dims, 1]
+        self.teacher_encoder = nn.Sequential(*_seq_mlp(self.t_dims), L2Norm())
+        self.student_encoder = nn.Sequential(*_seq_mlp(self.s_dims), L2Norm())
+        self.actor = nn.Sequential(*_seq_mlp(self.a_dims))
+        self.critic = nn.Sequential(*_seq_mlp(self.c_dims))
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+
+    def _segments(self):
+        names = [k for k, _ in self.named_parameters()]
+        seg1 = [k for k in names if k.startswith("teacher_encoder.")] + [k for k in names if k.startswith("critic.")] + \
+               [k for k in names if k.startswith("actor.")] + ["std"]
+        seg2 = [k for k in names if k.startswith("student_encoder.")]
+        return seg1, seg2
+
+    def _build_engines(self, dev, max_rows, tr1, trt, trs):
+        self.teacher_engine = self._engine(_linear_names("teacher_encoder", len(self.t_dims) - 1), self.t_dims, max_rows, max(trt, trs))
+        self.actor_engine = self._engine(_linear_names("actor", len(self.a_dims) - 1), self.a_dims, max_rows, tr1, need_dx=True)
+        self.critic_engine = self._engine(_linear_names("critic", len(self.c_dims) - 1), self.c_dims, max_rows, tr1)
+        self.student = _StudentMLP(self, _linear_names("student_encoder", len(self.s_dims) - 1), self.s_dims, max_rows, trs)
+        ActorCriticMoECTS._common_buffers(self, dev, max_rows, max(trt, trs))

@@ -204,7 +204,7 @@ int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratc
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */
 int go2_sample_actions(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A, uint64_t seed, uint32_t step, int env_offset, void* stream);
 /* PPO.process_env_step (ppo.py:104-111): rewards += gamma V time_out; rows of the transition */
-int go2_process_env_step(const float* rew, const uint8_t* dones, const uint8_t* time_outs, const float* values, float* rew_out, uint8_t* dones_out, int N, float gamma, void* stream);
+int go2_process_env_step(const float* rew, const uint8_t* dones, const uint8_t* time_outs, const float* values, float* rew_out, uint8_t* dones_out, int N, float gamma, const int64_t* perm, void* stream);
 /* RolloutStorage.compute_returns (rollout_storage.py:123-134), all [T,N]; stats[2] (double) receives sum / sum of squares of adv */
 int go2_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, float* returns, float* advantages, int T, int N, float gamma, float lam, double* stats, void* stream);
 /* advantages = (adv - mean) / (std + 1e-8) with the (possibly all-reduced) stats and global count (rollout_storage.py:136-137) */
@@ -212,15 +212,36 @@ int go2_adv_normalize(float* advantages, long n, const double* stats, double glo
 /* mini-batch gather (rollout_storage.py:173-181): dst[i, :width] = src[idx[i], :width] (idx NULL = identity), zero padded to ldd;
  * dst_t (optional) receives the transposed copy [width, n] */
 int go2_gather_rows(const float* src, int width, const int64_t* idx, float* dst, int ldd, float* dst_t, long n, void* stream);
-/* PPO losses forward + backward (ppo.py:131-171). scal[20]: sum KL, sum surrogate, sum value loss, sum entropy, d/d std[16] */
+/* PPO losses forward + backward (ppo.py:131-171). scal[20]: sum KL, sum surrogate (rows < split), sum value loss, sum entropy, d/d std[<=15],
+ * scal[19] = sum surrogate of rows >= split.  CTS: rows [0,split) are teacher samples weighted inv_count_a, the rest student samples weighted
+ * inv_count_b (cts.py / moe_cts.py:160-168); plain PPO passes split = M and inv_count_a = inv_count */
 int go2_ppo_loss(const float* mu, const float* std_param, const float* value, const float* actions, const float* old_logp, const float* adv,
                  const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dmu_t, float* dvalue,
-                 float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss, float inv_count, void* stream);
-/* KL-adaptive learning rate on the device (ppo.py:139-151); log_out[4] accumulates value/surrogate loss, holds kl, lr */
-int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* lr_state, float* log_out, void* stream);
+                 float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss, float inv_count,
+                 int split, float inv_count_a, float inv_count_b, void* stream);
+/* KL-adaptive learning rate on the device (ppo.py:139-151); log_out[5]: += value loss, += surrogate loss, = kl, = lr, += entropy */
+int go2_kl_adaptive_lr(const float* scal, float count, float desired_kl, float* lr_state, float* log_out, float count_a, float count_b, void* stream);
 /* clip_grad_norm_ + Adam.step on a flat parameter vector (ppo.py:176-177); lr_state[4] = {lr, step count, 1-beta1^t, sqrt(1-beta2^t)} lives on the
  * device (the call increments the step), scratch >= 1025 floats */
 int go2_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float max_grad_norm, float* lr_state, float grad_scale, float* scratch, void* stream);
+
+/* ---- Concurrent Teacher-Student / MoE pieces (csrc/cts_kernels.cu) ------------------------------------------------------ */
+/* out[i] = [a[i, :wa] | b[i, :wb]] zero padded to ld; out_t (optional) transposed copy   (actor_critic_moe_cts.py:121,140) */
+int go2_concat2(const float* a, int wa, int lda, const float* b, int wb, int ldb, float* out, int ld, float* out_t, long n, void* stream);
+/* L2Norm forward / backward (modules/utils.py:24-30) */
+int go2_l2norm_forward(const float* x, int ldx, float* y, int ldy, float* norm, long n, int d, void* stream);
+int go2_l2norm_backward(const float* dy, int lddy, const float* y, int ldy, const float* norm, float* dx, int lddx, float* dx_t, long n, int d, void* stream);
+/* softmax gate + weighted sum of the expert outputs (modules/utils.py:122-126) and its backward incl. the load-balance term (moe_cts.py:210-216) */
+int go2_moe_combine_forward(const float* logits, const float* expert_out, float* gates, float* pre, long n, int E, int D, void* stream);
+int go2_moe_combine_backward(const float* dpre, const float* gates, const float* expert_out, float* usage, float lb_coef, float* dexpert_out,
+                             float* dexpert_out_t, float* dlogits, float* dlogits_t, long n, int E, int D, void* stream);
+/* latent reconstruction loss mean((teacher - student)^2) and its gradient (moe_cts.py:205-207); acc[1] receives the sum of squares */
+int go2_latent_loss(const float* student, const float* teacher, float* dstudent, float* acc, long n, int d, void* stream);
+/* log[0] += latent loss, log[1] += load-balance loss from usage[E] (NULL -> 0) */
+int go2_cts_log(const float* acc, const float* usage, float* log, long count, int E, void* stream);
+/* rolling observation history [n, H, d]: zero on done, shift, append (on_policy_runner_cts.py:155-156) */
+int go2_history_update(float* history, const float* obs, const uint8_t* dones, long n, int H, int d, void* stream);
+int go2_gather_u8(const uint8_t* src, const int64_t* perm, uint8_t* out, long n, void* stream);
 
 #ifdef __cplusplus
 }

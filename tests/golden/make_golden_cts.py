@@ -1,0 +1,66 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/rl_moe_cts.npz from the REFERENCE's rsl_rl (ActorCriticMoECTS + MoECTS + RolloutStorageCTS, imported
+unmodified from /root/reference/rsl_rl): a seeded synthetic rollout through act / process_env_step / compute_returns and one
+update() with injected teacher / student permutations.  Build container only.  Usage: python tests/golden/make_golden_cts.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
+sys.path[:0] = ["/root/reference/rsl_rl", HERE]
+
+from rsl_rl.algorithms.moe_cts import MoECTS  # noqa: E402
+from rsl_rl.modules.actor_critic_moe_cts import ActorCriticMoECTS  # noqa: E402
+import rsl_rl.storage.rollout_storage_cts as RS  # noqa: E402
+from cts_cfg import ALG, POLICY  # noqa: E402
+
+
+def main():
+    torch.manual_seed(0)
+    N, T, H = 32, 24, 5
+    model = ActorCriticMoECTS(45, 263, 12, N, H, **POLICY)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    alg = MoECTS(model, N, H, device="cpu", **ALG)
+    alg.init_storage(N, T, [45], [263], [12])
+    g = torch.Generator().manual_seed(1)
+    obs = torch.randn(T + 1, N, 45, generator=g)
+    priv = torch.randn(T + 1, N, 263, generator=g)
+    hist = torch.randn(T + 1, N, H * 45, generator=g)
+    rew = 0.1 * torch.randn(T, N, generator=g)
+    dones = (torch.rand(T, N, generator=g) < 0.03)
+    touts = dones & (torch.rand(T, N, generator=g) < 0.5)
+    with torch.inference_mode():
+        for t in range(T):
+            alg.act(obs[t], priv[t], hist[t])
+            alg.process_env_step(rew[t], dones[t], {"time_outs": touts[t]})
+        alg.compute_returns(priv[T], hist[T])
+    st = alg.storage
+    save = {f"sd0_{k}": v.numpy() for k, v in sd0.items()}
+    for k in ("observations", "privileged_observations", "history", "actions", "rewards", "dones", "values", "returns", "advantages",
+              "actions_log_prob", "mu", "sigma"):
+        save["st_" + k] = getattr(st, k).clone().numpy()
+    save.update(in_obs=obs.numpy(), in_priv=priv.numpy(), in_hist=hist.numpy(), in_rew=rew.numpy(), in_dones=dones.numpy(), in_touts=touts.numpy())
+    nt, ns = alg.teacher_num_envs * T, alg.student_num_envs * T
+    tperm, sperm = torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)
+    save["tperm"], save["sperm"] = tperm.numpy(), sperm.numpy()
+    queue = [tperm.clone(), sperm.clone()]
+    orig = RS.torch.randperm
+    RS.torch.randperm = lambda n, **kw: queue.pop(0)
+    try:
+        losses = alg.update()
+    finally:
+        RS.torch.randperm = orig
+    for k, v in model.state_dict().items():
+        save[f"sd1_{k}"] = v.detach().clone().numpy()
+    save["losses"] = np.array(losses, dtype=np.float64)
+    save["lr"] = alg.learning_rate
+    path = os.path.join(HERE, "rl_moe_cts.npz")
+    np.savez_compressed(path, **save)
+    print("wrote", path, f"{os.path.getsize(path)/1024:.0f} KiB losses", losses, "lr", alg.learning_rate)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
-sys.path[:0] = [ROOT, HERE, "/root/reference/rsl_rl"]
+sys.path[:0] = ["/root/reference/rsl_rl", HERE]
 
 from rsl_rl.algorithms.ppo import PPO  # noqa: E402
 from rsl_rl.modules.actor_critic import ActorCritic  # noqa: E402

@@ -1,0 +1,87 @@
+"""GPU parity of the Concurrent Teacher-Student (MoE) trainer against the fixture made by the REFERENCE's rsl_rl
+(ActorCriticMoECTS + MoECTS + RolloutStorageCTS; tests/golden/make_golden_cts.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rl_moe_cts.npz"))
+
+
+def _t(k, dev="cuda"):
+    return torch.from_numpy(Z[k]).to(dev)
+
+
+def _make(gemm, monkeypatch):
+    monkeypatch.setenv("GO2_GEMM", gemm)
+    from golden.cts_cfg import ALG, POLICY
+    from go2_rl_gym_b200.rl.algorithms import MoECTS
+    from go2_rl_gym_b200.rl.modules import ActorCriticMoECTS
+    T, N = Z["st_rewards"].shape[:2]
+    model = ActorCriticMoECTS(45, 263, 12, N, 5, **POLICY)
+    model.load_state_dict({k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")})
+    alg = MoECTS(model, N, 5, device="cuda", **ALG)
+    alg.init_storage(N, T, [45], [263], [12])
+    return model, alg, T, N
+
+
+@pytest.mark.parametrize("gemm", ["simt", "tc"])
+def test_moe_cts_act_matches_reference(gemm, monkeypatch):
+    model, alg, T, N = _make(gemm, monkeypatch)
+    tol = 2e-5 if gemm == "simt" else 3e-3
+    a = alg.act(_t("in_obs")[0], _t("in_priv")[0], _t("in_hist")[0])
+    st = alg.storage
+    assert torch.allclose(st.mu[0].cpu(), torch.from_numpy(Z["st_mu"][0]), atol=tol)
+    assert torch.allclose(st.values[0].cpu(), torch.from_numpy(Z["st_values"][0]), atol=tol)
+    assert torch.equal(st.observations[0].cpu(), torch.from_numpy(Z["st_observations"][0]))       # teacher-first reordering
+    assert torch.equal(st.history[0].cpu(), torch.from_numpy(Z["st_history"][0]))
+    assert torch.equal(a[alg.perm], st.actions[0])                                                 # actions back in env order
+    alg.process_env_step(_t("in_rew")[0], _t("in_dones")[0], {"time_outs": _t("in_touts")[0]})
+    ti, si = alg.teacher_env_idxs.cpu(), alg.student_env_idxs.cpu()
+    assert torch.equal(st.dones[0].cpu().squeeze(-1).bool(), torch.cat([torch.from_numpy(Z["in_dones"][0])[ti], torch.from_numpy(Z["in_dones"][0])[si]]))
+
+
+@pytest.mark.parametrize("gemm", ["simt", "tc"])
+def test_moe_cts_update_matches_reference(gemm, monkeypatch):
+    """Both passes of MoECTS.update (moe_cts.py:104-234).  simt: parameters to 1e-3 rel / 3e-5 abs.  tc: relative error of the whole
+    update < 5 %, losses within 3e-3, same learning-rate path."""
+    model, alg, T, N = _make(gemm, monkeypatch)
+    st = alg.storage
+    for k in ("observations", "privileged_observations", "history", "actions", "rewards", "dones", "values", "returns", "advantages",
+              "actions_log_prob", "mu", "sigma"):
+        getattr(st, k).copy_(_t("st_" + k))
+    losses = alg.update(_t("tperm"), _t("sperm"))
+    ref = Z["losses"]
+    tol = 2e-4 if gemm == "simt" else 3e-3
+    for a, b, name in zip(losses, ref, ("value", "surrogate", "entropy", "latent", "load_balance")):
+        assert abs(a - b) < tol * max(1.0, abs(b)), (name, a, b)
+    assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
+    num = den = 0.0
+    worst = ("", 0.0)
+    for k, v in model.state_dict().items():
+        r, o = torch.from_numpy(Z["sd1_" + k]), torch.from_numpy(Z["sd0_" + k])
+        e = float((v.cpu() - r).abs().max())
+        worst = (k, e) if e > worst[1] else worst
+        num += float(((v.cpu() - o) - (r - o)).pow(2).sum()); den += float((r - o).pow(2).sum())
+        if gemm == "simt":
+            assert torch.allclose(v.cpu(), r, rtol=1e-3, atol=3e-5), (k, e)
+    rel = (num / den) ** 0.5
+    print(f"[{gemm}] MoE-CTS update: worst |param - ref| = {worst}, relative error of the update = {rel:.3e}")
+    assert rel < (2e-3 if gemm == "simt" else 5e-2)
+
+
+def test_moe_cts_runner_two_iterations(tmp_path):
+    from go2_rl_gym_b200.envs import task_registry
+    from go2_rl_gym_b200.utils import get_args
+    args = get_args(["--task", "go2_moe_cts", "--num_envs", "256", "--headless"])
+    env, _ = task_registry.make_env("go2_moe_cts", args)
+    runner, _ = task_registry.make_alg_runner(env, "go2_moe_cts", args, log_root=str(tmp_path))
+    runner.learn(2, init_at_random_ep_len=True)
+    sd = torch.load(os.path.join(runner.log_dir, "model_2.pt"), weights_only=False)
+    assert {"model_state_dict", "optimizer1_state_dict", "optimizer2_state_dict", "iter", "infos"} == set(sd)
+    assert "student_moe_encoder.moe.experts.experts.weight" in sd["model_state_dict"]
+    policy = runner.get_inference_policy()
+    a = policy(env.get_observations())
+    assert a.shape == (256, 12) and torch.isfinite(a).all()

@@ -1,0 +1,27 @@
+"""Checkpoint interop: the modules expose exactly the reference's state_dict keys and shapes (fixtures made by the reference)."""
+import os
+
+import numpy as np
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _keys(z):
+    return {k[4:]: z[k].shape for k in z.files if k.startswith("sd0_")}
+
+
+def test_actor_critic_keys():
+    from go2_rl_gym_b200.rl.modules import ActorCritic
+    ref = _keys(np.load(os.path.join(G, "rl_ppo.npz")))
+    m = ActorCritic(45, 263, 12, actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in ref.items()}
+
+
+def test_actor_critic_moe_cts_keys():
+    from go2_rl_gym_b200.rl.modules import ActorCriticMoECTS
+    from golden.cts_cfg import POLICY
+    ref = _keys(np.load(os.path.join(G, "rl_moe_cts.npz")))
+    m = ActorCriticMoECTS(45, 263, 12, 32, 5, **POLICY)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in ref.items()}
+    full = ActorCriticMoECTS(45, 263, 12, 32, 5)
+    assert sum(p.numel() for p in full.parameters()) == 1884609
