@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Generate tests/golden/rl_moe_cts.npz from the REFERENCE's rsl_rl (ActorCriticMoECTS + MoECTS + RolloutStorageCTS, imported
 unmodified from /root/reference/rsl_rl): a seeded synthetic rollout through act / process_env_step / compute_returns and one
-update() with injected teacher / student permutations.  Build container only.  Usage: python tests/golden/make_golden_cts.py"""
+update() with injected teacher / student permutations.  `--variant cts` does the same for ActorCriticCTS + CTS (-> rl_cts.npz; the
+reference allocates that module's history on 'cuda' at construction, actor_critic_cts.py:48, so torch.zeros is wrapped to drop the
+device while the module is built).  Build container only.  Usage (from /tmp): python /root/repo/tests/golden/make_golden_cts.py [--variant cts]"""
 import os
 import sys
 
@@ -15,15 +17,26 @@ sys.path[:0] = ["/root/reference/rsl_rl", HERE]
 from rsl_rl.algorithms.moe_cts import MoECTS  # noqa: E402
 from rsl_rl.modules.actor_critic_moe_cts import ActorCriticMoECTS  # noqa: E402
 import rsl_rl.storage.rollout_storage_cts as RS  # noqa: E402
-from cts_cfg import ALG, POLICY  # noqa: E402
+from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS  # noqa: E402
 
 
 def main():
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else "moe_cts"
     torch.manual_seed(0)
-    N, T, H = 32, 24, 5
-    model = ActorCriticMoECTS(45, 263, 12, N, H, **POLICY)
+    N, T, H = 32, (24 if variant == "moe_cts" else 12), 5
+    if variant == "moe_cts":
+        model = ActorCriticMoECTS(45, 263, 12, N, H, **POLICY)
+    else:
+        from rsl_rl.algorithms.cts import CTS
+        import rsl_rl.modules.actor_critic_cts as ACC
+        zeros = torch.zeros
+        ACC.torch.zeros = lambda *a, **kw: zeros(*a, **{k: v for k, v in kw.items() if k != "device"})
+        try:
+            model = ACC.ActorCriticCTS(45, 263, 12, N, H, **POLICY_CTS)
+        finally:
+            ACC.torch.zeros = zeros
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    alg = MoECTS(model, N, H, device="cpu", **ALG)
+    alg = MoECTS(model, N, H, device="cpu", **ALG) if variant == "moe_cts" else CTS(model, N, H, device="cpu", **ALG_CTS)
     alg.init_storage(N, T, [45], [263], [12])
     g = torch.Generator().manual_seed(1)
     obs = torch.randn(T + 1, N, 45, generator=g)
@@ -57,7 +70,7 @@ def main():
         save[f"sd1_{k}"] = v.detach().clone().numpy()
     save["losses"] = np.array(losses, dtype=np.float64)
     save["lr"] = alg.learning_rate
-    path = os.path.join(HERE, "rl_moe_cts.npz")
+    path = os.path.join(HERE, f"rl_{variant}.npz")
     np.savez_compressed(path, **save)
     print("wrote", path, f"{os.path.getsize(path)/1024:.0f} KiB losses", losses, "lr", alg.learning_rate)
 

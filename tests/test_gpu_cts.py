@@ -7,29 +7,34 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rl_moe_cts.npz"))
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ZS = {v: np.load(os.path.join(G, f"rl_{v}.npz")) for v in ("moe_cts", "cts")}
+Z = None
 
 
 def _t(k, dev="cuda"):
     return torch.from_numpy(Z[k]).to(dev)
 
 
-def _make(gemm, monkeypatch):
+def _make(gemm, monkeypatch, variant="moe_cts"):
+    global Z
+    Z = ZS[variant]
     monkeypatch.setenv("GO2_GEMM", gemm)
-    from golden.cts_cfg import ALG, POLICY
-    from go2_rl_gym_b200.rl.algorithms import MoECTS
-    from go2_rl_gym_b200.rl.modules import ActorCriticMoECTS
+    from golden.cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS
+    from go2_rl_gym_b200.rl.algorithms import CTS, MoECTS
+    from go2_rl_gym_b200.rl.modules import ActorCriticCTS, ActorCriticMoECTS
     T, N = Z["st_rewards"].shape[:2]
-    model = ActorCriticMoECTS(45, 263, 12, N, 5, **POLICY)
+    model = ActorCriticMoECTS(45, 263, 12, N, 5, **POLICY) if variant == "moe_cts" else ActorCriticCTS(45, 263, 12, N, 5, **POLICY_CTS)
     model.load_state_dict({k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")})
-    alg = MoECTS(model, N, 5, device="cuda", **ALG)
+    alg = MoECTS(model, N, 5, device="cuda", **ALG) if variant == "moe_cts" else CTS(model, N, 5, device="cuda", **ALG_CTS)
     alg.init_storage(N, T, [45], [263], [12])
     return model, alg, T, N
 
 
+@pytest.mark.parametrize("variant", ["moe_cts", "cts"])
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
-def test_moe_cts_act_matches_reference(gemm, monkeypatch):
-    model, alg, T, N = _make(gemm, monkeypatch)
+def test_cts_act_matches_reference(gemm, variant, monkeypatch):
+    model, alg, T, N = _make(gemm, monkeypatch, variant)
     tol = 2e-5 if gemm == "simt" else 3e-3
     a = alg.act(_t("in_obs")[0], _t("in_priv")[0], _t("in_hist")[0])
     st = alg.storage
@@ -43,11 +48,12 @@ def test_moe_cts_act_matches_reference(gemm, monkeypatch):
     assert torch.equal(st.dones[0].cpu().squeeze(-1).bool(), torch.cat([torch.from_numpy(Z["in_dones"][0])[ti], torch.from_numpy(Z["in_dones"][0])[si]]))
 
 
+@pytest.mark.parametrize("variant", ["moe_cts", "cts"])
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
-def test_moe_cts_update_matches_reference(gemm, monkeypatch):
-    """Both passes of MoECTS.update (moe_cts.py:104-234).  simt: parameters to 1e-3 rel / 3e-5 abs.  tc: relative error of the whole
+def test_cts_update_matches_reference(gemm, variant, monkeypatch):
+    """Both passes of MoECTS.update (moe_cts.py:104-234) / CTS.update (cts.py:167-285).  simt: parameters to 1e-3 rel / 3e-5 abs.  tc: relative error of the whole
     update < 5 %, losses within 3e-3, same learning-rate path."""
-    model, alg, T, N = _make(gemm, monkeypatch)
+    model, alg, T, N = _make(gemm, monkeypatch, variant)
     st = alg.storage
     for k in ("observations", "privileged_observations", "history", "actions", "rewards", "dones", "values", "returns", "advantages",
               "actions_log_prob", "mu", "sigma"):
@@ -68,20 +74,28 @@ def test_moe_cts_update_matches_reference(gemm, monkeypatch):
         if gemm == "simt":
             assert torch.allclose(v.cpu(), r, rtol=1e-3, atol=3e-5), (k, e)
     rel = (num / den) ** 0.5
-    print(f"[{gemm}] MoE-CTS update: worst |param - ref| = {worst}, relative error of the update = {rel:.3e}")
+    print(f"[{gemm}] {variant} update: worst |param - ref| = {worst}, relative error of the update = {rel:.3e}")
     assert rel < (2e-3 if gemm == "simt" else 5e-2)
 
 
-def test_moe_cts_runner_two_iterations(tmp_path):
+@pytest.mark.parametrize("task", ["go2_moe_cts", "go2_cts"])
+def test_cts_runner_two_iterations(task, tmp_path):
     from go2_rl_gym_b200.envs import task_registry
     from go2_rl_gym_b200.utils import get_args
-    args = get_args(["--task", "go2_moe_cts", "--num_envs", "256", "--headless"])
-    env, _ = task_registry.make_env("go2_moe_cts", args)
-    runner, _ = task_registry.make_alg_runner(env, "go2_moe_cts", args, log_root=str(tmp_path))
+    args = get_args(["--task", task, "--num_envs", "256", "--headless"])
+    env, _ = task_registry.make_env(task, args)
+    runner, _ = task_registry.make_alg_runner(env, task, args, log_root=str(tmp_path))
     runner.learn(2, init_at_random_ep_len=True)
     sd = torch.load(os.path.join(runner.log_dir, "model_2.pt"), weights_only=False)
     assert {"model_state_dict", "optimizer1_state_dict", "optimizer2_state_dict", "iter", "infos"} == set(sd)
-    assert "student_moe_encoder.moe.experts.experts.weight" in sd["model_state_dict"]
+    key = "student_moe_encoder.moe.experts.experts.weight" if task == "go2_moe_cts" else "student_encoder.0.weight"
+    assert key in sd["model_state_dict"]
+    # resume: the saved optimiser / model state loads back into a fresh runner
+    runner2, _ = task_registry.make_alg_runner(env, task, args, log_root=None)
+    runner2.load(os.path.join(runner.log_dir, "model_2.pt"))
+    assert runner2.current_learning_iteration == 2
+    for (k, a), b in zip(runner.alg.model.state_dict().items(), runner2.alg.model.state_dict().values()):
+        assert torch.equal(a, b), k
     policy = runner.get_inference_policy()
     a = policy(env.get_observations())
     assert a.shape == (256, 12) and torch.isfinite(a).all()
