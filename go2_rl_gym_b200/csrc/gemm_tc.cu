@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "../../include/go2_b200.h"
@@ -276,15 +277,216 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// One CTA per SM walks a static list of (split, m-tile, n-tile) units.  The accumulator is double-buffered in TMEM (columns 0 /
+// 256), so the MMA warp starts the next unit while the four epilogue warps drain the previous one; the operand ring (4 stages)
+// keeps running across units.  The epilogue never issues a global store itself: each 128 x 32 chunk is staged in shared memory
+// (128B-swizzled for the row-major copy, dense [32][128] for the transposed copy) and leaves through TMA bulk-tensor stores,
+// which clip the M / N tails; the ELU' operand of dgrad arrives the same way (TMA load into the staging buffer, used in place).
+struct TcParamsP {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_per_split, total_kb;
+  int rows_pad;            // rows between consecutive split slices in the C map (multiple of 128)
+  const float* bias;
+  int epi, has_c, has_ct, has_aux;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int TCP_STAGES = 4;
+constexpr int TCP_CST = 3, TCP_TST = 2, TCP_CHUNK_BYTES = TC_BM * 32 * 4;
+template <int BN> constexpr int tcp_smem_bytes() { return TCP_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + (TCP_CST + TCP_TST) * TCP_CHUNK_BYTES + 256 + 1024; }
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                         const __grid_constant__ CUtensorMap tmCt, const __grid_constant__ CUtensorMap tmAux, const TcParamsP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int S = TCP_STAGES, A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int NCH = (BN + 31) / 32;
+  uint8_t* cst = smem + S * STAGE_BYTES;                       // TCP_CST row-major staging chunks [128 rows][128 B], SW128
+  uint8_t* tst = cst + TCP_CST * TCP_CHUNK_BYTES;              // TCP_TST transposed staging chunks [32 n][128 m] floats, dense
+  uint64_t* full_bar = (uint64_t*)(tst + TCP_TST * TCP_CHUNK_BYTES);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull = empty_bar + S;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* auxb = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(auxb + TCP_CST);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    if (p.has_c) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
+    if (p.has_ct) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmCt) : "memory");
+    if (p.has_aux) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmAux) : "memory");
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+    for (int b = 0; b < TCP_CST; ++b) mbar_init(auxb + b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // the whole TMEM: two accumulators of up to 256 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: the stage ring runs straight through the unit list
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
+        const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(empty_bar + s, ((it / S) & 1) ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          tma_load_2d(&tmA, full_bar + s, sa, (kb0 + kb) * TC_BK, mt * TC_BM);
+          tma_load_2d(&tmB, full_bar + s, sa + A_BYTES, (kb0 + kb) * TC_BK, nt * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      uint32_t it = 0;
+      int ui = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+        const int z = u / (p.n_tiles * p.m_tiles);
+        const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+        const int buf = ui & 1;
+        mbar_wait(tempty + buf, ((ui >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar + s, (it / S) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar + s);
+        }
+        umma_commit(tfull + buf);
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quadrant q; thread = one row of the tile)
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const bool leader = (threadIdx.x == 64);
+    uint32_t g = 0;        // running chunk counter: selects the staging buffers and the aux barrier phase
+    int ui = 0;
+    if (p.has_aux && leader && (int)blockIdx.x < units) {
+      const int u = blockIdx.x, nt = u % p.n_tiles, mt = (u / p.n_tiles) % p.m_tiles;
+      mbar_expect_tx(auxb + 0, TCP_CHUNK_BYTES);
+      tma_load_2d(&tmAux, auxb + 0, cst, nt * BN, mt * TC_BM);
+    }
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+      const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
+      const int m0 = mt * TC_BM, n0 = nt * BN;
+      const int nch = min(NCH, (p.N - n0 + 31) / 32);
+      const int buf = ui & 1;
+      mbar_wait(tfull + buf, (ui >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int nb = n0 + c * 32;
+        const int cb = g % TCP_CST, tb = g & 1;
+        float* cs = reinterpret_cast<float*>(cst + cb * TCP_CHUNK_BYTES);
+        float* ts = reinterpret_cast<float*>(tst + tb * TCP_CHUNK_BYTES);
+        if (leader) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // stores of chunks <= g-2 have left their staging buffers
+          if (p.has_aux) {                                                    // prefetch the ELU' operand of chunk g+1
+            int nu = u, nc = c + 1;
+            if (nc == nch) { nu = u + gridDim.x; nc = 0; }
+            if (nu < units) {
+              const int nnt = nu % p.n_tiles, nmt = (nu / p.n_tiles) % p.m_tiles, nbuf = (g + 1) % TCP_CST;
+              mbar_expect_tx(auxb + nbuf, TCP_CHUNK_BYTES);
+              tma_load_2d(&tmAux, auxb + nbuf, cst + nbuf * TCP_CHUNK_BYTES, nnt * BN + nc * 32, nmt * TC_BM);
+            }
+          }
+        }
+        epi_bar();
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 256 + c * 32), r);
+        if (c == nch - 1) {                                                   // accumulator fully read: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + buf)) : "memory");
+        }
+        float v[32];
+        float bias_lane = 0.0f;
+        if ((p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) && nb + lane < p.N) bias_lane = __ldg(p.bias + nb + lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) x += __shfl_sync(0xffffffffu, bias_lane, j);
+          if (p.epi == TC_EPI_BIAS_ELU) x = x > 0.0f ? x : (__expf(x) - 1.0f);
+          v[j] = x;
+        }
+        const int sw = row & 7;
+        if (p.has_aux) {
+          mbar_wait(auxb + cb, (g / TCP_CST) & 1);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 y = *reinterpret_cast<const float4*>(cs + row * 32 + ((j4 ^ sw) << 2));
+            v[4 * j4 + 0] *= (y.x > 0.0f ? 1.0f : y.x + 1.0f);
+            v[4 * j4 + 1] *= (y.y > 0.0f ? 1.0f : y.y + 1.0f);
+            v[4 * j4 + 2] *= (y.z > 0.0f ? 1.0f : y.z + 1.0f);
+            v[4 * j4 + 3] *= (y.w > 0.0f ? 1.0f : y.w + 1.0f);
+          }
+        }
+        if (p.has_c) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(cs + row * 32 + ((j4 ^ sw) << 2)) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+        if (p.has_ct) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ts[j * TC_BM + row] = v[j];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar();
+        if (leader) {
+          if (p.has_c) tma_store_2d(&tmC, cs, nb, z * p.rows_pad + m0);
+          if (p.has_ct) tma_store_2d(&tmCt, ts, m0, nb);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // out[i] = sum_z part[z][i] (deterministic split-K reduction); rows x cols with output leading dimension ld_out
 // cols = K (+1 when the bias gradient rides along as an extra "ones" column of X^T: that column goes to db)
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int Z, long ld_part, long ld_out, int cols,
-                                        int k_real, float* __restrict__ db) {
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int Z, long ld_part, long split_stride, long ld_out,
+                                        int cols, int k_real, float* __restrict__ db) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long r = i / cols, c = i % cols;
   float s = 0;
-  for (int z = 0; z < Z; ++z) s += part[(long)z * ld_part * (n / cols) + r * ld_part + c];
+  for (int z = 0; z < Z; ++z) s += part[(long)z * split_stride + r * ld_part + c];
   if (c < k_real) out[r * ld_out + c] = s;
   else if (db) db[r] = s;
 }
@@ -312,17 +514,19 @@ static EncodeTiledFn get_encode() {
   });
   return fn;
 }
-// row-major [rows, cols] fp32 with leading dimension ld (elements); box = 32 floats x box_rows, 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, int box_rows) {
+// row-major [rows, cols] fp32 with leading dimension ld (elements); box = box_cols floats x box_rows; 128B swizzle when the box is
+// one swizzle atom wide (32 floats), dense otherwise; zero OOB fill on loads, clipping on stores
+static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, int box_rows, int box_cols = TC_BK) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(4, "cuTensorMapEncodeTiled unavailable");
   if (((uintptr_t)ptr & 15) || ((ld * 4) & 15)) return set_error(5, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols == TC_BK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(6, "cuTensorMapEncodeTiled failed");
   return 0;
 }
@@ -341,8 +545,80 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParam
   return 0;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+static bool legacy_only() {
+  static int v = -1;
+  if (v < 0) v = getenv("GO2_GEMM_LEGACY") ? 1 : 0;
+  return v == 1;
+}
+static bool aligned16(const void* ptr, long ld) { return (((uintptr_t)ptr & 15) == 0) && ((ld & 3) == 0); }
+// tile width of the persistent kernel: 160 wins when N is just past a multiple of 128 (the "ones" column of the bias gradient)
+static int persist_bn(int N) {
+  const long c128 = (long)((N + 127) / 128) * (128 + 128), c160 = (long)((N + 159) / 160) * (128 + 160);
+  return c160 < c128 ? 160 : 128;
+}
+static bool persist_ok(const TcParams& p) {
+  if (legacy_only() || p.dbg || p.N <= 64) return false;
+  if (p.split_stride && p.split_stride != (long)((p.M + TC_BM - 1) / TC_BM * TC_BM) * p.ldc) return false;
+  if (p.C && !aligned16(p.C, p.ldc)) return false;
+  if (p.Ct && !aligned16(p.Ct, p.ldct)) return false;
+  if (p.epi == TC_EPI_MUL_ELU_GRAD && !(p.aux && aligned16(p.aux, p.ldaux))) return false;
+  return p.C || p.Ct;
+}
+
+template <int BN>
+static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tct, const CUtensorMap& taux,
+                          const TcParamsP& pp, cudaStream_t st) {
+  constexpr int smem = tcp_smem_bytes<BN>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int units = pp.m_tiles * pp.n_tiles * pp.splits;
+  gemm_tf32_persist_kernel<BN><<<min(units, sm_count()), TC_THREADS, smem, st>>>(ta, tb, tc, tct, taux, pp);
+  count_launch();
+  return 0;
+}
+
+// split-K slices of C sit rows_pad = roundup(M, 128) rows apart so that one 2-D map covers all of them
+static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
+  const int BN = persist_bn(p.N);
+  TcParamsP pp{};
+  pp.M = p.M; pp.N = p.N; pp.K = p.K;
+  pp.m_tiles = (p.M + TC_BM - 1) / TC_BM; pp.n_tiles = (p.N + BN - 1) / BN;
+  pp.total_kb = (p.K + TC_BK - 1) / TC_BK;
+  pp.kb_per_split = (pp.total_kb + splits - 1) / splits;
+  pp.splits = (pp.total_kb + pp.kb_per_split - 1) / pp.kb_per_split;      // every slice gets at least one K block
+  pp.rows_pad = pp.m_tiles * TC_BM;
+  pp.bias = p.bias; pp.epi = p.epi; pp.has_c = p.C != nullptr; pp.has_ct = p.Ct != nullptr; pp.has_aux = p.epi == TC_EPI_MUL_ELU_GRAD;
+  if (splits > 1 && p.split_stride != (long)pp.rows_pad * p.ldc) return set_error(5, "gemm_tc_persist: split stride must be roundup(M,128) * ldc");
+  CUtensorMap ta, tb, tc, tct, taux;
+  int rc = make_map(&ta, A, p.M, p.K, lda, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&tb, B, p.N, p.K, ldb, BN);
+  if (rc) return rc;
+  tc = ta; tct = ta; taux = ta;
+  if (p.C) { rc = make_map(&tc, p.C, splits > 1 ? (long)splits * pp.rows_pad : p.M, p.N, p.ldc, TC_BM); if (rc) return rc; }
+  if (p.Ct) { rc = make_map(&tct, p.Ct, p.N, p.M, p.ldct, 32, TC_BM); if (rc) return rc; }
+  if (pp.has_aux) { rc = make_map(&taux, p.aux, p.M, p.N, p.ldaux, TC_BM); if (rc) return rc; }
+  rc = BN == 160 ? launch_persist<160>(ta, tb, tc, tct, taux, pp, st) : launch_persist<128>(ta, tb, tc, tct, taux, pp, st);
+  if (rc) return rc;
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // C[M,N] = A[M,K] B[N,K]^T with both operands K-major; see TcParams for the epilogue
 static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams p, int splits, cudaStream_t st) {
+  if (persist_ok(p)) return gemm_tc_persist(A, lda, B, ldb, p, splits, st);
   const int BN = p.N > 64 ? 128 : 64;
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, p.M, p.K, lda, TC_BM);
@@ -389,25 +665,31 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
   cudaStream_t st = (cudaStream_t)stream;
   const int k_real = K;
   if (db) K = K + 1;
-  const int BN = K > 64 ? 128 : 64;
-  const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);
-  const int total_kb = (M + TC_BK - 1) / TC_BK;
-  int splits = max(1, min(min(total_kb / 4, 64), (296 + tiles - 1) / tiles));
   const long ldp = (K + 3) / 4 * 4;
-  while (splits > 1 && (long)splits * N * ldp > workspace_floats) --splits;
+  const int total_kb = (M + TC_BK - 1) / TC_BK;
+  const int rows_pad = (N + TC_BM - 1) / TC_BM * TC_BM;                   // slice pitch in rows (what the persistent kernel's C map needs)
+  const bool persist = !legacy_only() && K > 64 && workspace && (long)rows_pad * ldp <= workspace_floats;
+  const int rows_slice = persist ? rows_pad : N;                          // the legacy kernel takes any slice pitch
+  const int BN = persist ? persist_bn(K) : (K > 64 ? 128 : 64);
+  const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);
+  int splits;
+  if (persist) splits = max(1, min(min(total_kb / 8, 48), (sm_count() + tiles / 2) / tiles));   // ~ one unit per SM
+  else splits = max(1, min(min(total_kb / 4, 64), (296 + tiles - 1) / tiles));
+  while (splits > 1 && (long)splits * rows_slice * ldp > workspace_floats) --splits;
   if (!workspace) splits = 1;
+  splits = (total_kb + (total_kb + splits - 1) / splits - 1) / ((total_kb + splits - 1) / splits);   // drop empty trailing slices
   TcParams p{};
   p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN;
   if (splits == 1 && lddw % 4 == 0 && !db) {
     p.C = dW; p.ldc = lddw;
     return gemm_tc(dZt, lddzt, Xt, ldxt, p, 1, st);
   }
-  if (!workspace || (long)N * ldp > workspace_floats) return set_error(5, "go2_linear_wgrad_tc: workspace too small");
-  p.C = workspace; p.ldc = ldp; p.split_stride = (long)N * ldp;
+  if (!workspace || (long)rows_slice * ldp > workspace_floats) return set_error(5, "go2_linear_wgrad_tc: workspace too small");
+  p.C = workspace; p.ldc = ldp; p.split_stride = (long)rows_slice * ldp;
   int rc = gemm_tc(dZt, lddzt, Xt, ldxt, p, splits, st);
   if (rc) return rc;
   const long n = (long)N * K;
-  tc_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, ldp, lddw, K, k_real, db);
+  tc_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, ldp, p.split_stride, lddw, K, k_real, db);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

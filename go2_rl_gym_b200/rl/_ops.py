@@ -100,7 +100,7 @@ class MlpEngine:
         hmax = max(dims[1:-1]) if self.L > 1 else dims[-1]
         self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(2)]
         self.dbufT = [torch.empty(hmax, max(train_rows, 1), device=dev) for _ in range(2)] if (train_rows and self.tc) else None
-        self.work = torch.empty(64 * max(_pad4(dims[l] + 1) * dims[l + 1] for l in range(self.L)), device=dev)
+        self.work = torch.empty(64 * max(_pad4(dims[l] + 1) * ((dims[l + 1] + 127) // 128 * 128) for l in range(self.L)), device=dev)
         self.kpad0 = _pad4(dims[0])
         self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if (self.tc and self.kpad0 != dims[0]) else None
         first_wt = 0 if need_dx else 1
@@ -180,7 +180,7 @@ class MlpEngine:
             if l > 0:
                 nxt, nxtT = self.dbuf[l % 2], (self.dbufT[l % 2] if self.dbufT is not None else None)
                 if self.tc and n_out % 4 == 0:
-                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], 0, 0, ptr(self.actsT[l - 1]), self.train_rows,
+                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], ptr(self.acts[l - 1]), n_in, ptr(self.actsT[l - 1]), self.train_rows,
                          ptr(nxt), n_in, ptr(nxtT), self.train_rows, M, n_out, n_in)
                 else:
                     call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,

@@ -225,7 +225,7 @@ class _StudentMoE:
         self.dfeat, self.dfeat_t = z(tr, E * self.H), z(E * self.H, tr)
         self.usage = torch.zeros(E, device=dev)
         self.Wet = torch.zeros(E * self.H, D, device=dev)   # per expert W_e^T [H, D], stacked
-        self.work = torch.empty(64 * D * (self.H + 4), device=dev)
+        self.work = torch.empty(64 * 128 * (self.H + 4), device=dev)
         self._dirty = True
         self.train_rows = train_rows
 
@@ -265,7 +265,7 @@ class _StudentMoE:
             if tc:
                 call("go2_linear_wgrad_tc", ptr(self.deo_t) + 4 * e * D * M, M, ptr(featT) + 4 * e * H * tr, tr, ptr(self.gWe) + 4 * e * D * H, H, 0,
                      M, D, H, ptr(self.work), self.work.numel())
-                call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, 0, 0, ptr(featT) + 4 * e * H * tr, tr,
+                call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, ptr(feat) + 4 * e * H, E * H, ptr(featT) + 4 * e * H * tr, tr,
                      ptr(self.dfeat) + 4 * e * H, E * H, ptr(self.dfeat_t) + 4 * e * H * tr, tr, M, D, H)
             else:
                 call("go2_linear_wgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, E * H, ptr(self.gWe) + 4 * e * D * H, H, 0,

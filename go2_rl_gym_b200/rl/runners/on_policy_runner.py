@@ -57,6 +57,22 @@ class OnPolicyRunner:
         self._done_rew = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
         self._done_len = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
 
+    def run_iteration(self, sync=None):
+        """One un-logged iteration (rollout + returns + update) — the timing loop of bench.py / tools."""
+        env, alg = self.env, self.alg
+        obs, priv = env.get_observations(), env.get_privileged_observations()
+        cobs = priv if priv is not None else obs
+        with torch.inference_mode():
+            for _ in range(self.num_steps_per_env):
+                actions = alg.act(obs, cobs)
+                obs, priv, rewards, dones, infos = env.step(actions)
+                cobs = priv if priv is not None else obs
+                alg.process_env_step(rewards, dones, infos)
+            if sync is not None:
+                sync()
+            alg.compute_returns(cobs)
+        return alg.update()
+
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         if self.log_dir is not None and self.writer is None and SummaryWriter is not None:
             self.writer = SummaryWriter(log_dir=self.log_dir, flush_secs=10)

@@ -49,6 +49,24 @@ class OnPolicyRunnerCTS:
         d8 = None if dones is None else (dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8))
         _ops.call("go2_history_update", _ops.ptr(self.history), _ops.ptr(obs), _ops.ptr(d8), self.env.num_envs, self.history_length, self.env.num_obs)
 
+    def run_iteration(self, sync=None):
+        """One un-logged iteration (rollout + returns + both update passes) — the timing loop of bench.py / tools."""
+        env, alg = self.env, self.alg
+        obs, priv = env.get_observations(), env.get_privileged_observations()
+        if not getattr(self, "_hist_primed", False):
+            self._roll_history(obs, None)
+            self._hist_primed = True
+        with torch.inference_mode():
+            for _ in range(self.num_steps_per_env):
+                actions = alg.act(obs, priv, self.history.flatten(1))
+                obs, priv, rewards, dones, infos = env.step(actions)
+                self._roll_history(obs, dones)
+                alg.process_env_step(rewards, dones, infos)
+            if sync is not None:
+                sync()
+            alg.compute_returns(priv, self.history.flatten(1))
+        return alg.update()
+
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         if self.log_dir is not None and self.writer is None and SummaryWriter is not None:
             self.writer = SummaryWriter(log_dir=self.log_dir, flush_secs=10)

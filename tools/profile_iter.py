@@ -14,17 +14,7 @@ env_cfg, _ = task_registry.get_cfgs(a.task); env_cfg.terrain.mesh_type = "height
 env, _ = task_registry.make_env(a.task, args, env_cfg)
 runner, _ = task_registry.make_alg_runner(env, a.task, args, log_root=None)
 alg = runner.alg
-obs, cobs = env.get_observations(), env.get_privileged_observations()
-
-def iteration():
-    global obs, cobs
-    with torch.inference_mode():
-        for i in range(24):
-            act = alg.act(obs, cobs)
-            obs, cobs, rew, dones, infos = env.step(act)
-            alg.process_env_step(rew, dones, infos)
-        alg.compute_returns(cobs)
-    alg.update()
+iteration = runner.run_iteration
 
 for _ in range(3):
     iteration()
