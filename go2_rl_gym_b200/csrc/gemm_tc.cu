@@ -279,14 +279,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ------------------------------------------------------------------------------------------------ persistent variant
 // One CTA per SM walks a static list of (split, m-tile, n-tile) units.  The accumulator is double-buffered in TMEM (columns 0 /
-// 256), so the MMA warp starts the next unit while the four epilogue warps drain the previous one; the operand ring (4 stages)
-// keeps running across units.  The epilogue never issues a global store itself: each 128 x 32 chunk is staged in shared memory
-// (128B-swizzled for the row-major copy, dense [32][128] for the transposed copy) and leaves through TMA bulk-tensor stores,
-// which clip the M / N tails; the ELU' operand of dgrad arrives the same way (TMA load into the staging buffer, used in place).
+// 256), so the MMA warp starts the next unit while the epilogue drains the previous one; the operand ring keeps running across
+// units.  The epilogue (two groups of four warps, alternating 32-column chunks) never issues a global store itself: each
+// 128 x 32 chunk is staged in shared memory (128B-swizzled for the row-major copy, dense [32][128] for the transposed copy) and
+// leaves through TMA bulk-tensor stores, which clip the M / N tails; the ELU' operand of dgrad arrives the same way (TMA load
+// into the row-major staging buffer, consumed in place).
 struct TcParamsP {
   int M, N, K;
   int m_tiles, n_tiles, splits, kb_per_split, total_kb;
   int rows_pad;            // rows between consecutive split slices in the C map (multiple of 128)
+  int stages;              // operand ring depth
   const float* bias;
   int epi, has_c, has_ct, has_aux;
 };
@@ -295,28 +297,31 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-constexpr int TCP_STAGES = 4;
-constexpr int TCP_CST = 3, TCP_TST = 2, TCP_CHUNK_BYTES = TC_BM * 32 * 4;
-template <int BN> constexpr int tcp_smem_bytes() { return TCP_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + (TCP_CST + TCP_TST) * TCP_CHUNK_BYTES + 256 + 1024; }
+constexpr int TCP_THREADS = 320;                 // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int TCP_CHUNK_BYTES = TC_BM * 32 * 4;  // one staged 128 x 32 chunk
+constexpr int TCP_MAX_STAGES = 4;
+static int tcp_smem_bytes(int BN, int stages, bool has_ct) {
+  return stages * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + (has_ct ? 6 : 4) * TCP_CHUNK_BYTES + 256 + 1024;
+}
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                          const __grid_constant__ CUtensorMap tmCt, const __grid_constant__ CUtensorMap tmAux, const TcParamsP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int S = TCP_STAGES, A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int NCH = (BN + 31) / 32;
-  uint8_t* cst = smem + S * STAGE_BYTES;                       // TCP_CST row-major staging chunks [128 rows][128 B], SW128
-  uint8_t* tst = cst + TCP_CST * TCP_CHUNK_BYTES;              // TCP_TST transposed staging chunks [32 n][128 m] floats, dense
-  uint64_t* full_bar = (uint64_t*)(tst + TCP_TST * TCP_CHUNK_BYTES);
-  uint64_t* empty_bar = full_bar + S;
-  uint64_t* tfull = empty_bar + S;
+  const int S = p.stages;
+  uint8_t* cst = smem + S * STAGE_BYTES;                       // [group][2] row-major staging chunks [128 rows][128 B], SW128
+  uint8_t* tst = cst + 4 * TCP_CHUNK_BYTES;                    // [group] transposed staging chunk [32 n][128 m] floats (only with Ct)
+  uint64_t* full_bar = (uint64_t*)(tst + (p.has_ct ? 2 * TCP_CHUNK_BYTES : 0));
+  uint64_t* empty_bar = full_bar + TCP_MAX_STAGES;
+  uint64_t* tfull = empty_bar + TCP_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* auxb = tempty + 2;
-  uint32_t* tmem_slot = (uint32_t*)(auxb + TCP_CST);
+  uint64_t* auxb = tempty + 2;                                 // [group][2]
+  uint32_t* tmem_slot = (uint32_t*)(auxb + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = p.m_tiles * p.n_tiles * p.splits;
@@ -328,8 +333,8 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (p.has_ct) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmCt) : "memory");
     if (p.has_aux) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmAux) : "memory");
     for (int s = 0; s < S; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
-    for (int b = 0; b < TCP_CST; ++b) mbar_init(auxb + b, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 8); }
+    for (int b = 0; b < 4; ++b) mbar_init(auxb + b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the whole TMEM: two accumulators of up to 256 columns
@@ -344,17 +349,18 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0) {
     // ===== TMA producer: the stage ring runs straight through the unit list
     if (elect_one()) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
         const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(empty_bar + s, ((it / S) & 1) ^ 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
           tma_load_2d(&tmA, full_bar + s, sa, (kb0 + kb) * TC_BK, mt * TC_BM);
           tma_load_2d(&tmB, full_bar + s, sa + A_BYTES, (kb0 + kb) * TC_BK, nt * BN);
+          if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -362,8 +368,8 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===== MMA issuer (one thread)
     if (elect_one()) {
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t it = 0;
-      int ui = 0;
+      int s = 0, ui = 0;
+      uint32_t ph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
         const int z = u / (p.n_tiles * p.m_tiles);
         const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
@@ -371,63 +377,71 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(tempty + buf, ((ui >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(full_bar + s, (it / S) & 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
           umma_commit(empty_bar + s);
+          if (++s == S) { s = 0; ph ^= 1; }
         }
         umma_commit(tfull + buf);
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quadrant q; thread = one row of the tile)
-    const int q = warp & 3;
+    // ===== epilogue: group grp takes chunks grp, grp+2, ... of every unit; warp -> TMEM lane quadrant q; thread = one tile row
+    const int grp = (warp - 2) >> 2, q = warp & 3;
     const int row = 32 * q + lane;
-    const bool leader = (threadIdx.x == 64);
-    uint32_t g = 0;        // running chunk counter: selects the staging buffers and the aux barrier phase
+    const bool leader = (((warp - 2) & 3) == 0) && lane == 0;
+    const int sw = row & 7;
+    uint8_t* cst_g = cst + grp * 2 * TCP_CHUNK_BYTES;
+    float* ts = reinterpret_cast<float*>(tst + grp * TCP_CHUNK_BYTES);
+    uint64_t* auxb_g = auxb + grp * 2;
+    auto n_chunks = [&](int u) { return min(NCH, (p.N - (u % p.n_tiles) * BN + 31) / 32); };
+    // the chunk this group handles after (u, c) — the leader uses it to prefetch the ELU' operand one chunk ahead
+    auto advance = [&](int& u, int& c) {
+      c += 2;
+      while (u < units && c >= n_chunks(u)) { u += gridDim.x; c = grp; }
+      return u < units;
+    };
+    auto aux_load = [&](int u, int c, int slot) {
+      const int nt = u % p.n_tiles, mt = (u / p.n_tiles) % p.m_tiles;
+      mbar_expect_tx(auxb_g + slot, TCP_CHUNK_BYTES);
+      tma_load_2d(&tmAux, auxb_g + slot, cst_g + slot * TCP_CHUNK_BYTES, nt * BN + c * 32, mt * TC_BM);
+    };
+    uint32_t g = 0;        // this group's running chunk counter: staging slot = g & 1, aux barrier phase = (g >> 1) & 1
     int ui = 0;
-    if (p.has_aux && leader && (int)blockIdx.x < units) {
-      const int u = blockIdx.x, nt = u % p.n_tiles, mt = (u / p.n_tiles) % p.m_tiles;
-      mbar_expect_tx(auxb + 0, TCP_CHUNK_BYTES);
-      tma_load_2d(&tmAux, auxb + 0, cst, nt * BN, mt * TC_BM);
+    if (p.has_aux && leader) {
+      int u0 = blockIdx.x, c0 = grp - 2;
+      if (advance(u0, c0)) aux_load(u0, c0, 0);
     }
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
       const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
       const int m0 = mt * TC_BM, n0 = nt * BN;
-      const int nch = min(NCH, (p.N - n0 + 31) / 32);
+      const int nch = n_chunks(u);
       const int buf = ui & 1;
       mbar_wait(tfull + buf, (ui >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = 0; c < nch; ++c, ++g) {
+      for (int c = grp; c < nch; c += 2, ++g) {
         const int nb = n0 + c * 32;
-        const int cb = g % TCP_CST, tb = g & 1;
-        float* cs = reinterpret_cast<float*>(cst + cb * TCP_CHUNK_BYTES);
-        float* ts = reinterpret_cast<float*>(tst + tb * TCP_CHUNK_BYTES);
+        const int slot = g & 1;
+        float* cs = reinterpret_cast<float*>(cst_g + slot * TCP_CHUNK_BYTES);
         if (leader) {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // stores of chunks <= g-2 have left their staging buffers
-          if (p.has_aux) {                                                    // prefetch the ELU' operand of chunk g+1
-            int nu = u, nc = c + 1;
-            if (nc == nch) { nu = u + gridDim.x; nc = 0; }
-            if (nu < units) {
-              const int nnt = nu % p.n_tiles, nmt = (nu / p.n_tiles) % p.m_tiles, nbuf = (g + 1) % TCP_CST;
-              mbar_expect_tx(auxb + nbuf, TCP_CHUNK_BYTES);
-              tma_load_2d(&tmAux, auxb + nbuf, cst + nbuf * TCP_CHUNK_BYTES, nnt * BN + nc * 32, nmt * TC_BM);
-            }
+          if (p.has_aux) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the other slot's store has left it: refill it with chunk g+1's operand
+            int nu = u, nc = c;
+            if (advance(nu, nc)) aux_load(nu, nc, slot ^ 1);
+          } else {
+            // groups are committed transposed-first: at most one pending = the row-major store of chunk g-1 (other slot);
+            // the transposed staging chunk and this row-major slot (chunk g-2) have been read out
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
         }
-        epi_bar();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 256 + c * 32), r);
-        if (c == nch - 1) {                                                   // accumulator fully read: hand it back to the MMA warp
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + buf)) : "memory");
-        }
         float v[32];
         float bias_lane = 0.0f;
         if ((p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) && nb + lane < p.N) bias_lane = __ldg(p.bias + nb + lane);
@@ -438,9 +452,8 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (p.epi == TC_EPI_BIAS_ELU) x = x > 0.0f ? x : (__expf(x) - 1.0f);
           v[j] = x;
         }
-        const int sw = row & 7;
         if (p.has_aux) {
-          mbar_wait(auxb + cb, (g / TCP_CST) & 1);
+          mbar_wait(auxb_g + slot, (g >> 1) & 1);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 y = *reinterpret_cast<const float4*>(cs + row * 32 + ((j4 ^ sw) << 2));
@@ -460,13 +473,22 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) ts[j * TC_BM + row] = v[j];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        epi_bar();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if (leader) {
-          if (p.has_c) tma_store_2d(&tmC, cs, nb, z * p.rows_pad + m0);
-          if (p.has_ct) tma_store_2d(&tmCt, ts, m0, nb);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (p.has_ct) {
+            tma_store_2d(&tmCt, ts, m0, nb);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (p.has_c) {
+            tma_store_2d(&tmC, cs, nb, z * p.rows_pad + m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
+      // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + buf)) : "memory");
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -480,15 +502,32 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 // out[i] = sum_z part[z][i] (deterministic split-K reduction); rows x cols with output leading dimension ld_out
 // cols = K (+1 when the bias gradient rides along as an extra "ones" column of X^T: that column goes to db)
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int Z, long ld_part, long split_stride, long ld_out,
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int Z, long ld_part, long split_stride, long ld_out,
                                         int cols, int k_real, float* __restrict__ db) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const long r = i / cols, c = i % cols;
-  float s = 0;
-  for (int z = 0; z < Z; ++z) s += part[(long)z * split_stride + r * ld_part + c];
-  if (c < k_real) out[r * ld_out + c] = s;
-  else if (db) db[r] = s;
+  // block = 32 column-quads x 8 slice lanes: lane y sums slices y, y+8, ... of four consecutive columns of one row (ld_part is a
+  // multiple of 4, slices 16-byte aligned); the eight partial sums are combined in a fixed order -> deterministic
+  __shared__ float4 sm[8][32];
+  const int groups = (int)(ld_part >> 2);
+  const long i = (long)blockIdx.x * 32 + threadIdx.x;
+  const bool live = i < (long)rows * groups;
+  const int r = live ? (int)(i / groups) : 0, c0 = live ? (int)(i % groups) * 4 : 0;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live && c0 < cols) {
+    const float4* src = reinterpret_cast<const float4*>(part + (long)r * ld_part + c0);
+    const long zs = split_stride >> 2;
+    for (int z = threadIdx.y; z < Z; z += 8) { const float4 a = __ldg(src + (long)z * zs); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+  }
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || !live || c0 >= cols) return;
+  for (int y = 1; y < 8; ++y) { const float4 a = sm[y][threadIdx.x]; s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+  const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    if (c < k_real) out[(long)r * ld_out + c] = v[j];
+    else if (c < cols && db) db[r] = v[j];
+  }
 }
 
 // out[r][c] = in[c][r]  (weights W -> W^T for dgrad), tile transpose through shared memory
@@ -577,22 +616,23 @@ static bool persist_ok(const TcParams& p) {
 template <int BN>
 static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tct, const CUtensorMap& taux,
                           const TcParamsP& pp, cudaStream_t st) {
-  constexpr int smem = tcp_smem_bytes<BN>();
+  const int smem = tcp_smem_bytes(BN, pp.stages, pp.has_ct != 0);
   static bool attr_set = false;
   if (!attr_set) {
-    GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int units = pp.m_tiles * pp.n_tiles * pp.splits;
-  gemm_tf32_persist_kernel<BN><<<min(units, sm_count()), TC_THREADS, smem, st>>>(ta, tb, tc, tct, taux, pp);
+  gemm_tf32_persist_kernel<BN><<<min(units, sm_count()), TCP_THREADS, smem, st>>>(ta, tb, tc, tct, taux, pp);
   count_launch();
   return 0;
 }
 
 // split-K slices of C sit rows_pad = roundup(M, 128) rows apart so that one 2-D map covers all of them
 static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
-  const int BN = persist_bn(p.N);
+  const int BN = p.Ct ? 128 : persist_bn(p.N);          // the 160-wide tile has no room for the transposed staging buffers
   TcParamsP pp{};
+  pp.stages = 4;
   pp.M = p.M; pp.N = p.N; pp.K = p.K;
   pp.m_tiles = (p.M + TC_BM - 1) / TC_BM; pp.n_tiles = (p.N + BN - 1) / BN;
   pp.total_kb = (p.K + TC_BK - 1) / TC_BK;
@@ -688,8 +728,8 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
   p.C = workspace; p.ldc = ldp; p.split_stride = (long)rows_slice * ldp;
   int rc = gemm_tc(dZt, lddzt, Xt, ldxt, p, splits, st);
   if (rc) return rc;
-  const long n = (long)N * K;
-  tc_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, n, splits, ldp, p.split_stride, lddw, K, k_real, db);
+  const long n = (long)N * (ldp / 4);
+  tc_splitk_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 8), 0, st>>>(workspace, dW, N, splits, ldp, p.split_stride, lddw, K, k_real, db);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
