@@ -598,6 +598,11 @@ static bool legacy_only() {
   if (v < 0) v = getenv("GO2_GEMM_LEGACY") ? 1 : 0;
   return v == 1;
 }
+static int persist_min_n() {   // narrowest output the persistent kernel takes (GO2_GEMM_PERSIST_MIN_N, tuning aid)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GO2_GEMM_PERSIST_MIN_N"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static bool aligned16(const void* ptr, long ld) { return (((uintptr_t)ptr & 15) == 0) && ((ld & 3) == 0); }
 // tile width of the persistent kernel: 160 wins when N is just past a multiple of 128 (the "ones" column of the bias gradient)
 static int persist_bn(int N) {
@@ -605,7 +610,7 @@ static int persist_bn(int N) {
   return c160 < c128 ? 160 : 128;
 }
 static bool persist_ok(const TcParams& p) {
-  if (legacy_only() || p.dbg || p.N <= 64) return false;
+  if (legacy_only() || p.dbg || p.N < persist_min_n()) return false;
   if (p.split_stride && p.split_stride != (long)((p.M + TC_BM - 1) / TC_BM * TC_BM) * p.ldc) return false;
   if (p.C && !aligned16(p.C, p.ldc)) return false;
   if (p.Ct && !aligned16(p.Ct, p.ldct)) return false;
@@ -708,7 +713,7 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
   const long ldp = (K + 3) / 4 * 4;
   const int total_kb = (M + TC_BK - 1) / TC_BK;
   const int rows_pad = (N + TC_BM - 1) / TC_BM * TC_BM;                   // slice pitch in rows (what the persistent kernel's C map needs)
-  const bool persist = !legacy_only() && K > 64 && workspace && (long)rows_pad * ldp <= workspace_floats;
+  const bool persist = !legacy_only() && K >= persist_min_n() && workspace && (long)rows_pad * ldp <= workspace_floats;
   const int rows_slice = persist ? rows_pad : N;                          // the legacy kernel takes any slice pitch
   const int BN = persist ? persist_bn(K) : (K > 64 ? 128 : 64);
   const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);

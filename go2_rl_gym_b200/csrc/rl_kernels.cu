@@ -391,6 +391,35 @@ static int launch_gemm(int a_k_contig, int b_j_contig, const float* A, long sai,
 
 extern "C" {
 
+}  // extern "C"
+namespace go2 {
+// dX[m][k] = dy[m] * w[k] * ELU'(act[m][k]) (+ transposed copy): backward of a 1-wide Linear, 32 x 32 tiles
+__global__ void dgrad_rank1_kernel(const float* __restrict__ dY, long lddy, const float* __restrict__ w, const float* __restrict__ act, long ldact,
+                                   float* __restrict__ dX, long lddx, float* __restrict__ dXt, long lddxt, int M, int K) {
+  __shared__ float t[32][33];
+  const int k = blockIdx.x * 32 + threadIdx.x, m0 = blockIdx.y * 32;
+  const float wk = k < K ? __ldg(w + k) : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int m = m0 + threadIdx.y + i;
+    float v = 0.0f;
+    if (m < M && k < K) {
+      v = __ldg(dY + (long)m * lddy) * wk;
+      if (act) { const float y = act[(long)m * ldact + k]; v *= (y > 0.0f ? 1.0f : y + 1.0f); }
+      dX[(long)m * lddx + k] = v;
+    }
+    t[threadIdx.y + i][threadIdx.x] = v;
+  }
+  if (!dXt) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int kk = blockIdx.x * 32 + threadIdx.y + i, m = m0 + threadIdx.x;
+    if (kk < K && m < M) dXt[(long)kk * lddxt + m] = t[threadIdx.x][threadIdx.y + i];
+  }
+}
+}  // namespace go2
+extern "C" {
 int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N, int K, int act, void* stream) {
   int rc = launch_gemm(1, 0, X, ldx, 1, W, 1, ldw, Y, ldy, M, N, K, 1, b, act ? EPI_BIAS_ELU : EPI_BIAS, nullptr, 0, 0, (cudaStream_t)stream, Yt, ldyt);
   if (rc) return rc;
@@ -400,6 +429,13 @@ int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, co
 
 int go2_linear_dgrad_simt(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, float* dXt, int lddxt, int M, int N, int K, void* stream) {
   // dX[M,K] = dY[M,N] W[N,K], times ELU'(act_in) when act_in != NULL
+  if (N == 1) {   // the critic's scalar head: an outer product, one streaming pass
+    dim3 block(32, 8), grid((K + 31) / 32, (M + 31) / 32);
+    dgrad_rank1_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dY, lddy, W, act_in, ldact, dX, lddx, dXt, lddxt, M, K);
+    count_launch();
+    GO2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   int rc = launch_gemm(1, 1, dY, lddy, 1, W, ldw, 1, dX, lddx, M, K, N, 1, nullptr, act_in ? EPI_MUL_ELU_GRAD : EPI_NONE, act_in, ldact, 0, (cudaStream_t)stream, dXt, lddxt);
   if (rc) return rc;
   GO2_CUDA_OK(cudaGetLastError());

@@ -70,6 +70,40 @@ def use_tc():
     return os.environ.get("GO2_GEMM", "tc") != "simt"
 
 
+class GraphSet:
+    """CUDA-graph cache for launch sequences that depend only on device-resident state.  run(key, fn): first call eager
+    (allocations, cudaFuncSetAttribute, tensor-map encodes), second call captured, replayed afterwards.  GO2_GRAPH=0 disables
+    graphs; a failed capture makes that key eager for good.  Collectives are never captured: with world_size > 1 the callers cut
+    the optimiser step into [gradient graph] -> eager NCCL all-reduce -> [Adam graph]."""
+
+    def __init__(self):
+        self._g, self._warm, self._failed = {}, set(), set()
+        self.enabled = os.environ.get("GO2_GRAPH", "1") != "0"
+
+    def run(self, key, fn):
+        if not self.enabled or key in self._failed:
+            return fn()
+        g = self._g.get(key)
+        if g is not None:
+            return g.replay()
+        if key not in self._warm:
+            self._warm.add(key)
+            return fn()
+        import warnings
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fn()
+        except Exception as e:  # noqa: BLE001 - anything the capture rejects
+            self._failed.add(key)
+            warnings.warn(f"CUDA-graph capture of {key} failed ({type(e).__name__}: {e}); using eager launches")
+            torch.cuda.synchronize()
+            return fn()
+        self._g[key] = g
+        g.replay()
+
+
 def _pad4(n):
     return (n + 3) // 4 * 4
 

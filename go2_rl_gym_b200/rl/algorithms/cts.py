@@ -79,7 +79,7 @@ class CTS:
         self._last_values = z(N, 1)
         self._hist_p = z(N, self.history_length * actor_obs_shape[0])
         self._rew_p, self._actions_env = z(N), z(N, A)
-        self._graph, self._graph_warm = None, 0
+        self._graphs = _ops.GraphSet()
 
     def test_mode(self):
         self.model.eval()
@@ -163,21 +163,23 @@ class CTS:
         self._sh = st.shuffled(idx, pads, transposed=("critic_obs", "history") if tc else ())
         self._total = idx.numel()
         self._log.zero_(); self._log2.zero_()
-        use_graph = self.world_size == 1 and os.environ.get("GO2_GRAPH", "1") != "0"
-        if not use_graph:
-            self._update_body()
-        elif self._graph is None and self._graph_warm < 1:
-            self._update_body()
-            self._graph_warm += 1
-        elif self._graph is None:
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                self._update_body()
-            self._graph = g
-            g.replay()
+        if self.world_size == 1:
+            self._graphs.run("update", self._update_body)
         else:
-            self._graph.replay()
+            ws, n1, G = self.world_size, m.n1, m.flat_grads
+            for epoch in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    self._graphs.run(("grad1", i), lambda: self._grad1(i))
+                    self._comm1 = dist_utils.allreduce_grads_and_tail(G[:n1], self._scal, getattr(self, "_comm1", None))
+                    self._graphs.run("step1", self._step1)
+                    m.mark_dirty()                    # replays skip the Python side of the step
+            if self.sm > 0:
+                for epoch in range(self.num_learning_epochs):
+                    for i in range(self.num_mini_batches):
+                        self._graphs.run(("grad2", i), lambda: self._grad2(i))
+                        dist.all_reduce(G[n1:])
+                        self._graphs.run("step2", self._step2)
+                        m.mark_dirty()
         m.mark_dirty()
         n = self.num_learning_epochs * self.num_mini_batches
         log, log2 = self._log.tolist(), self._log2.tolist()      # the single host sync of update()
@@ -189,59 +191,69 @@ class CTS:
     _moe = False
 
     def _update_body(self):
-        st, m, sh, total = self.storage, self.model, self._sh, self._total
-        tm, sm, mb, A, D = self.tm, self.sm, self.mb, st.actions.shape[-1], m.latent_dim
-        tc = _ops.use_tc()
-        adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
-        ws = self.world_size
-        n1, n2 = m.n1, m.n2
-        P, G = m.flat_params, m.flat_grads
-        # ---------------- pass 1: PPO on teacher + student rows, optimizer 1 (moe_cts.py:114-195)
+        # pass 1: PPO on teacher + student rows, optimizer 1 (moe_cts.py:114-195)
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                s = slice(i * mb, (i + 1) * mb)
-                obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
-                priv_t = sh["critic_obs_t"][:, i * mb:i * mb + tm] if tc else None
-                self._latents(priv_b, hist_b, tm, sm, train_teacher=True, priv_t=priv_t, ld_t=total)
-                self._heads(obs_b, priv_b, mb, train=True)
-                call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
-                     ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
-                     ptr(self._dmu_t) if tc else 0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
-                     int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
-                m.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
-                m.critic_engine.backward(self._dval, 1, self._dval if tc else None, mb)
-                # d loss / d latent = first D columns of the actor's input gradient, teacher rows only (student latents carry no grad)
-                m.teacher_backward(m.actor_engine.dx, m.actor_engine.kpad0, self._lat, D, tm)
-                m._gviews["std"].copy_(self._scal[4:4 + A])
-                if ws > 1:
-                    self._comm1 = dist_utils.allreduce_grads_and_tail(G[:n1], self._scal, getattr(self, "_comm1", None))
-                call("go2_kl_adaptive_lr", ptr(self._scal), float(mb * ws), float(self.desired_kl) if adaptive else -1.0, ptr(self._lr1), ptr(self._log),
-                     float(tm * ws), float(max(sm, 1) * ws))
-                call("go2_adam_clip_step", ptr(P), ptr(G), ptr(self.exp_avg), ptr(self.exp_avg_sq), n1, self.max_grad_norm, ptr(self._lr1), 1.0,
-                     ptr(self._scratch))
-                for e in (m.teacher_engine, m.actor_engine, m.critic_engine):
-                    e.mark_dirty()
-        # ---------------- pass 2: student encoder towards the (updated) teacher latent, optimizer 2 (moe_cts.py:197-224)
-        if sm == 0:
+                self._grad1(i)
+                self._step1()
+        # pass 2: student encoder towards the (updated) teacher latent, optimizer 2 (moe_cts.py:197-224)
+        if self.sm == 0:
             return
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                s = slice(i * mb + tm, (i + 1) * mb)
-                priv_b, hist_b = sh["critic_obs"][s], sh["history"][s]
-                hist_t = sh["history_t"][:, i * mb + tm:(i + 1) * mb] if tc else None
-                m.teacher_latent(priv_b, sm, self._lat_t)
-                m.student.forward(hist_b, sm, self._lat[:sm], train=True, Xt=hist_t, ldxt=total)
-                call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t), ptr(self._dls), ptr(self._acc), sm, D)
-                m.student.backward(self._dls, self.load_balance_coef)
-                call("go2_cts_log", ptr(self._acc), ptr(m.student.usage) if self._moe else 0, ptr(self._log2), sm * D, m.student.E if self._moe else 1)
-                if ws > 1:
-                    dist.all_reduce(G[n1:])
-                    G[n1:].div_(ws)
-                call("go2_adam_clip_step", ptr(P) + 4 * n1, ptr(G) + 4 * n1, ptr(self.exp_avg) + 4 * n1, ptr(self.exp_avg_sq) + 4 * n1, n2,
-                     self.max_grad_norm, ptr(self._lr2), 1.0, ptr(self._scratch))
-                for e in m.student.engines():
-                    e.mark_dirty()
-                m.student.mark_dirty()
+                self._grad2(i)
+                self._step2()
+
+    def _grad1(self, i):
+        st, m, sh, total = self.storage, self.model, self._sh, self._total
+        tm, sm, mb, A, D = self.tm, self.sm, self.mb, st.actions.shape[-1], m.latent_dim
+        tc, ws = _ops.use_tc(), self.world_size
+        s = slice(i * mb, (i + 1) * mb)
+        obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
+        priv_t = sh["critic_obs_t"][:, i * mb:i * mb + tm] if tc else None
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True, priv_t=priv_t, ld_t=total)
+        self._heads(obs_b, priv_b, mb, train=True)
+        call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
+             ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
+             ptr(self._dmu_t) if tc else 0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+             int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
+        m.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
+        m.critic_engine.backward(self._dval, 1, self._dval if tc else None, mb)
+        # d loss / d latent = first D columns of the actor's input gradient, teacher rows only (student latents carry no grad)
+        m.teacher_backward(m.actor_engine.dx, m.actor_engine.kpad0, self._lat, D, tm)
+        m._gviews["std"].copy_(self._scal[4:4 + A])
+
+    def _step1(self):
+        m, ws = self.model, self.world_size
+        adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
+        call("go2_kl_adaptive_lr", ptr(self._scal), float(self.mb * ws), float(self.desired_kl) if adaptive else -1.0, ptr(self._lr1), ptr(self._log),
+             float(self.tm * ws), float(max(self.sm, 1) * ws))
+        call("go2_adam_clip_step", ptr(m.flat_params), ptr(m.flat_grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), m.n1, self.max_grad_norm, ptr(self._lr1),
+             1.0, ptr(self._scratch))
+        for e in (m.teacher_engine, m.actor_engine, m.critic_engine):
+            e.mark_dirty()
+
+    def _grad2(self, i):
+        m, sh, total = self.model, self._sh, self._total
+        tm, sm, mb, D = self.tm, self.sm, self.mb, m.latent_dim
+        tc = _ops.use_tc()
+        s = slice(i * mb + tm, (i + 1) * mb)
+        priv_b, hist_b = sh["critic_obs"][s], sh["history"][s]
+        hist_t = sh["history_t"][:, i * mb + tm:(i + 1) * mb] if tc else None
+        m.teacher_latent(priv_b, sm, self._lat_t)
+        m.student.forward(hist_b, sm, self._lat[:sm], train=True, Xt=hist_t, ldxt=total)
+        call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t), ptr(self._dls), ptr(self._acc), sm, D)
+        m.student.backward(self._dls, self.load_balance_coef)
+        call("go2_cts_log", ptr(self._acc), ptr(m.student.usage) if self._moe else 0, ptr(self._log2), sm * D, m.student.E if self._moe else 1)
+
+    def _step2(self):
+        m, n1 = self.model, self.model.n1
+        # with world_size > 1 the gradient arrives SUM-reduced: fold the 1/world_size of the mean loss into the step
+        call("go2_adam_clip_step", ptr(m.flat_params) + 4 * n1, ptr(m.flat_grads) + 4 * n1, ptr(self.exp_avg) + 4 * n1, ptr(self.exp_avg_sq) + 4 * n1, m.n2,
+             self.max_grad_norm, ptr(self._lr2), 1.0 / self.world_size, ptr(self._scratch))
+        for e in m.student.engines():
+            e.mark_dirty()
+        m.student.mark_dirty()
 
     # ---- checkpoint interop (two torch.optim.Adam state dicts, on_policy_runner_cts.py:287-294) --------------------------
     def _opt_state(self, names, lr, lr_state):

@@ -56,8 +56,7 @@ class PPO:
         self.exp_avg_sq = torch.zeros(n, device=dev)
         self._lr = torch.zeros(4, device=dev)      # {lr, optimiser step, Adam bias corrections} — device resident
         self._lr[0] = float(self.learning_rate)
-        self._graph = None
-        self._graph_warm = 0
+        self._graphs = _ops.GraphSet()
         self._scal = torch.zeros(20, device=dev)
         self._log = torch.zeros(5, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
@@ -124,22 +123,15 @@ class PPO:
         total = indices.numel()
         self._log.zero_()
         self._sh, self._total, self._tc = sh, total, tc
-        use_graph = self.world_size == 1 and os.environ.get("GO2_GRAPH", "1") != "0"
-        if not use_graph:
-            self._update_body()
-        elif self._graph is None and self._graph_warm < 1:
-            self._update_body()                       # first call eager: allocations, cudaFuncSetAttribute, tensor maps
-            self._graph_warm += 1
-        elif self._graph is None:
-            # every launch of the 20 optimiser steps depends only on device-resident state -> capture once, replay per iteration
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                self._update_body()
-            self._graph = g
-            g.replay()
+        if self.world_size == 1:
+            self._graphs.run("update", self._update_body)
         else:
-            self._graph.replay()
+            for epoch in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    self._graphs.run(("grad", i), lambda: self._grad_part(i))
+                    self._allreduce_grads()           # one collective per optimiser step: flat gradient + the scalar tail (KL / loss sums)
+                    self._graphs.run("step", self._step_part)
+                    ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()     # replays skip the Python side of _step_part
         ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
         self._opt_step += self.num_learning_epochs * self.num_mini_batches
         num_updates = self.num_learning_epochs * self.num_mini_batches
@@ -149,36 +141,42 @@ class PPO:
         return log[0] / num_updates, log[1] / num_updates
 
     def _update_body(self):
+        for epoch in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                self._grad_part(i)
+                self._step_part()
+
+    def _grad_part(self, i):
+        """Forward, loss and backward of mini-batch i: fills the flat gradient and the scalar tail."""
         st, ac = self.storage, self.actor_critic
         sh, total, tc = self._sh, self._total, self._tc
         mb, A = self.mini_batch_size, st.actions.shape[-1]
         inv_count = 1.0 / (mb * self.world_size)
+        s = slice(i * mb, (i + 1) * mb)
+        obs_b, cobs_b = sh["obs"][s], sh["critic_obs"][s]
+        obs_t = sh["obs_t"][:, s] if tc else None
+        cobs_t = sh["critic_obs_t"][:, s] if tc else None
+        ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A, train=True, Xt=obs_t, ldxt=total)
+        ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, Xt=cobs_t, ldxt=total)
+        _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
+                  _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
+                  _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0,
+                  _ops.ptr(self._dval), _ops.ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+                  int(self.use_clipped_value_loss), inv_count, mb, inv_count, inv_count)
+        ac.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
+        ac.critic_engine.backward(self._dval, 1, self._dval_t if tc else None, mb)
+        ac._gviews["std"].copy_(self._scal[4:4 + A])
+
+    def _step_part(self):
+        """KL-adaptive learning rate (ppo.py:139-151) + clip + Adam on the (all-reduced) flat gradient."""
+        ac = self.actor_critic
+        mb = self.mini_batch_size
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
-        std_grad = ac._gviews["std"]
-        for epoch in range(self.num_learning_epochs):
-            for i in range(self.num_mini_batches):
-                s = slice(i * mb, (i + 1) * mb)
-                obs_b, cobs_b = sh["obs"][s], sh["critic_obs"][s]
-                obs_t = sh["obs_t"][:, s] if tc else None
-                cobs_t = sh["critic_obs_t"][:, s] if tc else None
-                ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A, train=True, Xt=obs_t, ldxt=total)
-                ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, Xt=cobs_t, ldxt=total)
-                _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
-                          _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
-                          _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0,
-                          _ops.ptr(self._dval), _ops.ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
-                          int(self.use_clipped_value_loss), inv_count, mb, inv_count, inv_count)
-                ac.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
-                ac.critic_engine.backward(self._dval, 1, self._dval_t if tc else None, mb)
-                std_grad.copy_(self._scal[4:4 + A])
-                if self.world_size > 1:
-                    # one collective per optimiser step: flat gradient + the scalar tail (KL / loss sums) ride together
-                    self._allreduce_grads()
-                _ops.call("go2_kl_adaptive_lr", _ops.ptr(self._scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
-                          _ops.ptr(self._lr), _ops.ptr(self._log), float(mb * self.world_size), 1.0)
-                _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
-                          ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), 1.0, _ops.ptr(self._scratch))
-                ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
+        _ops.call("go2_kl_adaptive_lr", _ops.ptr(self._scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
+                  _ops.ptr(self._lr), _ops.ptr(self._log), float(mb * self.world_size), 1.0)
+        _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
+                  ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), 1.0, _ops.ptr(self._scratch))
+        ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
 
     def _allreduce_grads(self):
         self._comm = dist_utils.allreduce_grads_and_tail(self.actor_critic.flat_grads, self._scal[:4], getattr(self, "_comm", None))

@@ -24,13 +24,13 @@ print(f"{'op':8s} {'M':>6s} {'N':>5s} {'K':>5s} {'us':>8s} {'TFLOP/s':>8s} {'GB/
 tot = {}
 for M in (24576, 4096):
     tot[M] = 0.0
-    for (N, K) in ((512, 48), (512, 264), (256, 512), (128, 256)):
+    for (N, K) in ((512, 48), (512, 264), (256, 512), (128, 256), (12, 128)):
         X = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / math.sqrt(K); b = torch.randn(N, device="cuda")
         Y = torch.empty(M, N, device="cuda"); Yt = torch.ones(N + 1, M, device="cuda")
         train = M == 24576
         us = graph_time(lambda: _ops.call("go2_linear_forward_tc", P(X), K, P(W), K, P(b), P(Y), N, P(Yt) if train else 0, M, M, N, K, 1))
         byts = 4 * (M * K + N * K + M * N * (2 if train else 1))
-        mult = 1 if (N, K) in ((512, 48), (512, 264)) else 2
+        mult = 1 if (N, K) in ((512, 48), (512, 264), (12, 128)) else 2
         tot[M] += us * mult
         print(f"{'fwd+T' if train else 'fwd':8s} {M:6d} {N:5d} {K:5d} {us:8.1f} {2*M*N*K/us/1e6:8.1f} {byts/us/1e3:8.0f}")
 M = 24576
