@@ -161,7 +161,9 @@ def main():
     env_cfg.seed = train_cfg.seed
     dev = f"cuda:{local}"
     env = Go2Robot(env_cfg, None, None, dev, True, env_offset=rank * N, num_envs_global=world * N)
-    runner = OnPolicyRunner(env, class_to_dict(train_cfg), log_dir=None, device=dev)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # the module prints its layer tables like the reference does; stdout carries the JSON line only
+        runner = OnPolicyRunner(env, class_to_dict(train_cfg), log_dir=None, device=dev)
     alg = runner.alg
     lib = _abi.load_library()
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
@@ -196,14 +198,15 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    l0 = lib.go2_kernel_launch_count()
+    from go2_rl_gym_b200.rl._ops import GraphSet
+    l0 = lib.go2_kernel_launch_count() + GraphSet.replayed_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         iteration(timed_kernel=True)
     ev1.record()
     sync()
-    launches = lib.go2_kernel_launch_count() - l0
+    launches = lib.go2_kernel_launch_count() + GraphSet.replayed_launches - l0      # direct launches + launches replayed from CUDA graphs
     clocks = sampler.stop()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
@@ -245,6 +248,37 @@ def main():
     h2d = STEPS_PER_ENV * N * 12 * 4
     d2h = STEPS_PER_ENV * (N * 12 * 4 + N * (45 + 263 + 1) * 4 + N) + 16
 
+    # ---- second roofline: the largest GEMM of the update (critic layer 0 forward + transposed copy, one mini-batch), timed alone
+    gemm = None
+    if rank == 0:
+        from go2_rl_gym_b200.rl import _ops
+        Mg, Ng, Kg = 6 * N, 512, 264
+        Xg, Wg, bg = torch.randn(Mg, Kg, device=dev), torch.randn(Ng, Kg, device=dev) / 16, torch.randn(Ng, device=dev)
+        Yg, Ytg = torch.empty(Mg, Ng, device=dev), torch.ones(Ng + 1, Mg, device=dev)
+        run = lambda: _ops.call("go2_linear_forward_tc", Xg.data_ptr(), Kg, Wg.data_ptr(), Kg, bg.data_ptr(), Yg.data_ptr(), Ng, Ytg.data_ptr(), Mg, Mg, Ng, Kg, 1)
+        for _ in range(5):
+            run()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(20):
+            run()
+        g1.record()
+        torch.cuda.synchronize()
+        us = g0.elapsed_time(g1) / 20 * 1e3
+        gbytes = 4.0 * (Mg * Kg + Ng * Kg + 2 * Mg * Ng)          # operands read once, both output copies written once
+        gemm = {"kernel": "go2::gemm_tf32_persist_kernel<128> (Y = ELU(X W^T + b), + transposed copy)", "shape": [Mg, Ng, Kg], "bound": "hbm",
+                "achieved": gbytes / us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbytes / us / 1e3 / peaks["hbm_gbs"],
+                "kernel_us": us, "tflops": 2.0 * Mg * Ng * Kg / us / 1e6,
+                "note": "fp32 activations make every MLP GEMM of the update HBM/L2-bound (33 flop/B); 20 back-to-back launches, includes host launch gaps"}
+    traffic = None
+    try:
+        d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_kernel_dram.json")))
+        if d.get("num_envs") == N:
+            traffic = d["dram_bytes_read"] + d["dram_bytes_write"]          # ncu --set full capture of this build (see profiles/)
+    except Exception:  # noqa: BLE001
+        pass
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu_worker(N, 1, 3, 20.0, 150.0)
@@ -260,10 +294,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "go2::step_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                              "kernel_us": kern_ms * 1e3, "env_steps_per_s_kernel_only": N / (kern_ms * 1e-3),
                              "note": "latency/issue-bound serial 13-body recursion; HBM fraction is structurally tiny (SURVEY 7.2)"},
-                "clocks": clocks, "cpu_baseline": cpu}
+                "roofline_gemm": gemm, "clocks": clocks, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -80,7 +80,7 @@ class Go2EnvBuffers(C.Structure):
 PTR_FIELDS = tuple(_PTR_FIELDS)
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgo2b200.so")
+_LIB_PATH = os.environ.get("GO2_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgo2b200.so")     # GO2_B200_LIB: tuning builds of the same library
 
 
 def library_path():

@@ -26,7 +26,7 @@
 
 #if defined(__CUDACC__)
 #define GO2_LANES_BEGIN {
-#define GO2_LANES_END } __syncwarp();
+#define GO2_LANES_END } go2_phase_sync(L);
 #define GO2_FMUL(a, b) __fmul_rn((a), (b))
 #define GO2_FADD(a, b) __fadd_rn((a), (b))
 #define GO2_LDG(p) __ldg(p)
@@ -241,7 +241,24 @@ struct Lane {
   // collider lanes
   float n[3], Winv[6], vt, mu, r[3], p[3], gcount;
   int body, act;
+  // phase barrier: 0 = warp-level (__syncwarp); otherwise the number of threads of a CTA-wide named barrier that keeps the
+  // warps of one CTA on the same stretch of code (instruction-cache sharing; same results either way)
+  int nsync;
+  int nmid;      // same, at three more points inside a substep (GO2_MID_SYNC)
+  int ncoarse;   // same, but only at the few GO2_COARSE_SYNC points (substep boundaries): loose re-alignment of the CTA's warps
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void go2_phase_sync(const Lane& L) {
+  if (L.nsync) asm volatile("bar.sync 1, %0;" ::"r"(L.nsync) : "memory");
+  else __syncwarp();
+}
+#define GO2_COARSE_SYNC() do { if (L.ncoarse) asm volatile("bar.sync 2, %0;" ::"r"(L.ncoarse) : "memory"); } while (0)
+#define GO2_MID_SYNC() do { if (L.nmid) asm volatile("bar.sync 3, %0;" ::"r"(L.nmid) : "memory"); } while (0)
+#else
+#define GO2_COARSE_SYNC() do { } while (0)
+#define GO2_MID_SYNC() do { } while (0)
+#endif
 
 struct StepCtx {
   const Go2EnvConfig* cfg; const Go2Model* mdl; const Go2EnvBuffers* buf; const Go2StepParams* sp;
@@ -536,6 +553,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
     }
   GO2_LANES_END
   // ---- S5: leg lanes: pass 3, unconstrained velocities, mobility recursion
+  GO2_MID_SYNC();
   GO2_LANES_BEGIN
     if (lane < 4) {
       V6 a0; ld6(S.a0, a0);
@@ -611,6 +629,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
     }
   GO2_LANES_END
   // ---- Jacobi sweeps with exact propagation through the tree
+  GO2_MID_SYNC();
   for (int it = 0; it < C->solver_iters; ++it) {
     GO2_LANES_BEGIN
       if (L.act) {
@@ -680,6 +699,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
     GO2_LANES_END
   }
   // ---- S12: final velocities, joint velocity clamp, integration, contact force report
+  GO2_MID_SYNC();
   GO2_LANES_BEGIN
     if (lane < GO2_NUM_DOF) {
       float x = S.qdm[lane] + S.dqd[lane], vl = M->vel_limit[lane];
@@ -975,9 +995,11 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
   const uint32_t ge = (uint32_t)(C->env_offset + e);
   load_env(GO2_LANE_PASS, S, X, e);
   for (int sub = 0; sub < C->decimation; ++sub) {
+    GO2_COARSE_SYNC();
     compute_torques(GO2_LANE_PASS, S, X, sub);
     physics_substep(GO2_LANE_PASS, S, X, e, sub == C->decimation - 1);
   }
+  GO2_COARSE_SYNC();
   feet_kinematics(GO2_LANE_PASS, S, X);
   // ---- post_physics_step (legged_robot.py:102-142)
   GO2_LANES_BEGIN
@@ -1099,7 +1121,11 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
     if (lane < GO2_NUM_REW) B->episode_sums[(size_t)e * GO2_NUM_REW + lane] += S.termv[lane];
     if (lane == 31) B->rew_buf[e] = S.rew;
   GO2_LANES_END
+#if defined(__CUDACC__)
+  { const int ns = L.nsync; L.nsync = 0; if (S.reset) reset_phases(GO2_LANE_PASS, S, X, e, false); L.nsync = ns; }   // per-env branch: warp-level phases
+#else
   if (S.reset) reset_phases(GO2_LANE_PASS, S, X, e, false);
+#endif
   GO2_LANES_BEGIN
     if (lane == 0) {
       if (C->push_robots && (S.ep_len % C->push_interval == 0)) {  // _push_robots, legged_robot.py:709-724

@@ -76,8 +76,10 @@ class GraphSet:
     graphs; a failed capture makes that key eager for good.  Collectives are never captured: with world_size > 1 the callers cut
     the optimiser step into [gradient graph] -> eager NCCL all-reduce -> [Adam graph]."""
 
+    replayed_launches = 0     # kernel launches issued through graph replays (the library's own counter only sees direct launches)
+
     def __init__(self):
-        self._g, self._warm, self._failed = {}, set(), set()
+        self._g, self._warm, self._failed, self._n = {}, set(), set(), {}
         self.enabled = os.environ.get("GO2_GRAPH", "1") != "0"
 
     def run(self, key, fn):
@@ -85,6 +87,7 @@ class GraphSet:
             return fn()
         g = self._g.get(key)
         if g is not None:
+            GraphSet.replayed_launches += self._n[key]
             return g.replay()
         if key not in self._warm:
             self._warm.add(key)
@@ -92,6 +95,7 @@ class GraphSet:
         import warnings
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        n0 = lib().go2_kernel_launch_count()
         try:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 fn()
@@ -100,7 +104,8 @@ class GraphSet:
             warnings.warn(f"CUDA-graph capture of {key} failed ({type(e).__name__}: {e}); using eager launches")
             torch.cuda.synchronize()
             return fn()
-        self._g[key] = g
+        self._g[key], self._n[key] = g, lib().go2_kernel_launch_count() - n0     # launches counted during capture did not run
+        GraphSet.replayed_launches += self._n[key]
         g.replay()
 
 
