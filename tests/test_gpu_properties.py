@@ -1,0 +1,94 @@
+"""Size-independent properties of the CUDA env step at BASELINE.json's full sizes (65 536 envs), determinism, and the
+shard == slice-of-the-whole rule of the multi-GPU layout, all through the C ABI on one GPU."""
+import math
+
+import pytest
+import torch
+
+from go2_rl_gym_b200.envs.env_arrays import EnvArrays
+from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+from cuda_util import CudaEnv
+
+pytestmark = pytest.mark.gpu
+KEYS = ("root_states", "dof_pos", "dof_vel", "obs_buf", "privileged_obs_buf", "rew_buf", "commands", "terrain_levels", "reset_buf",
+        "time_out_buf", "episode_length_buf", "contact_forces", "measured_heights", "episode_sums", "torques")
+
+
+def _env(N, seed=3, offset=0, n_global=None, start_iter=800):
+    cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = seed
+    A = EnvArrays(cfg, "cuda:0", num_envs=N, env_offset=offset, num_envs_global=n_global or N, seed=seed)
+    e = CudaEnv(A)
+    e.common_step_counter = 24 * start_iter
+    e.reset_all()
+    return cfg, A, e
+
+
+def test_invariants_at_full_size():
+    N = 65536
+    cfg, A, e = _env(N)
+    T = A.tensors
+    T["episode_length_buf"].copy_(torch.randint(0, 1250, (N,), device="cuda"))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lim_lo = torch.tensor([A.model.q_lower[j] for j in range(12)], device="cuda")
+    lim_hi = torch.tensor([A.model.q_upper[j] for j in range(12)], device="cuda")
+    vel_lim = torch.tensor([A.model.vel_limit[j] for j in range(12)], device="cuda")
+    eff = torch.tensor([A.model.effort[j] for j in range(12)], device="cuda")
+    n_reset = n_tout = 0
+    viol_max = viol_frac = 0.0
+    prev_len = T["episode_length_buf"].clone()
+    for it in range(40):
+        e.step(torch.randn(N, 12, device="cuda", generator=g))
+        for k in ("root_states", "dof_pos", "dof_vel", "obs_buf", "privileged_obs_buf", "rew_buf", "commands", "contact_forces", "torques"):
+            assert torch.isfinite(T[k]).all(), (it, k)
+        q = T["root_states"][:, 3:7]
+        assert (q.norm(dim=1) - 1).abs().max() < 1e-4                                         # unit quaternions
+        assert T["obs_buf"].abs().max() <= 100.0 and T["privileged_obs_buf"].abs().max() <= 100.0   # clip_observations
+        reset, tout, ln = T["reset_buf"].bool(), T["time_out_buf"].bool(), T["episode_length_buf"]
+        assert (tout & ~reset).sum() == 0                                                     # time-outs are resets (legged_robot.py:170-178)
+        assert (ln[reset] == 0).all() and (ln[~reset] == prev_len[~reset] + 1).all()         # counters: +1 or back to 0
+        assert (prev_len[tout] + 1 > 1250).all()                                              # a time-out means the horizon was passed
+        assert T["terrain_levels"].min() >= 0 and T["terrain_levels"].max() < cfg.terrain.num_rows
+        viol = torch.maximum(torch.relu(T["dof_pos"] - lim_hi), torch.relu(lim_lo - T["dof_pos"]))
+        viol_max = max(viol_max, float(viol.max()))
+        viol_frac = max(viol_frac, float((viol > 0.1).float().mean()))
+        assert (T["dof_vel"].abs() <= vel_lim + 1e-3).all()                                    # URDF joint velocity limits
+        n_reset += int(reset.sum()); n_tout += int(tout.sum())
+        prev_len = ln.clone()
+    assert n_reset > 0 and n_tout > 0                                                         # both paths were exercised
+    # joint limits are unilateral velocity rows (not hard clamps) and _reset_dofs draws q0 * U[0.5, 1.5] unclamped (legged_robot.py:620-634:
+    # the calf can start 0.088 rad past its upper limit): under N(0,1) actions overshoot stays rare and bounded
+    print(f"joint-limit overshoot: max {viol_max:.3f} rad, worst per-step fraction of joints > 0.1 rad: {viol_frac:.2e}")
+    assert viol_max < 0.6 and viol_frac < 1e-4
+    cmd = T["commands"]
+    assert cmd[:, 0].abs().max() <= 2.0 + 1e-6 and cmd[:, 1].abs().max() <= 1.0 + 1e-6        # within the (curriculum-widened) ranges
+
+
+def test_same_seed_same_bits():
+    N = 8192
+    outs = []
+    for _ in range(2):
+        cfg, A, e = _env(N, seed=11)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        for _ in range(12):
+            e.step(torch.randn(N, 12, device="cuda", generator=g))
+        outs.append({k: A.tensors[k].clone() for k in KEYS})
+        del e
+    for k in KEYS:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_shards_equal_slices_of_the_whole():
+    NG, R = 4096, 4                                           # 4 ranks x 1024 envs, global ids for terrain type / level / RNG keys
+    cfg, A, e = _env(NG, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = [torch.randn(NG, 12, device="cuda", generator=g) for _ in range(10)]
+    for a in acts:
+        e.step(a)
+    for r in range(R):
+        n = NG // R
+        _, As, es = _env(n, seed=5, offset=r * n, n_global=NG)
+        for a in acts:
+            es.step(a[r * n:(r + 1) * n])
+        for k in KEYS:
+            assert torch.equal(As.tensors[k], A.tensors[k][r * n:(r + 1) * n]), (r, k)
+        del es
