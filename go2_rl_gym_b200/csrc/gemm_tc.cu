@@ -39,6 +39,7 @@ struct TcParams {
   int epi;
   long split_stride;       // elements between consecutive split slices of C
   long long* dbg;          // optional [gridDim.x*gridDim.y][8] clock64 stamps (profiling aid)
+  int mn_major;            // persistent kernel only: A [K, M] and B [K, N] row-major (contraction index = rows)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -100,6 +101,19 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// MN-major tf32 operand tile (the only layout tcgen05 accepts for it: 128B swizzle with 32-byte atoms, written by TMA mode
+// SWIZZLE_128B_ATOM_32B): boxes of [32 contraction rows][32 MN elements = 128 B]; 4-row groups 512 B apart (stride offset),
+// 32-element MN groups one 4 KB box apart (leading offset)
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128_32b(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;                  // leading byte offset: next group of 32 MN elements
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: next group of 4 contraction rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -289,6 +303,7 @@ struct TcParamsP {
   int m_tiles, n_tiles, splits, kb_per_split, total_kb;
   int rows_pad;            // rows between consecutive split slices in the C map (multiple of 128)
   int stages;              // operand ring depth
+  int mn_major;            // wgrad from row-major operands: A = dZ[batch, out], B = X[batch, in] are MN-major (contraction index = rows)
   const float* bias;
   int epi, has_c, has_ct, has_aux;
 };
@@ -358,8 +373,15 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
-          tma_load_2d(&tmA, full_bar + s, sa, (kb0 + kb) * TC_BK, mt * TC_BM);
-          tma_load_2d(&tmB, full_bar + s, sa + A_BYTES, (kb0 + kb) * TC_BK, nt * BN);
+          if (!p.mn_major) {
+            tma_load_2d(&tmA, full_bar + s, sa, (kb0 + kb) * TC_BK, mt * TC_BM);
+            tma_load_2d(&tmB, full_bar + s, sa + A_BYTES, (kb0 + kb) * TC_BK, nt * BN);
+          } else {   // one [32 rows][32 features] box per 32-wide feature group
+#pragma unroll
+            for (int g = 0; g < TC_BM / 32; ++g) tma_load_2d(&tmA, full_bar + s, sa + g * 4096, mt * TC_BM + 32 * g, (kb0 + kb) * TC_BK);
+#pragma unroll
+            for (int g = 0; g < BN / 32; ++g) tma_load_2d(&tmB, full_bar + s, sa + A_BYTES + g * 4096, nt * BN + 32 * g, (kb0 + kb) * TC_BK);
+          }
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -381,9 +403,16 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(full_bar + s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
+          if (!p.mn_major) {
+            const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+          } else {   // 8 contraction rows per instruction = 1024 B further into every box
+            const uint64_t da = make_desc_mnmajor_sw128_32b(sa), db = make_desc_mnmajor_sw128_32b(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDESC | (1u << 15) | (1u << 16), (kb | k) ? 1u : 0u);
+          }
           umma_commit(empty_bar + s);
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -555,7 +584,7 @@ static EncodeTiledFn get_encode() {
 }
 // row-major [rows, cols] fp32 with leading dimension ld (elements); box = box_cols floats x box_rows; 128B swizzle when the box is
 // one swizzle atom wide (32 floats), dense otherwise; zero OOB fill on loads, clipping on stores
-static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, int box_rows, int box_cols = TC_BK) {
+static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, int box_rows, int box_cols = TC_BK, bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(4, "cuTensorMapEncodeTiled unavailable");
   if (((uintptr_t)ptr & 15) || ((ld * 4) & 15)) return set_error(5, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
@@ -564,7 +593,8 @@ static int make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_cols == TC_BK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : box_cols == TC_BK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(6, "cuTensorMapEncodeTiled failed");
   return 0;
@@ -647,9 +677,10 @@ static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, c
   pp.bias = p.bias; pp.epi = p.epi; pp.has_c = p.C != nullptr; pp.has_ct = p.Ct != nullptr; pp.has_aux = p.epi == TC_EPI_MUL_ELU_GRAD;
   if (splits > 1 && p.split_stride != (long)pp.rows_pad * p.ldc) return set_error(5, "gemm_tc_persist: split stride must be roundup(M,128) * ldc");
   CUtensorMap ta, tb, tc, tct, taux;
-  int rc = make_map(&ta, A, p.M, p.K, lda, TC_BM);
+  pp.mn_major = p.mn_major;
+  int rc = p.mn_major ? make_map(&ta, A, p.K, p.M, lda, 32, 32, true) : make_map(&ta, A, p.M, p.K, lda, TC_BM);
   if (rc) return rc;
-  rc = make_map(&tb, B, p.N, p.K, ldb, BN);
+  rc = p.mn_major ? make_map(&tb, B, p.K, p.N, ldb, 32, 32, true) : make_map(&tb, B, p.N, p.K, ldb, BN);
   if (rc) return rc;
   tc = ta; tct = ta; taux = ta;
   if (p.C) { rc = make_map(&tc, p.C, splits > 1 ? (long)splits * pp.rows_pad : p.M, p.N, p.ldc, TC_BM); if (rc) return rc; }
@@ -732,6 +763,35 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
   if (!workspace || (long)rows_slice * ldp > workspace_floats) return set_error(5, "go2_linear_wgrad_tc: workspace too small");
   p.C = workspace; p.ldc = ldp; p.split_stride = (long)rows_slice * ldp;
   int rc = gemm_tc(dZt, lddzt, Xt, ldxt, p, splits, st);
+  if (rc) return rc;
+  const long n = (long)N * (ldp / 4);
+  tc_splitk_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 8), 0, st>>>(workspace, dW, N, splits, ldp, p.split_stride, lddw, K, k_real, db);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// dW[N,K] = dZ[M,N]^T X[M,K] straight from the ROW-MAJOR activations / gradients (MN-major tf32 operands: no transposed copies).
+// db != NULL: X carries a column of ones at column K (ldx > K), so column K of the product is the bias gradient.
+int go2_linear_wgrad_tc_rm(const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K, float* workspace,
+                           long workspace_floats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int k_real = K;
+  if (db) K = K + 1;
+  if (!workspace) return set_error(5, "go2_linear_wgrad_tc_rm: workspace required");
+  const long ldp = (K + 3) / 4 * 4;
+  const int total_kb = (M + TC_BK - 1) / TC_BK;
+  const int rows_pad = (N + TC_BM - 1) / TC_BM * TC_BM;
+  const int BN = persist_bn(K);
+  const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);
+  int splits = max(1, min(min(total_kb / 8, 48), (sm_count() + tiles / 2) / tiles));
+  while (splits > 1 && (long)splits * rows_pad * ldp > workspace_floats) --splits;
+  if ((long)rows_pad * ldp > workspace_floats) return set_error(5, "go2_linear_wgrad_tc_rm: workspace too small");
+  splits = (total_kb + (total_kb + splits - 1) / splits - 1) / ((total_kb + splits - 1) / splits);
+  TcParams p{};
+  p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN; p.mn_major = 1;
+  p.C = workspace; p.ldc = ldp; p.split_stride = (long)rows_pad * ldp;
+  int rc = gemm_tc_persist(dZ, lddz, X, ldx, p, splits, st);
   if (rc) return rc;
   const long n = (long)N * (ldp / 4);
   tc_splitk_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 8), 0, st>>>(workspace, dW, N, splits, ldp, p.split_stride, lddw, K, k_real, db);

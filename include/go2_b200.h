@@ -197,6 +197,11 @@ int go2_linear_wgrad_simt(const float* dY, int lddy, const float* X, int ldx, fl
 /* tensor-core wgrad from the transposed copies dZt [N,M], Xt [K,M] (contraction over the M rows is then K-major for both operands);
  * db != NULL: Xt has one extra row of ones (row K) and db[N] receives the bias gradient from the same contraction */
 int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, float* dW, int lddw, float* db, int M, int N, int K, float* workspace, long workspace_floats, void* stream);
+/* The same weight gradient straight from the ROW-MAJOR tensors (MN-major tf32 operands through TMA's 128B / 32-byte-atom swizzle):
+ * dW[N,K] = dZ[M,N]^T X[M,K]; with db != NULL X has a column of ones at column K (ldx > K) and db[N] = column sums of dZ.
+ * Replaces autograd's weight gradient of nn.Linear (rsl_rl/algorithms/ppo.py:175 loss.backward()).  workspace is required. */
+int go2_linear_wgrad_tc_rm(const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K,
+                           float* workspace, long workspace_floats, void* stream);
 /* out[cols,rows] = in[rows,cols]^T */
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
 /* db[N] = column sums of dY[M,N] */

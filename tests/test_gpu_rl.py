@@ -89,6 +89,30 @@ def test_linear_backward_tensor_core(M, N, K):
         assert torch.equal(dXt.t().contiguous(), dX)
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 256, 512), (24576, 128, 256), (777 * 4, 12, 128), (24576, 512, 263), (6148, 2048, 256), (4099, 32, 256), (24576, 1, 128)])
+def test_wgrad_from_row_major_operands(M, N, K):
+    """MN-major tf32 operands (TMA SWIZZLE_128B_ATOM_32B + UMMA 128B_BASE32B descriptors): dW = dZ^T X and db from the ones column,
+    no transposed copies.  Same tolerance as the K-major path."""
+    from go2_rl_gym_b200.rl import _ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    X = torch.nn.functional.elu(torch.randn(M, K, generator=g))
+    dY = torch.randn(M, N, generator=g)
+    ldx = (K + 1 + 3) // 4 * 4
+    Xp = torch.zeros(M, ldx, device="cuda"); Xp[:, :K] = X.cuda(); Xp[:, K] = 1.0
+    ldy = (N + 3) // 4 * 4
+    dYp = torch.zeros(M, ldy, device="cuda"); dYp[:, :N] = dY.cuda()
+    dW, db = torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda")
+    work = torch.empty(64 * ((N + 127) // 128 * 128) * ((K + 4) // 4 * 4), device="cuda")
+    _ops.call("go2_linear_wgrad_tc_rm", dYp.data_ptr(), ldy, Xp.data_ptr(), ldx, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
+    torch.cuda.synchronize()
+    assert _rel(dW.cpu(), dY.t() @ X) < 2e-3, _rel(dW.cpu(), dY.t() @ X)
+    assert _rel(db.cpu(), dY.sum(0)) < 2e-3
+    dW2 = torch.zeros(N, K, device="cuda")
+    _ops.call("go2_linear_wgrad_tc_rm", dYp.data_ptr(), ldy, Xp.data_ptr(), ldx, dW2.data_ptr(), K, 0, M, N, K, work.data_ptr(), work.numel())
+    torch.cuda.synchronize()
+    assert _rel(dW2.cpu(), dY.t() @ X) < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 512, 45), (8192, 256, 512), (24576, 128, 256), (777, 12, 128)])
 def test_linear_backward(M, N, K):
     from go2_rl_gym_b200.rl import _ops
