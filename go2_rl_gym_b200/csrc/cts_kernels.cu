@@ -23,7 +23,7 @@ __global__ void concat2_kernel(const float* __restrict__ a, int wa, long lda, co
   const int w = wa + wb;
   for (int c0 = 0; c0 < ld; c0 += 32) {
     const int c = c0 + threadIdx.x;
-    float v = 0.0f;
+    float v = (c == w) ? 1.0f : 0.0f;                  // padding: column w = 1 (bias-gradient "ones" column), the rest 0
     if (i < n && c < w) v = c < wa ? a[i * lda + c] : b[i * ldb + (c - wa)];
     if (i < n && c < ld) out[i * ld + c] = v;
     if (out_t) {

@@ -212,7 +212,9 @@ __global__ void adv_normalize_kernel(float* __restrict__ adv, long n, const doub
   adv[i] = (adv[i] - (float)mean) / (sd + 1e-8f);
 }
 
-// mini_batch_generator gather (rollout_storage.py:173-181): dst[i, 0:w] = src[idx[i], 0:w], dst row stride ldd (zero padded)
+// mini_batch_generator gather (rollout_storage.py:173-181): dst[i, 0:w] = src[idx[i], 0:w], dst row stride ldd; padding columns are zero
+// except column w, which is 1 (the "ones" column that yields the bias gradient in the row-major wgrad; the first layer's padded weight
+// has zeros there, so the forward pass does not see it)
 __global__ void gather_rows_kernel(const float* __restrict__ src, int w, const int64_t* __restrict__ idx, float* __restrict__ dst, int ldd, long n,
                                    float* __restrict__ dst_t) {
   __shared__ float tile[8][33];
@@ -220,7 +222,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int w, const i
   const long s = (i < n) ? (idx ? idx[i] : i) : 0;
   for (int c0 = 0; c0 < ldd; c0 += 32) {
     const int c = c0 + threadIdx.x;
-    float v = (i < n && c < w) ? src[s * w + c] : 0.0f;
+    float v = (i < n && c < w) ? src[s * w + c] : (c == w ? 1.0f : 0.0f);
     if (i < n && c < ldd && dst) dst[i * ldd + c] = v;
     if (dst_t) {  // transposed copy dst_t[c][i] (row pitch n), staged through shared memory so both sides stay coalesced
       tile[threadIdx.y][threadIdx.x] = v;

@@ -114,19 +114,24 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+def pad_in(width):
+    """Row pitch of a tensor-core MLP input of `width` features: room for the ones column, multiple of 4 floats (16 bytes)."""
+    return _pad4(width + 1)
+
+
 class MlpEngine:
     """A chain of Linear(+ELU) layers on views of a flat parameter vector, evaluated by the library's GEMM kernels.
 
     dims = [in, h1, ..., out]; ELU after every layer but the last (actor_critic.py:58-79), or after the last one too when
-    last_act (the experts' backbone, modules/utils.py:81).  Tensor-core path (tcgen05, tf32 multiply / fp32 accumulate): every
-    contraction is K-major, so
-      * forward needs X [M, in] and W [out, in] with 16-byte row pitches -> the first layer uses a zero-padded copy of its
-        weight (refreshed after each optimiser step) and callers pass inputs whose leading dimension is a multiple of 4;
-      * dgrad needs W^T (refreshed with the weights) and writes dZ both row-major and transposed;
-      * wgrad contracts over the batch rows and therefore reads the TRANSPOSED activations / gradients, which the forward and
-        dgrad epilogues (and the gather / concat / loss kernels for the two ends of the chain) emit next to the row-major
-        copies; each transposed activation carries one extra row of ones so the bias gradient falls out of the same GEMM.
-    Layers whose shapes cannot meet the TMA alignment rules (a 1-wide output in dgrad) run on the CUDA-core GEMM."""
+    last_act (the experts' backbone, modules/utils.py:81).  Tensor-core path (tcgen05, tf32 multiply / fp32 accumulate):
+      * forward / dgrad are K-major contractions: X [M, in] and W [out, in] (dgrad: W^T, refreshed with the weights) need
+        16-byte row pitches -> the first layer uses a zero-padded copy of its weight (refreshed after each optimiser step) and
+        inputs whose leading dimension is not a multiple of 4 go through a padded staging copy;
+      * wgrad contracts over the batch rows and reads the ROW-MAJOR activations / gradients as MN-major operands
+        (go2_linear_wgrad_tc_rm): no transposed copies anywhere;
+      * every hidden activation buffer is [rows, d + 4] with column d = 1, and padded inputs carry a 1 in their first padding
+        column (x_ones), so the bias gradient is one more column of the same wgrad GEMM.
+    Layers whose shapes cannot meet the TMA alignment rules (the critic's 1-wide head) run on CUDA-core kernels."""
 
     def __init__(self, dims, weights, biases, gweights, gbiases, max_rows, device, train_rows=0, last_act=False, need_dx=False):
         self.dims, self.L = list(dims), len(dims) - 1
@@ -135,14 +140,12 @@ class MlpEngine:
         self.tc = use_tc()
         dev = device
         hidden = dims[1:] if last_act else dims[1:-1]
-        self.acts = [torch.empty(max_rows, d, device=dev) for d in hidden]
-        self.actsT = [torch.ones(d + 1, train_rows, device=dev) for d in hidden] if (train_rows and self.tc) else None
+        self.acts = [torch.ones(max_rows, d + 4, device=dev) for d in hidden]       # column d stays 1
         hmax = max(dims[1:-1]) if self.L > 1 else dims[-1]
         self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(2)]
-        self.dbufT = [torch.empty(hmax, max(train_rows, 1), device=dev) for _ in range(2)] if (train_rows and self.tc) else None
         self.work = torch.empty(64 * max(_pad4(dims[l] + 1) * ((dims[l + 1] + 127) // 128 * 128) for l in range(self.L)), device=dev)
-        self.kpad0 = _pad4(dims[0])
-        self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if (self.tc and self.kpad0 != dims[0]) else None
+        self.kpad0 = pad_in(dims[0]) if self.tc else dims[0]               # room for the ones column
+        self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if self.tc else None
         first_wt = 0 if need_dx else 1
         self.Wt = ([None] * first_wt + [torch.zeros(dims[l], _pad4(dims[l + 1]), device=dev) for l in range(first_wt, self.L)]) if self.tc else None
         self._xpad = torch.zeros(max_rows, self.kpad0, device=dev) if self.tc else None
@@ -156,8 +159,7 @@ class MlpEngine:
         if not self.tc:
             return
         if self._dirty_w0:
-            if self.W0p is not None:
-                self.W0p[:, :self.dims[0]].copy_(self.W[0])
+            self.W0p[:, :self.dims[0]].copy_(self.W[0])
             self._dirty_w0 = False
         if need_wt and self._dirty_wt:
             for l in range(0 if self.need_dx else 1, self.L):
@@ -166,66 +168,67 @@ class MlpEngine:
 
     @property
     def out(self):
-        """Last-layer activation buffer (last_act engines)."""
+        """Last-layer activation buffer (last_act engines): [rows, dims[-1] + 4], leading dimension ld_out."""
         return self.acts[-1]
 
     @property
-    def outT(self):
-        return self.actsT[-1]
+    def ld_out(self):
+        return self.acts[-1].shape[1]
 
-    def forward(self, X, ldx, M, out=None, ld_out=0, train=False, Xt=None, ldxt=0):
-        """out[M, dims[-1]] = MLP(X[M, dims[0]]).  train=True keeps what backward() needs (Xt = X^T [in (+ ones row), M] for wgrad).
-        last_act engines write their output (and its transpose) into self.out / self.outT."""
+    def forward(self, X, ldx, M, out=None, ld_out=0, train=False, x_ones=False, **_unused):
+        """out[M, dims[-1]] = MLP(X[M, dims[0]]).  train=True keeps what backward() needs.  x_ones: X[:, dims[0]] == 1 (ldx > dims[0]),
+        e.g. rows written by go2_gather_rows / go2_concat2 with a padded pitch.  last_act engines write their output into self.out."""
         assert M <= self.max_rows and (not train or M <= self.train_rows)
         self._refresh(need_wt=train)
         src, lds = X, ldx
-        if self.tc and (ldx % 4 or X.data_ptr() % 16):  # inputs straight from the env rows (ld 45 / 263): zero-padded staging copy
+        if self.tc and (ldx % 4 or X.data_ptr() % 16 or ldx < self.kpad0):
+            # inputs straight from the env rows (ld 45 / 263): padded staging copy (zeros, ones column at dims[0])
             call("go2_gather_rows", ptr(X), self.dims[0], 0, ptr(self._xpad), self.kpad0, 0, M)
-            src, lds = self._xpad, self.kpad0
-        self._Xin, self._ldxin = src, lds
+            src, lds, x_ones = self._xpad, self.kpad0, True
+        self._Xin, self._ldxin, self._x_ones = src, lds, x_ones
         for l in range(self.L):
             last = l == self.L - 1
             if last and not self.last_act:
-                dst, ldd, dstT, lddT = out, ld_out, None, 0
+                dst, ldd = out, ld_out
             else:
-                dst, ldd = self.acts[l], self.dims[l + 1]
-                dstT, lddT = (self.actsT[l], self.train_rows) if (train and self.tc) else (None, 0)
+                dst, ldd = self.acts[l], self.dims[l + 1] + 4
             act = 0 if (last and not self.last_act) else 1
             if self.tc:
-                W, ldw = (self.W0p, self.kpad0) if (l == 0 and self.W0p is not None) else (self.W[l], self.dims[l])
-                call("go2_linear_forward_tc", ptr(src), lds, ptr(W), ldw, ptr(self.b[l]), ptr(dst), ldd, ptr(dstT), lddT, M, self.dims[l + 1],
-                     self.dims[l], act)
+                # layer 0 contracts over the padded width: the padding columns of W0p are zero
+                W, ldw, K = (self.W0p, self.kpad0, self.kpad0) if l == 0 else (self.W[l], self.dims[l], self.dims[l])
+                call("go2_linear_forward_tc", ptr(src), lds, ptr(W), ldw, ptr(self.b[l]), ptr(dst), ldd, 0, 0, M, self.dims[l + 1], K, act)
             else:
                 call("go2_linear_forward_simt", ptr(src), lds, ptr(self.W[l]), self.dims[l], ptr(self.b[l]), ptr(dst), ldd, 0, 0, M,
                      self.dims[l + 1], self.dims[l], act)
             src, lds = dst, ldd
-        self._M, self._Xt, self._ldxt = M, Xt, ldxt
+        self._M = M
 
-    def backward(self, dY, lddy, dYt=None, lddyt=0):
+    def backward(self, dY, lddy, *_unused):
         """Overwrites gW/gb with d loss / d params for the rows of the last forward(train=True).
-        dY [M, out] = gradient w.r.t. the LAST LINEAR's output (for last_act engines the caller has already applied ELU');
-        dYt [out, M] its transpose (tensor-core wgrad).  With need_dx the gradient w.r.t. the input lands in self.dx [M, pad4(in)]."""
+        dY [M, out] = gradient w.r.t. the LAST LINEAR's output (for last_act engines the caller has already applied ELU').
+        With need_dx the gradient w.r.t. the input lands in self.dx [M, kpad0]."""
         M = self._M
-        d, ldd, dT, lddT = dY, lddy, dYt, lddyt
+        d, ldd = dY, lddy
         for l in range(self.L - 1, -1, -1):
             n_out, n_in = self.dims[l + 1], self.dims[l]
-            xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in)
-            if self.tc and dT is not None and (l > 0 or self._Xt is not None):
-                xT, ldxT = (self._Xt, self._ldxt) if l == 0 else (self.actsT[l - 1], self.train_rows)   # both end with a row of ones
-                call("go2_linear_wgrad_tc", ptr(dT), lddT, ptr(xT), ldxT, ptr(self.gW[l]), n_in, ptr(self.gb[l]), M, n_out, n_in, ptr(self.work),
-                     self.work.numel())
+            xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in + 4)
+            ones = self._x_ones if l == 0 else True
+            if self.tc and ldd % 4 == 0 and d.data_ptr() % 16 == 0:
+                if not ones:
+                    call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
+                call("go2_linear_wgrad_tc_rm", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]) if ones else 0, M, n_out, n_in,
+                     ptr(self.work), self.work.numel())
             else:
                 call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
                 call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())
             if l > 0:
-                nxt, nxtT = self.dbuf[l % 2], (self.dbufT[l % 2] if self.dbufT is not None else None)
+                nxt = self.dbuf[l % 2]
                 if self.tc and n_out % 4 == 0:
-                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], ptr(self.acts[l - 1]), n_in, ptr(self.actsT[l - 1]), self.train_rows,
-                         ptr(nxt), n_in, ptr(nxtT), self.train_rows, M, n_out, n_in)
+                    call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], ptr(self.acts[l - 1]), n_in + 4, 0, 0,
+                         ptr(nxt), n_in, 0, 0, M, n_out, n_in)
                 else:
-                    call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in, ptr(nxt), n_in,
-                         ptr(nxtT), self.train_rows if nxtT is not None else 0, M, n_out, n_in)
-                d, ldd, dT, lddT = nxt, n_in, nxtT, self.train_rows
+                    call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in + 4, ptr(nxt), n_in, 0, 0, M, n_out, n_in)
+                d, ldd = nxt, n_in
             elif self.need_dx:
                 if self.tc and n_out % 4 == 0:
                     call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[0]), self.Wt[0].shape[1], 0, 0, 0, 0, ptr(self.dx), self.kpad0, 0, 0, M, n_out, n_in)

@@ -68,12 +68,10 @@ class CTS:
         rows = max(N, self.mb)
         self._lat = z(rows, D)
         self._lat_t = z(max(self.sm, 1), D)          # teacher latents of the student rows (pass 2 target)
-        self._xa = z(rows, (D + actor_obs_shape[0] + 3) // 4 * 4)
-        self._xc = z(rows, (D + critic_obs_shape[0] + 3) // 4 * 4)
-        self._xa_t = torch.ones(D + actor_obs_shape[0] + 1, self.mb, device=dev)
-        self._xc_t = torch.ones(D + critic_obs_shape[0] + 1, self.mb, device=dev)
+        self._xa = z(rows, _ops.pad_in(D + actor_obs_shape[0]))
+        self._xc = z(rows, _ops.pad_in(D + critic_obs_shape[0]))
         self._mu, self._val = z(rows, A), z(rows, 1)
-        self._dmu, self._dmu_t, self._dval = z(self.mb, A), z(A, self.mb), z(self.mb + 4, 1)[:self.mb]
+        self._dmu, self._dval = z(self.mb, A), z(self.mb + 4, 1)[:self.mb]
         self._dlat = z(self.mb, D)
         self._dls = z(max(self.sm, 1), D)
         self._last_values = z(N, 1)
@@ -88,23 +86,23 @@ class CTS:
         self.model.train()
 
     # ---- shared forward pieces -----------------------------------------------------------------------------------------
-    def _latents(self, priv, hist, n_t, n_s, train_teacher=False, priv_t=None, ld_t=0):
+    def _latents(self, priv, hist, n_t, n_s, train_teacher=False):
         """self._lat[0:n_t] = teacher latent of the first n_t rows, self._lat[n_t:n_t+n_s] = student latent of the rest (no grad)."""
         m = self.model
         if n_t:
-            m.teacher_latent(priv[:n_t], n_t, self._lat[:n_t], train=train_teacher, Xt=priv_t, ldxt=ld_t)
+            m.teacher_latent(priv[:n_t], n_t, self._lat[:n_t], train=train_teacher, x_ones=train_teacher and _ops.use_tc())
         if n_s:
             m.student.forward(hist[n_t:n_t + n_s], n_s, self._lat[n_t:n_t + n_s])
 
     def _heads(self, obs, priv, M, train=False):
         m, D = self.model, self.model.latent_dim
         tc = _ops.use_tc()
-        xa_t = self._xa_t if (train and tc) else None
-        xc_t = self._xc_t if (train and tc) else None
-        call("go2_concat2", ptr(self._lat), D, D, ptr(obs), m.num_obs, obs.stride(0), ptr(self._xa), self._xa.shape[1], ptr(xa_t), M)
-        call("go2_concat2", ptr(self._lat), D, D, ptr(priv), m.num_critic_obs, priv.stride(0), ptr(self._xc), self._xc.shape[1], ptr(xc_t), M)
-        m.actor_engine.forward(self._xa, self._xa.shape[1], M, self._mu[:M], m.num_actions, train=train, Xt=xa_t, ldxt=M)
-        m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, Xt=xc_t, ldxt=M)
+        # go2_concat2 writes a 1 into the first padding column of its output (bias-gradient column of the row-major wgrad)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(obs), m.num_obs, obs.stride(0), ptr(self._xa), self._xa.shape[1], 0, M)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(priv), m.num_critic_obs, priv.stride(0), ptr(self._xc), self._xc.shape[1], 0, M)
+        ones = self._xa.shape[1] > D + m.num_obs
+        m.actor_engine.forward(self._xa, self._xa.shape[1], M, self._mu[:M], m.num_actions, train=train, x_ones=ones)
+        m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, x_ones=self._xc.shape[1] > D + m.num_critic_obs)
 
     # ---- rollout -------------------------------------------------------------------------------------------------------
     def act(self, obs, privileged_obs, history):
@@ -159,8 +157,8 @@ class CTS:
         st, m = self.storage, self.model
         idx, tm, sm = st.batch_indices(self.num_mini_batches, teacher_perm, student_perm)
         tc = _ops.use_tc()
-        pads = {"critic_obs": (m.num_critic_obs + 3) // 4 * 4, "history": (st.history.shape[-1] + 3) // 4 * 4} if tc else {}
-        self._sh = st.shuffled(idx, pads, transposed=("critic_obs", "history") if tc else ())
+        pads = {"critic_obs": _ops.pad_in(m.num_critic_obs), "history": _ops.pad_in(st.history.shape[-1])} if tc else {}
+        self._sh = st.shuffled(idx, pads)
         self._total = idx.numel()
         self._log.zero_(); self._log2.zero_()
         if self.world_size == 1:
@@ -210,15 +208,14 @@ class CTS:
         tc, ws = _ops.use_tc(), self.world_size
         s = slice(i * mb, (i + 1) * mb)
         obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
-        priv_t = sh["critic_obs_t"][:, i * mb:i * mb + tm] if tc else None
-        self._latents(priv_b, hist_b, tm, sm, train_teacher=True, priv_t=priv_t, ld_t=total)
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True)
         self._heads(obs_b, priv_b, mb, train=True)
         call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
              ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
-             ptr(self._dmu_t) if tc else 0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+             0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
              int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
-        m.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
-        m.critic_engine.backward(self._dval, 1, self._dval if tc else None, mb)
+        m.actor_engine.backward(self._dmu, A)
+        m.critic_engine.backward(self._dval, 1)
         # d loss / d latent = first D columns of the actor's input gradient, teacher rows only (student latents carry no grad)
         m.teacher_backward(m.actor_engine.dx, m.actor_engine.kpad0, self._lat, D, tm)
         m._gviews["std"].copy_(self._scal[4:4 + A])
@@ -239,9 +236,8 @@ class CTS:
         tc = _ops.use_tc()
         s = slice(i * mb + tm, (i + 1) * mb)
         priv_b, hist_b = sh["critic_obs"][s], sh["history"][s]
-        hist_t = sh["history_t"][:, i * mb + tm:(i + 1) * mb] if tc else None
         m.teacher_latent(priv_b, sm, self._lat_t)
-        m.student.forward(hist_b, sm, self._lat[:sm], train=True, Xt=hist_t, ldxt=total)
+        m.student.forward(hist_b, sm, self._lat[:sm], train=True, x_ones=tc)
         call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t), ptr(self._dls), ptr(self._acc), sm, D)
         m.student.backward(self._dls, self.load_balance_coef)
         call("go2_cts_log", ptr(self._acc), ptr(m.student.usage) if self._moe else 0, ptr(self._log2), sm * D, m.student.E if self._moe else 1)

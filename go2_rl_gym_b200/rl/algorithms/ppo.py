@@ -61,10 +61,8 @@ class PPO:
         self._log = torch.zeros(5, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
         self._dmu = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
-        self._dmu_t = torch.empty(action_shape[0], self.mini_batch_size, device=dev)
         self._dval = torch.empty(self.mini_batch_size + 4, 1, device=dev)[:self.mini_batch_size]
         # [1+1, mb] view of the value gradient for the tensor-core wgrad: row 0 = dV^T (same storage), then the engine's ones row is not needed here
-        self._dval_t = self._dval
         self._mu_b = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
         self._val_b = torch.empty(self.mini_batch_size, 1, device=dev)
         self._last_values = torch.empty(num_envs, 1, device=dev)
@@ -118,8 +116,8 @@ class PPO:
         if indices is None:
             indices = torch.randperm(self.num_mini_batches * mb, device=self.device)
         tc = _ops.use_tc()
-        pads = {"obs": (st.observations.shape[-1] + 3) // 4 * 4, "critic_obs": (sh_w + 3) // 4 * 4} if tc else {}
-        sh = st.shuffled(indices, pads, transposed=("obs", "critic_obs") if tc else ())
+        pads = {"obs": _ops.pad_in(st.observations.shape[-1]), "critic_obs": _ops.pad_in(sh_w)} if tc else {}
+        sh = st.shuffled(indices, pads)
         total = indices.numel()
         self._log.zero_()
         self._sh, self._total, self._tc = sh, total, tc
@@ -154,17 +152,16 @@ class PPO:
         inv_count = 1.0 / (mb * self.world_size)
         s = slice(i * mb, (i + 1) * mb)
         obs_b, cobs_b = sh["obs"][s], sh["critic_obs"][s]
-        obs_t = sh["obs_t"][:, s] if tc else None
-        cobs_t = sh["critic_obs_t"][:, s] if tc else None
-        ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A, train=True, Xt=obs_t, ldxt=total)
-        ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, Xt=cobs_t, ldxt=total)
+        # padded gathers carry a 1 in their first padding column (the bias-gradient column of the row-major wgrad)
+        ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A, train=True, x_ones=tc)
+        ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, x_ones=tc)
         _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
                   _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
-                  _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), _ops.ptr(self._dmu_t) if tc else 0,
+                  _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), 0,
                   _ops.ptr(self._dval), _ops.ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
                   int(self.use_clipped_value_loss), inv_count, mb, inv_count, inv_count)
-        ac.actor_engine.backward(self._dmu, A, self._dmu_t if tc else None, mb)
-        ac.critic_engine.backward(self._dval, 1, self._dval_t if tc else None, mb)
+        ac.actor_engine.backward(self._dmu, A)
+        ac.critic_engine.backward(self._dval, 1)
         ac._gviews["std"].copy_(self._scal[4:4 + A])
 
     def _step_part(self):

@@ -145,17 +145,15 @@ class _CTSBase(nn.Module):
     def forward(self):
         raise NotImplementedError
 
-    def teacher_latent(self, priv, M, out, train=False, Xt=None, ldxt=0):
+    def teacher_latent(self, priv, M, out, train=False, x_ones=False):
         """out[M, latent] = L2Norm(teacher_encoder(priv))  (actor_critic_moe_cts.py:116-117)"""
         e = self.teacher_engine
-        e.forward(priv, priv.shape[1] if priv.dim() == 2 else 0, M, self._t_pre[:M], self.latent_dim, train=train, Xt=Xt, ldxt=ldxt)
+        e.forward(priv, priv.shape[1] if priv.dim() == 2 else 0, M, self._t_pre[:M], self.latent_dim, train=train, x_ones=x_ones)
         call("go2_l2norm_forward", ptr(self._t_pre), self.latent_dim, ptr(out), out.stride(0), ptr(self._t_norm), M, self.latent_dim)
 
     def teacher_backward(self, dlatent, lddl, latent, ldl, M):
-        call("go2_l2norm_backward", ptr(dlatent), lddl, ptr(latent), ldl, ptr(self._t_norm), ptr(self._t_dpre), self.latent_dim,
-             ptr(self._t_dpre_t) if self._t_dpre_t is not None else 0, M, self.latent_dim)
-        # the transposed copy is written with row pitch M (the rows of this call)
-        self.teacher_engine.backward(self._t_dpre, self.latent_dim, self._t_dpre_t, M)
+        call("go2_l2norm_backward", ptr(dlatent), lddl, ptr(latent), ldl, ptr(self._t_norm), ptr(self._t_dpre), self.latent_dim, 0, M, self.latent_dim)
+        self.teacher_engine.backward(self._t_dpre, self.latent_dim)
 
     def act_inference(self, obs):
         """Student policy (actor_critic_moe_cts.py:127-132): roll the history, encode it, act on [latent | obs]."""
@@ -180,7 +178,6 @@ class _StudentMLP:
         self.pre = torch.empty(max_rows, self.D, device=dev)
         self.norm = torch.empty(max_rows, device=dev)
         self.dpre = torch.empty(max(train_rows, 1), self.D, device=dev)
-        self.dpre_t = torch.empty(self.D, max(train_rows, 1), device=dev) if _ops.use_tc() else None
 
     def engines(self):
         return [self.engine]
@@ -188,16 +185,15 @@ class _StudentMLP:
     def mark_dirty(self):
         pass
 
-    def forward(self, hist, M, out, train=False, Xt=None, ldxt=0):
-        self.engine.forward(hist, hist.shape[1], M, self.pre[:M], self.D, train=train, Xt=Xt, ldxt=ldxt)
+    def forward(self, hist, M, out, train=False, x_ones=False):
+        self.engine.forward(hist, hist.shape[1], M, self.pre[:M], self.D, train=train, x_ones=x_ones)
         call("go2_l2norm_forward", ptr(self.pre), self.D, ptr(out), out.stride(0), ptr(self.norm), M, self.D)
         self._out, self._M = out, M
 
     def backward(self, dlatent, lb_coef=0.0):
         M = self._M
-        call("go2_l2norm_backward", ptr(dlatent), self.D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), self.D,
-             ptr(self.dpre_t), M, self.D)
-        self.engine.backward(self.dpre, self.D, self.dpre_t, M)
+        call("go2_l2norm_backward", ptr(dlatent), self.D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), self.D, 0, M, self.D)
+        self.engine.backward(self.dpre, self.D)
         return None
 
 
@@ -220,9 +216,9 @@ class _StudentMoE:
         z = lambda *s: torch.empty(*s, device=dev)
         self.eo, self.logits, self.gates = z(max_rows, E * D), z(max_rows, E), z(max_rows, E)
         self.pre, self.norm = z(max_rows, D), z(max_rows)
-        self.dpre, self.deo, self.deo_t = z(tr, D), z(tr, E * D), z(E * D, tr)
-        self.dlogits, self.dlogits_t = z(tr, E), z(E, tr)
-        self.dfeat, self.dfeat_t = z(tr, E * self.H), z(E * self.H, tr)
+        self.dpre, self.deo = z(tr, D), z(tr, E * D)
+        self.dlogits = z(tr, E)
+        self.dfeat = z(tr, E * self.H)
         self.usage = torch.zeros(E, device=dev)
         self.Wet = torch.zeros(E * self.H, D, device=dev)   # per expert W_e^T [H, D], stacked
         self.work = torch.empty(64 * 128 * (self.H + 4), device=dev)
@@ -235,15 +231,15 @@ class _StudentMoE:
     def mark_dirty(self):
         self._dirty = True
 
-    def forward(self, hist, M, out, train=False, Xt=None, ldxt=0):
+    def forward(self, hist, M, out, train=False, x_ones=False):
         E, D, H = self.E, self.D, self.H
-        self.backbone.forward(hist, hist.shape[1], M, train=train, Xt=Xt, ldxt=ldxt)
-        feat = self.backbone.out
+        self.backbone.forward(hist, hist.shape[1], M, train=train, x_ones=x_ones)
+        feat, ldf = self.backbone.out, self.backbone.ld_out
         for e in range(E):  # block-diagonal expert layer = Conv1d(groups=E, kernel 1)
             fn = "go2_linear_forward_tc" if _ops.use_tc() else "go2_linear_forward_simt"
-            call(fn, ptr(feat) + 4 * e * H, E * H, ptr(self.We) + 4 * e * D * H, H, ptr(self.be) + 4 * e * D, ptr(self.eo) + 4 * e * D, E * D, 0, 0,
+            call(fn, ptr(feat) + 4 * e * H, ldf, ptr(self.We) + 4 * e * D * H, H, ptr(self.be) + 4 * e * D, ptr(self.eo) + 4 * e * D, E * D, 0, 0,
                  M, D, H, 0)
-        self.gate.forward(hist, hist.shape[1], M, self.logits[:M], E, train=train, Xt=Xt, ldxt=ldxt)
+        self.gate.forward(hist, hist.shape[1], M, self.logits[:M], E, train=train, x_ones=x_ones)
         call("go2_moe_combine_forward", ptr(self.logits), ptr(self.eo), ptr(self.gates), ptr(self.pre), M, E, D)
         call("go2_l2norm_forward", ptr(self.pre), D, ptr(out), out.stride(0), ptr(self.norm), M, D)
         self._out, self._M = out, M
@@ -252,28 +248,27 @@ class _StudentMoE:
         E, D, H, M, tr = self.E, self.D, self.H, self._M, self.train_rows
         tc = _ops.use_tc()
         call("go2_l2norm_backward", ptr(dlatent), D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), D, 0, M, D)
-        call("go2_moe_combine_backward", ptr(self.dpre), ptr(self.gates), ptr(self.eo), ptr(self.usage), float(lb_coef), ptr(self.deo),
-             ptr(self.deo_t) if tc else 0, ptr(self.dlogits), ptr(self.dlogits_t) if tc else 0, M, E, D)
-        # NOTE deo_t / dlogits_t are written with row pitch M by the kernel
+        call("go2_moe_combine_backward", ptr(self.dpre), ptr(self.gates), ptr(self.eo), ptr(self.usage), float(lb_coef), ptr(self.deo), 0,
+             ptr(self.dlogits), 0, M, E, D)
         if self._dirty and tc:
             for e in range(E):
                 call("go2_transpose", ptr(self.We) + 4 * e * D * H, H, ptr(self.Wet) + 4 * e * H * D, D, D, H)
             self._dirty = False
         call("go2_colsum", ptr(self.deo), E * D, ptr(self.gbe), M, E * D, ptr(self.work))
-        feat, featT = self.backbone.out, self.backbone.outT if tc else None
+        feat, ldf = self.backbone.out, self.backbone.ld_out
         for e in range(E):
             if tc:
-                call("go2_linear_wgrad_tc", ptr(self.deo_t) + 4 * e * D * M, M, ptr(featT) + 4 * e * H * tr, tr, ptr(self.gWe) + 4 * e * D * H, H, 0,
+                call("go2_linear_wgrad_tc_rm", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, ldf, ptr(self.gWe) + 4 * e * D * H, H, 0,
                      M, D, H, ptr(self.work), self.work.numel())
-                call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, ptr(feat) + 4 * e * H, E * H, ptr(featT) + 4 * e * H * tr, tr,
-                     ptr(self.dfeat) + 4 * e * H, E * H, ptr(self.dfeat_t) + 4 * e * H * tr, tr, M, D, H)
-            else:
-                call("go2_linear_wgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, E * H, ptr(self.gWe) + 4 * e * D * H, H, 0,
-                     M, D, H, ptr(self.work), self.work.numel())
-                call("go2_linear_dgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(self.We) + 4 * e * D * H, H, ptr(feat) + 4 * e * H, E * H,
+                call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, ptr(feat) + 4 * e * H, ldf, 0, 0,
                      ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
-        self.backbone.backward(self.dfeat, E * H, self.dfeat_t if tc else None, tr)
-        self.gate.backward(self.dlogits, E, self.dlogits_t if tc else None, M)
+            else:
+                call("go2_linear_wgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, ldf, ptr(self.gWe) + 4 * e * D * H, H, 0,
+                     M, D, H, ptr(self.work), self.work.numel())
+                call("go2_linear_dgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(self.We) + 4 * e * D * H, H, ptr(feat) + 4 * e * H, ldf,
+                     ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
+        self.backbone.backward(self.dfeat, E * H)
+        self.gate.backward(self.dlogits, E)
 
 
 class ActorCriticMoECTS(_CTSBase):
@@ -319,9 +314,8 @@ class ActorCriticMoECTS(_CTSBase):
         self._t_pre = torch.empty(max_rows, D, device=dev)
         self._t_norm = torch.empty(max_rows, device=dev)
         self._t_dpre = torch.empty(max(trt, 1), D, device=dev)
-        self._t_dpre_t = torch.empty(D, max(trt, 1), device=dev) if _ops.use_tc() else None
         self._inf_lat = torch.empty(max_rows, D, device=dev)
-        self._inf_xa = torch.zeros(max_rows, (self.a_dims[0] + 3) // 4 * 4, device=dev)
+        self._inf_xa = torch.zeros(max_rows, _ops.pad_in(self.a_dims[0]), device=dev)
         self._inf_mu = torch.empty(max_rows, self.num_actions, device=dev)
 
 
