@@ -192,8 +192,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # timed region: the runner's own iteration (rollout replayed as ONE CUDA graph over device-resident step parameters, update() as another)
     for _ in range(max(args.warmup, 3)):
-        iteration()
+        runner.run_iteration()
     sync()
     sampler = ClockSampler(local)
     sampler.start()
@@ -203,7 +204,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        iteration(timed_kernel=True)
+        runner.run_iteration()
     ev1.record()
     sync()
     launches = lib.go2_kernel_launch_count() + GraphSet.replayed_launches - l0      # direct launches + launches replayed from CUDA graphs
@@ -213,6 +214,11 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms) / args.steps
     value = world * N * STEPS_PER_ENV / (ms * 1e-3)
+    # the fused step kernel's own duration: the same iterations launched step by step with CUDA events around every env.step()
+    obs, cobs = env.get_observations(), env.get_privileged_observations()
+    for _ in range(2):
+        iteration(timed_kernel=True)
+    sync()
     kern_ms = sum(a.elapsed_time(b) for a, b in step_ev) / len(step_ev)          # fused step kernel (+ its 2 us finalize kernel)
     peaks, peak_kind = _peaks()
     achieved = ALGO_BYTES_PER_ENV_STEP * N / (kern_ms * 1e-3) / 1e9
@@ -272,10 +278,10 @@ def main():
                 "kernel_us": us, "tflops": 2.0 * Mg * Ng * Kg / us / 1e6,
                 "note": "fp32 activations make every MLP GEMM of the update HBM/L2-bound (33 flop/B); 20 back-to-back launches, includes host launch gaps"}
     traffic = None
-    try:
-        d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_kernel_dram.json")))
+    try:   # ncu --set full capture of the step kernel of this build at this size (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
+        d = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_dram.json")))
         if d.get("num_envs") == N:
-            traffic = d["dram_bytes_read"] + d["dram_bytes_write"]          # ncu --set full capture of this build (see profiles/)
+            traffic = d["dram_bytes_read"] + d["dram_bytes_write"]
     except Exception:  # noqa: BLE001
         pass
 
@@ -293,7 +299,7 @@ def main():
                            "parallelism": f"env-sharded dp{world}, NCCL all-reduce per optimiser step"},
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "go2::step_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "roofline": {"kernel": "go2::step_kernel_packed<2>" if os.environ.get("GO2_STEP_MODE", "P2").startswith("P") else "go2::step_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                              "kernel_us": kern_ms * 1e3, "env_steps_per_s_kernel_only": N / (kern_ms * 1e-3),
                              "note": "latency/issue-bound serial 13-body recursion; HBM fraction is structurally tiny (SURVEY 7.2)"},

@@ -104,6 +104,10 @@ def load_library():
     lib.go2_env_destroy.restype = None
     lib.go2_env_step.argtypes = [vp, vp, C.POINTER(Go2StepParams), vp]
     lib.go2_env_step.restype = C.c_int
+    lib.go2_env_set_step_mode.argtypes = [vp, C.c_char_p]
+    lib.go2_env_set_step_mode.restype = C.c_int
+    lib.go2_env_step_dev.argtypes = [vp, vp, vp, vp]
+    lib.go2_env_step_dev.restype = C.c_int
     lib.go2_env_step_host.argtypes = [vp, vp, C.POINTER(Go2StepParams), vp, vp, vp, vp, vp]
     lib.go2_env_step_host.restype = C.c_int
     lib.go2_env_reset_all.argtypes = [vp, C.POINTER(Go2StepParams), vp]

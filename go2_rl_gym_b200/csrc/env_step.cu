@@ -17,66 +17,79 @@ constexpr int WARPS_PER_CTA = 4;
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 4)
 step_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
-            const __grid_constant__ Go2StepParams sp, const float* __restrict__ actions) {
+            const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WARPS_PER_CTA + warp;
-  if (e >= cfg->num_envs) return;
-  StepCtx X{cfg, mdl, &buf, &sp, actions};
+  const int e0 = blockIdx.x * WARPS_PER_CTA;
+  StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
-  L.nsync = 0; L.ncoarse = 0; L.nmid = 0;
-  step_env(lane, L, smem[warp], X, e);
+  init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
+  if (!L.own) return;
+  step_env(L, smem, X);
 }
 
-// Same step, W warps per CTA with dynamic shared memory; LOCKSTEP: phases end in a CTA-wide named barrier over the warps that own an
-// env, so all warps of the CTA stream the same instructions (the step is instruction-fetch bound: ~155 KB of straight-line code)
-template <int W, int MINB, int LOCKSTEP>     // LOCKSTEP: 0 none, 1 every phase, 2 substep boundaries only
+// Same step, W warps per CTA with dynamic shared memory; LOCKSTEP: phases end in a CTA-wide named barrier, so all warps of the CTA
+// stream the same instructions (the step is instruction-fetch bound: ~155 KB of straight-line code)
+template <int W, int MINB, int LOCKSTEP>     // LOCKSTEP: 0 none, 1 every phase, 2 substep boundaries only, 3 + three points inside a substep
 __global__ void __launch_bounds__(32 * W, MINB)
 step_kernel_wide(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
-                 const __grid_constant__ Go2StepParams sp, const float* __restrict__ actions) {
+                 const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * W + warp;
-  if (e >= cfg->num_envs) return;
-  StepCtx X{cfg, mdl, &buf, &sp, actions};
+  const int e0 = blockIdx.x * W, n_local = min(W, cfg->num_envs - e0);
+  StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
-  L.nsync = LOCKSTEP == 1 ? 32 * min(W, cfg->num_envs - blockIdx.x * W) : 0;
-  L.ncoarse = LOCKSTEP >= 2 ? 32 * min(W, cfg->num_envs - blockIdx.x * W) : 0;
+  init_roles(L, threadIdx.x, 0, e0, n_local, W);
+  if (!L.own) return;
+  L.nsync = LOCKSTEP == 1 ? 32 * n_local : 0;
+  L.ncoarse = LOCKSTEP >= 2 ? 32 * n_local : 0;
   L.nmid = LOCKSTEP == 3 ? L.ncoarse : 0;
-  step_env(lane, L, smem[warp], X, e);
+  step_env(L, smem, X);
+}
+
+// PACKED thread map (env_step_core.cuh): a CTA of 8 warps owns 8 envs; the serial leg recursions of all 8 envs run in warp 0 (one
+// (env, leg) item per lane), the base 6x6 factorisations in warps 1-2; every phase ends in a CTA barrier.  The leg code is ~80 % of the
+// step's instructions and used 4 of 32 lanes with the warp-per-env map: here it is issued once per 8 envs.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
+                   const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
+  const int e0 = blockIdx.x * 8;
+  StepCtx X{cfg, mdl, &buf, sp, actions};
+  Lane L;
+  init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8);
+  step_env(L, smem, X);
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
 reset_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
-             const __grid_constant__ Go2StepParams sp) {
+             const Go2StepParams* __restrict__ sp) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WARPS_PER_CTA + warp;
-  if (e >= cfg->num_envs) return;
-  StepCtx X{cfg, mdl, &buf, &sp, nullptr};
+  const int e0 = blockIdx.x * WARPS_PER_CTA;
+  StepCtx X{cfg, mdl, &buf, sp, nullptr};
   Lane L;
-  L.nsync = 0; L.ncoarse = 0; L.nmid = 0;
-  reset_env_initial(lane, L, smem[warp], X, e);
+  init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
+  if (!L.own) return;
+  reset_env_initial(L, smem, X);
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
 substeps_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
                 const float* __restrict__ tau, int n) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WARPS_PER_CTA + warp;
-  if (e >= cfg->num_envs) return;
+  const int e0 = blockIdx.x * WARPS_PER_CTA;
   StepCtx X{cfg, mdl, &buf, nullptr, nullptr};
   Lane L;
-  L.nsync = 0; L.ncoarse = 0; L.nmid = 0;
-  substeps_env(lane, L, smem[warp], X, e, tau, n);
+  init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
+  if (!L.own) return;
+  substeps_env(L, smem, X, tau, n);
 }
 
 // extras["episode"] (legged_robot.py:229-242): refreshed only when at least one env reset this step; then clear the sums
 __global__ void finalize_kernel(const Go2EnvConfig* __restrict__ cfg, float* __restrict__ ep_accum, float* __restrict__ ep_stats,
-                                const float* __restrict__ id_counts, int slot) {
-  const int k = threadIdx.x;
+                                const float* __restrict__ id_counts, const Go2StepParams* __restrict__ sp) {
+  const int k = threadIdx.x, slot = sp->ep_slot;
   const float n_reset = ep_accum[GO2_NUM_REW + 10];
   __syncthreads();
   if (n_reset > 0.0f && ep_stats != nullptr) {
@@ -102,8 +115,14 @@ struct Go2Env {
   Go2Model* d_mdl = nullptr;
   float* d_actions = nullptr;     // staging for the host-buffer entry point
   float* d_id_counts = nullptr;
+  Go2StepParams* d_sp = nullptr;  // staging slot of the host-parameter entry points (the kernels read the step parameters from device memory)
   int grid = 0;
+  int step_mode = 2;              // thread map of the step kernel, see go2_env_set_step_mode
 };
+
+static int parse_step_mode(const char* m) {
+  return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : -1;
+}
 
 namespace go2 {
 template <int W, int MINB, int LOCKSTEP>
@@ -114,7 +133,18 @@ static int launch_wide(Go2Env* h, const float* actions, const Go2StepParams* sp,
     GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_wide<W, MINB, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  step_kernel_wide<W, MINB, LOCKSTEP><<<(h->cfg.num_envs + W - 1) / W, 32 * W, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, *sp, actions);
+  step_kernel_wide<W, MINB, LOCKSTEP><<<(h->cfg.num_envs + W - 1) / W, 32 * W, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
+  return 0;
+}
+template <int MINB>
+static int launch_packed(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
+  const int smem = 8 * (int)sizeof(WarpSmem);
+  static bool attr = false;
+  if (!attr) {
+    GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  step_kernel_packed<MINB><<<(h->cfg.num_envs + 7) / 8, 256, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   return 0;
 }
 }  // namespace go2
@@ -140,6 +170,7 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
   GO2_CUDA_OK(cudaMalloc(&h->d_mdl, sizeof(Go2Model)));
   GO2_CUDA_OK(cudaMalloc(&h->d_actions, sizeof(float) * GO2_NUM_DOF * cfg->num_envs));
   GO2_CUDA_OK(cudaMalloc(&h->d_id_counts, sizeof(float) * 9));
+  GO2_CUDA_OK(cudaMalloc(&h->d_sp, sizeof(Go2StepParams)));
   GO2_CUDA_OK(cudaMemcpy(h->d_cfg, cfg, sizeof(Go2EnvConfig), cudaMemcpyHostToDevice));
   GO2_CUDA_OK(cudaMemcpy(h->d_mdl, model, sizeof(Go2Model), cudaMemcpyHostToDevice));
   std::vector<int32_t> ids(cfg->num_envs);
@@ -148,41 +179,49 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
   for (int e = 0; e < cfg->num_envs; ++e) if (ids[e] >= 0 && ids[e] < 9) counts[ids[e]] += 1.0f;
   GO2_CUDA_OK(cudaMemcpy(h->d_id_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
   GO2_CUDA_OK(cudaMemset(bufs->ep_accum, 0, sizeof(float) * (GO2_EP_STATS + 2)));
+  if (const char* m = getenv("GO2_STEP_MODE")) {
+    if (parse_step_mode(m) < 0) { go2_env_destroy(h); return go2::set_error(1, "go2_env_create: unknown GO2_STEP_MODE"); }
+    h->step_mode = parse_step_mode(m);
+  }
   *out = h;
+  return 0;
+}
+
+// Thread map of the step kernel (same results bit for bit; tuning / A-B aid).  Default "P2"; the GO2_STEP_MODE environment variable
+// presets it at create time.
+//   "P2": packed map, 8 envs per 256-thread CTA, 2 CTAs/SM (128 registers) · "P3": the same with 3 CTAs/SM (80 registers)
+//   "8p": warp per env, 8 warps per CTA, CTA barrier at substep boundaries (the previous default: 203 us at 4096 envs)
+//   "4" : warp per env, 4 warps per CTA, no barrier (the first kernel: 239 us)
+int go2_env_set_step_mode(Go2Env* h, const char* mode) {
+  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P3, 8p, 4)");
+  h->step_mode = parse_step_mode(mode);
   return 0;
 }
 
 void go2_env_destroy(Go2Env* h) {
   if (!h) return;
-  cudaFree(h->d_cfg); cudaFree(h->d_mdl); cudaFree(h->d_actions); cudaFree(h->d_id_counts);
+  cudaFree(h->d_cfg); cudaFree(h->d_mdl); cudaFree(h->d_actions); cudaFree(h->d_id_counts); cudaFree(h->d_sp);
   delete h;
 }
 
 int go2_env_step(Go2Env* h, const float* actions, const Go2StepParams* sp, void* stream) {
   if (!h || !actions || !sp) return go2::set_error(1, "go2_env_step: null argument");
+  // stream-ordered upload of the 72-byte parameter block (the source is staged before the call returns)
+  GO2_CUDA_OK(cudaMemcpyAsync(h->d_sp, sp, sizeof(Go2StepParams), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return go2_env_step_dev(h, actions, h->d_sp, stream);
+}
+
+int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, void* stream) {
+  if (!h || !actions || !sp) return go2::set_error(1, "go2_env_step_dev: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  // default: 8 warps (envs) per CTA, 2 CTAs/SM, CTA-wide barrier at substep boundaries only ("8p"): the step is instruction-fetch bound
-  // (~155 KB of straight-line code), and warps that stay on the same stretch of code share the instruction caches: 239 -> 203 us at
-  // 4096 envs, 447 -> 356 us at 8192.  GO2_STEP_MODE (tuning aid): "4" = 4 warps/CTA, no barrier; "<W>" / "<W>s" (every phase) /
-  // "<W>p" (substep boundaries) / "<W>q" (+3 points inside a substep)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* m = getenv("GO2_STEP_MODE");
-    mode = !m ? 7 : !strcmp(m, "4") ? 0 : !strcmp(m, "16s") ? 3 : !strcmp(m, "16") ? 2 : !strcmp(m, "8s") ? 1 : !strcmp(m, "4s") ? 4 : !strcmp(m, "8") ? 5 : !strcmp(m, "16p") ? 6
-           : !strcmp(m, "8p") ? 7 : !strcmp(m, "12") ? 8 : !strcmp(m, "8q") ? 9 : !strcmp(m, "4p") ? 10 : !strcmp(m, "4q") ? 11 : !strcmp(m, "16q") ? 12 : 0;
-  }
-  if (mode == 0) go2::step_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, *sp, actions);
+  const int mode = h->step_mode;
+  if (mode == 0) go2::step_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   else {
-    int rc = mode == 3 ? go2::launch_wide<16, 1, 1>(h, actions, sp, st) : mode == 2 ? go2::launch_wide<16, 1, 0>(h, actions, sp, st)
-           : mode == 1 ? go2::launch_wide<8, 2, 1>(h, actions, sp, st) : mode == 4 ? go2::launch_wide<4, 4, 1>(h, actions, sp, st)
-           : mode == 5 ? go2::launch_wide<8, 2, 0>(h, actions, sp, st) : mode == 6 ? go2::launch_wide<16, 1, 2>(h, actions, sp, st)
-           : mode == 7 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 9 ? go2::launch_wide<8, 2, 3>(h, actions, sp, st)
-           : mode == 10 ? go2::launch_wide<4, 4, 2>(h, actions, sp, st) : mode == 11 ? go2::launch_wide<4, 4, 3>(h, actions, sp, st)
-           : mode == 12 ? go2::launch_wide<16, 1, 3>(h, actions, sp, st) : go2::launch_wide<12, 1, 0>(h, actions, sp, st);
+    int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2>(h, actions, sp, st) : go2::launch_packed<3>(h, actions, sp, st);
     if (rc) return rc;
   }
   go2::count_launch();
-  go2::finalize_kernel<<<1, 32, 0, st>>>(h->d_cfg, h->buf.ep_accum, h->buf.ep_stats, h->d_id_counts, sp->ep_slot);
+  go2::finalize_kernel<<<1, 32, 0, st>>>(h->d_cfg, h->buf.ep_accum, h->buf.ep_stats, h->d_id_counts, sp);
   go2::count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -207,7 +246,8 @@ int go2_env_step_host(Go2Env* h, const float* h_actions, const Go2StepParams* sp
 int go2_env_reset_all(Go2Env* h, const Go2StepParams* sp, void* stream) {
   if (!h || !sp) return go2::set_error(1, "go2_env_reset_all: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  go2::reset_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, *sp);
+  GO2_CUDA_OK(cudaMemcpyAsync(h->d_sp, sp, sizeof(Go2StepParams), cudaMemcpyHostToDevice, st));
+  go2::reset_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, h->d_sp);
   go2::count_launch();
   GO2_CUDA_OK(cudaMemsetAsync(h->buf.ep_accum, 0, sizeof(float) * (GO2_EP_STATS + 2), st));
   GO2_CUDA_OK(cudaGetLastError());

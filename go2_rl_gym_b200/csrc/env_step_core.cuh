@@ -3,16 +3,22 @@
 // Replaces LeggedRobot.step + post_physics_step of the reference (legged_gym/envs/base/legged_robot.py:60-142 and
 // everything they call; go2_env.py:23-60) and the gym.simulate call inside it (physics spec: DESIGN.md section 3).
 //
-// Execution model: a sequence of PHASES.  Inside a phase every lane works on its own item (a joint, a leg, a collider,
-// a height sample, an observation column ...) and lanes only communicate through the per-warp shared-memory block
-// `WarpSmem` ACROSS phase boundaries (phase end = __syncwarp()).  No shuffles or ballots are used, so all cross-lane sums
-// run in a fixed order (bit-reproducible run to run) and the very same source can be executed lane-by-lane on the host:
-//   * nvcc, sm_100a : GO2_LANES_BEGIN/END expand to a block followed by __syncwarp(); `lane` = threadIdx.x & 31.
-//   * g++ (tests/emu): they expand to `for (lane = 0..31)`, giving a faithful functional emulation of the kernel that the
-//     CPU test-suite compares against the oracle without a GPU.  The emulation is test tooling, not a product path.
+// Execution model: a sequence of PHASES.  Inside a phase every thread works on its own item (a joint, a leg, a collider,
+// a height sample, an observation column ...) and threads only communicate through the per-env shared-memory block
+// `WarpSmem` ACROSS phase boundaries (GO2_SYNC()).  No shuffles or ballots are used, so all cross-lane sums run in a fixed
+// order (bit-reproducible run to run) and the very same source can be executed thread-by-thread on the host:
+//   * nvcc, sm_100a : GO2_WIDE / GO2_LEGS / GO2_COLS guard a block by the thread's role; GO2_SYNC() = __syncwarp() or a CTA barrier.
+//   * g++ (tests/emu): they expand to a loop over the threads of the group, giving a faithful functional emulation of the
+//     kernel that the CPU test-suite compares against the oracle without a GPU.  The emulation is test tooling, not a product path.
 //
-// Lane roles:  joints j = lane (0..11) · legs l = lane (0..3) · base 6x6 columns k = lane (0..5) · colliders c = lane (0..31)
-//              reported bodies b = lane (0..18) · height samples i = lane + 32 k · observation columns i = lane + 32 k.
+// Roles (filled by init_roles()):
+//   WIDE  one warp per env, item = lane: joints j = lane (0..11) · colliders c = lane (0..31) · reported bodies · height samples
+//         i = lane + 32 k · observation columns i = lane + 32 k · the scalar per-env bookkeeping on lane 0.
+//   LEGS  one thread per (env, leg): the serial 6x6 articulated-body recursions along hip -> thigh -> calf.
+//   COLS  one thread per (env, column of the base's 6x6 articulated inertia).
+// Two thread maps exist.  "warp per env": LEGS = lanes 0..3 and COLS = lanes 0..5 of the env's own warp (28 / 26 lanes idle in the
+// heaviest phases).  "packed": a CTA of 8 warps owns 8 envs; the 32 (env, leg) items fill warp 0 and the 48 (env, column) items sit
+// in warps 1-2, so the long serial leg code is issued once per 8 envs instead of once per env; all phases end in a CTA barrier.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -25,18 +31,23 @@
 #endif
 
 #if defined(__CUDACC__)
-#define GO2_LANES_BEGIN {
-#define GO2_LANES_END } go2_phase_sync(L);
+#define GO2_EACH
+#define GO2_SYNC() go2_phase_sync(L)
 #define GO2_FMUL(a, b) __fmul_rn((a), (b))
 #define GO2_FADD(a, b) __fadd_rn((a), (b))
 #define GO2_LDG(p) __ldg(p)
 #else
-#define GO2_LANES_BEGIN for (int lane = 0; lane < 32; ++lane) { Lane& L = lanes[lane]; (void)L;
-#define GO2_LANES_END }
+#define GO2_EACH for (int tid_ = 0; tid_ < NT; ++tid_) if (Lane& L = lanes[tid_]; true)
+#define GO2_SYNC() do { } while (0)
 #define GO2_FMUL(a, b) ((a) * (b))
 #define GO2_FADD(a, b) ((a) + (b))
 #define GO2_LDG(p) (*(p))
 #endif
+// bind S (the item's env scratch), e (its env id) and lane (the item index within the role) for the block that follows
+#define GO2_BIND(slot, idx) if (WarpSmem& S = SM[slot]; true) if (const int e = L.e0 + (slot), lane = (idx); (void)e, (void)lane, true)
+#define GO2_WIDE GO2_EACH if (L.own) GO2_BIND(L.w, L.lane)
+#define GO2_LEGS GO2_EACH if (L.leg >= 0) GO2_BIND(L.wl, L.leg)
+#define GO2_COLS GO2_EACH if (L.col >= 0) GO2_BIND(L.wc, L.col)
 
 namespace go2 {
 
@@ -228,7 +239,9 @@ struct WarpSmem {
   float env_origin[3];
   int active[GO2_NUM_COL];
   int ep_len, reset, tout, last_lim, level, ttype, tid, delay_start;
+  int pad_;   // 2017 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
 };
+static_assert((sizeof(WarpSmem) / 4) % 32 == 1, "WarpSmem stride must be 1 mod 32 words");
 
 struct Lane {
   // joint lanes (0..11)
@@ -241,8 +254,13 @@ struct Lane {
   // collider lanes
   float n[3], Winv[6], vt, mu, r[3], p[3], gcount;
   int body, act;
-  // phase barrier: 0 = warp-level (__syncwarp); otherwise the number of threads of a CTA-wide named barrier that keeps the
-  // warps of one CTA on the same stretch of code (instruction-cache sharing; same results either way)
+  // thread map (init_roles): own env slot / lane, leg item, base-column item, first env id of the group, slots of the group
+  int own, w, lane;
+  int leg, wl;
+  int col, wc;
+  int e0, w0, nw;
+  // phase barrier: 0 = warp-level (__syncwarp); otherwise the number of threads of the CTA-wide named barrier every phase ends in
+  // (required by the packed map; with the warp-per-env map it only keeps the warps of a CTA on the same stretch of code)
   int nsync;
   int nmid;      // same, at three more points inside a substep (GO2_MID_SYNC)
   int ncoarse;   // same, but only at the few GO2_COARSE_SYNC points (substep boundaries): loose re-alignment of the CTA's warps
@@ -259,6 +277,35 @@ __device__ __forceinline__ void go2_phase_sync(const Lane& L) {
 #define GO2_COARSE_SYNC() do { } while (0)
 #define GO2_MID_SYNC() do { } while (0)
 #endif
+
+// Thread map of thread `tid` of a group of `nwarps` warps whose first env is e0 and which holds n_local (>= 1) envs.
+//   packed == 0: warp w owns env e0 + w; its lanes 0..3 / 0..5 are that env's LEGS / COLS items.
+//   packed == 1: 8 warps, up to 8 envs; warp w still owns env e0 + w for the WIDE role, but the LEGS items of all envs sit in
+//                warp 0 (lane = 4 * slot + leg) and the COLS items in warps 1-2 (8 lanes per env, 6 used).
+GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nwarps) {
+  const int warp = tid >> 5, lane = tid & 31;
+  L.e0 = e0; L.w = warp; L.lane = lane;
+  L.own = warp < n_local;
+  L.ncoarse = 0; L.nmid = 0;
+  if (!packed) {
+    L.leg = (L.own && lane < 4) ? lane : -1; L.wl = warp;
+    L.col = (L.own && lane < 6) ? lane : -1; L.wc = warp;
+    L.w0 = warp; L.nw = 1;
+    L.nsync = 0;
+  } else {
+    L.leg = (warp == 0 && (lane >> 2) < n_local) ? (lane & 3) : -1; L.wl = lane >> 2;
+    const int cs = (warp - 1) * 4 + (lane >> 3);
+    L.col = ((warp == 1 || warp == 2) && (lane & 7) < 6 && cs < n_local) ? (lane & 7) : -1; L.wc = L.col >= 0 ? cs : 0;
+    L.w0 = 0; L.nw = n_local;
+    L.nsync = 32 * nwarps;
+  }
+}
+// does any env of the thread's group reset this step?  (uniform over the threads that share phase barriers)
+GO2_HD bool group_any_reset(const Lane& L, const WarpSmem* SM) {
+  bool any = false;
+  for (int k = 0; k < L.nw; ++k) any = any || (SM[L.w0 + k].reset != 0);
+  return any;
+}
 
 struct StepCtx {
   const Go2EnvConfig* cfg; const Go2Model* mdl; const Go2EnvBuffers* buf; const Go2StepParams* sp;
@@ -460,19 +507,21 @@ GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, 
 // ================================================================================================ one physics substep
 // `lane`/`L` come from the enclosing GO2_LANES_BEGIN; S is this warp's scratch.  last = last substep (report forces).
 #if defined(__CUDACC__)
-#define GO2_LANE_ARGS int lane, Lane& L
-#define GO2_LANE_PASS lane, L
+#define GO2_LANE_ARGS Lane& L
+#define GO2_LANE_PASS L
+#define GO2_L0 L
 #else
-#define GO2_LANE_ARGS Lane* lanes
-#define GO2_LANE_PASS lanes
+#define GO2_LANE_ARGS Lane* lanes, int NT
+#define GO2_LANE_PASS lanes, NT
+#define GO2_L0 lanes[0]
 #endif
 
-GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e, bool last) {
+GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool last) {
   const Go2EnvConfig* C = X.cfg;
   const Go2Model* M = X.mdl;
   const float dt = C->sim_dt;
   // ---- S1: joint lanes: sin/cos, limit targets; lane 12: base kinematics
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
       float q = S.q[lane];
       float sn, cn;
@@ -496,9 +545,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
       st3(S.vs[0], wb); st3(S.vs[0] + 3, vb);
     }
     if (lane >= 13 && lane < 13 + GO2_NUM_DYN) { for (int k = 0; k < 6; ++k) S.dv[lane - 13][k] = 0; }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- S2: leg lanes: ABA pass 1 and 2
-  GO2_LANES_BEGIN
+  GO2_LEGS {
     if (lane < 4) {
       V6 vpar; ld6(S.vs[0], vpar);
       M3 Rwp = ldm(S.Rw[0]); V3 pwp = ld3(S.pw[0]);
@@ -520,9 +569,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
       stm(S.legIA[lane], Iout.A); stm(S.legIA[lane] + 9, Iout.B); stm(S.legIA[lane] + 18, Iout.C);
       st6(S.legpA[lane], pout);
     }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- S3: base column lanes: assemble I^A_0, Cholesky, column k of the inverse, a0[k]
-  GO2_LANES_BEGIN
+  GO2_COLS {
     if (lane < 6) {
       Sym6 I0 = rigid_inertia(S.inertia);
       V6 v0; ld6(S.vs[0], v0);
@@ -551,10 +600,10 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
       for (int i = 0; i < 6; ++i) { L.Lcol[i] = x[i]; S.Lam0[6 * lane + i] = x[i]; acc += x[i] * pv[i]; }
       S.a0[lane] = -acc;
     }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- S5: leg lanes: pass 3, unconstrained velocities, mobility recursion
   GO2_MID_SYNC();
-  GO2_LANES_BEGIN
+  GO2_LEGS {
     if (lane < 4) {
       V6 a0; ld6(S.a0, a0);
       V6 v0; ld6(S.vs[0], v0);
@@ -572,9 +621,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
       leg_pass3<2>(lane, L, S, M, dt, ap, vmp, P, Q, R);
       if (lane == 0) st6(S.v[0], vm0);
     }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- S6: collider lanes: narrow phase + per-contact 3x3 mobility
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     {
       const int ci = lane;
       const int b = M->col_dyn[ci];
@@ -619,19 +668,19 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
         L.vt = vt;
       }
     }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- S7: mass-splitting count of the collider's group (base = colliders 0..7, leg l = 8+6l .. 13+6l)
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     {
       int g0 = lane < 8 ? 0 : 8 + 6 * ((lane - 8) / 6), gn = lane < 8 ? 8 : 6, cnt = 0;
       for (int k = 0; k < gn; ++k) cnt += S.active[g0 + k];
       L.gcount = (float)cnt;
     }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- Jacobi sweeps with exact propagation through the tree
   GO2_MID_SYNC();
   for (int it = 0; it < C->solver_iters; ++it) {
-    GO2_LANES_BEGIN
+    GO2_WIDE {
       if (L.act) {
         const int b = L.body;
         V3 r = mk(L.r[0], L.r[1], L.r[2]), n = mk(L.n[0], L.n[1], L.n[2]);
@@ -661,9 +710,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
         L.lam_hi = fminf(0.0f, L.lam_hi + (L.tgt_hi - cur) * Dj);
         S.tauimp[lane] = L.lam_lo + L.lam_hi;
       }
-    GO2_LANES_END
+    } GO2_SYNC();
     // inward: leg lanes gather their colliders' impulses (fixed order) and push them to the base
-    GO2_LANES_BEGIN
+    GO2_LEGS {
       if (lane < 4) {
         const int c0 = 8 + 6 * lane;
         V6 p2, p1, p0, out;
@@ -676,9 +725,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
         leg_imp_in<0>(lane, L, S, M, p0, out);
         st6(S.legp[lane], out);
       }
-    GO2_LANES_END
+    } GO2_SYNC();
     // base: dv0 = -Lam0 p0, one row per lane
-    GO2_LANES_BEGIN
+    GO2_COLS {
       if (lane < 6) {
         float p0[6] = {0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 8; ++c) for (int k = 0; k < 6; ++k) p0[k] -= S.fcol[c][k];
@@ -687,20 +736,20 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
         for (int k = 0; k < 6; ++k) acc += L.Lcol[k] * p0[k];
         S.dv[0][lane] = -acc;
       }
-    GO2_LANES_END
+    } GO2_SYNC();
     // outward: leg lanes
-    GO2_LANES_BEGIN
+    GO2_LEGS {
       if (lane < 4) {
         V6 dvp; ld6(S.dv[0], dvp);
         leg_imp_out<0>(lane, L, S, M, dvp);
         leg_imp_out<1>(lane, L, S, M, dvp);
         leg_imp_out<2>(lane, L, S, M, dvp);
       }
-    GO2_LANES_END
+    } GO2_SYNC();
   }
   // ---- S12: final velocities, joint velocity clamp, integration, contact force report
   GO2_MID_SYNC();
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
       float x = S.qdm[lane] + S.dqd[lane], vl = M->vel_limit[lane];
       x = fminf(fmaxf(x, -vl), vl);
@@ -740,13 +789,13 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e,
       float idt = 1.0f / dt;
       S.cf[b][0] = f.x * idt; S.cf[b][1] = f.y * idt; S.cf[b][2] = f.z * idt;
     }
-  GO2_LANES_END
+  } GO2_SYNC();
 }
 
 // feet position / velocity at the current configuration (rigid_body_states refresh, legged_robot.py:109)
-GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X) {
+GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   const Go2Model* M = X.mdl;
-  GO2_LANES_BEGIN
+  GO2_LEGS {
     if (lane < 4) {
       M3 Rw = quat_to_mat(S.root[3], S.root[4], S.root[5], S.root[6]);
       V3 pw = ld3(S.root);
@@ -773,7 +822,7 @@ GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X) {
       st3(S.feet[lane], pw + mul(Rw, r));
       st3(S.feet[lane] + 3, mul(Rw, v.l + cross(v.a, r)));
     }
-  GO2_LANES_END
+  } GO2_SYNC();
 }
 
 // ================================================================================================ commands / reset (lane 0)
@@ -848,12 +897,12 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
 #endif
 
 // reset_idx for this env (legged_robot.py:180-245, :620-707, :1143-1169); `initial` = the reset at construction
-GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e, bool initial) {
+GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool initial) {
   const Go2EnvConfig* C = X.cfg;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
-  const uint32_t ge = (uint32_t)(C->env_offset + e);
-  GO2_LANES_BEGIN
+  GO2_WIDE if (initial || S.reset) {   // only the envs of the group that reset
+    const uint32_t ge = (uint32_t)(C->env_offset + e);
     if (lane < GO2_NUM_DOF) {
       const size_t o = (size_t)e * GO2_NUM_DOF + lane;
       U4 r = philox(ge, sp->common_step_counter, ST_RESET_DR, (uint32_t)lane, C->seed_lo, C->seed_hi);
@@ -907,14 +956,14 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e, bo
       S.acc_xy[0] = 0; S.acc_xy[1] = 0;
       resample_commands(S, X, e, ST_CMD_RESET);
     }
-  GO2_LANES_END
+  } GO2_SYNC();
 }
 
 // ================================================================================================ load / store
-GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
+GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cfg;
   const Go2EnvBuffers* B = X.buf;
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     for (int i = lane; i < GO2_NUM_DYN * GO2_INERTIA_STRIDE; i += 32) S.inertia[i] = GO2_LDG(B->body_inertia + (size_t)e * GO2_NUM_DYN * GO2_INERTIA_STRIDE + i);
     if (lane < 13) S.root[lane] = B->root_states[(size_t)e * 13 + lane];
     if (lane < GO2_NUM_DOF) {
@@ -940,12 +989,12 @@ GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
         S.delay_start = (int)(philox((uint32_t)(C->env_offset + e), X.sp->common_step_counter, ST_DELAY, 0, C->seed_lo, C->seed_hi).x % (uint32_t)(C->decimation + 1));
     }
     for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) S.cf[i / 3][i % 3] = B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i];
-  GO2_LANES_END
+  } GO2_SYNC();
 }
 
-GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
+GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   const Go2EnvBuffers* B = X.buf;
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     if (lane < 13) B->root_states[(size_t)e * 13 + lane] = S.root[lane];
     if (lane < GO2_NUM_DOF) {
       const size_t o = (size_t)e * GO2_NUM_DOF + lane;
@@ -966,14 +1015,14 @@ GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       if (k < 3) B->feet_pos[(size_t)e * 12 + l * 3 + k] = S.feet[l][k];
       else B->feet_vel[(size_t)e * 12 + l * 3 + (k - 3)] = S.feet[l][k];
     }
-  GO2_LANES_END
+  } GO2_SYNC();
 }
 
 // torques for the current substep (legged_robot.py:74-81, :594-618, control_type 'P')
-GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int sub) {
+GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, int sub) {
   const Go2EnvConfig* C = X.cfg;
   const Go2Model* M = X.mdl;
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
       float a_in = (C->randomize_action_delay && sub < S.delay_start) ? S.lact[lane] : S.act[lane];
       float t = L.kp * (a_in * C->action_scale + C->default_dof_pos[lane] - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
@@ -983,26 +1032,25 @@ GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int su
       S.tq[lane] = t;                               // what the reference reports (legged_robot.py:79-81)
       S.tau[lane] = fminf(fmaxf(t, -lim), lim);     // effort clamp of the actuator (physics spec)
     }
-  GO2_LANES_END
+  } GO2_SYNC();
 }
 
 // ================================================================================================ the full step
-GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
+GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cfg;
   const Go2Model* M = X.mdl;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
-  const uint32_t ge = (uint32_t)(C->env_offset + e);
-  load_env(GO2_LANE_PASS, S, X, e);
+  load_env(GO2_LANE_PASS, SM, X);
   for (int sub = 0; sub < C->decimation; ++sub) {
     GO2_COARSE_SYNC();
-    compute_torques(GO2_LANE_PASS, S, X, sub);
-    physics_substep(GO2_LANE_PASS, S, X, e, sub == C->decimation - 1);
+    compute_torques(GO2_LANE_PASS, SM, X, sub);
+    physics_substep(GO2_LANE_PASS, SM, X, sub == C->decimation - 1);
   }
   GO2_COARSE_SYNC();
-  feet_kinematics(GO2_LANE_PASS, S, X);
+  feet_kinematics(GO2_LANE_PASS, SM, X);
   // ---- post_physics_step (legged_robot.py:102-142)
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     // height scan (legged_robot.py:1188-1224, math.py:8-12): yaw-only rotation of the body-frame grid
     if (C->mesh_type == 0) {
       for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) S.heights[i] = 0;
@@ -1033,8 +1081,8 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       S.max_move = fmaxf(S.max_move, sqrtf(dx * dx + dy * dy));
       if (S.resamp_step <= 0.0f && S.ep_len < C->max_episode_length - 1) resample_commands(S, X, e, ST_CMD_CB);
     }
-  GO2_LANES_END
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  GO2_WIDE {
     {
       float sh = 0;
       for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) sh += S.heights[i] * C->base_height_mask[i];
@@ -1058,8 +1106,8 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       const float* f = S.cf[3 + 4 * l + k];
       S.coll[lane - 16] = (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
     }
-  GO2_LANES_END
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  GO2_WIDE {
     if (lane == 0) {
       float sh = 0;
       for (int k = 0; k < 32; ++k) sh += S.part[k];
@@ -1069,16 +1117,16 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       S.tout = S.ep_len > C->max_episode_length;
       S.reset = term || S.tout;
     }
-  GO2_LANES_END
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  GO2_LEGS {
     if (lane < 4) {  // feet_regulation per foot, legged_robot.py:1404-1414
       const float* fp = S.feet[lane];
       float f2b = (fp[0] - S.root[0]) * S.pg[0] + (fp[1] - S.root[1]) * S.pg[1] + (fp[2] - S.root[2]) * S.pg[2];
       float fh = fmaxf(S.base_height - f2b, 0.0f);
       S.fterm[lane] = (fp[3] * fp[3] + fp[4] * fp[4]) * expf(-fh / (0.025f * C->base_height_target));
     }
-  GO2_LANES_END
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  GO2_WIDE {
     if (lane == 0) {
       float tv[GO2_NUM_REW];
       float ds_on = (C->terrain_curriculum && C->dynamic_sigma && C->mesh_type != 0) ? 1.0f : 0.0f;
@@ -1116,19 +1164,16 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       }
       S.rew = rew;
     }
-  GO2_LANES_END
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  GO2_WIDE {
     if (lane < GO2_NUM_REW) B->episode_sums[(size_t)e * GO2_NUM_REW + lane] += S.termv[lane];
     if (lane == 31) B->rew_buf[e] = S.rew;
-  GO2_LANES_END
-#if defined(__CUDACC__)
-  { const int ns = L.nsync; L.nsync = 0; if (S.reset) reset_phases(GO2_LANE_PASS, S, X, e, false); L.nsync = ns; }   // per-env branch: warp-level phases
-#else
-  if (S.reset) reset_phases(GO2_LANE_PASS, S, X, e, false);
-#endif
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  if (group_any_reset(GO2_L0, SM)) reset_phases(GO2_LANE_PASS, SM, X, false);   // uniform over the group; items are predicated by their env
+  GO2_WIDE {
     if (lane == 0) {
       if (C->push_robots && (S.ep_len % C->push_interval == 0)) {  // _push_robots, legged_robot.py:709-724
+        const uint32_t ge = (uint32_t)(C->env_offset + e);
         U4 p0 = philox(ge, sp->common_step_counter, ST_PUSH, 0, C->seed_lo, C->seed_hi);
         U4 p1 = philox(ge, sp->common_step_counter, ST_PUSH, 1, C->seed_lo, C->seed_hi);
         float mv = C->max_push_vel_xy, ma = C->max_push_ang_vel;
@@ -1140,9 +1185,9 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW, (float)S.level);
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW + 1 + S.tid, (float)S.level);
     }
-  GO2_LANES_END
+  } GO2_SYNC();
   // ---- compute_observations (go2_env.py:23-53) + clip (legged_robot.py:96-99); rows are written coalesced
-  GO2_LANES_BEGIN
+  GO2_WIDE {
     for (int i = lane; i < GO2_NUM_PRIV; i += 32) {
       float x;
       if (i < 3) x = S.blv[i] * C->obs_scale_lin_vel;
@@ -1161,6 +1206,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
       if (i >= 3 && i < 48) {
         const int o = i - 3;
         if (C->add_noise) {
+          const uint32_t ge = (uint32_t)(C->env_offset + e);
           U4 r = philox(ge, sp->common_step_counter, ST_NOISE, (uint32_t)(o / 4), C->seed_lo, C->seed_hi);
           x = GO2_FADD(x, GO2_FMUL(GO2_FADD(GO2_FMUL(2.0f, u01(pick(r, o % 4))), -1.0f), C->noise_scale_vec[o]));
         }
@@ -1169,40 +1215,40 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
     }
     for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) B->measured_heights[(size_t)e * GO2_NUM_HEIGHT + i] = S.heights[i];
     if (lane < 3) { B->base_lin_vel[(size_t)e * 3 + lane] = S.blv[lane]; B->base_ang_vel[(size_t)e * 3 + lane] = S.bav[lane]; B->projected_gravity[(size_t)e * 3 + lane] = S.pg[lane]; }
-  GO2_LANES_END
-  GO2_LANES_BEGIN
+  } GO2_SYNC();
+  GO2_WIDE {
     if (lane < GO2_NUM_DOF) { S.lact[lane] = S.act[lane]; S.lqd[lane] = S.qd[lane]; }
-  GO2_LANES_END
-  store_state(GO2_LANE_PASS, S, X, e);
+  } GO2_SYNC();
+  store_state(GO2_LANE_PASS, SM, X);
 }
 
 // reset_idx(all envs) at construction (base_task.py:82-86; the zero-action step that follows is issued by the caller)
-GO2_HD void reset_env_initial(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e) {
-  load_env(GO2_LANE_PASS, S, X, e);
-  GO2_LANES_BEGIN
+GO2_HD void reset_env_initial(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+  load_env(GO2_LANE_PASS, SM, X);
+  GO2_WIDE {
     if (lane == 0) { S.tout = 0; }
     if (lane < 4) for (int k = 0; k < 6; ++k) S.feet[lane][k] = 0;
-  GO2_LANES_END
-  reset_phases(GO2_LANE_PASS, S, X, e, true);
-  feet_kinematics(GO2_LANE_PASS, S, X);
-  store_state(GO2_LANE_PASS, S, X, e);
+  } GO2_SYNC();
+  reset_phases(GO2_LANE_PASS, SM, X, true);
+  feet_kinematics(GO2_LANE_PASS, SM, X);
+  store_state(GO2_LANE_PASS, SM, X);
 }
 
 // n physics substeps with given joint torques (dynamics parity in isolation)
-GO2_HD void substeps_env(GO2_LANE_ARGS, WarpSmem& S, const StepCtx& X, int e, const float* tau_in, int n) {
+GO2_HD void substeps_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, const float* tau_in, int n) {
   const Go2Model* M = X.mdl;
-  load_env(GO2_LANE_PASS, S, X, e);
+  load_env(GO2_LANE_PASS, SM, X);
   for (int s = 0; s < n; ++s) {
-    GO2_LANES_BEGIN
+    GO2_WIDE {
       if (lane < GO2_NUM_DOF) { float lim = M->effort[lane]; S.tau[lane] = fminf(fmaxf(tau_in[(size_t)e * GO2_NUM_DOF + lane], -lim), lim); }
-    GO2_LANES_END
-    physics_substep(GO2_LANE_PASS, S, X, e, s == n - 1);
+    } GO2_SYNC();
+    physics_substep(GO2_LANE_PASS, SM, X, s == n - 1);
   }
-  feet_kinematics(GO2_LANE_PASS, S, X);
-  GO2_LANES_BEGIN
+  feet_kinematics(GO2_LANE_PASS, SM, X);
+  GO2_WIDE {
     if (lane == 0) { S.reset = X.buf->reset_buf[e]; S.tout = X.buf->time_out_buf[e]; }
-  GO2_LANES_END
-  store_state(GO2_LANE_PASS, S, X, e);
+  } GO2_SYNC();
+  store_state(GO2_LANE_PASS, SM, X);
 }
 
 }  // namespace go2

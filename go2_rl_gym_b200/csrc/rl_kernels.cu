@@ -131,9 +131,10 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 // mu [N,A] -> actions [N,A], logp [N], mu_out, sigma_out [N,A].  z from Philox(seed; env, step, stream 16, block).
 __global__ void sample_actions_kernel(const float* __restrict__ mu, const float* __restrict__ std_param, float* __restrict__ actions,
                                       float* __restrict__ logp, float* __restrict__ mu_out, float* __restrict__ sigma_out, int N, int A,
-                                      uint32_t seed_lo, uint32_t seed_hi, uint32_t step, int env_offset) {
+                                      uint32_t seed_lo, uint32_t seed_hi, uint32_t step, const uint32_t* __restrict__ d_step, int env_offset) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
+  if (d_step) step = *d_step;      // device-resident step counter (CUDA-graph replays of the rollout)
   float lp = 0;
   for (int b = 0; b < (A + 3) / 4; ++b) {
     U4 r = philox((uint32_t)(env_offset + e), step, 16u, (uint32_t)b, seed_lo, seed_hi);
@@ -483,7 +484,17 @@ int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratc
 int go2_sample_actions(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A,
                        uint64_t seed, uint32_t step, int env_offset, void* stream) {
   sample_actions_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, std_param, actions, logp, mu_out, sigma_out, N, A, (uint32_t)seed,
-                                                                         (uint32_t)(seed >> 32), step, env_offset);
+                                                                         (uint32_t)(seed >> 32), step, nullptr, env_offset);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int go2_sample_actions_dev(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A,
+                           uint64_t seed, const uint32_t* d_step, int env_offset, void* stream) {
+  if (!d_step) return set_error(1, "go2_sample_actions_dev: null step pointer");
+  sample_actions_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, std_param, actions, logp, mu_out, sigma_out, N, A, (uint32_t)seed,
+                                                                         (uint32_t)(seed >> 32), 0u, d_step, env_offset);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -95,7 +95,6 @@ class LeggedRobot:
         self.reward_curriculum_configs = list(cfg.rewards.curriculum_rewards or [])
         self.reward_curriculum_scales = {c["reward_name"]: c["start_value"] for c in self.reward_curriculum_configs}
         self.zero_command_proba = 0.0
-        self._stream = 0  # legacy default stream: ordered with torch's current stream
         self._ep_names = ["rew_" + n for n in _abi.REWARD_NAMES if n in A.reward_scales]
         self._ep_cols = [k for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales]
         # ---- library handle
@@ -103,6 +102,11 @@ class LeggedRobot:
         _abi.check(self._lib.go2_env_create(ctypes.byref(A.config), ctypes.byref(A.model), ctypes.byref(A.buffers), ctypes.byref(h)), self._lib)
         self._h = h
         self.init_done = True
+
+    @property
+    def _stream(self):
+        """Kernels are launched on torch's current stream (the capture stream while a CUDA graph is being recorded)."""
+        return torch.cuda.current_stream().cuda_stream
 
     # episode_length_buf is re-ASSIGNED by the runner (on_policy_runner.py:118): keep the device row the kernel owns
     @property
@@ -160,6 +164,51 @@ class LeggedRobot:
         self._fill_extras(slot)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
+    # ---- rollout with device-resident step parameters (CUDA-graph capturable: nothing in a launch depends on host values) -------
+    def begin_rollout(self, T):
+        """Upload the parameter blocks of the next T steps (Go2StepParams[T], exactly what T step() calls would pass) and advance the
+        host counters past them.  Returns False when this rollout has to step eagerly: a command-range curriculum boundary
+        (legged_robot.py:433-446) rewrites env_command_ranges from the host in the middle of the rollout."""
+        A = self._A
+        it_end = (self.common_step_counter + T) // self.num_steps_per_env
+        if any(it_end >= entry["iter"] for entry in A.command_range_curriculum):
+            return False
+        blocks = (_abi.Go2StepParams * T)()
+        slots = []
+        for t in range(T):
+            self.common_step_counter += 1
+            self.update_reward_curriculum()
+            slot = self.common_step_counter % EP_SLOTS
+            blocks[t] = A.step_params(self.common_step_counter, ep_slot=slot, reward_curriculum=self.reward_curriculum_scales)
+            slots.append(slot)
+        self.zero_command_proba = blocks[T - 1].zero_command_proba
+        nbytes = ctypes.sizeof(_abi.Go2StepParams) * T
+        if getattr(self, "_sp_dev", None) is None or self._sp_dev.numel() != nbytes:
+            self._sp_dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self._sp_dev.copy_(torch.frombuffer(bytearray(blocks), dtype=torch.uint8), non_blocking=False)
+        self._rollout_slots = slots
+        return True
+
+    def step_dev(self, actions, t):
+        """Step t of the rollout opened by begin_rollout(): same kernel as step(), parameters read from the device block t."""
+        a = actions
+        if a.dtype != torch.float32 or not a.is_contiguous():
+            a = a.to(torch.float32).contiguous()
+        sp = self._sp_dev.data_ptr() + t * ctypes.sizeof(_abi.Go2StepParams)
+        _abi.check(self._lib.go2_env_step_dev(self._h, a.data_ptr(), sp, self._stream), self._lib)
+        self._last_actions_in = a
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def end_rollout(self):
+        """extras of the rollout's steps (what step() would have returned in infos['episode'] at each of them)."""
+        eps = []
+        for slot in self._rollout_slots:
+            self._fill_extras(slot)
+            eps.append(self.extras["episode"])
+        return eps
+
     def step_host(self, actions_np, obs_out, priv_out, rew_out, reset_out):
         """Same step through HOST buffers (numpy, ideally pinned): H2D, kernel, D2H inside the C call (bench e2e)."""
         self.common_step_counter += 1
@@ -189,6 +238,10 @@ class LeggedRobot:
         self.extras["episode_valid"] = row[_abi.NUM_REW + 11]
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self.time_out_buf
+
+    def set_step_mode(self, mode):
+        """Thread map of the step kernel: "P2" (default), "P3", "8p", "4" — identical results, different speed (tuning / tests)."""
+        _abi.check(self._lib.go2_env_set_step_mode(self._h, str(mode).encode()), self._lib)
 
     def substeps(self, tau, n):
         """n bare physics substeps under given joint torques (tests)."""

@@ -19,6 +19,7 @@ _SIGS = {
     "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
     "go2_colsum": [_vp, _i, _vp, _i, _i, _vp, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
+    "go2_sample_actions_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, _vp, _i, _vp],
     "go2_process_env_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp],
     "go2_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp],
     "go2_adv_normalize": [_vp, _l, _vp, C.c_double, _vp],
@@ -64,6 +65,15 @@ def call(name, *args):
 
 def ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+def upload_steps(buf, first, T, device):
+    """int32 device array {first + 1, ..., first + T}: per-step Philox counters of a graph-replayed rollout."""
+    host = torch.arange(first + 1, first + T + 1, dtype=torch.int64).to(torch.int32)     # wraps like the uint32 kernel argument
+    if buf is None or buf.numel() != T:
+        buf = torch.zeros(T, dtype=torch.int32, device=device)
+    buf.copy_(host)
+    return buf
 
 
 def use_tc():

@@ -46,6 +46,7 @@ class CTS:
         self.inv_perm[self.perm] = torch.arange(num_envs, device=device)                             # env -> storage row
         self.seed, self.env_offset = int(seed), int(env_offset)
         self._act_step = 0
+        self._dev_steps = None
         self.world_size = dist_utils.world_size()
         self.optimizer1 = self.optimizer2 = None
 
@@ -105,6 +106,17 @@ class CTS:
         m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, x_ones=self._xc.shape[1] > D + m.num_critic_obs)
 
     # ---- rollout -------------------------------------------------------------------------------------------------------
+    def begin_rollout(self, T):
+        """See PPO.begin_rollout: device-resident sampling counters for a graph-replayed rollout."""
+        self._dev_steps = _ops.upload_steps(getattr(self, "_dev_steps_buf", None), self._act_step, T, self.device)
+        self._dev_steps_buf = self._dev_steps
+        self._act_step += T
+        self.model.mark_dirty()
+
+    def end_rollout(self, T):
+        self._dev_steps = None
+        self.storage.step = T
+
     def act(self, obs, privileged_obs, history):
         st, t, m = self.storage, self.storage.step, self.model
         if t >= st.num_transitions_per_env:
@@ -118,9 +130,13 @@ class CTS:
         self._latents(st.privileged_observations[t], st.history[t], nt, ns)
         self._heads(st.observations[t], st.privileged_observations[t], N)
         st.values[t].copy_(self._val[:N])
-        self._act_step += 1
-        call("go2_sample_actions", ptr(self._mu), ptr(m.std.data), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
-             N, A, self.seed, self._act_step, self.env_offset)
+        if self._dev_steps is not None:      # rollout opened by begin_rollout(): the Philox step counter comes from device memory
+            call("go2_sample_actions_dev", ptr(self._mu), ptr(m.std.data), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
+                 N, A, self.seed, self._dev_steps.data_ptr() + 4 * t, self.env_offset)
+        else:
+            self._act_step += 1
+            call("go2_sample_actions", ptr(self._mu), ptr(m.std.data), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
+                 N, A, self.seed, self._act_step, self.env_offset)
         call("go2_gather_rows", ptr(st.actions[t]), A, ptr(self.inv_perm), ptr(self._actions_env), A, 0, N)   # back to env order
         return self._actions_env
 

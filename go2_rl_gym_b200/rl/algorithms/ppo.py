@@ -40,6 +40,7 @@ class PPO:
         self.seed = int(seed)
         self.env_offset = int(env_offset)
         self._act_step = 0
+        self._dev_steps = None
         self._opt_step = 0
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.optimizer = None  # Adam state lives in flat vectors; see optimizer_state_dict()
@@ -74,6 +75,18 @@ class PPO:
         self.actor_critic.train()
 
     # ---- rollout ---------------------------------------------------------------------------------------------
+    def begin_rollout(self, T):
+        """The next T act() calls read their sampling step counter from a device array (same values act() would pass by value), so the
+        whole rollout can be replayed as one CUDA graph.  end_rollout() returns to host-side counters."""
+        self._dev_steps = _ops.upload_steps(getattr(self, "_dev_steps_buf", None), self._act_step, T, self.device)
+        self._dev_steps_buf = self._dev_steps
+        self._act_step += T
+        self.actor_critic.actor_engine.mark_dirty(); self.actor_critic.critic_engine.mark_dirty()    # the graph always refreshes the padded weights
+
+    def end_rollout(self, T):
+        self._dev_steps = None
+        self.storage.step = T
+
     def act(self, obs, critic_obs):
         st, t, ac = self.storage, self.storage.step, self.actor_critic
         if t >= st.num_transitions_per_env:
@@ -83,9 +96,13 @@ class PPO:
         (st.privileged_observations if st.privileged_observations is not None else st.observations)[t].copy_(critic_obs)
         mu = ac._actor_forward(st.observations[t])
         ac.evaluate(critic_obs, out=st.values[t])
-        self._act_step += 1
-        _ops.call("go2_sample_actions", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
-                  _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._act_step, self.env_offset)
+        if self._dev_steps is not None:      # rollout opened by begin_rollout(): the Philox step counter comes from device memory
+            _ops.call("go2_sample_actions_dev", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
+                      _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._dev_steps.data_ptr() + 4 * t, self.env_offset)
+        else:
+            self._act_step += 1
+            _ops.call("go2_sample_actions", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
+                      _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._act_step, self.env_offset)
         self.transition.actions = st.actions[t]
         self.transition.values = st.values[t]
         return st.actions[t]

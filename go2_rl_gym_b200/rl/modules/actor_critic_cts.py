@@ -140,7 +140,8 @@ class _CTSBase(nn.Module):
     # ---- reference API --------------------------------------------------------------------------------------------
     def reset(self, dones=None):
         if dones is not None:
-            self.history[dones > 0] = 0.0
+            # masked_fill_ with a broadcast mask: no nonzero() / host sync (the reference's boolean-index assignment, actor_critic_cts.py:100-101)
+            self.history.masked_fill_((dones > 0).view(-1, *([1] * (self.history.dim() - 1))), 0.0)
 
     def forward(self):
         raise NotImplementedError

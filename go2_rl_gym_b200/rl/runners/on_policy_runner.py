@@ -12,6 +12,7 @@ from pathlib import Path
 import torch
 import yaml
 
+from .. import _ops
 from ..algorithms import PPO
 from ..modules import ActorCritic
 from ...envs.env_arrays import class_to_dict
@@ -56,22 +57,59 @@ class OnPolicyRunner:
         # per-iteration device-side episode log: [T, N] finished-episode returns / lengths (NaN where no episode ended)
         self._done_rew = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
         self._done_len = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
+        self._rollout_graphs = _ops.GraphSet()
 
-    def run_iteration(self, sync=None):
-        """One un-logged iteration (rollout + returns + update) — the timing loop of bench.py / tools."""
+    # ---- rollout (on_policy_runner.py:136-153) -----------------------------------------------------------------------------
+    def _rollout_steps(self, log, dev):
+        """The num_steps_per_env act -> step -> process_env_step loop.  dev: step parameters / sampling counters are device-resident
+        (begin_rollout), so the launch sequence depends on nothing the host computes per step and can be captured in one CUDA graph."""
         env, alg = self.env, self.alg
         obs, priv = env.get_observations(), env.get_privileged_observations()
         cobs = priv if priv is not None else obs
+        nan = float("nan")
+        ep_infos = []
+        alg.storage.step = 0
+        for i in range(self.num_steps_per_env):
+            actions = alg.act(obs, cobs)
+            obs, priv, rewards, dones, infos = env.step_dev(actions, i) if dev else env.step(actions)
+            cobs = priv if priv is not None else obs
+            alg.process_env_step(rewards, dones, infos)
+            if log:
+                if not dev and 'episode' in infos:
+                    ep_infos.append(infos['episode'])
+                self._cur_reward_sum += rewards
+                self._cur_episode_length += 1
+                self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
+                self._done_len[i] = torch.where(dones, self._cur_episode_length, nan)
+                self._cur_reward_sum *= ~dones
+                self._cur_episode_length *= ~dones
+        return ep_infos
+
+    def collect(self, log=False):
+        """One rollout.  Replayed as a single CUDA graph (GO2_GRAPH=0 or an env without begin_rollout: eager per-step launches).
+        Returns the list of per-step infos['episode'] dicts when logging."""
+        env, alg, T = self.env, self.alg, self.num_steps_per_env
         with torch.inference_mode():
-            for _ in range(self.num_steps_per_env):
-                actions = alg.act(obs, cobs)
-                obs, priv, rewards, dones, infos = env.step(actions)
-                cobs = priv if priv is not None else obs
-                alg.process_env_step(rewards, dones, infos)
+            if self._rollout_graphs.enabled and hasattr(env, "begin_rollout") and env.begin_rollout(T):
+                alg.begin_rollout(T)
+                try:
+                    self._rollout_graphs.run(("rollout", bool(log)), lambda: self._rollout_steps(log, True))
+                finally:
+                    alg.end_rollout(T)
+                ep_infos = env.end_rollout()
+                return ep_infos if log else []
+            return self._rollout_steps(log, False)
+
+    def run_iteration(self, sync=None):
+        """One un-logged iteration (rollout + returns + update) — the timing loop of bench.py / tools."""
+        self.collect(False)
+        priv = self.env.get_privileged_observations()
+        cobs = priv if priv is not None else self.env.get_observations()
+        with torch.inference_mode():
             if sync is not None:
                 sync()
-            alg.compute_returns(cobs)
-        return alg.update()
+            self.alg.compute_returns(cobs)
+        return self.alg.update()
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         if self.log_dir is not None and self.writer is None and SummaryWriter is not None:
@@ -89,21 +127,10 @@ class OnPolicyRunner:
         it = self.current_learning_iteration
         for it in range(self.current_learning_iteration, tot_iter):
             start = time.time()
+            ep_infos = self.collect(log=self.log_dir is not None)
+            privileged_obs = self.env.get_privileged_observations()
+            critic_obs = privileged_obs if privileged_obs is not None else self.env.get_observations()
             with torch.inference_mode():
-                for i in range(self.num_steps_per_env):
-                    actions = self.alg.act(obs, critic_obs)
-                    obs, privileged_obs, rewards, dones, infos = self.env.step(actions)
-                    critic_obs = privileged_obs if privileged_obs is not None else obs
-                    self.alg.process_env_step(rewards, dones, infos)
-                    if self.log_dir is not None:
-                        if 'episode' in infos:
-                            ep_infos.append(infos['episode'])
-                        self._cur_reward_sum += rewards
-                        self._cur_episode_length += 1
-                        self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
-                        self._done_len[i] = torch.where(dones, self._cur_episode_length, nan)
-                        self._cur_reward_sum *= ~dones
-                        self._cur_episode_length *= ~dones
                 if self.log_dir is not None:  # one fetch per iteration, time-major order like the reference's per-step extend
                     dr, dl = self._done_rew.flatten(), self._done_len.flatten()
                     keep = ~torch.isnan(dr)

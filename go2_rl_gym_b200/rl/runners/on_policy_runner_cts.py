@@ -42,6 +42,7 @@ class OnPolicyRunnerCTS:
         self._cur_reward_sum, self._cur_episode_length = torch.zeros(N, device=device), torch.zeros(N, device=device)
         self._done_rew = torch.full((self.num_steps_per_env, N), float("nan"), device=device)
         self._done_len = torch.full((self.num_steps_per_env, N), float("nan"), device=device)
+        self._rollout_graphs = _ops.GraphSet()
         self._is_teacher = torch.zeros(N, dtype=torch.bool, device=device)
         self._is_teacher[self.alg.teacher_env_idxs] = True
 
@@ -49,22 +50,56 @@ class OnPolicyRunnerCTS:
         d8 = None if dones is None else (dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8))
         _ops.call("go2_history_update", _ops.ptr(self.history), _ops.ptr(obs), _ops.ptr(d8), self.env.num_envs, self.history_length, self.env.num_obs)
 
+    # ---- rollout (on_policy_runner_cts.py:147-170) -------------------------------------------------------------------------
+    def _rollout_steps(self, log, dev):
+        """act -> step -> history roll -> process_env_step, num_steps_per_env times.  dev: device-resident step parameters / sampling
+        counters (begin_rollout), i.e. a launch sequence that can be captured in one CUDA graph."""
+        env, alg = self.env, self.alg
+        obs, priv = env.get_observations(), env.get_privileged_observations()
+        nan = float("nan")
+        ep_infos = []
+        alg.storage.step = 0
+        for i in range(self.num_steps_per_env):
+            actions = alg.act(obs, priv, self.history.flatten(1))
+            obs, priv, rewards, dones, infos = env.step_dev(actions, i) if dev else env.step(actions)
+            self._roll_history(obs, dones)
+            alg.process_env_step(rewards, dones, infos)
+            if log:
+                if not dev and 'episode' in infos:
+                    ep_infos.append(infos['episode'])
+                self._cur_reward_sum += rewards
+                self._cur_episode_length += 1
+                self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
+                self._done_len[i] = torch.where(dones, self._cur_episode_length, nan)
+                self._cur_reward_sum *= ~dones
+                self._cur_episode_length *= ~dones
+        return ep_infos
+
+    def collect(self, log=False):
+        """One rollout, replayed as a single CUDA graph when possible (see OnPolicyRunner.collect)."""
+        env, alg, T = self.env, self.alg, self.num_steps_per_env
+        with torch.inference_mode():
+            if self._rollout_graphs.enabled and hasattr(env, "begin_rollout") and env.begin_rollout(T):
+                alg.begin_rollout(T)
+                try:
+                    self._rollout_graphs.run(("rollout", bool(log)), lambda: self._rollout_steps(log, True))
+                finally:
+                    alg.end_rollout(T)
+                ep_infos = env.end_rollout()
+                return ep_infos if log else []
+            return self._rollout_steps(log, False)
+
     def run_iteration(self, sync=None):
         """One un-logged iteration (rollout + returns + both update passes) — the timing loop of bench.py / tools."""
         env, alg = self.env, self.alg
-        obs, priv = env.get_observations(), env.get_privileged_observations()
         if not getattr(self, "_hist_primed", False):
-            self._roll_history(obs, None)
+            self._roll_history(env.get_observations(), None)
             self._hist_primed = True
+        self.collect(False)
         with torch.inference_mode():
-            for _ in range(self.num_steps_per_env):
-                actions = alg.act(obs, priv, self.history.flatten(1))
-                obs, priv, rewards, dones, infos = env.step(actions)
-                self._roll_history(obs, dones)
-                alg.process_env_step(rewards, dones, infos)
             if sync is not None:
                 sync()
-            alg.compute_returns(priv, self.history.flatten(1))
+            alg.compute_returns(env.get_privileged_observations(), self.history.flatten(1))
         return alg.update()
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
@@ -83,21 +118,9 @@ class OnPolicyRunnerCTS:
         it = self.current_learning_iteration
         for it in range(self.current_learning_iteration, tot_iter):
             start = time.time()
+            ep_infos = self.collect(log=self.log_dir is not None)
+            privileged_obs = self.env.get_privileged_observations()
             with torch.inference_mode():
-                for i in range(self.num_steps_per_env):
-                    actions = self.alg.act(obs, privileged_obs, self.history.flatten(1))
-                    obs, privileged_obs, rewards, dones, infos = self.env.step(actions)
-                    self._roll_history(obs, dones)
-                    self.alg.process_env_step(rewards, dones, infos)
-                    if self.log_dir is not None:
-                        if 'episode' in infos:
-                            ep_infos.append(infos['episode'])
-                        self._cur_reward_sum += rewards
-                        self._cur_episode_length += 1
-                        self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
-                        self._done_len[i] = torch.where(dones, self._cur_episode_length, nan)
-                        self._cur_reward_sum *= ~dones
-                        self._cur_episode_length *= ~dones
                 if self.log_dir is not None:
                     for who, mask in (("teacher", self._is_teacher), ("student", ~self._is_teacher)):
                         dr, dl = self._done_rew[:, mask].flatten(), self._done_len[:, mask].flatten()

@@ -168,8 +168,13 @@ typedef struct Go2Env Go2Env;
 /* Replaces gym.create_sim/prepare_sim + acquire_*_tensor (legged_robot.py:292-310,769-787). 0 on success. */
 int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvBuffers* bufs, Go2Env** out);
 void go2_env_destroy(Go2Env* env);
+/* Thread map of the fused step kernel: "P2" (default; 8 envs packed per CTA), "P3", "8p", "4" (warp per env).  Same results bit for bit. */
+int go2_env_set_step_mode(Go2Env* env, const char* mode);
 /* Replaces LeggedRobot.step (legged_robot.py:60-100): the fused kernel. actions: device [N,12]. */
 int go2_env_step(Go2Env* env, const float* actions, const Go2StepParams* sp, void* cuda_stream);
+/* Same, with the step parameters already in DEVICE memory (d_sp): nothing in the launch depends on host values, so a whole rollout
+ * (OnPolicyRunner.learn's 24-step loop, on_policy_runner.py:136-153) can be captured in one CUDA graph over an array of parameter blocks. */
+int go2_env_step_dev(Go2Env* env, const float* actions, const Go2StepParams* d_sp, void* cuda_stream);
 /* Same, HOST buffers: H2D of actions, kernel, D2H of obs/priv/rew/reset inside the call (bench e2e). */
 int go2_env_step_host(Go2Env* env, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv,
                       float* h_rew, uint8_t* h_reset, void* cuda_stream);
@@ -208,6 +213,8 @@ int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, in
 int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */
 int go2_sample_actions(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A, uint64_t seed, uint32_t step, int env_offset, void* stream);
+/* same, the step counter read from device memory (rollout captured in a CUDA graph) */
+int go2_sample_actions_dev(const float* mu, const float* std_param, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A, uint64_t seed, const uint32_t* d_step, int env_offset, void* stream);
 /* PPO.process_env_step (ppo.py:104-111): rewards += gamma V time_out; rows of the transition */
 int go2_process_env_step(const float* rew, const uint8_t* dones, const uint8_t* time_outs, const float* values, float* rew_out, uint8_t* dones_out, int N, float gamma, const int64_t* perm, void* stream);
 /* RolloutStorage.compute_returns (rollout_storage.py:123-134), all [T,N]; stats[2] (double) receives sum / sum of squares of adv */

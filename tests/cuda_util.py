@@ -12,13 +12,15 @@ STATE = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "last_l
 
 
 class CudaEnv:
-    def __init__(self, arrays):
+    def __init__(self, arrays, mode=None):
         assert arrays.device.type == "cuda"
         self.A = arrays
         self.lib = _abi.load_library()
         self.h = C.c_void_p()
         _abi.check(self.lib.go2_env_create(C.byref(arrays.config), C.byref(arrays.model), C.byref(arrays.buffers), C.byref(self.h)), self.lib)
         self.common_step_counter = 0
+        if mode is not None:
+            _abi.check(self.lib.go2_env_set_step_mode(self.h, mode.encode()), self.lib)
 
     def __del__(self):
         if getattr(self, "h", None):

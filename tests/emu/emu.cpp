@@ -1,19 +1,30 @@
 // Host emulation of the CUDA step kernel: compiles go2_rl_gym_b200/csrc/env_step_core.cuh with g++ and runs the 32 lanes
 // of each phase in a loop.  TEST TOOLING (CPU test-suite compares it against the oracle); never a product path.
+#include <algorithm>
 #include <vector>
 #include "../../go2_rl_gym_b200/csrc/env_step_core.cuh"
 
 using namespace go2;
 
+// One group = the threads that share phase barriers: a single warp (warp-per-env map) or a CTA of 8 warps / 8 envs (packed map).
+static int g_packed = 0;
+template <class F> static void for_groups(const Go2EnvConfig* C, F&& f) {
+  const int per = g_packed ? 8 : 1, nwarps = g_packed ? 8 : 1, NT = 32 * nwarps;
+  std::vector<WarpSmem> SM(per);
+  std::vector<Lane> lanes(NT);
+  for (int e0 = 0; e0 < C->num_envs; e0 += per) {
+    const int n_local = std::min(per, C->num_envs - e0);
+    for (int t = 0; t < NT; ++t) init_roles(lanes[t], t, g_packed, e0, n_local, nwarps);
+    f(lanes.data(), NT, SM.data());
+  }
+}
+
 extern "C" {
+void go2_emu_set_packed(int packed) { g_packed = packed; }
 int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const float* actions, const Go2StepParams* sp) {
   for (int k = 0; k < GO2_EP_STATS + 2; ++k) B->ep_accum[k] = 0;
   StepCtx X{C, M, B, sp, actions};
-  for (int e = 0; e < C->num_envs; ++e) {
-    WarpSmem S;
-    Lane lanes[32];
-    step_env(lanes, S, X, e);
-  }
+  for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { step_env(lanes, NT, SM, X); });
   // finalize extras["episode"] (mirrors the tiny finalize kernel)
   float n_reset = B->ep_accum[GO2_NUM_REW + 10];
   if (n_reset > 0 && B->ep_stats) {
@@ -30,12 +41,12 @@ int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* 
 }
 int go2_emu_reset_all(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const Go2StepParams* sp) {
   StepCtx X{C, M, B, sp, nullptr};
-  for (int e = 0; e < C->num_envs; ++e) { WarpSmem S; Lane lanes[32]; reset_env_initial(lanes, S, X, e); }
+  for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { reset_env_initial(lanes, NT, SM, X); });
   return 0;
 }
 int go2_emu_substeps(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const float* tau, int n) {
   StepCtx X{C, M, B, nullptr, nullptr};
-  for (int e = 0; e < C->num_envs; ++e) { WarpSmem S; Lane lanes[32]; substeps_env(lanes, S, X, e, tau, n); }
+  for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { substeps_env(lanes, NT, SM, X, tau, n); });
   return 0;
 }
 int go2_emu_sizeof_warp_smem(void) { return (int)sizeof(WarpSmem); }

@@ -19,23 +19,28 @@ def load():
 
 
 class EmuEnv:
-    def __init__(self, arrays):
+    def __init__(self, arrays, packed=False):
+        """packed: emulate the 8-envs-per-CTA thread map (LEGS / COLS items of 8 envs share warps) instead of warp-per-env."""
         assert arrays.device.type == "cpu"
         self.A = arrays
         self.lib = load()
+        self.packed = int(packed)
         self.common_step_counter = 0
 
     def reset_all(self):
         sp = self.A.step_params(self.common_step_counter)
+        self.lib.go2_emu_set_packed(self.packed)
         self.lib.go2_emu_reset_all(C.byref(self.A.config), C.byref(self.A.model), C.byref(self.A.buffers), C.byref(sp))
 
     def step(self, actions, reward_curriculum=None):
         self.common_step_counter += 1
         sp = self.A.step_params(self.common_step_counter, ep_slot=self.common_step_counter % 64, reward_curriculum=reward_curriculum)
         a = actions.contiguous().float()
+        self.lib.go2_emu_set_packed(self.packed)
         self.lib.go2_emu_step(C.byref(self.A.config), C.byref(self.A.model), C.byref(self.A.buffers), a.data_ptr(), C.byref(sp))
         return sp
 
     def substeps(self, tau, n):
         t = tau.contiguous().float()
+        self.lib.go2_emu_set_packed(self.packed)
         self.lib.go2_emu_substeps(C.byref(self.A.config), C.byref(self.A.model), C.byref(self.A.buffers), t.data_ptr(), n)

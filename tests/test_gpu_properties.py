@@ -14,10 +14,10 @@ KEYS = ("root_states", "dof_pos", "dof_vel", "obs_buf", "privileged_obs_buf", "r
         "time_out_buf", "episode_length_buf", "contact_forces", "measured_heights", "episode_sums", "torques")
 
 
-def _env(N, seed=3, offset=0, n_global=None, start_iter=800):
+def _env(N, seed=3, offset=0, n_global=None, start_iter=800, mode=None):
     cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = seed
     A = EnvArrays(cfg, "cuda:0", num_envs=N, env_offset=offset, num_envs_global=n_global or N, seed=seed)
-    e = CudaEnv(A)
+    e = CudaEnv(A, mode=mode)
     e.common_step_counter = 24 * start_iter
     e.reset_all()
     return cfg, A, e
@@ -92,3 +92,24 @@ def test_shards_equal_slices_of_the_whole():
         for k in KEYS:
             assert torch.equal(As.tensors[k], A.tensors[k][r * n:(r + 1) * n]), (r, k)
         del es
+
+
+@pytest.mark.parametrize("mode", ["8p", "4", "P3"])
+def test_thread_maps_give_identical_bits(mode):
+    """The packed map (default, "P2") and the warp-per-env maps run the same arithmetic in the same order: bit-identical buffers, including
+    a partially filled last CTA (N % 8 != 0) and steps with time-outs / terminations."""
+    N = 4099
+    outs = []
+    for m in ("P2", mode):
+        cfg, A, e = _env(N, seed=7, mode=m)
+        A.tensors["episode_length_buf"].copy_(torch.randint(1230, 1250, (N,), generator=torch.Generator().manual_seed(2)).int().cuda())
+        g = torch.Generator(device="cuda").manual_seed(5)
+        n_reset = 0
+        for _ in range(30):
+            e.step(1.5 * torch.randn(N, 12, device="cuda", generator=g))
+            n_reset += int(A.tensors["reset_buf"].sum())
+        assert n_reset > N // 2
+        outs.append({k: A.tensors[k].clone() for k in KEYS})
+        del e
+    for k in KEYS:
+        assert torch.equal(outs[0][k], outs[1][k]), k

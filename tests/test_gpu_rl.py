@@ -222,3 +222,40 @@ def test_runner_learns_two_iterations(tmp_path):
     assert any(f.startswith("model_") for f in os.listdir(runner.log_dir))
     sd = torch.load(os.path.join(runner.log_dir, "model_2.pt"), weights_only=False)
     assert set(sd) == {"model_state_dict", "optimizer_state_dict", "iter", "infos"} and "actor.0.weight" in sd["model_state_dict"]
+
+
+@pytest.mark.parametrize("task", ["go2", "go2_moe_cts"])
+@pytest.mark.parametrize("log", [False, True])
+def test_graph_rollout_equals_eager_rollout(task, log):
+    """The rollout replayed as ONE CUDA graph over device-resident step parameters (runner.collect) must leave exactly the bits the
+    per-step launches leave: env state, counters and every row of the rollout storage, over 3 rollouts (eager, capture + replay, replay)."""
+    from go2_rl_gym_b200.envs import task_registry
+    from go2_rl_gym_b200.utils import get_args
+    outs = []
+    for graphs in (True, False):
+        args = get_args(["--task", task, "--num_envs", "512", "--headless"])
+        env, _ = task_registry.make_env(task, args)
+        runner, _ = task_registry.make_alg_runner(env, task, args, log_root=None)
+        runner._rollout_graphs.enabled = graphs
+        if task != "go2":
+            runner._roll_history(env.get_observations(), None)
+        env.episode_length_buf = torch.randint(1100, 1250, (512,), generator=torch.Generator().manual_seed(1)).cuda()     # time-outs inside the rollouts
+        infos = []
+        for _ in range(3):
+            infos = runner.collect(log)
+        torch.cuda.synchronize()
+        if graphs:
+            assert ("rollout", log) in runner._rollout_graphs._g and not runner._rollout_graphs._failed      # the graph path really ran
+        assert len(infos) == (24 if log else 0)
+        st = runner.alg.storage
+        out = {k: getattr(st, k).clone() for k in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "mu", "actions_log_prob")}
+        out.update(root=env.root_states.clone(), q=env.dof_pos.clone(), ep_len=env.episode_length_buf.clone(), levels=env.terrain_levels.clone(),
+                   cmd=env.commands.clone(), counter=env.common_step_counter, act_step=runner.alg._act_step, st_step=st.step)
+        if log:
+            out.update(done_rew=torch.nan_to_num(runner._done_rew.clone(), nan=-1e9), rew_sum=runner._cur_reward_sum.clone())
+        outs.append(out)
+        assert int(st.dones.sum()) > 100
+        del runner, env
+    for k in outs[0]:
+        a, b = outs[0][k], outs[1][k]
+        assert (torch.equal(a, b) if torch.is_tensor(a) else a == b), k

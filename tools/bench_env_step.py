@@ -15,11 +15,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--num_envs", type=int, nargs="+", default=[4096, 8192])
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--mesh", default="heightfield")
+ap.add_argument("--modes", nargs="+", default=["P2"], help="thread maps to time: P2 (default kernel), P3, 8p, 4")
 args = ap.parse_args()
-for N in args.num_envs:
+for N, mode in [(n, m) for n in args.num_envs for m in args.modes]:
     cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = args.mesh
     t0 = time.time()
     env = Go2Robot(cfg, None, None, "cuda:0", True)
+    env.set_step_mode(mode)
     env.reset()
     torch.cuda.synchronize()
     t_init = time.time() - t0
@@ -33,5 +35,5 @@ for N in args.num_envs:
         env.step(acts[i % 8])
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    print(f"N={N} mesh={args.mesh}: {ms*1e3:.1f} us/step  {N/ms*1e3/1e6:.2f} M env-steps/s  (init {t_init:.1f}s, resets/step ~{float(env.reset_buf.float().mean())*N:.1f})", flush=True)
+    print(f"N={N} mesh={args.mesh} mode={mode}: {ms*1e3:.1f} us/step  {N/ms*1e3/1e6:.2f} M env-steps/s  (init {t_init:.1f}s, resets/step ~{float(env.reset_buf.float().mean())*N:.1f})", flush=True)
     del env
