@@ -214,6 +214,20 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms) / args.steps
     value = world * N * STEPS_PER_ENV / (ms * 1e-3)
+    # split of the iteration like the reference's log line (collection / learning, on_policy_runner.py:138-165), device-timed
+    sp_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    col_ms = lrn_ms = 0.0
+    for _ in range(3):
+        sp_ev[0].record()
+        runner.collect(False)
+        sp_ev[1].record()
+        with torch.inference_mode():
+            alg.compute_returns(env.get_privileged_observations())
+        alg.update()
+        sp_ev[2].record()
+        torch.cuda.synchronize()
+        col_ms += sp_ev[0].elapsed_time(sp_ev[1]) / 3
+        lrn_ms += sp_ev[1].elapsed_time(sp_ev[2]) / 3
     # the fused step kernel's own duration: the same iterations launched step by step with CUDA events around every env.step()
     obs, cobs = env.get_observations(), env.get_privileged_observations()
     for _ in range(2):
@@ -303,7 +317,8 @@ def main():
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                              "kernel_us": kern_ms * 1e3, "env_steps_per_s_kernel_only": N / (kern_ms * 1e-3),
                              "note": "latency/issue-bound serial 13-body recursion; HBM fraction is structurally tiny (SURVEY 7.2)"},
-                "roofline_gemm": gemm, "clocks": clocks, "cpu_baseline": cpu}
+                "roofline_gemm": gemm, "clocks": clocks, "cpu_baseline": cpu,
+                "split_ms": {"collection": col_ms, "learning": lrn_ms}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

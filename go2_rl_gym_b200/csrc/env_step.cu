@@ -59,7 +59,14 @@ step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restr
   StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
   init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8);
+#if defined(GO2_PHASE_TIMING)
+  if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { go2_ph_count = 1; go2_ph_clock[0] = clock64(); }
+#endif
   step_env(L, smem, X);
+#if defined(GO2_PHASE_TIMING)
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { const int k = go2_ph_count; if (k < 512) go2_ph_clock[k] = clock64(); go2_ph_count = k + 1; }
+#endif
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
@@ -148,6 +155,17 @@ static int launch_packed(Go2Env* h, const float* actions, const Go2StepParams* s
   return 0;
 }
 }  // namespace go2
+
+#if defined(GO2_PHASE_TIMING)
+extern "C" int go2_debug_phase_clocks(long long* out, int cap) {   // tuning build only: clock64() after each phase barrier of the last step
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, go2::go2_ph_count, sizeof(int));
+  n = n < cap ? n : cap;
+  cudaMemcpyFromSymbol(out, go2::go2_ph_clock, sizeof(long long) * (n < 512 ? n : 512));
+  return n;
+}
+#endif
 
 extern "C" {
 

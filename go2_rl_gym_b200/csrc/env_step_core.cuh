@@ -7,18 +7,18 @@
 // a height sample, an observation column ...) and threads only communicate through the per-env shared-memory block
 // `WarpSmem` ACROSS phase boundaries (GO2_SYNC()).  No shuffles or ballots are used, so all cross-lane sums run in a fixed
 // order (bit-reproducible run to run) and the very same source can be executed thread-by-thread on the host:
-//   * nvcc, sm_100a : GO2_WIDE / GO2_LEGS / GO2_COLS guard a block by the thread's role; GO2_SYNC() = __syncwarp() or a CTA barrier.
+//   * nvcc, sm_100a : GO2_WIDE / GO2_LEGS guard a block by the thread's role; GO2_SYNC() = __syncwarp() or a CTA barrier.
 //   * g++ (tests/emu): they expand to a loop over the threads of the group, giving a faithful functional emulation of the
 //     kernel that the CPU test-suite compares against the oracle without a GPU.  The emulation is test tooling, not a product path.
 //
 // Roles (filled by init_roles()):
 //   WIDE  one warp per env, item = lane: joints j = lane (0..11) · colliders c = lane (0..31) · reported bodies · height samples
 //         i = lane + 32 k · observation columns i = lane + 32 k · the scalar per-env bookkeeping on lane 0.
-//   LEGS  one thread per (env, leg): the serial 6x6 articulated-body recursions along hip -> thigh -> calf.
-//   COLS  one thread per (env, column of the base's 6x6 articulated inertia).
-// Two thread maps exist.  "warp per env": LEGS = lanes 0..3 and COLS = lanes 0..5 of the env's own warp (28 / 26 lanes idle in the
-// heaviest phases).  "packed": a CTA of 8 warps owns 8 envs; the 32 (env, leg) items fill warp 0 and the 48 (env, column) items sit
-// in warps 1-2, so the long serial leg code is issued once per 8 envs instead of once per env; all phases end in a CTA barrier.
+//   LEGS  one thread per (env, leg): the serial 6x6 articulated-body recursions along hip -> thigh -> calf, and (redundantly on the 4
+//         leg threads of an env) the base's 6x6 inverse and impulse response, so that consecutive LEGS phases only need a warp sync.
+// Two thread maps exist.  "warp per env": LEGS = lanes 0..3 of the env's own warp (28 lanes idle in the heaviest phases).
+// "packed": a CTA of 8 warps owns 8 envs and the 32 (env, leg) items fill warp 0, so the long serial leg code is issued once per
+// 8 envs instead of once per env; WIDE <-> LEGS transitions are CTA barriers, LEGS -> LEGS transitions stay inside warp 0.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -33,12 +33,14 @@
 #if defined(__CUDACC__)
 #define GO2_EACH
 #define GO2_SYNC() go2_phase_sync(L)
+#define GO2_SYNC_WARP() __syncwarp()   /* between two phases of the SAME role: the threads of a role that touch one env always share a warp */
 #define GO2_FMUL(a, b) __fmul_rn((a), (b))
 #define GO2_FADD(a, b) __fadd_rn((a), (b))
 #define GO2_LDG(p) __ldg(p)
 #else
 #define GO2_EACH for (int tid_ = 0; tid_ < NT; ++tid_) if (Lane& L = lanes[tid_]; true)
 #define GO2_SYNC() do { } while (0)
+#define GO2_SYNC_WARP() do { } while (0)
 #define GO2_FMUL(a, b) ((a) * (b))
 #define GO2_FADD(a, b) ((a) + (b))
 #define GO2_LDG(p) (*(p))
@@ -47,7 +49,6 @@
 #define GO2_BIND(slot, idx) if (WarpSmem& S = SM[slot]; true) if (const int e = L.e0 + (slot), lane = (idx); (void)e, (void)lane, true)
 #define GO2_WIDE GO2_EACH if (L.own) GO2_BIND(L.w, L.lane)
 #define GO2_LEGS GO2_EACH if (L.leg >= 0) GO2_BIND(L.wl, L.leg)
-#define GO2_COLS GO2_EACH if (L.col >= 0) GO2_BIND(L.wc, L.col)
 
 namespace go2 {
 
@@ -208,6 +209,33 @@ GO2_HD Sym6 rigid_inertia(const float* rec) {  // mass, com, Ixx Iyy Izz Ixy Ixz
   return I;
 }
 
+// inverse of a symmetric positive definite 3x3 (adjugate / determinant; symmetric by construction)
+GO2_HD M3 sym_inverse(const M3& M) {
+  const float a = M.m[0], b = M.m[1], c = M.m[2], d = M.m[4], e = M.m[5], f = M.m[8];
+  const float c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const float id = 1.0f / (a * c00 + b * c01 + c * c02);
+  M3 R;
+  R.m[0] = c00 * id; R.m[1] = c01 * id; R.m[2] = c02 * id;
+  R.m[3] = R.m[1]; R.m[4] = (a * f - c * c) * id; R.m[5] = (b * c - a * e) * id;
+  R.m[6] = R.m[2]; R.m[7] = R.m[5]; R.m[8] = (a * d - b * b) * id;
+  return R;
+}
+// (I^A_0)^-1 of the floating base by 3x3 blocks: I = [A B; B^T C]  ->  [P Q; Q^T R] with the Schur complement of the linear block,
+//   P = (A - B C^-1 B^T)^-1,  Q = -P B C^-1,  R = C^-1 - (B C^-1)^T Q.
+// Two closed-form 3x3 inverses and four 3x3 products: a short dependency chain with wide instruction-level parallelism (the 6x6
+// Cholesky + 12 triangular solves it replaces was a ~4.7 k-cycle serial chain of divisions and square roots per substep).
+GO2_HD void base_inverse(const Sym6& I, M3& P, M3& Q, M3& R) {
+  const M3 Ci = sym_inverse(I.C);
+  const M3 T = mul(I.B, Ci);
+  M3 S = sub(I.A, mul(T, transpose(I.B)));
+  S.m[3] = S.m[1]; S.m[6] = S.m[2]; S.m[7] = S.m[5];      // exact symmetry (upper triangle wins)
+  P = sym_inverse(S);
+  const M3 PT = mul(P, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Q.m[i] = -PT.m[i];
+  R = sub(Ci, mul(transpose(T), Q));
+}
+
 // ------------------------------------------------------------------------------------------------ per-warp scratch
 struct WarpSmem {
   float inertia[GO2_NUM_DYN * GO2_INERTIA_STRIDE];
@@ -221,6 +249,8 @@ struct WarpSmem {
   float legIA[4][27], legpA[4][6], legp[4][6];
   float fcol[GO2_NUM_COL][6];  // spatial impulse of each collider on its body (body coords)
   float pcol[GO2_NUM_COL][3];  // world impulse of each collider
+  float tgt[12][2];            // joint-limit target velocities (lower, upper row)
+  float mu_env, rest_env;      // contact friction / restitution of this env (combined with the terrain's)
   float a0[6];
   float q[12], qd[12], tau[12], cs[12][2], qdm[12], dqd[12], tauimp[12], Dj[12];
   float act[12], lact[12], llact[12], lqd[12], tq[12];
@@ -239,25 +269,23 @@ struct WarpSmem {
   float env_origin[3];
   int active[GO2_NUM_COL];
   int ep_len, reset, tout, last_lim, level, ttype, tid, delay_start;
-  int pad_;   // 2017 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
+  int pad_[7];   // stride = 1 mod 32 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
 };
 static_assert((sizeof(WarpSmem) / 4) % 32 == 1, "WarpSmem stride must be 1 mod 32 words");
 
 struct Lane {
   // joint lanes (0..11)
-  float kp, kd, mzo, mstr, lam_lo, lam_hi, tgt_lo, tgt_hi;
+  float kp, kd, mzo, mstr;
   // leg lanes (0..3): per link i of the leg
   float c[3], s[3], Dinv[3], u[3], uI[3];
   float U[3][6], cb[3][6];
-  // base column lanes (0..5)
-  float Lcol[6];  // column k of Lam0 (also row k)
-  // collider lanes
-  float n[3], Winv[6], vt, mu, r[3], p[3], gcount;
+  float lam_lo[3], lam_hi[3];   // accumulated joint-limit impulses of the leg's joints
+  // collider lanes (0..31)
+  float n[3], Winv[6], vt, r[3], p[3], gsplit;
   int body, act;
   // thread map (init_roles): own env slot / lane, leg item, base-column item, first env id of the group, slots of the group
   int own, w, lane;
   int leg, wl;
-  int col, wc;
   int e0, w0, nw;
   // phase barrier: 0 = warp-level (__syncwarp); otherwise the number of threads of the CTA-wide named barrier every phase ends in
   // (required by the packed map; with the warp-per-env map it only keeps the warps of a CTA on the same stretch of code)
@@ -267,9 +295,16 @@ struct Lane {
 };
 
 #if defined(__CUDACC__)
+#if defined(GO2_PHASE_TIMING)   // tuning build (tools/phase_timing.py): CTA GO2_PHASE_TIMING records clock64() after every phase barrier
+__device__ long long go2_ph_clock[512];
+__device__ int go2_ph_count;
+#endif
 __device__ __forceinline__ void go2_phase_sync(const Lane& L) {
   if (L.nsync) asm volatile("bar.sync 1, %0;" ::"r"(L.nsync) : "memory");
   else __syncwarp();
+#if defined(GO2_PHASE_TIMING)
+  if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { const int k = go2_ph_count; if (k < 512) go2_ph_clock[k] = clock64(); go2_ph_count = k + 1; }
+#endif
 }
 #define GO2_COARSE_SYNC() do { if (L.ncoarse) asm volatile("bar.sync 2, %0;" ::"r"(L.ncoarse) : "memory"); } while (0)
 #define GO2_MID_SYNC() do { if (L.nmid) asm volatile("bar.sync 3, %0;" ::"r"(L.nmid) : "memory"); } while (0)
@@ -279,9 +314,9 @@ __device__ __forceinline__ void go2_phase_sync(const Lane& L) {
 #endif
 
 // Thread map of thread `tid` of a group of `nwarps` warps whose first env is e0 and which holds n_local (>= 1) envs.
-//   packed == 0: warp w owns env e0 + w; its lanes 0..3 / 0..5 are that env's LEGS / COLS items.
+//   packed == 0: warp w owns env e0 + w; its lanes 0..3 are that env's LEGS items.
 //   packed == 1: 8 warps, up to 8 envs; warp w still owns env e0 + w for the WIDE role, but the LEGS items of all envs sit in
-//                warp 0 (lane = 4 * slot + leg) and the COLS items in warps 1-2 (8 lanes per env, 6 used).
+//                warp 0 (lane = 4 * slot + leg).
 GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nwarps) {
   const int warp = tid >> 5, lane = tid & 31;
   L.e0 = e0; L.w = warp; L.lane = lane;
@@ -289,13 +324,10 @@ GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nw
   L.ncoarse = 0; L.nmid = 0;
   if (!packed) {
     L.leg = (L.own && lane < 4) ? lane : -1; L.wl = warp;
-    L.col = (L.own && lane < 6) ? lane : -1; L.wc = warp;
     L.w0 = warp; L.nw = 1;
     L.nsync = 0;
   } else {
     L.leg = (warp == 0 && (lane >> 2) < n_local) ? (lane & 3) : -1; L.wl = lane >> 2;
-    const int cs = (warp - 1) * 4 + (lane >> 3);
-    L.col = ((warp == 1 || warp == 2) && (lane & 7) < 6 && cs < n_local) ? (lane & 7) : -1; L.wc = L.col >= 0 ? cs : 0;
     L.w0 = 0; L.nw = n_local;
     L.nsync = 32 * nwarps;
   }
@@ -509,11 +541,11 @@ GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, 
 #if defined(__CUDACC__)
 #define GO2_LANE_ARGS Lane& L
 #define GO2_LANE_PASS L
-#define GO2_L0 L
+#define GO2_ANY_RESET(SM) (SM[L.w].reset != 0)          /* the env's own warp decides alone: reset_phases holds WIDE phases only */
 #else
 #define GO2_LANE_ARGS Lane* lanes, int NT
 #define GO2_LANE_PASS lanes, NT
-#define GO2_L0 lanes[0]
+#define GO2_ANY_RESET(SM) group_any_reset(lanes[0], SM)   /* the emulated group walks reset_phases when any of its envs resets */
 #endif
 
 GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool last) {
@@ -532,9 +564,8 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
 #endif
       S.cs[lane][0] = cn; S.cs[lane][1] = sn;
       float glo = q - M->q_lower[lane], ghi = M->q_upper[lane] - q;
-      L.tgt_lo = (glo >= 0) ? -glo / dt : -glo * C->limit_erp / dt;
-      L.tgt_hi = (ghi >= 0) ? ghi / dt : ghi * C->limit_erp / dt;
-      L.lam_lo = 0; L.lam_hi = 0;
+      S.tgt[lane][0] = (glo >= 0) ? -glo / dt : -glo * C->limit_erp / dt;
+      S.tgt[lane][1] = (ghi >= 0) ? ghi / dt : ghi * C->limit_erp / dt;
       S.dqd[lane] = 0; S.tauimp[lane] = 0;
     }
     if (lane == 12) {
@@ -569,10 +600,13 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       stm(S.legIA[lane], Iout.A); stm(S.legIA[lane] + 9, Iout.B); stm(S.legIA[lane] + 18, Iout.C);
       st6(S.legpA[lane], pout);
     }
-  } GO2_SYNC();
-  // ---- S3: base column lanes: assemble I^A_0, Cholesky, column k of the inverse, a0[k]
-  GO2_COLS {
-    if (lane < 6) {
+  }
+  // ---- S3 + S5: leg lanes.  Every leg lane of an env assembles I^A_0 and inverts it (same instruction stream on the 4 lanes, no
+  // cross-lane traffic), then runs pass 3 / unconstrained velocities / the mobility recursion for its own leg.  The only dependency on
+  // the other legs is their legIA / legpA: a warp-level sync (the 4 leg lanes of an env always share a warp).
+  GO2_SYNC_WARP();
+  GO2_LEGS {
+    if (lane < 4) {
       Sym6 I0 = rigid_inertia(S.inertia);
       V6 v0; ld6(S.vs[0], v0);
       V6 h = mul(I0, v0);
@@ -582,44 +616,31 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
         V6 pl; ld6(S.legpA[l], pl);
         p0.a = p0.a + pl.a; p0.l = p0.l + pl.l;
       }
-      float A6[6][6];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { A6[i][j] = I0.A.m[3 * i + j]; A6[i][j + 3] = I0.B.m[3 * i + j]; A6[i + 3][j] = I0.B.m[3 * j + i]; A6[i + 3][j + 3] = I0.C.m[3 * i + j]; }
-      float Lc[6][6];
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j <= i; ++j) {
-          float sm = A6[i][j];
-          for (int k = 0; k < j; ++k) sm -= Lc[i][k] * Lc[j][k];
-          Lc[i][j] = (i == j) ? sqrtf(sm) : sm / Lc[j][j];
-        }
-      float y[6], x[6];
-      for (int i = 0; i < 6; ++i) { float sm = (i == lane) ? 1.0f : 0.0f; for (int k = 0; k < i; ++k) sm -= Lc[i][k] * y[k]; y[i] = sm / Lc[i][i]; }
-      for (int i = 5; i >= 0; --i) { float sm = y[i]; for (int k = i + 1; k < 6; ++k) sm -= Lc[k][i] * x[k]; x[i] = sm / Lc[i][i]; }
-      float pv[6] = {p0.a.x, p0.a.y, p0.a.z, p0.l.x, p0.l.y, p0.l.z};
-      float acc = 0;
-      for (int i = 0; i < 6; ++i) { L.Lcol[i] = x[i]; S.Lam0[6 * lane + i] = x[i]; acc += x[i] * pv[i]; }
-      S.a0[lane] = -acc;
-    }
-  } GO2_SYNC();
-  // ---- S5: leg lanes: pass 3, unconstrained velocities, mobility recursion
-  GO2_MID_SYNC();
-  GO2_LEGS {
-    if (lane < 4) {
-      V6 a0; ld6(S.a0, a0);
-      V6 v0; ld6(S.vs[0], v0);
+      M3 P, Q, R;
+      base_inverse(I0, P, Q, R);
+      V6 a0;   // a0 = -Lam0 p0
+      {
+        V3 ta = mul(P, p0.a) + mul(Q, p0.l), tl = mulT(Q, p0.a) + mul(R, p0.l);
+        a0.a = mk(-ta.x, -ta.y, -ta.z); a0.l = mk(-tl.x, -tl.y, -tl.z);
+      }
+      if (lane == 0) {   // the base's mobility for the contact phases (colliders on body 0, impulse response of the base)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) {
+            S.Lam0[6 * i + j] = P.m[3 * i + j]; S.Lam0[6 * i + j + 3] = Q.m[3 * i + j];
+            S.Lam0[6 * (i + 3) + j] = Q.m[3 * j + i]; S.Lam0[6 * (i + 3) + j + 3] = R.m[3 * i + j];
+          }
+      }
       M3 R0 = ldm(S.Rw[0]);
       V3 gb = mulT(R0, mk(0.0f, 0.0f, C->gravity_z));
       V6 vm0;
       vm0.a = v0.a + dt * a0.a;
       vm0.l = v0.l + dt * (a0.l + gb + cross(v0.a, v0.l));  // components stay in the frame of the start of the step
-      M3 P, Q, R;
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { P.m[3 * i + j] = S.Lam0[6 * i + j]; Q.m[3 * i + j] = S.Lam0[6 * i + j + 3]; R.m[3 * i + j] = S.Lam0[6 * (i + 3) + j + 3]; }
       V6 ap = a0, vmp = vm0;
       leg_pass3<0>(lane, L, S, M, dt, ap, vmp, P, Q, R);
       leg_pass3<1>(lane, L, S, M, dt, ap, vmp, P, Q, R);
       leg_pass3<2>(lane, L, S, M, dt, ap, vmp, P, Q, R);
       if (lane == 0) st6(S.v[0], vm0);
+      for (int i = 0; i < 3; ++i) { L.lam_lo[i] = 0; L.lam_hi[i] = 0; }
     }
   } GO2_SYNC();
   // ---- S6: collider lanes: narrow phase + per-contact 3x3 mobility
@@ -658,26 +679,25 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
         float id = 1.0f / (a * c00 + bq * c01 + c2 * c02);
         L.Winv[0] = c00 * id; L.Winv[1] = c01 * id; L.Winv[2] = c02 * id;
         L.Winv[3] = (a * f - c2 * c2) * id; L.Winv[4] = (bq * c2 - a * e2) * id; L.Winv[5] = (a * d - bq * bq) * id;
-        L.mu = 0.5f * (C->terrain_friction + GO2_LDG(X.buf->friction_coeffs + e));
         // normal velocity target; restitution looks at the approach speed at the START of the step
         V6 vsb; ld6(S.vs[b], vsb);
         float vn0 = dot(mul(Rw, vsb.l + cross(vsb.a, r)), n);
         float vt = (gap >= 0) ? -gap / dt : fminf(fmaxf(-gap - C->penetration_slop, 0.0f) * C->erp / dt, C->max_depen_vel);
-        float rest = 0.5f * (C->terrain_restitution + GO2_LDG(X.buf->restitutions + e));
-        if (vn0 < -C->bounce_threshold) vt = fmaxf(vt, -rest * vn0);
+        if (vn0 < -C->bounce_threshold) vt = fmaxf(vt, -S.rest_env * vn0);
         L.vt = vt;
       }
     }
-  } GO2_SYNC();
-  // ---- S7: mass-splitting count of the collider's group (base = colliders 0..7, leg l = 8+6l .. 13+6l)
+  } GO2_SYNC_WARP();
+  // ---- S7: mass-splitting factor of the collider's group (base = colliders 0..7, leg l = 8+6l .. 13+6l)
   GO2_WIDE {
     {
       int g0 = lane < 8 ? 0 : 8 + 6 * ((lane - 8) / 6), gn = lane < 8 ? 8 : 6, cnt = 0;
       for (int k = 0; k < gn; ++k) cnt += S.active[g0 + k];
-      L.gcount = (float)cnt;
+      L.gsplit = 1.0f / (float)cnt;      // only read by active colliders: cnt >= 1
     }
-  } GO2_SYNC();
-  // ---- Jacobi sweeps with exact propagation through the tree
+  }
+  // ---- Jacobi sweeps with exact propagation through the tree: [collider lanes: block-solve every contact] | CTA barrier |
+  // [leg threads: limit rows, impulses inward, base response, outward] | CTA barrier
   GO2_MID_SYNC();
   for (int it = 0; it < C->solver_iters; ++it) {
     GO2_WIDE {
@@ -689,14 +709,14 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
         vb.a = vb.a + db.a; vb.l = vb.l + db.l;
         V3 vp = mul(Rw, vb.l + cross(vb.a, r));
         V3 err = vp - L.vt * n;
-        float is = 1.0f / L.gcount;
+        float is = L.gsplit;
         V3 we = mk(L.Winv[0] * err.x + L.Winv[1] * err.y + L.Winv[2] * err.z, L.Winv[1] * err.x + L.Winv[3] * err.y + L.Winv[4] * err.z,
                    L.Winv[2] * err.x + L.Winv[4] * err.y + L.Winv[5] * err.z);
         V3 pc = mk(L.p[0], L.p[1], L.p[2]) - is * we;
         float pcn = dot(pc, n);
         float pn = fmaxf(0.0f, pcn);
         V3 pt = pc - pcn * n;
-        float ptn = sqrtf(dot(pt, pt)), lim = L.mu * pn;
+        float ptn = sqrtf(dot(pt, pt)), lim = S.mu_env * pn;
         if (ptn > lim) pt = (ptn > 0 ? lim / ptn : 0.0f) * pt;
         V3 p = pn * n + pt;
         L.p[0] = p.x; L.p[1] = p.y; L.p[2] = p.z;
@@ -704,16 +724,17 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
         st3(S.fcol[lane], fn); st3(S.fcol[lane] + 3, fl);
         st3(S.pcol[lane], p);
       }
-      if (lane < GO2_NUM_DOF) {  // joint-limit rows (unilateral, velocity level)
-        float cur = S.qdm[lane] + S.dqd[lane], Dj = S.Dj[lane];
-        L.lam_lo = fmaxf(0.0f, L.lam_lo + (L.tgt_lo - cur) * Dj);
-        L.lam_hi = fminf(0.0f, L.lam_hi + (L.tgt_hi - cur) * Dj);
-        S.tauimp[lane] = L.lam_lo + L.lam_hi;
-      }
     } GO2_SYNC();
-    // inward: leg lanes gather their colliders' impulses (fixed order) and push them to the base
     GO2_LEGS {
       if (lane < 4) {
+        for (int i = 0; i < 3; ++i) {  // joint-limit rows of the leg's joints (unilateral, velocity level)
+          const int j = 3 * lane + i;
+          float cur = S.qdm[j] + S.dqd[j], Dj = S.Dj[j];
+          L.lam_lo[i] = fmaxf(0.0f, L.lam_lo[i] + (S.tgt[j][0] - cur) * Dj);
+          L.lam_hi[i] = fminf(0.0f, L.lam_hi[i] + (S.tgt[j][1] - cur) * Dj);
+          S.tauimp[j] = L.lam_lo[i] + L.lam_hi[i];
+        }
+        // inward: gather the leg's collider impulses (fixed order) and push them to the base
         const int c0 = 8 + 6 * lane;
         V6 p2, p1, p0, out;
         p2.a = mk(0, 0, 0); p2.l = mk(0, 0, 0);
@@ -725,22 +746,21 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
         leg_imp_in<0>(lane, L, S, M, p0, out);
         st6(S.legp[lane], out);
       }
-    } GO2_SYNC();
-    // base: dv0 = -Lam0 p0, one row per lane
-    GO2_COLS {
-      if (lane < 6) {
+    } GO2_SYNC_WARP();
+    // base: dv0 = -Lam0 p0, evaluated by every leg lane of the env (same stream, no extra phase), then outward along the leg
+    GO2_LEGS {
+      if (lane < 4) {
         float p0[6] = {0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 8; ++c) for (int k = 0; k < 6; ++k) p0[k] -= S.fcol[c][k];
         for (int l = 3; l >= 0; --l) for (int k = 0; k < 6; ++k) p0[k] += S.legp[l][k];
-        float acc = 0;
-        for (int k = 0; k < 6; ++k) acc += L.Lcol[k] * p0[k];
-        S.dv[0][lane] = -acc;
-      }
-    } GO2_SYNC();
-    // outward: leg lanes
-    GO2_LEGS {
-      if (lane < 4) {
-        V6 dvp; ld6(S.dv[0], dvp);
+        float d0[6];
+        for (int i = 0; i < 6; ++i) {
+          float acc = 0;
+          for (int k = 0; k < 6; ++k) acc += S.Lam0[6 * i + k] * p0[k];
+          d0[i] = -acc;
+        }
+        V6 dvp; dvp.a = mk(d0[0], d0[1], d0[2]); dvp.l = mk(d0[3], d0[4], d0[5]);
+        if (lane == 0) st6(S.dv[0], dvp);
         leg_imp_out<0>(lane, L, S, M, dvp);
         leg_imp_out<1>(lane, L, S, M, dvp);
         leg_imp_out<2>(lane, L, S, M, dvp);
@@ -789,13 +809,13 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       float idt = 1.0f / dt;
       S.cf[b][0] = f.x * idt; S.cf[b][1] = f.y * idt; S.cf[b][2] = f.z * idt;
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
 }
 
 // feet position / velocity at the current configuration (rigid_body_states refresh, legged_robot.py:109)
 GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   const Go2Model* M = X.mdl;
-  GO2_LEGS {
+  GO2_WIDE {   // lanes 0..3 of the env's own warp: once per step, between WIDE phases (no CTA barrier on either side)
     if (lane < 4) {
       M3 Rw = quat_to_mat(S.root[3], S.root[4], S.root[5], S.root[6]);
       V3 pw = ld3(S.root);
@@ -822,7 +842,7 @@ GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       st3(S.feet[lane], pw + mul(Rw, r));
       st3(S.feet[lane] + 3, mul(Rw, v.l + cross(v.a, r)));
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
 }
 
 // ================================================================================================ commands / reset (lane 0)
@@ -956,7 +976,7 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool ini
       S.acc_xy[0] = 0; S.acc_xy[1] = 0;
       resample_commands(S, X, e, ST_CMD_RESET);
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
 }
 
 // ================================================================================================ load / store
@@ -983,13 +1003,17 @@ GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     if (lane == 26) { S.acc_xy[0] = B->commands_xy_accumulation[(size_t)e * 2]; S.acc_xy[1] = B->commands_xy_accumulation[(size_t)e * 2 + 1]; }
     if (lane == 27) { S.max_move = B->max_move_distance[e]; S.last_lim = B->last_is_limit_vel[e]; }
     if (lane == 28) { S.level = B->terrain_levels[e]; S.ttype = B->terrain_types[e]; S.tid = B->terrain_ids[e]; }
+    if (lane == 30) {
+      S.mu_env = 0.5f * (C->terrain_friction + GO2_LDG(B->friction_coeffs + e));
+      S.rest_env = 0.5f * (C->terrain_restitution + GO2_LDG(B->restitutions + e));
+    }
     if (lane == 29) {
       S.delay_start = 0;
       if (C->randomize_action_delay && X.sp)
         S.delay_start = (int)(philox((uint32_t)(C->env_offset + e), X.sp->common_step_counter, ST_DELAY, 0, C->seed_lo, C->seed_hi).x % (uint32_t)(C->decimation + 1));
     }
     for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) S.cf[i / 3][i % 3] = B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i];
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
 }
 
 GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
@@ -1015,7 +1039,7 @@ GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       if (k < 3) B->feet_pos[(size_t)e * 12 + l * 3 + k] = S.feet[l][k];
       else B->feet_vel[(size_t)e * 12 + l * 3 + (k - 3)] = S.feet[l][k];
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
 }
 
 // torques for the current substep (legged_robot.py:74-81, :594-618, control_type 'P')
@@ -1032,7 +1056,7 @@ GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, int s
       S.tq[lane] = t;                               // what the reference reports (legged_robot.py:79-81)
       S.tau[lane] = fminf(fmaxf(t, -lim), lim);     // effort clamp of the actuator (physics spec)
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
 }
 
 // ================================================================================================ the full step
@@ -1081,7 +1105,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       S.max_move = fmaxf(S.max_move, sqrtf(dx * dx + dy * dy));
       if (S.resamp_step <= 0.0f && S.ep_len < C->max_episode_length - 1) resample_commands(S, X, e, ST_CMD_CB);
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   GO2_WIDE {
     {
       float sh = 0;
@@ -1106,7 +1130,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       const float* f = S.cf[3 + 4 * l + k];
       S.coll[lane - 16] = (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   GO2_WIDE {
     if (lane == 0) {
       float sh = 0;
@@ -1117,15 +1141,15 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       S.tout = S.ep_len > C->max_episode_length;
       S.reset = term || S.tout;
     }
-  } GO2_SYNC();
-  GO2_LEGS {
+  } GO2_SYNC_WARP();
+  GO2_WIDE {
     if (lane < 4) {  // feet_regulation per foot, legged_robot.py:1404-1414
       const float* fp = S.feet[lane];
       float f2b = (fp[0] - S.root[0]) * S.pg[0] + (fp[1] - S.root[1]) * S.pg[1] + (fp[2] - S.root[2]) * S.pg[2];
       float fh = fmaxf(S.base_height - f2b, 0.0f);
       S.fterm[lane] = (fp[3] * fp[3] + fp[4] * fp[4]) * expf(-fh / (0.025f * C->base_height_target));
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   GO2_WIDE {
     if (lane == 0) {
       float tv[GO2_NUM_REW];
@@ -1164,12 +1188,12 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       }
       S.rew = rew;
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   GO2_WIDE {
     if (lane < GO2_NUM_REW) B->episode_sums[(size_t)e * GO2_NUM_REW + lane] += S.termv[lane];
     if (lane == 31) B->rew_buf[e] = S.rew;
-  } GO2_SYNC();
-  if (group_any_reset(GO2_L0, SM)) reset_phases(GO2_LANE_PASS, SM, X, false);   // uniform over the group; items are predicated by their env
+  } GO2_SYNC_WARP();
+  if (GO2_ANY_RESET(SM)) reset_phases(GO2_LANE_PASS, SM, X, false);   // warp-uniform (WIDE phases only); items are predicated by their env
   GO2_WIDE {
     if (lane == 0) {
       if (C->push_robots && (S.ep_len % C->push_interval == 0)) {  // _push_robots, legged_robot.py:709-724
@@ -1185,7 +1209,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW, (float)S.level);
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW + 1 + S.tid, (float)S.level);
     }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   // ---- compute_observations (go2_env.py:23-53) + clip (legged_robot.py:96-99); rows are written coalesced
   GO2_WIDE {
     for (int i = lane; i < GO2_NUM_PRIV; i += 32) {
@@ -1215,10 +1239,10 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     }
     for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) B->measured_heights[(size_t)e * GO2_NUM_HEIGHT + i] = S.heights[i];
     if (lane < 3) { B->base_lin_vel[(size_t)e * 3 + lane] = S.blv[lane]; B->base_ang_vel[(size_t)e * 3 + lane] = S.bav[lane]; B->projected_gravity[(size_t)e * 3 + lane] = S.pg[lane]; }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) { S.lact[lane] = S.act[lane]; S.lqd[lane] = S.qd[lane]; }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   store_state(GO2_LANE_PASS, SM, X);
 }
 
@@ -1228,7 +1252,7 @@ GO2_HD void reset_env_initial(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   GO2_WIDE {
     if (lane == 0) { S.tout = 0; }
     if (lane < 4) for (int k = 0; k < 6; ++k) S.feet[lane][k] = 0;
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   reset_phases(GO2_LANE_PASS, SM, X, true);
   feet_kinematics(GO2_LANE_PASS, SM, X);
   store_state(GO2_LANE_PASS, SM, X);
@@ -1241,13 +1265,13 @@ GO2_HD void substeps_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, const fl
   for (int s = 0; s < n; ++s) {
     GO2_WIDE {
       if (lane < GO2_NUM_DOF) { float lim = M->effort[lane]; S.tau[lane] = fminf(fmaxf(tau_in[(size_t)e * GO2_NUM_DOF + lane], -lim), lim); }
-    } GO2_SYNC();
+    } GO2_SYNC_WARP();
     physics_substep(GO2_LANE_PASS, SM, X, s == n - 1);
   }
   feet_kinematics(GO2_LANE_PASS, SM, X);
   GO2_WIDE {
     if (lane == 0) { S.reset = X.buf->reset_buf[e]; S.tout = X.buf->time_out_buf[e]; }
-  } GO2_SYNC();
+  } GO2_SYNC_WARP();
   store_state(GO2_LANE_PASS, SM, X);
 }
 

@@ -421,8 +421,61 @@ __global__ void dgrad_rank1_kernel(const float* __restrict__ dY, long lddy, cons
     if (kk < K && m < M) dXt[(long)kk * lddxt + m] = t[threadIdx.x][threadIdx.y + i];
   }
 }
+// dW[k] = sum_m dy[m] X[m][k], db = sum_m dy[m]: weight gradient of a 1-wide Linear (the critic's head).  One streaming pass over X:
+// CTA c takes a contiguous block of rows, warp w its rows w, w+8, ..., lane l the columns l, l+32, ... (coalesced row reads);
+// partial[c][0..K-1] = column sums, partial[c][K] = sum of dy.  Fixed summation order everywhere (deterministic).
+constexpr int WG1_CTAS = 296, WG1_MAXK = 512;
+__global__ void __launch_bounds__(256) wgrad_rank1_partial_kernel(const float* __restrict__ dY, long lddy, const float* __restrict__ X, long ldx,
+                                                                 float* __restrict__ partial, int M, int K) {
+  __shared__ float red[8][WG1_MAXK + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = (M + gridDim.x - 1) / gridDim.x, m0 = blockIdx.x * rows, m1 = min(M, m0 + rows);
+  float acc[WG1_MAXK / 32], sdy = 0.0f;
+#pragma unroll
+  for (int j = 0; j < WG1_MAXK / 32; ++j) acc[j] = 0.0f;
+  for (int m = m0 + warp; m < m1; m += 8) {
+    const float dy = __ldg(dY + (long)m * lddy);
+    sdy += dy;
+    const float* x = X + (long)m * ldx;
+#pragma unroll
+    for (int j = 0; j < WG1_MAXK / 32; ++j) { const int k = lane + 32 * j; if (k < K) acc[j] = fmaf(dy, __ldg(x + k), acc[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < WG1_MAXK / 32; ++j) { const int k = lane + 32 * j; if (k < K) red[warp][k] = acc[j]; }
+  if (lane == 0) red[warp][K] = sdy;
+  __syncthreads();
+  for (int k = threadIdx.x; k <= K; k += 256) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][k];
+    partial[(long)blockIdx.x * (K + 1) + k] = t;
+  }
+}
+__global__ void wgrad_rank1_final_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int K, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > K) return;
+  float t = 0.0f;
+  for (int c = 0; c < n; ++c) t += partial[(long)c * (K + 1) + k];
+  if (k < K) dW[k] = t;
+  else if (db) db[0] = t;
+}
 }  // namespace go2
 extern "C" {
+int go2_linear_wgrad_rank1(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int K, float* workspace,
+                           long workspace_floats, void* stream) {
+  if (!dY || !X || !dW || !workspace) return set_error(1, "go2_linear_wgrad_rank1: null argument");
+  if (K > WG1_MAXK) return set_error(1, "go2_linear_wgrad_rank1: K > 512");
+  const int ctas = (int)min((long)WG1_CTAS, min((long)((M + 7) / 8), workspace_floats / (K + 1)));
+  if (ctas < 1) return set_error(1, "go2_linear_wgrad_rank1: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_rank1_partial_kernel<<<ctas, 256, 0, st>>>(dY, lddy, X, ldx, workspace, M, K);
+  count_launch();
+  wgrad_rank1_final_kernel<<<(K + 1 + 127) / 128, 128, 0, st>>>(workspace, dW, db, K, ctas);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int go2_linear_forward_simt(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N, int K, int act, void* stream) {
   int rc = launch_gemm(1, 0, X, ldx, 1, W, 1, ldw, Y, ldy, M, N, K, 1, b, act ? EPI_BIAS_ELU : EPI_BIAS, nullptr, 0, 0, (cudaStream_t)stream, Yt, ldyt);
   if (rc) return rc;

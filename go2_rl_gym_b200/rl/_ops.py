@@ -16,6 +16,7 @@ _SIGS = {
     "go2_linear_wgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_linear_wgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_linear_wgrad_tc_rm": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
+    "go2_linear_wgrad_rank1": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _l, _vp],
     "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
     "go2_colsum": [_vp, _i, _vp, _i, _i, _vp, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
@@ -228,6 +229,8 @@ class MlpEngine:
                     call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
                 call("go2_linear_wgrad_tc_rm", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]) if ones else 0, M, n_out, n_in,
                      ptr(self.work), self.work.numel())
+            elif n_out == 1 and n_in <= 512:      # the critic's scalar head: one streaming pass (weights + bias)
+                call("go2_linear_wgrad_rank1", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), ptr(self.gb[l]), M, n_in, ptr(self.work), self.work.numel())
             else:
                 call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
                 call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())

@@ -1,0 +1,136 @@
+"""Policy export (drop-in for legged_gym/utils/exporter.py:13-58): TorchScript `policy.pt` / state-dict `policy.pkl` of a trained
+actor, with the call signatures the deployment loops expect (deploy/deploy_mujoco/deploy_go2.py:235-240):
+
+    ActorCritic        forward(obs[1,45]) -> action[1,12]                                  (exporter.py:127-128)
+    ActorCriticCTS     forward(obs)       -> (action, (None, latent[1,32]))                (exporter.py:130-135)
+    ActorCriticMoECTS  forward(obs)       -> (action, (gate weights[1,8], latent[1,32]))   (exporter.py:145-150)
+
+The CTS variants keep the rolling observation history ([1, H, 45], shift-append) inside the module and expose `reset()`.
+The exported module is plain PyTorch built from the policy's state_dict (inference on the robot / in MuJoCo has no B200);
+it is rebuilt from weights rather than deep-copied because this package's modules evaluate through the CUDA library.
+ONNX export and the recurrent / ablation variants are out of scope."""
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _mlp_from(sd, prefix, last_activation=False):
+    """nn.Sequential of Linear / ELU from the `prefix.{0,2,4,..}.{weight,bias}` entries of a state dict."""
+    idx = sorted({int(k[len(prefix) + 1:].split(".")[0]) for k in sd if k.startswith(prefix + ".") and k.endswith(".weight")})
+    if not idx:
+        raise ValueError(f"no '{prefix}.*' layers in the policy state dict")
+    layers = []
+    for n, i in enumerate(idx):
+        w, b = sd[f"{prefix}.{i}.weight"], sd[f"{prefix}.{i}.bias"]
+        lin = nn.Linear(w.shape[1], w.shape[0])
+        lin.weight.data.copy_(w.detach().cpu())
+        lin.bias.data.copy_(b.detach().cpu())
+        layers.append(lin)
+        if n < len(idx) - 1 or last_activation:
+            layers.append(nn.ELU())
+    return nn.Sequential(*layers)
+
+
+class _ActorPolicy(nn.Module):
+    def __init__(self, sd, normalizer=None):
+        super().__init__()
+        self.actor = _mlp_from(sd, "actor")
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.actor(self.normalizer(x))
+
+    @torch.jit.export
+    def reset(self):
+        pass
+
+
+class _CTSPolicy(nn.Module):
+    def __init__(self, sd, history_length, num_obs, normalizer=None):
+        super().__init__()
+        self.student_encoder = _mlp_from(sd, "student_encoder")
+        self.actor = _mlp_from(sd, "actor.network" if any(k.startswith("actor.network.") for k in sd) else "actor")
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+        self.history = torch.zeros(1, history_length, num_obs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[Optional[torch.Tensor], torch.Tensor]]:
+        x = self.normalizer(x)
+        self.history = torch.cat([self.history[:, 1:], x.unsqueeze(1)], dim=1)
+        latent = F.normalize(self.student_encoder(self.history.flatten(1)), p=2.0, dim=-1)
+        none: Optional[torch.Tensor] = None
+        return self.actor(torch.cat([latent, x], dim=1)), (none, latent)
+
+    @torch.jit.export
+    def reset(self):
+        self.history = torch.zeros_like(self.history)
+
+
+class _MoECTSPolicy(nn.Module):
+    def __init__(self, sd, history_length, num_obs, expert_num, normalizer=None):
+        super().__init__()
+        p = "student_moe_encoder.moe."
+        self.backbone = _mlp_from(sd, p + "experts.backbone.network", last_activation=True)
+        w = sd[p + "experts.experts.weight"].detach().cpu()          # Conv1d(E*H -> E*D, k=1, groups=E): [E*D, H, 1]
+        self.expert_num = int(expert_num)
+        self.out_dim = w.shape[0] // self.expert_num
+        self.register_buffer("expert_w", w.reshape(self.expert_num, self.out_dim, w.shape[1]).clone())      # [E, D, H]
+        self.register_buffer("expert_b", sd[p + "experts.experts.bias"].detach().cpu().reshape(self.expert_num, self.out_dim).clone())
+        self.gate = _mlp_from(sd, p + "gating_network.0.network")
+        self.actor = _mlp_from(sd, "actor.network")
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+        self.history = torch.zeros(1, history_length, num_obs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        x = self.normalizer(x)
+        self.history = torch.cat([self.history[:, 1:], x.unsqueeze(1)], dim=1)
+        h = self.history.flatten(1)
+        weights = torch.softmax(self.gate(h), dim=-1)                                   # [B, E]
+        feat = self.backbone(h).reshape(-1, self.expert_num, self.expert_w.shape[2])      # [B, E, H]
+        outs = torch.einsum("beh,edh->bed", feat, self.expert_w) + self.expert_b          # grouped 1x1 convolution
+        latent = F.normalize(torch.sum(weights.unsqueeze(-1) * outs, dim=1), p=2.0, dim=-1)
+        return self.actor(torch.cat([latent, x], dim=1)), (weights, latent)
+
+    @torch.jit.export
+    def reset(self):
+        self.history = torch.zeros_like(self.history)
+
+
+def build_export_module(policy, normalizer=None):
+    """The plain-PyTorch inference module of `policy` (ActorCritic / ActorCriticCTS / ActorCriticMoECTS, or any module whose state
+    dict has the reference's key layout, e.g. one loaded from a reference checkpoint)."""
+    sd = {k: v for k, v in policy.state_dict().items()}
+    if getattr(policy, "is_recurrent", False):
+        raise NotImplementedError("recurrent policies are not part of the go2 tasks (SURVEY section 2)")
+    hist = getattr(policy, "history", None)
+    if any(k.startswith("student_moe_encoder.") for k in sd):
+        E = sd["student_moe_encoder.moe.gating_network.0.network.%d.weight" % max(
+            int(k.split(".")[-2]) for k in sd if k.startswith("student_moe_encoder.moe.gating_network.0.network.") and k.endswith(".weight"))].shape[0]
+        return _MoECTSPolicy(sd, hist.shape[1], hist.shape[2], E, normalizer)
+    if any(k.startswith("student_encoder.") for k in sd):
+        return _CTSPolicy(sd, hist.shape[1], hist.shape[2], normalizer)
+    if any(k.startswith("actor.") for k in sd):
+        return _ActorPolicy(sd, normalizer)
+    raise ValueError("Policy does not have an actor/student module.")
+
+
+def export_policy_as_jit(policy, path, normalizer=None, filename="policy.pt"):
+    """TorchScript file of the inference policy (same arguments as the reference's export_policy_as_jit)."""
+    os.makedirs(path, exist_ok=True)
+    module = build_export_module(policy, normalizer).to("cpu").eval()
+    scripted = torch.jit.script(module)
+    scripted.save(os.path.join(path, filename))
+    return os.path.join(path, filename)
+
+
+def export_policy_as_pkl(policy, path, filename="policy.pkl"):
+    """state_dict pickle (exporter.py:44-58)."""
+    os.makedirs(path, exist_ok=True)
+    torch.save({k: v.detach().cpu().clone() for k, v in policy.state_dict().items()}, os.path.join(path, filename))
+    return os.path.join(path, filename)
+
+
+def export_policy_as_onnx(policy, path, normalizer=None, filename="policy.onnx", verbose=False):
+    raise NotImplementedError("ONNX export is out of scope (the deployment loops in deploy/ load policy.pt)")

@@ -207,6 +207,10 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
  * Replaces autograd's weight gradient of nn.Linear (rsl_rl/algorithms/ppo.py:175 loss.backward()).  workspace is required. */
 int go2_linear_wgrad_tc_rm(const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K,
                            float* workspace, long workspace_floats, void* stream);
+/* weight / bias gradient of a 1-wide Linear (the critic's head, actor_critic.py:79): dW[K] = dY^T X, db = sum(dY); one streaming pass over X,
+ * deterministic two-stage reduction.  workspace >= 297 * (K + 1) floats for full parallelism. */
+int go2_linear_wgrad_rank1(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int K, float* workspace,
+                           long workspace_floats, void* stream);
 /* out[cols,rows] = in[rows,cols]^T */
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
 /* db[N] = column sums of dY[M,N] */

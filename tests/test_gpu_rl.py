@@ -113,6 +113,27 @@ def test_wgrad_from_row_major_operands(M, N, K):
     assert _rel(dW2.cpu(), dY.t() @ X) < 2e-3
 
 
+@pytest.mark.parametrize("M,K,ldx", [(24576, 128, 132), (1000, 45, 45), (7, 512, 516), (49152, 128, 132)])
+def test_wgrad_rank1(M, K, ldx):
+    """Weight / bias gradient of the critic's 1-wide head (go2_linear_wgrad_rank1) vs fp64 torch; same bits on a second run."""
+    from go2_rl_gym_b200.rl import _ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    X = torch.randn(M, ldx, generator=g)
+    dY = torch.randn(M, 1, generator=g)
+    Xd, dYd = X.cuda(), dY.cuda()
+    work = torch.empty(300 * (K + 1), device="cuda")
+    outs = []
+    for _ in range(2):
+        dW, db = torch.zeros(1, K, device="cuda"), torch.zeros(1, device="cuda")
+        _ops.call("go2_linear_wgrad_rank1", dYd.data_ptr(), 1, Xd.data_ptr(), ldx, dW.data_ptr(), db.data_ptr(), M, K, work.data_ptr(), work.numel())
+        outs.append((dW.clone(), db.clone()))
+    ref_w = (dY.double().t() @ X[:, :K].double()).float()
+    scale = math.sqrt(M)
+    assert torch.allclose(outs[0][0].cpu(), ref_w, rtol=1e-4, atol=2e-5 * scale)
+    assert torch.allclose(outs[0][1].cpu(), dY.double().sum().float().reshape(1), rtol=1e-4, atol=2e-5 * scale)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 512, 45), (8192, 256, 512), (24576, 128, 256), (777, 12, 128)])
 def test_linear_backward(M, N, K):
     from go2_rl_gym_b200.rl import _ops
