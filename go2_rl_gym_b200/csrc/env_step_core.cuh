@@ -258,6 +258,7 @@ struct WarpSmem {
   float cf[GO2_NUM_REPORT][3];
   float feet[4][6];
   float heights[GO2_NUM_HEIGHT];
+  float obsrow[76];            // proprioceptive columns of the privileged observation (go2_env.py:36-47), before clipping
   float part[32];
   float jterm[7][12];
   float fterm[4], coll[8];
@@ -269,7 +270,7 @@ struct WarpSmem {
   float env_origin[3];
   int active[GO2_NUM_COL];
   int ep_len, reset, tout, last_lim, level, ttype, tid, delay_start;
-  int pad_[7];   // stride = 1 mod 32 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
+  int pad_[27];   // stride = 1 mod 32 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
 };
 static_assert((sizeof(WarpSmem) / 4) % 32 == 1, "WarpSmem stride must be 1 mod 32 words");
 
@@ -1082,7 +1083,10 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       float qz = S.root[5], qw = S.root[6];
       float nrm = fmaxf(sqrtf(qz * qz + qw * qw), 1e-9f);
       qz /= nrm; qw /= nrm;
-      for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) {
+#pragma unroll
+      for (int k6 = 0; k6 < (GO2_NUM_HEIGHT + 31) / 32; ++k6) {      // unrolled: the 3 x 6 heightfield loads of a lane are all in flight together
+        const int i = lane + 32 * k6;
+        if (i >= GO2_NUM_HEIGHT) break;
         float bx = C->height_points[i][0], by = C->height_points[i][1];
         float tx = GO2_FMUL(2.0f, -GO2_FMUL(qz, by)), ty = GO2_FMUL(2.0f, GO2_FMUL(qz, bx));
         float px = GO2_FADD(GO2_FADD(bx, GO2_FMUL(qw, tx)), -GO2_FMUL(qz, ty)), py = GO2_FADD(GO2_FADD(by, GO2_FMUL(qw, ty)), GO2_FMUL(qz, tx));
@@ -1210,31 +1214,42 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW + 1 + S.tid, (float)S.level);
     }
   } GO2_SYNC_WARP();
-  // ---- compute_observations (go2_env.py:23-53) + clip (legged_robot.py:96-99); rows are written coalesced
+  // ---- compute_observations (go2_env.py:23-53) + clip (legged_robot.py:96-99).  The 76 proprioceptive columns are first written to
+  // shared memory by the lanes that own their sources (no divergent 12-way branch per column), then rows leave coalesced.
   GO2_WIDE {
-    for (int i = lane; i < GO2_NUM_PRIV; i += 32) {
-      float x;
-      if (i < 3) x = S.blv[i] * C->obs_scale_lin_vel;
-      else if (i < 6) x = S.bav[i - 3] * C->obs_scale_ang_vel;
-      else if (i < 9) x = S.pg[i - 6];
-      else if (i < 11) x = S.cmd[i - 9] * C->obs_scale_lin_vel;
-      else if (i < 12) x = S.cmd[2] * C->obs_scale_ang_vel;
-      else if (i < 24) x = (S.q[i - 12] - C->default_dof_pos[i - 12]) * C->obs_scale_dof_pos;
-      else if (i < 36) x = S.qd[i - 24] * C->obs_scale_dof_vel;
-      else if (i < 48) x = S.act[i - 36];
-      else if (i < 52) { const float* f = S.cf[6 + 4 * (i - 48)]; x = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) * 1e-3f; }
-      else if (i < 64) x = S.tq[i - 52] / M->effort[i - 52];
-      else if (i < 76) x = (S.lqd[i - 64] - S.qd[i - 64]) / C->dt * 1e-4f;
-      else x = fminf(fmaxf(S.root[2] - 0.5f - S.heights[i - 76], -1.0f), 1.0f) * C->obs_scale_height;
-      B->privileged_obs_buf[(size_t)e * GO2_NUM_PRIV + i] = fminf(fmaxf(x, -C->clip_obs), C->clip_obs);
-      if (i >= 3 && i < 48) {
-        const int o = i - 3;
-        if (C->add_noise) {
-          const uint32_t ge = (uint32_t)(C->env_offset + e);
-          U4 r = philox(ge, sp->common_step_counter, ST_NOISE, (uint32_t)(o / 4), C->seed_lo, C->seed_hi);
-          x = GO2_FADD(x, GO2_FMUL(GO2_FADD(GO2_FMUL(2.0f, u01(pick(r, o % 4))), -1.0f), C->noise_scale_vec[o]));
+    if (lane < GO2_NUM_DOF) {
+      S.obsrow[12 + lane] = (S.q[lane] - C->default_dof_pos[lane]) * C->obs_scale_dof_pos;
+      S.obsrow[24 + lane] = S.qd[lane] * C->obs_scale_dof_vel;
+      S.obsrow[36 + lane] = S.act[lane];
+      S.obsrow[52 + lane] = S.tq[lane] / M->effort[lane];
+      S.obsrow[64 + lane] = (S.lqd[lane] - S.qd[lane]) / C->dt * 1e-4f;
+    } else if (lane < 15) {
+      const int k = lane - 12;
+      S.obsrow[k] = S.blv[k] * C->obs_scale_lin_vel; S.obsrow[3 + k] = S.bav[k] * C->obs_scale_ang_vel; S.obsrow[6 + k] = S.pg[k];
+    } else if (lane < 18) {
+      const int k = lane - 15;
+      S.obsrow[9 + k] = S.cmd[k] * (k < 2 ? C->obs_scale_lin_vel : C->obs_scale_ang_vel);
+    } else if (lane < 22) {
+      const float* f = S.cf[6 + 4 * (lane - 18)];
+      S.obsrow[48 + lane - 18] = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) * 1e-3f;
+    }
+  } GO2_SYNC_WARP();
+  GO2_WIDE {
+#pragma unroll
+    for (int k = 0; k < (GO2_NUM_PRIV + 31) / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i < GO2_NUM_PRIV) {
+        float x = (i < 76) ? S.obsrow[i] : fminf(fmaxf(S.root[2] - 0.5f - S.heights[i < 76 ? 0 : i - 76], -1.0f), 1.0f) * C->obs_scale_height;
+        B->privileged_obs_buf[(size_t)e * GO2_NUM_PRIV + i] = fminf(fmaxf(x, -C->clip_obs), C->clip_obs);
+        if (k < 2 && i >= 3 && i < 48) {
+          const int o = i - 3;
+          if (C->add_noise) {
+            const uint32_t ge = (uint32_t)(C->env_offset + e);
+            U4 r = philox(ge, sp->common_step_counter, ST_NOISE, (uint32_t)(o / 4), C->seed_lo, C->seed_hi);
+            x = GO2_FADD(x, GO2_FMUL(GO2_FADD(GO2_FMUL(2.0f, u01(pick(r, o % 4))), -1.0f), C->noise_scale_vec[o]));
+          }
+          B->obs_buf[(size_t)e * GO2_NUM_OBS + o] = fminf(fmaxf(x, -C->clip_obs), C->clip_obs);
         }
-        B->obs_buf[(size_t)e * GO2_NUM_OBS + o] = fminf(fmaxf(x, -C->clip_obs), C->clip_obs);
       }
     }
     for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) B->measured_heights[(size_t)e * GO2_NUM_HEIGHT + i] = S.heights[i];

@@ -569,6 +569,41 @@ __global__ void transpose_kernel(const float* __restrict__ in, long ldin, float*
   for (int i = 0; i < 32; i += 8) if (orow + i < cols && oc < rows) out[(long)(orow + i) * ldout + oc] = t[threadIdx.x][threadIdx.y + i];
 }
 
+// Up to 8 pitch-copies / transposes of small matrices in ONE launch: the operand copies an MLP engine refreshes after every optimiser
+// step (zero-padded first-layer weight, W^T of the hidden layers for dgrad).  32 x 32 tiles; CTA -> (job, tile) by a prefix scan.
+struct RefreshJobs {
+  const float* src[8]; float* dst[8];
+  int ldin[8], ldout[8], rows[8], cols[8], transpose[8], tile0[9];
+  int n;
+};
+__global__ void refresh_weights_kernel(const __grid_constant__ RefreshJobs J) {
+  __shared__ float t[32][33];
+  int j = 0;
+  while (j + 1 < J.n && (int)blockIdx.x >= J.tile0[j + 1]) ++j;
+  const int tile = blockIdx.x - J.tile0[j], tx = (J.cols[j] + 31) / 32;
+  const int c0 = (tile % tx) * 32, r0 = (tile / tx) * 32;
+  const float* in = J.src[j];
+  float* out = J.dst[j];
+  const int rows = J.rows[j], cols = J.cols[j];
+  const long ldin = J.ldin[j], ldout = J.ldout[j];
+  if (!J.transpose[j]) {
+    for (int i = 0; i < 32; i += 8) {
+      const int r = r0 + threadIdx.y + i, c = c0 + threadIdx.x;
+      if (r < rows && c < cols) out[(long)r * ldout + c] = in[(long)r * ldin + c];
+    }
+    return;
+  }
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + threadIdx.y + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) t[threadIdx.y + i][threadIdx.x] = in[(long)r * ldin + c];
+  }
+  __syncthreads();
+  for (int i = 0; i < 32; i += 8) {
+    const int orow = c0 + threadIdx.y + i, oc = r0 + threadIdx.x;
+    if (orow < cols && oc < rows) out[(long)orow * ldout + oc] = t[threadIdx.x][threadIdx.y + i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -806,6 +841,25 @@ int go2_linear_forward_tc_dbg(const float* X, int ldx, const float* W, int ldw, 
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.C = Y; p.ldc = ldy; p.Ct = Yt; p.ldct = ldyt; p.bias = b; p.epi = act ? TC_EPI_BIAS_ELU : TC_EPI_BIAS; p.dbg = dbg;
   return gemm_tc(X, ldx, W, ldw, p, 1, (cudaStream_t)stream);
+}
+
+int go2_refresh_weights(int n, const float* const* src, const int* ldin, float* const* dst, const int* ldout, const int* rows, const int* cols,
+                        const int* transpose, void* stream) {
+  if (n < 1 || n > 8 || !src || !dst || !ldin || !ldout || !rows || !cols || !transpose) return set_error(1, "go2_refresh_weights: 1..8 jobs, no null arrays");
+  RefreshJobs J{};
+  J.n = n;
+  int tiles = 0;
+  for (int j = 0; j < n; ++j) {
+    if (!src[j] || !dst[j] || rows[j] <= 0 || cols[j] <= 0) return set_error(1, "go2_refresh_weights: bad job");
+    J.src[j] = src[j]; J.dst[j] = dst[j]; J.ldin[j] = ldin[j]; J.ldout[j] = ldout[j]; J.rows[j] = rows[j]; J.cols[j] = cols[j]; J.transpose[j] = transpose[j];
+    J.tile0[j] = tiles;
+    tiles += ((rows[j] + 31) / 32) * ((cols[j] + 31) / 32);
+  }
+  J.tile0[n] = tiles;
+  refresh_weights_kernel<<<tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(J);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream) {

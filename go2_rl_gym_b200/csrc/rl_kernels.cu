@@ -294,23 +294,29 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs p) {
                 - p.entropy_coef * p.inv_count / s;                         // - coef * d mean(entropy) / d s
     }
   }
-  // block reduction (fixed tree) then one atomic per block per scalar
-  __shared__ float red[256];
-  auto block_sum = [&](float v) {
-    red[threadIdx.x] = v;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
-    float r = red[0];
-    __syncthreads();
-    return r;
+  // block reduction: warp-shuffle butterflies (fixed tree), one shared-memory hop across the 8 warps, then one atomic per block per scalar
+  __shared__ float red[8][22];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto warp_sum = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
   };
-  float t;
-  t = block_sum(kl); if (threadIdx.x == 0) atomicAdd(p.scal + 0, t);
-  t = block_sum(surr); if (threadIdx.x == 0) atomicAdd(p.scal + 1, t);
-  t = block_sum(vl); if (threadIdx.x == 0) atomicAdd(p.scal + 2, t);
-  t = block_sum(ent); if (threadIdx.x == 0) atomicAdd(p.scal + 3, t);
-  t = block_sum(surr_b); if (threadIdx.x == 0) atomicAdd(p.scal + 19, t);
-  for (int k = 0; k < p.A; ++k) { t = block_sum(dstd[k]); if (threadIdx.x == 0) atomicAdd(p.scal + 4 + k, t); }
+  float vals[5] = {kl, surr, vl, ent, surr_b};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { const float t = warp_sum(vals[k]); if (lane == 0) red[warp][k] = t; }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { const float t = warp_sum(dstd[k]); if (lane == 0) red[warp][5 + k] = t; }
+  __syncthreads();
+  if (threadIdx.x < 21) {
+    const int k = threadIdx.x;
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][k];
+    if (k < 4) atomicAdd(p.scal + k, t);
+    else if (k == 4) atomicAdd(p.scal + 19, t);
+    else if (k - 5 < p.A) atomicAdd(p.scal + 4 + (k - 5), t);
+  }
 }
 
 // KL-adaptive learning rate (ppo.py:139-151), entirely on the device: lr_state = {lr}
@@ -421,6 +427,149 @@ __global__ void dgrad_rank1_kernel(const float* __restrict__ dY, long lddy, cons
     if (kk < K && m < M) dXt[(long)kk * lddxt + m] = t[threadIdx.x][threadIdx.y + i];
   }
 }
+// ---- Linear layers with a narrow output (N <= 16, K <= 128): the actor's 12-wide head (actor_critic.py:66).  A 128-wide tensor-core
+// tile would be 90 % padding there; these are streaming fp32 kernels, one warp per row, lane l owning the columns l, l + 32, ...
+constexpr int SN_MAXN = 16, SN_KJ = 4;
+// Y[m][n] = sum_k X[m][k] W[n][k] + b[n]
+__global__ void __launch_bounds__(256) linear_fwd_smalln_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ W, long ldw,
+                                                               const float* __restrict__ b, float* __restrict__ Y, long ldy, int M, int N, int K) {
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  float w[SN_MAXN][SN_KJ];
+#pragma unroll
+  for (int n = 0; n < SN_MAXN; ++n)
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; w[n][j] = (n < N && k < K) ? __ldg(W + (long)n * ldw + k) : 0.0f; }
+  const float bias = (lane < N && b) ? __ldg(b + lane) : 0.0f;
+  float xn[SN_KJ];
+#pragma unroll
+  for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; xn[j] = (gw < M && k < K) ? __ldg(X + (long)gw * ldx + k) : 0.0f; }
+  for (int m = gw; m < M; m += nw) {
+    float x[SN_KJ];
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) x[j] = xn[j];
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; xn[j] = (m + nw < M && k < K) ? __ldg(X + (long)(m + nw) * ldx + k) : 0.0f; }   // next row in flight
+    float mine = 0.0f;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; ++n) {
+      if (n < N) {
+        float p = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SN_KJ; ++j) p = fmaf(x[j], w[n][j], p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == n) mine = p;
+      }
+    }
+    if (lane < N) Y[(long)m * ldy + lane] = mine + bias;
+  }
+}
+// dX[m][k] = (sum_n dY[m][n] W[n][k]) * ELU'(act[m][k])
+__global__ void __launch_bounds__(256) linear_dgrad_smalln_kernel(const float* __restrict__ dY, long lddy, const float* __restrict__ W, long ldw,
+                                                                 const float* __restrict__ act, long ldact, float* __restrict__ dX, long lddx,
+                                                                 int M, int N, int K) {
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  float w[SN_MAXN][SN_KJ];
+#pragma unroll
+  for (int n = 0; n < SN_MAXN; ++n)
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; w[n][j] = (n < N && k < K) ? __ldg(W + (long)n * ldw + k) : 0.0f; }
+  float dyn = (gw < M && lane < N) ? __ldg(dY + (long)gw * lddy + lane) : 0.0f;
+  for (int m = gw; m < M; m += nw) {
+    const float dyl = dyn;
+    dyn = (m + nw < M && lane < N) ? __ldg(dY + (long)(m + nw) * lddy + lane) : 0.0f;                 // next row in flight
+    float yact[SN_KJ];
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; yact[j] = (act && k < K) ? __ldg(act + (long)m * ldact + k) : 1.0f; }
+    float acc[SN_KJ] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; ++n) {
+      if (n < N) {
+        const float dy = __shfl_sync(0xffffffffu, dyl, n);
+#pragma unroll
+        for (int j = 0; j < SN_KJ; ++j) acc[j] = fmaf(dy, w[n][j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) {
+      const int k = lane + 32 * j;
+      if (k < K) {
+        float v = acc[j];
+        if (act) { const float y = yact[j]; v *= (y > 0.0f ? 1.0f : y + 1.0f); }
+        dX[(long)m * lddx + k] = v;
+      }
+    }
+  }
+}
+// partial[c][n][k] = sum over CTA c's rows of dY[m][n] X[m][k];  partial[c][N*K + n] = sum of dY[m][n]   (4 warps per CTA)
+__global__ void __launch_bounds__(128) linear_wgrad_smalln_partial_kernel(const float* __restrict__ dY, long lddy, const float* __restrict__ X, long ldx,
+                                                                         float* __restrict__ partial, int M, int N, int K) {
+  __shared__ float red[4][SN_MAXN * 32 * SN_KJ / 4 + 4];      // one 32-column slab at a time: [warp][n][lane] (+ bias sums)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = (M + gridDim.x - 1) / gridDim.x, m0 = blockIdx.x * rows, m1 = min(M, m0 + rows);
+  float acc[SN_MAXN][SN_KJ], sdy = 0.0f;
+#pragma unroll
+  for (int n = 0; n < SN_MAXN; ++n)
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) acc[n][j] = 0.0f;
+  float xn[SN_KJ], dyn = (m0 + warp < m1 && lane < N) ? __ldg(dY + (long)(m0 + warp) * lddy + lane) : 0.0f;
+#pragma unroll
+  for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; xn[j] = (m0 + warp < m1 && k < K) ? __ldg(X + (long)(m0 + warp) * ldx + k) : 0.0f; }
+  for (int m = m0 + warp; m < m1; m += 4) {
+    const float dyl = dyn;
+    sdy += dyl;
+    float x[SN_KJ];
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) x[j] = xn[j];
+    dyn = (m + 4 < m1 && lane < N) ? __ldg(dY + (long)(m + 4) * lddy + lane) : 0.0f;                  // next row in flight
+#pragma unroll
+    for (int j = 0; j < SN_KJ; ++j) { const int k = lane + 32 * j; xn[j] = (m + 4 < m1 && k < K) ? __ldg(X + (long)(m + 4) * ldx + k) : 0.0f; }
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; ++n) {
+      if (n < N) {
+        const float dy = __shfl_sync(0xffffffffu, dyl, n);
+#pragma unroll
+        for (int j = 0; j < SN_KJ; ++j) acc[n][j] = fmaf(dy, x[j], acc[n][j]);
+      }
+    }
+  }
+  float* out = partial + (long)blockIdx.x * (N * K + N);
+#pragma unroll
+  for (int j = 0; j < SN_KJ; ++j) {              // cross-warp reduction, one 32-column slab per pass, fixed order
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; ++n) red[warp][n * 32 + lane] = acc[n][j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < N * 32; t += 128) {
+      const int n = t >> 5, k = (t & 31) + 32 * j;
+      if (k < K) out[n * K + k] = (red[0][t] + red[1][t]) + (red[2][t] + red[3][t]);
+    }
+    __syncthreads();
+  }
+  red[warp][lane] = sdy;
+  __syncthreads();
+  if (threadIdx.x < N) out[N * K + threadIdx.x] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+// out[t] = sum over the n_part partial blocks, t in [0, N K + N): warp w of a CTA sums blocks w, w + 8, ... (independent coalesced loads in
+// flight), then the 8 warp sums are added in a fixed tree.  t < N K lands in dW (row pitch lddw), the rest in db.
+__global__ void __launch_bounds__(256) wgrad_partials_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, long lddw,
+                                                                   float* __restrict__ db, int N, int K, int n_part) {
+  __shared__ float red[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, per = N * K + N;
+  const int t = blockIdx.x * 32 + lane;
+  float s = 0.0f;
+  if (t < per) {
+#pragma unroll 8
+    for (int c = warp; c < n_part; c += 8) s += __ldg(partial + (long)c * per + t);
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && t < per) {
+    const float r = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+    if (t < N * K) dW[(long)(t / K) * lddw + (t % K)] = r;
+    else if (db) db[t - N * K] = r;
+  }
+}
+
 // dW[k] = sum_m dy[m] X[m][k], db = sum_m dy[m]: weight gradient of a 1-wide Linear (the critic's head).  One streaming pass over X:
 // CTA c takes a contiguous block of rows, warp w its rows w, w+8, ..., lane l the columns l, l+32, ... (coalesced row reads);
 // partial[c][0..K-1] = column sums, partial[c][K] = sum of dy.  Fixed summation order everywhere (deterministic).
@@ -451,16 +600,45 @@ __global__ void __launch_bounds__(256) wgrad_rank1_partial_kernel(const float* _
     partial[(long)blockIdx.x * (K + 1) + k] = t;
   }
 }
-__global__ void wgrad_rank1_final_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int K, int n) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > K) return;
-  float t = 0.0f;
-  for (int c = 0; c < n; ++c) t += partial[(long)c * (K + 1) + k];
-  if (k < K) dW[k] = t;
-  else if (db) db[0] = t;
-}
 }  // namespace go2
 extern "C" {
+int go2_linear_forward_smalln(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int N, int K, void* stream) {
+  if (!X || !W || !Y) return set_error(1, "go2_linear_forward_smalln: null argument");
+  if (N > SN_MAXN || K > 32 * SN_KJ) return set_error(1, "go2_linear_forward_smalln: needs N <= 16 and K <= 128");
+  const int ctas = max(1, min(148 * 2, (M + 7) / 8));
+  linear_fwd_smalln_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(X, ldx, W, ldw, b, Y, ldy, M, N, K);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int go2_linear_dgrad_smalln(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, int M, int N, int K,
+                            void* stream) {
+  if (!dY || !W || !dX) return set_error(1, "go2_linear_dgrad_smalln: null argument");
+  if (N > SN_MAXN || K > 32 * SN_KJ) return set_error(1, "go2_linear_dgrad_smalln: needs N <= 16 and K <= 128");
+  const int ctas = max(1, min(148 * 2, (M + 7) / 8));
+  linear_dgrad_smalln_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(dY, lddy, W, ldw, act_in, ldact, dX, lddx, M, N, K);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int go2_linear_wgrad_smalln(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K, float* workspace,
+                            long workspace_floats, void* stream) {
+  if (!dY || !X || !dW || !workspace) return set_error(1, "go2_linear_wgrad_smalln: null argument");
+  if (N > SN_MAXN || K > 32 * SN_KJ) return set_error(1, "go2_linear_wgrad_smalln: needs N <= 16 and K <= 128");
+  const long per = (long)N * K + N;
+  const int ctas = (int)min((long)296, min((long)((M + 3) / 4), workspace_floats / per));
+  if (ctas < 1) return set_error(1, "go2_linear_wgrad_smalln: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  linear_wgrad_smalln_partial_kernel<<<ctas, 128, 0, st>>>(dY, lddy, X, ldx, workspace, M, N, K);
+  count_launch();
+  wgrad_partials_reduce_kernel<<<(unsigned)((per + 31) / 32), 256, 0, st>>>(workspace, dW, lddw, db, N, K, ctas);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int go2_linear_wgrad_rank1(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int K, float* workspace,
                            long workspace_floats, void* stream) {
   if (!dY || !X || !dW || !workspace) return set_error(1, "go2_linear_wgrad_rank1: null argument");
@@ -470,7 +648,7 @@ int go2_linear_wgrad_rank1(const float* dY, int lddy, const float* X, int ldx, f
   cudaStream_t st = (cudaStream_t)stream;
   wgrad_rank1_partial_kernel<<<ctas, 256, 0, st>>>(dY, lddy, X, ldx, workspace, M, K);
   count_launch();
-  wgrad_rank1_final_kernel<<<(K + 1 + 127) / 128, 128, 0, st>>>(workspace, dW, db, K, ctas);
+  wgrad_partials_reduce_kernel<<<(K + 1 + 31) / 32, 256, 0, st>>>(workspace, dW, K, db, 1, K, ctas);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -16,7 +16,11 @@ _SIGS = {
     "go2_linear_wgrad_simt": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_linear_wgrad_tc": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_linear_wgrad_tc_rm": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
+    "go2_linear_forward_smalln": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp],
+    "go2_linear_dgrad_smalln": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "go2_linear_wgrad_smalln": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _l, _vp],
     "go2_linear_wgrad_rank1": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _l, _vp],
+    "go2_refresh_weights": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "go2_transpose": [_vp, _i, _vp, _i, _i, _i, _vp],
     "go2_colsum": [_vp, _i, _vp, _i, _i, _vp, _vp],
     "go2_sample_actions": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _i, _vp],
@@ -162,20 +166,29 @@ class MlpEngine:
         self._xpad = torch.zeros(max_rows, self.kpad0, device=dev) if self.tc else None
         self.dx = torch.zeros(max(train_rows, 1), self.kpad0, device=dev) if need_dx else None
         self._dirty_w0, self._dirty_wt = True, True
+        self._jobs = None
 
     def mark_dirty(self):
         self._dirty_w0, self._dirty_wt = True, True
 
     def _refresh(self, need_wt):
-        if not self.tc:
+        """Operand copies derived from the weights, rebuilt in ONE launch after the weights changed: the zero-padded first-layer weight and
+        W^T of every layer whose dgrad runs on the tensor cores (narrow heads read W directly)."""
+        if not self.tc or not (self._dirty_w0 or (need_wt and self._dirty_wt)):
             return
-        if self._dirty_w0:
-            self.W0p[:, :self.dims[0]].copy_(self.W[0])
-            self._dirty_w0 = False
-        if need_wt and self._dirty_wt:
+        if self._jobs is None:
+            jobs = [(self.W[0], self.dims[0], self.W0p, self.kpad0, self.dims[1], self.dims[0], 0)]
             for l in range(0 if self.need_dx else 1, self.L):
-                call("go2_transpose", ptr(self.W[l]), self.dims[l], ptr(self.Wt[l]), self.Wt[l].shape[1], self.dims[l + 1], self.dims[l])
-            self._dirty_wt = False
+                if self.dims[l + 1] <= 16 and self.dims[l] <= 128 and l > 0:
+                    continue
+                jobs.append((self.W[l], self.dims[l], self.Wt[l], self.Wt[l].shape[1], self.dims[l + 1], self.dims[l], 1))
+            assert len(jobs) <= 8
+            n = len(jobs)
+            vp, ia = (C.c_void_p * n), (C.c_int * n)
+            self._jobs = (n, vp(*[j[0].data_ptr() for j in jobs]), ia(*[j[1] for j in jobs]), vp(*[j[2].data_ptr() for j in jobs]),
+                          ia(*[j[3] for j in jobs]), ia(*[j[4] for j in jobs]), ia(*[j[5] for j in jobs]), ia(*[j[6] for j in jobs]))
+        call("go2_refresh_weights", *self._jobs)
+        self._dirty_w0 = self._dirty_wt = False
 
     @property
     def out(self):
@@ -204,7 +217,10 @@ class MlpEngine:
             else:
                 dst, ldd = self.acts[l], self.dims[l + 1] + 4
             act = 0 if (last and not self.last_act) else 1
-            if self.tc:
+            if act == 0 and self.dims[l + 1] <= 16 and self.dims[l] <= 128 and l > 0:
+                # narrow heads (12 actions, 1 value): streaming fp32 kernel instead of a 128-wide tensor-core tile
+                call("go2_linear_forward_smalln", ptr(src), lds, ptr(self.W[l]), self.dims[l], ptr(self.b[l]), ptr(dst), ldd, M, self.dims[l + 1], self.dims[l])
+            elif self.tc:
                 # layer 0 contracts over the padded width: the padding columns of W0p are zero
                 W, ldw, K = (self.W0p, self.kpad0, self.kpad0) if l == 0 else (self.W[l], self.dims[l], self.dims[l])
                 call("go2_linear_forward_tc", ptr(src), lds, ptr(W), ldw, ptr(self.b[l]), ptr(dst), ldd, 0, 0, M, self.dims[l + 1], K, act)
@@ -224,7 +240,10 @@ class MlpEngine:
             n_out, n_in = self.dims[l + 1], self.dims[l]
             xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in + 4)
             ones = self._x_ones if l == 0 else True
-            if self.tc and ldd % 4 == 0 and d.data_ptr() % 16 == 0:
+            small = n_out <= 16 and n_in <= 128 and l > 0
+            if small:       # narrow heads: streaming fp32 kernels (weights + bias in one pass)
+                call("go2_linear_wgrad_smalln", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]), M, n_out, n_in, ptr(self.work), self.work.numel())
+            elif self.tc and ldd % 4 == 0 and d.data_ptr() % 16 == 0:
                 if not ones:
                     call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
                 call("go2_linear_wgrad_tc_rm", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]) if ones else 0, M, n_out, n_in,
@@ -236,7 +255,9 @@ class MlpEngine:
                 call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())
             if l > 0:
                 nxt = self.dbuf[l % 2]
-                if self.tc and n_out % 4 == 0:
+                if small:
+                    call("go2_linear_dgrad_smalln", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in + 4, ptr(nxt), n_in, M, n_out, n_in)
+                elif self.tc and n_out % 4 == 0:
                     call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[l]), self.Wt[l].shape[1], ptr(self.acts[l - 1]), n_in + 4, 0, 0,
                          ptr(nxt), n_in, 0, 0, M, n_out, n_in)
                 else:

@@ -251,9 +251,11 @@ class _StudentMoE:
         call("go2_l2norm_backward", ptr(dlatent), D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), D, 0, M, D)
         call("go2_moe_combine_backward", ptr(self.dpre), ptr(self.gates), ptr(self.eo), ptr(self.usage), float(lb_coef), ptr(self.deo), 0,
              ptr(self.dlogits), 0, M, E, D)
-        if self._dirty and tc:
-            for e in range(E):
-                call("go2_transpose", ptr(self.We) + 4 * e * D * H, H, ptr(self.Wet) + 4 * e * H * D, D, D, H)
+        if self._dirty and tc:      # W_e^T of the 8 experts in one launch
+            import ctypes as C
+            vp, ia = (C.c_void_p * E), (C.c_int * E)
+            call("go2_refresh_weights", E, vp(*[ptr(self.We) + 4 * e * D * H for e in range(E)]), ia(*([H] * E)),
+                 vp(*[ptr(self.Wet) + 4 * e * H * D for e in range(E)]), ia(*([D] * E)), ia(*([D] * E)), ia(*([H] * E)), ia(*([1] * E)))
             self._dirty = False
         call("go2_colsum", ptr(self.deo), E * D, ptr(self.gbe), M, E * D, ptr(self.work))
         feat, ldf = self.backbone.out, self.backbone.ld_out

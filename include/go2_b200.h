@@ -207,10 +207,22 @@ int go2_linear_wgrad_tc(const float* dZt, int lddzt, const float* Xt, int ldxt, 
  * Replaces autograd's weight gradient of nn.Linear (rsl_rl/algorithms/ppo.py:175 loss.backward()).  workspace is required. */
 int go2_linear_wgrad_tc_rm(const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K,
                            float* workspace, long workspace_floats, void* stream);
+/* Linear layers with a narrow output (N <= 16, K <= 128; the actor's 12-wide head, actor_critic.py:66): streaming fp32 kernels, one warp per
+ * row, warp-shuffle reductions.  forward: Y = X W^T + b; dgrad: dX = (dY W) * ELU'(act_in) (act_in optional); wgrad: dW = dY^T X, db = sum(dY)
+ * (deterministic two-stage reduction, workspace >= 296 * (N K + N) floats for full parallelism). */
+int go2_linear_forward_smalln(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int M, int N, int K, void* stream);
+int go2_linear_dgrad_smalln(const float* dY, int lddy, const float* W, int ldw, const float* act_in, int ldact, float* dX, int lddx, int M, int N, int K,
+                            void* stream);
+int go2_linear_wgrad_smalln(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int M, int N, int K, float* workspace,
+                            long workspace_floats, void* stream);
 /* weight / bias gradient of a 1-wide Linear (the critic's head, actor_critic.py:79): dW[K] = dY^T X, db = sum(dY); one streaming pass over X,
  * deterministic two-stage reduction.  workspace >= 297 * (K + 1) floats for full parallelism. */
 int go2_linear_wgrad_rank1(const float* dY, int lddy, const float* X, int ldx, float* dW, float* db, int M, int K, float* workspace,
                            long workspace_floats, void* stream);
+/* n <= 8 small pitch-copies (transpose[j] = 0) / transposes (1) in one launch: dst_j[cols_j or rows_j ...] from src_j[rows_j, cols_j].  The operand
+ * copies an MLP refreshes after each optimiser step (padded first-layer weight, W^T for dgrad).  The arrays are HOST arrays of device pointers / sizes. */
+int go2_refresh_weights(int n, const float* const* src, const int* ldin, float* const* dst, const int* ldout, const int* rows, const int* cols,
+                        const int* transpose, void* stream);
 /* out[cols,rows] = in[rows,cols]^T */
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
 /* db[N] = column sums of dY[M,N] */

@@ -113,6 +113,35 @@ def test_wgrad_from_row_major_operands(M, N, K):
     assert _rel(dW2.cpu(), dY.t() @ X) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(24576, 12, 128), (4096, 1, 128), (1001, 16, 100), (5, 8, 32)])
+def test_small_n_linear_kernels(M, N, K):
+    """Narrow-output Linear layers (actor / critic heads): forward, dgrad (with ELU'), wgrad + bias gradient vs fp64 torch; deterministic."""
+    from go2_rl_gym_b200.rl import _ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    ldx = K + 4
+    Xp = torch.nn.functional.elu(torch.randn(M, ldx, generator=g))
+    X = Xp[:, :K]
+    W, b, dY = torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    Xd, Wd, bd, dYd = Xp.cuda(), W.cuda(), b.cuda(), dY.cuda()
+    Y = torch.zeros(M, N, device="cuda")
+    _ops.call("go2_linear_forward_smalln", Xd.data_ptr(), ldx, Wd.data_ptr(), K, bd.data_ptr(), Y.data_ptr(), N, M, N, K)
+    assert torch.allclose(Y.cpu(), (X.double() @ W.double().t() + b.double()).float(), rtol=1e-5, atol=1e-5)
+    dX = torch.zeros(M, K, device="cuda")
+    _ops.call("go2_linear_dgrad_smalln", dYd.data_ptr(), N, Wd.data_ptr(), K, Xd.data_ptr(), ldx, dX.data_ptr(), K, M, N, K)
+    ref = (dY.double() @ W.double()) * torch.where(X > 0, torch.ones_like(X), X + 1).double()
+    assert torch.allclose(dX.cpu(), ref.float(), rtol=1e-5, atol=1e-5)
+    work = torch.empty(296 * (N * K + N), device="cuda")
+    outs = []
+    for _ in range(2):
+        dW, db = torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda")
+        _ops.call("go2_linear_wgrad_smalln", dYd.data_ptr(), N, Xd.data_ptr(), ldx, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
+        outs.append((dW.clone(), db.clone()))
+    scale = math.sqrt(M)
+    assert torch.allclose(outs[0][0].cpu(), (dY.double().t() @ X.double()).float(), rtol=1e-4, atol=2e-5 * scale)
+    assert torch.allclose(outs[0][1].cpu(), dY.double().sum(0).float(), rtol=1e-4, atol=2e-5 * scale)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("M,K,ldx", [(24576, 128, 132), (1000, 45, 45), (7, 512, 516), (49152, 128, 132)])
 def test_wgrad_rank1(M, K, ldx):
     """Weight / bias gradient of the critic's 1-wide head (go2_linear_wgrad_rank1) vs fp64 torch; same bits on a second run."""
