@@ -309,3 +309,31 @@ def test_graph_rollout_equals_eager_rollout(task, log):
     for k in outs[0]:
         a, b = outs[0][k], outs[1][k]
         assert (torch.equal(a, b) if torch.is_tensor(a) else a == b), k
+
+
+@pytest.mark.parametrize("task", ["go2", "go2_moe_cts"])
+def test_play_loop_and_policy_export(task, tmp_path):
+    """legged_gym/scripts/play.py (reference play.py:15-66): 7 x 7 non-curriculum terrain, noise / pushes / randomisation off, deterministic
+    act_inference for a few steps, TorchScript export whose output matches the CUDA inference path on the same observations."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("play_script", os.path.join(root, "legged_gym", "scripts", "play.py"))
+    play_script = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(play_script)
+    from go2_rl_gym_b200.envs import task_registry
+    from go2_rl_gym_b200.utils import get_args
+    args = get_args(["--task", task, "--num_envs", "64", "--headless"])
+    env, _ = task_registry.make_env(task, args)
+    runner, _ = task_registry.make_alg_runner(env, task, args, log_root=None)
+    stats = play_script.play(get_args(["--task", task, "--num_envs", "49", "--headless"]), num_steps=30, runner=runner, export_dir=str(tmp_path))
+    assert stats["steps"] == 30 and all(math.isfinite(v) for v in stats.values())
+    m = torch.jit.load(os.path.join(tmp_path, "policy.pt"))
+    model = runner.alg.actor_critic if task == "go2" else runner.alg.model
+    obs = torch.randn(1, 45)
+    out = m(obs)
+    out = out[0] if isinstance(out, tuple) else out
+    if task == "go2":       # feed-forward actor: the exported module and the CUDA inference path see the same input
+        ref = model.act_inference(obs.cuda().repeat(64, 1))[0:1].cpu()
+        assert torch.allclose(out, ref, atol=5e-3)          # tf32 GEMMs on the CUDA side
+    else:
+        assert out.shape == (1, 12) and torch.isfinite(out).all()
