@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_worker(num_envs, warmup, steps, budget_s):
+def cpu_worker(num_envs, warmup, steps, budget_s, out):
     """Runs in a child process: the CPU pipeline for `steps` iterations (or until the time budget), prints one JSON line."""
     import torch
     from oracle.cpu_pipeline import CpuPipeline
@@ -89,7 +89,7 @@ def cpu_worker(num_envs, warmup, steps, budget_s):
         n, c, l = pipe.iteration()
         n_steps += n; iters += 1; tc += c; tl += l
     dt = time.time() - t0
-    print(json.dumps({"value": n_steps / dt, "iters": iters, "seconds": dt, "cores": cores, "collect_s": tc, "learn_s": tl}))
+    print(json.dumps({"value": n_steps / dt, "iters": iters, "seconds": dt, "cores": cores, "collect_s": tc, "learn_s": tl}), file=out, flush=True)
 
 
 def run_cpu_worker(num_envs, warmup, steps, budget_s, hard_timeout_s):
@@ -101,7 +101,7 @@ def run_cpu_worker(num_envs, warmup, steps, budget_s, hard_timeout_s):
         return {"value": None, "error": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, out):
     """The reference's algorithm on the host cores: oracle env (C++, OpenMP) + fp32 PyTorch PPO (all threads)."""
     if rank != 0:
         return
@@ -110,7 +110,7 @@ def reference_arm(args, rank, world):
     v, cores = r.get("value"), r.get("cores", os.cpu_count())
     dt = r.get("seconds", 0.0) or 0.0
     if v is None:
-        print(json.dumps({"impl": "reference", "unavailable": r.get("error", "cpu pipeline failed")}))
+        print(json.dumps({"impl": "reference", "unavailable": r.get("error", "cpu pipeline failed")}), file=out, flush=True)
         return
     line = {"impl": "reference", "metric": "go2 env-steps/sec (PPO iteration)", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(r.get("iters", 1), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -118,10 +118,27 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": f"{n_sample} envs x 24 steps + full PPO update per step (oracle physics: PhysX is closed source)"},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: libraries write to file descriptor 1 on their own (NCCL prints its version banner there),
+    so fd 1 is pointed at stderr for the whole run and the line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
 
 
 def main():
+    out = _claim_stdout()
+    try:
+        _main(out)
+    finally:
+        out.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -133,9 +150,9 @@ def main():
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.cpu_worker:
-        return cpu_worker(int(args.cpu_worker[0]), int(args.cpu_worker[1]), int(args.cpu_worker[2]), float(args.cpu_worker[3]))
+        return cpu_worker(int(args.cpu_worker[0]), int(args.cpu_worker[1]), int(args.cpu_worker[2]), float(args.cpu_worker[3]), out)
     if args.impl == "reference":
-        return reference_arm(args, rank, world)
+        return reference_arm(args, rank, world, out)
 
     import numpy as np
     import torch
@@ -319,7 +336,7 @@ def main():
                              "note": "latency/issue-bound serial 13-body recursion; HBM fraction is structurally tiny (SURVEY 7.2)"},
                 "roofline_gemm": gemm, "clocks": clocks, "cpu_baseline": cpu,
                 "split_ms": {"collection": col_ms, "learning": lrn_ms}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

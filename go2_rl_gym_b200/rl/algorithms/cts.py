@@ -307,3 +307,7 @@ class MoECTS(CTS):
 
     def __init__(self, model, num_envs, history_length, load_balance_coef=0.01, **kwargs):
         super().__init__(model, num_envs, history_length, load_balance_coef=load_balance_coef, **kwargs)
+
+
+class MoENGCTS(MoECTS):
+    """MoENGCTS (rsl_rl/algorithms/moe_ng_cts.py:40-234): identical to MoECTS; the no-goal column selection lives in the model's student encoder."""

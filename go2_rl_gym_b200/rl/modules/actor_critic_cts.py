@@ -201,18 +201,26 @@ class _StudentMLP:
 class _StudentMoE:
     """StudentMoEEncoder (modules/utils.py:69-151): shared backbone -> 8 block-diagonal experts, softmax gate, weighted sum, L2Norm."""
 
-    def __init__(self, model, prefix, in_dim, hidden_dims, E, D, max_rows, train_rows):
+    def __init__(self, model, prefix, in_dim, hidden_dims, E, D, max_rows, train_rows, names=None, expert_cols=None):
+        """names: parameter names {backbone: [...], gate: [...], experts: name} when they differ from the MoE-CTS layout (the no-goal variant);
+        expert_cols: column indices of the history the experts' backbone sees (gate: the full history), actor_critic_moe_ng_cts.py:185-188."""
         self.m, self.E, self.D, self.H = model, E, D, hidden_dims[-1]
         dev = model.device
-        bdims = [in_dim, *hidden_dims[:-1], E * self.H]
+        self.expert_cols = None if expert_cols is None else expert_cols.to(dev)
+        b_in = in_dim if expert_cols is None else int(expert_cols.numel())
+        bdims = [b_in, *hidden_dims[:-1], E * self.H]
         gdims = [in_dim, *hidden_dims[:-1], E]
         nb = len(bdims) - 1
-        self.backbone = model._engine(_linear_names(prefix + ".moe.experts.backbone.network", nb), bdims, max_rows, train_rows, last_act=True)
-        self.gate = model._engine(_linear_names(prefix + ".moe.gating_network.0.network", len(gdims) - 1), gdims, max_rows, train_rows)
-        self.We = model._views[prefix + ".moe.experts.experts.weight"].view(E * D, self.H)     # Conv1d [E*D, H, 1] -> E blocks of [D, H]
-        self.be = model._views[prefix + ".moe.experts.experts.bias"]
-        self.gWe = model._gviews[prefix + ".moe.experts.experts.weight"].view(E * D, self.H)
-        self.gbe = model._gviews[prefix + ".moe.experts.experts.bias"]
+        if names is None:
+            names = {"backbone": _linear_names(prefix + ".moe.experts.backbone.network", nb),
+                     "gate": _linear_names(prefix + ".moe.gating_network.0.network", len(gdims) - 1), "experts": prefix + ".moe.experts.experts"}
+        self.backbone = model._engine(names["backbone"], bdims, max_rows, train_rows, last_act=True)
+        self.gate = model._engine(names["gate"], gdims, max_rows, train_rows)
+        self._hsel = torch.zeros(max_rows, b_in, device=dev) if expert_cols is not None else None
+        self.We = model._views[names["experts"] + ".weight"].view(E * D, self.H)     # Conv1d [E*D, H, 1] -> E blocks of [D, H]
+        self.be = model._views[names["experts"] + ".bias"]
+        self.gWe = model._gviews[names["experts"] + ".weight"].view(E * D, self.H)
+        self.gbe = model._gviews[names["experts"] + ".bias"]
         tr = max(train_rows, 1)
         z = lambda *s: torch.empty(*s, device=dev)
         self.eo, self.logits, self.gates = z(max_rows, E * D), z(max_rows, E), z(max_rows, E)
@@ -234,7 +242,11 @@ class _StudentMoE:
 
     def forward(self, hist, M, out, train=False, x_ones=False):
         E, D, H = self.E, self.D, self.H
-        self.backbone.forward(hist, hist.shape[1], M, train=train, x_ones=x_ones)
+        if self.expert_cols is None:
+            self.backbone.forward(hist, hist.shape[1], M, train=train, x_ones=x_ones)
+        else:   # the experts see the history without its command columns (gather into a dense buffer; the engine pads it itself)
+            torch.index_select(hist[:M], 1, self.expert_cols, out=self._hsel[:M])
+            self.backbone.forward(self._hsel, self._hsel.shape[1], M, train=train, x_ones=False)
         feat, ldf = self.backbone.out, self.backbone.ld_out
         for e in range(E):  # block-diagonal expert layer = Conv1d(groups=E, kernel 1)
             fn = "go2_linear_forward_tc" if _ops.use_tc() else "go2_linear_forward_simt"
@@ -357,3 +369,69 @@ class ActorCriticCTS(_CTSBase):
         self.critic_engine = self._engine(_linear_names("critic", len(self.c_dims) - 1), self.c_dims, max_rows, tr1)
         self.student = _StudentMLP(self, _linear_names("student_encoder", len(self.s_dims) - 1), self.s_dims, max_rows, trs)
         ActorCriticMoECTS._common_buffers(self, dev, max_rows, max(trt, trs))
+
+
+class _NGStudentParams(nn.Module):
+    """Parameter container with the reference's key layout (actor_critic_moe_ng_cts.py:187-230): experts_backbone.{0,2,..}, experts_hidden.0,
+    experts_out (grouped 1x1 conv), gating_network.{0,2,..}."""
+
+    def __init__(self, expert_dim, gating_dim, hidden_dims, expert_num, expert_hidden_dim, latent_dim):
+        super().__init__()
+        self.norm_layer = L2Norm()
+        layers, last = [], expert_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(last, h), nn.ELU()]
+            last = h
+        self.experts_backbone = nn.Sequential(*layers)
+        self.experts_hidden = nn.Sequential(nn.Linear(last, expert_num * expert_hidden_dim), nn.ELU())
+        self.experts_out = nn.Conv1d(expert_num * expert_hidden_dim, expert_num * latent_dim, kernel_size=1, groups=expert_num)
+        layers, last = [], gating_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(last, h), nn.ELU()]
+            last = h
+        layers += [nn.Linear(last, expert_num), nn.Softmax(dim=-1)]
+        self.gating_network = nn.Sequential(*layers)
+
+
+class ActorCriticMoENGCTS(ActorCriticMoECTS):
+    """ActorCriticMoENGCTS (rsl_rl/modules/actor_critic_moe_ng_cts.py:18-188): MoE-CTS whose experts see the observation history WITHOUT the
+    command ("goal") columns while the gate sees all of it.  Same kernels as ActorCriticMoECTS; the expert input is a column gather."""
+
+    def __init__(self, num_obs, num_critic_obs, num_actions, num_envs, history_length, obs_no_goal_mask, actor_hidden_dims=[512, 256, 128],
+                 critic_hidden_dims=[512, 256, 128], teacher_encoder_hidden_dims=[512, 256], student_encoder_hidden_dims=[512, 256],
+                 student_expert_num=8, activation='elu', init_noise_std=1.0, latent_dim=32, norm_type='l2norm', expert_hidden_dim=256, **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        if activation != 'elu' or norm_type != 'l2norm':
+            raise NotImplementedError("fused epilogues implement ELU / L2Norm (the go2_moe_ng_cts configuration)")
+        _CTSBase.__init__(self)
+        self.num_obs, self.num_critic_obs, self.num_actions = num_obs, num_critic_obs, num_actions
+        self.history_length, self.latent_dim, self.expert_num = history_length, latent_dim, student_expert_num
+        self.register_buffer("obs_no_goal_mask", torch.tensor(obs_no_goal_mask, dtype=torch.bool), persistent=False)
+        self.register_buffer("history", torch.zeros((num_envs, history_length, num_obs)), persistent=False)
+        n_ng = int(self.obs_no_goal_mask.sum())
+        self.t_dims = [num_critic_obs, *teacher_encoder_hidden_dims, latent_dim]
+        self.s_hidden = [*student_encoder_hidden_dims, expert_hidden_dim]
+        self.a_dims = [latent_dim + num_obs, *actor_hidden_dims, num_actions]
+        self.c_dims = [latent_dim + num_critic_obs, *critic_hidden_dims, 1]
+        self.teacher_encoder = nn.Sequential(*_seq_mlp(self.t_dims), L2Norm())
+        self.student_moe_encoder = _NGStudentParams(n_ng * history_length, num_obs * history_length, student_encoder_hidden_dims, student_expert_num,
+                                                    expert_hidden_dim, latent_dim)
+        self.actor = nn.Sequential(*_seq_mlp(self.a_dims))
+        self.critic = nn.Sequential(*_seq_mlp(self.c_dims))
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        self.student_prefix = "student_moe_encoder"
+        # columns of the flattened [history_length x num_obs] history the experts see
+        cols = torch.nonzero(self.obs_no_goal_mask).flatten()
+        self._expert_cols = torch.cat([cols + t * num_obs for t in range(history_length)])
+
+    def _build_engines(self, dev, max_rows, tr1, trt, trs):
+        self.teacher_engine = self._engine(_linear_names("teacher_encoder", len(self.t_dims) - 1), self.t_dims, max_rows, max(trt, trs))
+        self.actor_engine = self._engine(_linear_names("actor", len(self.a_dims) - 1), self.a_dims, max_rows, tr1, need_dx=True)
+        self.critic_engine = self._engine(_linear_names("critic", len(self.c_dims) - 1), self.c_dims, max_rows, tr1)
+        p, nh = "student_moe_encoder", len(self.s_hidden) - 1
+        names = {"backbone": _linear_names(p + ".experts_backbone", nh) + [p + ".experts_hidden.0"],
+                 "gate": _linear_names(p + ".gating_network", nh + 1), "experts": p + ".experts_out"}
+        self.student = _StudentMoE(self, p, self.num_obs * self.history_length, self.s_hidden, self.expert_num, self.latent_dim, max_rows, trs,
+                                   names=names, expert_cols=self._expert_cols)
+        self._common_buffers(dev, max_rows, max(trt, trs))

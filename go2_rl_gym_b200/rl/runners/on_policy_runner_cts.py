@@ -11,8 +11,8 @@ import torch
 import yaml
 
 from .. import _ops
-from ..algorithms import CTS, MoECTS
-from ..modules import ActorCriticCTS, ActorCriticMoECTS
+from ..algorithms import CTS, MoECTS, MoENGCTS
+from ..modules import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS
 from ...utils.cfg_dict import class_to_dict
 from .on_policy_runner import SummaryWriter
 
@@ -24,9 +24,10 @@ class OnPolicyRunnerCTS:
         history_length = train_cfg["history_length"]
         self.history_length = history_length
         num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
-        model_class = {"ActorCriticCTS": ActorCriticCTS, "ActorCriticMoECTS": ActorCriticMoECTS}[self.cfg["policy_class_name"]]
+        model_class = {"ActorCriticCTS": ActorCriticCTS, "ActorCriticMoECTS": ActorCriticMoECTS,
+                       "ActorCriticMoENGCTS": ActorCriticMoENGCTS}[self.cfg["policy_class_name"]]
         model = model_class(self.env.num_obs, num_critic_obs, self.env.num_actions, self.env.num_envs, history_length, **self.policy_cfg)
-        alg_class = {"CTS": CTS, "MoECTS": MoECTS}[self.cfg["algorithm_class_name"]]
+        alg_class = {"CTS": CTS, "MoECTS": MoECTS, "MoENGCTS": MoENGCTS}[self.cfg["algorithm_class_name"]]
         off = env._A.env_offset if hasattr(env, "_A") else 0
         self.alg = alg_class(model, self.env.num_envs, history_length, device=self.device, seed=train_cfg.get("seed", 0), env_offset=off, **self.alg_cfg)
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]

@@ -4,6 +4,7 @@ actor, with the call signatures the deployment loops expect (deploy/deploy_mujoc
     ActorCritic        forward(obs[1,45]) -> action[1,12]                                  (exporter.py:127-128)
     ActorCriticCTS     forward(obs)       -> (action, (None, latent[1,32]))                (exporter.py:130-135)
     ActorCriticMoECTS  forward(obs)       -> (action, (gate weights[1,8], latent[1,32]))   (exporter.py:145-150)
+    ActorCriticMoENGCTS forward(obs)      -> (action, (gate weights[1,8], latent[1,32]))   (exporter.py:137-143; experts on the no-goal history)
 
 The CTS variants keep the rolling observation history ([1, H, 45], shift-append) inside the module and expose `reset()`.
 The exported module is plain PyTorch built from the policy's state_dict (inference on the robot / in MuJoCo has no B200);
@@ -98,6 +99,41 @@ class _MoECTSPolicy(nn.Module):
         self.history = torch.zeros_like(self.history)
 
 
+class _MoENGCTSPolicy(nn.Module):
+    """MoE student whose experts see the history without its command columns (exporter.py:137-143, actor_critic_moe_ng_cts.py:185-230)."""
+
+    def __init__(self, sd, history_length, num_obs, obs_no_goal_mask, normalizer=None):
+        super().__init__()
+        p = "student_moe_encoder."
+        self.backbone = _mlp_from(sd, p + "experts_backbone", last_activation=True)
+        self.hidden = _mlp_from(sd, p + "experts_hidden", last_activation=True)
+        self.gate = _mlp_from(sd, p + "gating_network")
+        self.expert_num = int(self.gate[len(self.gate) - 1].out_features)
+        w = sd[p + "experts_out.weight"].detach().cpu()              # Conv1d(E*H -> E*D, k=1, groups=E): [E*D, H, 1]
+        self.out_dim = w.shape[0] // self.expert_num
+        self.register_buffer("expert_w", w.reshape(self.expert_num, self.out_dim, w.shape[1]).clone())
+        self.register_buffer("expert_b", sd[p + "experts_out.bias"].detach().cpu().reshape(self.expert_num, self.out_dim).clone())
+        self.actor = _mlp_from(sd, "actor")
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+        self.history_length = int(history_length)
+        self.register_buffer("obs_no_goal_mask", torch.as_tensor(obs_no_goal_mask, dtype=torch.bool).cpu().clone())
+        self.history = torch.zeros(1, history_length, num_obs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        x = self.normalizer(x)
+        self.history = torch.cat([self.history[:, 1:], x.unsqueeze(1)], dim=1)
+        no_goal = self.history.reshape(1, self.history_length, -1)[:, :, self.obs_no_goal_mask].reshape(1, -1)
+        weights = torch.softmax(self.gate(self.history.flatten(1)), dim=-1)
+        feat = self.hidden(self.backbone(no_goal)).reshape(-1, self.expert_num, self.expert_w.shape[2])
+        outs = torch.einsum("beh,edh->bed", feat, self.expert_w) + self.expert_b
+        latent = F.normalize(torch.sum(weights.unsqueeze(-1) * outs, dim=1), p=2.0, dim=-1)
+        return self.actor(torch.cat([latent, x], dim=1)), (weights, latent)
+
+    @torch.jit.export
+    def reset(self):
+        self.history = torch.zeros_like(self.history)
+
+
 def build_export_module(policy, normalizer=None):
     """The plain-PyTorch inference module of `policy` (ActorCritic / ActorCriticCTS / ActorCriticMoECTS, or any module whose state
     dict has the reference's key layout, e.g. one loaded from a reference checkpoint)."""
@@ -105,6 +141,8 @@ def build_export_module(policy, normalizer=None):
     if getattr(policy, "is_recurrent", False):
         raise NotImplementedError("recurrent policies are not part of the go2 tasks (SURVEY section 2)")
     hist = getattr(policy, "history", None)
+    if "student_moe_encoder.experts_out.weight" in sd:
+        return _MoENGCTSPolicy(sd, hist.shape[1], hist.shape[2], policy.obs_no_goal_mask, normalizer)
     if any(k.startswith("student_moe_encoder.") for k in sd):
         E = sd["student_moe_encoder.moe.gating_network.0.network.%d.weight" % max(
             int(k.split(".")[-2]) for k in sd if k.startswith("student_moe_encoder.moe.gating_network.0.network.") and k.endswith(".weight"))].shape[0]

@@ -8,3 +8,7 @@ ALG = dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, ent
 POLICY_CTS = dict(actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16], teacher_encoder_hidden_dims=[64, 32],
                   student_encoder_hidden_dims=[64, 32], activation="elu", init_noise_std=1.0, latent_dim=32, norm_type="l2norm")
 ALG_CTS = {k: v for k, v in ALG.items() if k != "load_balance_coef"}
+# MoE-CTS with no-goal experts (LeggedRobotCfgMoENGCTS, legged_robot_config.py:361-371; GO2CfgMoENGCTS go2_config.py:231-243)
+NO_GOAL_MASK = [True] * 6 + [False] * 3 + [True] * 36
+POLICY_NG = dict(obs_no_goal_mask=NO_GOAL_MASK, actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16], teacher_encoder_hidden_dims=[64, 32],
+                 student_encoder_hidden_dims=[64, 32], student_expert_num=8, activation="elu", init_noise_std=1.0, latent_dim=32, norm_type="l2norm")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate tests/golden/rl_moe_cts.npz from the REFERENCE's rsl_rl (ActorCriticMoECTS + MoECTS + RolloutStorageCTS, imported
 unmodified from /root/reference/rsl_rl): a seeded synthetic rollout through act / process_env_step / compute_returns and one
-update() with injected teacher / student permutations.  `--variant cts` does the same for ActorCriticCTS + CTS (-> rl_cts.npz; the
+update() with injected teacher / student permutations.  `--variant moe_ng_cts` does the same for ActorCriticMoENGCTS + MoENGCTS (-> rl_moe_ng_cts.npz), `--variant cts` for ActorCriticCTS + CTS (-> rl_cts.npz; the
 reference allocates that module's history on 'cuda' at construction, actor_critic_cts.py:48, so torch.zeros is wrapped to drop the
 device while the module is built).  Build container only.  Usage (from /tmp): python /root/repo/tests/golden/make_golden_cts.py [--variant cts]"""
 import os
@@ -17,7 +17,7 @@ sys.path[:0] = ["/root/reference/rsl_rl", HERE]
 from rsl_rl.algorithms.moe_cts import MoECTS  # noqa: E402
 from rsl_rl.modules.actor_critic_moe_cts import ActorCriticMoECTS  # noqa: E402
 import rsl_rl.storage.rollout_storage_cts as RS  # noqa: E402
-from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS  # noqa: E402
+from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS, POLICY_NG  # noqa: E402
 
 
 def main():
@@ -26,6 +26,9 @@ def main():
     N, T, H = 32, (24 if variant == "moe_cts" else 12), 5
     if variant == "moe_cts":
         model = ActorCriticMoECTS(45, 263, 12, N, H, **POLICY)
+    elif variant == "moe_ng_cts":     # experts on the history without its command columns (actor_critic_moe_ng_cts.py)
+        from rsl_rl.modules.actor_critic_moe_ng_cts import ActorCriticMoENGCTS
+        model = ActorCriticMoENGCTS(45, 263, 12, N, H, **POLICY_NG)
     else:
         from rsl_rl.algorithms.cts import CTS
         import rsl_rl.modules.actor_critic_cts as ACC
@@ -36,7 +39,11 @@ def main():
         finally:
             ACC.torch.zeros = zeros
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    alg = MoECTS(model, N, H, device="cpu", **ALG) if variant == "moe_cts" else CTS(model, N, H, device="cpu", **ALG_CTS)
+    if variant == "moe_ng_cts":
+        from rsl_rl.algorithms.moe_ng_cts import MoENGCTS
+        alg = MoENGCTS(model, N, H, device="cpu", **ALG)
+    else:
+        alg = MoECTS(model, N, H, device="cpu", **ALG) if variant == "moe_cts" else CTS(model, N, H, device="cpu", **ALG_CTS)
     alg.init_storage(N, T, [45], [263], [12])
     g = torch.Generator().manual_seed(1)
     obs = torch.randn(T + 1, N, 45, generator=g)

@@ -117,3 +117,49 @@ def test_cts_export_reproduces_shipped_policy(tmp_path):
         act, (none, latent) = m(x)
         assert none is None and latent.shape == (1, 32) and abs(float(latent.norm()) - 1.0) < 1e-5
         assert torch.allclose(act, ref, atol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "deploy/pre_train/go2/go2_moe_cts_137k_0.6739.pt")), reason="needs the reference's shipped policy")
+def test_moe_ng_cts_export_reproduces_shipped_policy(tmp_path):
+    """Known-answer test: the trained MoE policy the reference ships has the no-goal variant's parameter layout (experts_backbone /
+    experts_hidden / experts_out / gating_network) with experts that still read the full 225-wide history (its scripted forward ignores the
+    masked input).  Its weights loaded into THIS package's ActorCriticMoENGCTS (mask = keep every column) and re-exported reproduce the
+    original file's actions, gate weights and latents."""
+    shipped = torch.jit.load(os.path.join(REF, "deploy/pre_train/go2/go2_moe_cts_137k_0.6739.pt"), map_location="cpu")
+    from go2_rl_gym_b200.rl.modules import ActorCriticMoENGCTS
+    assert shipped.state_dict()["student_moe_encoder.experts_backbone.0.weight"].shape[1] == 45 * int(shipped.history_length)
+    mask = [True] * 45
+    pol = ActorCriticMoENGCTS(45, 263, 12, 1, int(shipped.history_length), mask)
+    sd = pol.state_dict()
+    sd.update({k: v.clone() for k, v in shipped.state_dict().items()})          # student encoder + actor; teacher / critic stay random (unused)
+    pol.load_state_dict(sd)
+    m = torch.jit.load(ex.export_policy_as_jit(pol, str(tmp_path)))
+    for x in _obs_seq(12, 7):
+        act_r, (w_r, lat_r) = shipped(x)
+        act, (w, lat) = m(x)
+        assert torch.allclose(act, act_r, atol=1e-5) and torch.allclose(w, w_r, atol=1e-6) and torch.allclose(lat, lat_r, atol=1e-6)
+
+
+@pytest.mark.skipif(not has_ref, reason="needs the reference tree (runs in the build container)")
+def test_moe_ng_cts_export_matches_reference_exporter(tmp_path):
+    """Reference ActorCriticMoENGCTS (GO2 no-goal mask) -> reference exporter vs the same weights in this package's module -> this exporter."""
+    sys.path.insert(0, os.path.join(REF, "rsl_rl"))
+    try:
+        from rsl_rl.modules.actor_critic_moe_ng_cts import ActorCriticMoENGCTS as RefNG
+    finally:
+        sys.path.pop(0)
+    spec = importlib.util.spec_from_file_location("ref_exporter", os.path.join(REF, "legged_gym", "utils", "exporter.py"))
+    ref_ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ex)
+    from go2_rl_gym_b200.rl.modules import ActorCriticMoENGCTS
+    mask = [True] * 6 + [False] * 3 + [True] * 36
+    torch.manual_seed(5)
+    ref = RefNG(45, 263, 12, 4, 5, mask)
+    mine = ActorCriticMoENGCTS(45, 263, 12, 4, 5, mask)
+    mine.load_state_dict(ref.state_dict())
+    ref_ex.export_policy_as_jit(ref, str(tmp_path / "ref"))
+    ex.export_policy_as_jit(mine, str(tmp_path / "mine"))
+    mr, mm = torch.jit.load(str(tmp_path / "ref" / "policy.pt")), torch.jit.load(str(tmp_path / "mine" / "policy.pt"))
+    for x in _obs_seq(9, 3):
+        (ar, (wr, lr)), (am, (wm, lm)) = mr(x), mm(x)
+        assert torch.allclose(ar, am, atol=1e-5) and torch.allclose(wr, wm, atol=1e-6) and torch.allclose(lr, lm, atol=1e-6)

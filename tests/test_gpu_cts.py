@@ -8,7 +8,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ZS = {v: np.load(os.path.join(G, f"rl_{v}.npz")) for v in ("moe_cts", "cts")}
+ZS = {v: np.load(os.path.join(G, f"rl_{v}.npz")) for v in ("moe_cts", "cts", "moe_ng_cts")}
 Z = None
 
 
@@ -20,18 +20,23 @@ def _make(gemm, monkeypatch, variant="moe_cts"):
     global Z
     Z = ZS[variant]
     monkeypatch.setenv("GO2_GEMM", gemm)
-    from golden.cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS
-    from go2_rl_gym_b200.rl.algorithms import CTS, MoECTS
-    from go2_rl_gym_b200.rl.modules import ActorCriticCTS, ActorCriticMoECTS
+    from golden.cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS, POLICY_NG
+    from go2_rl_gym_b200.rl.algorithms import CTS, MoECTS, MoENGCTS
+    from go2_rl_gym_b200.rl.modules import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS
     T, N = Z["st_rewards"].shape[:2]
-    model = ActorCriticMoECTS(45, 263, 12, N, 5, **POLICY) if variant == "moe_cts" else ActorCriticCTS(45, 263, 12, N, 5, **POLICY_CTS)
+    if variant == "moe_cts":
+        model = ActorCriticMoECTS(45, 263, 12, N, 5, **POLICY)
+    elif variant == "moe_ng_cts":
+        model = ActorCriticMoENGCTS(45, 263, 12, N, 5, **POLICY_NG)
+    else:
+        model = ActorCriticCTS(45, 263, 12, N, 5, **POLICY_CTS)
     model.load_state_dict({k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")})
-    alg = MoECTS(model, N, 5, device="cuda", **ALG) if variant == "moe_cts" else CTS(model, N, 5, device="cuda", **ALG_CTS)
+    alg = {"moe_cts": MoECTS, "moe_ng_cts": MoENGCTS, "cts": CTS}[variant](model, N, 5, device="cuda", **(ALG_CTS if variant == "cts" else ALG))
     alg.init_storage(N, T, [45], [263], [12])
     return model, alg, T, N
 
 
-@pytest.mark.parametrize("variant", ["moe_cts", "cts"])
+@pytest.mark.parametrize("variant", ["moe_cts", "cts", "moe_ng_cts"])
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
 def test_cts_act_matches_reference(gemm, variant, monkeypatch):
     model, alg, T, N = _make(gemm, monkeypatch, variant)
@@ -48,7 +53,7 @@ def test_cts_act_matches_reference(gemm, variant, monkeypatch):
     assert torch.equal(st.dones[0].cpu().squeeze(-1).bool(), torch.cat([torch.from_numpy(Z["in_dones"][0])[ti], torch.from_numpy(Z["in_dones"][0])[si]]))
 
 
-@pytest.mark.parametrize("variant", ["moe_cts", "cts"])
+@pytest.mark.parametrize("variant", ["moe_cts", "cts", "moe_ng_cts"])
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
 def test_cts_update_matches_reference(gemm, variant, monkeypatch):
     """Both passes of MoECTS.update (moe_cts.py:104-234) / CTS.update (cts.py:167-285).  simt: parameters to 1e-3 rel / 3e-5 abs.  tc: relative error of the whole
@@ -78,7 +83,7 @@ def test_cts_update_matches_reference(gemm, variant, monkeypatch):
     assert rel < (2e-3 if gemm == "simt" else 5e-2)
 
 
-@pytest.mark.parametrize("task", ["go2_moe_cts", "go2_cts"])
+@pytest.mark.parametrize("task", ["go2_moe_cts", "go2_cts", "go2_moe_ng_cts"])
 def test_cts_runner_two_iterations(task, tmp_path):
     from go2_rl_gym_b200.envs import task_registry
     from go2_rl_gym_b200.utils import get_args
@@ -88,7 +93,8 @@ def test_cts_runner_two_iterations(task, tmp_path):
     runner.learn(2, init_at_random_ep_len=True)
     sd = torch.load(os.path.join(runner.log_dir, "model_2.pt"), weights_only=False)
     assert {"model_state_dict", "optimizer1_state_dict", "optimizer2_state_dict", "iter", "infos"} == set(sd)
-    key = "student_moe_encoder.moe.experts.experts.weight" if task == "go2_moe_cts" else "student_encoder.0.weight"
+    key = {"go2_moe_cts": "student_moe_encoder.moe.experts.experts.weight", "go2_cts": "student_encoder.0.weight",
+           "go2_moe_ng_cts": "student_moe_encoder.experts_out.weight"}[task]
     assert key in sd["model_state_dict"]
     # resume: the saved optimiser / model state loads back into a fresh runner
     runner2, _ = task_registry.make_alg_runner(env, task, args, log_root=None)

@@ -25,3 +25,14 @@ def test_actor_critic_moe_cts_keys():
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in ref.items()}
     full = ActorCriticMoECTS(45, 263, 12, 32, 5)
     assert sum(p.numel() for p in full.parameters()) == 1884609
+
+
+def test_actor_critic_moe_ng_cts_keys():
+    from go2_rl_gym_b200.rl.modules import ActorCriticMoENGCTS
+    from golden.cts_cfg import POLICY_NG
+    ref = _keys(np.load(os.path.join(G, "rl_moe_ng_cts.npz")))
+    m = ActorCriticMoENGCTS(45, 263, 12, 32, 5, **POLICY_NG)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in ref.items()}
+    assert [k for k, _ in m.named_parameters()] == [k[4:] for k in np.load(os.path.join(G, "rl_moe_ng_cts.npz")).files if k.startswith("sd0_")]
+    full = ActorCriticMoENGCTS(45, 263, 12, 32, 5, POLICY_NG["obs_no_goal_mask"])
+    assert sum(p.numel() for p in full.parameters()) == 1876929          # the reference's ActorCriticMoENGCTS at GO2CfgMoENGCTS widths
