@@ -9,7 +9,8 @@ actor, with the call signatures the deployment loops expect (deploy/deploy_mujoc
 The CTS variants keep the rolling observation history ([1, H, 45], shift-append) inside the module and expose `reset()`.
 The exported module is plain PyTorch built from the policy's state_dict (inference on the robot / in MuJoCo has no B200);
 it is rebuilt from weights rather than deep-copied because this package's modules evaluate through the CUDA library.
-ONNX export and the recurrent / ablation variants are out of scope."""
+The three remaining ablation variants (MCP / AC-MoE / Dual-MoE) are exported from any module or checkpoint with the reference's key layout
+(their training path is not on the CUDA kernels yet); ONNX export and the recurrent policy are out of scope."""
 import os
 from typing import Optional, Tuple
 
@@ -134,6 +135,111 @@ class _MoENGCTSPolicy(nn.Module):
         self.history = torch.zeros_like(self.history)
 
 
+class _MoEBlock(nn.Module):
+    """modules/utils.py:96-126 (`MoE`): shared backbone -> E block-diagonal experts (grouped 1x1 conv), softmax gate, weighted sum."""
+
+    def __init__(self, sd, prefix):
+        super().__init__()
+        self.backbone = _mlp_from(sd, prefix + ".experts.backbone.network", last_activation=True)
+        self.gate = _mlp_from(sd, prefix + ".gating_network.0.network")
+        self.expert_num = int(self.gate[len(self.gate) - 1].out_features)
+        w = sd[prefix + ".experts.experts.weight"].detach().cpu()
+        self.out_dim = w.shape[0] // self.expert_num
+        self.register_buffer("expert_w", w.reshape(self.expert_num, self.out_dim, w.shape[1]).clone())
+        self.register_buffer("expert_b", sd[prefix + ".experts.experts.bias"].detach().cpu().reshape(self.expert_num, self.out_dim).clone())
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        weights = torch.softmax(self.gate(x), dim=-1)
+        feat = self.backbone(x).reshape(-1, self.expert_num, self.expert_w.shape[2])
+        outs = torch.einsum("beh,edh->bed", feat, self.expert_w) + self.expert_b
+        return torch.sum(weights.unsqueeze(-1) * outs, dim=1), weights
+
+
+class _ACMoECTSPolicy(nn.Module):
+    """MLP student encoder + MoE actor (exporter.py:162-168, actor_critic_ac_moe_cts.py:127-133)."""
+
+    def __init__(self, sd, history_length, num_obs, normalizer=None):
+        super().__init__()
+        self.student_encoder = _mlp_from(sd, "student_encoder.0.network")
+        self.actor = _MoEBlock(sd, "actor_moe")
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+        self.history = torch.zeros(1, history_length, num_obs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        x = self.normalizer(x)
+        self.history = torch.cat([self.history[:, 1:], x.unsqueeze(1)], dim=1)
+        latent = F.normalize(self.student_encoder(self.history.flatten(1)), p=2.0, dim=-1)
+        mean, weights = self.actor(torch.cat([latent, x], dim=1))
+        return mean, (weights, latent)
+
+    @torch.jit.export
+    def reset(self):
+        self.history = torch.zeros_like(self.history)
+
+
+class _DualMoECTSPolicy(nn.Module):
+    """MoE student encoder + MoE actor (exporter.py:170-176, actor_critic_dual_moe_cts.py)."""
+
+    def __init__(self, sd, history_length, num_obs, normalizer=None):
+        super().__init__()
+        self.student = _MoEBlock(sd, "student_moe_encoder.moe")
+        self.actor = _MoEBlock(sd, "actor_moe")
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+        self.history = torch.zeros(1, history_length, num_obs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        x = self.normalizer(x)
+        self.history = torch.cat([self.history[:, 1:], x.unsqueeze(1)], dim=1)
+        lat, student_weights = self.student(self.history.flatten(1))
+        latent = F.normalize(lat, p=2.0, dim=-1)
+        mean, actor_weights = self.actor(torch.cat([latent, x], dim=1))
+        return mean, (student_weights, actor_weights, latent)
+
+    @torch.jit.export
+    def reset(self):
+        self.history = torch.zeros_like(self.history)
+
+
+class _MCPCTSPolicy(nn.Module):
+    """MLP student encoder + multiplicative-composition actor (exporter.py:152-160, actor_critic_mcp_cts.py:172-247): E Gaussian primitives
+    on [latent | obs without commands], sigmoid gate on [latent | obs]; the composite mean is the precision-weighted mean of the primitives."""
+
+    def __init__(self, sd, history_length, num_obs, obs_no_goal_mask, normalizer=None):
+        super().__init__()
+        self.student_encoder = _mlp_from(sd, "student_encoder")
+        p = "actor_mcp."
+        self.gate = _mlp_from(sd, p + "gating_network")
+        self.backbone = _mlp_from(sd, p + "experts_backbone", last_activation=True)
+        self.hidden = _mlp_from(sd, p + "experts_hidden", last_activation=True)
+        self.expert_num = int(self.gate[len(self.gate) - 1].out_features)
+        w = sd[p + "experts_out.weight"].detach().cpu()              # [E * 2A, H, 1]
+        self.out_dim = w.shape[0] // self.expert_num                # 2 * actions: mean | log std
+        self.register_buffer("expert_w", w.reshape(self.expert_num, self.out_dim, w.shape[1]).clone())
+        self.register_buffer("expert_b", sd[p + "experts_out.bias"].detach().cpu().reshape(self.expert_num, self.out_dim).clone())
+        self.normalizer = normalizer if normalizer is not None else nn.Identity()
+        self.register_buffer("obs_no_goal_mask", torch.as_tensor(obs_no_goal_mask, dtype=torch.bool).cpu().clone())
+        self.history = torch.zeros(1, history_length, num_obs)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        x = self.normalizer(x)
+        self.history = torch.cat([self.history[:, 1:], x.unsqueeze(1)], dim=1)
+        latent = F.normalize(self.student_encoder(self.history.flatten(1)), p=2.0, dim=-1)
+        full = torch.cat([latent, x], dim=1)
+        no_goal = torch.cat([latent, x[:, self.obs_no_goal_mask]], dim=1)
+        weights = torch.sigmoid(self.gate(full)).unsqueeze(-1)                                   # [B, E, 1]
+        feat = self.hidden(self.backbone(no_goal)).reshape(-1, self.expert_num, self.expert_w.shape[2])
+        out = torch.einsum("beh,edh->bed", feat, self.expert_w) + self.expert_b                  # [B, E, 2A]
+        mu, log_std = torch.chunk(out, 2, dim=-1)
+        var = torch.exp(2 * torch.clamp(log_std, -5.0, 2.0)) + 1e-9
+        var_total = 1.0 / (torch.sum(weights / var, dim=1) + 1e-9)
+        mean = var_total * torch.sum(weights * mu / var, dim=1)
+        return mean, (weights.squeeze(-1), latent)
+
+    @torch.jit.export
+    def reset(self):
+        self.history = torch.zeros_like(self.history)
+
+
 def build_export_module(policy, normalizer=None):
     """The plain-PyTorch inference module of `policy` (ActorCritic / ActorCriticCTS / ActorCriticMoECTS, or any module whose state
     dict has the reference's key layout, e.g. one loaded from a reference checkpoint)."""
@@ -141,6 +247,12 @@ def build_export_module(policy, normalizer=None):
     if getattr(policy, "is_recurrent", False):
         raise NotImplementedError("recurrent policies are not part of the go2 tasks (SURVEY section 2)")
     hist = getattr(policy, "history", None)
+    if any(k.startswith("actor_mcp.") for k in sd):
+        return _MCPCTSPolicy(sd, hist.shape[1], hist.shape[2], policy.obs_no_goal_mask, normalizer)
+    if any(k.startswith("actor_moe.") for k in sd):
+        if any(k.startswith("student_moe_encoder.") for k in sd):
+            return _DualMoECTSPolicy(sd, hist.shape[1], hist.shape[2], normalizer)
+        return _ACMoECTSPolicy(sd, hist.shape[1], hist.shape[2], normalizer)
     if "student_moe_encoder.experts_out.weight" in sd:
         return _MoENGCTSPolicy(sd, hist.shape[1], hist.shape[2], policy.obs_no_goal_mask, normalizer)
     if any(k.startswith("student_moe_encoder.") for k in sd):

@@ -163,3 +163,38 @@ def test_moe_ng_cts_export_matches_reference_exporter(tmp_path):
     for x in _obs_seq(9, 3):
         (ar, (wr, lr)), (am, (wm, lm)) = mr(x), mm(x)
         assert torch.allclose(ar, am, atol=1e-5) and torch.allclose(wr, wm, atol=1e-6) and torch.allclose(lr, lm, atol=1e-6)
+
+
+@pytest.mark.skipif(not has_ref, reason="needs the reference tree (runs in the build container)")
+@pytest.mark.parametrize("variant", ["mcp_cts", "ac_moe_cts", "dual_moe_cts"])
+def test_ablation_variants_export_matches_reference_exporter(variant, tmp_path):
+    """The three CTS ablation variants: the reference's module -> the reference's exporter vs THIS exporter on the same module (it only reads
+    the state dict, the history shape and the no-goal mask)."""
+    import contextlib, io
+    sys.path.insert(0, os.path.join(REF, "rsl_rl"))
+    try:
+        from rsl_rl.modules.actor_critic_mcp_cts import ActorCriticMCPCTS
+        from rsl_rl.modules.actor_critic_ac_moe_cts import ActorCriticACMoECTS
+        from rsl_rl.modules.actor_critic_dual_moe_cts import ActorCriticDualMoECTS
+    finally:
+        sys.path.pop(0)
+    spec = importlib.util.spec_from_file_location("ref_exporter", os.path.join(REF, "legged_gym", "utils", "exporter.py"))
+    ref_ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ex)
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if variant == "mcp_cts":
+            ref = ActorCriticMCPCTS(45, 263, 12, 4, 5, obs_no_goal_mask=[True] * 6 + [False] * 3 + [True] * 36)
+        elif variant == "ac_moe_cts":
+            ref = ActorCriticACMoECTS(45, 263, 12, 4, 5)
+        else:
+            ref = ActorCriticDualMoECTS(45, 263, 12, 4, 5)
+    ref_ex.export_policy_as_jit(ref, str(tmp_path / "ref"))
+    ex.export_policy_as_jit(ref, str(tmp_path / "mine"))
+    mr, mm = torch.jit.load(str(tmp_path / "ref" / "policy.pt")), torch.jit.load(str(tmp_path / "mine" / "policy.pt"))
+    for x in _obs_seq(9, 6):
+        (ar, extra_r), (am, extra_m) = mr(x), mm(x)
+        assert torch.allclose(ar, am, atol=1e-5), variant
+        assert len(extra_r) == len(extra_m)
+        for a, b in zip(extra_r, extra_m):
+            assert torch.allclose(a, b, atol=1e-5), variant
