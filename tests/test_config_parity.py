@@ -1,0 +1,60 @@
+"""Config layer parity: the nested-class config trees of every registered go2 task (env + train cfgs, flattened
+by class_to_dict) must equal the REFERENCE's own trees, imported from /root/reference through the isaacgym stand-in.  Runs in the build
+container only (the reference tree does not travel); in a subprocess because the reference package is also called `legged_gym`."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys, json, io, contextlib
+sys.path[:0] = [ROOT + "/tests/ref_stub", REF, REF + "/rsl_rl", ROOT]
+with contextlib.redirect_stdout(io.StringIO()):
+    import legged_gym.envs.go2.go2_config as ref
+    from legged_gym.utils.helpers import class_to_dict as ref_c2d
+    import importlib
+    mine = importlib.import_module("go2_rl_gym_b200.envs.go2.go2_config")
+    from go2_rl_gym_b200.utils.cfg_dict import class_to_dict as c2d
+assert "reference" in ref.__file__
+def diff(a, b, path=""):
+    out = []
+    for k in sorted(set(a) | set(b)):
+        if k not in a: out.append([path + k, "only here", repr(b[k])])
+        elif k not in b: out.append([path + k, "only in reference", repr(a[k])])
+        elif isinstance(a[k], dict) and isinstance(b[k], dict): out += diff(a[k], b[k], path + k + ".")
+        elif a[k] != b[k]: out.append([path + k, repr(a[k]), repr(b[k])])
+    return out
+res = {}
+for name in ("GO2Cfg", "GO2CfgPPO", "GO2CfgCTS", "GO2CfgMoECTS", "GO2CfgMoENGCTS", "GO2CfgMCPCTS", "GO2CfgACMoECTS", "GO2CfgDualMoECTS"):
+    res[name] = diff(ref_c2d(getattr(ref, name)()), c2d(getattr(mine, name)()))
+print("RESULT" + json.dumps(res))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "legged_gym")), reason="needs the reference tree (runs in the build container)")
+def test_config_trees_equal_the_reference():
+    code = SCRIPT.replace("ROOT", repr(ROOT)).replace("REF", repr(REF))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    assert line, out.stderr[-2000:]
+    res = json.loads(line[0][len("RESULT"):])
+    # the only additions allowed: this package's own physics-solver block (the reference delegates those to PhysX)
+    for name, d in res.items():
+        d = [x for x in d if not x[0].startswith("sim.b200")]
+        assert not d, (name, d[:10])
+    assert any(x[0].startswith("sim.b200") for x in res["GO2Cfg"])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "legged_gym")), reason="needs the reference tree (runs in the build container)")
+def test_registered_tasks_are_a_subset_of_the_reference():
+    src = open(os.path.join(REF, "legged_gym", "envs", "__init__.py")).read()
+    import re
+    ref_tasks = set(re.findall(r'task_registry\.register\(\s*"([a-z0-9_]+)"', src))
+    from go2_rl_gym_b200.envs import task_registry
+    mine = set(task_registry.task_classes)
+    assert mine <= ref_tasks and {"go2", "go2_cts", "go2_moe_cts", "go2_moe_ng_cts"} <= mine, (mine, ref_tasks)

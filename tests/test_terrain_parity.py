@@ -1,0 +1,63 @@
+"""Terrain layout parity: the REFERENCE's `legged_gym.utils.terrain.Terrain` (imported from /root/reference; its
+isaacgym.terrain_utils generators are absent from the tree and are served by the stand-in in tests/ref_stub, i.e. by this package's restated
+generators) and this package's Terrain must build the same 10 x 20 curriculum heightfield, env origins and column -> terrain-id map from
+the same numpy seed.  That pins everything terrain.py itself does (difficulty / proportion logic, tile placement, borders, origin heights);
+the generators' own formulas stay 'as documented for Isaac Gym' (unpinned).  Build container only, in a subprocess."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys, json, io, contextlib
+import numpy as np
+sys.path[:0] = [ROOT + "/tests/ref_stub", REF, REF + "/rsl_rl", ROOT]
+with contextlib.redirect_stdout(io.StringIO()):
+    from legged_gym.envs.go2.go2_config import GO2Cfg as RefCfg          # (envs first: the reference's utils <-> envs import cycle)
+    from legged_gym.utils.terrain import Terrain as RefTerrain
+    import importlib
+    mine_t = importlib.import_module("go2_rl_gym_b200.utils.terrain")
+    MyCfg = importlib.import_module("go2_rl_gym_b200.envs.go2.go2_config").GO2Cfg
+out = {}
+for mode in ("curriculum", "random"):
+    rc, mc = RefCfg().terrain, MyCfg().terrain
+    for c in (rc, mc):
+        c.mesh_type = "heightfield"
+        c.curriculum = mode == "curriculum"
+        if mode == "random":
+            c.num_rows, c.num_cols = 4, 5
+    np.random.seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = RefTerrain(rc, 64)
+    m = mine_t.Terrain(mc, 64, seed=7)
+    out[mode] = {"shape": [list(r.height_field_raw.shape), list(m.height_field_raw.shape)],
+                 "hf_equal": bool(np.array_equal(r.height_field_raw, m.height_field_raw)),
+                 "hf_maxdiff": int(np.abs(r.height_field_raw.astype(np.int64) - m.height_field_raw.astype(np.int64)).max()),
+                 "origins_equal": bool(np.array_equal(np.asarray(r.env_origins), np.asarray(m.env_origins))),
+                 "nonflat": int((m.height_field_raw != 0).sum())}
+    if mode == "curriculum":
+        out[mode]["cols2id"] = [list(map(int, getattr(r, "cols2id", []))), list(map(int, m.cols2id))]
+        out[mode]["name2cols"] = [{k: sorted(map(int, v)) for k, v in getattr(r, "name2cols", {}).items()}, {k: sorted(map(int, v)) for k, v in m.name2cols.items()}]
+print("RESULT" + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "legged_gym")), reason="needs the reference tree (runs in the build container)")
+def test_terrain_grid_equals_the_reference():
+    code = SCRIPT.replace("ROOT", repr(ROOT)).replace("REF", repr(REF))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    assert line, out.stderr[-3000:]
+    res = json.loads(line[0][len("RESULT"):])
+    for mode, r in res.items():
+        assert r["shape"][0] == r["shape"][1], (mode, r["shape"])
+        assert r["hf_equal"] and r["origins_equal"], (mode, r)
+        assert r["nonflat"] > 10000, (mode, r["nonflat"])
+    c = res["curriculum"]
+    assert c["cols2id"][0] == c["cols2id"][1] and c["name2cols"][0] == c["name2cols"][1], c
+    assert c["shape"][1] == [1345, 2195]          # 10 x 20 tiles of 8 m at 0.1 m, 0.5 m spacing, 25 m border
