@@ -11,7 +11,7 @@ post-physics restatement and compares: this pins PD torques, action delay, prelu
 termination, all 14 rewards, reset / terrain curriculum, pushes, both observation vectors and their ordering quirks
 against the reference's own code.  (gym.simulate itself — PhysX — stays unpinned.)
 
-Usage: python tests/golden/make_golden_env.py   (writes tests/golden/env_rough.npz, env_plane.npz)
+Usage: python tests/golden/make_golden_env.py   (writes tests/golden/env_rough.npz, env_plane.npz, env_cmdcur.npz)
 """
 import os
 import sys
@@ -22,7 +22,8 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests", "ref_stub"), "/root/reference", "/root/reference/rsl_rl"]
+# the reference tree first: the repo root carries import shims that are also called legged_gym / rsl_rl
+sys.path[:0] = [os.path.join(ROOT, "tests", "ref_stub"), "/root/reference", "/root/reference/rsl_rl", ROOT]
 
 from go2_rl_gym_b200 import _abi  # noqa: E402
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays  # noqa: E402
@@ -422,3 +423,5 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700):
 if __name__ == "__main__":
     make_case("rough", plane=False)
     make_case("plane", plane=True, N=32, K=4)
+    # crosses learning iteration 20 000: the command-range curriculum widens the ranges (go2_config.py:112-124, legged_robot.py:433-446)
+    make_case("cmdcur", plane=False, N=32, K=5, seed=9, start_counter=24 * 20000 - 33)

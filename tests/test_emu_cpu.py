@@ -70,3 +70,19 @@ def test_packed_map_is_bit_identical_to_warp_per_env():
                 continue        # scratch of the cross-env logging sums (summation order differs)
             assert torch.equal(v, A1.tensors[k]) or (torch.isnan(v) == torch.isnan(A1.tensors[k])).all() and torch.equal(torch.nan_to_num(v), torch.nan_to_num(A1.tensors[k])), (step, k)
     assert n_reset > 5
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_emulated_kernel_crosses_command_range_curriculum(packed):
+    """Fixture made by the reference across learning iteration 20 000 (the command-range curriculum widens lin_vel_x / ang_vel_yaw,
+    legged_robot.py:433-446): the kernel source must draw the same commands, timers and flags at every step of the window."""
+    z, A = load_case("cmdcur")
+    env = EmuEnv(A, packed=packed)
+    env.common_step_counter = int(z["meta_start_counter"])
+    acts = torch.from_numpy(z["actions"])
+    assert env.common_step_counter < 24 * 20000 <= env.common_step_counter + int(z["meta_K"])
+    for i in range(int(z["meta_K"])):
+        env.step(acts[i])
+        bad = compare_step(z, i, A.tensors, keys=("commands", "commands_resampling_step", "last_is_limit_vel", "reset_buf", "time_out_buf",
+                                                  "episode_length_buf", "terrain_levels", "motor_strengths", "p_gains_multiplier"))
+        assert not bad, (i, bad)
