@@ -86,3 +86,58 @@ def test_emulated_kernel_crosses_command_range_curriculum(packed):
         bad = compare_step(z, i, A.tensors, keys=("commands", "commands_resampling_step", "last_is_limit_vel", "reset_buf", "time_out_buf",
                                                   "episode_length_buf", "terrain_levels", "motor_strengths", "p_gains_multiplier"))
         assert not bad, (i, bad)
+
+
+# ---- the physics of the kernel's own source against mechanics (same checks as tests/test_oracle_physics.py makes on the oracle) ----------
+def _emu_env(num_envs=2, packed=False, **dr_off):
+    cfg = GO2Cfg(); cfg.terrain.mesh_type = "plane"; cfg.env.num_envs = num_envs; cfg.domain_rand.push_robots = False
+    for k in ("randomize_motor_strength", "randomize_pd_gains", "randomize_motor_zero_offset", "randomize_friction"):
+        setattr(cfg.domain_rand, k, False)
+    A = EnvArrays(cfg, "cpu", seed=3)
+    env = EmuEnv(A, packed=packed)
+    env.reset_all()
+    return A, env
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_emulated_kernel_free_flight_momentum(packed):
+    """No contacts, no torques: linear momentum changes by -M g t, horizontal and angular (about the COM) momentum are conserved to the
+    first-order accuracy of the 5 ms semi-implicit step (fp32 kernel source; the fp64 oracle test shows the error is O(dt))."""
+    from physics_checks import mechanics
+    A, env = _emu_env(packed=packed)
+    T = A.tensors
+    T["root_states"][:, 2] = 10.0
+    T["root_states"][:, 7:13] = torch.tensor([0.3, -0.2, 0.5, 1.0, -2.0, 1.5])
+    T["dof_vel"][:] = torch.linspace(-3, 3, 12)
+    mech = lambda: mechanics(A.model_json, T["body_inertia"][0].numpy(), T["root_states"][0].numpy(), T["dof_pos"][0].numpy().astype(np.float64),
+                             T["dof_vel"][0].numpy().astype(np.float64))
+    M, c0, KE0, PE0, P0, L0 = mech()
+    env.substeps(torch.zeros(2, 12), 20)
+    M, c, KE, PE, P, L = mech()
+    assert abs(P[2] - (P0[2] - M * 9.81 * 0.1)) < 2e-2
+    assert np.linalg.norm(P[:2] - P0[:2]) < 2e-2
+    assert np.linalg.norm((L - np.cross(c, P)) - (L0 - np.cross(c0, P0))) < 2e-2
+
+
+def test_emulated_kernel_stance_and_drop():
+    """Standing on the plane under the PD controller: the trunk settles, the feet stick and carry m g; a robot dropped from 0.6 m lands, stays
+    finite and comes to rest on its feet or terminates on base contact (never tunnels below the ground)."""
+    A, env = _emu_env(num_envs=2)
+    T = A.tensors
+    T["root_states"][:] = 0; T["root_states"][:, 6] = 1
+    T["root_states"][0, 2] = 0.34; T["root_states"][1, 2] = 0.60
+    T["dof_pos"][:] = torch.tensor(A.default_dof_pos_np); T["dof_vel"][:] = 0
+    min_z = 1.0
+    for _ in range(300):
+        env.step(torch.zeros(2, 12))
+        for k in ("root_states", "dof_pos", "dof_vel", "contact_forces", "obs_buf"):
+            assert torch.isfinite(T[k]).all(), k
+        min_z = min(min_z, float(T["root_states"][:, 2].min()))
+    assert min_z > 0.05                                                 # nothing sinks through the plane
+    z = float(T["root_states"][0, 2])
+    assert 0.22 < z < 0.32, z
+    mass = float(T["body_inertia"][0, :, 0].sum())
+    fz = float(T["contact_forces"][0, :, 2].sum())
+    assert abs(fz - mass * 9.81) < 0.05 * mass * 9.81
+    assert float(T["feet_vel"][0].abs().max()) < 0.02                   # feet stick
+    assert float(T["projected_gravity"][0, 2]) < -0.99
