@@ -333,7 +333,8 @@ def _main(out):
                 "roofline": {"kernel": "go2::step_kernel_packed<2>" if os.environ.get("GO2_STEP_MODE", "P2").startswith("P") else "go2::step_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                              "kernel_us": kern_ms * 1e3, "env_steps_per_s_kernel_only": N / (kern_ms * 1e-3),
-                             "note": "latency/issue-bound serial 13-body recursion; HBM fraction is structurally tiny (SURVEY 7.2)"},
+                             "note": "bound by the latency of one serial articulated-body chain per 8-env CTA (2 CTAs / SM by registers), not by bytes: "
+                                     "DESIGN.md 5.1, profiles/r01k_step_kernel_phase_cycles.txt; traffic = ncu dram bytes per launch (profiles/step_kernel_dram.json)"},
                 "roofline_gemm": gemm, "clocks": clocks, "cpu_baseline": cpu,
                 "split_ms": {"collection": col_ms, "learning": lrn_ms}}
         print(json.dumps(line), file=out, flush=True)
