@@ -76,6 +76,11 @@ def update_cfg_from_args(env_cfg, cfg_train, args):
             cfg_train.runner.load_run = args.load_run
         if args.checkpoint is not None:
             cfg_train.runner.checkpoint = args.checkpoint
+        # the RoboGauge evaluation client itself is out of scope; its switches are still carried in the config like the reference does
+        if getattr(args, "robogauge", None) is not None and hasattr(cfg_train, "robogauge"):
+            cfg_train.robogauge.enabled = args.robogauge
+        if getattr(args, "robogauge_port", None) is not None and hasattr(cfg_train, "robogauge"):
+            cfg_train.robogauge.port = args.robogauge_port
     return env_cfg, cfg_train
 
 
