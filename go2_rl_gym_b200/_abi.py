@@ -52,6 +52,7 @@ class Go2EnvConfig(C.Structure):
         ("obs_scale_height", f32), ("noise_scale_vec", f32 * NUM_OBS),
         ("height_points", f32 * 2 * NUM_HEIGHT), ("base_height_mask", f32 * NUM_HEIGHT),
         ("num_base_height_points", f32), ("base_init_state", f32 * 13),
+        ("limit_relax", f32), ("contact_relax", f32),
     ]
 
 

@@ -50,6 +50,13 @@
 #define GO2_WIDE GO2_EACH if (L.own) GO2_BIND(L.w, L.lane)
 #define GO2_LEGS GO2_EACH if (L.leg >= 0) GO2_BIND(L.wl, L.leg)
 
+// The relaxed contact / joint-limit solver (Go2EnvConfig.limit_relax / contact_relax) is compiled into the host
+// emulation, where it is validated against the oracle; the sm_100a library of this round is built WITHOUT it (identical code to the build
+// that was measured and tested on the B200) and rejects those settings at create time.
+#ifndef GO2_RELAXED_SOLVER
+#define GO2_RELAXED_SOLVER 0
+#endif
+
 namespace go2 {
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
@@ -250,6 +257,10 @@ struct WarpSmem {
   float fcol[GO2_NUM_COL][6];  // spatial impulse of each collider on its body (body coords)
   float pcol[GO2_NUM_COL][3];  // world impulse of each collider
   float tgt[12][2];            // joint-limit target velocities (lower, upper row)
+#if GO2_RELAXED_SOLVER
+  float Dje[12];               // limit-row step limit_relax / (M^-1)_jj (relaxed solver only)
+  int pad_relaxed_[20];        // keeps the row stride at 1 mod 32 words in this build too
+#endif
   float mu_env, rest_env;      // contact friction / restitution of this env (combined with the terrain's)
   float a0[6];
   float q[12], qd[12], tau[12], cs[12][2], qdm[12], dqd[12], tauimp[12], Dj[12];
@@ -490,7 +501,7 @@ GO2_HD void leg_imp_out(int l, Lane& L, WarpSmem& S, const Go2Model* M, V6& dvpa
 }
 // pass 3 + unconstrained velocity + mobility, outward for link I
 template <int I>
-GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, V6& apar, V6& vmpar, M3& Pp, M3& Qp, M3& Rp) {
+GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, float limit_relax, V6& apar, V6& vmpar, M3& Pp, M3& Qp, M3& Rp) {
   constexpr int AX = LinkAxis<I>::ax;
   const int j = 3 * l + I, b = j + 1;
   float c = L.c[I], s = L.s[I];
@@ -533,6 +544,11 @@ GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, 
     Q.m[3 * AX + t] -= ylv[t] * Dinv;   // row k of Q (= column k of Q^T)
   }
   P.m[3 * AX + AX] += alpha * Dinv * Dinv + Dinv;
+#if GO2_RELAXED_SOLVER
+  if (limit_relax > 0.0f) S.Dje[j] = limit_relax / P.m[3 * AX + AX];   // P[k][k] = (M^-1)_jj: the joint's own response with every other joint free
+#else
+  (void)limit_relax;
+#endif
   stm(S.Lam[b], P); stm(S.Lam[b] + 9, Q); stm(S.Lam[b] + 18, R);
   Pp = P; Qp = Q; Rp = R;
 }
@@ -637,9 +653,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       vm0.a = v0.a + dt * a0.a;
       vm0.l = v0.l + dt * (a0.l + gb + cross(v0.a, v0.l));  // components stay in the frame of the start of the step
       V6 ap = a0, vmp = vm0;
-      leg_pass3<0>(lane, L, S, M, dt, ap, vmp, P, Q, R);
-      leg_pass3<1>(lane, L, S, M, dt, ap, vmp, P, Q, R);
-      leg_pass3<2>(lane, L, S, M, dt, ap, vmp, P, Q, R);
+      leg_pass3<0>(lane, L, S, M, dt, GO2_RELAXED_SOLVER ? C->limit_relax : 0.0f, ap, vmp, P, Q, R);
+      leg_pass3<1>(lane, L, S, M, dt, GO2_RELAXED_SOLVER ? C->limit_relax : 0.0f, ap, vmp, P, Q, R);
+      leg_pass3<2>(lane, L, S, M, dt, GO2_RELAXED_SOLVER ? C->limit_relax : 0.0f, ap, vmp, P, Q, R);
       if (lane == 0) st6(S.v[0], vm0);
       for (int i = 0; i < 3; ++i) { L.lam_lo[i] = 0; L.lam_hi[i] = 0; }
     }
@@ -694,7 +710,11 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
     {
       int g0 = lane < 8 ? 0 : 8 + 6 * ((lane - 8) / 6), gn = lane < 8 ? 8 : 6, cnt = 0;
       for (int k = 0; k < gn; ++k) cnt += S.active[g0 + k];
-      L.gsplit = 1.0f / (float)cnt;      // only read by active colliders: cnt >= 1
+#if GO2_RELAXED_SOLVER
+      L.gsplit = C->contact_relax / (float)cnt;      // block step of the contact rows; only read by active colliders: cnt >= 1
+#else
+      L.gsplit = 1.0f / (float)cnt;                  // mass-splitting factor; only read by active colliders: cnt >= 1
+#endif
     }
   }
   // ---- Jacobi sweeps with exact propagation through the tree: [collider lanes: block-solve every contact] | CTA barrier |
@@ -730,7 +750,11 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       if (lane < 4) {
         for (int i = 0; i < 3; ++i) {  // joint-limit rows of the leg's joints (unilateral, velocity level)
           const int j = 3 * lane + i;
+#if GO2_RELAXED_SOLVER
+          float cur = S.qdm[j] + S.dqd[j], Dj = C->limit_relax > 0.0f ? S.Dje[j] : S.Dj[j];
+#else
           float cur = S.qdm[j] + S.dqd[j], Dj = S.Dj[j];
+#endif
           L.lam_lo[i] = fmaxf(0.0f, L.lam_lo[i] + (S.tgt[j][0] - cur) * Dj);
           L.lam_hi[i] = fminf(0.0f, L.lam_hi[i] + (S.tgt[j][1] - cur) * Dj);
           S.tauimp[j] = L.lam_lo[i] + L.lam_hi[i];

@@ -224,6 +224,10 @@ class LeggedRobotCfg(BaseConfig):
             erp = 0.2
             limit_erp = 0.2
             penetration_slop = 0.004
+            # relaxation of the Jacobi sweeps (include/go2_b200.h).  0 / 1 = the solver every fixture of this round was generated with.  The
+            # convergent setting found in this round: limit_relax = 0.5, contact_relax = 0.7, limit_erp = 0.8.
+            limit_relax = 0.0
+            contact_relax = 1.0
 
 
 class _TrainCfgBase(BaseConfig):

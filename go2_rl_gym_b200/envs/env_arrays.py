@@ -182,6 +182,7 @@ class EnvArrays:
         c.max_depen_vel = cfg.sim.physx.max_depenetration_velocity
         c.bounce_threshold = cfg.sim.physx.bounce_threshold_velocity
         c.terrain_friction, c.terrain_restitution = cfg.terrain.static_friction, cfg.terrain.restitution
+        c.limit_relax, c.contact_relax = getattr(b200, "limit_relax", 0.0), getattr(b200, "contact_relax", 1.0)
         c.mesh_type = 0 if self.plane else 1
         c.hf_rows, c.hf_cols = hs.shape
         c.hscale, c.vscale, c.border = cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.border_size

@@ -97,6 +97,11 @@ typedef struct Go2EnvConfig {
   float base_height_mask[GO2_NUM_HEIGHT];   /* legged_robot.py:790-795 */
   float num_base_height_points;
   float base_init_state[13];                /* pos, quat xyzw, lin vel, ang vel (legged_robot.py:1000) */
+  /* relaxation of the Jacobi sweeps (appended: earlier offsets are unchanged).  limit_relax = 0: joint-limit rows step with D_j (the first
+     solver of this build: over-relaxed when the parent link recoils, divergent for > 4 sweeps); limit_relax = w > 0: rows step with
+     w / (M^-1)_jj, the exact joint-space diagonal the mobility recursion already computes (convergent for w <= 0.5).  contact_relax scales
+     the contact rows' block step (1 = unchanged). */
+  float limit_relax, contact_relax;
 } Go2EnvConfig;
 
 /* Per-step scalars the host derives from common_step_counter (curricula), no device sync involved. */

@@ -383,7 +383,7 @@ static void physics_substep(const Go2EnvConfig& C, const Go2Model& M, const Terr
       // block solve toward (normal velocity = target, zero slip), split by the group's contact count, then
       // project the accumulated impulse onto the friction cone
       V3 err = vp - k.vt * k.n;
-      V3 pc = k.p - (1 / s) * mul(k.Winv, err);
+      V3 pc = k.p - ((real)C.contact_relax / s) * mul(k.Winv, err);
       real pn = std::max((real)0, dot(pc, k.n));
       V3 pt = pc - dot(pc, k.n) * k.n;
       real ptn = norm(pt), lim = k.mu * pn;
@@ -392,6 +392,7 @@ static void physics_substep(const Go2EnvConfig& C, const Go2Model& M, const Terr
     }
     for (int j = 0; j < GO2_NUM_DOF; ++j) {
       real cur = qdm[j] + dqd[j], Dj = D[j + 1];
+      if (C.limit_relax > 0) Dj = (real)C.limit_relax / Lam[j + 1].m[M.joint_axis[j]][M.joint_axis[j]];   // exact joint-space diagonal
       lam_lo[j] = std::max((real)0, lam_lo[j] + (tgt_lo[j] - cur) * Dj);
       lam_hi[j] = std::min((real)0, lam_hi[j] + (tgt_hi[j] - cur) * Dj);
     }

@@ -41,3 +41,17 @@ def test_product_fails_loudly_without_cuda():
     cfg = GO2Cfg(); cfg.env.num_envs = 4
     with pytest.raises(RuntimeError):
         Go2Robot(cfg, None, None, "cuda:0", True)
+
+
+def test_create_rejects_solver_settings_the_build_does_not_carry():
+    """The sm_100a library of this round is built without the relaxed solver (GO2_RELAXED_SOLVER=0): go2_env_create must refuse
+    limit_relax / contact_relax instead of silently running the first solver (checked before any CUDA call, so it runs without a GPU)."""
+    import __graft_entry__ as ge
+    ge.build()
+    from go2_rl_gym_b200 import _abi
+    lib = _abi.load_library()
+    cfg, mdl, buf = _abi.Go2EnvConfig(), _abi.Go2Model(), _abi.Go2EnvBuffers()
+    cfg.num_envs, cfg.limit_relax, cfg.contact_relax = 8, 0.5, 0.7
+    h = ctypes.c_void_p()
+    rc = lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
+    assert rc != 0 and b"relaxed solver" in lib.go2_last_error()
