@@ -10,3 +10,10 @@ for mb in "$@"; do
   rm -f $C/_v_env_step.cu
   echo built libgo2b200_mb$mb.so
 done
+
+# relaxed-solver variant of the whole library: GO2_B200_LIB=go2_rl_gym_b200/libgo2b200_relaxed.so + sim.b200.limit_relax = 0.5
+if [ "$RELAXED" = "1" ]; then
+  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DGO2_RELAXED_SOLVER=1 -c $C/env_step.cu -o build/_relaxed_env_step.o
+  nvcc -shared -o go2_rl_gym_b200/libgo2b200_relaxed.so build/_relaxed_env_step.o build/common.cu.o build/rl_kernels.cu.o build/gemm_tc.cu.o build/cts_kernels.cu.o -lcudart -lcuda
+  echo built libgo2b200_relaxed.so
+fi
