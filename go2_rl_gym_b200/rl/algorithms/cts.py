@@ -205,10 +205,14 @@ class CTS:
         log, log2 = self._log.tolist(), self._log2.tolist()      # the single host sync of update()
         self.learning_rate = log[3]
         st.clear()
-        out = (log[0] / n, log[1] / n, log[4] / n, log2[0] / n)
-        return out + (log2[1] / n,) if self._moe else out
+        return self._losses(log, log2, n)
 
     _moe = False
+
+    def _losses(self, log, log2, n):
+        """update()'s return value: mean value / surrogate / entropy / latent loss (cts.py:280-285) + the student's load-balance loss (moe_cts.py:229-234)."""
+        out = (log[0] / n, log[1] / n, log[4] / n, log2[0] / n)
+        return out + (log2[1] / n,) if self._moe else out
 
     def _update_body(self):
         # pass 1: PPO on teacher + student rows, optimizer 1 (moe_cts.py:114-195)
@@ -264,7 +268,7 @@ class CTS:
              float(self.tm * ws), float(max(self.sm, 1) * ws))
         call("go2_adam_clip_step", ptr(m.flat_params), ptr(m.flat_grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), m.n1, self.max_grad_norm, ptr(self._lr1),
              1.0, ptr(self._scratch))
-        for e in (m.teacher_engine, m.actor_engine, m.critic_engine):
+        for e in m.pass1_engines():
             e.mark_dirty()
 
     def _grad2(self, i):
@@ -332,3 +336,76 @@ class MoECTS(CTS):
 
 class MoENGCTS(MoECTS):
     """MoENGCTS (rsl_rl/algorithms/moe_ng_cts.py:40-234): identical to MoECTS; the no-goal column selection lives in the model's student encoder."""
+
+
+class ACMoECTS(CTS):
+    """ACMoECTS (rsl_rl/algorithms/ac_moe_cts.py:40-277): CTS with a mixture-of-experts actor and value experts weighted by the actor's
+    gate (ActorCriticACMoECTS); pass 1 adds the load-balance loss of the actor's gate over the whole mini-batch (:225-235); pass 2 is plain
+    CTS (MLP student).  compute_returns takes the last observations too (:136-142): the value needs the actor's gate.
+
+    The reference evaluates the gate twice per row (act and evaluate); both see the same input and weights, so their gradients are summed
+    into ONE backward of the gate here.  Gradients the reference lets flow into the student encoder during pass 1 are discarded there
+    (optimizer 2 zeroes them before pass 2, :261-262) and never computed here."""
+    _moe = False        # pass 2: no student load-balance term
+    _n_losses = 5
+
+    def __init__(self, model, num_envs, history_length, load_balance_coef=0.01, **kwargs):
+        super().__init__(model, num_envs, history_length, load_balance_coef=load_balance_coef, **kwargs)
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        super().init_storage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape)
+        dev = self.device
+        self._log3, self._zero1 = torch.zeros(2, device=dev), torch.zeros(1, device=dev)
+        self._obs_p = torch.zeros(num_envs, actor_obs_shape[0], device=dev)
+
+    def _heads(self, obs, priv, M, train=False):
+        m, D = self.model, self.model.latent_dim
+        call("go2_concat2", ptr(self._lat), D, D, ptr(obs), m.num_obs, obs.stride(0), ptr(self._xa), self._xa.shape[1], 0, M)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(priv), m.num_critic_obs, priv.stride(0), ptr(self._xc), self._xc.shape[1], 0, M)
+        m.heads_forward(self._xa, self._xc, M, self._mu, self._val, train=train)
+
+    def compute_returns(self, last_obs, last_privileged_obs, last_history):
+        N, m = self.storage.num_envs, self.model
+        g = lambda src, dst: call("go2_gather_rows", ptr(src.contiguous()), src.shape[1], ptr(self.perm), ptr(dst), src.shape[1], 0, N)
+        g(last_obs, self._obs_p); g(last_privileged_obs, self._xc_p(N)); g(last_history, self._hist_p)
+        self._latents(self._priv_p, self._hist_p, self.teacher_num_envs, self.student_num_envs)
+        self._heads(self._obs_p, self._priv_p, N)
+        self._last_values.copy_(self._val[:N])
+        self.storage.compute_returns(self._last_values, self.gamma, self.lam,
+                                     reduce_stats=(lambda s: dist_utils.allreduce_adv_stats(s, N * self.storage.num_transitions_per_env)) if self.world_size > 1 else None)
+
+    def update(self, teacher_perm=None, student_perm=None):
+        self._log3.zero_()
+        return super().update(teacher_perm, student_perm)
+
+    def _grad1(self, i):
+        st, m, sh = self.storage, self.model, self._sh
+        tm, sm, mb, A, D = self.tm, self.sm, self.mb, st.actions.shape[-1], m.latent_dim
+        ws = self.world_size
+        s = slice(i * mb, (i + 1) * mb)
+        obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True)
+        self._heads(obs_b, priv_b, mb, train=True)
+        call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
+             ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
+             0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+             int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
+        # the gradient is SUM-reduced over the ranks: each rank's load-balance term (on its own rows' mean usage) enters with 1 / world_size
+        dx = m.heads_backward(self._dmu, self._dval, mb, self.load_balance_coef / ws)
+        m.teacher_backward(dx, dx.shape[1], self._lat, D, tm)           # teacher rows only: student latents carry no gradient in pass 1
+        m._gviews["std"].copy_(self._scal[4:4 + A])
+        call("go2_cts_log", ptr(self._zero1), ptr(m.actor_head.usage), ptr(self._log3), 1, m.actor_head.E)
+
+    def _losses(self, log, log2, n):
+        actor_lb = self._log3.tolist()[1] / n
+        return (log[0] / n, log[1] / n, log[4] / n, log2[0] / n, actor_lb)
+
+
+class DualMoECTS(ACMoECTS):
+    """DualMoECTS (rsl_rl/algorithms/dual_moe_cts.py:40-287): ACMoECTS with the MoE student encoder of MoECTS; update() returns the student's and
+    the actor's load-balance losses (:287)."""
+    _moe = True
+
+    def _losses(self, log, log2, n):
+        out = super()._losses(log, log2, n)
+        return out[:4] + (log2[1] / n, out[4])

@@ -1,2 +1,2 @@
 from .actor_critic import ActorCritic
-from .actor_critic_cts import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS
+from .actor_critic_cts import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS

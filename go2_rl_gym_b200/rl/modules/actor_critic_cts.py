@@ -114,8 +114,12 @@ class _CTSBase(nn.Module):
     def flat_grads(self):
         return self._grad
 
+    def pass1_engines(self):
+        """Engines whose weights optimizer 1 changes (cts.py:72-79)."""
+        return [self.teacher_engine, self.actor_engine, self.critic_engine]
+
     def engines(self):
-        return [self.teacher_engine, self.actor_engine, self.critic_engine] + self.student.engines()
+        return self.pass1_engines() + self.student.engines()
 
     def mark_dirty(self):
         for e in self.engines():
@@ -435,3 +439,249 @@ class ActorCriticMoENGCTS(ActorCriticMoECTS):
         self.student = _StudentMoE(self, p, self.num_obs * self.history_length, self.s_hidden, self.expert_num, self.latent_dim, max_rows, trs,
                                    names=names, expert_cols=self._expert_cols)
         self._common_buffers(dev, max_rows, max(trt, trs))
+
+
+# ---- MoE actor + gated critic experts (ac_moe_cts / dual_moe_cts) -----------------------------------------------------------------
+class _ExpertLayer:
+    """Conv1d(E*H -> E*D, kernel 1, groups=E) (modules/utils.py:83-88) = E block-diagonal Linear(H -> D) over the backbone's feature
+    blocks.  Narrow experts (D <= 16, H <= 128: the 12-action and 1-value experts of the default configuration) run on the streaming
+    fp32 kernels, wider ones on the GEMM path the student's experts use."""
+
+    def __init__(self, model, pname, E, H, D, max_rows, train_rows):
+        dev = model.device
+        self.E, self.H, self.D = E, H, D
+        self.W = model._views[pname + ".weight"].view(E * D, H)
+        self.b = model._views[pname + ".bias"]
+        self.gW = model._gviews[pname + ".weight"].view(E * D, H)
+        self.gb = model._gviews[pname + ".bias"]
+        self.small = D <= 16 and H <= 128
+        self.tc = _ops.use_tc() and not self.small and D % 4 == 0
+        self.out = torch.empty(max_rows, E * D, device=dev)
+        self.dfeat = torch.empty(max(train_rows, 1), E * H, device=dev)
+        self.Wt = torch.zeros(E * H, D, device=dev) if self.tc else None
+        self.work = torch.empty(max(296 * (D * H + D), 64 * 128 * (H + 4), 64 * E * D), device=dev)
+        self._dirty = True
+
+    def mark_dirty(self):
+        self._dirty = True
+
+    def forward(self, feat, ldf, M):
+        E, D, H = self.E, self.D, self.H
+        for e in range(E):
+            x, w, b, y = ptr(feat) + 4 * e * H, ptr(self.W) + 4 * e * D * H, ptr(self.b) + 4 * e * D, ptr(self.out) + 4 * e * D
+            if self.small:
+                call("go2_linear_forward_smalln", x, ldf, w, H, b, y, E * D, M, D, H)
+            else:
+                call("go2_linear_forward_tc" if self.tc else "go2_linear_forward_simt", x, ldf, w, H, b, y, E * D, 0, 0, M, D, H, 0)
+
+    def backward(self, dout, feat, ldf, M):
+        """dout [M, E*D] -> gW, gb and self.dfeat [M, E*H] = gradient w.r.t. the backbone's last LINEAR output (ELU' applied)."""
+        E, D, H = self.E, self.D, self.H
+        if self.tc and self._dirty:
+            import ctypes as C
+            vp, ia = (C.c_void_p * E), (C.c_int * E)
+            call("go2_refresh_weights", E, vp(*[ptr(self.W) + 4 * e * D * H for e in range(E)]), ia(*([H] * E)),
+                 vp(*[ptr(self.Wt) + 4 * e * H * D for e in range(E)]), ia(*([D] * E)), ia(*([D] * E)), ia(*([H] * E)), ia(*([1] * E)))
+            self._dirty = False
+        if not self.small:
+            call("go2_colsum", ptr(dout), E * D, ptr(self.gb), M, E * D, ptr(self.work))
+        for e in range(E):
+            d, x, gw = ptr(dout) + 4 * e * D, ptr(feat) + 4 * e * H, ptr(self.gW) + 4 * e * D * H
+            df = ptr(self.dfeat) + 4 * e * H
+            if self.small:
+                call("go2_linear_wgrad_smalln", d, E * D, x, ldf, gw, H, ptr(self.gb) + 4 * e * D, M, D, H, ptr(self.work), self.work.numel())
+                call("go2_linear_dgrad_smalln", d, E * D, ptr(self.W) + 4 * e * D * H, H, x, ldf, df, E * H, M, D, H)
+            elif self.tc:
+                call("go2_linear_wgrad_tc_rm", d, E * D, x, ldf, gw, H, 0, M, D, H, ptr(self.work), self.work.numel())
+                call("go2_linear_dgrad_tc", d, E * D, ptr(self.Wt) + 4 * e * H * D, D, x, ldf, 0, 0, df, E * H, 0, 0, M, D, H)
+            else:
+                call("go2_linear_wgrad_simt", d, E * D, x, ldf, gw, H, 0, M, D, H, ptr(self.work), self.work.numel())
+                call("go2_linear_dgrad_simt", d, E * D, ptr(self.W) + 4 * e * D * H, H, x, ldf, df, E * H, 0, 0, M, D, H)
+
+
+class _MoEHead:
+    """MoE (modules/utils.py:96-126) as a policy head: shared backbone -> E experts, softmax gate on the same input, weighted sum.
+    Both the backbone and the gate return the gradient w.r.t. their input (the [latent | obs] row)."""
+
+    def __init__(self, model, prefix, in_dim, hidden_dims, E, D, max_rows, train_rows):
+        dev = model.device
+        self.E, self.D, self.H = E, D, hidden_dims[-1]
+        bdims = [in_dim, *hidden_dims[:-1], E * self.H]
+        gdims = [in_dim, *hidden_dims[:-1], E]
+        self.backbone = model._engine(_linear_names(prefix + ".experts.backbone.network", len(bdims) - 1), bdims, max_rows, train_rows,
+                                      last_act=True, need_dx=True)
+        self.gate = model._engine(_linear_names(prefix + ".gating_network.0.network", len(gdims) - 1), gdims, max_rows, train_rows, need_dx=True)
+        self.layer = _ExpertLayer(model, prefix + ".experts.experts", E, self.H, D, max_rows, train_rows)
+        tr = max(train_rows, 1)
+        self.logits, self.gates = torch.empty(max_rows, E, device=dev), torch.empty(max_rows, E, device=dev)
+        self.dlogits, self.deo = torch.empty(tr, E, device=dev), torch.empty(tr, E * D, device=dev)
+        self.usage = torch.zeros(E, device=dev)
+
+    def engines(self):
+        return [self.backbone, self.gate]
+
+    def mark_dirty(self):
+        self.layer.mark_dirty()
+
+    def forward(self, x, ldx, M, out, train=False, x_ones=False):
+        """out[M, D] (dense) = sum_e softmax(gate(x))_e * expert_e(backbone(x))"""
+        self.backbone.forward(x, ldx, M, train=train, x_ones=x_ones)
+        self.layer.forward(self.backbone.out, self.backbone.ld_out, M)
+        self.gate.forward(x, ldx, M, self.logits[:M], self.E, train=train, x_ones=x_ones)
+        call("go2_moe_combine_forward", ptr(self.logits), ptr(self.layer.out), ptr(self.gates), ptr(out), M, self.E, self.D)
+        self._M = M
+
+    def backward(self, dout, lb_coef=0.0, extra_dlogits=None):
+        """dout [M, D] dense.  lb_coef: load-balance term on the mean gate usage of these M rows (ac_moe_cts.py:226-228).  extra_dlogits: the
+        gate's gradient from another consumer of the same gates (the critic's weighted value), already through the softmax."""
+        M, E, D = self._M, self.E, self.D
+        call("go2_moe_combine_backward", ptr(dout), ptr(self.gates), ptr(self.layer.out), ptr(self.usage), float(lb_coef), ptr(self.deo), 0,
+             ptr(self.dlogits), 0, M, E, D)
+        if extra_dlogits is not None:
+            self.dlogits[:M].add_(extra_dlogits[:M])
+        self.layer.backward(self.deo, self.backbone.out, self.backbone.ld_out, M)
+        self.backbone.backward(self.layer.dfeat, E * self.H)
+        self.gate.backward(self.dlogits, E)
+
+
+class _GatedExpertsHead:
+    """Experts (modules/utils.py:69-94) with one output each, weighted by gates computed elsewhere (the actor's gating network,
+    actor_critic_ac_moe_cts.py:139-145): value = sum_e gates_e * v_e."""
+
+    def __init__(self, model, prefix, in_dim, backbone_hidden_dims, H, E, max_rows, train_rows):
+        dev = model.device
+        self.E, self.H = E, H
+        bdims = [in_dim, *backbone_hidden_dims, E * H]
+        self.backbone = model._engine(_linear_names(prefix + ".backbone.network", len(bdims) - 1), bdims, max_rows, train_rows, last_act=True)
+        self.layer = _ExpertLayer(model, prefix + ".experts", E, H, 1, max_rows, train_rows)
+        tr = max(train_rows, 1)
+        self.gates = torch.empty(max_rows, E, device=dev)
+        self.deo, self.dlogits = torch.empty(tr, E, device=dev), torch.empty(tr, E, device=dev)
+        self.usage = torch.zeros(E, device=dev)
+
+    def engines(self):
+        return [self.backbone]
+
+    def mark_dirty(self):
+        self.layer.mark_dirty()
+
+    def forward(self, x, ldx, M, logits, out, train=False, x_ones=False):
+        self.backbone.forward(x, ldx, M, train=train, x_ones=x_ones)
+        self.layer.forward(self.backbone.out, self.backbone.ld_out, M)
+        call("go2_moe_combine_forward", ptr(logits), ptr(self.layer.out), ptr(self.gates), ptr(out), M, self.E, 1)
+        self._M = M
+
+    def backward(self, dvalue):
+        """dvalue [M, 1] dense -> parameter gradients; self.dlogits [M, E] = the gate logits' gradient from the value."""
+        M, E = self._M, self.E
+        call("go2_moe_combine_backward", ptr(dvalue), ptr(self.gates), ptr(self.layer.out), ptr(self.usage), 0.0, ptr(self.deo), 0,
+             ptr(self.dlogits), 0, M, E, 1)
+        self.layer.backward(self.deo, self.backbone.out, self.backbone.ld_out, M)
+        self.backbone.backward(self.layer.dfeat, E * self.H)
+
+
+class ActorCriticACMoECTS(_CTSBase):
+    """ActorCriticACMoECTS (rsl_rl/modules/actor_critic_ac_moe_cts.py:21-146): CTS whose actor is a mixture of experts on [latent | obs] and
+    whose critic is a set of value experts on [latent | privileged obs] weighted by the ACTOR's gate.  Same constructor arguments and
+    state_dict keys (teacher_encoder.0.network.*, student_encoder.0.network.*, actor_moe.*, critic_experts.*, std)."""
+    moe_heads = True
+
+    def __init__(self, num_obs, num_critic_obs, num_actions, num_envs, history_length, actor_hidden_dims=[512, 256, 128],
+                 critic_hidden_dims=[512, 256, 128], teacher_encoder_hidden_dims=[512, 256], student_encoder_hidden_dims=[512, 256],
+                 expert_num=8, activation='elu', init_noise_std=1.0, latent_dim=32, norm_type='l2norm', **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        if activation != 'elu' or norm_type != 'l2norm':
+            raise NotImplementedError("fused epilogues implement ELU / L2Norm (the go2_ac_moe_cts / go2_dual_moe_cts configuration)")
+        super().__init__()
+        self.num_obs, self.num_critic_obs, self.num_actions = num_obs, num_critic_obs, num_actions
+        self.history_length, self.latent_dim, self.expert_num = history_length, latent_dim, expert_num
+        self.register_buffer("history", torch.zeros((num_envs, history_length, num_obs)), persistent=False)
+        self.t_dims = [num_critic_obs, *teacher_encoder_hidden_dims, latent_dim]
+        self.a_hidden, self.c_hidden = list(actor_hidden_dims), list(critic_hidden_dims)
+        self.a_dims = [latent_dim + num_obs, *actor_hidden_dims, num_actions]       # input / output widths (the hidden part is the MoE's)
+        self.c_dims = [latent_dim + num_critic_obs, *critic_hidden_dims, 1]
+        self.teacher_encoder = nn.Sequential(MLP(self.t_dims), L2Norm())
+        self._make_student(num_obs * history_length, list(student_encoder_hidden_dims), latent_dim, expert_num)
+        self.actor_moe = MoE(expert_num, self.a_dims[0], self.a_hidden, num_actions)
+        self.critic_experts = Experts(expert_num, self.c_dims[0], self.c_hidden[:-1], self.c_hidden[-1], 1)
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+
+    student_prefix = "student_encoder"
+
+    def _make_student(self, in_dim, hidden, latent_dim, expert_num):
+        self.s_dims = [in_dim, *hidden, latent_dim]
+        self.student_encoder = nn.Sequential(MLP(self.s_dims), L2Norm())
+
+    def _segments(self):
+        names = [k for k, _ in self.named_parameters()]
+        seg1 = [k for k in names if k.startswith("teacher_encoder.")] + [k for k in names if k.startswith("critic_experts.")] + \
+               [k for k in names if k.startswith("actor_moe.")] + ["std"]
+        seg2 = [k for k in names if k.startswith(self.student_prefix + ".")]
+        return seg1, seg2
+
+    def _build_student(self, max_rows, trs):
+        return _StudentMLP(self, _linear_names("student_encoder.0.network", len(self.s_dims) - 1), self.s_dims, max_rows, trs)
+
+    def _build_engines(self, dev, max_rows, tr1, trt, trs):
+        E = self.expert_num
+        self.teacher_engine = self._engine(_linear_names("teacher_encoder.0.network", len(self.t_dims) - 1), self.t_dims, max_rows, max(trt, trs))
+        self.actor_head = _MoEHead(self, "actor_moe", self.a_dims[0], self.a_hidden, E, self.num_actions, max_rows, tr1)
+        self.critic_head = _GatedExpertsHead(self, "critic_experts", self.c_dims[0], self.c_hidden[:-1], self.c_hidden[-1], E, max_rows, tr1)
+        self.student = self._build_student(max_rows, trs)
+        ActorCriticMoECTS._common_buffers(self, dev, max_rows, max(trt, trs))
+        self._dx = torch.zeros(max(tr1, 1), self.actor_head.backbone.kpad0, device=dev)
+
+    def pass1_engines(self):
+        return [self.teacher_engine] + self.actor_head.engines() + self.critic_head.engines()
+
+    def engines(self):
+        return self.pass1_engines() + self.student.engines()
+
+    def mark_dirty(self):
+        super().mark_dirty()
+        self.actor_head.mark_dirty()
+        self.critic_head.mark_dirty()
+
+    def heads_forward(self, xa, xc, M, mu, val, train=False):
+        """mu[M, A], val[M, 1] from the padded [latent | obs] / [latent | privileged obs] rows (actor_critic_ac_moe_cts.py:103-145)."""
+        a, c = self.actor_head, self.critic_head
+        a.forward(xa, xa.shape[1], M, mu, train=train, x_ones=xa.shape[1] > self.a_dims[0])
+        c.forward(xc, xc.shape[1], M, a.logits, val, train=train, x_ones=xc.shape[1] > self.c_dims[0])
+
+    def heads_backward(self, dmu, dval, M, lb_coef):
+        """-> [M, kpad0] whose first latent_dim columns are d loss / d latent through the actor's backbone AND gate (the critic's input
+        latent is detached, actor_critic_ac_moe_cts.py:142; its gate gradient arrives through the shared gates)."""
+        a, c = self.actor_head, self.critic_head
+        c.backward(dval)
+        a.backward(dmu, lb_coef, extra_dlogits=c.dlogits)
+        torch.add(a.backbone.dx[:M], a.gate.dx[:M], out=self._dx[:M])
+        return self._dx
+
+    def act_inference(self, obs):
+        """Student policy (actor_critic_ac_moe_cts.py:127-132)."""
+        N = obs.shape[0]
+        call("go2_history_update", ptr(self.history), ptr(obs.contiguous()), 0, N, self.history_length, self.num_obs)
+        lat = self._inf_lat[:N]
+        self.student.forward(self.history.view(N, -1), N, lat)
+        xa = self._inf_xa[:N]
+        call("go2_concat2", ptr(lat), self.latent_dim, self.latent_dim, ptr(obs), self.num_obs, obs.shape[1], ptr(xa), xa.shape[1], 0, N)
+        out = self._inf_mu[:N]
+        self.actor_head.forward(xa, xa.shape[1], N, out, x_ones=xa.shape[1] > self.a_dims[0])
+        return out.clone()
+
+
+class ActorCriticDualMoECTS(ActorCriticACMoECTS):
+    """ActorCriticDualMoECTS (rsl_rl/modules/actor_critic_dual_moe_cts.py:21-149): ActorCriticACMoECTS with the MoE student encoder of
+    ActorCriticMoECTS (student_moe_encoder.moe.*)."""
+    student_prefix = "student_moe_encoder"
+
+    def __init__(self, num_obs, num_critic_obs, num_actions, num_envs, history_length, student_encoder_hidden_dims=[512, 256, 256], **kwargs):
+        super().__init__(num_obs, num_critic_obs, num_actions, num_envs, history_length, student_encoder_hidden_dims=student_encoder_hidden_dims, **kwargs)
+
+    def _make_student(self, in_dim, hidden, latent_dim, expert_num):
+        self.s_hidden = hidden
+        self.student_moe_encoder = StudentMoEEncoder(expert_num, in_dim, hidden, latent_dim)
+
+    def _build_student(self, max_rows, trs):
+        return _StudentMoE(self, "student_moe_encoder", self.num_obs * self.history_length, self.s_hidden, self.expert_num, self.latent_dim, max_rows, trs)

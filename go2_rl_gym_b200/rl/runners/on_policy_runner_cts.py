@@ -11,8 +11,8 @@ import torch
 import yaml
 
 from .. import _ops
-from ..algorithms import CTS, MoECTS, MoENGCTS
-from ..modules import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS
+from ..algorithms import CTS, MoECTS, MoENGCTS, ACMoECTS, DualMoECTS
+from ..modules import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS
 from ...utils.cfg_dict import class_to_dict
 from .on_policy_runner import SummaryWriter
 
@@ -24,10 +24,14 @@ class OnPolicyRunnerCTS:
         history_length = train_cfg["history_length"]
         self.history_length = history_length
         num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
-        model_class = {"ActorCriticCTS": ActorCriticCTS, "ActorCriticMoECTS": ActorCriticMoECTS,
-                       "ActorCriticMoENGCTS": ActorCriticMoENGCTS}[self.cfg["policy_class_name"]]
+        model_class = {"ActorCriticCTS": ActorCriticCTS, "ActorCriticMoECTS": ActorCriticMoECTS, "ActorCriticMoENGCTS": ActorCriticMoENGCTS,
+                       "ActorCriticACMoECTS": ActorCriticACMoECTS, "ActorCriticDualMoECTS": ActorCriticDualMoECTS}.get(self.cfg["policy_class_name"])
+        if model_class is None:
+            raise NotImplementedError(f"policy class {self.cfg['policy_class_name']} is not on the kernel path yet (DESIGN.md section 8)")
         model = model_class(self.env.num_obs, num_critic_obs, self.env.num_actions, self.env.num_envs, history_length, **self.policy_cfg)
-        alg_class = {"CTS": CTS, "MoECTS": MoECTS, "MoENGCTS": MoENGCTS}[self.cfg["algorithm_class_name"]]
+        alg_class = {"CTS": CTS, "MoECTS": MoECTS, "MoENGCTS": MoENGCTS, "ACMoECTS": ACMoECTS, "DualMoECTS": DualMoECTS}[self.cfg["algorithm_class_name"]]
+        # the value of the MoE-actor variants needs the actor's gate, hence the observations (on_policy_runner_cts.py:182-185)
+        self._returns_need_obs = self.cfg["algorithm_class_name"] in ("ACMoECTS", "DualMoECTS")
         off = env._A.env_offset if hasattr(env, "_A") else 0
         self.alg = alg_class(model, self.env.num_envs, history_length, device=self.device, seed=train_cfg.get("seed", 0), env_offset=off, **self.alg_cfg)
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
@@ -100,8 +104,14 @@ class OnPolicyRunnerCTS:
         with torch.inference_mode():
             if sync is not None:
                 sync()
-            alg.compute_returns(env.get_privileged_observations(), self.history.flatten(1))
+            self._compute_returns(env.get_observations(), env.get_privileged_observations())
         return alg.update()
+
+    def _compute_returns(self, obs, privileged_obs):
+        if self._returns_need_obs:
+            self.alg.compute_returns(obs, privileged_obs, self.history.flatten(1))
+        else:
+            self.alg.compute_returns(privileged_obs, self.history.flatten(1))
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         if self.log_dir is not None and self.writer is None and SummaryWriter is not None:
@@ -132,7 +142,7 @@ class OnPolicyRunnerCTS:
                 stop = time.time()
                 collection_time = stop - start
                 start = stop
-                self.alg.compute_returns(privileged_obs, self.history.flatten(1))
+                self._compute_returns(self.env.get_observations(), privileged_obs)
             losses = self.alg.update()
             stop = time.time()
             learn_time = stop - start
@@ -148,7 +158,7 @@ class OnPolicyRunnerCTS:
     def log(self, locs, width=80, pad=35):
         self.tot_timesteps += self.num_steps_per_env * self.env.num_envs
         self.tot_time += locs['collection_time'] + locs['learn_time']
-        names = ["value_function", "surrogate", "entropy", "latent", "load_balance"]
+        names = ["value_function", "surrogate", "entropy", "latent", "load_balance", "actor_load_balance"]      # on_policy_runner_cts.py:227-237
         fps = int(self.num_steps_per_env * self.env.num_envs / (locs['collection_time'] + locs['learn_time']))
         mean_std = self.alg.model.std.mean()
         ep_string = ''

@@ -12,3 +12,7 @@ ALG_CTS = {k: v for k, v in ALG.items() if k != "load_balance_coef"}
 NO_GOAL_MASK = [True] * 6 + [False] * 3 + [True] * 36
 POLICY_NG = dict(obs_no_goal_mask=NO_GOAL_MASK, actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16], teacher_encoder_hidden_dims=[64, 32],
                  student_encoder_hidden_dims=[64, 32], student_expert_num=8, activation="elu", init_noise_std=1.0, latent_dim=32, norm_type="l2norm")
+# MoE actor + gated value experts (LeggedRobotCfgACMoECTS / DualMoECTS, legged_robot_config.py:382-397): MLP student / MoE student
+POLICY_AC = dict(actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16], teacher_encoder_hidden_dims=[64, 32],
+                 student_encoder_hidden_dims=[64, 32], expert_num=8, activation="elu", init_noise_std=1.0, latent_dim=32, norm_type="l2norm")
+POLICY_DUAL = dict(POLICY_AC, student_encoder_hidden_dims=[64, 32, 32])

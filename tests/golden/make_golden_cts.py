@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate tests/golden/rl_moe_cts.npz from the REFERENCE's rsl_rl (ActorCriticMoECTS + MoECTS + RolloutStorageCTS, imported
 unmodified from /root/reference/rsl_rl): a seeded synthetic rollout through act / process_env_step / compute_returns and one
-update() with injected teacher / student permutations.  `--variant moe_ng_cts` does the same for ActorCriticMoENGCTS + MoENGCTS (-> rl_moe_ng_cts.npz), `--variant cts` for ActorCriticCTS + CTS (-> rl_cts.npz; the
+update() with injected teacher / student permutations.  `--variant moe_ng_cts` does the same for ActorCriticMoENGCTS + MoENGCTS (-> rl_moe_ng_cts.npz), `--variant ac_moe_cts` / `dual_moe_cts` for ActorCriticACMoECTS + ACMoECTS / ActorCriticDualMoECTS + DualMoECTS, `--variant cts` for ActorCriticCTS + CTS (-> rl_cts.npz; the
 reference allocates that module's history on 'cuda' at construction, actor_critic_cts.py:48, so torch.zeros is wrapped to drop the
 device while the module is built).  Build container only.  Usage (from /tmp): python /root/repo/tests/golden/make_golden_cts.py [--variant cts]"""
 import os
@@ -17,7 +17,7 @@ sys.path[:0] = ["/root/reference/rsl_rl", HERE]
 from rsl_rl.algorithms.moe_cts import MoECTS  # noqa: E402
 from rsl_rl.modules.actor_critic_moe_cts import ActorCriticMoECTS  # noqa: E402
 import rsl_rl.storage.rollout_storage_cts as RS  # noqa: E402
-from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_CTS, POLICY_NG  # noqa: E402
+from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_AC, POLICY_CTS, POLICY_DUAL, POLICY_NG  # noqa: E402
 
 
 def main():
@@ -29,6 +29,12 @@ def main():
     elif variant == "moe_ng_cts":     # experts on the history without its command columns (actor_critic_moe_ng_cts.py)
         from rsl_rl.modules.actor_critic_moe_ng_cts import ActorCriticMoENGCTS
         model = ActorCriticMoENGCTS(45, 263, 12, N, H, **POLICY_NG)
+    elif variant == "ac_moe_cts":     # MoE actor, value experts weighted by the actor's gate (actor_critic_ac_moe_cts.py)
+        from rsl_rl.modules.actor_critic_ac_moe_cts import ActorCriticACMoECTS
+        model = ActorCriticACMoECTS(45, 263, 12, N, H, **POLICY_AC)
+    elif variant == "dual_moe_cts":   # the same with the MoE student encoder (actor_critic_dual_moe_cts.py)
+        from rsl_rl.modules.actor_critic_dual_moe_cts import ActorCriticDualMoECTS
+        model = ActorCriticDualMoECTS(45, 263, 12, N, H, **POLICY_DUAL)
     else:
         from rsl_rl.algorithms.cts import CTS
         import rsl_rl.modules.actor_critic_cts as ACC
@@ -42,6 +48,12 @@ def main():
     if variant == "moe_ng_cts":
         from rsl_rl.algorithms.moe_ng_cts import MoENGCTS
         alg = MoENGCTS(model, N, H, device="cpu", **ALG)
+    elif variant == "ac_moe_cts":
+        from rsl_rl.algorithms.ac_moe_cts import ACMoECTS
+        alg = ACMoECTS(model, N, H, device="cpu", **ALG)
+    elif variant == "dual_moe_cts":
+        from rsl_rl.algorithms.dual_moe_cts import DualMoECTS
+        alg = DualMoECTS(model, N, H, device="cpu", **ALG)
     else:
         alg = MoECTS(model, N, H, device="cpu", **ALG) if variant == "moe_cts" else CTS(model, N, H, device="cpu", **ALG_CTS)
     alg.init_storage(N, T, [45], [263], [12])
@@ -56,7 +68,10 @@ def main():
         for t in range(T):
             alg.act(obs[t], priv[t], hist[t])
             alg.process_env_step(rew[t], dones[t], {"time_outs": touts[t]})
-        alg.compute_returns(priv[T], hist[T])
+        if variant in ("ac_moe_cts", "dual_moe_cts"):      # the value needs the actor's gate, hence the observations (ac_moe_cts.py:136)
+            alg.compute_returns(obs[T], priv[T], hist[T])
+        else:
+            alg.compute_returns(priv[T], hist[T])
     st = alg.storage
     save = {f"sd0_{k}": v.numpy() for k, v in sd0.items()}
     for k in ("observations", "privileged_observations", "history", "actions", "rewards", "dones", "values", "returns", "advantages",

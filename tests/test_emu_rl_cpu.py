@@ -11,14 +11,13 @@ import pytest
 import torch
 
 import emu_rl
+from cts_util import STORAGE_KEYS, make_cts
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KAT = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
        ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
 CTS_VARIANTS = ["moe_cts", "cts", "moe_ng_cts", "ac_moe_cts", "dual_moe_cts", "mcp_cts"]
-STORAGE_KEYS = ("observations", "privileged_observations", "history", "actions", "rewards", "dones", "values", "returns", "advantages",
-                "actions_log_prob", "mu", "sigma")
 
 
 def test_emulated_philox_known_answers():
@@ -89,26 +88,6 @@ def test_gae_host_logic_matches_reference_fixture(monkeypatch):
     assert torch.allclose(st.advantages, torch.from_numpy(Z["st_advantages"]), atol=2e-5)
 
 
-def make_cts(variant, Z, device):
-    """(model, algorithm, T, N) of a CTS-family variant with the fixture's initial weights (shared with tests/test_gpu_cts.py)."""
-    from golden import cts_cfg as cc
-    from go2_rl_gym_b200.rl import algorithms as A, modules as Mo
-    T, N = Z["st_rewards"].shape[:2]
-    model_cls, alg_cls, policy, alg_kw = {
-        "moe_cts": (Mo.ActorCriticMoECTS, A.MoECTS, cc.POLICY, cc.ALG),
-        "moe_ng_cts": (Mo.ActorCriticMoENGCTS, A.MoENGCTS, cc.POLICY_NG, cc.ALG),
-        "cts": (Mo.ActorCriticCTS, A.CTS, cc.POLICY_CTS, cc.ALG_CTS),
-        "ac_moe_cts": (getattr(Mo, "ActorCriticACMoECTS", None), getattr(A, "ACMoECTS", None), getattr(cc, "POLICY_AC", None), cc.ALG),
-        "dual_moe_cts": (getattr(Mo, "ActorCriticDualMoECTS", None), getattr(A, "DualMoECTS", None), getattr(cc, "POLICY_DUAL", None), cc.ALG),
-        "mcp_cts": (getattr(Mo, "ActorCriticMCPCTS", None), getattr(A, "MCPCTS", None), getattr(cc, "POLICY_MCP", None), cc.ALG_CTS),
-    }[variant]
-    model = model_cls(45, 263, 12, N, 5, **policy)
-    model.load_state_dict({k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")})
-    alg = alg_cls(model, N, 5, device=device, **alg_kw)
-    alg.init_storage(N, T, [45], [263], [12])
-    return model, alg, T, N
-
-
 def _variant_or_skip(variant):
     if not os.path.exists(os.path.join(G, f"rl_{variant}.npz")):
         pytest.skip(f"no fixture for {variant}")
@@ -165,3 +144,127 @@ def test_cts_returns_and_update_host_logic_match_reference(gemm, variant, monkey
         assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (losses, Z["losses"])
     assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
     assert _check_update(model, Z) < 2e-3
+
+
+@pytest.mark.parametrize("variant", CTS_VARIANTS)
+def test_act_inference_host_logic_matches_exported_policy(variant, monkeypatch):
+    """model.act_inference (the play / deploy path: history roll -> student encoder -> actor) against the plain-PyTorch module the exporter
+    builds from the same state dict, over a few steps so that the rolling history is exercised."""
+    Z = _variant_or_skip(variant)
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    from go2_rl_gym_b200.utils.exporter import build_export_module
+    model, alg, T, N = make_cts(variant, Z, "cpu")
+    ref = build_export_module(model)
+    ref.eval()
+    for t in range(4):
+        obs = torch.from_numpy(Z["in_obs"][t])
+        a = model.act_inference(obs)
+        with torch.no_grad():
+            b = ref(obs[0:1])[0][0]                  # the exported policy is single-env (it owns one history buffer): follow env 0
+        assert torch.allclose(a[0], b, atol=2e-5), (t, float((a[0] - b).abs().max()))
+
+
+class _Holder:
+    """The two attributes _ExpertLayer needs from a flattened model."""
+
+    def __init__(self, conv):
+        self.device = torch.device("cpu")
+        self._views = {"x.weight": conv.weight.data, "x.bias": conv.bias.data}
+        self._gviews = {"x.weight": torch.zeros_like(conv.weight), "x.bias": torch.zeros_like(conv.bias)}
+
+
+@pytest.mark.parametrize("gemm,E,H,D", [("tc", 8, 256, 32), ("simt", 8, 256, 32), ("tc", 4, 200, 6), ("tc", 8, 128, 12), ("simt", 8, 128, 1)])
+def test_expert_layer_paths_match_grouped_conv(gemm, E, H, D, monkeypatch):
+    """The block-diagonal expert layer (Conv1d, groups=E; modules/utils.py:83-88) on its three kernel paths (narrow-head, tensor-core, CUDA-core
+    wiring) against torch autograd, including the ELU' of the backbone's last activation."""
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", gemm)
+    from go2_rl_gym_b200.rl.modules.actor_critic_cts import _ExpertLayer
+    torch.manual_seed(E * H + D)
+    M = 37
+    conv = torch.nn.Conv1d(E * H, E * D, kernel_size=1, groups=E)
+    pre = torch.randn(M, E * H, requires_grad=True)
+    feat = torch.nn.functional.elu(pre)
+    out = conv(feat.unsqueeze(-1)).squeeze(-1)
+    dout = torch.randn(M, E * D)
+    out.backward(dout)
+    layer = _ExpertLayer(_Holder(conv), "x", E, H, D, M, M)
+    fpad = torch.ones(M, E * H + 4)
+    fpad[:, :E * H] = feat.detach()
+    layer.forward(fpad, fpad.shape[1], M)
+    assert torch.allclose(layer.out, out.detach(), atol=1e-5)
+    layer.backward(dout.contiguous(), fpad, fpad.shape[1], M)
+    assert torch.allclose(layer.gW.view_as(conv.weight), conv.weight.grad, atol=1e-4)
+    assert torch.allclose(layer.gb, conv.bias.grad, atol=1e-4)
+    assert torch.allclose(layer.dfeat, pre.grad, atol=1e-5)
+
+
+REF_RSL = "/root/reference/rsl_rl"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")
+@pytest.mark.parametrize("variant", ["ac_moe_cts", "dual_moe_cts"])
+def test_default_width_variants_match_the_imported_reference(variant, monkeypatch):
+    """The registered go2_ac_moe_cts / go2_dual_moe_cts widths (512-256-128, 8 experts): one act + compute_returns + update against the reference's
+    own module and algorithm run side by side on the same data (checks the operand alignment rules at the real sizes, too)."""
+    import sys
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    monkeypatch.syspath_prepend(REF_RSL)
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        monkeypatch.delitem(sys.modules, k)
+    import rsl_rl.storage.rollout_storage_cts as RS
+    from golden.cts_cfg import ALG
+    from go2_rl_gym_b200.rl import algorithms as A, modules as Mo
+    if variant == "ac_moe_cts":
+        from rsl_rl.algorithms.ac_moe_cts import ACMoECTS as RefAlg
+        from rsl_rl.modules.actor_critic_ac_moe_cts import ActorCriticACMoECTS as RefModel
+        ours_m, ours_a = Mo.ActorCriticACMoECTS, A.ACMoECTS
+    else:
+        from rsl_rl.algorithms.dual_moe_cts import DualMoECTS as RefAlg
+        from rsl_rl.modules.actor_critic_dual_moe_cts import ActorCriticDualMoECTS as RefModel
+        ours_m, ours_a = Mo.ActorCriticDualMoECTS, A.DualMoECTS
+    torch.manual_seed(0)
+    N, T, H = 16, 4, 5
+    ref = RefModel(45, 263, 12, N, H)
+    model = ours_m(45, 263, 12, N, H)
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    model.load_state_dict(ref.state_dict())
+    ralg, alg = RefAlg(ref, N, H, device="cpu", **ALG), ours_a(model, N, H, device="cpu", **ALG)
+    ralg.init_storage(N, T, [45], [263], [12]); alg.init_storage(N, T, [45], [263], [12])
+    g = torch.Generator().manual_seed(1)
+    obs, priv, hist = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g), torch.randn(T + 1, N, H * 45, generator=g)
+    rew, dones = 0.1 * torch.randn(T, N, generator=g), torch.rand(T, N, generator=g) < 0.05
+    with torch.inference_mode():
+        for t in range(T):
+            ralg.act(obs[t], priv[t], hist[t])
+            alg.act(obs[t], priv[t], hist[t])
+            assert torch.allclose(alg.storage.mu[t], ralg.transition.action_mean, atol=2e-5)
+            assert torch.allclose(alg.storage.values[t], ralg.transition.values, atol=2e-5)
+            # same actions on both sides from here on
+            for k in ("actions", "actions_log_prob"):
+                getattr(alg.storage, k)[t].copy_(getattr(ralg.transition, k).view_as(getattr(alg.storage, k)[t]))
+            ralg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+            alg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+        ralg.compute_returns(obs[T], priv[T], hist[T])
+        alg.compute_returns(obs[T], priv[T], hist[T])
+    assert torch.allclose(alg.storage.returns, ralg.storage.returns, atol=2e-5)
+    assert torch.allclose(alg.storage.advantages, ralg.storage.advantages, atol=2e-4)
+    nt, ns = alg.teacher_num_envs * T, alg.student_num_envs * T
+    tperm, sperm = torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)
+    queue = [tperm.clone(), sperm.clone()]
+    monkeypatch.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    rl = ralg.update()
+    monkeypatch.undo()
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    ol = alg.update(tperm, sperm)
+    for a, b in zip(ol, rl):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (ol, rl)
+    assert abs(alg.learning_rate - ralg.learning_rate) < 1e-9
+    num = den = 0.0
+    for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
+        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
+    assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5

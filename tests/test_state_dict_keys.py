@@ -36,3 +36,15 @@ def test_actor_critic_moe_ng_cts_keys():
     assert [k for k, _ in m.named_parameters()] == [k[4:] for k in np.load(os.path.join(G, "rl_moe_ng_cts.npz")).files if k.startswith("sd0_")]
     full = ActorCriticMoENGCTS(45, 263, 12, 32, 5, POLICY_NG["obs_no_goal_mask"])
     assert sum(p.numel() for p in full.parameters()) == 1876929          # the reference's ActorCriticMoENGCTS at GO2CfgMoENGCTS widths
+
+
+def test_actor_critic_ac_moe_and_dual_moe_cts_keys():
+    """Keys, shapes AND parameter order (the optimiser state dicts index parameters by position) of the MoE-actor variants."""
+    from go2_rl_gym_b200.rl.modules import ActorCriticACMoECTS, ActorCriticDualMoECTS
+    from golden.cts_cfg import POLICY_AC, POLICY_DUAL
+    for cls, pol, name in ((ActorCriticACMoECTS, POLICY_AC, "ac_moe_cts"), (ActorCriticDualMoECTS, POLICY_DUAL, "dual_moe_cts")):
+        z = np.load(os.path.join(G, f"rl_{name}.npz"))
+        ref = _keys(z)
+        m = cls(45, 263, 12, 32, 5, **pol)
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in ref.items()}
+        assert [k for k, _ in m.named_parameters()] == [k[4:] for k in z.files if k.startswith("sd0_")]
