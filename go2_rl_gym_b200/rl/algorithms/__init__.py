@@ -1,2 +1,2 @@
 from .ppo import PPO
-from .cts import CTS, MoECTS, MoENGCTS, ACMoECTS, DualMoECTS
+from .cts import CTS, MoECTS, MoENGCTS, ACMoECTS, DualMoECTS, MCPCTS

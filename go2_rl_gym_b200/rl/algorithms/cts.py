@@ -134,6 +134,13 @@ class CTS:
         self._latents(st.privileged_observations[t], st.history[t], nt, ns)
         self._heads(st.observations[t], st.privileged_observations[t], N)
         st.values[t].copy_(self._val[:N])
+        self._sample(t, N, A)
+        call("go2_gather_rows", ptr(st.actions[t]), A, ptr(self.inv_perm), ptr(self._actions_env), A, 0, N)   # back to env order
+        return self._actions_env
+
+    def _sample(self, t, N, A):
+        """actions ~ N(mu, std), their log-prob and the (mu, sigma) rows of transition t (cts.py:114-131)."""
+        st, m = self.storage, self.model
         if self._dev_steps is not None:      # rollout opened by begin_rollout(): the Philox step counter comes from device memory
             call("go2_sample_actions_dev", ptr(self._mu), ptr(m.std.data), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
                  N, A, self.seed, self._dev_steps.data_ptr() + 4 * t, self.env_offset)
@@ -141,8 +148,6 @@ class CTS:
             self._act_step += 1
             call("go2_sample_actions", ptr(self._mu), ptr(m.std.data), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
                  N, A, self.seed, self._act_step, self.env_offset)
-        call("go2_gather_rows", ptr(st.actions[t]), A, ptr(self.inv_perm), ptr(self._actions_env), A, 0, N)   # back to env order
-        return self._actions_env
 
     def process_env_step(self, rewards, dones, infos):
         st, t = self.storage, self.storage.step
@@ -409,3 +414,50 @@ class DualMoECTS(ACMoECTS):
     def _losses(self, log, log2, n):
         out = super()._losses(log, log2, n)
         return out[:4] + (log2[1] / n, out[4])
+
+
+class MCPCTS(CTS):
+    """MCPCTS (rsl_rl/algorithms/mcp_cts.py:40-220): CTS with the multiplicative-compositional actor of ActorCriticMCPCTS.  The action sigma is a
+    network output, so sampling, the PPO loss and its backward run on the state-dependent-sigma kernels (csrc/mcp_kernels.cu) and optimizer 1
+    holds teacher encoder + critic + actor_mcp (no std parameter, :72-78)."""
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        super().init_storage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape)
+        dev, m, A = self.device, self.model, action_shape[0]
+        rows = max(num_envs, self.mb)
+        self._sigma, self._dsigma = torch.zeros(rows, A, device=dev), torch.zeros(self.mb, A, device=dev)
+        self._ng = torch.zeros(rows, m.num_obs_no_goal, device=dev)
+        self._xng = torch.zeros(rows, _ops.pad_in(m.ng_dim), device=dev)
+
+    def _heads(self, obs, priv, M, train=False):
+        m, D = self.model, self.model.latent_dim
+        ng = m.no_goal(obs, M, self._ng)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(obs), m.num_obs, obs.stride(0), ptr(self._xa), self._xa.shape[1], 0, M)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(ng), m.num_obs_no_goal, ng.stride(0), ptr(self._xng), self._xng.shape[1], 0, M)
+        call("go2_concat2", ptr(self._lat), D, D, ptr(priv), m.num_critic_obs, priv.stride(0), ptr(self._xc), self._xc.shape[1], 0, M)
+        m.heads_forward(self._xa, self._xng, self._xc, M, self._mu, self._sigma, self._val, train=train)
+
+    def _sample(self, t, N, A):
+        st = self.storage
+        if self._dev_steps is not None:
+            step, d_step = 0, self._dev_steps.data_ptr() + 4 * t
+        else:
+            self._act_step += 1
+            step, d_step = self._act_step, 0
+        call("go2_sample_actions_sigma", ptr(self._mu), ptr(self._sigma), ptr(st.actions[t]), ptr(st.actions_log_prob[t]), ptr(st.mu[t]), ptr(st.sigma[t]),
+             N, A, self.seed, step, d_step, self.env_offset)
+
+    def _grad1(self, i):
+        st, m, sh = self.storage, self.model, self._sh
+        tm, sm, mb, A, D = self.tm, self.sm, self.mb, st.actions.shape[-1], m.latent_dim
+        ws = self.world_size
+        s = slice(i * mb, (i + 1) * mb)
+        obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True)
+        self._heads(obs_b, priv_b, mb, train=True)
+        call("go2_ppo_loss_sigma", ptr(self._mu), ptr(self._sigma), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
+             ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
+             ptr(self._dsigma), ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
+             int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
+        dlat = m.heads_backward(self._dmu, self._dsigma, self._dval, mb)
+        m.teacher_backward(dlat, dlat.shape[1], self._lat, D, tm)       # teacher rows only: student latents carry no gradient in pass 1

@@ -1,2 +1,3 @@
 from .actor_critic import ActorCritic
-from .actor_critic_cts import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS
+from .actor_critic_cts import (ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS,
+                               ActorCriticMCPCTS)

@@ -518,7 +518,8 @@ class _MoEHead:
         self.usage = torch.zeros(E, device=dev)
 
     def engines(self):
-        return [self.backbone, self.gate]
+        """Everything that keeps operand copies derived from the weights (refreshed after an optimiser step)."""
+        return [self.backbone, self.gate, self.layer]
 
     def mark_dirty(self):
         self.layer.mark_dirty()
@@ -560,7 +561,7 @@ class _GatedExpertsHead:
         self.usage = torch.zeros(E, device=dev)
 
     def engines(self):
-        return [self.backbone]
+        return [self.backbone, self.layer]
 
     def mark_dirty(self):
         self.layer.mark_dirty()
@@ -685,3 +686,130 @@ class ActorCriticDualMoECTS(ActorCriticACMoECTS):
 
     def _build_student(self, max_rows, trs):
         return _StudentMoE(self, "student_moe_encoder", self.num_obs * self.history_length, self.s_hidden, self.expert_num, self.latent_dim, max_rows, trs)
+
+
+# ---- multiplicative compositional policy (mcp_cts) ---------------------------------------------------------------------------------
+class _ActorMCPParams(nn.Module):
+    """Parameter container with the reference's key layout (actor_critic_mcp_cts.py:183-218): gating_network.{0,2,..}, experts_backbone.{0,2,..},
+    experts_hidden.0, experts_out (grouped 1x1 conv with 2 * action_dim outputs per expert: mean and log-std)."""
+
+    def __init__(self, input_dim, input_dim_no_goal, action_dim, hidden_dims, expert_num, expert_hidden_dim):
+        super().__init__()
+        layers, last = [], input_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(last, h), nn.ELU()]
+            last = h
+        layers += [nn.Linear(last, expert_num), nn.Sigmoid()]
+        self.gating_network = nn.Sequential(*layers)
+        layers, last = [], input_dim_no_goal
+        for h in hidden_dims:
+            layers += [nn.Linear(last, h), nn.ELU()]
+            last = h
+        self.experts_backbone = nn.Sequential(*layers)
+        self.experts_hidden = nn.Sequential(nn.Linear(last, expert_num * expert_hidden_dim), nn.ELU())
+        self.experts_out = nn.Conv1d(expert_num * expert_hidden_dim, expert_num * action_dim * 2, kernel_size=1, groups=expert_num)
+
+
+class ActorCriticMCPCTS(_CTSBase):
+    """ActorCriticMCPCTS (rsl_rl/modules/actor_critic_mcp_cts.py:19-180): CTS whose actor composes E expert Gaussians multiplicatively
+    (MCP, arXiv 1905.09808): a sigmoid gate on [latent | obs], experts on [latent | obs without the command columns], action distribution
+    N(mu, sigma) with a STATE-DEPENDENT sigma (no `std` parameter).  Same constructor arguments and state_dict keys."""
+    mcp_head = True
+    EXPERT_HIDDEN = 256          # ActorMCP's expert_hidden_dim default; ActorCriticMCPCTS never overrides it (:94-101)
+
+    def __init__(self, num_obs, num_critic_obs, num_actions, num_envs, history_length, obs_no_goal_mask, actor_hidden_dims=[512, 256],
+                 critic_hidden_dims=[512, 256, 128], teacher_encoder_hidden_dims=[512, 256], student_encoder_hidden_dims=[512, 256],
+                 student_expert_num=8, activation='elu', latent_dim=32, norm_type='l2norm', **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        if activation != 'elu' or norm_type != 'l2norm':
+            raise NotImplementedError("fused epilogues implement ELU / L2Norm (the go2_mcp_cts configuration)")
+        super().__init__()
+        self.num_obs, self.num_critic_obs, self.num_actions = num_obs, num_critic_obs, num_actions
+        self.history_length, self.latent_dim, self.expert_num = history_length, latent_dim, student_expert_num
+        self.register_buffer("obs_no_goal_mask", torch.tensor(obs_no_goal_mask, dtype=torch.bool), persistent=False)
+        self.num_obs_no_goal = int(self.obs_no_goal_mask.sum())
+        self.register_buffer("history", torch.zeros((num_envs, history_length, num_obs)), persistent=False)
+        self.t_dims = [num_critic_obs, *teacher_encoder_hidden_dims, latent_dim]
+        self.s_dims = [num_obs * history_length, *student_encoder_hidden_dims, latent_dim]
+        self.a_hidden = list(actor_hidden_dims)
+        self.a_dims = [latent_dim + num_obs, *actor_hidden_dims, num_actions]
+        self.ng_dim = latent_dim + self.num_obs_no_goal
+        self.c_dims = [latent_dim + num_critic_obs, *critic_hidden_dims, 1]
+        self.teacher_encoder = nn.Sequential(*_seq_mlp(self.t_dims), L2Norm())
+        self.student_encoder = nn.Sequential(*_seq_mlp(self.s_dims), L2Norm())
+        self.actor_mcp = _ActorMCPParams(self.a_dims[0], self.ng_dim, num_actions, self.a_hidden, student_expert_num, self.EXPERT_HIDDEN)
+        self.critic = nn.Sequential(*_seq_mlp(self.c_dims))
+        self._ng_cols = torch.nonzero(self.obs_no_goal_mask).flatten()
+
+    def _segments(self):
+        names = [k for k, _ in self.named_parameters()]
+        seg1 = [k for k in names if k.startswith("teacher_encoder.")] + [k for k in names if k.startswith("critic.")] + \
+               [k for k in names if k.startswith("actor_mcp.")]
+        seg2 = [k for k in names if k.startswith("student_encoder.")]
+        return seg1, seg2
+
+    def _build_engines(self, dev, max_rows, tr1, trt, trs):
+        E, A, H, nh = self.expert_num, self.num_actions, self.EXPERT_HIDDEN, len(self.a_hidden)
+        self.teacher_engine = self._engine(_linear_names("teacher_encoder", len(self.t_dims) - 1), self.t_dims, max_rows, max(trt, trs))
+        self.critic_engine = self._engine(_linear_names("critic", len(self.c_dims) - 1), self.c_dims, max_rows, tr1)
+        self.gate_engine = self._engine(_linear_names("actor_mcp.gating_network", nh + 1), [self.a_dims[0], *self.a_hidden, E], max_rows, tr1, need_dx=True)
+        self.backbone_engine = self._engine(_linear_names("actor_mcp.experts_backbone", nh) + ["actor_mcp.experts_hidden.0"],
+                                            [self.ng_dim, *self.a_hidden, E * H], max_rows, tr1, last_act=True, need_dx=True)
+        self.layer = _ExpertLayer(self, "actor_mcp.experts_out", E, H, 2 * A, max_rows, tr1)
+        self.student = _StudentMLP(self, _linear_names("student_encoder", len(self.s_dims) - 1), self.s_dims, max_rows, trs)
+        ActorCriticMoECTS._common_buffers(self, dev, max_rows, max(trt, trs))
+        tr = max(tr1, 1)
+        z = lambda *s: torch.zeros(*s, device=dev)
+        self.logits, self.gates = z(max_rows, E), z(max_rows, E)
+        self.dlogits, self.deo, self._dlat = z(tr, E), z(tr, E * 2 * A), z(tr, self.latent_dim)
+        self._ng_cols = self._ng_cols.to(dev)
+        self._inf_ng = z(max_rows, self.num_obs_no_goal)
+        self._inf_xng = z(max_rows, _ops.pad_in(self.ng_dim))
+        self._inf_sigma = z(max_rows, A)
+
+    def pass1_engines(self):
+        return [self.teacher_engine, self.critic_engine, self.gate_engine, self.backbone_engine, self.layer]
+
+    def mark_dirty(self):
+        super().mark_dirty()
+        self.layer.mark_dirty()
+
+    def heads_forward(self, xa, xng, xc, M, mu, sigma, val, train=False):
+        """mu, sigma [M, A] and val [M, 1] from the padded [latent | obs], [latent | obs without commands], [latent | privileged obs] rows."""
+        E, A = self.expert_num, self.num_actions
+        self.gate_engine.forward(xa, xa.shape[1], M, self.logits[:M], E, train=train, x_ones=xa.shape[1] > self.a_dims[0])
+        self.backbone_engine.forward(xng, xng.shape[1], M, train=train, x_ones=xng.shape[1] > self.ng_dim)
+        self.layer.forward(self.backbone_engine.out, self.backbone_engine.ld_out, M)
+        call("go2_mcp_compose_forward", ptr(self.layer.out), ptr(self.logits), ptr(self.gates), ptr(mu), ptr(sigma), M, E, A)
+        if val is not None:
+            self.critic_engine.forward(xc, xc.shape[1], M, val[:M], 1, train=train, x_ones=xc.shape[1] > self.c_dims[0])
+
+    def heads_backward(self, dmu, dsigma, dval, M):
+        """-> [M, latent_dim]: d loss / d latent through the gate AND the experts' backbone (the critic's input latent is detached, :178)."""
+        E, A, D = self.expert_num, self.num_actions, self.latent_dim
+        call("go2_mcp_compose_backward", ptr(dmu), ptr(dsigma), ptr(self.layer.out), ptr(self.gates), ptr(self.deo), ptr(self.dlogits), M, E, A)
+        self.layer.backward(self.deo, self.backbone_engine.out, self.backbone_engine.ld_out, M)
+        self.backbone_engine.backward(self.layer.dfeat, E * self.EXPERT_HIDDEN)
+        self.gate_engine.backward(self.dlogits, E)
+        self.critic_engine.backward(dval, 1)
+        torch.add(self.gate_engine.dx[:M, :D], self.backbone_engine.dx[:M, :D], out=self._dlat[:M])
+        return self._dlat
+
+    def no_goal(self, obs, M, out):
+        """out[M, n_ng] = obs[:, obs_no_goal_mask]  (actor_critic_mcp_cts.py:156)"""
+        torch.index_select(obs[:M], 1, self._ng_cols, out=out[:M])
+        return out
+
+    def act_inference(self, obs):
+        """Student policy, mean action (actor_critic_mcp_cts.py:166-173)."""
+        N, D = obs.shape[0], self.latent_dim
+        call("go2_history_update", ptr(self.history), ptr(obs.contiguous()), 0, N, self.history_length, self.num_obs)
+        lat = self._inf_lat[:N]
+        self.student.forward(self.history.view(N, -1), N, lat)
+        xa, xng, ng = self._inf_xa[:N], self._inf_xng[:N], self.no_goal(obs, N, self._inf_ng)
+        call("go2_concat2", ptr(lat), D, D, ptr(obs), self.num_obs, obs.shape[1], ptr(xa), xa.shape[1], 0, N)
+        call("go2_concat2", ptr(lat), D, D, ptr(ng), self.num_obs_no_goal, ng.shape[1], ptr(xng), xng.shape[1], 0, N)
+        out = self._inf_mu[:N]
+        self.heads_forward(xa, xng, None, N, out, self._inf_sigma, None)
+        return out.clone()

@@ -11,8 +11,9 @@ import torch
 import yaml
 
 from .. import _ops
-from ..algorithms import CTS, MoECTS, MoENGCTS, ACMoECTS, DualMoECTS
-from ..modules import ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS
+from ..algorithms import CTS, MoECTS, MoENGCTS, ACMoECTS, DualMoECTS, MCPCTS
+from ..modules import (ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS,
+                       ActorCriticMCPCTS)
 from ...utils.cfg_dict import class_to_dict
 from .on_policy_runner import SummaryWriter
 
@@ -25,11 +26,11 @@ class OnPolicyRunnerCTS:
         self.history_length = history_length
         num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
         model_class = {"ActorCriticCTS": ActorCriticCTS, "ActorCriticMoECTS": ActorCriticMoECTS, "ActorCriticMoENGCTS": ActorCriticMoENGCTS,
-                       "ActorCriticACMoECTS": ActorCriticACMoECTS, "ActorCriticDualMoECTS": ActorCriticDualMoECTS}.get(self.cfg["policy_class_name"])
-        if model_class is None:
-            raise NotImplementedError(f"policy class {self.cfg['policy_class_name']} is not on the kernel path yet (DESIGN.md section 8)")
+                       "ActorCriticACMoECTS": ActorCriticACMoECTS, "ActorCriticDualMoECTS": ActorCriticDualMoECTS,
+                       "ActorCriticMCPCTS": ActorCriticMCPCTS}[self.cfg["policy_class_name"]]
         model = model_class(self.env.num_obs, num_critic_obs, self.env.num_actions, self.env.num_envs, history_length, **self.policy_cfg)
-        alg_class = {"CTS": CTS, "MoECTS": MoECTS, "MoENGCTS": MoENGCTS, "ACMoECTS": ACMoECTS, "DualMoECTS": DualMoECTS}[self.cfg["algorithm_class_name"]]
+        alg_class = {"CTS": CTS, "MoECTS": MoECTS, "MoENGCTS": MoENGCTS, "ACMoECTS": ACMoECTS, "DualMoECTS": DualMoECTS,
+                     "MCPCTS": MCPCTS}[self.cfg["algorithm_class_name"]]
         # the value of the MoE-actor variants needs the actor's gate, hence the observations (on_policy_runner_cts.py:182-185)
         self._returns_need_obs = self.cfg["algorithm_class_name"] in ("ACMoECTS", "DualMoECTS")
         off = env._A.env_offset if hasattr(env, "_A") else 0
@@ -160,7 +161,8 @@ class OnPolicyRunnerCTS:
         self.tot_time += locs['collection_time'] + locs['learn_time']
         names = ["value_function", "surrogate", "entropy", "latent", "load_balance", "actor_load_balance"]      # on_policy_runner_cts.py:227-237
         fps = int(self.num_steps_per_env * self.env.num_envs / (locs['collection_time'] + locs['learn_time']))
-        mean_std = self.alg.model.std.mean()
+        std = getattr(self.alg.model, "std", None)       # the MCP policy has no std parameter (on_policy_runner_cts.py:226-227): log the last batch's mean sigma
+        mean_std = std.mean() if std is not None else self.alg._sigma.mean()
         ep_string = ''
         if locs['ep_infos']:
             for key in locs['ep_infos'][0]:

@@ -276,6 +276,25 @@ int go2_cts_log(const float* acc, const float* usage, float* log, long count, in
 int go2_history_update(float* history, const float* obs, const uint8_t* dones, long n, int H, int d, void* stream);
 int go2_gather_u8(const uint8_t* src, const int64_t* perm, uint8_t* out, long n, void* stream);
 
+/* ---- Multiplicative-compositional-policy actor head (csrc/mcp_kernels.cu; go2_mcp_cts) ------------------------------------------ */
+/* ActorMCP.forward (rsl_rl/modules/actor_critic_mcp_cts.py:220-247).  expert_out [n, E*2A]: expert e = [mu_e (A) | log_std_e (A)];
+ * gates = sigmoid(logits [n,E]); var_e = exp(2 clamp(log_std_e, -5, 2)) + 1e-9; sigma^2 = 1 / (sum_e gates_e / var_e + 1e-9);
+ * mu = sigma^2 sum_e gates_e mu_e / var_e.  All matrices dense.  E <= 16, A <= 16. */
+int go2_mcp_compose_forward(const float* expert_out, const float* logits, float* gates, float* mu, float* sigma, long n, int E, int A, void* stream);
+/* its backward: (d loss / d mu, d loss / d sigma) [n,A] -> d loss / d expert_out [n, E*2A], d loss / d logits [n,E] (through the sigmoid) */
+int go2_mcp_compose_backward(const float* dmu, const float* dsigma, const float* expert_out, const float* gates, float* dexpert_out, float* dlogits, long n,
+                             int E, int A, void* stream);
+/* go2_sample_actions / go2_sample_actions_dev for a state-dependent sigma [N,A] (Normal(mean, std), actor_critic_mcp_cts.py:146-149);
+ * the step counter is read from d_step when it is not NULL.  Same Philox draws as go2_sample_actions. */
+int go2_sample_actions_sigma(const float* mu, const float* sigma, float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A, uint64_t seed,
+                             uint32_t step, const uint32_t* d_step, int env_offset, void* stream);
+/* go2_ppo_loss for a state-dependent sigma [M,A] (rsl_rl/algorithms/mcp_cts.py:133-181): d loss / d sigma goes to dsigma [M,A] (entropy term
+ * included); scal[0..3] and scal[19] as in go2_ppo_loss, scal[4..18] = 0 */
+int go2_ppo_loss_sigma(const float* mu, const float* sigma, const float* value, const float* actions, const float* old_logp, const float* adv,
+                       const float* target_values, const float* returns, const float* old_mu, const float* old_sigma, float* dmu, float* dsigma,
+                       float* dvalue, float* scal, int M, int A, float clip, float value_coef, float entropy_coef, int use_clipped_value_loss,
+                       float inv_count, int split, float inv_count_a, float inv_count_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

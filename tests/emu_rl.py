@@ -467,6 +467,31 @@ def go2_history_update(history, obs, dones, n, H, d, stream):
     return 0
 
 
+_mcp = None
+
+
+def _kernel_source_entry(name):
+    """Entry points whose row arithmetic is the KERNEL'S OWN SOURCE compiled with g++ (tests/emu/emu_mcp.cpp over csrc/mcp_core.cuh)."""
+    global _mcp
+    if _mcp is None:
+        import os
+        import subprocess
+        d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+        subprocess.check_call(["make", "-C", d, "-s"])
+        _mcp = C.CDLL(os.path.join(d, "libgo2emu_mcp.so"))
+    fn = getattr(_mcp, name, None)
+    if fn is None:
+        return None
+    from go2_rl_gym_b200.rl._ops import _SIGS
+    fn.argtypes, fn.restype = _SIGS[name], C.c_int
+
+    def checked(*args):
+        if fn(*args) != 0:
+            raise EmuError(f"{name}: argument check failed")
+        return 0
+    return checked
+
+
 class _FakeLib:
     """Attribute access like a ctypes CDLL; unknown entry points fail loudly."""
 
@@ -474,6 +499,8 @@ class _FakeLib:
 
     def __getattr__(self, name):
         fn = globals().get(name)
+        if fn is None and name.startswith("go2_"):
+            fn = _kernel_source_entry(name)
         if fn is None or not name.startswith("go2_"):
             raise AttributeError(f"emu_rl: {name} is not emulated")
 

@@ -16,3 +16,6 @@ POLICY_NG = dict(obs_no_goal_mask=NO_GOAL_MASK, actor_hidden_dims=[64, 32, 16], 
 POLICY_AC = dict(actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16], teacher_encoder_hidden_dims=[64, 32],
                  student_encoder_hidden_dims=[64, 32], expert_num=8, activation="elu", init_noise_std=1.0, latent_dim=32, norm_type="l2norm")
 POLICY_DUAL = dict(POLICY_AC, student_encoder_hidden_dims=[64, 32, 32])
+# multiplicative compositional actor (LeggedRobotCfgMCPCTS, legged_robot_config.py:373-380; GO2CfgMCPCTS go2_config.py:245-254)
+POLICY_MCP = dict(obs_no_goal_mask=NO_GOAL_MASK, actor_hidden_dims=[64, 32], critic_hidden_dims=[64, 32, 16], teacher_encoder_hidden_dims=[64, 32],
+                  student_encoder_hidden_dims=[64, 32], student_expert_num=8, activation="elu", latent_dim=32, norm_type="l2norm")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate tests/golden/rl_moe_cts.npz from the REFERENCE's rsl_rl (ActorCriticMoECTS + MoECTS + RolloutStorageCTS, imported
 unmodified from /root/reference/rsl_rl): a seeded synthetic rollout through act / process_env_step / compute_returns and one
-update() with injected teacher / student permutations.  `--variant moe_ng_cts` does the same for ActorCriticMoENGCTS + MoENGCTS (-> rl_moe_ng_cts.npz), `--variant ac_moe_cts` / `dual_moe_cts` for ActorCriticACMoECTS + ACMoECTS / ActorCriticDualMoECTS + DualMoECTS, `--variant cts` for ActorCriticCTS + CTS (-> rl_cts.npz; the
+update() with injected teacher / student permutations.  `--variant moe_ng_cts` does the same for ActorCriticMoENGCTS + MoENGCTS (-> rl_moe_ng_cts.npz), `--variant mcp_cts` for ActorCriticMCPCTS + MCPCTS, `--variant ac_moe_cts` / `dual_moe_cts` for ActorCriticACMoECTS + ACMoECTS / ActorCriticDualMoECTS + DualMoECTS, `--variant cts` for ActorCriticCTS + CTS (-> rl_cts.npz; the
 reference allocates that module's history on 'cuda' at construction, actor_critic_cts.py:48, so torch.zeros is wrapped to drop the
 device while the module is built).  Build container only.  Usage (from /tmp): python /root/repo/tests/golden/make_golden_cts.py [--variant cts]"""
 import os
@@ -17,7 +17,7 @@ sys.path[:0] = ["/root/reference/rsl_rl", HERE]
 from rsl_rl.algorithms.moe_cts import MoECTS  # noqa: E402
 from rsl_rl.modules.actor_critic_moe_cts import ActorCriticMoECTS  # noqa: E402
 import rsl_rl.storage.rollout_storage_cts as RS  # noqa: E402
-from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_AC, POLICY_CTS, POLICY_DUAL, POLICY_NG  # noqa: E402
+from cts_cfg import ALG, ALG_CTS, POLICY, POLICY_AC, POLICY_CTS, POLICY_DUAL, POLICY_MCP, POLICY_NG  # noqa: E402
 
 
 def main():
@@ -32,6 +32,9 @@ def main():
     elif variant == "ac_moe_cts":     # MoE actor, value experts weighted by the actor's gate (actor_critic_ac_moe_cts.py)
         from rsl_rl.modules.actor_critic_ac_moe_cts import ActorCriticACMoECTS
         model = ActorCriticACMoECTS(45, 263, 12, N, H, **POLICY_AC)
+    elif variant == "mcp_cts":        # multiplicative compositional actor with a state-dependent sigma (actor_critic_mcp_cts.py)
+        from rsl_rl.modules.actor_critic_mcp_cts import ActorCriticMCPCTS
+        model = ActorCriticMCPCTS(45, 263, 12, N, H, **POLICY_MCP)
     elif variant == "dual_moe_cts":   # the same with the MoE student encoder (actor_critic_dual_moe_cts.py)
         from rsl_rl.modules.actor_critic_dual_moe_cts import ActorCriticDualMoECTS
         model = ActorCriticDualMoECTS(45, 263, 12, N, H, **POLICY_DUAL)
@@ -51,6 +54,9 @@ def main():
     elif variant == "ac_moe_cts":
         from rsl_rl.algorithms.ac_moe_cts import ACMoECTS
         alg = ACMoECTS(model, N, H, device="cpu", **ALG)
+    elif variant == "mcp_cts":
+        from rsl_rl.algorithms.mcp_cts import MCPCTS
+        alg = MCPCTS(model, N, H, device="cpu", **ALG_CTS)
     elif variant == "dual_moe_cts":
         from rsl_rl.algorithms.dual_moe_cts import DualMoECTS
         alg = DualMoECTS(model, N, H, device="cpu", **ALG)

@@ -46,7 +46,7 @@ def _check_update(model, Z, strict=True):
         num += float(((v - o) - (r - o)).pow(2).sum()); den += float((r - o).pow(2).sum())
         if strict:      # Adam divides by sqrt(v): a handful of near-zero-gradient elements amplify summation-order differences
             e = (v - r).abs()
-            assert float((e > 3e-5 + 1e-3 * r.abs()).float().mean()) <= 1e-3 and float(e.max()) < 5e-4, (k, float(e.max()))
+            assert int((e > 3e-5 + 1e-3 * r.abs()).sum()) <= max(1, e.numel() // 1000) and float(e.max()) < 5e-4, (k, float(e.max()))
     return (num / den) ** 0.5
 
 
@@ -204,10 +204,12 @@ REF_RSL = "/root/reference/rsl_rl"
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")
-@pytest.mark.parametrize("variant", ["ac_moe_cts", "dual_moe_cts"])
-def test_default_width_variants_match_the_imported_reference(variant, monkeypatch):
-    """The registered go2_ac_moe_cts / go2_dual_moe_cts widths (512-256-128, 8 experts): one act + compute_returns + update against the reference's
-    own module and algorithm run side by side on the same data (checks the operand alignment rules at the real sizes, too)."""
+@pytest.mark.parametrize("variant,policy", [("ac_moe_cts", {}), ("dual_moe_cts", {}), ("mcp_cts", {}),
+                                            ("ac_moe_cts", dict(actor_hidden_dims=[64, 32, 160], critic_hidden_dims=[64, 32, 136]))])
+def test_registered_width_variants_match_the_imported_reference(variant, policy, monkeypatch):
+    """The registered go2_ac_moe_cts / go2_dual_moe_cts / go2_mcp_cts widths (512-256-128, 8 experts) and a configuration whose experts are too
+    wide for the narrow-head kernels: act + compute_returns + update against the reference's own module and algorithm run side by side on the
+    same data (checks the operand alignment rules and the refresh of derived operands at real sizes, too)."""
     import sys
     emu_rl.install(monkeypatch)
     monkeypatch.setenv("GO2_GEMM", "tc")
@@ -215,23 +217,29 @@ def test_default_width_variants_match_the_imported_reference(variant, monkeypatc
     for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
         monkeypatch.delitem(sys.modules, k)
     import rsl_rl.storage.rollout_storage_cts as RS
-    from golden.cts_cfg import ALG
+    from golden.cts_cfg import ALG, ALG_CTS, NO_GOAL_MASK
     from go2_rl_gym_b200.rl import algorithms as A, modules as Mo
+    alg_kw, needs_obs = ALG, True
     if variant == "ac_moe_cts":
         from rsl_rl.algorithms.ac_moe_cts import ACMoECTS as RefAlg
         from rsl_rl.modules.actor_critic_ac_moe_cts import ActorCriticACMoECTS as RefModel
         ours_m, ours_a = Mo.ActorCriticACMoECTS, A.ACMoECTS
-    else:
+    elif variant == "dual_moe_cts":
         from rsl_rl.algorithms.dual_moe_cts import DualMoECTS as RefAlg
         from rsl_rl.modules.actor_critic_dual_moe_cts import ActorCriticDualMoECTS as RefModel
         ours_m, ours_a = Mo.ActorCriticDualMoECTS, A.DualMoECTS
+    else:
+        from rsl_rl.algorithms.mcp_cts import MCPCTS as RefAlg
+        from rsl_rl.modules.actor_critic_mcp_cts import ActorCriticMCPCTS as RefModel
+        ours_m, ours_a, alg_kw, needs_obs = Mo.ActorCriticMCPCTS, A.MCPCTS, ALG_CTS, False
+        policy = dict(policy, obs_no_goal_mask=NO_GOAL_MASK, actor_hidden_dims=[512, 256, 128])       # GO2CfgMCPCTS
     torch.manual_seed(0)
     N, T, H = 16, 4, 5
-    ref = RefModel(45, 263, 12, N, H)
-    model = ours_m(45, 263, 12, N, H)
+    ref = RefModel(45, 263, 12, N, H, **policy)
+    model = ours_m(45, 263, 12, N, H, **policy)
     assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
     model.load_state_dict(ref.state_dict())
-    ralg, alg = RefAlg(ref, N, H, device="cpu", **ALG), ours_a(model, N, H, device="cpu", **ALG)
+    ralg, alg = RefAlg(ref, N, H, device="cpu", **alg_kw), ours_a(model, N, H, device="cpu", **alg_kw)
     ralg.init_storage(N, T, [45], [263], [12]); alg.init_storage(N, T, [45], [263], [12])
     g = torch.Generator().manual_seed(1)
     obs, priv, hist = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g), torch.randn(T + 1, N, H * 45, generator=g)
@@ -241,25 +249,25 @@ def test_default_width_variants_match_the_imported_reference(variant, monkeypatc
             ralg.act(obs[t], priv[t], hist[t])
             alg.act(obs[t], priv[t], hist[t])
             assert torch.allclose(alg.storage.mu[t], ralg.transition.action_mean, atol=2e-5)
+            assert torch.allclose(alg.storage.sigma[t], ralg.transition.action_sigma, atol=2e-5)
             assert torch.allclose(alg.storage.values[t], ralg.transition.values, atol=2e-5)
             # same actions on both sides from here on
             for k in ("actions", "actions_log_prob"):
                 getattr(alg.storage, k)[t].copy_(getattr(ralg.transition, k).view_as(getattr(alg.storage, k)[t]))
             ralg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
             alg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
-        ralg.compute_returns(obs[T], priv[T], hist[T])
-        alg.compute_returns(obs[T], priv[T], hist[T])
+        last = (obs[T], priv[T], hist[T])
+        ralg.compute_returns(*(last if needs_obs else last[1:]))
+        alg.compute_returns(*(last if needs_obs else last[1:]))
     assert torch.allclose(alg.storage.returns, ralg.storage.returns, atol=2e-5)
     assert torch.allclose(alg.storage.advantages, ralg.storage.advantages, atol=2e-4)
     nt, ns = alg.teacher_num_envs * T, alg.student_num_envs * T
     tperm, sperm = torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)
     queue = [tperm.clone(), sperm.clone()]
-    monkeypatch.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
     sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
-    rl = ralg.update()
-    monkeypatch.undo()
-    emu_rl.install(monkeypatch)
-    monkeypatch.setenv("GO2_GEMM", "tc")
+    with monkeypatch.context() as mp:
+        mp.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
+        rl = ralg.update()
     ol = alg.update(tperm, sperm)
     for a, b in zip(ol, rl):
         assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (ol, rl)
@@ -268,3 +276,72 @@ def test_default_width_variants_match_the_imported_reference(variant, monkeypatc
     for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
         num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
     assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
+
+
+def _mcp_ref(eo, logits, E, A):
+    """ActorMCP.forward's composition (actor_critic_mcp_cts.py:229-247) in plain torch."""
+    w = torch.sigmoid(logits).unsqueeze(-1)
+    mu, log_std = torch.chunk(eo.view(-1, E, 2 * A), 2, dim=-1)
+    var = torch.exp(2 * torch.clamp(log_std, -5.0, 2.0)) + 1e-9
+    var_total = 1.0 / (torch.sum(w / var, dim=1) + 1e-9)
+    return var_total * torch.sum(w * mu / var, dim=1), torch.sqrt(var_total)
+
+
+def test_mcp_kernel_source_matches_torch_autograd(monkeypatch):
+    """csrc/mcp_core.cuh (the kernels' row arithmetic, built with g++) against torch: composition forward / backward incl. log-std values outside
+    the clamp range, the sigma-dependent PPO loss and its gradients, and the sampler's log-prob."""
+    lib = emu_rl.install(monkeypatch)
+    from go2_rl_gym_b200.rl._ops import call, ptr
+    torch.manual_seed(3)
+    n, E, A = 53, 8, 12
+    eo = torch.randn(n, E * 2 * A)
+    eo.view(n, E, 2 * A)[:, :, A:] *= 3.0                      # log-std spread beyond [-5, 2]
+    logits = torch.randn(n, E)
+    eo_r, lg_r = eo.clone().requires_grad_(), logits.clone().requires_grad_()
+    mu_r, sg_r = _mcp_ref(eo_r, lg_r, E, A)
+    gates, mu, sg = torch.empty(n, E), torch.empty(n, A), torch.empty(n, A)
+    call("go2_mcp_compose_forward", ptr(eo), ptr(logits), ptr(gates), ptr(mu), ptr(sg), n, E, A)
+    assert torch.allclose(mu, mu_r.detach(), atol=1e-5) and torch.allclose(sg, sg_r.detach(), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(gates, torch.sigmoid(logits), atol=1e-6)
+    # PPO loss with per-sample sigma vs autograd on the reference's formulas (mcp_cts.py:133-181)
+    actions = mu + sg * torch.randn(n, A)
+    old_mu, old_sigma = mu + 0.05 * sg * torch.randn(n, A), sg * (1 + 0.1 * torch.rand(n, A))
+    old_logp = torch.distributions.Normal(old_mu, old_sigma).log_prob(actions).sum(-1)
+    adv, value, tv, ret = torch.randn(n), torch.randn(n), torch.randn(n), torch.randn(n)
+    split, clip, vc, ec = 40, 0.2, 1.0, 0.01
+    value_r = value.clone().requires_grad_()
+    dist = torch.distributions.Normal(mu_r, sg_r)
+    ratio = torch.exp(dist.log_prob(actions).sum(-1) - old_logp)
+    surr = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - clip, 1 + clip))
+    vclip = tv + (value_r - tv).clamp(-clip, clip)
+    vloss = torch.max((value_r - ret).pow(2), (vclip - ret).pow(2)).mean()
+    ent = dist.entropy().sum(-1)
+    loss = surr[:split].mean() + surr[split:].mean() + vc * vloss - ec * ent.mean()
+    loss.backward()
+    dmu, dsg, dval, scal = torch.empty(n, A), torch.empty(n, A), torch.empty(n, 1), torch.empty(20)
+    call("go2_ppo_loss_sigma", ptr(mu), ptr(sg), ptr(value), ptr(actions), ptr(old_logp), ptr(adv), ptr(tv), ptr(ret), ptr(old_mu), ptr(old_sigma),
+         ptr(dmu), ptr(dsg), ptr(dval), ptr(scal), n, A, clip, vc, ec, 1, 1.0 / n, split, 1.0 / split, 1.0 / (n - split))
+    assert torch.allclose(dval.squeeze(-1), value_r.grad, atol=1e-6)
+    assert abs(float(scal[1]) / split + float(scal[19]) / (n - split) - float(surr[:split].mean() + surr[split:].mean())) < 1e-4
+    assert abs(float(scal[2]) / n - float(vloss)) < 1e-5 and abs(float(scal[3]) / n - float(ent.mean())) < 1e-4
+    kl = torch.sum(torch.log(sg / old_sigma + 1e-5) + (old_sigma ** 2 + (old_mu - mu) ** 2) / (2 * sg ** 2) - 0.5, -1)
+    assert abs(float(scal[0]) - float(kl.sum())) < 1e-3
+    deo, dlg = torch.empty(n, E * 2 * A), torch.empty(n, E)
+    call("go2_mcp_compose_backward", ptr(dmu), ptr(dsg), ptr(eo), ptr(gates), ptr(deo), ptr(dlg), n, E, A)
+    assert torch.allclose(deo, eo_r.grad, rtol=2e-3, atol=2e-6), float((deo - eo_r.grad).abs().max())
+    assert torch.allclose(dlg, lg_r.grad, rtol=2e-3, atol=2e-6), float((dlg - lg_r.grad).abs().max())
+    assert float((eo_r.grad.view(n, E, 2 * A)[:, :, A:] == 0).float().mean()) > 0.2       # clamped log-stds really occur in this sample
+    # sampler: a = mu + sigma z, log-prob of the stored action under (mu, sigma); same draws as the fixed-std sampler
+    a, lp, mo, so = torch.empty(n, A), torch.empty(n), torch.empty(n, A), torch.empty(n, A)
+    call("go2_sample_actions_sigma", ptr(mu), ptr(sg), ptr(a), ptr(lp), ptr(mo), ptr(so), n, A, 7, 3, 0, 5)
+    assert torch.allclose(lp, torch.distributions.Normal(mu, sg).log_prob(a).sum(-1), atol=2e-4)
+    assert torch.equal(mo, mu) and torch.equal(so, sg)
+    a2, ones, zeros = torch.empty(n, A), torch.ones(A), torch.zeros(n, A)
+    call("go2_sample_actions", ptr(zeros), ptr(ones), ptr(a2), ptr(lp), ptr(mo), ptr(so), n, A, 7, 3, 5)
+    assert torch.allclose(a, mu + sg * a2, atol=1e-6)
+    z = a2.flatten()
+    assert abs(float(z.mean())) < 0.15 and abs(float(z.std()) - 1.0) < 0.15
+    step = torch.tensor([3], dtype=torch.int32)
+    a3 = torch.empty(n, A)
+    call("go2_sample_actions_sigma", ptr(mu), ptr(sg), ptr(a3), ptr(lp), ptr(mo), ptr(so), n, A, 7, 0, ptr(step), 5)
+    assert torch.equal(a3, a)

@@ -48,3 +48,13 @@ def test_actor_critic_ac_moe_and_dual_moe_cts_keys():
         m = cls(45, 263, 12, 32, 5, **pol)
         assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in ref.items()}
         assert [k for k, _ in m.named_parameters()] == [k[4:] for k in z.files if k.startswith("sd0_")]
+
+
+def test_actor_critic_mcp_cts_keys():
+    from go2_rl_gym_b200.rl.modules import ActorCriticMCPCTS
+    from golden.cts_cfg import POLICY_MCP
+    z = np.load(os.path.join(G, "rl_mcp_cts.npz"))
+    m = ActorCriticMCPCTS(45, 263, 12, 32, 5, **POLICY_MCP)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in _keys(z).items()}
+    assert [k for k, _ in m.named_parameters()] == [k[4:] for k in z.files if k.startswith("sd0_")]
+    assert "std" not in m.state_dict()          # sigma is a network output (actor_critic_mcp_cts.py:236-247)
