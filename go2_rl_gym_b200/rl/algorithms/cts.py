@@ -207,12 +207,18 @@ class CTS:
                         m.mark_dirty()
         m.mark_dirty()
         n = self.num_learning_epochs * self.num_mini_batches
+        if self.world_size > 1:      # pass 2's logged means are per-rank sums (pass 1's travel in the gradient's scalar tail): one small collective per iteration
+            self._reduce_logs()
         log, log2 = self._log.tolist(), self._log2.tolist()      # the single host sync of update()
         self.learning_rate = log[3]
         st.clear()
         return self._losses(log, log2, n)
 
     _moe = False
+
+    def _reduce_logs(self):
+        dist.all_reduce(self._log2)
+        self._log2 /= self.world_size
 
     def _losses(self, log, log2, n):
         """update()'s return value: mean value / surrogate / entropy / latent loss (cts.py:280-285) + the student's load-balance loss (moe_cts.py:229-234)."""
@@ -400,6 +406,11 @@ class ACMoECTS(CTS):
         m.teacher_backward(dx, dx.shape[1], self._lat, D, tm)           # teacher rows only: student latents carry no gradient in pass 1
         m._gviews["std"].copy_(self._scal[4:4 + A])
         call("go2_cts_log", ptr(self._zero1), ptr(m.actor_head.usage), ptr(self._log3), 1, m.actor_head.E)
+
+    def _reduce_logs(self):
+        super()._reduce_logs()
+        dist.all_reduce(self._log3)
+        self._log3 /= self.world_size
 
     def _losses(self, log, log2, n):
         actor_lb = self._log3.tolist()[1] / n

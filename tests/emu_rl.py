@@ -529,3 +529,14 @@ def install(monkeypatch):
     monkeypatch.setattr(_ops, "_stream", lambda: 0)
     monkeypatch.setenv("GO2_GRAPH", "0")
     return fake
+
+
+def install_process():
+    """install() for a process that is not under pytest's monkeypatch (spawned gloo workers)."""
+    import os
+    from go2_rl_gym_b200.rl import _ops
+    fake = _FakeLib()
+    _ops.lib = lambda: fake
+    _ops._stream = lambda: 0
+    os.environ["GO2_GRAPH"] = "0"
+    return fake
