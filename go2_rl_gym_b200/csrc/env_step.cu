@@ -172,9 +172,9 @@ extern "C" {
 int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvBuffers* bufs, Go2Env** out) {
   if (!cfg || !model || !bufs || !out) return go2::set_error(1, "go2_env_create: null argument");
   if (cfg->num_envs <= 0) return go2::set_error(1, "go2_env_create: num_envs must be positive");
-  if (!GO2_RELAXED_SOLVER && (cfg->limit_relax != 0.0f || cfg->contact_relax != 1.0f))
-    return go2::set_error(2, "go2_env_create: this build of the step kernel has no relaxed solver (limit_relax must be 0, contact_relax 1); "
-                             "rebuild with -DGO2_RELAXED_SOLVER=1");
+  if (!GO2_RELAXED_SOLVER && (cfg->limit_relax != 0.0f || cfg->contact_relax != 1.0f || cfg->state_guard != 0))
+    return go2::set_error(2, "go2_env_create: this build of the step kernel has no relaxed solver / state guard (limit_relax must be 0, "
+                             "contact_relax 1, state_guard 0); rebuild with -DGO2_RELAXED_SOLVER=1");
   // the kernel bakes the Go2 topology: hip = x axis, thigh/calf = y axis, collider lanes grouped per body
   for (int j = 0; j < GO2_NUM_DOF; ++j)
     if (model->joint_axis[j] != ((j % 3 == 0) ? 0 : 1)) return go2::set_error(2, "go2_env_create: joint axes must be x,y,y per leg");

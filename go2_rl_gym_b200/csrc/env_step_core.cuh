@@ -259,7 +259,8 @@ struct WarpSmem {
   float tgt[12][2];            // joint-limit target velocities (lower, upper row)
 #if GO2_RELAXED_SOLVER
   float Dje[12];               // limit-row step limit_relax / (M^-1)_jj (relaxed solver only)
-  int pad_relaxed_[20];        // keeps the row stride at 1 mod 32 words in this build too
+  int bad;                     // state guard: this env's state went non-finite in this step (sanitised, resets)
+  int pad_relaxed_[19];        // keeps the row stride at 1 mod 32 words in this build too
 #endif
   float mu_env, rest_env;      // contact friction / restitution of this env (combined with the terrain's)
   float a0[6];
@@ -806,6 +807,13 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       V6 v0; ld6(S.v[0], v0);
       V6 d0; ld6(S.dv[0], d0);
       V3 lw = mul(R0, v0.l + d0.l), aw = mul(R0, v0.a + d0.a);
+#if GO2_RELAXED_SOLVER
+      if (C->state_guard) {   // asset.max_linear_velocity / max_angular_velocity (legged_robot_config.py:131-132)
+        const float nl = sqrtf(dot(lw, lw)), na = sqrtf(dot(aw, aw));
+        if (nl > C->max_base_lin_vel) lw = (C->max_base_lin_vel / nl) * lw;
+        if (na > C->max_base_ang_vel) aw = (C->max_base_ang_vel / na) * aw;
+      }
+#endif
       st3(S.root + 7, lw); st3(S.root + 10, aw);
       S.root[0] += dt * lw.x; S.root[1] += dt * lw.y; S.root[2] += dt * lw.z;
       float wn = sqrtf(dot(aw, aw)), th = wn * dt, hx, hy, hz, hw;  // q <- exp(aw dt / 2) * q (world-frame angular velocity)
@@ -836,6 +844,31 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
     }
   } GO2_SYNC_WARP();
 }
+
+#if GO2_RELAXED_SOLVER
+// State guard (Go2EnvConfig.state_guard): an env whose state is non-finite after the substeps restarts from its initial pose at its origin and
+// resets in this step, so that nothing non-finite reaches the observations / rewards the shared networks train on.  One WIDE phase, lane 0.
+GO2_HD void state_guard(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+  const Go2EnvConfig* C = X.cfg;
+  GO2_WIDE {
+    if (lane == 0) {
+      int bad = 0;
+      if (C->state_guard) {
+        for (int k = 0; k < 13; ++k) bad |= !(fabsf(S.root[k]) <= 3.0e38f);
+        for (int k = 0; k < GO2_NUM_DOF; ++k) bad |= !(fabsf(S.q[k]) <= 3.0e38f) | !(fabsf(S.qd[k]) <= 3.0e38f);
+        if (bad) {
+          for (int k = 0; k < 3; ++k) S.root[k] = S.env_origin[k] + C->base_init_state[k];
+          for (int k = 3; k < 7; ++k) S.root[k] = C->base_init_state[k];
+          for (int k = 7; k < 13; ++k) S.root[k] = 0.0f;
+          for (int k = 0; k < GO2_NUM_DOF; ++k) { S.q[k] = C->default_dof_pos[k]; S.qd[k] = 0.0f; S.lqd[k] = 0.0f; S.tq[k] = 0.0f; }
+          for (int b = 0; b < GO2_NUM_REPORT; ++b) { S.cf[b][0] = 0.0f; S.cf[b][1] = 0.0f; S.cf[b][2] = 0.0f; }
+        }
+      }
+      S.bad = bad;
+    }
+  } GO2_SYNC_WARP();
+}
+#endif
 
 // feet position / velocity at the current configuration (rigid_body_states refresh, legged_robot.py:109)
 GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
@@ -1097,6 +1130,9 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     physics_substep(GO2_LANE_PASS, SM, X, sub == C->decimation - 1);
   }
   GO2_COARSE_SYNC();
+#if GO2_RELAXED_SOLVER
+  state_guard(GO2_LANE_PASS, SM, X);
+#endif
   feet_kinematics(GO2_LANE_PASS, SM, X);
   // ---- post_physics_step (legged_robot.py:102-142)
   GO2_WIDE {
@@ -1168,6 +1204,9 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       int term = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
       S.tout = S.ep_len > C->max_episode_length;
       S.reset = term || S.tout;
+#if GO2_RELAXED_SOLVER
+      S.reset |= S.bad;
+#endif
     }
   } GO2_SYNC_WARP();
   GO2_WIDE {

@@ -228,6 +228,9 @@ class LeggedRobotCfg(BaseConfig):
             # convergent setting found in this round: limit_relax = 0.5, contact_relax = 0.7, limit_erp = 0.8.
             limit_relax = 0.0
             contact_relax = 1.0
+            # 1: clamp the base twist at asset.max_linear_velocity / max_angular_velocity and reset any env whose state went non-finite
+            # (include/go2_b200.h).  Needs a library built with -DGO2_RELAXED_SOLVER=1, like the two knobs above.
+            state_guard = 0
 
 
 class _TrainCfgBase(BaseConfig):

@@ -183,6 +183,8 @@ class EnvArrays:
         c.bounce_threshold = cfg.sim.physx.bounce_threshold_velocity
         c.terrain_friction, c.terrain_restitution = cfg.terrain.static_friction, cfg.terrain.restitution
         c.limit_relax, c.contact_relax = getattr(b200, "limit_relax", 0.0), getattr(b200, "contact_relax", 1.0)
+        c.state_guard = int(getattr(b200, "state_guard", 0))
+        c.max_base_lin_vel, c.max_base_ang_vel = cfg.asset.max_linear_velocity, cfg.asset.max_angular_velocity
         c.mesh_type = 0 if self.plane else 1
         c.hf_rows, c.hf_cols = hs.shape
         c.hscale, c.vscale, c.border = cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.border_size

@@ -102,6 +102,12 @@ typedef struct Go2EnvConfig {
      w / (M^-1)_jj, the exact joint-space diagonal the mobility recursion already computes (convergent for w <= 0.5).  contact_relax scales
      the contact rows' block step (1 = unchanged). */
   float limit_relax, contact_relax;
+  /* state guard (appended).  0: off (the build every measurement of round 1 was made with).  1: the base twist is clamped to the asset's
+     max_linear_velocity / max_angular_velocity after every substep (legged_robot_config.py:131-132; PhysX clamps rigid-body velocities), and an
+     env whose state (root 13, dof_pos 12, dof_vel 12) holds a non-finite value after the substeps is put into its initial pose at its origin
+     with zero velocities / torques / contact forces and RESETS in this step (reset_buf = 1, time_out_buf = 0): one diverged env can never feed
+     a NaN into the shared policy / value networks. */
+  int32_t state_guard; float max_base_lin_vel, max_base_ang_vel;
 } Go2EnvConfig;
 
 /* Per-step scalars the host derives from common_step_counter (curricula), no device sync involved. */

@@ -437,6 +437,11 @@ static void physics_substep(const Go2EnvConfig& C, const Go2Model& M, const Terr
     q[j] += dt * qd[j];
   }
   V3 lw = mul(K.Rw[0], lin(v0p)), aw = mul(K.Rw[0], ang(v0p));
+  if (C.state_guard) {   // asset.max_linear_velocity / max_angular_velocity (legged_robot_config.py:131-132)
+    const real nl = norm(lw), na = norm(aw);
+    if (nl > (real)C.max_base_lin_vel) lw = ((real)C.max_base_lin_vel / nl) * lw;
+    if (na > (real)C.max_base_ang_vel) aw = ((real)C.max_base_ang_vel / na) * aw;
+  }
   linw[0] = lw.x; linw[1] = lw.y; linw[2] = lw.z;
   angw[0] = aw.x; angw[1] = aw.y; angw[2] = aw.z;
   pos[0] += dt * lw.x; pos[1] += dt * lw.y; pos[2] += dt * lw.z;
@@ -653,6 +658,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
   std::vector<double> acc(GO2_EP_STATS, 0.0);
   std::vector<double> lvl_sum(9, 0.0), lvl_cnt(9, 0.0);
   int n_reset = 0;
+  std::vector<char> bad(N, 0);
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < N; ++e) {
     uint32_t ge = (uint32_t)(C.env_offset + e);
@@ -685,6 +691,24 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     for (int i = 0; i < 4; ++i) rs[3 + i] = (float)quat[i];
     for (int j = 0; j < GO2_NUM_DOF; ++j) { B.dof_pos[(size_t)e * GO2_NUM_DOF + j] = (float)q[j]; B.dof_vel[(size_t)e * GO2_NUM_DOF + j] = (float)qd[j]; }
     for (int b = 0; b < GO2_NUM_REPORT; ++b) for (int i = 0; i < 3; ++i) B.contact_forces[((size_t)e * GO2_NUM_REPORT + b) * 3 + i] = (float)so.contact_force[b][i];
+    bad[e] = 0;
+    if (C.state_guard) {   // Go2EnvConfig.state_guard: non-finite state -> initial pose at the origin, zero velocities / torques / contacts, forced reset
+      bool nf = false;
+      for (int i = 0; i < 13; ++i) nf |= !(std::fabs(rs[i]) <= 3.0e38f);
+      for (int j = 0; j < GO2_NUM_DOF; ++j) nf |= !(std::fabs(B.dof_pos[(size_t)e * GO2_NUM_DOF + j]) <= 3.0e38f) | !(std::fabs(B.dof_vel[(size_t)e * GO2_NUM_DOF + j]) <= 3.0e38f);
+      if (nf) {
+        bad[e] = 1;
+        for (int i = 0; i < 3; ++i) { rs[i] = B.env_origins[(size_t)e * 3 + i] + C.base_init_state[i]; pos[i] = rs[i]; }
+        for (int i = 3; i < 7; ++i) { rs[i] = C.base_init_state[i]; quat[i - 3] = rs[i]; }
+        for (int i = 7; i < 13; ++i) rs[i] = 0;
+        for (int i = 0; i < 3; ++i) lw[i] = aw[i] = 0;
+        for (int j = 0; j < GO2_NUM_DOF; ++j) {
+          size_t o = (size_t)e * GO2_NUM_DOF + j;
+          B.dof_pos[o] = C.default_dof_pos[j]; B.dof_vel[o] = 0; B.last_dof_vel[o] = 0; tq[j] = 0; q[j] = C.default_dof_pos[j]; qd[j] = 0;
+        }
+        for (int i = 0; i < GO2_NUM_REPORT * 3; ++i) B.contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = 0;
+      }
+    }
     {  // feet position / velocity at the new configuration (rigid_body_states refresh, legged_robot.py:109)
       Kin K;
       kinematics(M, pos, quat, q, K);
@@ -724,7 +748,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     const float* cf = B.contact_forces + (size_t)e * GO2_NUM_REPORT * 3;
     bool term = std::sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.0f;
     bool tout = B.episode_length_buf[e] > C.max_episode_length;
-    B.time_out_buf[e] = tout; B.reset_buf[e] = term || tout;
+    B.time_out_buf[e] = tout; B.reset_buf[e] = term || tout || bad[e];
     // compute_reward, legged_robot.py:247-274, terms in enum order
     const float* cmd = B.commands + (size_t)e * GO2_NUM_CMD;
     const float* q = B.dof_pos + (size_t)e * GO2_NUM_DOF; const float* qd = B.dof_vel + (size_t)e * GO2_NUM_DOF;

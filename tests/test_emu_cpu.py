@@ -245,3 +245,45 @@ def test_relaxed_solver_holds_joint_stops_in_free_flight(kind):
         assert w is not None and w < 0.2, (scale, w)
     legacy = run(0.05, False)
     assert legacy is None or legacy > 1.0, legacy          # the first solver: runaway joints / non-finite state
+
+
+@pytest.mark.parametrize("kind", ["oracle", "emu", "emu_packed"])
+def test_state_guard_contains_a_diverged_env(kind):
+    """sim.b200.state_guard = 1 (include/go2_b200.h): envs whose state turns non-finite restart from the initial pose and reset in the same step;
+    every output stays finite, their neighbours are untouched bit for bit, and the base twist is clamped at asset.max_*_velocity."""
+    N = 16
+    make = {"oracle": OracleEnv, "emu": lambda A: EmuEnv(A, packed=False), "emu_packed": lambda A: EmuEnv(A, packed=True)}[kind]
+
+    def run(poison):
+        cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 4
+        cfg.sim.b200.limit_relax, cfg.sim.b200.contact_relax, cfg.sim.b200.limit_erp, cfg.sim.b200.state_guard = 0.5, 0.7, 0.8, 1
+        A = EnvArrays(cfg, "cpu", seed=4)
+        env = make(A)
+        env.common_step_counter = 24 * 100
+        env.reset_all()
+        g = torch.Generator().manual_seed(1)
+        T = A.tensors
+        outs = []
+        for step in range(4):
+            if poison and step == 1:
+                T["root_states"][3, 2] = float("nan")
+                T["dof_vel"][5, 7] = float("inf")
+                T["root_states"][9, 7:10] = torch.tensor([5000.0, 0.0, 0.0])      # finite but absurd: clamped, not reset
+            env.step(0.3 * torch.randn(N, 12, generator=g))
+            outs.append({k: T[k].clone() for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "reset_buf", "time_out_buf", "root_states", "dof_pos",
+                                                   "dof_vel", "torques", "contact_forces", "episode_sums", "last_dof_vel")})
+        return outs
+
+    clean, dirty = run(False), run(True)
+    o = dirty[1]
+    assert bool(o["reset_buf"][3]) and bool(o["reset_buf"][5]) and not bool(o["time_out_buf"][3]) and not bool(o["time_out_buf"][5])
+    for step in range(1, 4):
+        for k, v in dirty[step].items():
+            assert torch.isfinite(v.float()).all(), (step, k)
+    others = [e for e in range(N) if e not in (3, 5, 9)]
+    for step in range(4):
+        for k in ("obs_buf", "rew_buf", "root_states", "dof_pos", "reset_buf"):
+            assert torch.equal(dirty[step][k][others], clean[step][k][others]), (step, k)
+    assert float(dirty[1]["root_states"][9, 7:10].norm()) <= 1000.0 * (1 + 1e-5) or bool(dirty[1]["reset_buf"][9])
+    # the restarted envs continue like any freshly reset env
+    assert float(dirty[3]["root_states"][3, 2]) > -5.0 and float(dirty[3]["dof_pos"][5].abs().max()) < 10.0
