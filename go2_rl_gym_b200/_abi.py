@@ -89,16 +89,23 @@ def library_path():
     return _LIB_PATH
 
 
-def load_library():
-    """Load libgo2b200.so (hand-written sm_100a kernels + C ABI). Raises if it has not been built."""
+_VARIANTS = {}
+
+
+def load_library(path=None):
+    """Load libgo2b200.so (hand-written sm_100a kernels + C ABI). Raises if it has not been built.
+    path: another build of the same library (e.g. libgo2b200_relaxed.so), loaded side by side with its own handle."""
     global _LIB
-    if _LIB is not None:
+    if path is None and _LIB is not None:
         return _LIB
-    if not os.path.exists(_LIB_PATH):
+    if path is not None and path in _VARIANTS:
+        return _VARIANTS[path]
+    lib_path = path or _LIB_PATH
+    if not os.path.exists(lib_path):
         raise RuntimeError(
-            f"{_LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            f"{lib_path} not found: the CUDA extension is required (no CPU fallback). "
             "Build it with: python -c 'import __graft_entry__ as g; g.build()'")
-    lib = C.CDLL(_LIB_PATH)
+    lib = C.CDLL(lib_path)
     vp = C.c_void_p
     lib.go2_env_create.argtypes = [C.POINTER(Go2EnvConfig), C.POINTER(Go2Model), C.POINTER(Go2EnvBuffers), C.POINTER(vp)]
     lib.go2_env_create.restype = C.c_int
@@ -118,7 +125,10 @@ def load_library():
     lib.go2_env_substeps.restype = C.c_int
     lib.go2_last_error.restype = C.c_char_p
     lib.go2_kernel_launch_count.restype = C.c_longlong
-    _LIB = lib
+    if path is None:
+        _LIB = lib
+    else:
+        _VARIANTS[path] = lib
     return lib
 
 

@@ -12,10 +12,10 @@ STATE = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "last_l
 
 
 class CudaEnv:
-    def __init__(self, arrays, mode=None):
+    def __init__(self, arrays, mode=None, lib_path=None):
         assert arrays.device.type == "cuda"
         self.A = arrays
-        self.lib = _abi.load_library()
+        self.lib = _abi.load_library(lib_path)
         self.h = C.c_void_p()
         _abi.check(self.lib.go2_env_create(C.byref(arrays.config), C.byref(arrays.model), C.byref(arrays.buffers), C.byref(self.h)), self.lib)
         self.common_step_counter = 0

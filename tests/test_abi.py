@@ -8,10 +8,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_library_exports_header_symbols():
+@pytest.mark.parametrize("name", ["libgo2b200.so", "libgo2b200_relaxed.so"])
+def test_library_exports_header_symbols(name):
     import __graft_entry__ as ge
     ge.build()
-    lib = ctypes.CDLL(os.path.join(ROOT, "go2_rl_gym_b200", "libgo2b200.so"))
+    lib = ctypes.CDLL(os.path.join(ROOT, "go2_rl_gym_b200", name))
     hdr = open(os.path.join(ROOT, "include", "go2_b200.h")).read()
     names = sorted(set(re.findall(r"\b(go2_[a-z0-9_]+)\s*\(", hdr)))
     assert len(names) >= 8
@@ -55,3 +56,11 @@ def test_create_rejects_solver_settings_the_build_does_not_carry():
     h = ctypes.c_void_p()
     rc = lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
     assert rc != 0 and b"relaxed solver" in lib.go2_last_error()
+    cfg.limit_relax, cfg.contact_relax, cfg.state_guard = 0.0, 1.0, 1
+    rc = lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
+    assert rc != 0 and b"state guard" in lib.go2_last_error()
+    # the second build (libgo2b200_relaxed.so) accepts them: it gets past this check to the topology check of the (empty) model
+    relaxed = _abi.load_library(os.path.join(ROOT, "go2_rl_gym_b200", "libgo2b200_relaxed.so"))
+    cfg.limit_relax, cfg.contact_relax = 0.5, 0.7
+    rc = relaxed.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
+    assert rc != 0 and b"joint axes" in relaxed.go2_last_error()
