@@ -165,6 +165,33 @@ def test_act_inference_host_logic_matches_exported_policy(variant, monkeypatch):
         assert torch.allclose(a[0], b, atol=2e-5), (t, float((a[0] - b).abs().max()))
 
 
+@pytest.mark.parametrize("variant", CTS_VARIANTS)
+def test_tf32_operand_noise_stays_within_the_gpu_bars(variant, monkeypatch):
+    """GO2_EMU_TF32=1 truncates the operands of the emulated tensor-core entry points to tf32 (10 mantissa bits), the arithmetic tcgen05 kind::tf32
+    applies to fp32 data: the fixture comparisons must then stay inside the bars the GPU tests use for GO2_GEMM=tc (act 3e-3, losses 3e-3, update 5e-2
+    for the hardware-verified variants, tests/test_gpu_cts.py; TC_UPDATE_BAR for the new ones, tests/test_gpu_x_moe_heads.py)."""
+    Z = _variant_or_skip(variant)
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    monkeypatch.setenv("GO2_EMU_TF32", "1")
+    t = lambda k: torch.from_numpy(Z[k])
+    model, alg, T, N = make_cts(variant, Z, "cpu")
+    alg.act(t("in_obs")[0], t("in_priv")[0], t("in_hist")[0])
+    st = alg.storage
+    for k in ("mu", "sigma", "values"):
+        assert torch.allclose(getattr(st, k)[0], t("st_" + k)[0], atol=3e-3), k
+    assert float((st.mu[0] - t("st_mu")[0]).abs().max()) > 1e-6            # the truncation is really applied
+    model, alg, T, N = make_cts(variant, Z, "cpu")
+    for k in STORAGE_KEYS:
+        getattr(alg.storage, k).copy_(t("st_" + k))
+    losses = alg.update(t("tperm"), t("sperm"))
+    for a, b in zip(losses, Z["losses"]):
+        assert abs(a - b) < 3e-3 * max(1.0, abs(b)), (losses, Z["losses"])
+    assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
+    rel = _check_update(model, Z, strict=False)
+    assert rel < (5e-2 if variant in ("moe_cts", "cts", "moe_ng_cts") else 0.15), rel
+
+
 class _Holder:
     """The two attributes _ExpertLayer needs from a flattened model."""
 
