@@ -98,3 +98,24 @@ def test_variant_runner_two_iterations(task, tmp_path):
         assert torch.equal(a, b), k
     a = runner.get_inference_policy()(env.get_observations())
     assert a.shape == (256, 12) and torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("task", ["go2_" + v for v in VARIANTS])
+def test_variant_play_loop_and_policy_export(task, tmp_path):
+    """legged_gym/scripts/play.py for the registered task (see tests/test_gpu_rl.py::test_play_loop_and_policy_export)."""
+    import importlib.util
+    import math
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("play_script", os.path.join(root, "legged_gym", "scripts", "play.py"))
+    play_script = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(play_script)
+    from go2_rl_gym_b200.envs import task_registry
+    from go2_rl_gym_b200.utils import get_args
+    args = get_args(["--task", task, "--num_envs", "64", "--headless"])
+    env, _ = task_registry.make_env(task, args)
+    runner, _ = task_registry.make_alg_runner(env, task, args, log_root=None)
+    stats = play_script.play(get_args(["--task", task, "--num_envs", "49", "--headless"]), num_steps=30, runner=runner, export_dir=str(tmp_path))
+    assert stats["steps"] == 30 and all(math.isfinite(v) for v in stats.values())
+    out = torch.jit.load(os.path.join(tmp_path, "policy.pt"))(torch.randn(1, 45))
+    out = out[0] if isinstance(out, tuple) else out
+    assert out.shape == (1, 12) and torch.isfinite(out).all()
