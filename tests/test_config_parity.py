@@ -51,10 +51,10 @@ def test_config_trees_equal_the_reference():
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "legged_gym")), reason="needs the reference tree (runs in the build container)")
-def test_registered_tasks_are_a_subset_of_the_reference():
+def test_registered_tasks_equal_the_reference():
     src = open(os.path.join(REF, "legged_gym", "envs", "__init__.py")).read()
     import re
     ref_tasks = set(re.findall(r'task_registry\.register\(\s*"([a-z0-9_]+)"', src))
     from go2_rl_gym_b200.envs import task_registry
     mine = set(task_registry.task_classes)
-    assert mine <= ref_tasks and {"go2", "go2_cts", "go2_moe_cts", "go2_moe_ng_cts"} <= mine, (mine, ref_tasks)
+    assert mine == ref_tasks and len(mine) == 7, (mine, ref_tasks)       # legged_gym/envs/__init__.py:9-15
