@@ -54,6 +54,7 @@ class Go2EnvConfig(C.Structure):
         ("num_base_height_points", f32), ("base_init_state", f32 * 13),
         ("limit_relax", f32), ("contact_relax", f32),
         ("state_guard", i32), ("max_base_lin_vel", f32), ("max_base_ang_vel", f32),
+        ("control_type", i32), ("only_positive_rewards", i32),
     ]
 
 

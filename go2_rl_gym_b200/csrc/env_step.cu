@@ -175,6 +175,10 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
   if (!GO2_RELAXED_SOLVER && (cfg->limit_relax != 0.0f || cfg->contact_relax != 1.0f || cfg->state_guard != 0))
     return go2::set_error(2, "go2_env_create: this build of the step kernel has no relaxed solver / state guard (limit_relax must be 0, "
                              "contact_relax 1, state_guard 0); rebuild with -DGO2_RELAXED_SOLVER=1");
+  if (!GO2_RELAXED_SOLVER && (cfg->control_type != 0 || cfg->only_positive_rewards != 0))
+    return go2::set_error(2, "go2_env_create: control_type 'V' / 'T' and only_positive_rewards need the build with -DGO2_RELAXED_SOLVER=1 "
+                             "(libgo2b200_relaxed.so)");
+  if (cfg->control_type < 0 || cfg->control_type > 2) return go2::set_error(2, "go2_env_create: control_type must be 0 (P), 1 (V) or 2 (T)");
   // the kernel bakes the Go2 topology: hip = x axis, thigh/calf = y axis, collider lanes grouped per body
   for (int j = 0; j < GO2_NUM_DOF; ++j)
     if (model->joint_axis[j] != ((j % 3 == 0) ? 0 : 1)) return go2::set_error(2, "go2_env_create: joint axes must be x,y,y per leg");

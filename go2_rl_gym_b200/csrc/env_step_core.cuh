@@ -1108,6 +1108,10 @@ GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, int s
     if (lane < GO2_NUM_DOF) {
       float a_in = (C->randomize_action_delay && sub < S.delay_start) ? S.lact[lane] : S.act[lane];
       float t = L.kp * (a_in * C->action_scale + C->default_dof_pos[lane] - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
+#if GO2_RELAXED_SOLVER
+      if (C->control_type == 1) t = L.kp * (a_in * C->action_scale - S.qd[lane]) - L.kd * (S.qd[lane] - S.lqd[lane]) / C->sim_dt;   // 'V', legged_robot.py:612-613
+      else if (C->control_type == 2) t = a_in * C->action_scale;                                                                  // 'T', :614-615
+#endif
       float lim = M->effort[lane];
       t = fminf(fmaxf(t, -lim), lim);
       if (C->randomize_motor_strength) t *= L.mstr;
@@ -1253,6 +1257,9 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
         rew += rk;
         S.termv[k] = rk;
       }
+#if GO2_RELAXED_SOLVER
+      if (C->only_positive_rewards) rew = fmaxf(rew, 0.0f);     // the episode sums keep the unclipped terms (legged_robot.py:263-267)
+#endif
       S.rew = rew;
     }
   } GO2_SYNC_WARP();

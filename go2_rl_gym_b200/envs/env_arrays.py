@@ -74,7 +74,9 @@ class EnvArrays:
             hs = np.ascontiguousarray(t.heightsamples, dtype=np.int16)
             max_init = cfg.terrain.max_init_terrain_level if cfg.terrain.curriculum else cfg.terrain.num_rows - 1
             levels = np.fmod(gidx, max_init + 1).astype(np.int32)
-            types = np.floor(gidx / (NG / cfg.terrain.num_cols)).astype(np.int32)
+            # torch's own arithmetic (legged_robot.py:1072): int64 arange / python float is a FLOAT32 division, which lands just below the
+            # integer at i = k NG / 4 (e.g. env 1024 of 4096 -> type 4, not 5); a float64 floor would differ from the reference there
+            types = torch.div(torch.arange(NG), (NG / cfg.terrain.num_cols), rounding_mode="floor").to(torch.long).numpy()[gidx].astype(np.int32)
             cols2id = np.asarray(t.cols2id if len(t.cols2id) else [8] * cfg.terrain.num_cols, dtype=np.int32)
             ids = cols2id[types]
             origins_grid = t.env_origins.astype(np.float32)
@@ -152,8 +154,9 @@ class EnvArrays:
         c.num_envs, c.env_offset = N, self.env_offset
         c.seed_lo, c.seed_hi = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
         c.sim_dt, c.decimation, c.gravity_z = cfg.sim.dt, cfg.control.decimation, cfg.sim.gravity[2]
-        if cfg.control.control_type != "P":
-            raise NotImplementedError("only control_type 'P' is on the hot path (SURVEY 8f-3)")
+        if cfg.control.control_type not in ("P", "V", "T"):
+            raise NameError(f"Unknown controller type: {cfg.control.control_type}")          # legged_robot.py:616-617
+        c.control_type = "PVT".index(cfg.control.control_type)      # 'V' / 'T' need libgo2b200_relaxed.so (go2_env_create rejects them otherwise)
         default = np.zeros(12, np.float32)
         for j, name in enumerate(dof_names):
             default[j] = cfg.init_state.default_joint_angles[name]
@@ -205,8 +208,7 @@ class EnvArrays:
         c.max_episode_length, c.max_episode_length_s, c.dt = self.max_episode_length, self.max_episode_length_s, self.dt
         for k, name in enumerate(_abi.REWARD_NAMES):
             c.reward_scales[k] = self.reward_scales.get(name, 0.0)
-        if cfg.rewards.only_positive_rewards:
-            raise NotImplementedError("only_positive_rewards is off for every go2 task (go2_config.py:159)")
+        c.only_positive_rewards = int(bool(cfg.rewards.only_positive_rewards))     # off for every go2 task (go2_config.py:159); needs libgo2b200_relaxed.so
         c.tracking_sigma, c.base_height_target = cfg.rewards.tracking_sigma, cfg.rewards.base_height_target
         for j in range(12):
             lo, hi = self.model.q_lower[j], self.model.q_upper[j]

@@ -108,6 +108,9 @@ typedef struct Go2EnvConfig {
      with zero velocities / torques / contact forces and RESETS in this step (reset_buf = 1, time_out_buf = 0): one diverged env can never feed
      a NaN into the shared policy / value networks. */
   int32_t state_guard; float max_base_lin_vel, max_base_ang_vel;
+  /* env switches outside the GO2 defaults (appended; need the same build as the fields above, 0 = the GO2 defaults):
+     control_type 0 'P' / 1 'V' / 2 'T' (legged_robot.py:605-618); only_positive_rewards clips the summed reward at 0 (legged_robot.py:266-267) */
+  int32_t control_type, only_positive_rewards;
 } Go2EnvConfig;
 
 /* Per-step scalars the host derives from common_step_counter (curricula), no device sync involved. */

@@ -679,6 +679,8 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
         float a_in = (C.randomize_action_delay && s < start) ? lact[j] : act[j];
         float kp = C.kp[j] * B.p_gains_multiplier[o], kd = C.kd[j] * B.d_gains_multiplier[o];
         float t = kp * (a_in * C.action_scale + C.default_dof_pos[j] - (float)q[j] + B.motor_zero_offsets[o]) - kd * (float)qd[j];
+        if (C.control_type == 1) t = kp * (a_in * C.action_scale - (float)qd[j]) - kd * ((float)qd[j] - B.last_dof_vel[o]) / C.sim_dt;   // 'V', legged_robot.py:612-613
+        else if (C.control_type == 2) t = a_in * C.action_scale;                                                                     // 'T', :614-615
         t = std::min(std::max(t, -M.effort[j]), M.effort[j]);
         if (C.randomize_motor_strength) t *= B.motor_strengths[o];
         tq[j] = t;                                                   // what the reference reports (legged_robot.py:79-81)
@@ -812,6 +814,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
       rew += rk;
       B.episode_sums[(size_t)e * GO2_NUM_REW + k] += rk;
     }
+    if (C.only_positive_rewards) rew = std::max(rew, 0.0f);   // legged_robot.py:266-267 (episode sums keep the unclipped terms)
     B.rew_buf[e] = rew;
     if (B.reset_buf[e]) {
       n_reset++;

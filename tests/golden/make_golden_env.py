@@ -338,12 +338,13 @@ def load_state_into_reference(r, A):
     r.contact_forces.copy_(T["contact_forces"])
 
 
-def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700):
+def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False):
     torch.manual_seed(seed)
     cfg = MyGO2Cfg()
     cfg.env.num_envs = N
     cfg.terrain.mesh_type = "plane" if plane else "heightfield"
     cfg.seed = seed
+    cfg.control.control_type, cfg.rewards.only_positive_rewards = control_type, only_positive     # switches outside the GO2 defaults
     A = EnvArrays(cfg, "cpu", seed=seed)
     O = OracleEnv(A)
     O.common_step_counter = start_counter
@@ -378,6 +379,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700):
     ref_cfg = RefGO2Cfg()
     ref_cfg.env.num_envs = N
     ref_cfg.terrain.mesh_type = cfg.terrain.mesh_type
+    ref_cfg.control.control_type, ref_cfg.rewards.only_positive_rewards = control_type, only_positive
     draws = Draws(seed)
     install_rng(draws, N)
     r = build_reference_env(A, O, ref_cfg)
@@ -408,7 +410,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700):
         rec["ep_terrain_level_all"] = torch.tensor(float(ep.get("terrain_level_all", float("nan"))))
         outs.append({kk: vv.clone().numpy() for kk, vv in rec.items()})
     save = {"meta_N": N, "meta_K": K, "meta_seed": seed, "meta_plane": int(plane), "meta_start_counter": start_counter + 30,
-            "actions": actions.numpy()}
+            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "actions": actions.numpy()}
     for k, v in S0.items():
         save["s0_" + k] = v.numpy()
     for i, o in enumerate(outs):
@@ -421,6 +423,10 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700):
 
 
 if __name__ == "__main__":
+    if "--switches" in sys.argv:      # env switches outside the GO2 defaults: velocity / torque control, only_positive_rewards
+        make_case("ctrl_v_pos", plane=False, N=32, K=4, seed=13, control_type="V", only_positive=True)
+        make_case("ctrl_t", plane=True, N=32, K=3, seed=14, control_type="T")
+        sys.exit(0)
     make_case("rough", plane=False)
     make_case("plane", plane=True, N=32, K=4)
     # crosses learning iteration 20 000: the command-range curriculum widens the ranges (go2_config.py:112-124, legged_robot.py:433-446)

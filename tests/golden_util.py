@@ -33,6 +33,9 @@ def load_case(name, device="cpu", **kw):
     cfg.env.num_envs = N
     cfg.terrain.mesh_type = "plane" if plane else "heightfield"
     cfg.seed = seed
+    if "meta_control_type" in z.files:       # fixtures with env switches outside the GO2 defaults (make_golden_env.py --switches)
+        cfg.control.control_type = "PVT"[int(z["meta_control_type"])]
+        cfg.rewards.only_positive_rewards = bool(z["meta_only_positive"])
     A = EnvArrays(cfg, device, seed=seed, **kw)
     for k in z.files:
         if k.startswith("s0_"):

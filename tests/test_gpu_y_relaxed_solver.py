@@ -117,3 +117,18 @@ def test_state_guard_contains_a_diverged_env_on_the_gpu():
         for k in ("obs_buf", "rew_buf", "root_states", "dof_pos", "reset_buf"):
             assert torch.equal(dirty[step][k][others], clean[step][k][others]), (step, k)
     assert float(dirty[1]["root_states"][9, 7:10].norm()) <= 1000.0 * (1 + 1e-5) or bool(dirty[1]["reset_buf"][9])
+
+
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t"])
+def test_env_switches_match_reference_golden(name):
+    """control_type 'V' / 'T' and only_positive_rewards (legged_robot.py:605-618,266-267) against the fixture made by the REFERENCE's
+    own Python: first recorded step, same tolerances as the kernel-source emulation (tests/test_emu_cpu.py)."""
+    from cuda_util import CudaEnv
+    from golden_util import compare_step, load_case
+    z, A = load_case(name, device="cuda")
+    env = CudaEnv(A, lib_path=LIB)
+    env.common_step_counter = int(z["meta_start_counter"])
+    env.step(torch.from_numpy(z["actions"][0]))
+    tol = dict(TOL, dof_vel=(1e-3, 0.1), last_dof_vel=(1e-3, 0.1), torques=(1e-3, 0.1), privileged_obs_buf=(1e-3, 1e-2), obs_buf=(1e-3, 1e-2))
+    bad = compare_step(z, 0, A.tensors, tol=tol)
+    assert not bad, bad

@@ -61,3 +61,26 @@ def test_terrain_grid_equals_the_reference():
     c = res["curriculum"]
     assert c["cols2id"][0] == c["cols2id"][1] and c["name2cols"][0] == c["name2cols"][1], c
     assert c["shape"][1] == [1345, 2195]          # 10 x 20 tiles of 8 m at 0.1 m, 0.5 m spacing, 25 m border
+
+
+@pytest.mark.parametrize("N", [32, 48, 64, 4096, 8192, 16384, 65536, 100])
+def test_round_robin_terrain_assignment_uses_torch_float32_semantics(N):
+    """legged_robot.py:1071-1072: levels = i % 6, types = floor(i / (N / 20)) evaluated by torch in FLOAT32 — at i = k N / 4 the quotient lands just
+    below the integer (env 1024 of 4096 is on column 4, not 5).  EnvArrays must reproduce that, for whole runs and for shards (global env ids)."""
+    import torch
+    from go2_rl_gym_b200.envs.env_arrays import EnvArrays
+    from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+    ref_types = torch.div(torch.arange(N), (N / 20), rounding_mode="floor").to(torch.long)
+    ref_levels = torch.fmod(torch.arange(N), 5 + 1)
+    if N <= 8192:
+        cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"
+        A = EnvArrays(cfg, "cpu", seed=1)
+        assert torch.equal(A.tensors["terrain_types"].long(), ref_types) and torch.equal(A.tensors["terrain_levels"].long(), ref_levels)
+    # a shard keeps the global assignment
+    Ns = min(N // 4, 2048) if N % 4 == 0 else None
+    if Ns:
+        cfg = GO2Cfg(); cfg.env.num_envs = Ns; cfg.terrain.mesh_type = "heightfield"
+        off = N // 4
+        A = EnvArrays(cfg, "cpu", num_envs=Ns, env_offset=off, num_envs_global=N, seed=1)
+        assert torch.equal(A.tensors["terrain_types"].long(), ref_types[off:off + Ns])
+        assert int(A.tensors["terrain_types"][0]) == int(ref_types[off]) == (5 if N == 100 else 4)   # the float32 boundary case itself (100 / 20 is exact)
