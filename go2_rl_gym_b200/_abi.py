@@ -55,6 +55,8 @@ class Go2EnvConfig(C.Structure):
         ("limit_relax", f32), ("contact_relax", f32),
         ("state_guard", i32), ("max_base_lin_vel", f32), ("max_base_ang_vel", f32),
         ("control_type", i32), ("only_positive_rewards", i32),
+        ("heading_command", i32), ("stop_heading_at_limit", i32), ("ext_stop_heading_lo", u32), ("ext_stop_heading_hi", u32),
+        ("ext_heading_ranges_lo", u32), ("ext_heading_ranges_hi", u32),
     ]
 
 

@@ -260,7 +260,9 @@ struct WarpSmem {
 #if GO2_RELAXED_SOLVER
   float Dje[12];               // limit-row step limit_relax / (M^-1)_jj (relaxed solver only)
   int bad;                     // state guard: this env's state went non-finite in this step (sanitised, resets)
-  int pad_relaxed_[19];        // keeps the row stride at 1 mod 32 words in this build too
+  int stop_heading;            // heading commands: the yaw command no longer follows the heading target (legged_robot.py:412,431,548,582)
+  float hrng[2];               // this env's heading range
+  int pad_relaxed_[16];        // keeps the row stride at 1 mod 32 words in this build too
 #endif
   float mu_env, rest_env;      // contact friction / restitution of this env (combined with the terrain's)
   float a0[6];
@@ -917,6 +919,10 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
   float remaining = fmaxf(GO2_FADD(GO2_FMUL(0.625f, C->terrain_length), -GO2_FMUL(accn, C->resampling_time)), 0.0f);
   const float full = C->resampling_time / C->dt;
   S.resamp_step = full;
+#if GO2_RELAXED_SOLVER
+  const bool heading = C->heading_command != 0;
+  S.stop_heading = 0;                                                   // legged_robot.py:431
+#endif
   if (C->dynamic_resample_commands) {
     float vlow = fmaxf(remaining / GO2_FMUL(GO2_FADD(max_len - ep_len, 1e-9f), C->dt), 0.0f);
     for (int a = 0; a < 2; ++a) {
@@ -926,10 +932,18 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
       float u = GO2_FMUL(u01(a == 0 ? r0.x : r0.y), total);
       S.cmd[a] = (u < wneg) ? GO2_FADD(lo, u) : GO2_FADD(hi - wpos, u - wneg);
     }
+#if GO2_RELAXED_SOLVER
+    if (heading) S.cmd[3] = affine(S.hrng[1] - S.hrng[0], u01(r0.z), S.hrng[0]);       // the same draw feeds the heading target (:468-472)
+    else
+#endif
     S.cmd[2] = affine(rng[5] - rng[4], u01(r0.z), rng[4]);
   } else {
     S.cmd[0] = GO2_FADD(rng[0], GO2_FMUL(u01(r0.x), rng[1] - rng[0]));
     S.cmd[1] = GO2_FADD(rng[2], GO2_FMUL(u01(r0.y), rng[3] - rng[2]));
+#if GO2_RELAXED_SOLVER
+    if (heading) S.cmd[3] = GO2_FADD(S.hrng[0], GO2_FMUL(u01(r0.z), S.hrng[1] - S.hrng[0]));
+    else
+#endif
     S.cmd[2] = GO2_FADD(rng[4], GO2_FMUL(u01(r0.z), rng[5] - rng[4]));
     float nrm = sqrtf(S.cmd[0] * S.cmd[0] + S.cmd[1] * S.cmd[1]);
     if (!(nrm > 0.2f)) { S.cmd[0] = 0; S.cmd[1] = 0; }
@@ -950,6 +964,9 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
         S.cmd[1] = cy == 0 ? rng[2] : rng[3];
         S.cmd[2] = cz == 0 ? rng[4] : (cz == 1 ? 0.0f : rng[5]);
       }
+#if GO2_RELAXED_SOLVER
+      if (heading && C->stop_heading_at_limit) S.stop_heading = 1;      // :547-548
+#endif
     }
     S.last_lim = lim ? 1 : 0;
     min_p += C->limit_vel_prob;
@@ -961,12 +978,32 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
     if (prob >= min_p && prob < max_p && next > 0) {
       S.cmd[0] = 0; S.cmd[1] = 0;
       S.resamp_step = next;
-      if (C->limit_ang_vel_at_zero_command_prob > 0 && u01(r1.y) < C->limit_ang_vel_at_zero_command_prob)
+      if (C->limit_ang_vel_at_zero_command_prob > 0 && u01(r1.y) < C->limit_ang_vel_at_zero_command_prob) {
         S.cmd[2] = (u01(r1.z) < 0.5f) ? rng[4] : rng[5];
+#if GO2_RELAXED_SOLVER
+        if (heading) S.stop_heading = 1;                                // :581-582
+#endif
+      }
     }
   }
   S.acc_xy[0] += S.cmd[0]; S.acc_xy[1] += S.cmd[1];
 }
+
+#if GO2_RELAXED_SOLVER
+// yaw-rate command from the heading target (legged_robot.py:411-419; quat_apply and wrap_to_pi in torch's operation order)
+GO2_HD void heading_to_yaw(WarpSmem& S) {
+  const float qx = S.root[3], qy = S.root[4], qz = S.root[5], qw = S.root[6];
+  // t = 2 (q_xyz x [1,0,0]) = 2 (0, qz, -qy);  forward = [1,0,0] + qw t + q_xyz x t
+  const float ty = GO2_FMUL(qz, 2.0f), tz = GO2_FMUL(-qy, 2.0f);
+  const float fx = GO2_FADD(1.0f, GO2_FADD(GO2_FMUL(qy, tz), -GO2_FMUL(qz, ty)));
+  const float fy = GO2_FADD(GO2_FMUL(qw, ty), GO2_FADD(GO2_FMUL(qz, 0.0f), -GO2_FMUL(qx, tz)));
+  const float hd = atan2f(fy, fx);
+  float a = fmodf(S.cmd[3] - hd, 6.2831855f);                           // torch: angles %= 2 pi (result takes the divisor's sign)
+  if (a != 0.0f && a < 0.0f) a = GO2_FADD(a, 6.2831855f);
+  if (a > 3.1415927f) a = GO2_FADD(a, -6.2831855f);
+  S.cmd[2] = fminf(fmaxf(GO2_FMUL(0.5f, a), S.cmd_rng[4]), S.cmd_rng[5]);
+}
+#endif
 
 #if defined(__CUDACC__)
 #define GO2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -1060,6 +1097,15 @@ GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     if (lane == 25) { S.ep_len = B->episode_length_buf[e]; S.resamp_step = B->commands_resampling_step[e]; }
     if (lane == 26) { S.acc_xy[0] = B->commands_xy_accumulation[(size_t)e * 2]; S.acc_xy[1] = B->commands_xy_accumulation[(size_t)e * 2 + 1]; }
     if (lane == 27) { S.max_move = B->max_move_distance[e]; S.last_lim = B->last_is_limit_vel[e]; }
+#if GO2_RELAXED_SOLVER
+    if (lane == 30) {
+      S.stop_heading = 0; S.hrng[0] = 0.0f; S.hrng[1] = 0.0f;
+      if (C->heading_command) {
+        const float* hr = GO2_EXT_PTR(const float*, C, ext_heading_ranges);
+        S.stop_heading = GO2_EXT_PTR(const uint8_t*, C, ext_stop_heading)[e]; S.hrng[0] = hr[(size_t)e * 2]; S.hrng[1] = hr[(size_t)e * 2 + 1];
+      }
+    }
+#endif
     if (lane == 28) { S.level = B->terrain_levels[e]; S.ttype = B->terrain_types[e]; S.tid = B->terrain_ids[e]; }
     if (lane == 30) {
       S.mu_env = 0.5f * (C->terrain_friction + GO2_LDG(B->friction_coeffs + e));
@@ -1089,6 +1135,9 @@ GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     if (lane == 25) { B->episode_length_buf[e] = S.ep_len; B->commands_resampling_step[e] = S.resamp_step; }
     if (lane == 26) { B->commands_xy_accumulation[(size_t)e * 2] = S.acc_xy[0]; B->commands_xy_accumulation[(size_t)e * 2 + 1] = S.acc_xy[1]; }
     if (lane == 27) { B->max_move_distance[e] = S.max_move; B->last_is_limit_vel[e] = (uint8_t)S.last_lim; }
+#if GO2_RELAXED_SOLVER
+    if (lane == 30 && X.cfg->heading_command) GO2_EXT_PTR(uint8_t*, X.cfg, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
+#endif
     if (lane == 28) B->terrain_levels[e] = S.level;
     if (lane == 29) { B->reset_buf[e] = (uint8_t)S.reset; B->time_out_buf[e] = (uint8_t)S.tout; }
     for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = S.cf[i / 3][i % 3];
@@ -1172,6 +1221,9 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       float dx = S.root[0] - S.env_origin[0], dy = S.root[1] - S.env_origin[1];
       S.max_move = fmaxf(S.max_move, sqrtf(dx * dx + dy * dy));
       if (S.resamp_step <= 0.0f && S.ep_len < C->max_episode_length - 1) resample_commands(S, X, e, ST_CMD_CB);
+#if GO2_RELAXED_SOLVER
+      if (C->heading_command && !S.stop_heading) heading_to_yaw(S);
+#endif
     }
   } GO2_SYNC_WARP();
   GO2_WIDE {

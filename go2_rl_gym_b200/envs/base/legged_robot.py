@@ -64,7 +64,8 @@ class LeggedRobot:
         self.friction_coeffs = T["friction_coeffs"]
         self.episode_sums = {n: T["episode_sums"][:, k] for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales}
         self.env_command_ranges = {"lin_vel_x": T["env_command_ranges"][:, 0:2], "lin_vel_y": T["env_command_ranges"][:, 2:4],
-                                   "ang_vel_yaw": T["env_command_ranges"][:, 4:6]}
+                                   "ang_vel_yaw": T["env_command_ranges"][:, 4:6], "heading": T["heading_ranges"]}
+        self.stop_heading = T["stop_heading"].view(torch.bool)
         self.dt = A.dt
         self.max_episode_length_s = A.max_episode_length_s
         self.max_episode_length = A.max_episode_length

@@ -129,6 +129,7 @@ class EnvArrays:
         for n in _U8:
             z(n, N, dtype=torch.uint8)
         z("episode_length_buf", N, dtype=torch.int32)
+        z("stop_heading", N, dtype=torch.uint8); z("heading_ranges", N, 2)      # heading commands (Go2EnvConfig.ext_*)
         T["terrain_levels"] = torch.from_numpy(levels).to(dev)
         T["terrain_types"] = torch.from_numpy(types).to(dev)
         T["terrain_ids"] = torch.from_numpy(ids.astype(np.int32)).to(dev)
@@ -197,8 +198,12 @@ class EnvArrays:
         c.move_down_by_accumulated_xy_command = int(cfg.terrain.move_down_by_accumulated_xy_command)
         c.custom_origins = int(self.custom_origins)
         cm = cfg.commands
-        if cm.heading_command or cfg.init_state.turn_over or cm.curriculum:
-            raise NotImplementedError("heading_command / turn_over / commands.curriculum are outside the hot path (SURVEY 8f-3)")
+        if cfg.init_state.turn_over or cm.curriculum:
+            raise NotImplementedError("turn_over / commands.curriculum are outside the hot path (SURVEY 8f-3)")
+        # heading commands (legged_robot.py:411-419): served by libgo2b200_relaxed.so only (go2_env_create of the default build rejects them)
+        c.heading_command, c.stop_heading_at_limit = int(bool(cm.heading_command)), int(bool(getattr(cm, "stop_heading_at_limit", False)))
+        for name, key in (("ext_stop_heading", "stop_heading"), ("ext_heading_ranges", "heading_ranges")):       # addresses as 32-bit halves (go2_b200.h)
+            setattr(c, name + "_lo", T[key].data_ptr() & 0xFFFFFFFF); setattr(c, name + "_hi", T[key].data_ptr() >> 32)
         c.resampling_time, c.dynamic_resample_commands = cm.resampling_time, int(cm.dynamic_resample_commands)
         c.limit_vel_prob = cm.limit_vel_prob
         c.limit_vel_invert_when_continuous = int(cm.limit_vel_invert_when_continuous)
@@ -265,17 +270,19 @@ class EnvArrays:
 
     def _update_env_command_ranges(self):  # legged_robot.py:861-907
         r = self.command_ranges
-        table = np.zeros((9, 6), np.float32)
+        table = np.zeros((9, 8), np.float32)
+        table[:, 6:8] = r["heading"]                   # per-terrain heading limits apply only with heading commands (:899-907)
         for tid, tr in enumerate(self.cfg.commands.terrain_max_command_ranges):
-            for a, key in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw")):
+            for a, key in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw") + (("heading",) if self.cfg.commands.heading_command else ())):
                 table[tid, 2 * a] = max(tr[key][0], r[key][0])
                 table[tid, 2 * a + 1] = min(tr[key][1], r[key][1])
         if self.plane:  # no terrain_ids attribute in the reference -> global ranges
             rows = np.tile(np.array([r["lin_vel_x"][0], r["lin_vel_x"][1], r["lin_vel_y"][0], r["lin_vel_y"][1],
-                                     r["ang_vel_yaw"][0], r["ang_vel_yaw"][1]], np.float32), (self.num_envs, 1))
+                                     r["ang_vel_yaw"][0], r["ang_vel_yaw"][1], r["heading"][0], r["heading"][1]], np.float32), (self.num_envs, 1))
         else:
             rows = table[self.terrain_ids_np]
-        self.tensors["env_command_ranges"].copy_(torch.from_numpy(np.ascontiguousarray(rows)))
+        self.tensors["env_command_ranges"].copy_(torch.from_numpy(np.ascontiguousarray(rows[:, :6])))
+        self.tensors["heading_ranges"].copy_(torch.from_numpy(np.ascontiguousarray(rows[:, 6:8])))
 
     @staticmethod
     def _scale(config, it):  # get_current_scale, legged_robot.py:154-168

@@ -111,7 +111,14 @@ typedef struct Go2EnvConfig {
   /* env switches outside the GO2 defaults (appended; need the same build as the fields above, 0 = the GO2 defaults):
      control_type 0 'P' / 1 'V' / 2 'T' (legged_robot.py:605-618); only_positive_rewards clips the summed reward at 0 (legged_robot.py:266-267) */
   int32_t control_type, only_positive_rewards;
+  /* heading commands (legged_robot.py:411-419,468-472,547-548,581-582): commands[:,3] is a heading target, the yaw-rate command follows it
+     every step unless stop_heading is set.  The two per-env arrays are caller-owned device memory like Go2EnvBuffers': stop_heading [N] uint8,
+     heading_ranges [N,2] (lower, upper).  Their addresses are kept HERE, as two 32-bit halves each, so that neither the by-value Go2EnvBuffers
+     kernel argument nor this struct's 4-byte alignment changes (a pointer member raises it to 8 and alters the default build's code). */
+  int32_t heading_command, stop_heading_at_limit;
+  uint32_t ext_stop_heading_lo, ext_stop_heading_hi, ext_heading_ranges_lo, ext_heading_ranges_hi;
 } Go2EnvConfig;
+#define GO2_EXT_PTR(type, cfg, name) ((type)(uintptr_t)(((uint64_t)(cfg)->name##_hi << 32) | (uint64_t)(cfg)->name##_lo))
 
 /* Per-step scalars the host derives from common_step_counter (curricula), no device sync involved. */
 typedef struct Go2StepParams {

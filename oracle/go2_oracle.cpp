@@ -495,6 +495,10 @@ static void resample_commands(const Go2EnvConfig& C, const Go2EnvBuffers& B, con
   float max_len = (float)C.max_episode_length;
   float remaining = std::max(0.625f * C.terrain_length - std::sqrt(acc[0] * acc[0] + acc[1] * acc[1]) * C.resampling_time, 0.0f);
   B.commands_resampling_step[e] = C.resampling_time / C.dt;
+  const bool heading = C.heading_command != 0;
+  const float* hr = heading ? GO2_EXT_PTR(const float*, &C, ext_heading_ranges) + (size_t)e * 2 : nullptr;
+  uint8_t* stop_heading = heading ? GO2_EXT_PTR(uint8_t*, &C, ext_stop_heading) : nullptr;
+  if (heading) stop_heading[e] = 0;                               // legged_robot.py:431
   if (C.dynamic_resample_commands) {
     float vlow = std::max(remaining / ((max_len - ep_len + 1e-9f) * C.dt), 0.0f);
     for (int a = 0; a < 2; ++a) {  // sample_disjoint_intervals, isaacgym_utils.py:32-47
@@ -504,11 +508,13 @@ static void resample_commands(const Go2EnvConfig& C, const Go2EnvBuffers& B, con
       float u = u01(a == 0 ? r0.x : r0.y) * total;
       cmd[a] = (u < wneg) ? lo + u : hi - wpos + (u - wneg);
     }
-    cmd[2] = (rng[5] - rng[4]) * u01(r0.z) + rng[4];
+    if (heading) cmd[3] = (hr[1] - hr[0]) * u01(r0.z) + hr[0];          // the same draw feeds the heading target (:468-472)
+    else cmd[2] = (rng[5] - rng[4]) * u01(r0.z) + rng[4];
   } else {
     cmd[0] = rng[0] + u01(r0.x) * (rng[1] - rng[0]);
     cmd[1] = rng[2] + u01(r0.y) * (rng[3] - rng[2]);
-    cmd[2] = rng[4] + u01(r0.z) * (rng[5] - rng[4]);
+    if (heading) cmd[3] = hr[0] + u01(r0.z) * (hr[1] - hr[0]);
+    else cmd[2] = rng[4] + u01(r0.z) * (rng[5] - rng[4]);
     float nrm = std::sqrt(cmd[0] * cmd[0] + cmd[1] * cmd[1]);
     if (!(nrm > 0.2f)) { cmd[0] = 0; cmd[1] = 0; }
   }
@@ -529,6 +535,7 @@ static void resample_commands(const Go2EnvConfig& C, const Go2EnvBuffers& B, con
         cmd[1] = cy == 0 ? rng[2] : rng[3];
         cmd[2] = cz == 0 ? rng[4] : (cz == 1 ? 0.0f : rng[5]);
       }
+      if (heading && C.stop_heading_at_limit) stop_heading[e] = 1;   // :547-548
     }
     B.last_is_limit_vel[e] = lim ? 1 : 0;
     min_p += C.limit_vel_prob;
@@ -540,11 +547,29 @@ static void resample_commands(const Go2EnvConfig& C, const Go2EnvBuffers& B, con
     if (prob >= min_p && prob < max_p && next > 0) {
       cmd[0] = 0; cmd[1] = 0;
       B.commands_resampling_step[e] = next;
-      if (C.limit_ang_vel_at_zero_command_prob > 0 && u01(r1.y) < C.limit_ang_vel_at_zero_command_prob)
+      if (C.limit_ang_vel_at_zero_command_prob > 0 && u01(r1.y) < C.limit_ang_vel_at_zero_command_prob) {
         cmd[2] = (u01(r1.z) < 0.5f) ? rng[4] : rng[5];
+        if (heading) stop_heading[e] = 1;                          // :581-582
+      }
     }
   }
   acc[0] += cmd[0]; acc[1] += cmd[1];
+}
+
+// yaw-rate command from the heading target (legged_robot.py:411-419): quat_apply(base_quat, [1,0,0]), atan2, wrap_to_pi (math.py:15-18), clip
+static void heading_to_yaw(const Go2EnvBuffers& B, int e) {
+  const float* rs = B.root_states + (size_t)e * 13;
+  float* cmd = B.commands + (size_t)e * GO2_NUM_CMD;
+  const float* rng = B.env_command_ranges + (size_t)e * 6;
+  const float qx = rs[3], qy = rs[4], qz = rs[5], qw = rs[6];
+  const float ty = qz * 2.0f, tz = -qy * 2.0f;                           // t = 2 (q_xyz x [1,0,0])
+  const float fx = 1.0f + (qy * tz - qz * ty);
+  const float fy = qw * ty + (qz * 0.0f - qx * tz);
+  const float hd = std::atan2(fy, fx);
+  float a = std::fmod(cmd[3] - hd, 6.2831855f);
+  if (a != 0.0f && a < 0.0f) a += 6.2831855f;
+  if (a > 3.1415927f) a -= 6.2831855f;
+  cmd[2] = std::min(std::max(0.5f * a, rng[4]), rng[5]);
 }
 
 static void reset_env(const Go2EnvConfig& C, const Go2Model& M, const Go2EnvBuffers& B, const Go2StepParams& sp, int e,
@@ -745,6 +770,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
       B.max_move_distance[e] = std::max(B.max_move_distance[e], std::sqrt(dx * dx + dy * dy));
     }
     if (B.commands_resampling_step[e] <= 0.0f && B.episode_length_buf[e] < C.max_episode_length - 1) resample_commands(C, B, sp, e, ST_CMD_CB);
+    if (C.heading_command && !GO2_EXT_PTR(const uint8_t*, &C, ext_stop_heading)[e]) heading_to_yaw(B, e);
     measure_heights(C, B, e);
     // check_termination, legged_robot.py:170-178
     const float* cf = B.contact_forces + (size_t)e * GO2_NUM_REPORT * 3;

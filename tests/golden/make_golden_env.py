@@ -138,7 +138,7 @@ def install_rng(draws, num_envs):
                 comp = {454: 0, 461: 1}[fr.f_back.f_lineno]
                 return draws.u(ids, ST_CMD_RESET if in_reset() else ST_CMD_CB, 0, comp)
             stream = ST_CMD_RESET if in_reset() else ST_CMD_CB
-            if line == 474:
+            if line in (469, 474):      # the yaw draw; with heading commands the same draw feeds the heading target (:469)
                 return draws.u(_ids(fr.f_locals["env_ids"]), stream, 0, 2)
             if line == 509:
                 return draws.u(_ids(fr.f_locals["env_ids"]), stream, 0, 3)
@@ -329,6 +329,7 @@ def load_state_into_reference(r, A):
         getattr(r, k).copy_(T[k])
     r.last_last_actions = T["last_last_actions"].clone()
     r.last_is_limit_vel.copy_(T["last_is_limit_vel"].bool())
+    r.stop_heading.copy_(T["stop_heading"].bool())
     r.episode_length_buf.copy_(T["episode_length_buf"].long())
     if not A.plane:
         r.terrain_levels.copy_(T["terrain_levels"].long())
@@ -338,13 +339,18 @@ def load_state_into_reference(r, A):
     r.contact_forces.copy_(T["contact_forces"])
 
 
-def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False):
+def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False, heading=False):
     torch.manual_seed(seed)
     cfg = MyGO2Cfg()
     cfg.env.num_envs = N
     cfg.terrain.mesh_type = "plane" if plane else "heightfield"
     cfg.seed = seed
     cfg.control.control_type, cfg.rewards.only_positive_rewards = control_type, only_positive     # switches outside the GO2 defaults
+    cfg.commands.heading_command = heading
+    if heading:
+        # the reference clips the masked yaw command with UNMASKED [N] bounds (legged_robot.py:415-419): it raises a shape error as soon as one
+        # env holds its heading (stop_heading), so its heading mode only runs while no env ever stops: no stop at limits, no yaw kick at zero commands
+        cfg.commands.stop_heading_at_limit, cfg.commands.limit_ang_vel_at_zero_command_prob = False, 0.0
     A = EnvArrays(cfg, "cpu", seed=seed)
     O = OracleEnv(A)
     O.common_step_counter = start_counter
@@ -369,7 +375,9 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
     # two robots lying on their side / upside down -> base contact termination
     T["root_states"][20, 3:7] = torch.tensor([0.7071, 0.0, 0.0, 0.7071]); T["root_states"][20, 2] = T["env_origins"][20, 2] + 0.12
     T["root_states"][21, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0]); T["root_states"][21, 2] = T["env_origins"][21, 2] + 0.15
-    S0 = {k: T[k].clone() for k in STATE_KEYS}
+    if heading:      # mid-episode state of the heading mode: targets drawn
+        T["commands"][:, 3] = (torch.rand(N, generator=g) * 2 - 1) * 3.14
+    S0 = {k: T[k].clone() for k in STATE_KEYS + ["stop_heading"]}
     actions = 0.8 * torch.randn(K, N, 12, generator=g)
     actions[2, 5] = 150.0                                            # exercises clip_actions
 
@@ -380,6 +388,9 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
     ref_cfg.env.num_envs = N
     ref_cfg.terrain.mesh_type = cfg.terrain.mesh_type
     ref_cfg.control.control_type, ref_cfg.rewards.only_positive_rewards = control_type, only_positive
+    ref_cfg.commands.heading_command = heading
+    if heading:
+        ref_cfg.commands.stop_heading_at_limit, ref_cfg.commands.limit_ang_vel_at_zero_command_prob = False, 0.0
     draws = Draws(seed)
     install_rng(draws, N)
     r = build_reference_env(A, O, ref_cfg)
@@ -395,7 +406,8 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
                "time_out_buf": r.time_out_buf.to(torch.uint8), "root_states": T["root_states"], "dof_pos": T["dof_pos"],
                "dof_vel": T["dof_vel"], "torques": r.torques, "commands": r.commands,
                "commands_resampling_step": r.commands_resampling_step, "commands_xy_accumulation": r.commands_xy_accumulation,
-               "last_is_limit_vel": r.last_is_limit_vel.to(torch.uint8), "episode_length_buf": r.episode_length_buf.int(),
+               "last_is_limit_vel": r.last_is_limit_vel.to(torch.uint8), "stop_heading": r.stop_heading.to(torch.uint8),
+               "episode_length_buf": r.episode_length_buf.int(),
                "max_move_distance": r.max_move_distance, "motor_strengths": r.motor_strengths,
                "motor_zero_offsets": r.motor_zero_offsets, "p_gains_multiplier": r.p_gains_multiplier,
                "d_gains_multiplier": r.d_gains_multiplier,
@@ -410,7 +422,8 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
         rec["ep_terrain_level_all"] = torch.tensor(float(ep.get("terrain_level_all", float("nan"))))
         outs.append({kk: vv.clone().numpy() for kk, vv in rec.items()})
     save = {"meta_N": N, "meta_K": K, "meta_seed": seed, "meta_plane": int(plane), "meta_start_counter": start_counter + 30,
-            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "actions": actions.numpy()}
+            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "meta_heading": int(heading),
+            "actions": actions.numpy()}
     for k, v in S0.items():
         save["s0_" + k] = v.numpy()
     for i, o in enumerate(outs):
@@ -426,6 +439,7 @@ if __name__ == "__main__":
     if "--switches" in sys.argv:      # env switches outside the GO2 defaults: velocity / torque control, only_positive_rewards
         make_case("ctrl_v_pos", plane=False, N=32, K=4, seed=13, control_type="V", only_positive=True)
         make_case("ctrl_t", plane=True, N=32, K=3, seed=14, control_type="T")
+        make_case("heading", plane=False, N=48, K=6, seed=15, heading=True)
         sys.exit(0)
     make_case("rough", plane=False)
     make_case("plane", plane=True, N=32, K=4)

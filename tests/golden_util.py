@@ -10,7 +10,7 @@ from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # tolerances: integer / flag state is bit-exact; float state within fp32 rounding of a different summation order
-EXACT = ["reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel"]
+EXACT = ["reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel", "stop_heading"]
 # TOL_TIGHT: oracle post-physics vs the reference's Python over the SAME physics code (only summation order differs).
 TOL_TIGHT = {"default": (2e-5, 2e-5), "rew_buf": (1e-5, 1e-5), "episode_sums": (1e-4, 1e-5), "privileged_obs_buf": (1e-4, 1e-4),
              "contact_forces": (1e-3, 1e-3), "torques": (1e-4, 1e-4), "dof_vel": (1e-4, 1e-4), "root_states": (1e-4, 1e-4),
@@ -36,6 +36,9 @@ def load_case(name, device="cpu", **kw):
     if "meta_control_type" in z.files:       # fixtures with env switches outside the GO2 defaults (make_golden_env.py --switches)
         cfg.control.control_type = "PVT"[int(z["meta_control_type"])]
         cfg.rewards.only_positive_rewards = bool(z["meta_only_positive"])
+        cfg.commands.heading_command = bool(z["meta_heading"]) if "meta_heading" in z.files else False
+        if cfg.commands.heading_command:      # the settings under which the reference's heading mode runs at all (make_golden_env.py)
+            cfg.commands.stop_heading_at_limit, cfg.commands.limit_ang_vel_at_zero_command_prob = False, 0.0
     A = EnvArrays(cfg, device, seed=seed, **kw)
     for k in z.files:
         if k.startswith("s0_"):

@@ -24,7 +24,7 @@ def test_emulated_kernel_matches_reference_golden(name, packed):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t"])
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading"])
 def test_emulated_kernel_matches_reference_golden_with_env_switches(name, packed):
     """control_type 'V' / 'T' and only_positive_rewards (compiled into the kernel with -DGO2_RELAXED_SOLVER=1 like the emulation):
     every recorded step of the reference-made fixture, state re-synchronised to the fixture between steps."""
@@ -308,3 +308,41 @@ def test_state_guard_contains_a_diverged_env(kind):
     assert float(dirty[1]["root_states"][9, 7:10].norm()) <= 1000.0 * (1 + 1e-5) or bool(dirty[1]["reset_buf"][9])
     # the restarted envs continue like any freshly reset env
     assert float(dirty[3]["root_states"][3, 2]) > -5.0 and float(dirty[3]["dof_pos"][5].abs().max()) < 10.0
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_heading_mode_with_stop_flags_kernel_source_equals_oracle(packed):
+    """heading_command with the GO2 defaults stop_heading_at_limit = True / limit_ang_vel_at_zero_command_prob > 0.  The reference itself cannot
+    run this combination (it clips the masked yaw command with unmasked bounds, legged_robot.py:415-419, and raises once an env holds its
+    heading), so the evident intent is pinned between the oracle and the kernel source: identical stop flags and commands, stopped envs keep
+    their yaw command, the others follow 0.5 * wrap_to_pi(target - heading) clipped to their yaw range."""
+    N = 64
+    cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 21
+    cfg.commands.heading_command = True
+    cfg.commands.resampling_time = 0.2                       # resample every 10 steps: many draws in a short run
+    Ac, Ae = EnvArrays(cfg, "cpu", seed=21), EnvArrays(cfg, "cpu", seed=21)
+    orc, env = OracleEnv(Ac), EmuEnv(Ae, packed=packed)
+    orc.common_step_counter = env.common_step_counter = 24 * 2000      # zero-command probability at its final value
+    orc.reset_all(); env.reset_all()
+    g = torch.Generator().manual_seed(3)
+    seen_stop = 0
+    for step in range(40):
+        a = 0.4 * torch.randn(N, 12, generator=g)
+        prev_cmd, prev_stop = Ac.tensors["commands"].clone(), Ac.tensors["stop_heading"].clone()
+        orc.step(a); env.step(a)
+        for k in ("stop_heading", "reset_buf", "last_is_limit_vel"):
+            assert torch.equal(Ac.tensors[k], Ae.tensors[k]), (step, k)
+        assert torch.allclose(Ac.tensors["commands"], Ae.tensors["commands"], atol=1e-5), step
+        stop = Ac.tensors["stop_heading"].bool()
+        seen_stop += int(stop.sum())
+        held = stop & prev_stop.bool() & ~Ac.tensors["reset_buf"].bool() & (Ac.tensors["commands"][:, 3] == prev_cmd[:, 3])
+        assert torch.equal(Ac.tensors["commands"][held, 2], prev_cmd[held, 2])               # a held heading keeps its yaw command
+        q = Ac.tensors["root_states"][:, 3:7]
+        fwd_x = 1 - 2 * (q[:, 1] ** 2 + q[:, 2] ** 2); fwd_y = 2 * (q[:, 0] * q[:, 1] + q[:, 3] * q[:, 2])
+        err = Ac.tensors["commands"][:, 3] - torch.atan2(fwd_y, fwd_x)
+        want = torch.clip(0.5 * (torch.remainder(err + np.pi, 2 * np.pi) - np.pi), Ac.tensors["env_command_ranges"][:, 4], Ac.tensors["env_command_ranges"][:, 5])
+        free = ~stop & ~Ac.tensors["reset_buf"].bool()
+        assert torch.allclose(Ac.tensors["commands"][free, 2], want[free], atol=2e-4), step
+        copy_state(Ac.tensors, Ae.tensors)
+        Ae.tensors["stop_heading"].copy_(Ac.tensors["stop_heading"])
+    assert seen_stop > 0
