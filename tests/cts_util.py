@@ -23,3 +23,89 @@ def make_cts(variant, Z, device):
     alg = alg_cls(model, N, 5, device=device, **alg_kw)
     alg.init_storage(N, T, [45], [263], [12])
     return model, alg, T, N
+
+
+REF_RSL = "/root/reference/rsl_rl"
+
+
+def side_by_side(variant, policy, alg_kw, N, T, seed, monkeypatch, H=5):
+    """Run the REFERENCE's module + algorithm (imported from /root/reference/rsl_rl; build container only) and this package's over the emulated C
+    ABI on the same random data: T x (act, process_env_step), compute_returns, update with shared permutations.  Returns the worst deviations:
+    act (mu / sigma / value), returns, adv, loss (relative), lr, update_rel (relative error of the parameter update)."""
+    import sys
+    monkeypatch.syspath_prepend(REF_RSL)
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        monkeypatch.delitem(sys.modules, k)
+    import contextlib
+    import io
+    import rsl_rl.storage.rollout_storage_cts as RS
+    from golden.cts_cfg import NO_GOAL_MASK
+    from go2_rl_gym_b200.rl import algorithms as A, modules as Mo
+    import importlib
+    names = {"cts": ("cts", "CTS", "actor_critic_cts", "ActorCriticCTS"), "moe_cts": ("moe_cts", "MoECTS", "actor_critic_moe_cts", "ActorCriticMoECTS"),
+             "moe_ng_cts": ("moe_ng_cts", "MoENGCTS", "actor_critic_moe_ng_cts", "ActorCriticMoENGCTS"),
+             "ac_moe_cts": ("ac_moe_cts", "ACMoECTS", "actor_critic_ac_moe_cts", "ActorCriticACMoECTS"),
+             "dual_moe_cts": ("dual_moe_cts", "DualMoECTS", "actor_critic_dual_moe_cts", "ActorCriticDualMoECTS"),
+             "mcp_cts": ("mcp_cts", "MCPCTS", "actor_critic_mcp_cts", "ActorCriticMCPCTS")}[variant]
+    RefAlg = getattr(importlib.import_module("rsl_rl.algorithms." + names[0]), names[1])
+    ref_mod = importlib.import_module("rsl_rl.modules." + names[2])
+    RefModel = getattr(ref_mod, names[3])
+    ours_m, ours_a = getattr(Mo, names[3]), getattr(A, names[1])
+    needs_obs = variant in ("ac_moe_cts", "dual_moe_cts")
+    policy = dict(policy)
+    if variant in ("mcp_cts", "moe_ng_cts"):
+        policy.setdefault("obs_no_goal_mask", NO_GOAL_MASK)
+    if variant == "mcp_cts":
+        policy.setdefault("actor_hidden_dims", [512, 256, 128])       # GO2CfgMCPCTS
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if variant == "cts":      # the reference allocates this module's history on 'cuda' (actor_critic_cts.py:48)
+            zeros = torch.zeros
+            ref_mod.torch.zeros = lambda *a, **kw: zeros(*a, **{k: v for k, v in kw.items() if k != "device"})
+            try:
+                ref = RefModel(45, 263, 12, N, H, **policy)
+            finally:
+                ref_mod.torch.zeros = zeros
+        else:
+            ref = RefModel(45, 263, 12, N, H, **policy)
+        model = ours_m(45, 263, 12, N, H, **policy)
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    model.load_state_dict(ref.state_dict())
+    ralg, alg = RefAlg(ref, N, H, device="cpu", **alg_kw), ours_a(model, N, H, device="cpu", **alg_kw)
+    ralg.init_storage(N, T, [45], [263], [12]); alg.init_storage(N, T, [45], [263], [12])
+    g = torch.Generator().manual_seed(seed + 1)
+    obs, priv, hist = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g), torch.randn(T + 1, N, H * 45, generator=g)
+    rew, dones = 0.1 * torch.randn(T, N, generator=g), torch.rand(T, N, generator=g) < 0.05
+    out = {"act": 0.0}
+    with torch.inference_mode():
+        for t in range(T):
+            ralg.act(obs[t], priv[t], hist[t])
+            alg.act(obs[t], priv[t], hist[t])
+            for a, b in ((alg.storage.mu[t], ralg.transition.action_mean), (alg.storage.sigma[t], ralg.transition.action_sigma),
+                         (alg.storage.values[t], ralg.transition.values)):
+                out["act"] = max(out["act"], float((a - b).abs().max()))
+            for k in ("actions", "actions_log_prob"):       # same actions on both sides from here on
+                getattr(alg.storage, k)[t].copy_(getattr(ralg.transition, k).view_as(getattr(alg.storage, k)[t]))
+            ralg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+            alg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+        last = (obs[T], priv[T], hist[T])
+        ralg.compute_returns(*(last if needs_obs else last[1:]))
+        alg.compute_returns(*(last if needs_obs else last[1:]))
+    out["returns"] = float((alg.storage.returns - ralg.storage.returns).abs().max())
+    out["adv"] = float((alg.storage.advantages - ralg.storage.advantages).abs().max())
+    nt, ns = alg.teacher_num_envs * T, alg.student_num_envs * T
+    tperm, sperm = torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)
+    queue = [tperm.clone(), sperm.clone()]
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    with monkeypatch.context() as mp:
+        mp.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
+        rl = ralg.update()
+    ol = alg.update(tperm, sperm)
+    assert len(ol) == len(rl)
+    out["loss"] = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(ol, rl))
+    out["lr"] = abs(alg.learning_rate - ralg.learning_rate)
+    num = den = 0.0
+    for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
+        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
+    out["update_rel"] = (num / max(den, 1e-30)) ** 0.5
+    return out

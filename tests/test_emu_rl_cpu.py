@@ -237,72 +237,13 @@ def test_registered_width_variants_match_the_imported_reference(variant, policy,
     """The registered go2_ac_moe_cts / go2_dual_moe_cts / go2_mcp_cts widths (512-256-128, 8 experts) and a configuration whose experts are too
     wide for the narrow-head kernels: act + compute_returns + update against the reference's own module and algorithm run side by side on the
     same data (checks the operand alignment rules and the refresh of derived operands at real sizes, too)."""
-    import sys
+    from cts_util import side_by_side
+    from golden.cts_cfg import ALG, ALG_CTS
     emu_rl.install(monkeypatch)
     monkeypatch.setenv("GO2_GEMM", "tc")
-    monkeypatch.syspath_prepend(REF_RSL)
-    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
-        monkeypatch.delitem(sys.modules, k)
-    import rsl_rl.storage.rollout_storage_cts as RS
-    from golden.cts_cfg import ALG, ALG_CTS, NO_GOAL_MASK
-    from go2_rl_gym_b200.rl import algorithms as A, modules as Mo
-    alg_kw, needs_obs = ALG, True
-    if variant == "ac_moe_cts":
-        from rsl_rl.algorithms.ac_moe_cts import ACMoECTS as RefAlg
-        from rsl_rl.modules.actor_critic_ac_moe_cts import ActorCriticACMoECTS as RefModel
-        ours_m, ours_a = Mo.ActorCriticACMoECTS, A.ACMoECTS
-    elif variant == "dual_moe_cts":
-        from rsl_rl.algorithms.dual_moe_cts import DualMoECTS as RefAlg
-        from rsl_rl.modules.actor_critic_dual_moe_cts import ActorCriticDualMoECTS as RefModel
-        ours_m, ours_a = Mo.ActorCriticDualMoECTS, A.DualMoECTS
-    else:
-        from rsl_rl.algorithms.mcp_cts import MCPCTS as RefAlg
-        from rsl_rl.modules.actor_critic_mcp_cts import ActorCriticMCPCTS as RefModel
-        ours_m, ours_a, alg_kw, needs_obs = Mo.ActorCriticMCPCTS, A.MCPCTS, ALG_CTS, False
-        policy = dict(policy, obs_no_goal_mask=NO_GOAL_MASK, actor_hidden_dims=[512, 256, 128])       # GO2CfgMCPCTS
-    torch.manual_seed(0)
-    N, T, H = 16, 4, 5
-    ref = RefModel(45, 263, 12, N, H, **policy)
-    model = ours_m(45, 263, 12, N, H, **policy)
-    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
-    model.load_state_dict(ref.state_dict())
-    ralg, alg = RefAlg(ref, N, H, device="cpu", **alg_kw), ours_a(model, N, H, device="cpu", **alg_kw)
-    ralg.init_storage(N, T, [45], [263], [12]); alg.init_storage(N, T, [45], [263], [12])
-    g = torch.Generator().manual_seed(1)
-    obs, priv, hist = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g), torch.randn(T + 1, N, H * 45, generator=g)
-    rew, dones = 0.1 * torch.randn(T, N, generator=g), torch.rand(T, N, generator=g) < 0.05
-    with torch.inference_mode():
-        for t in range(T):
-            ralg.act(obs[t], priv[t], hist[t])
-            alg.act(obs[t], priv[t], hist[t])
-            assert torch.allclose(alg.storage.mu[t], ralg.transition.action_mean, atol=2e-5)
-            assert torch.allclose(alg.storage.sigma[t], ralg.transition.action_sigma, atol=2e-5)
-            assert torch.allclose(alg.storage.values[t], ralg.transition.values, atol=2e-5)
-            # same actions on both sides from here on
-            for k in ("actions", "actions_log_prob"):
-                getattr(alg.storage, k)[t].copy_(getattr(ralg.transition, k).view_as(getattr(alg.storage, k)[t]))
-            ralg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
-            alg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
-        last = (obs[T], priv[T], hist[T])
-        ralg.compute_returns(*(last if needs_obs else last[1:]))
-        alg.compute_returns(*(last if needs_obs else last[1:]))
-    assert torch.allclose(alg.storage.returns, ralg.storage.returns, atol=2e-5)
-    assert torch.allclose(alg.storage.advantages, ralg.storage.advantages, atol=2e-4)
-    nt, ns = alg.teacher_num_envs * T, alg.student_num_envs * T
-    tperm, sperm = torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)
-    queue = [tperm.clone(), sperm.clone()]
-    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
-    with monkeypatch.context() as mp:
-        mp.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
-        rl = ralg.update()
-    ol = alg.update(tperm, sperm)
-    for a, b in zip(ol, rl):
-        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (ol, rl)
-    assert abs(alg.learning_rate - ralg.learning_rate) < 1e-9
-    num = den = 0.0
-    for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
-        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
-    assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
+    r = side_by_side(variant, policy, ALG_CTS if variant == "mcp_cts" else ALG, N=16, T=4, seed=0, monkeypatch=monkeypatch)
+    assert r["act"] < 2e-5 and r["returns"] < 2e-5 and r["adv"] < 2e-4, r
+    assert r["loss"] < 2e-4 and r["lr"] < 1e-9 and r["update_rel"] < 5e-3, r
 
 
 def _mcp_ref(eo, logits, E, A):
