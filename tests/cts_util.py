@@ -109,3 +109,59 @@ def side_by_side(variant, policy, alg_kw, N, T, seed, monkeypatch, H=5):
         num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
     out["update_rel"] = (num / max(den, 1e-30)) ** 0.5
     return out
+
+
+def side_by_side_ppo(policy, alg_kw, N, T, seed, monkeypatch):
+    """side_by_side for the plain PPO task: the reference's ActorCritic + PPO + RolloutStorage against this package's over the emulated C ABI."""
+    import contextlib
+    import importlib
+    import io
+    import sys
+    monkeypatch.syspath_prepend(REF_RSL)
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        monkeypatch.delitem(sys.modules, k)
+    RS = importlib.import_module("rsl_rl.storage.rollout_storage")
+    RefPPO = importlib.import_module("rsl_rl.algorithms.ppo").PPO
+    RefAC = importlib.import_module("rsl_rl.modules.actor_critic").ActorCritic
+    from go2_rl_gym_b200.rl.algorithms import PPO
+    from go2_rl_gym_b200.rl.modules import ActorCritic
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefAC(45, 263, 12, **policy)
+        ac = ActorCritic(45, 263, 12, **policy)
+    ac.load_state_dict(ref.state_dict())
+    ralg, alg = RefPPO(ref, device="cpu", **alg_kw), PPO(ac, device="cpu", **alg_kw)
+    ralg.init_storage(N, T, [45], [263], [12]); alg.init_storage(N, T, [45], [263], [12])
+    g = torch.Generator().manual_seed(seed + 1)
+    obs, priv = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g)
+    rew, dones = 0.1 * torch.randn(T, N, generator=g), torch.rand(T, N, generator=g) < 0.05
+    out = {"act": 0.0}
+    with torch.inference_mode():
+        for t in range(T):
+            ralg.act(obs[t], priv[t])
+            alg.act(obs[t], priv[t])
+            for a, b in ((alg.storage.mu[t], ralg.transition.action_mean), (alg.storage.sigma[t], ralg.transition.action_sigma),
+                         (alg.storage.values[t], ralg.transition.values)):
+                out["act"] = max(out["act"], float((a - b).abs().max()))
+            for k in ("actions", "actions_log_prob"):
+                getattr(alg.storage, k)[t].copy_(getattr(ralg.transition, k).view_as(getattr(alg.storage, k)[t]))
+            ralg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+            alg.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+        ralg.compute_returns(priv[T])
+        alg.compute_returns(priv[T])
+    out["returns"] = float((alg.storage.returns - ralg.storage.returns).abs().max())
+    out["adv"] = float((alg.storage.advantages - ralg.storage.advantages).abs().max())
+    nb = alg_kw["num_mini_batches"]
+    perm = torch.randperm(nb * (N * T // nb), generator=g)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    with monkeypatch.context() as mp:
+        mp.setattr(RS.torch, "randperm", lambda n, **kw: perm.clone())
+        rl = ralg.update()
+    ol = alg.update(indices=perm)
+    out["loss"] = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(ol, rl))
+    out["lr"] = abs(alg.learning_rate - ralg.learning_rate)
+    num = den = 0.0
+    for (k, v), r in zip(ac.state_dict().items(), ref.state_dict().values()):
+        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
+    out["update_rel"] = (num / max(den, 1e-30)) ** 0.5
+    return out

@@ -15,7 +15,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import emu_rl  # noqa: E402
-from cts_util import side_by_side  # noqa: E402
+from cts_util import side_by_side, side_by_side_ppo  # noqa: E402
 
 
 def main():
@@ -26,7 +26,7 @@ def main():
     n_bad = 0
     for seed in range(lo, hi):
         rng = np.random.default_rng(seed)
-        variant = ["cts", "moe_cts", "moe_ng_cts", "ac_moe_cts", "dual_moe_cts", "mcp_cts"][int(rng.integers(0, 6))]
+        variant = ["ppo", "cts", "moe_cts", "moe_ng_cts", "ac_moe_cts", "dual_moe_cts", "mcp_cts"][int(rng.integers(0, 7))]
         w = lambda: int(rng.choice([16, 32, 64, 136, 160]))
         policy = dict(actor_hidden_dims=[w(), w(), w()], critic_hidden_dims=[w(), w(), w()], teacher_encoder_hidden_dims=[w(), w()],
                       student_encoder_hidden_dims=[w(), w()] + ([w()] if variant in ("moe_cts", "dual_moe_cts") else []),
@@ -49,7 +49,13 @@ def main():
         try:
             emu_rl.install(mp)
             mp.setenv("GO2_GEMM", gemm)
-            r = side_by_side(variant, policy, alg, N=N, T=T, seed=seed, monkeypatch=mp)
+            if variant == "ppo":
+                pol = dict(actor_hidden_dims=policy["actor_hidden_dims"], critic_hidden_dims=policy["critic_hidden_dims"], activation="elu",
+                           init_noise_std=policy["init_noise_std"])
+                akw = {k: v for k, v in alg.items() if k not in ("student_encoder_learning_rate", "teacher_env_ratio", "load_balance_coef")}
+                r = side_by_side_ppo(pol, akw, N=N, T=T, seed=seed, monkeypatch=mp)
+            else:
+                r = side_by_side(variant, policy, alg, N=N, T=T, seed=seed, monkeypatch=mp)
             ok = r["act"] < 5e-5 and r["returns"] < 5e-5 and r["adv"] < 5e-4 and r["loss"] < 5e-4 and r["lr"] < 1e-9 and r["update_rel"] < 2e-2
             msg = " ".join(f"{k}={v:.1e}" for k, v in r.items())
         except Exception as e:  # noqa: BLE001 - report and continue
