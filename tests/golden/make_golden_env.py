@@ -133,9 +133,13 @@ def install_rng(draws, num_envs):
             fr = sys._getframe(1)
             line, fn = fr.f_lineno, fr.f_code.co_name
             if self._where == "IU":
-                assert fn == "sample_disjoint_intervals" and line == 40, (fn, line)
                 ids = _ids(fr.f_locals["env_ids"])
-                comp = {454: 0, 461: 1}[fr.f_back.f_lineno]
+                if fn == "sample_single_interval":      # commands.dynamic_resample_commands = False (legged_robot.py:479-504)
+                    assert line == 53, line
+                    comp = {479: 0, 485: 1, 492: 2, 499: 2}[fr.f_back.f_lineno]
+                else:
+                    assert fn == "sample_disjoint_intervals" and line == 40, (fn, line)
+                    comp = {454: 0, 461: 1}[fr.f_back.f_lineno]
                 return draws.u(ids, ST_CMD_RESET if in_reset() else ST_CMD_CB, 0, comp)
             stream = ST_CMD_RESET if in_reset() else ST_CMD_CB
             if line in (469, 474):      # the yaw draw; with heading commands the same draw feeds the heading target (:469)
@@ -270,8 +274,9 @@ def build_reference_env(A, oracle, ref_cfg):
     r.motor_zero_offsets = torch.zeros(N, 12)
     r.p_gains_multiplier = torch.ones(N, 12)
     r.d_gains_multiplier = torch.ones(N, 12)
-    r.dynamic_sigma_cfg = ref_cfg.rewards.dynamic_sigma
-    r.terrain_max_sigmas = torch.tensor(r.dynamic_sigma_cfg["max_sigma"])
+    if ref_cfg.rewards.dynamic_sigma:        # legged_robot.py:1009-1011
+        r.dynamic_sigma_cfg = ref_cfg.rewards.dynamic_sigma
+        r.terrain_max_sigmas = torch.tensor(r.dynamic_sigma_cfg["max_sigma"])
     if not A.plane:
         r.terrain = A.terrain
         r.height_samples = torch.tensor(A.terrain.heightsamples).view(A.terrain.tot_rows, A.terrain.tot_cols)
@@ -339,7 +344,18 @@ def load_state_into_reference(r, A):
     r.contact_forces.copy_(T["contact_forces"])
 
 
-def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False, heading=False):
+def _apply(cfg, overrides):
+    """overrides: {"domain_rand.push_robots": False, ...} set on a config tree by dotted path."""
+    for path, val in (overrides or {}).items():
+        node = cfg
+        parts = path.split(".")
+        for p in parts[:-1]:
+            node = getattr(node, p)
+        assert hasattr(node, parts[-1]), path
+        setattr(node, parts[-1], val)
+
+
+def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False, heading=False, overrides=None):
     torch.manual_seed(seed)
     cfg = MyGO2Cfg()
     cfg.env.num_envs = N
@@ -347,6 +363,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
     cfg.seed = seed
     cfg.control.control_type, cfg.rewards.only_positive_rewards = control_type, only_positive     # switches outside the GO2 defaults
     cfg.commands.heading_command = heading
+    _apply(cfg, overrides)
     if heading:
         # the reference clips the masked yaw command with UNMASKED [N] bounds (legged_robot.py:415-419): it raises a shape error as soon as one
         # env holds its heading (stop_heading), so its heading mode only runs while no env ever stops: no stop at limits, no yaw kick at zero commands
@@ -389,6 +406,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
     ref_cfg.terrain.mesh_type = cfg.terrain.mesh_type
     ref_cfg.control.control_type, ref_cfg.rewards.only_positive_rewards = control_type, only_positive
     ref_cfg.commands.heading_command = heading
+    _apply(ref_cfg, overrides)
     if heading:
         ref_cfg.commands.stop_heading_at_limit, ref_cfg.commands.limit_ang_vel_at_zero_command_prob = False, 0.0
     draws = Draws(seed)
@@ -422,7 +440,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
         rec["ep_terrain_level_all"] = torch.tensor(float(ep.get("terrain_level_all", float("nan"))))
         outs.append({kk: vv.clone().numpy() for kk, vv in rec.items()})
     save = {"meta_N": N, "meta_K": K, "meta_seed": seed, "meta_plane": int(plane), "meta_start_counter": start_counter + 30,
-            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "meta_heading": int(heading),
+            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "meta_heading": int(heading), "meta_overrides": np.array(repr(overrides or {})),
             "actions": actions.numpy()}
     for k, v in S0.items():
         save["s0_" + k] = v.numpy()

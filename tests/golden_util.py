@@ -37,8 +37,15 @@ def load_case(name, device="cpu", **kw):
         cfg.control.control_type = "PVT"[int(z["meta_control_type"])]
         cfg.rewards.only_positive_rewards = bool(z["meta_only_positive"])
         cfg.commands.heading_command = bool(z["meta_heading"]) if "meta_heading" in z.files else False
-        if cfg.commands.heading_command:      # the settings under which the reference's heading mode runs at all (make_golden_env.py)
-            cfg.commands.stop_heading_at_limit, cfg.commands.limit_ang_vel_at_zero_command_prob = False, 0.0
+    if "meta_overrides" in z.files:          # config switches applied to both sides by make_golden_env.make_case(overrides=...)
+        import ast
+        for path, val in ast.literal_eval(str(z["meta_overrides"])).items():
+            node, parts = cfg, path.split(".")
+            for p in parts[:-1]:
+                node = getattr(node, p)
+            setattr(node, parts[-1], val)
+    if cfg.commands.heading_command:      # the settings under which the reference's heading mode runs at all (make_golden_env.py; applied last there too)
+        cfg.commands.stop_heading_at_limit, cfg.commands.limit_ang_vel_at_zero_command_prob = False, 0.0
     A = EnvArrays(cfg, device, seed=seed, **kw)
     for k in z.files:
         if k.startswith("s0_"):

@@ -346,3 +346,50 @@ def test_heading_mode_with_stop_flags_kernel_source_equals_oracle(packed):
         copy_state(Ac.tensors, Ae.tensors)
         Ae.tensors["stop_heading"].copy_(Ac.tensors["stop_heading"])
     assert seen_stop > 0
+
+
+PLAY = {"terrain.num_rows": 7, "terrain.num_cols": 7, "terrain.curriculum": False, "noise.add_noise": False, "domain_rand.randomize_friction": False,
+        "domain_rand.push_robots": False, "domain_rand.randomize_base_mass": False, "domain_rand.randomize_link_mass": False,
+        "domain_rand.randomize_base_com": False, "domain_rand.randomize_pd_gains": False, "domain_rand.randomize_motor_zero_offset": False}
+ODD = {"domain_rand.randomize_action_delay": False, "domain_rand.randomize_motor_strength": False, "commands.limit_vel_prob": 0.5,
+       "commands.limit_vel_invert_when_continuous": False, "commands.limit_ang_vel_at_zero_command_prob": 0.6, "commands.resampling_time": 0.2,
+       "terrain.move_down_by_accumulated_xy_command": False, "rewards.dynamic_sigma": None, "rewards.curriculum_rewards": [],
+       "commands.dynamic_resample_commands": False, "env.episode_length_s": 2, "normalization.clip_observations": 5.0, "control.action_scale": 0.5}
+BARE = {"commands.zero_command_curriculum": None, "commands.limit_vel_prob": 0.0, "domain_rand.push_interval_s": 0.3, "rewards.soft_dof_pos_limit": 0.5,
+        "rewards.base_height_target": 0.3, "rewards.tracking_sigma": 0.5, "normalization.clip_actions": 1.0}
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("name,overrides", [("play", PLAY), ("odd", ODD), ("bare", BARE)])
+def test_emulated_kernel_tracks_oracle_off_the_training_defaults(name, overrides, packed):
+    """The kernel's branches for configurations other than GO2 training: legged_gym/scripts/play.py's evaluation set-up (7 x 7 terrain without
+    curriculum, noise / pushes / most randomisation off) and two mixes of the remaining switches (single-interval command sampling, no dynamic
+    sigma, no reward / zero-command curricula, short episodes, other clips and scales).  The oracle side of the same switches is pinned against
+    the reference by tools/fuzz_reference_parity.py --switches."""
+    N = 40
+    cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 17
+    for path, val in overrides.items():
+        node, parts = cfg, path.split(".")
+        for p in parts[:-1]:
+            node = getattr(node, p)
+        assert hasattr(node, parts[-1]), path
+        setattr(node, parts[-1], val)
+    Ac, Ae = EnvArrays(cfg, "cpu", seed=17), EnvArrays(cfg, "cpu", seed=17)
+    orc, env = OracleEnv(Ac), EmuEnv(Ae, packed=packed)
+    orc.common_step_counter = env.common_step_counter = 24 * 3000
+    orc.reset_all(); env.reset_all()
+    g = torch.Generator().manual_seed(9)
+    Ac.tensors["episode_length_buf"].copy_(torch.randint(0, int(Ac.max_episode_length), (N,), generator=g).int())
+    copy_state(Ac.tensors, Ae.tensors)
+    n_reset = 0
+    for step in range(30):
+        a = 0.7 * torch.randn(N, 12, generator=g)
+        orc.step(a); env.step(a)
+        for k in ("reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel"):
+            assert torch.equal(Ac.tensors[k], Ae.tensors[k]), (name, step, k)
+        for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums"):
+            rtol, atol = TOL.get(k, TOL["default"])
+            assert np.allclose(Ae.tensors[k].numpy(), Ac.tensors[k].numpy(), rtol=rtol, atol=atol), (name, step, k)
+        n_reset += int(Ac.tensors["reset_buf"].sum())
+        copy_state(Ac.tensors, Ae.tensors)
+    assert n_reset > 0

@@ -19,11 +19,23 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import make_golden_env as H  # noqa: E402
 
 
+SWITCHES = {
+    "domain_rand.randomize_action_delay": [False], "domain_rand.randomize_motor_strength": [False], "domain_rand.randomize_motor_zero_offset": [False],
+    "domain_rand.randomize_pd_gains": [False], "domain_rand.push_robots": [False], "noise.add_noise": [False], "terrain.curriculum": [False],
+    "terrain.move_down_by_accumulated_xy_command": [False], "commands.limit_vel_prob": [0.0, 0.5], "commands.limit_vel_invert_when_continuous": [False],
+    "commands.limit_ang_vel_at_zero_command_prob": [0.0, 0.6], "commands.zero_command_curriculum": [None], "commands.resampling_time": [0.1, 1.0],
+    "rewards.dynamic_sigma": [None], "rewards.curriculum_rewards": [[]], "domain_rand.push_interval_s": [0.5], "env.episode_length_s": [5],
+    "normalization.clip_observations": [5.0], "normalization.clip_actions": [1.0], "control.action_scale": [0.5], "rewards.soft_dof_pos_limit": [0.5],
+    "rewards.base_height_target": [0.3], "rewards.tracking_sigma": [0.5], "commands.dynamic_resample_commands": [False],
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="20:30")
     ap.add_argument("--N", type=int, default=64)
     ap.add_argument("--K", type=int, default=8)
+    ap.add_argument("--switches", action="store_true", help="also flip config switches away from the GO2 defaults on both sides")
     ap.add_argument("--control_types", action="store_true", help="also draw control_type V / T (violent: the first contact solver can diverge to NaN there, and V control amplifies rounding; expect tolerance-level mismatches)")
     args = ap.parse_args()
     lo, hi = (int(x) for x in args.seeds.split(":"))
@@ -39,9 +51,16 @@ def main():
         N = int(args.N + 4 * rng.integers(0, 8))
         start = int(24 * rng.integers(10, 60000) - rng.integers(0, 24))
         heading = bool(rng.integers(0, 5) == 0)
+        if heading:      # a FRESH reference object applies its command-range curriculum lazily, at the first resampling after construction
+            start = start % (24 * 19000) + 240   # (legged_robot.py:433-446); the per-step heading clip would see the stale yaw range until then
         ctrl = "PPPVT"[int(rng.integers(0, 5))] if args.control_types else "P"
         name = f"fuzz{seed}"
-        H.make_case(name, plane=plane, N=N, K=args.K, seed=seed, start_counter=start, control_type=ctrl, heading=heading)
+        ov = {}
+        if args.switches:        # flip config switches away from the GO2 training defaults (the play.py configuration among them)
+            for path, vals in SWITCHES.items():
+                if rng.integers(0, 3) == 0:
+                    ov[path] = vals[int(rng.integers(0, len(vals)))]
+        H.make_case(name, plane=plane, N=N, K=args.K, seed=seed, start_counter=start, control_type=ctrl, heading=heading, overrides=ov)
         z, A = GU.load_case(name)
         O = OracleEnv(A)
         O.common_step_counter = int(z["meta_start_counter"])
@@ -53,8 +72,13 @@ def main():
             if bad:
                 bad_all.append((i, bad))
                 break
+            for k in z.files:          # continue from the reference's own state: tolerance-level drift must not accumulate over the steps
+                key = k[len(f"out{i}_"):]
+                if k.startswith(f"out{i}_") and key in A.tensors and key not in ("obs_buf", "privileged_obs_buf", "rew_buf"):
+                    t = A.tensors[key]
+                    t.copy_(torch.from_numpy(z[k]).to(t.dtype).reshape(t.shape))
         n_bad += bool(bad_all)
-        print(f"seed {seed}: N={N} plane={plane} start={start} ctrl={ctrl} heading={heading} resets={[int(z[f'out{i}_reset_buf'].sum()) for i in range(args.K)]} "
+        print(f"seed {seed}: N={N} plane={plane} start={start} ctrl={ctrl} heading={heading} switches={ov} resets={[int(z[f'out{i}_reset_buf'].sum()) for i in range(args.K)]} "
               f"-> {'OK' if not bad_all else 'MISMATCH ' + str(bad_all)[:600]}", flush=True)
     print("mismatching cases:", n_bad)
     return 1 if n_bad else 0
