@@ -313,3 +313,106 @@ def test_mcp_kernel_source_matches_torch_autograd(monkeypatch):
     a3 = torch.empty(n, A)
     call("go2_sample_actions_sigma", ptr(mu), ptr(sg), ptr(a3), ptr(lp), ptr(mo), ptr(so), n, A, 7, 0, ptr(step), 5)
     assert torch.equal(a3, a)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")
+@pytest.mark.parametrize("variant", ["ppo", "moe_cts", "ac_moe_cts", "mcp_cts"])
+def test_resume_from_a_reference_checkpoint(variant, monkeypatch, tmp_path):
+    """Checkpoint interop in the direction a user of the reference needs: a checkpoint written by the REFERENCE (its modules' state_dict and its
+    torch.optim.Adam state dicts after one update, the dict layout of on_policy_runner.py:268-277 / on_policy_runner_cts.py:287-294) is loaded into
+    this package's classes, then both sides run the NEXT update on the same data: the results must agree, i.e. weights, both Adam moments, the
+    step counts (bias correction) and the learning rate all arrived where they belong."""
+    import contextlib
+    import importlib
+    import io
+    import sys
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    monkeypatch.syspath_prepend(REF_RSL)
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        monkeypatch.delitem(sys.modules, k)
+    from golden import cts_cfg as cc
+    from golden.rl_cfg import CFG
+    from go2_rl_gym_b200.rl import algorithms as A, modules as Mo
+    torch.manual_seed(5)
+    N, T, H = 16, 6, 5
+    cts = variant != "ppo"
+    with contextlib.redirect_stdout(io.StringIO()):
+        if not cts:
+            pol, akw = dict(actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16]), CFG
+            ref = importlib.import_module("rsl_rl.modules.actor_critic").ActorCritic(45, 263, 12, **pol)
+            ralg = importlib.import_module("rsl_rl.algorithms.ppo").PPO(ref, device="cpu", **akw)
+            RS = importlib.import_module("rsl_rl.storage.rollout_storage")
+            mk = lambda: (lambda m: (m, A.PPO(m, device="cpu", **akw)))(Mo.ActorCritic(45, 263, 12, **pol))
+        else:
+            mod, cls, amod, acls, pol, akw = {"moe_cts": ("actor_critic_moe_cts", "ActorCriticMoECTS", "moe_cts", "MoECTS", cc.POLICY, cc.ALG),
+                                              "ac_moe_cts": ("actor_critic_ac_moe_cts", "ActorCriticACMoECTS", "ac_moe_cts", "ACMoECTS", cc.POLICY_AC, cc.ALG),
+                                              "mcp_cts": ("actor_critic_mcp_cts", "ActorCriticMCPCTS", "mcp_cts", "MCPCTS", cc.POLICY_MCP, cc.ALG_CTS)}[variant]
+            ref = getattr(importlib.import_module("rsl_rl.modules." + mod), cls)(45, 263, 12, N, H, **pol)
+            ralg = getattr(importlib.import_module("rsl_rl.algorithms." + amod), acls)(ref, N, H, device="cpu", **akw)
+            RS = importlib.import_module("rsl_rl.storage.rollout_storage_cts")
+            mk = lambda: (lambda m: (m, getattr(A, acls)(m, N, H, device="cpu", **akw)))(getattr(Mo, cls)(45, 263, 12, N, H, **pol))
+    ralg.init_storage(N, T, [45], [263], [12])
+    g = torch.Generator().manual_seed(6)
+
+    def rollout(alg_list, ref_first):
+        obs, priv, hist = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g), torch.randn(T + 1, N, H * 45, generator=g)
+        rew, dones = 0.1 * torch.randn(T, N, generator=g), torch.rand(T, N, generator=g) < 0.05
+        needs_obs = variant == "ac_moe_cts"
+        with torch.inference_mode():
+            for t in range(T):
+                args = (obs[t], priv[t], hist[t]) if cts else (obs[t], priv[t])
+                ref_first.act(*args)
+                for a in alg_list:
+                    a.act(*args)
+                    for k in ("actions", "actions_log_prob"):
+                        getattr(a.storage, k)[t].copy_(getattr(ref_first.transition, k).view_as(getattr(a.storage, k)[t]))
+                for a in [ref_first] + alg_list:
+                    a.process_env_step(rew[t], dones[t], {"time_outs": dones[t]})
+            last = (obs[T], priv[T], hist[T])
+            for a in [ref_first] + alg_list:
+                a.compute_returns(*((last if needs_obs else last[1:]) if cts else (priv[T],)))
+
+    def perms():
+        if cts:
+            nt, ns = ralg.teacher_num_envs * T, ralg.student_num_envs * T
+            return [torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)]
+        return [torch.randperm(N * T, generator=g)]
+
+    def ref_update(ps):
+        queue = [p.clone() for p in ps]
+        with monkeypatch.context() as mp:
+            mp.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
+            return ralg.update()
+
+    rollout([], ralg)
+    ref_update(perms())                                   # the reference trains one iteration ...
+    ckpt = {"model_state_dict": ref.state_dict(), "iter": 1, "infos": None}
+    if cts:
+        ckpt.update(optimizer1_state_dict=ralg.optimizer1.state_dict(), optimizer2_state_dict=ralg.optimizer2.state_dict())
+    else:
+        ckpt["optimizer_state_dict"] = ralg.optimizer.state_dict()
+    path = os.path.join(str(tmp_path), "model_1.pt")
+    torch.save(ckpt, path)                                # ... and writes its checkpoint
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, alg = mk()
+    alg.init_storage(N, T, [45], [263], [12])
+    d = torch.load(path, weights_only=False)
+    model.load_state_dict(d["model_state_dict"])
+    if cts:
+        alg.load_optimizer_state_dicts(d["optimizer1_state_dict"], d["optimizer2_state_dict"])
+    else:
+        alg.load_optimizer_state_dict(d["optimizer_state_dict"])
+    assert abs(alg.learning_rate - ralg.learning_rate) < 1e-12
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    rollout([alg], ralg)
+    ps = perms()
+    rl = ref_update(ps)
+    ol = alg.update(*ps) if cts else alg.update(indices=ps[0])
+    for a, b in zip(ol, rl):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (ol, rl)
+    assert abs(alg.learning_rate - ralg.learning_rate) < 1e-9
+    num = den = 0.0
+    for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
+        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
+    assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
