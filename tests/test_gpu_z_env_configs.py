@@ -1,0 +1,47 @@
+"""GPU parity of the DEFAULT library's env step against the CPU oracle for configurations other than GO2 training: the evaluation set-up of
+legged_gym/scripts/play.py and two mixes of the remaining config switches (the CPU twin, on the kernel-source emulation, is
+tests/test_emu_cpu.py::test_emulated_kernel_tracks_oracle_off_the_training_defaults; the oracle side of the same switches is pinned against the
+reference's own Python by tools/fuzz_reference_parity.py --switches).  Written after the round's GPU budget was spent: first run on hardware at
+round end, collected last."""
+import numpy as np
+import pytest
+import torch
+
+from go2_rl_gym_b200.envs.env_arrays import EnvArrays
+from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+from golden_util import TOL
+from test_emu_cpu import BARE, ODD, PLAY
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,overrides", [("play", PLAY), ("odd", ODD), ("bare", BARE)])
+def test_cuda_tracks_oracle_off_the_training_defaults(name, overrides):
+    from cuda_util import CudaEnv, copy_state
+    from oracle.oracle import OracleEnv
+    N = 256
+    cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 17
+    for path, val in overrides.items():
+        node, parts = cfg, path.split(".")
+        for p in parts[:-1]:
+            node = getattr(node, p)
+        setattr(node, parts[-1], val)
+    Ac, Ag = EnvArrays(cfg, "cpu", seed=17), EnvArrays(cfg, "cuda", seed=17)
+    orc, env = OracleEnv(Ac), CudaEnv(Ag)
+    orc.common_step_counter = env.common_step_counter = 24 * 3000
+    orc.reset_all(); env.reset_all(); torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(9)
+    Ac.tensors["episode_length_buf"].copy_(torch.randint(0, int(Ac.max_episode_length), (N,), generator=g).int())
+    copy_state(Ac.tensors, Ag.tensors)
+    n_reset = 0
+    for step in range(30):
+        a = 0.6 * torch.randn(N, 12, generator=g)
+        orc.step(a); env.step(a)
+        for k in ("reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel"):
+            assert torch.equal(Ac.tensors[k], Ag.tensors[k].cpu()), (name, step, k)
+        for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums"):
+            rtol, atol = TOL.get(k, TOL["default"])
+            assert np.allclose(Ag.tensors[k].cpu().numpy(), Ac.tensors[k].numpy(), rtol=rtol, atol=atol), (name, step, k)
+        n_reset += int(Ac.tensors["reset_buf"].sum())
+        copy_state(Ac.tensors, Ag.tensors)
+    assert n_reset > 0
