@@ -19,6 +19,8 @@ ap.add_argument("--modes", nargs="+", default=["P2"], help="thread maps to time:
 args = ap.parse_args()
 for N, mode in [(n, m) for n in args.num_envs for m in args.modes]:
     cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = args.mesh
+    if os.environ.get("GO2_RELAXED_CFG") == "1":      # the second library build's settings (GO2_B200_LIB=.../libgo2b200_relaxed.so)
+        cfg.sim.b200.limit_relax, cfg.sim.b200.contact_relax, cfg.sim.b200.limit_erp, cfg.sim.b200.state_guard = 0.5, 0.7, 0.8, 1
     t0 = time.time()
     env = Go2Robot(cfg, None, None, "cuda:0", True)
     env.set_step_mode(mode)
