@@ -26,7 +26,7 @@ def _need(cond, msg):
 
 def _vec(ptr, n, ctype=C.c_float):
     if n <= 0:
-        return np.zeros(0, dtype=np.ctypeslib.as_array((ctype * 1)()).dtype)
+        return np.zeros(0, dtype=np.dtype(ctype))
     _need(ptr, "null pointer")
     return np.ctypeslib.as_array((ctype * int(n)).from_address(int(ptr)))
 

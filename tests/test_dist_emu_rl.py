@@ -3,7 +3,6 @@ compute_returns() + update() of the algorithm classes (C ABI emulated by tests/e
 gradient + scalar tail, the all-reduced advantage statistics, the 1 / world_size scaling of the student pass — and must end (a) bit-identical on
 both ranks and (b) equal, to summation-order tolerance, to ONE process that runs the whole batch with the mini-batches composed of the same samples."""
 import os
-import sys
 
 import numpy as np
 import pytest
@@ -11,7 +10,7 @@ import torch
 import torch.multiprocessing as mp
 
 import emu_rl
-from cts_util import STORAGE_KEYS, make_cts
+from cts_util import STORAGE_KEYS
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NB = 4          # mini-batches (golden/cts_cfg.py, golden/rl_cfg.py)
