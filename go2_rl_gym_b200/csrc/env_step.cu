@@ -69,6 +69,23 @@ step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restr
 #endif
 }
 
+// The packed map with FEWER envs per CTA (E = 4: 128 threads, 4 CTAs / SM at 128 registers): the same 16 envs per SM as P2, but four independent
+// barrier groups instead of two, so the serial LEGS phase of one CTA (one busy warp) overlaps the WIDE phases of three others.  The leg warp then
+// carries 4 E items (half its lanes at E = 4): more issued instructions, which the 25 %-used issue slots absorb.  Built after round 1's GPU budget
+// was spent: bit-identical to the other maps in the host emulation, unmeasured on hardware (mode "Q4").
+template <int E, int MINB>
+__global__ void __launch_bounds__(32 * E, MINB)
+step_kernel_quad(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
+                 const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
+  const int e0 = blockIdx.x * E;
+  StepCtx X{cfg, mdl, &buf, sp, actions};
+  Lane L;
+  init_roles(L, threadIdx.x, 1, e0, min(E, cfg->num_envs - e0), E);
+  step_env(L, smem, X);
+}
+
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
 reset_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
              const Go2StepParams* __restrict__ sp) {
@@ -128,7 +145,7 @@ struct Go2Env {
 };
 
 static int parse_step_mode(const char* m) {
-  return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : -1;
+  return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : -1;
 }
 
 namespace go2 {
@@ -152,6 +169,17 @@ static int launch_packed(Go2Env* h, const float* actions, const Go2StepParams* s
     attr = true;
   }
   step_kernel_packed<MINB><<<(h->cfg.num_envs + 7) / 8, 256, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
+  return 0;
+}
+template <int E, int MINB>
+static int launch_quad(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
+  const int smem = E * (int)sizeof(WarpSmem);
+  static bool attr = false;
+  if (!attr) {
+    GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_quad<E, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  step_kernel_quad<E, MINB><<<(h->cfg.num_envs + E - 1) / E, 32 * E, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   return 0;
 }
 }  // namespace go2
@@ -217,10 +245,11 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
 // Thread map of the step kernel (same results bit for bit; tuning / A-B aid).  Default "P2"; the GO2_STEP_MODE environment variable
 // presets it at create time.
 //   "P2": packed map, 8 envs per 256-thread CTA, 2 CTAs/SM (128 registers) · "P3": the same with 3 CTAs/SM (80 registers)
+//   "Q4": packed map with 4 envs per 128-thread CTA, 4 CTAs/SM (unmeasured: built after round 1's GPU budget was spent)
 //   "8p": warp per env, 8 warps per CTA, CTA barrier at substep boundaries (the previous default: 203 us at 4096 envs)
 //   "4" : warp per env, 4 warps per CTA, no barrier (the first kernel: 239 us)
 int go2_env_set_step_mode(Go2Env* h, const char* mode) {
-  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P3, 8p, 4)");
+  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P3, Q4, 8p, 4)");
   h->step_mode = parse_step_mode(mode);
   return 0;
 }
@@ -244,7 +273,8 @@ int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, v
   const int mode = h->step_mode;
   if (mode == 0) go2::step_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   else {
-    int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2>(h, actions, sp, st) : go2::launch_packed<3>(h, actions, sp, st);
+    int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2>(h, actions, sp, st)
+           : mode == 3 ? go2::launch_packed<3>(h, actions, sp, st) : go2::launch_quad<4, 4>(h, actions, sp, st);
     if (rc) return rc;
   }
   go2::count_launch();

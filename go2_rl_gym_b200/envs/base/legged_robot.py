@@ -241,7 +241,7 @@ class LeggedRobot:
             self.extras["time_outs"] = self.time_out_buf
 
     def set_step_mode(self, mode):
-        """Thread map of the step kernel: "P2" (default), "P3", "8p", "4" — identical results, different speed (tuning / tests)."""
+        """Thread map of the step kernel: "P2" (default), "P3", "Q4", "8p", "4" — identical results, different speed (tuning / tests)."""
         _abi.check(self._lib.go2_env_set_step_mode(self._h, str(mode).encode()), self._lib)
 
     def substeps(self, tau, n):

@@ -189,7 +189,8 @@ typedef struct Go2Env Go2Env;
 /* Replaces gym.create_sim/prepare_sim + acquire_*_tensor (legged_robot.py:292-310,769-787). 0 on success. */
 int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvBuffers* bufs, Go2Env** out);
 void go2_env_destroy(Go2Env* env);
-/* Thread map of the fused step kernel: "P2" (default; 8 envs packed per CTA), "P3", "8p", "4" (warp per env).  Same results bit for bit. */
+/* Thread map of the fused step kernel: "P2" (default; 8 envs packed per CTA), "P3", "Q4" (4 envs packed per CTA), "8p", "4" (warp per env).
+ * Same results (bit for bit in the host emulation; each map is its own kernel instantiation on the GPU). */
 int go2_env_set_step_mode(Go2Env* env, const char* mode);
 /* Replaces LeggedRobot.step (legged_robot.py:60-100): the fused kernel. actions: device [N,12]. */
 int go2_env_step(Go2Env* env, const float* actions, const Go2StepParams* sp, void* cuda_stream);

@@ -9,12 +9,12 @@ using namespace go2;
 // One group = the threads that share phase barriers: a single warp (warp-per-env map) or a CTA of 8 warps / 8 envs (packed map).
 static int g_packed = 0;
 template <class F> static void for_groups(const Go2EnvConfig* C, F&& f) {
-  const int per = g_packed ? 8 : 1, nwarps = g_packed ? 8 : 1, NT = 32 * nwarps;
+  const int per = g_packed == 1 ? 8 : (g_packed ? g_packed : 1), nwarps = per, NT = 32 * nwarps;   // g_packed: 0 warp per env, 1 / 8 = P2, 4 = Q4
   std::vector<WarpSmem> SM(per);
   std::vector<Lane> lanes(NT);
   for (int e0 = 0; e0 < C->num_envs; e0 += per) {
     const int n_local = std::min(per, C->num_envs - e0);
-    for (int t = 0; t < NT; ++t) init_roles(lanes[t], t, g_packed, e0, n_local, nwarps);
+    for (int t = 0; t < NT; ++t) init_roles(lanes[t], t, g_packed ? 1 : 0, e0, n_local, nwarps);
     f(lanes.data(), NT, SM.data());
   }
 }

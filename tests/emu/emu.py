@@ -20,7 +20,8 @@ def load():
 
 class EmuEnv:
     def __init__(self, arrays, packed=False):
-        """packed: emulate the 8-envs-per-CTA thread map (LEGS / COLS items of 8 envs share warps) instead of warp-per-env."""
+        """packed: True / 8 = emulate the 8-envs-per-CTA thread map (LEGS / COLS items of 8 envs share warps), 4 = the 4-envs-per-CTA map ("Q4"),
+        False = warp per env."""
         assert arrays.device.type == "cpu"
         self.A = arrays
         self.lib = load()

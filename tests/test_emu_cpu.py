@@ -70,12 +70,14 @@ def test_emulated_kernel_tracks_oracle(packed, N):
     assert n_reset > 0
 
 
-def test_packed_map_is_bit_identical_to_warp_per_env():
-    """The two thread maps run the same arithmetic in the same order: every buffer must be bit-identical over a rollout with resets."""
+@pytest.mark.parametrize("packed", [True, 4])
+def test_packed_map_is_bit_identical_to_warp_per_env(packed):
+    """The thread maps (warp per env; 8 envs packed per CTA = "P2"; 4 envs packed per CTA = "Q4") run the same arithmetic in the same order:
+    every buffer must be bit-identical over a rollout with resets."""
     N = 29   # partial last group
     cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 4
     A0, A1 = EnvArrays(cfg, "cpu", seed=4), EnvArrays(cfg, "cpu", seed=4)
-    e0, e1 = EmuEnv(A0, packed=False), EmuEnv(A1, packed=True)
+    e0, e1 = EmuEnv(A0, packed=False), EmuEnv(A1, packed=packed)
     e0.common_step_counter = e1.common_step_counter = 24 * 100
     e0.reset_all(); e1.reset_all()
     g = torch.Generator().manual_seed(9)

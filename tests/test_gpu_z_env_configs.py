@@ -45,3 +45,10 @@ def test_cuda_tracks_oracle_off_the_training_defaults(name, overrides):
         n_reset += int(Ac.tensors["reset_buf"].sum())
         copy_state(Ac.tensors, Ag.tensors)
     assert n_reset > 0
+
+
+def test_q4_thread_map_agrees_with_the_default():
+    """"Q4" (4 envs packed per 128-thread CTA, 4 CTAs / SM; go2_env_set_step_mode) against the default "P2" map: the comparison of
+    tests/test_gpu_properties.py::test_thread_maps_agree, incl. a partially filled last CTA and envs that time out."""
+    from test_gpu_properties import test_thread_maps_agree
+    test_thread_maps_agree("Q4")
