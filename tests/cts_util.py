@@ -28,7 +28,7 @@ def make_cts(variant, Z, device):
 REF_RSL = "/root/reference/rsl_rl"
 
 
-def side_by_side(variant, policy, alg_kw, N, T, seed, monkeypatch, H=5):
+def side_by_side(variant, policy, alg_kw, N, T, seed, monkeypatch, H=5, iters=1):
     """Run the REFERENCE's module + algorithm (imported from /root/reference/rsl_rl; build container only) and this package's over the emulated C
     ABI on the same random data: T x (act, process_env_step), compute_returns, update with shared permutations.  Returns the worst deviations:
     act (mu / sigma / value), returns, adv, loss (relative), lr, update_rel (relative error of the parameter update)."""
@@ -74,9 +74,21 @@ def side_by_side(variant, policy, alg_kw, N, T, seed, monkeypatch, H=5):
     ralg, alg = RefAlg(ref, N, H, device="cpu", **alg_kw), ours_a(model, N, H, device="cpu", **alg_kw)
     ralg.init_storage(N, T, [45], [263], [12]); alg.init_storage(N, T, [45], [263], [12])
     g = torch.Generator().manual_seed(seed + 1)
+    out = {"act": 0.0, "returns": 0.0, "adv": 0.0, "loss": 0.0}
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    for it in range(iters):          # consecutive iterations on the SAME instances: Adam moments / step counts, the learning rate and the storage carry over
+        _one_iteration(ralg, alg, RS, needs_obs, N, T, H, g, out, monkeypatch)
+    out["lr"] = abs(alg.learning_rate - ralg.learning_rate)
+    num = den = 0.0
+    for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
+        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
+    out["update_rel"] = (num / max(den, 1e-30)) ** 0.5
+    return out
+
+
+def _one_iteration(ralg, alg, RS, needs_obs, N, T, H, g, out, monkeypatch):
     obs, priv, hist = torch.randn(T + 1, N, 45, generator=g), torch.randn(T + 1, N, 263, generator=g), torch.randn(T + 1, N, H * 45, generator=g)
     rew, dones = 0.1 * torch.randn(T, N, generator=g), torch.rand(T, N, generator=g) < 0.05
-    out = {"act": 0.0}
     with torch.inference_mode():
         for t in range(T):
             ralg.act(obs[t], priv[t], hist[t])
@@ -91,24 +103,17 @@ def side_by_side(variant, policy, alg_kw, N, T, seed, monkeypatch, H=5):
         last = (obs[T], priv[T], hist[T])
         ralg.compute_returns(*(last if needs_obs else last[1:]))
         alg.compute_returns(*(last if needs_obs else last[1:]))
-    out["returns"] = float((alg.storage.returns - ralg.storage.returns).abs().max())
-    out["adv"] = float((alg.storage.advantages - ralg.storage.advantages).abs().max())
+    out["returns"] = max(out["returns"], float((alg.storage.returns - ralg.storage.returns).abs().max()))
+    out["adv"] = max(out["adv"], float((alg.storage.advantages - ralg.storage.advantages).abs().max()))
     nt, ns = alg.teacher_num_envs * T, alg.student_num_envs * T
     tperm, sperm = torch.randperm(nt, generator=g), torch.randperm(ns, generator=g)
     queue = [tperm.clone(), sperm.clone()]
-    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
     with monkeypatch.context() as mp:
         mp.setattr(RS.torch, "randperm", lambda n, **kw: queue.pop(0))
         rl = ralg.update()
     ol = alg.update(tperm, sperm)
     assert len(ol) == len(rl)
-    out["loss"] = max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(ol, rl))
-    out["lr"] = abs(alg.learning_rate - ralg.learning_rate)
-    num = den = 0.0
-    for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
-        num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
-    out["update_rel"] = (num / max(den, 1e-30)) ** 0.5
-    return out
+    out["loss"] = max(out["loss"], max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(ol, rl)))
 
 
 def side_by_side_ppo(policy, alg_kw, N, T, seed, monkeypatch):

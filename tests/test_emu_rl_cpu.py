@@ -246,6 +246,21 @@ def test_registered_width_variants_match_the_imported_reference(variant, policy,
     assert r["loss"] < 2e-4 and r["lr"] < 1e-9 and r["update_rel"] < 5e-3, r
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")
+@pytest.mark.parametrize("variant", ["moe_cts", "dual_moe_cts", "mcp_cts"])
+def test_three_consecutive_iterations_track_the_imported_reference(variant, monkeypatch):
+    """Rollout + returns + update, three times on the SAME instances, the reference alongside: what carries over between iterations (both Adam
+    states and their step counts, the KL-adaptive learning rate, the cleared storage, derived operand copies) must keep the two in step."""
+    from cts_util import side_by_side
+    from golden import cts_cfg as cc
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    policy, alg_kw = {"moe_cts": (cc.POLICY, cc.ALG), "dual_moe_cts": (cc.POLICY_DUAL, cc.ALG), "mcp_cts": (cc.POLICY_MCP, cc.ALG_CTS)}[variant]
+    r = side_by_side(variant, policy, alg_kw, N=16, T=6, seed=2, monkeypatch=monkeypatch, iters=3)
+    assert r["act"] < 2e-4 and r["returns"] < 2e-4 and r["adv"] < 2e-3, r            # the weights of iterations 2 and 3 already differ by rounding
+    assert r["loss"] < 1e-3 and r["lr"] < 1e-9 and r["update_rel"] < 1e-2, r
+
+
 def _mcp_ref(eo, logits, E, A):
     """ActorMCP.forward's composition (actor_critic_mcp_cts.py:229-247) in plain torch."""
     w = torch.sigmoid(logits).unsqueeze(-1)
