@@ -355,7 +355,7 @@ def _apply(cfg, overrides):
         setattr(node, parts[-1], val)
 
 
-def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False, heading=False, overrides=None):
+def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_type="P", only_positive=False, heading=False, overrides=None, b200=None):
     torch.manual_seed(seed)
     cfg = MyGO2Cfg()
     cfg.env.num_envs = N
@@ -364,6 +364,8 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
     cfg.control.control_type, cfg.rewards.only_positive_rewards = control_type, only_positive     # switches outside the GO2 defaults
     cfg.commands.heading_command = heading
     _apply(cfg, overrides)
+    for k, v in (b200 or {}).items():       # knobs of this package's contact solver (no reference counterpart: the oracle physics serves both sides)
+        setattr(cfg.sim.b200, k, v)
     if heading:
         # the reference clips the masked yaw command with UNMASKED [N] bounds (legged_robot.py:415-419): it raises a shape error as soon as one
         # env holds its heading (stop_heading), so its heading mode only runs while no env ever stops: no stop at limits, no yaw kick at zero commands
@@ -440,7 +442,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
         rec["ep_terrain_level_all"] = torch.tensor(float(ep.get("terrain_level_all", float("nan"))))
         outs.append({kk: vv.clone().numpy() for kk, vv in rec.items()})
     save = {"meta_N": N, "meta_K": K, "meta_seed": seed, "meta_plane": int(plane), "meta_start_counter": start_counter + 30,
-            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "meta_heading": int(heading), "meta_overrides": np.array(repr(overrides or {})),
+            "meta_control_type": "PVT".index(control_type), "meta_only_positive": int(only_positive), "meta_heading": int(heading), "meta_overrides": np.array(repr(dict(overrides or {}, **{"sim.b200." + k: v for k, v in (b200 or {}).items()}))),
             "actions": actions.numpy()}
     for k, v in S0.items():
         save["s0_" + k] = v.numpy()

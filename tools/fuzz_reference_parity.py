@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--N", type=int, default=64)
     ap.add_argument("--K", type=int, default=8)
     ap.add_argument("--switches", action="store_true", help="also flip config switches away from the GO2 defaults on both sides")
+    ap.add_argument("--relaxed", action="store_true", help="oracle physics with the relaxed contact solver + state guard (the second library build's settings)")
     ap.add_argument("--control_types", action="store_true", help="also draw control_type V / T (violent: the first contact solver can diverge to NaN there, and V control amplifies rounding; expect tolerance-level mismatches)")
     args = ap.parse_args()
     lo, hi = (int(x) for x in args.seeds.split(":"))
@@ -60,7 +61,8 @@ def main():
             for path, vals in SWITCHES.items():
                 if rng.integers(0, 3) == 0:
                     ov[path] = vals[int(rng.integers(0, len(vals)))]
-        H.make_case(name, plane=plane, N=N, K=args.K, seed=seed, start_counter=start, control_type=ctrl, heading=heading, overrides=ov)
+        H.make_case(name, plane=plane, N=N, K=args.K, seed=seed, start_counter=start, control_type=ctrl, heading=heading, overrides=ov,
+                    b200=dict(limit_relax=0.5, contact_relax=0.7, limit_erp=0.8, state_guard=1) if args.relaxed else None)
         z, A = GU.load_case(name)
         O = OracleEnv(A)
         O.common_step_counter = int(z["meta_start_counter"])
