@@ -24,7 +24,7 @@ def test_emulated_kernel_matches_reference_golden(name, packed):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading"])
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "rough_relaxed", "plane_relaxed"])
 def test_emulated_kernel_matches_reference_golden_with_env_switches(name, packed):
     """control_type 'V' / 'T' and only_positive_rewards (compiled into the kernel with -DGO2_RELAXED_SOLVER=1 like the emulation):
     every recorded step of the reference-made fixture, state re-synchronised to the fixture between steps."""

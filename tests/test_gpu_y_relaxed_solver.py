@@ -119,7 +119,7 @@ def test_state_guard_contains_a_diverged_env_on_the_gpu():
     assert float(dirty[1]["root_states"][9, 7:10].norm()) <= 1000.0 * (1 + 1e-5) or bool(dirty[1]["reset_buf"][9])
 
 
-@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading"])
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "rough_relaxed", "plane_relaxed"])
 def test_env_switches_match_reference_golden(name):
     """control_type 'V' / 'T' and only_positive_rewards (legged_robot.py:605-618,266-267) against the fixture made by the REFERENCE's
     own Python: first recorded step, same tolerances as the kernel-source emulation (tests/test_emu_cpu.py)."""
