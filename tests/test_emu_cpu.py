@@ -70,7 +70,7 @@ def test_emulated_kernel_tracks_oracle(packed, N):
     assert n_reset > 0
 
 
-@pytest.mark.parametrize("packed", [True, 4])
+@pytest.mark.parametrize("packed", [True, 4, 2])
 def test_packed_map_is_bit_identical_to_warp_per_env(packed):
     """The thread maps (warp per env; 8 envs packed per CTA = "P2"; 4 envs packed per CTA = "Q4") run the same arithmetic in the same order:
     every buffer must be bit-identical over a rollout with resets."""

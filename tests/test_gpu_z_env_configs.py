@@ -47,8 +47,9 @@ def test_cuda_tracks_oracle_off_the_training_defaults(name, overrides):
     assert n_reset > 0
 
 
-def test_q4_thread_map_agrees_with_the_default():
-    """"Q4" (4 envs packed per 128-thread CTA, 4 CTAs / SM; go2_env_set_step_mode) against the default "P2" map: the comparison of
-    tests/test_gpu_properties.py::test_thread_maps_agree, incl. a partially filled last CTA and envs that time out."""
+@pytest.mark.parametrize("mode", ["Q4", "Q2"])
+def test_q_thread_maps_agree_with_the_default(mode):
+    """"Q4" / "Q2" (4 / 2 envs packed per 128- / 64-thread CTA, 4 / 8 CTAs per SM; go2_env_set_step_mode) against the default "P2" map: the
+    comparison of tests/test_gpu_properties.py::test_thread_maps_agree, incl. a partially filled last CTA and envs that time out."""
     from test_gpu_properties import test_thread_maps_agree
-    test_thread_maps_agree("Q4")
+    test_thread_maps_agree(mode)

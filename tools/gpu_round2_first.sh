@@ -17,7 +17,7 @@ for cfg in "go2 4096" "go2 8192" "go2_cts 8192" "go2_moe_cts 8192" "go2_moe_ng_c
   set -- $cfg; timeout 300 python tools/bench_iter.py --task $1 --num_envs $2 --iters 6 2>&1 | grep "^it\|Error\|error" | tail -3 | sed "s/^/$1 $2: /" >> $O/iter_tasks_$TAG.log
 done
 # 4. the second library build (relaxed solver + state guard): step-kernel A/B against the default build, then the bench line with it
-timeout 240 python tools/bench_env_step.py --num_envs 4096 8192 --modes P2 Q4 8p --steps 100 > $O/env_step_default_$TAG.log 2>&1
+timeout 240 python tools/bench_env_step.py --num_envs 4096 8192 --modes P2 Q4 Q2 8p --steps 100 > $O/env_step_default_$TAG.log 2>&1
 GO2_B200_LIB=$PWD/go2_rl_gym_b200/libgo2b200_relaxed.so GO2_RELAXED_CFG=1 timeout 240 python tools/bench_env_step.py --num_envs 4096 8192 --modes P2 --steps 100 > $O/env_step_relaxed_$TAG.log 2>&1
 # 5. ncu: launch list of one iteration of the MCP task (new kernels), full capture of the step kernel of the relaxed build
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2000 -c 2500 --csv --log-file $O/launches_mcp_$TAG.csv python tools/bench_iter.py --task go2_mcp_cts --num_envs 4096 --iters 1 > $O/ncu_mcp_stdout_$TAG.log 2>&1
