@@ -64,3 +64,18 @@ def test_create_rejects_solver_settings_the_build_does_not_carry():
     cfg.limit_relax, cfg.contact_relax = 0.5, 0.7
     rc = relaxed.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
     assert rc != 0 and b"joint axes" in relaxed.go2_last_error()
+
+
+@pytest.mark.parametrize("name", ["libgo2b200.so", "libgo2b200_relaxed.so"])
+def test_every_bound_trainer_entry_point_is_exported_and_declared(name):
+    """rl/_ops.py binds its whole signature table when the library is first used: one missing symbol would take the trainer (and bench.py) down."""
+    import __graft_entry__ as ge
+    ge.build()
+    from go2_rl_gym_b200.rl import _ops
+    lib = ctypes.CDLL(os.path.join(ROOT, "go2_rl_gym_b200", name))
+    hdr = open(os.path.join(ROOT, "include", "go2_b200.h")).read()
+    for sym, sig in _ops._SIGS.items():
+        assert hasattr(lib, sym), sym
+        m = re.search(r"\bint\s+" + sym + r"\s*\(([^;]*)\)\s*;", hdr)
+        assert m, f"{sym} is not declared in include/go2_b200.h"
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(sig), (sym, m.group(1))      # argument count incl. the stream
