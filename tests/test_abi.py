@@ -78,4 +78,14 @@ def test_every_bound_trainer_entry_point_is_exported_and_declared(name):
         assert hasattr(lib, sym), sym
         m = re.search(r"\bint\s+" + sym + r"\s*\(([^;]*)\)\s*;", hdr)
         assert m, f"{sym} is not declared in include/go2_b200.h"
-        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(sig), (sym, m.group(1))      # argument count incl. the stream
+        params = [a.strip() for a in m.group(1).split(",") if a.strip()]
+        assert len(params) == len(sig), (sym, m.group(1))                       # argument count incl. the stream
+        for prm, ct in zip(params, sig):                                           # ... and each argument's C type against its ctypes type
+            prm = re.sub(r"/\*.*?\*/", "", prm).strip()
+            if "*" in prm:
+                want = ctypes.c_void_p
+            else:
+                base = " ".join(prm.split()[:-1]).replace("const ", "").strip()
+                want = {"int": ctypes.c_int, "long": ctypes.c_long, "float": ctypes.c_float, "double": ctypes.c_double, "uint64_t": ctypes.c_uint64,
+                        "uint32_t": ctypes.c_uint32}[base]
+            assert ct is want, (sym, prm, ct)
