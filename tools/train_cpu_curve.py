@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--num_envs", type=int, default=1024)
     ap.add_argument("--iterations", type=int, default=150)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--relaxed", action="store_true", help="oracle physics with the relaxed contact solver + state guard (second library build's settings)")
     args = ap.parse_args()
     from rsl_rl.algorithms import PPO
     from rsl_rl.modules import ActorCritic
@@ -40,6 +41,8 @@ def main():
     N, T = args.num_envs, 24
     cfg = GO2Cfg()
     cfg.env.num_envs, cfg.terrain.mesh_type, cfg.seed = N, "heightfield", args.seed
+    if args.relaxed:
+        cfg.sim.b200.limit_relax, cfg.sim.b200.contact_relax, cfg.sim.b200.limit_erp, cfg.sim.b200.state_guard = 0.5, 0.7, 0.8, 1
     A = EnvArrays(cfg, "cpu", seed=args.seed)
     env = OracleEnv(A)
     env.reset_all()
@@ -54,7 +57,7 @@ def main():
     cur_rew, cur_len = torch.zeros(N), torch.zeros(N)
     done_rew, done_len = [], []
     i_track = _abi.REWARD_NAMES.index("tracking_lin_vel")
-    print(f"# go2 rough-terrain heightfield, {N} envs, reference rsl_rl PPO (cpu, {torch.get_num_threads()} threads) on the oracle env; columns:")
+    print(f"# {'RELAXED contact solver + state guard; ' if args.relaxed else ''}go2 rough-terrain heightfield, {N} envs, reference rsl_rl PPO (cpu, {torch.get_num_threads()} threads) on the oracle env; columns:")
     print("# iter  mean_reward/step  mean_episode_return(last 100)  mean_episode_length(last 100)  mean_terrain_level  tracking_lin_vel/step  action_std  lr  s/iter")
     for it in range(args.iterations):
         t0 = time.time()
