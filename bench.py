@@ -339,6 +339,16 @@ def _main(out):
                 "split_ms": {"collection": col_ms, "learning": lrn_ms}}
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
+        try:    # CUDA graphs that captured NCCL kernels (GO2_DIST_GRAPH=1) must be gone before their communicator is: drop every graph set first
+            import gc
+            for o in (alg, runner):
+                for name in ("_graphs", "_rollout_graphs"):
+                    if hasattr(o, name):
+                        setattr(o, name, None)
+            gc.collect()
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001 - teardown must not turn a finished measurement into a failed run
+            pass
         dist.destroy_process_group()
 
 
