@@ -71,3 +71,15 @@ def compare_step(z, i, tensors, keys=None, skip=(), tol=None):
                 err = np.abs(got - ref)
                 bad.append((name, float(err.max()), np.unravel_index(err.argmax(), err.shape)))
     return bad
+
+
+# configurations other than GO2 training (tests/test_emu_cpu.py, tests/test_gpu_z_env_configs.py): play.py's evaluation set-up and two switch mixes
+PLAY = {"terrain.num_rows": 7, "terrain.num_cols": 7, "terrain.curriculum": False, "noise.add_noise": False, "domain_rand.randomize_friction": False,
+        "domain_rand.push_robots": False, "domain_rand.randomize_base_mass": False, "domain_rand.randomize_link_mass": False,
+        "domain_rand.randomize_base_com": False, "domain_rand.randomize_pd_gains": False, "domain_rand.randomize_motor_zero_offset": False}
+ODD = {"domain_rand.randomize_action_delay": False, "domain_rand.randomize_motor_strength": False, "commands.limit_vel_prob": 0.5,
+       "commands.limit_vel_invert_when_continuous": False, "commands.limit_ang_vel_at_zero_command_prob": 0.6, "commands.resampling_time": 0.2,
+       "terrain.move_down_by_accumulated_xy_command": False, "rewards.dynamic_sigma": None, "rewards.curriculum_rewards": [],
+       "commands.dynamic_resample_commands": False, "env.episode_length_s": 2, "normalization.clip_observations": 5.0, "control.action_scale": 0.5}
+BARE = {"commands.zero_command_curriculum": None, "commands.limit_vel_prob": 0.0, "domain_rand.push_interval_s": 0.3, "rewards.soft_dof_pos_limit": 0.5,
+        "rewards.base_height_target": 0.3, "rewards.tracking_sigma": 0.5, "normalization.clip_actions": 1.0}

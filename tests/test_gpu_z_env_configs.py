@@ -9,8 +9,7 @@ import torch
 
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays
 from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
-from golden_util import TOL
-from test_emu_cpu import BARE, ODD, PLAY
+from golden_util import BARE, ODD, PLAY, TOL
 
 pytestmark = pytest.mark.gpu
 
