@@ -73,7 +73,7 @@ def compare_step(z, i, tensors, keys=None, skip=(), tol=None):
     return bad
 
 
-# configurations other than GO2 training (tests/test_emu_cpu.py, tests/test_gpu_z_env_configs.py): play.py's evaluation set-up and two switch mixes
+# configurations other than GO2 training (tests/test_emu_cpu.py, tests/test_gpu_v_env_configs.py): play.py's evaluation set-up and two switch mixes
 PLAY = {"terrain.num_rows": 7, "terrain.num_cols": 7, "terrain.curriculum": False, "noise.add_noise": False, "domain_rand.randomize_friction": False,
         "domain_rand.push_robots": False, "domain_rand.randomize_base_mass": False, "domain_rand.randomize_link_mass": False,
         "domain_rand.randomize_base_com": False, "domain_rand.randomize_pd_gains": False, "domain_rand.randomize_motor_zero_offset": False}

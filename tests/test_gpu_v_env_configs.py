@@ -9,7 +9,9 @@ import torch
 
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays
 from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
-from golden_util import BARE, ODD, PLAY, TOL
+from golden_util import BARE, ODD, PLAY, TOL as _TOL
+
+TOL = {k: (3 * r, 3 * a) for k, (r, a) in _TOL.items()}      # first hardware run: 3 x the one-step bars of the verified kernel (golden_util.TOL)
 
 pytestmark = pytest.mark.gpu
 

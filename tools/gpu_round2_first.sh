@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 set -x
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi_$TAG.log 2>&1
-# 1. the whole GPU suite WITHOUT -x: the staged files (test_gpu_x_*, test_gpu_y_*, test_gpu_z_*) report every failure, not just the first
+# 1. the whole GPU suite WITHOUT -x: the staged files (test_gpu_v_*, test_gpu_w_*, test_gpu_x_*) report every failure, not just the first
 timeout 1500 python -m pytest tests -m gpu -q -rf 2>&1 | tail -60 > $O/gpu_tests_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1
 # 2. headline bench (default library) + reference arm
