@@ -356,7 +356,7 @@ def test_emulated_kernel_tracks_oracle_off_the_training_defaults(name, overrides
     """The kernel's branches for configurations other than GO2 training: legged_gym/scripts/play.py's evaluation set-up (7 x 7 terrain without
     curriculum, noise / pushes / most randomisation off) and two mixes of the remaining switches (single-interval command sampling, no dynamic
     sigma, no reward / zero-command curricula, short episodes, other clips and scales).  The oracle side of the same switches is pinned against
-    the reference by tools/fuzz_reference_parity.py --switches."""
+    the reference by tests/tools/fuzz_reference_parity.py --switches."""
     N = 40
     cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 17
     for path, val in overrides.items():

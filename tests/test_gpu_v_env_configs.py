@@ -1,7 +1,7 @@
 """GPU parity of the DEFAULT library's env step against the CPU oracle for configurations other than GO2 training: the evaluation set-up of
 legged_gym/scripts/play.py and two mixes of the remaining config switches (the CPU twin, on the kernel-source emulation, is
 tests/test_emu_cpu.py::test_emulated_kernel_tracks_oracle_off_the_training_defaults; the oracle side of the same switches is pinned against the
-reference's own Python by tools/fuzz_reference_parity.py --switches).  Written after the round's GPU budget was spent: first run on hardware at
+reference's own Python by tests/tools/fuzz_reference_parity.py --switches).  Written after the round's GPU budget was spent: first run on hardware at
 round end, collected last."""
 import numpy as np
 import pytest

@@ -2,9 +2,9 @@
 """Fuzz the step kernel's OWN SOURCE (csrc/env_step_core.cuh compiled with g++, tests/emu) against the CPU oracle: random env count (partially
 filled CTAs), thread map (warp per env / P2 / Q4), terrain or plane, config switches off the training defaults, control type, heading commands,
 relaxed solver and state guard; one step at a time from the oracle's state (flags exact, floats within tests/golden_util.TOL).  Complements
-tools/fuzz_reference_parity.py (reference vs oracle): together they tie the shipped kernel logic to the reference's Python.
+tests/tools/fuzz_reference_parity.py (reference vs oracle): together they tie the shipped kernel logic to the reference's Python.
 
-Usage: python tools/fuzz_kernel_source.py [--seeds 0:40] [--steps 25]"""
+Usage: python tests/tools/fuzz_kernel_source.py [--seeds 0:40] [--steps 25]"""
 import argparse
 import os
 import sys
@@ -12,8 +12,8 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")]
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "tools")]
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays  # noqa: E402
 from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg  # noqa: E402
 from cuda_util import copy_state  # noqa: E402

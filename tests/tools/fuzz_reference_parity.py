@@ -4,7 +4,7 @@
 tight tolerances of tests/golden_util.py.  Build container only (needs /root/reference).  The committed fixtures are three such cases; this tool
 widens the net (it found the float32 terrain-column assignment at env k N / 4).
 
-Usage: python tools/fuzz_reference_parity.py [--seeds 20:40] [--N 64] [--K 8]"""
+Usage: python tests/tools/fuzz_reference_parity.py [--seeds 20:40] [--N 64] [--K 8]"""
 import argparse
 import os
 import sys
@@ -13,7 +13,7 @@ import tempfile
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import make_golden_env as H  # noqa: E402

@@ -3,7 +3,7 @@
 algorithm options (clipped / unclipped value loss, fixed / adaptive schedule, entropy and load-balance coefficients, epochs, mini-batches), the
 REFERENCE's rsl_rl run side by side with this package's classes over the emulated C ABI (tests/cts_util.side_by_side).  Build container only.
 
-Usage: python tools/fuzz_trainer_parity.py [--seeds 0:30]"""
+Usage: python tests/tools/fuzz_trainer_parity.py [--seeds 0:30]"""
 import argparse
 import os
 import sys
@@ -12,7 +12,7 @@ import traceback
 import numpy as np
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import emu_rl  # noqa: E402
 from cts_util import side_by_side, side_by_side_ppo  # noqa: E402

@@ -8,7 +8,7 @@ it imports /root/reference, which does not exist on the GPU box (bench.py's `cpu
   (2) RL    the reference's rsl_rl `PPO` + `ActorCritic` + `RolloutStorage` on device='cpu' (all host threads): 24 x act /
             process_env_step, compute_returns, update at the bench's shapes
 
-Usage: python tools/time_reference_cpu.py [--num_envs 4096] [--steps 10] > profiles/<round>_reference_cpu_in_container.txt
+Usage: python tests/tools/time_reference_cpu.py [--num_envs 4096] [--steps 10] > profiles/<round>_reference_cpu_in_container.txt
 """
 import argparse
 import contextlib
@@ -19,7 +19,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import make_golden_env as H  # noqa: E402  (sets sys.path: ref_stub, /root/reference, /root/reference/rsl_rl, repo root)
 

@@ -7,7 +7,7 @@ Purpose: evidence that the environment this package simulates is LEARNABLE with 
 length and terrain level rise), independent of the CUDA path — which is compared with this oracle step by step elsewhere.  It is not the
 "mean episode return within 1e-3 of the reference" check of BASELINE.json: that needs PhysX (closed source, absent).
 
-Usage: python tools/train_cpu_curve.py [--num_envs 1024] [--iterations 150] > profiles/<round>_cpu_oracle_learning_curve.txt
+Usage: python tests/tools/train_cpu_curve.py [--num_envs 1024] [--iterations 150] > profiles/<round>_cpu_oracle_learning_curve.txt
 """
 import argparse
 import contextlib
@@ -18,7 +18,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = ["/root/reference/rsl_rl", ROOT]
 
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays  # noqa: E402
