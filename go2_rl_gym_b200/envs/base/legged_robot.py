@@ -240,6 +240,12 @@ class LeggedRobot:
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self.time_out_buf
 
+    def render(self, sync_frame_time=True):
+        """No viewer: this package is headless by construction (base_task.py:113-140 drives the Isaac Gym viewer)."""
+
+    def set_camera(self, position, lookat):
+        """No viewer (legged_robot.py:283-288); kept so that scripts written for the reference run unchanged."""
+
     def set_step_mode(self, mode):
         """Thread map of the step kernel: "P2" (default), "P3", "Q4", "8p", "4" — identical results, different speed (tuning / tests)."""
         _abi.check(self._lib.go2_env_set_step_mode(self._h, str(mode).encode()), self._lib)
