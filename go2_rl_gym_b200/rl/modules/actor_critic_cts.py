@@ -160,6 +160,73 @@ class _CTSBase(nn.Module):
         call("go2_l2norm_backward", ptr(dlatent), lddl, ptr(latent), ldl, ptr(self._t_norm), ptr(self._t_dpre), self.latent_dim, 0, M, self.latent_dim)
         self.teacher_engine.backward(self._t_dpre, self.latent_dim)
 
+    # ---- the reference's module-level API (actor_critic_cts.py:106-160 and its siblings): the algorithm classes above do not need it (their
+    # rollout / update paths call the engines directly with fused sampling), external callers written against the reference do
+    def _api_buffers(self, M):
+        if getattr(self, "_api_rows", 0) < M:
+            dev, D = self.device, self.latent_dim
+            self._api_lat = torch.zeros(M, D, device=dev)
+            self._api_xa = torch.zeros(M, _ops.pad_in(D + self.num_obs), device=dev)
+            self._api_xc = torch.zeros(M, _ops.pad_in(D + self.num_critic_obs), device=dev)
+            self._api_mu, self._api_sigma, self._api_val = (torch.zeros(M, self.num_actions, device=dev), torch.zeros(M, self.num_actions, device=dev),
+                                                            torch.zeros(M, 1, device=dev))
+            self._api_rows = M
+
+    def _api_latent(self, privileged_obs, history, is_teacher, M):
+        assert M <= self.teacher_engine.max_rows, "batch larger than the engines were sized for (flatten_ max_rows)"
+        self._api_buffers(M)
+        if is_teacher:
+            self.teacher_latent(privileged_obs.contiguous(), M, self._api_lat[:M])
+        else:
+            self.student.forward(history.contiguous(), M, self._api_lat[:M])
+        return self._api_lat
+
+    def _api_heads(self, obs, privileged_obs, M, actor=True, critic=True):
+        """mu (and sigma) / value of the [latent | obs] / [latent | privileged obs] rows; the plain-head families."""
+        D = self.latent_dim
+        if actor:
+            obs = obs.contiguous()
+            call("go2_concat2", ptr(self._api_lat), D, D, ptr(obs), self.num_obs, obs.shape[1], ptr(self._api_xa), self._api_xa.shape[1], 0, M)
+            self.actor_engine.forward(self._api_xa, self._api_xa.shape[1], M, self._api_mu[:M], self.num_actions, x_ones=self._api_xa.shape[1] > D + self.num_obs)
+            self._api_sigma[:M] = self.std.data
+        if critic:
+            priv = privileged_obs.contiguous()
+            call("go2_concat2", ptr(self._api_lat), D, D, ptr(priv), self.num_critic_obs, priv.shape[1], ptr(self._api_xc), self._api_xc.shape[1], 0, M)
+            self.critic_engine.forward(self._api_xc, self._api_xc.shape[1], M, self._api_val[:M], 1, x_ones=self._api_xc.shape[1] > D + self.num_critic_obs)
+
+    def update_distribution(self, obs, privileged_obs, history, is_teacher):
+        M = obs.shape[0]
+        self._api_latent(privileged_obs, history, is_teacher, M)
+        self._api_heads(obs, privileged_obs, M, critic=False)
+        self.distribution = torch.distributions.Normal(self._api_mu[:M].clone(), self._api_sigma[:M].clone())
+
+    def act(self, obs, privileged_obs, history, is_teacher, **kwargs):
+        """actor_critic_cts.py:129-139: sample from the policy of the teacher (privileged obs) or student (history) branch."""
+        self.update_distribution(obs, privileged_obs, history, is_teacher)
+        return self.distribution.sample()
+
+    def evaluate(self, privileged_obs, history, is_teacher, **kwargs):
+        """actor_critic_cts.py:152-160: value of [latent (detached) | privileged obs]."""
+        M = privileged_obs.shape[0]
+        self._api_latent(privileged_obs, history, is_teacher, M)
+        self._api_heads(None, privileged_obs, M, actor=False)
+        return self._api_val[:M].clone()
+
+    def get_actions_log_prob(self, actions):
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)
+
     def act_inference(self, obs):
         """Student policy (actor_critic_moe_cts.py:127-132): roll the history, encode it, act on [latent | obs]."""
         N = obs.shape[0]
@@ -659,6 +726,21 @@ class ActorCriticACMoECTS(_CTSBase):
         torch.add(a.backbone.dx[:M], a.gate.dx[:M], out=self._dx[:M])
         return self._dx
 
+    def _api_heads(self, obs, privileged_obs, M, actor=True, critic=True):
+        D = self.latent_dim
+        obs, priv = obs.contiguous(), privileged_obs.contiguous()
+        call("go2_concat2", ptr(self._api_lat), D, D, ptr(obs), self.num_obs, obs.shape[1], ptr(self._api_xa), self._api_xa.shape[1], 0, M)
+        call("go2_concat2", ptr(self._api_lat), D, D, ptr(priv), self.num_critic_obs, priv.shape[1], ptr(self._api_xc), self._api_xc.shape[1], 0, M)
+        self.heads_forward(self._api_xa, self._api_xc, M, self._api_mu, self._api_val)        # the value needs the actor's gate
+        self._api_sigma[:M] = self.std.data
+
+    def evaluate(self, obs, privileged_obs, history, is_teacher, **kwargs):
+        """actor_critic_ac_moe_cts.py:134-146: (value, gate weights); the value experts are weighted by the ACTOR's gate, hence obs."""
+        M = obs.shape[0]
+        self._api_latent(privileged_obs, history, is_teacher, M)
+        self._api_heads(obs, privileged_obs, M)
+        return self._api_val[:M].clone(), self.actor_head.gates[:M].clone()
+
     def act_inference(self, obs):
         """Student policy (actor_critic_ac_moe_cts.py:127-132)."""
         N = obs.shape[0]
@@ -795,6 +877,23 @@ class ActorCriticMCPCTS(_CTSBase):
         self.critic_engine.backward(dval, 1)
         torch.add(self.gate_engine.dx[:M, :D], self.backbone_engine.dx[:M, :D], out=self._dlat[:M])
         return self._dlat
+
+    def _api_heads(self, obs, privileged_obs, M, actor=True, critic=True):
+        D = self.latent_dim
+        if actor:
+            obs = obs.contiguous()
+            if getattr(self, "_api_ng_rows", 0) < M:
+                self._api_ng = torch.zeros(M, self.num_obs_no_goal, device=self.device)
+                self._api_xng = torch.zeros(M, _ops.pad_in(self.ng_dim), device=self.device)
+                self._api_ng_rows = M
+            ng = self.no_goal(obs, M, self._api_ng)
+            call("go2_concat2", ptr(self._api_lat), D, D, ptr(obs), self.num_obs, obs.shape[1], ptr(self._api_xa), self._api_xa.shape[1], 0, M)
+            call("go2_concat2", ptr(self._api_lat), D, D, ptr(ng), self.num_obs_no_goal, ng.shape[1], ptr(self._api_xng), self._api_xng.shape[1], 0, M)
+            self.heads_forward(self._api_xa, self._api_xng, None, M, self._api_mu, self._api_sigma, None)
+        if critic:
+            priv = privileged_obs.contiguous()
+            call("go2_concat2", ptr(self._api_lat), D, D, ptr(priv), self.num_critic_obs, priv.shape[1], ptr(self._api_xc), self._api_xc.shape[1], 0, M)
+            self.critic_engine.forward(self._api_xc, self._api_xc.shape[1], M, self._api_val[:M], 1, x_ones=self._api_xc.shape[1] > D + self.num_critic_obs)
 
     def no_goal(self, obs, M, out):
         """out[M, n_ng] = obs[:, obs_no_goal_mask]  (actor_critic_mcp_cts.py:156)"""

@@ -431,3 +431,58 @@ def test_resume_from_a_reference_checkpoint(variant, monkeypatch, tmp_path):
     for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
         num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
     assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")
+@pytest.mark.parametrize("variant", CTS_VARIANTS)
+def test_module_level_api_matches_the_reference_modules(variant, monkeypatch):
+    """act / evaluate / get_actions_log_prob / action_mean / action_std / entropy of the CTS-family modules (the API external callers of the
+    reference's modules use, actor_critic_cts.py:106-160 and siblings) against the reference's own modules with the same weights, for the
+    teacher and the student branch."""
+    import contextlib
+    import importlib
+    import io
+    import sys
+    Z = _variant_or_skip(variant)
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    model, alg, T, N = make_cts(variant, Z, "cpu")
+    monkeypatch.syspath_prepend(REF_RSL)
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        monkeypatch.delitem(sys.modules, k)
+    from golden import cts_cfg as cc
+    mod, cls, pol = {"cts": ("actor_critic_cts", "ActorCriticCTS", cc.POLICY_CTS), "moe_cts": ("actor_critic_moe_cts", "ActorCriticMoECTS", cc.POLICY),
+                     "moe_ng_cts": ("actor_critic_moe_ng_cts", "ActorCriticMoENGCTS", cc.POLICY_NG),
+                     "ac_moe_cts": ("actor_critic_ac_moe_cts", "ActorCriticACMoECTS", cc.POLICY_AC),
+                     "dual_moe_cts": ("actor_critic_dual_moe_cts", "ActorCriticDualMoECTS", cc.POLICY_DUAL),
+                     "mcp_cts": ("actor_critic_mcp_cts", "ActorCriticMCPCTS", cc.POLICY_MCP)}[variant]
+    ref_mod = importlib.import_module("rsl_rl.modules." + mod)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if variant == "cts":
+            zeros = torch.zeros
+            ref_mod.torch.zeros = lambda *a, **kw: zeros(*a, **{k: v for k, v in kw.items() if k != "device"})
+            try:
+                ref = getattr(ref_mod, cls)(45, 263, 12, N, 5, **pol)
+            finally:
+                ref_mod.torch.zeros = zeros
+        else:
+            ref = getattr(ref_mod, cls)(45, 263, 12, N, 5, **pol)
+    ref.load_state_dict({k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")})
+    g = torch.Generator().manual_seed(4)
+    M = 11
+    obs, priv, hist, actions = torch.randn(M, 45, generator=g), torch.randn(M, 263, generator=g), torch.randn(M, 225, generator=g), torch.randn(M, 12, generator=g)
+    needs_obs = variant in ("ac_moe_cts", "dual_moe_cts")
+    for is_teacher in (True, False):
+        with torch.no_grad():
+            ref.act(obs, priv, hist, is_teacher)
+            rv = ref.evaluate(obs, priv, hist, is_teacher) if needs_obs else ref.evaluate(priv, hist, is_teacher)
+        a = model.act(obs, priv, hist, is_teacher)
+        assert a.shape == (M, 12) and torch.isfinite(a).all()
+        assert torch.allclose(model.action_mean, ref.action_mean, atol=2e-5) and torch.allclose(model.action_std, ref.action_std, atol=2e-5)
+        assert torch.allclose(model.get_actions_log_prob(actions), ref.get_actions_log_prob(actions), atol=2e-3, rtol=1e-4)
+        assert torch.allclose(model.entropy, ref.entropy, atol=1e-4)
+        ov = model.evaluate(obs, priv, hist, is_teacher) if needs_obs else model.evaluate(priv, hist, is_teacher)
+        if needs_obs:
+            assert torch.allclose(ov[0], rv[0], atol=2e-5) and torch.allclose(ov[1], rv[1], atol=2e-5)
+        else:
+            assert torch.allclose(ov, rv, atol=2e-5)
