@@ -55,3 +55,15 @@ class RolloutStorageCTS(RolloutStorage):
         _ops.call("go2_gather_rows", _ops.ptr(self.history), w, _ops.ptr(indices), _ops.ptr(buf), ld, _ops.ptr(bt), n)
         out["history"] = buf
         return out
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8):
+        """Reference-shaped generator (rollout_storage_cts.py:153-211) for external callers: every mini-batch is a teacher slice followed by a
+        student slice, 12-tuples with the history in position 3; CTS.update uses `batch_indices` + `shuffled` (one gather per iteration)."""
+        idx, tm, sm = self.batch_indices(num_mini_batches)
+        sh = self.shuffled(idx, {})
+        mb = tm + sm
+        for epoch in range(num_epochs):
+            for i in range(num_mini_batches):
+                s = slice(i * mb, (i + 1) * mb)
+                yield (sh["obs"][s], sh["critic_obs"][s], sh["actions"][s], sh["history"][s], sh["values"][s], sh["adv"][s], sh["returns"][s],
+                       sh["old_logp"][s], sh["old_mu"][s], sh["old_sigma"][s], (None, None), None)

@@ -486,3 +486,35 @@ def test_module_level_api_matches_the_reference_modules(variant, monkeypatch):
             assert torch.allclose(ov[0], rv[0], atol=2e-5) and torch.allclose(ov[1], rv[1], atol=2e-5)
         else:
             assert torch.allclose(ov, rv, atol=2e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")
+def test_cts_mini_batch_generator_matches_the_reference(monkeypatch):
+    """RolloutStorageCTS.mini_batch_generator (rollout_storage_cts.py:153-211): same 12-tuples, teacher slice then student slice, same samples
+    for the same two permutations."""
+    import sys
+    emu_rl.install(monkeypatch)
+    monkeypatch.syspath_prepend(REF_RSL)
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        monkeypatch.delitem(sys.modules, k)
+    import rsl_rl.storage.rollout_storage_cts as RS
+    from go2_rl_gym_b200.rl.storage.rollout_storage_cts import RolloutStorageCTS
+    N, Nt, T, H = 16, 12, 6, 5
+    ref = RS.RolloutStorageCTS(N, Nt, H, T, [45], [263], [12], "cpu")
+    mine = RolloutStorageCTS(N, Nt, H, T, [45], [263], [12], "cpu")
+    g = torch.Generator().manual_seed(0)
+    for k in ("observations", "privileged_observations", "history", "actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
+        x = torch.randn(getattr(ref, k).shape, generator=g)
+        getattr(ref, k).copy_(x); getattr(mine, k).copy_(x)
+    ref.step = mine.step = T
+    perms = [torch.randperm(Nt * T, generator=g), torch.randperm((N - Nt) * T, generator=g)]
+    q1, q2 = [p.clone() for p in perms], [p.clone() for p in perms]
+    monkeypatch.setattr(RS.torch, "randperm", lambda n, **kw: q1.pop(0))
+    a = list(ref.mini_batch_generator(4, 2))
+    monkeypatch.setattr(torch, "randperm", lambda n, **kw: q2.pop(0))
+    b = list(mine.mini_batch_generator(4, 2))
+    assert len(a) == len(b) == 8
+    for ta, tb in zip(a, b):
+        assert len(ta) == len(tb) == 12 and tb[10] == (None, None) and tb[11] is None
+        for xa, xb in zip(ta[:10], tb[:10]):
+            assert torch.equal(xa, xb)
