@@ -138,7 +138,9 @@ class ActorCritic(nn.Module):
         return out
 
     def act(self, observations, **kwargs):
-        raise NotImplementedError("sampling is fused with the transition write: use PPO.act (ppo.py:90-102)")
+        """actor_critic.py:123-125 for external callers (torch's generator); PPO.act samples in its own kernel, fused with the transition write."""
+        self.update_distribution(observations)
+        return torch.normal(self._mean, self.action_std)
 
     def get_actions_log_prob(self, actions):
         mu, std = self._mean, self.std.data

@@ -518,3 +518,26 @@ def test_cts_mini_batch_generator_matches_the_reference(monkeypatch):
         assert len(ta) == len(tb) == 12 and tb[10] == (None, None) and tb[11] is None
         for xa, xb in zip(ta[:10], tb[:10]):
             assert torch.equal(xa, xb)
+
+
+def test_actor_critic_module_api(monkeypatch):
+    """ActorCritic.act / evaluate / get_actions_log_prob / action_mean / action_std / entropy (actor_critic.py:104-136) against the RL oracle."""
+    emu_rl.install(monkeypatch)
+    from golden.rl_cfg import CFG
+    from go2_rl_gym_b200.rl.algorithms import PPO
+    from go2_rl_gym_b200.rl.modules import ActorCritic
+    from oracle import rl_oracle as R
+    Z = _load("ppo")
+    ac = ActorCritic(45, 263, 12, actor_hidden_dims=[64, 32, 16], critic_hidden_dims=[64, 32, 16])
+    sd = {k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")}
+    ac.load_state_dict(sd)
+    alg = PPO(ac, device="cpu", **CFG)
+    alg.init_storage(32, 4, [45], [263], [12])
+    obs, priv = torch.from_numpy(Z["in_obs"][0]), torch.from_numpy(Z["in_priv"][0])
+    torch.manual_seed(0)
+    a = ac.act(obs)
+    mu = R.mlp_forward(sd, "actor", obs)
+    assert a.shape == mu.shape and torch.allclose(ac.action_mean, mu, atol=2e-5) and torch.allclose(ac.action_std, sd["std"].expand_as(mu))
+    assert torch.allclose(ac.get_actions_log_prob(a), R.log_prob(mu, sd["std"], a), atol=1e-4)
+    assert torch.allclose(ac.entropy, torch.distributions.Normal(mu, sd["std"].expand_as(mu)).entropy().sum(-1), atol=1e-5)
+    assert torch.allclose(ac.evaluate(priv), R.mlp_forward(sd, "critic", priv), atol=2e-5)
