@@ -59,6 +59,30 @@ with tempfile.TemporaryDirectory() as d:
         out["mine_raises"] = True
 # class_to_dict of a nested config
 out["c2d_equal"] = ref_h.class_to_dict(ref_cfg.GO2CfgCTS()) == my_h.class_to_dict(my_cfg.GO2CfgCTS())
+# legged_gym.utils.math / Logger (math.py:7-27, logger.py:5-40)
+import torch
+import legged_gym.utils.math as ref_m
+import legged_gym.utils.logger as ref_l
+my_m = importlib.import_module("go2_rl_gym_b200.utils.math")
+my_l = importlib.import_module("go2_rl_gym_b200.utils.logger")
+g = torch.Generator().manual_seed(0)
+q = torch.nn.functional.normalize(torch.randn(64, 4, generator=g), dim=-1); v = torch.randn(64, 3, generator=g); ang = 20 * torch.randn(257, generator=g)
+torch.manual_seed(3); a = ref_m.torch_rand_sqrt_float(-1.5, 2.0, (9, 2), "cpu")
+torch.manual_seed(3); b = my_m.torch_rand_sqrt_float(-1.5, 2.0, (9, 2), "cpu")
+out["math_equal"] = [bool(torch.equal(ref_m.quat_apply_yaw(q, v), my_m.quat_apply_yaw(q, v))), bool(torch.equal(ref_m.wrap_to_pi(ang.clone()), my_m.wrap_to_pi(ang.clone()))),
+                     bool(torch.equal(a, b))]
+logs = []
+for L in (ref_l.Logger(0.02), my_l.Logger(0.02)):
+    L.log_states({"x": 1.0, "y": 2.0}); L.log_state("x", 3.0)
+    L.log_rewards({"rew_a": torch.tensor(0.5), "rew_b": torch.tensor(-1.0), "terrain_level": torch.tensor(3.0)}, 4)
+    L.log_rewards({"rew_a": torch.tensor(1.5)}, 2)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        L.print_rewards()
+    logs.append([dict(L.state_log), dict(L.rew_log), L.num_episodes, buf.getvalue()])
+    L.reset()
+    logs[-1].append([len(L.state_log), len(L.rew_log)])
+out["logger_equal"] = logs[0] == logs[1]
 print("RESULT" + json.dumps(out))
 '''
 
@@ -77,3 +101,4 @@ def test_helpers_behave_like_the_reference():
     assert res["load_path"][0][1] == os.path.join("Sep30_10-00-00_", "model_1000.pt")      # runs sort by name: 'Sep30' > 'Oct01'
     assert res["ref_raises"] and res["mine_raises"]
     assert res["c2d_equal"]
+    assert res["math_equal"] == [True, True, True] and res["logger_equal"]
