@@ -58,3 +58,24 @@ def test_actor_critic_mcp_cts_keys():
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(s) for k, s in _keys(z).items()}
     assert [k for k, _ in m.named_parameters()] == [k[4:] for k in z.files if k.startswith("sd0_")]
     assert "std" not in m.state_dict()          # sigma is a network output (actor_critic_mcp_cts.py:236-247)
+
+
+def test_shim_packages_export_the_reference_names():
+    """`rsl_rl.*` / `legged_gym.utils` at the repo root re-export every name the reference's packages export (rsl_rl/rsl_rl/{algorithms,modules,
+    runners,storage}/__init__.py, legged_gym/utils/__init__.py) except the recurrent policy, which no go2 task uses."""
+    import importlib
+    import sys
+    for k in [k for k in sys.modules if k.split(".")[0] in ("rsl_rl", "legged_gym")]:
+        del sys.modules[k]
+    want = {"rsl_rl.algorithms": ["PPO", "CTS", "MoENGCTS", "MCPCTS", "ACMoECTS", "DualMoECTS", "MoECTS"],
+            "rsl_rl.modules": ["ActorCritic", "ActorCriticCTS", "ActorCriticMoENGCTS", "ActorCriticMCPCTS", "ActorCriticACMoECTS", "ActorCriticDualMoECTS",
+                               "ActorCriticMoECTS"],
+            "rsl_rl.runners": ["OnPolicyRunner", "OnPolicyRunnerCTS"], "rsl_rl.storage": ["RolloutStorage", "RolloutStorageCTS"], "rsl_rl.env": ["VecEnv"],
+            "legged_gym.utils": ["class_to_dict", "get_load_path", "get_args", "set_seed", "update_class_from_dict", "task_registry", "Logger", "Terrain",
+                                 "quat_apply_yaw", "wrap_to_pi", "torch_rand_sqrt_float"],
+            "legged_gym.utils.exporter": ["export_policy_as_jit", "export_policy_as_pkl", "export_policy_as_onnx"]}
+    for mod, names in want.items():
+        m = importlib.import_module(mod)
+        assert m.__file__.startswith(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), (mod, m.__file__)      # the shim, not the reference
+        for n in names:
+            assert hasattr(m, n), (mod, n)
