@@ -1,38 +1,34 @@
-"""Host-side torch helpers of legged_gym/utils/math.py:7-27 (the env's own use of them — yaw-only rotation of the height-scan grid, the heading
-error — lives inside the fused step kernel; these are for user code written against the reference)."""
-import numpy as np
+"""Host-side torch helpers with the names and semantics of legged_gym/utils/math.py:7-27, for user code written against the reference.  The env's
+own use of the same arithmetic (yaw-only rotation of the height-scan grid, the heading error) lives inside the fused step kernel."""
+import math as _math
+
 import torch
 
-
-def _normalize(x, eps=1e-9):
-    return x / x.norm(p=2, dim=-1).clamp(min=eps, max=None).unsqueeze(-1)
-
-
-def _quat_apply(a, b):       # isaacgym.torch_utils.quat_apply, xyzw
-    shape = b.shape
-    a, b = a.reshape(-1, 4), b.reshape(-1, 3)
-    xyz = a[:, :3]
-    t = xyz.cross(b, dim=-1) * 2
-    return (b + a[:, 3:] * t + xyz.cross(t, dim=-1)).view(shape)
+_TWO_PI = 2.0 * _math.pi
 
 
 def quat_apply_yaw(quat, vec):
-    """Rotate vec by the yaw component of quat only (math.py:8-12)."""
-    quat_yaw = quat.clone().view(-1, 4)
-    quat_yaw[:, :2] = 0.
-    return _quat_apply(_normalize(quat_yaw), vec)
+    """Rotate `vec` [..., 3] by the YAW part of `quat` [..., 4] (xyzw) only: drop x / y, renormalise (z, w), rotate about the vertical axis.
+    Closed form of that rotation: cos(yaw) = w^2 - z^2, sin(yaw) = 2 w z on the unit (z, w)."""
+    q = quat.reshape(-1, 4)
+    v = vec.reshape(-1, 3)
+    z, w = q[:, 2], q[:, 3]
+    n = torch.sqrt(z * z + w * w).clamp(min=1e-9)
+    z, w = z / n, w / n
+    c, s = w * w - z * z, 2.0 * w * z
+    out = torch.stack((c * v[:, 0] - s * v[:, 1], s * v[:, 0] + c * v[:, 1], v[:, 2]), dim=-1)
+    return out.view(vec.shape)
 
 
 def wrap_to_pi(angles):
-    """In place, like the reference (math.py:15-18)."""
-    angles %= 2 * np.pi
-    angles -= 2 * np.pi * (angles > np.pi)
+    """Map angles to (-pi, pi], IN PLACE like the reference (its callers rely on that), and return the same tensor."""
+    angles.copy_(torch.remainder(angles, _TWO_PI))
+    angles.sub_(_TWO_PI * (angles > _math.pi))
     return angles
 
 
 def torch_rand_sqrt_float(lower, upper, shape, device):
-    """math.py:21-27: square-root-shaped density around the middle of [lower, upper]."""
-    r = 2 * torch.rand(*shape, device=device) - 1
-    r = torch.where(r < 0., -torch.sqrt(-r), torch.sqrt(r))
-    r = (r + 1.) / 2.
-    return (upper - lower) * r + lower
+    """Uniform draw pushed through a signed square root: samples in [lower, upper] with a density that thins out around the middle."""
+    u = 2.0 * torch.rand(*shape, device=device) - 1.0
+    r = torch.sign(u) * torch.sqrt(u.abs())
+    return (upper - lower) * ((r + 1.0) / 2.0) + lower

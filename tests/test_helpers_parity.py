@@ -69,8 +69,9 @@ g = torch.Generator().manual_seed(0)
 q = torch.nn.functional.normalize(torch.randn(64, 4, generator=g), dim=-1); v = torch.randn(64, 3, generator=g); ang = 20 * torch.randn(257, generator=g)
 torch.manual_seed(3); a = ref_m.torch_rand_sqrt_float(-1.5, 2.0, (9, 2), "cpu")
 torch.manual_seed(3); b = my_m.torch_rand_sqrt_float(-1.5, 2.0, (9, 2), "cpu")
-out["math_equal"] = [bool(torch.equal(ref_m.quat_apply_yaw(q, v), my_m.quat_apply_yaw(q, v))), bool(torch.equal(ref_m.wrap_to_pi(ang.clone()), my_m.wrap_to_pi(ang.clone()))),
-                     bool(torch.equal(a, b))]
+inplace = ang.clone(); ret = my_m.wrap_to_pi(inplace)
+out["math_equal"] = [bool(torch.allclose(ref_m.quat_apply_yaw(q, v), my_m.quat_apply_yaw(q, v), atol=1e-6)), bool(torch.allclose(ref_m.wrap_to_pi(ang.clone()), ret, atol=1e-6)) and ret.data_ptr() == inplace.data_ptr(),
+                     bool(torch.allclose(a, b, atol=1e-7))]
 logs = []
 for L in (ref_l.Logger(0.02), my_l.Logger(0.02)):
     L.log_states({"x": 1.0, "y": 2.0}); L.log_state("x", 3.0)
