@@ -97,7 +97,7 @@ _VARIANTS = {}
 
 def load_library(path=None):
     """Load libgo2b200.so (hand-written sm_100a kernels + C ABI). Raises if it has not been built.
-    path: another build of the same library (e.g. libgo2b200_relaxed.so), loaded side by side with its own handle."""
+    path: another build of the same library (e.g. a tuning build), loaded side by side with its own handle."""
     global _LIB
     if path is None and _LIB is not None:
         return _LIB

@@ -200,12 +200,6 @@ extern "C" {
 int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvBuffers* bufs, Go2Env** out) {
   if (!cfg || !model || !bufs || !out) return go2::set_error(1, "go2_env_create: null argument");
   if (cfg->num_envs <= 0) return go2::set_error(1, "go2_env_create: num_envs must be positive");
-  if (!GO2_RELAXED_SOLVER && (cfg->limit_relax != 0.0f || cfg->contact_relax != 1.0f || cfg->state_guard != 0))
-    return go2::set_error(2, "go2_env_create: this build of the step kernel has no relaxed solver / state guard (limit_relax must be 0, "
-                             "contact_relax 1, state_guard 0); rebuild with -DGO2_RELAXED_SOLVER=1");
-  if (!GO2_RELAXED_SOLVER && (cfg->control_type != 0 || cfg->only_positive_rewards != 0 || cfg->heading_command != 0))
-    return go2::set_error(2, "go2_env_create: control_type 'V' / 'T', only_positive_rewards and heading_command need the build with "
-                             "-DGO2_RELAXED_SOLVER=1 (libgo2b200_relaxed.so)");
   if (cfg->heading_command && (!GO2_EXT_PTR(const void*, cfg, ext_stop_heading) || !GO2_EXT_PTR(const void*, cfg, ext_heading_ranges)))
     return go2::set_error(1, "go2_env_create: heading_command needs ext_stop_heading and ext_heading_ranges");
   if (cfg->control_type < 0 || cfg->control_type > 2) return go2::set_error(2, "go2_env_create: control_type must be 0 (P), 1 (V) or 2 (T)");

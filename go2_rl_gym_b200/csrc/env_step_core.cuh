@@ -50,13 +50,6 @@
 #define GO2_WIDE GO2_EACH if (L.own) GO2_BIND(L.w, L.lane)
 #define GO2_LEGS GO2_EACH if (L.leg >= 0) GO2_BIND(L.wl, L.leg)
 
-// The relaxed contact / joint-limit solver (Go2EnvConfig.limit_relax / contact_relax) is compiled into the host
-// emulation, where it is validated against the oracle; the sm_100a library of this round is built WITHOUT it (identical code to the build
-// that was measured and tested on the B200) and rejects those settings at create time.
-#ifndef GO2_RELAXED_SOLVER
-#define GO2_RELAXED_SOLVER 0
-#endif
-
 namespace go2 {
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
@@ -257,13 +250,10 @@ struct WarpSmem {
   float fcol[GO2_NUM_COL][6];  // spatial impulse of each collider on its body (body coords)
   float pcol[GO2_NUM_COL][3];  // world impulse of each collider
   float tgt[12][2];            // joint-limit target velocities (lower, upper row)
-#if GO2_RELAXED_SOLVER
-  float Dje[12];               // limit-row step limit_relax / (M^-1)_jj (relaxed solver only)
+  float Dje[12];               // limit-row step limit_relax / (M^-1)_jj (limit_relax > 0)
   int bad;                     // state guard: this env's state went non-finite in this step (sanitised, resets)
   int stop_heading;            // heading commands: the yaw command no longer follows the heading target (legged_robot.py:412,431,548,582)
   float hrng[2];               // this env's heading range
-  int pad_relaxed_[16];        // keeps the row stride at 1 mod 32 words in this build too
-#endif
   float mu_env, rest_env;      // contact friction / restitution of this env (combined with the terrain's)
   float a0[6];
   float q[12], qd[12], tau[12], cs[12][2], qdm[12], dqd[12], tauimp[12], Dj[12];
@@ -284,7 +274,7 @@ struct WarpSmem {
   float env_origin[3];
   int active[GO2_NUM_COL];
   int ep_len, reset, tout, last_lim, level, ttype, tid, delay_start;
-  int pad_[27];   // stride = 1 mod 32 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
+  int pad_[11];   // stride = 1 mod 32 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
 };
 static_assert((sizeof(WarpSmem) / 4) % 32 == 1, "WarpSmem stride must be 1 mod 32 words");
 
@@ -547,11 +537,7 @@ GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, 
     Q.m[3 * AX + t] -= ylv[t] * Dinv;   // row k of Q (= column k of Q^T)
   }
   P.m[3 * AX + AX] += alpha * Dinv * Dinv + Dinv;
-#if GO2_RELAXED_SOLVER
   if (limit_relax > 0.0f) S.Dje[j] = limit_relax / P.m[3 * AX + AX];   // P[k][k] = (M^-1)_jj: the joint's own response with every other joint free
-#else
-  (void)limit_relax;
-#endif
   stm(S.Lam[b], P); stm(S.Lam[b] + 9, Q); stm(S.Lam[b] + 18, R);
   Pp = P; Qp = Q; Rp = R;
 }
@@ -656,9 +642,9 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       vm0.a = v0.a + dt * a0.a;
       vm0.l = v0.l + dt * (a0.l + gb + cross(v0.a, v0.l));  // components stay in the frame of the start of the step
       V6 ap = a0, vmp = vm0;
-      leg_pass3<0>(lane, L, S, M, dt, GO2_RELAXED_SOLVER ? C->limit_relax : 0.0f, ap, vmp, P, Q, R);
-      leg_pass3<1>(lane, L, S, M, dt, GO2_RELAXED_SOLVER ? C->limit_relax : 0.0f, ap, vmp, P, Q, R);
-      leg_pass3<2>(lane, L, S, M, dt, GO2_RELAXED_SOLVER ? C->limit_relax : 0.0f, ap, vmp, P, Q, R);
+      leg_pass3<0>(lane, L, S, M, dt, C->limit_relax, ap, vmp, P, Q, R);
+      leg_pass3<1>(lane, L, S, M, dt, C->limit_relax, ap, vmp, P, Q, R);
+      leg_pass3<2>(lane, L, S, M, dt, C->limit_relax, ap, vmp, P, Q, R);
       if (lane == 0) st6(S.v[0], vm0);
       for (int i = 0; i < 3; ++i) { L.lam_lo[i] = 0; L.lam_hi[i] = 0; }
     }
@@ -713,11 +699,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
     {
       int g0 = lane < 8 ? 0 : 8 + 6 * ((lane - 8) / 6), gn = lane < 8 ? 8 : 6, cnt = 0;
       for (int k = 0; k < gn; ++k) cnt += S.active[g0 + k];
-#if GO2_RELAXED_SOLVER
       L.gsplit = C->contact_relax / (float)cnt;      // block step of the contact rows; only read by active colliders: cnt >= 1
-#else
-      L.gsplit = 1.0f / (float)cnt;                  // mass-splitting factor; only read by active colliders: cnt >= 1
-#endif
     }
   }
   // ---- Jacobi sweeps with exact propagation through the tree: [collider lanes: block-solve every contact] | CTA barrier |
@@ -753,11 +735,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       if (lane < 4) {
         for (int i = 0; i < 3; ++i) {  // joint-limit rows of the leg's joints (unilateral, velocity level)
           const int j = 3 * lane + i;
-#if GO2_RELAXED_SOLVER
           float cur = S.qdm[j] + S.dqd[j], Dj = C->limit_relax > 0.0f ? S.Dje[j] : S.Dj[j];
-#else
-          float cur = S.qdm[j] + S.dqd[j], Dj = S.Dj[j];
-#endif
           L.lam_lo[i] = fmaxf(0.0f, L.lam_lo[i] + (S.tgt[j][0] - cur) * Dj);
           L.lam_hi[i] = fminf(0.0f, L.lam_hi[i] + (S.tgt[j][1] - cur) * Dj);
           S.tauimp[j] = L.lam_lo[i] + L.lam_hi[i];
@@ -809,13 +787,11 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       V6 v0; ld6(S.v[0], v0);
       V6 d0; ld6(S.dv[0], d0);
       V3 lw = mul(R0, v0.l + d0.l), aw = mul(R0, v0.a + d0.a);
-#if GO2_RELAXED_SOLVER
       if (C->state_guard) {   // asset.max_linear_velocity / max_angular_velocity (legged_robot_config.py:131-132)
         const float nl = sqrtf(dot(lw, lw)), na = sqrtf(dot(aw, aw));
         if (nl > C->max_base_lin_vel) lw = (C->max_base_lin_vel / nl) * lw;
         if (na > C->max_base_ang_vel) aw = (C->max_base_ang_vel / na) * aw;
       }
-#endif
       st3(S.root + 7, lw); st3(S.root + 10, aw);
       S.root[0] += dt * lw.x; S.root[1] += dt * lw.y; S.root[2] += dt * lw.z;
       float wn = sqrtf(dot(aw, aw)), th = wn * dt, hx, hy, hz, hw;  // q <- exp(aw dt / 2) * q (world-frame angular velocity)
@@ -847,7 +823,6 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
   } GO2_SYNC_WARP();
 }
 
-#if GO2_RELAXED_SOLVER
 // State guard (Go2EnvConfig.state_guard): an env whose state is non-finite after the substeps restarts from its initial pose at its origin and
 // resets in this step, so that nothing non-finite reaches the observations / rewards the shared networks train on.  One WIDE phase, lane 0.
 GO2_HD void state_guard(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
@@ -870,7 +845,6 @@ GO2_HD void state_guard(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     }
   } GO2_SYNC_WARP();
 }
-#endif
 
 // feet position / velocity at the current configuration (rigid_body_states refresh, legged_robot.py:109)
 GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
@@ -919,10 +893,8 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
   float remaining = fmaxf(GO2_FADD(GO2_FMUL(0.625f, C->terrain_length), -GO2_FMUL(accn, C->resampling_time)), 0.0f);
   const float full = C->resampling_time / C->dt;
   S.resamp_step = full;
-#if GO2_RELAXED_SOLVER
   const bool heading = C->heading_command != 0;
   S.stop_heading = 0;                                                   // legged_robot.py:431
-#endif
   if (C->dynamic_resample_commands) {
     float vlow = fmaxf(remaining / GO2_FMUL(GO2_FADD(max_len - ep_len, 1e-9f), C->dt), 0.0f);
     for (int a = 0; a < 2; ++a) {
@@ -932,18 +904,14 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
       float u = GO2_FMUL(u01(a == 0 ? r0.x : r0.y), total);
       S.cmd[a] = (u < wneg) ? GO2_FADD(lo, u) : GO2_FADD(hi - wpos, u - wneg);
     }
-#if GO2_RELAXED_SOLVER
     if (heading) S.cmd[3] = affine(S.hrng[1] - S.hrng[0], u01(r0.z), S.hrng[0]);       // the same draw feeds the heading target (:468-472)
     else
-#endif
     S.cmd[2] = affine(rng[5] - rng[4], u01(r0.z), rng[4]);
   } else {
     S.cmd[0] = GO2_FADD(rng[0], GO2_FMUL(u01(r0.x), rng[1] - rng[0]));
     S.cmd[1] = GO2_FADD(rng[2], GO2_FMUL(u01(r0.y), rng[3] - rng[2]));
-#if GO2_RELAXED_SOLVER
     if (heading) S.cmd[3] = GO2_FADD(S.hrng[0], GO2_FMUL(u01(r0.z), S.hrng[1] - S.hrng[0]));
     else
-#endif
     S.cmd[2] = GO2_FADD(rng[4], GO2_FMUL(u01(r0.z), rng[5] - rng[4]));
     float nrm = sqrtf(S.cmd[0] * S.cmd[0] + S.cmd[1] * S.cmd[1]);
     if (!(nrm > 0.2f)) { S.cmd[0] = 0; S.cmd[1] = 0; }
@@ -964,9 +932,7 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
         S.cmd[1] = cy == 0 ? rng[2] : rng[3];
         S.cmd[2] = cz == 0 ? rng[4] : (cz == 1 ? 0.0f : rng[5]);
       }
-#if GO2_RELAXED_SOLVER
       if (heading && C->stop_heading_at_limit) S.stop_heading = 1;      // :547-548
-#endif
     }
     S.last_lim = lim ? 1 : 0;
     min_p += C->limit_vel_prob;
@@ -980,16 +946,13 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
       S.resamp_step = next;
       if (C->limit_ang_vel_at_zero_command_prob > 0 && u01(r1.y) < C->limit_ang_vel_at_zero_command_prob) {
         S.cmd[2] = (u01(r1.z) < 0.5f) ? rng[4] : rng[5];
-#if GO2_RELAXED_SOLVER
         if (heading) S.stop_heading = 1;                                // :581-582
-#endif
       }
     }
   }
   S.acc_xy[0] += S.cmd[0]; S.acc_xy[1] += S.cmd[1];
 }
 
-#if GO2_RELAXED_SOLVER
 // yaw-rate command from the heading target (legged_robot.py:411-419; quat_apply and wrap_to_pi in torch's operation order)
 GO2_HD void heading_to_yaw(WarpSmem& S) {
   const float qx = S.root[3], qy = S.root[4], qz = S.root[5], qw = S.root[6];
@@ -1003,7 +966,6 @@ GO2_HD void heading_to_yaw(WarpSmem& S) {
   if (a > 3.1415927f) a = GO2_FADD(a, -6.2831855f);
   S.cmd[2] = fminf(fmaxf(GO2_FMUL(0.5f, a), S.cmd_rng[4]), S.cmd_rng[5]);
 }
-#endif
 
 #if defined(__CUDACC__)
 #define GO2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -1097,7 +1059,6 @@ GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     if (lane == 25) { S.ep_len = B->episode_length_buf[e]; S.resamp_step = B->commands_resampling_step[e]; }
     if (lane == 26) { S.acc_xy[0] = B->commands_xy_accumulation[(size_t)e * 2]; S.acc_xy[1] = B->commands_xy_accumulation[(size_t)e * 2 + 1]; }
     if (lane == 27) { S.max_move = B->max_move_distance[e]; S.last_lim = B->last_is_limit_vel[e]; }
-#if GO2_RELAXED_SOLVER
     if (lane == 30) {
       S.stop_heading = 0; S.hrng[0] = 0.0f; S.hrng[1] = 0.0f;
       if (C->heading_command) {
@@ -1105,7 +1066,6 @@ GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
         S.stop_heading = GO2_EXT_PTR(const uint8_t*, C, ext_stop_heading)[e]; S.hrng[0] = hr[(size_t)e * 2]; S.hrng[1] = hr[(size_t)e * 2 + 1];
       }
     }
-#endif
     if (lane == 28) { S.level = B->terrain_levels[e]; S.ttype = B->terrain_types[e]; S.tid = B->terrain_ids[e]; }
     if (lane == 30) {
       S.mu_env = 0.5f * (C->terrain_friction + GO2_LDG(B->friction_coeffs + e));
@@ -1135,9 +1095,7 @@ GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     if (lane == 25) { B->episode_length_buf[e] = S.ep_len; B->commands_resampling_step[e] = S.resamp_step; }
     if (lane == 26) { B->commands_xy_accumulation[(size_t)e * 2] = S.acc_xy[0]; B->commands_xy_accumulation[(size_t)e * 2 + 1] = S.acc_xy[1]; }
     if (lane == 27) { B->max_move_distance[e] = S.max_move; B->last_is_limit_vel[e] = (uint8_t)S.last_lim; }
-#if GO2_RELAXED_SOLVER
     if (lane == 30 && X.cfg->heading_command) GO2_EXT_PTR(uint8_t*, X.cfg, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
-#endif
     if (lane == 28) B->terrain_levels[e] = S.level;
     if (lane == 29) { B->reset_buf[e] = (uint8_t)S.reset; B->time_out_buf[e] = (uint8_t)S.tout; }
     for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = S.cf[i / 3][i % 3];
@@ -1157,10 +1115,8 @@ GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, int s
     if (lane < GO2_NUM_DOF) {
       float a_in = (C->randomize_action_delay && sub < S.delay_start) ? S.lact[lane] : S.act[lane];
       float t = L.kp * (a_in * C->action_scale + C->default_dof_pos[lane] - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
-#if GO2_RELAXED_SOLVER
       if (C->control_type == 1) t = L.kp * (a_in * C->action_scale - S.qd[lane]) - L.kd * (S.qd[lane] - S.lqd[lane]) / C->sim_dt;   // 'V', legged_robot.py:612-613
       else if (C->control_type == 2) t = a_in * C->action_scale;                                                                  // 'T', :614-615
-#endif
       float lim = M->effort[lane];
       t = fminf(fmaxf(t, -lim), lim);
       if (C->randomize_motor_strength) t *= L.mstr;
@@ -1183,9 +1139,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     physics_substep(GO2_LANE_PASS, SM, X, sub == C->decimation - 1);
   }
   GO2_COARSE_SYNC();
-#if GO2_RELAXED_SOLVER
   state_guard(GO2_LANE_PASS, SM, X);
-#endif
   feet_kinematics(GO2_LANE_PASS, SM, X);
   // ---- post_physics_step (legged_robot.py:102-142)
   GO2_WIDE {
@@ -1221,9 +1175,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       float dx = S.root[0] - S.env_origin[0], dy = S.root[1] - S.env_origin[1];
       S.max_move = fmaxf(S.max_move, sqrtf(dx * dx + dy * dy));
       if (S.resamp_step <= 0.0f && S.ep_len < C->max_episode_length - 1) resample_commands(S, X, e, ST_CMD_CB);
-#if GO2_RELAXED_SOLVER
       if (C->heading_command && !S.stop_heading) heading_to_yaw(S);
-#endif
     }
   } GO2_SYNC_WARP();
   GO2_WIDE {
@@ -1260,9 +1212,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
       int term = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
       S.tout = S.ep_len > C->max_episode_length;
       S.reset = term || S.tout;
-#if GO2_RELAXED_SOLVER
       S.reset |= S.bad;
-#endif
     }
   } GO2_SYNC_WARP();
   GO2_WIDE {
@@ -1309,9 +1259,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
         rew += rk;
         S.termv[k] = rk;
       }
-#if GO2_RELAXED_SOLVER
       if (C->only_positive_rewards) rew = fmaxf(rew, 0.0f);     // the episode sums keep the unclipped terms (legged_robot.py:263-267)
-#endif
       S.rew = rew;
     }
   } GO2_SYNC_WARP();

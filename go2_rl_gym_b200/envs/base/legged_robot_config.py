@@ -222,15 +222,15 @@ class LeggedRobotCfg(BaseConfig):
             """Knobs of the B200 contact / joint-limit impulse solver (no reference counterpart)."""
             solver_iterations = 4
             erp = 0.2
-            limit_erp = 0.2
             penetration_slop = 0.004
-            # relaxation of the Jacobi sweeps (include/go2_b200.h).  0 / 1 = the solver every fixture of this round was generated with.  The
-            # convergent setting found in this round (DESIGN.md section 3): limit_relax = 0.5, contact_relax = 0.7, limit_erp = 0.8.
-            limit_relax = 0.0
-            contact_relax = 1.0
-            # 1: clamp the base twist at asset.max_linear_velocity / max_angular_velocity and reset any env whose state went non-finite
-            # (include/go2_b200.h).  Needs a library built with -DGO2_RELAXED_SOLVER=1, like the two knobs above.
-            state_guard = 0
+            # relaxation of the Jacobi sweeps (include/go2_b200.h; DESIGN.md section 3): joint-limit rows step with limit_relax / (M^-1)_jj,
+            # contact blocks with contact_relax / (active contacts of the group); the sweeps converge with these values (0 / 1 / limit_erp 0.2
+            # selects round 1's first solver, whose limit rows are over-relaxed: soft stops, divergent beyond 4 sweeps)
+            limit_relax = 0.5
+            contact_relax = 0.7
+            limit_erp = 0.8
+            # clamp the base twist at asset.max_linear_velocity / max_angular_velocity and reset any env whose state went non-finite
+            state_guard = 1
 
 
 class _TrainCfgBase(BaseConfig):

@@ -157,7 +157,7 @@ class EnvArrays:
         c.sim_dt, c.decimation, c.gravity_z = cfg.sim.dt, cfg.control.decimation, cfg.sim.gravity[2]
         if cfg.control.control_type not in ("P", "V", "T"):
             raise NameError(f"Unknown controller type: {cfg.control.control_type}")          # legged_robot.py:616-617
-        c.control_type = "PVT".index(cfg.control.control_type)      # 'V' / 'T' need libgo2b200_relaxed.so (go2_env_create rejects them otherwise)
+        c.control_type = "PVT".index(cfg.control.control_type)      # legged_robot.py:605-618
         default = np.zeros(12, np.float32)
         for j, name in enumerate(dof_names):
             default[j] = cfg.init_state.default_joint_angles[name]
@@ -180,14 +180,14 @@ class EnvArrays:
         c.push_interval, c.max_push_vel_xy, c.max_push_ang_vel = self.push_interval, dr.max_push_vel_xy, dr.max_push_ang_vel
         b200 = getattr(cfg.sim, "b200", None)
         c.solver_iters = getattr(b200, "solver_iterations", 4)
-        c.erp, c.limit_erp = getattr(b200, "erp", 0.2), getattr(b200, "limit_erp", 0.2)
+        c.erp, c.limit_erp = getattr(b200, "erp", 0.2), getattr(b200, "limit_erp", 0.8)
         c.contact_offset = cfg.sim.physx.contact_offset
         c.penetration_slop = getattr(b200, "penetration_slop", 0.004)
         c.max_depen_vel = cfg.sim.physx.max_depenetration_velocity
         c.bounce_threshold = cfg.sim.physx.bounce_threshold_velocity
         c.terrain_friction, c.terrain_restitution = cfg.terrain.static_friction, cfg.terrain.restitution
-        c.limit_relax, c.contact_relax = getattr(b200, "limit_relax", 0.0), getattr(b200, "contact_relax", 1.0)
-        c.state_guard = int(getattr(b200, "state_guard", 0))
+        c.limit_relax, c.contact_relax = getattr(b200, "limit_relax", 0.5), getattr(b200, "contact_relax", 0.7)
+        c.state_guard = int(getattr(b200, "state_guard", 1))
         c.max_base_lin_vel, c.max_base_ang_vel = cfg.asset.max_linear_velocity, cfg.asset.max_angular_velocity
         c.mesh_type = 0 if self.plane else 1
         c.hf_rows, c.hf_cols = hs.shape
@@ -200,7 +200,7 @@ class EnvArrays:
         cm = cfg.commands
         if cfg.init_state.turn_over or cm.curriculum:
             raise NotImplementedError("turn_over / commands.curriculum are outside the hot path (SURVEY 8f-3)")
-        # heading commands (legged_robot.py:411-419): served by libgo2b200_relaxed.so only (go2_env_create of the default build rejects them)
+        # heading commands (legged_robot.py:411-419)
         c.heading_command, c.stop_heading_at_limit = int(bool(cm.heading_command)), int(bool(getattr(cm, "stop_heading_at_limit", False)))
         for name, key in (("ext_stop_heading", "stop_heading"), ("ext_heading_ranges", "heading_ranges")):       # addresses as 32-bit halves (go2_b200.h)
             setattr(c, name + "_lo", T[key].data_ptr() & 0xFFFFFFFF); setattr(c, name + "_hi", T[key].data_ptr() >> 32)
@@ -213,7 +213,7 @@ class EnvArrays:
         c.max_episode_length, c.max_episode_length_s, c.dt = self.max_episode_length, self.max_episode_length_s, self.dt
         for k, name in enumerate(_abi.REWARD_NAMES):
             c.reward_scales[k] = self.reward_scales.get(name, 0.0)
-        c.only_positive_rewards = int(bool(cfg.rewards.only_positive_rewards))     # off for every go2 task (go2_config.py:159); needs libgo2b200_relaxed.so
+        c.only_positive_rewards = int(bool(cfg.rewards.only_positive_rewards))     # off for every go2 task (go2_config.py:159)
         c.tracking_sigma, c.base_height_target = cfg.rewards.tracking_sigma, cfg.rewards.base_height_target
         for j in range(12):
             lo, hi = self.model.q_lower[j], self.model.q_upper[j]

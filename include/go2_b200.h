@@ -97,18 +97,17 @@ typedef struct Go2EnvConfig {
   float base_height_mask[GO2_NUM_HEIGHT];   /* legged_robot.py:790-795 */
   float num_base_height_points;
   float base_init_state[13];                /* pos, quat xyzw, lin vel, ang vel (legged_robot.py:1000) */
-  /* relaxation of the Jacobi sweeps (appended: earlier offsets are unchanged).  limit_relax = 0: joint-limit rows step with D_j (the first
-     solver of this build: over-relaxed when the parent link recoils, divergent for > 4 sweeps); limit_relax = w > 0: rows step with
-     w / (M^-1)_jj, the exact joint-space diagonal the mobility recursion already computes (convergent for w <= 0.5).  contact_relax scales
-     the contact rows' block step (1 = unchanged). */
+  /* relaxation of the Jacobi sweeps.  limit_relax = w > 0 (default 0.5): joint-limit rows step with w / (M^-1)_jj, the exact joint-space
+     diagonal the mobility recursion already computes (convergent for w <= 0.5); limit_relax = 0: rows step with D_j (the first solver of
+     round 1: over-relaxed when the parent link recoils, soft stops, divergent for > 4 sweeps — kept selectable for A/B only).
+     contact_relax scales the contact rows' block step (default 0.7; 1 = plain mass splitting). */
   float limit_relax, contact_relax;
-  /* state guard (appended).  0: off (the build every measurement of round 1 was made with).  1: the base twist is clamped to the asset's
-     max_linear_velocity / max_angular_velocity after every substep (legged_robot_config.py:131-132; PhysX clamps rigid-body velocities), and an
-     env whose state (root 13, dof_pos 12, dof_vel 12) holds a non-finite value after the substeps is put into its initial pose at its origin
-     with zero velocities / torques / contact forces and RESETS in this step (reset_buf = 1, time_out_buf = 0): one diverged env can never feed
-     a NaN into the shared policy / value networks. */
+  /* state guard (default 1).  The base twist is clamped to the asset's max_linear_velocity / max_angular_velocity after every substep
+     (legged_robot_config.py:131-132; PhysX clamps rigid-body velocities), and an env whose state (root 13, dof_pos 12, dof_vel 12) holds a
+     non-finite value after the substeps is put into its initial pose at its origin with zero velocities / torques / contact forces and RESETS
+     in this step (reset_buf = 1, time_out_buf = 0): one diverged env can never feed a NaN into the shared policy / value networks. */
   int32_t state_guard; float max_base_lin_vel, max_base_ang_vel;
-  /* env switches outside the GO2 defaults (appended; need the same build as the fields above, 0 = the GO2 defaults):
+  /* env switches outside the GO2 defaults (0 = the GO2 defaults):
      control_type 0 'P' / 1 'V' / 2 'T' (legged_robot.py:605-618); only_positive_rewards clips the summed reward at 0 (legged_robot.py:266-267) */
   int32_t control_type, only_positive_rewards;
   /* heading commands (legged_robot.py:411-419,468-472,547-548,581-582): commands[:,3] is a heading target, the yaw-rate command follows it

@@ -460,10 +460,6 @@ if __name__ == "__main__":
         make_case("ctrl_v_pos", plane=False, N=32, K=4, seed=13, control_type="V", only_positive=True)
         make_case("ctrl_t", plane=True, N=32, K=3, seed=14, control_type="T")
         make_case("heading", plane=False, N=48, K=6, seed=15, heading=True)
-        # the GO2 defaults over the RELAXED contact solver + state guard (the second library build's physics)
-        R = dict(limit_relax=0.5, contact_relax=0.7, limit_erp=0.8, state_guard=1)
-        make_case("rough_relaxed", plane=False, N=48, K=6, seed=7, b200=R)
-        make_case("plane_relaxed", plane=True, N=32, K=4, seed=7, b200=R)
         sys.exit(0)
     make_case("rough", plane=False)
     make_case("plane", plane=True, N=32, K=4)

@@ -8,7 +8,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["libgo2b200.so", "libgo2b200_relaxed.so"])
+@pytest.mark.parametrize("name", ["libgo2b200.so"])
 def test_library_exports_header_symbols(name):
     import __graft_entry__ as ge
     ge.build()
@@ -44,29 +44,33 @@ def test_product_fails_loudly_without_cuda():
         Go2Robot(cfg, None, None, "cuda:0", True)
 
 
-def test_create_rejects_solver_settings_the_build_does_not_carry():
-    """The sm_100a library of this round is built without the relaxed solver (GO2_RELAXED_SOLVER=0): go2_env_create must refuse
-    limit_relax / contact_relax instead of silently running the first solver (checked before any CUDA call, so it runs without a GPU)."""
+def test_create_accepts_every_solver_setting_and_env_switch():
+    """ONE library carries the convergent solver, the state guard, control types V / T, only_positive_rewards and heading commands: go2_env_create
+    gets past the settings to the topology check of the (empty) model for each of them (checked before any CUDA call, so it runs without a GPU),
+    and still rejects what no build serves."""
     import __graft_entry__ as ge
     ge.build()
     from go2_rl_gym_b200 import _abi
     lib = _abi.load_library()
-    cfg, mdl, buf = _abi.Go2EnvConfig(), _abi.Go2Model(), _abi.Go2EnvBuffers()
-    cfg.num_envs, cfg.limit_relax, cfg.contact_relax = 8, 0.5, 0.7
+    assert not os.path.exists(os.path.join(ROOT, "go2_rl_gym_b200", "libgo2b200_relaxed.so"))
+    mdl, buf = _abi.Go2Model(), _abi.Go2EnvBuffers()
     h = ctypes.c_void_p()
-    rc = lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
-    assert rc != 0 and b"relaxed solver" in lib.go2_last_error()
-    cfg.limit_relax, cfg.contact_relax, cfg.state_guard = 0.0, 1.0, 1
-    rc = lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
-    assert rc != 0 and b"state guard" in lib.go2_last_error()
-    # the second build (libgo2b200_relaxed.so) accepts them: it gets past this check to the topology check of the (empty) model
-    relaxed = _abi.load_library(os.path.join(ROOT, "go2_rl_gym_b200", "libgo2b200_relaxed.so"))
-    cfg.limit_relax, cfg.contact_relax = 0.5, 0.7
-    rc = relaxed.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
-    assert rc != 0 and b"joint axes" in relaxed.go2_last_error()
+    for kw in (dict(limit_relax=0.5, contact_relax=0.7, state_guard=1), dict(limit_relax=0.0, contact_relax=1.0, state_guard=0),
+               dict(control_type=1), dict(control_type=2, only_positive_rewards=1)):
+        cfg = _abi.Go2EnvConfig()
+        cfg.num_envs = 8
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        rc = lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h))
+        assert rc != 0 and b"joint axes" in lib.go2_last_error(), (kw, lib.go2_last_error())
+    cfg = _abi.Go2EnvConfig()
+    cfg.num_envs, cfg.control_type = 8, 3
+    assert lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h)) != 0 and b"control_type" in lib.go2_last_error()
+    cfg.control_type, cfg.heading_command = 0, 1            # heading commands need their two per-env arrays
+    assert lib.go2_env_create(ctypes.byref(cfg), ctypes.byref(mdl), ctypes.byref(buf), ctypes.byref(h)) != 0 and b"ext_stop_heading" in lib.go2_last_error()
 
 
-@pytest.mark.parametrize("name", ["libgo2b200.so", "libgo2b200_relaxed.so"])
+@pytest.mark.parametrize("name", ["libgo2b200.so"])
 def test_every_bound_trainer_entry_point_is_exported_and_declared(name):
     """rl/_ops.py binds its whole signature table when the library is first used: one missing symbol would take the trainer (and bench.py) down."""
     import __graft_entry__ as ge

@@ -24,9 +24,9 @@ def test_emulated_kernel_matches_reference_golden(name, packed):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "rough_relaxed", "plane_relaxed"])
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "cmdcur"])
 def test_emulated_kernel_matches_reference_golden_with_env_switches(name, packed):
-    """control_type 'V' / 'T' and only_positive_rewards (compiled into the kernel with -DGO2_RELAXED_SOLVER=1 like the emulation):
+    """control_type 'V' / 'T', only_positive_rewards, heading commands and the command-range curriculum boundary:
     every recorded step of the reference-made fixture, state re-synchronised to the fixture between steps."""
     z, A = load_case(name)
     env = EmuEnv(A, packed=packed)
@@ -166,12 +166,19 @@ def test_emulated_kernel_stance_and_drop():
     assert float(T["projected_gravity"][0, 2]) < -0.99
 
 
-# ---- the opt-in relaxed contact / joint-limit solver (sim.b200.limit_relax > 0) ---------------------------------------
+# ---- the convergent contact / joint-limit solver (default: sim.b200.limit_relax = 0.5) vs round 1's first solver ------
+def _legacy(cfg):
+    """round 1's first solver: limit rows stepping with D_j, plain mass splitting, soft limit ERP, no state guard"""
+    cfg.sim.b200.limit_relax, cfg.sim.b200.contact_relax, cfg.sim.b200.limit_erp, cfg.sim.b200.state_guard = 0.0, 1.0, 0.2, 0
+    return cfg
+
+
 def _relaxed_cfg(N, iters=4):
     cfg = GO2Cfg(); cfg.terrain.mesh_type = "plane"; cfg.env.num_envs = N; cfg.domain_rand.push_robots = False
     for k in ("randomize_motor_strength", "randomize_pd_gains", "randomize_motor_zero_offset", "randomize_friction", "randomize_action_delay"):
         setattr(cfg.domain_rand, k, False)
     cfg.sim.b200.solver_iterations = iters
+    assert (cfg.sim.b200.limit_relax, cfg.sim.b200.contact_relax, cfg.sim.b200.limit_erp, cfg.sim.b200.state_guard) == (0.5, 0.7, 0.8, 1)   # the defaults
     return cfg
 
 
@@ -198,9 +205,9 @@ def test_relaxed_solver_converges_where_the_first_one_diverges():
     """Oracle (the physics spec): with the first solver the Jacobi sweeps DIVERGE when more of them are run (joint-limit rows stepping with D_j
     are over-relaxed); with the exact joint-space diagonal and a 0.5 step (contacts 0.7) nothing becomes non-finite and the overshoot shrinks as
     sweeps are added.  At the shipped 4 sweeps the joint stops get ~20x stiffer."""
-    legacy4 = _limit_probe(OracleEnv, _relaxed_cfg(8, 4))
+    legacy4 = _limit_probe(OracleEnv, _legacy(_relaxed_cfg(8, 4)))
     assert legacy4 is not None and float(legacy4.max()) > 1.0                      # the documented weakness of the first solver
-    assert _limit_probe(OracleEnv, _relaxed_cfg(8, 16), steps=40) is None           # ... and its divergence with more sweeps
+    assert _limit_probe(OracleEnv, _legacy(_relaxed_cfg(8, 16)), steps=40) is None           # ... and its divergence with more sweeps
     worst = []
     for iters in (4, 8, 16):
         cfg = _relaxed_cfg(8, iters)
@@ -247,8 +254,8 @@ def test_relaxed_solver_holds_joint_stops_in_free_flight(kind):
     the relaxed solver parks the joints at the stops (overshoot < 0.2 rad, finite)."""
     def run(scale, relaxed):
         cfg = _relaxed_cfg(2, 4)
-        if relaxed:
-            cfg.sim.b200.limit_relax, cfg.sim.b200.contact_relax, cfg.sim.b200.limit_erp = 0.5, 0.7, 0.8
+        if not relaxed:
+            _legacy(cfg)
         A = EnvArrays(cfg, "cpu", seed=3)
         env = OracleEnv(A) if kind == "oracle" else EmuEnv(A)
         env.reset_all(); T = A.tensors

@@ -15,6 +15,9 @@ def _free_flight(sim_dt):
     T["root_states"][:, 2] = 10.0
     T["root_states"][:, 7:13] = torch.tensor([0.3, -0.2, 0.5, 1.0, -2.0, 1.5])
     T["dof_vel"][:] = torch.linspace(-3, 3, 12)
+    # start inside the joint limits: _reset_dofs draws q0 * U[0.5, 1.5] unclamped (the calf can start 0.088 rad past its stop), and the stop's
+    # position correction limit_erp * penetration / dt is a velocity that GROWS as dt shrinks: not the first-order integration error measured here
+    T["dof_pos"][:] = torch.tensor(A.default_dof_pos_np)
     mech = lambda: mechanics(A.model_json, T["body_inertia"][0].numpy(), T["root_states"][0].numpy(), T["dof_pos"][0].numpy().astype(np.float64),
                              T["dof_vel"][0].numpy().astype(np.float64))
     M, c0, KE0, PE0, P0, L0 = mech()
