@@ -123,6 +123,8 @@ __global__ void finalize_kernel(const Go2EnvConfig* __restrict__ cfg, float* __r
     else if (k < GO2_NUM_REW + 10) st[k] = id_counts[k - GO2_NUM_REW - 1] > 0 ? ep_accum[k] / id_counts[k - GO2_NUM_REW - 1] : 0.0f;
     else if (k == GO2_NUM_REW + 10) st[k] = n_reset;
     else if (k == GO2_NUM_REW + 11) st[k] = 1.0f;
+  } else if (ep_stats != nullptr && k < GO2_EP_STATS) {   // no reset in this step: the previous step's row is served again (header: GO2_EP_SLOTS)
+    ep_stats[(size_t)slot * GO2_EP_STATS + k] = ep_stats[(size_t)((slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_EP_STATS + k];
   }
   __syncthreads();
   if (k < GO2_EP_STATS + 2) ep_accum[k] = 0.0f;

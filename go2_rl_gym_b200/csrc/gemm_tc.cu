@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 
 #include "../../include/go2_b200.h"
@@ -308,20 +309,44 @@ struct TcParamsP {
   int epi, has_c, has_ct, has_aux;
 };
 
+// ---- 3xTF32 (error-compensated split): every fp32 operand a is used as hi = rn_tf32(a) and lo = a - hi (exact in fp32), and the product is
+// accumulated as lo_a hi_b + hi_a lo_b + hi_a hi_b (the lo lo term, 2^-22 relative, is dropped; hardware truncation of lo adds 2^-21): fp32-class
+// products out of the tf32 tensor-core path, 3 MMAs per K step from the SAME TMA-loaded tiles.  Four "splitter" warps sit between the TMA ring and
+// the MMA warp: they rewrite each landed stage in place with hi and write lo into a 2-slot side ring of the same (swizzled) layout, so the
+// descriptors of the lo operands are the raw ones at another base address.  The GEMMs of this path are HBM / L2 bound (33 flop/B), so the two extra
+// MMAs and the shared-memory pass hide behind the operand stream.
+__device__ __forceinline__ float4 split_tf32(float4& v) {
+  float4 lo;
+  uint32_t h;
+#define GO2_SPLIT1(c) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.c)); { const float hf = __uint_as_float(h); lo.c = (fabsf(hf) < INFINITY) ? v.c - hf : 0.0f; v.c = hf; }
+  GO2_SPLIT1(x) GO2_SPLIT1(y) GO2_SPLIT1(z) GO2_SPLIT1(w)
+#undef GO2_SPLIT1
+  return lo;
+}
+constexpr int TCP_LO_SLOTS = 2;
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                : "memory");
 }
 
 constexpr int TCP_THREADS = 320;                 // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int TCP_THREADS_X3 = 448;              // + 4 splitter warps (3xTF32)
 constexpr int TCP_CHUNK_BYTES = TC_BM * 32 * 4;  // one staged 128 x 32 chunk
 constexpr int TCP_MAX_STAGES = 4;
-static int tcp_smem_bytes(int BN, int stages, bool has_ct) {
-  return stages * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + (has_ct ? 6 : 4) * TCP_CHUNK_BYTES + 256 + 1024;
+constexpr int TCP_SMEM_MAX = 232448;             // 227 KB opt-in limit per CTA
+static int tcp_smem_bytes(int BN, int stages, bool has_ct, bool x3) {
+  return (stages + (x3 ? TCP_LO_SLOTS : 0)) * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + (has_ct ? 6 : 4) * TCP_CHUNK_BYTES + 256 + 1024;
+}
+// ring depth: 4 stages for the single-pass kernel; with the lo side ring what the 227 KB leave (3 at BN = 128, 2 at BN = 160 or with Ct)
+static int tcp_stages(int BN, bool has_ct, bool x3) {
+  int s = TCP_MAX_STAGES;
+  while (s > 2 && tcp_smem_bytes(BN, s, has_ct, x3) > TCP_SMEM_MAX) --s;
+  return s;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(TCP_THREADS, 1)
+template <int BN, bool X3>
+__global__ void __launch_bounds__(X3 ? TCP_THREADS_X3 : TCP_THREADS, 1)
 gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                          const __grid_constant__ CUtensorMap tmCt, const __grid_constant__ CUtensorMap tmAux, const TcParamsP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -329,14 +354,17 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int NCH = (BN + 31) / 32;
   const int S = p.stages;
-  uint8_t* cst = smem + S * STAGE_BYTES;                       // [group][2] row-major staging chunks [128 rows][128 B], SW128
+  uint8_t* lo_ring = smem + S * STAGE_BYTES;                   // 3xTF32: TCP_LO_SLOTS stages holding the lo parts (same layout as the raw stage)
+  uint8_t* cst = lo_ring + (X3 ? TCP_LO_SLOTS * STAGE_BYTES : 0);   // [group][2] row-major staging chunks [128 rows][128 B], SW128
   uint8_t* tst = cst + 4 * TCP_CHUNK_BYTES;                    // [group] transposed staging chunk [32 n][128 m] floats (only with Ct)
   uint64_t* full_bar = (uint64_t*)(tst + (p.has_ct ? 2 * TCP_CHUNK_BYTES : 0));
   uint64_t* empty_bar = full_bar + TCP_MAX_STAGES;
   uint64_t* tfull = empty_bar + TCP_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* auxb = tempty + 2;                                 // [group][2]
-  uint32_t* tmem_slot = (uint32_t*)(auxb + 4);
+  uint64_t* lofull = auxb + 4;                                 // [TCP_LO_SLOTS] splitter -> MMA (4 warps arrive)
+  uint64_t* loempty = lofull + TCP_LO_SLOTS;                   // [TCP_LO_SLOTS] MMA commit -> splitter
+  uint32_t* tmem_slot = (uint32_t*)(loempty + TCP_LO_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = p.m_tiles * p.n_tiles * p.splits;
@@ -350,6 +378,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int s = 0; s < S; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 8); }
     for (int b = 0; b < 4; ++b) mbar_init(auxb + b, 1);
+    for (int b = 0; b < TCP_LO_SLOTS; ++b) { mbar_init(lofull + b, 4); mbar_init(loempty + b, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the whole TMEM: two accumulators of up to 256 columns
@@ -390,8 +419,8 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===== MMA issuer (one thread)
     if (elect_one()) {
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int s = 0, ui = 0;
-      uint32_t ph = 0;
+      int s = 0, ui = 0, l = 0;
+      uint32_t ph = 0, lph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
         const int z = u / (p.n_tiles * p.m_tiles);
         const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
@@ -401,22 +430,64 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar + s, ph);
+          if (X3) mbar_wait(lofull + l, lph);                     // the splitter warps have rewritten this stage as hi and filled the lo slot
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sl = smem_u32(lo_ring + l * STAGE_BYTES);
           if (!p.mn_major) {
             const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
+            const uint64_t la = make_desc_kmajor_sw128(sl), lb = make_desc_kmajor_sw128(sl + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              if (X3) {   // small terms first
+                umma_tf32(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+                umma_tf32(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
+                umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
+              } else umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+            }
           } else {   // 8 contraction rows per instruction = 1024 B further into every box
             const uint64_t da = make_desc_mnmajor_sw128_32b(sa), db = make_desc_mnmajor_sw128_32b(sa + A_BYTES);
+            const uint64_t la = make_desc_mnmajor_sw128_32b(sl), lb = make_desc_mnmajor_sw128_32b(sl + A_BYTES);
+            constexpr uint32_t IDT = IDESC | (1u << 15) | (1u << 16);
 #pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-              umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDESC | (1u << 15) | (1u << 16), (kb | k) ? 1u : 0u);
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              if (X3) {
+                umma_tf32(tacc, la + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDT, (kb | k) ? 1u : 0u);
+                umma_tf32(tacc, da + (uint64_t)(64 * k), lb + (uint64_t)(64 * k), IDT, 1u);
+                umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDT, 1u);
+              } else umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDT, (kb | k) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar + s);
+          if (X3) { umma_commit(loempty + l); if (++l == TCP_LO_SLOTS) { l = 0; lph ^= 1; } }
           if (++s == S) { s = 0; ph ^= 1; }
         }
         umma_commit(tfull + buf);
+      }
+    }
+  } else if (X3 && warp >= 10) {
+    // ===== splitter warps (3xTF32): stage s landed -> hi in place, lo into slot l; then hand both to the MMA warp
+    const int t = threadIdx.x - 320;
+    int s = 0, l = 0;
+    uint32_t ph = 0, lph = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int z = u / (p.n_tiles * p.m_tiles);
+      const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar + s, ph);                              // TMA bytes have landed (async proxy -> visible after the wait)
+        mbar_wait(loempty + l, lph ^ 1);                          // the MMAs that read this lo slot have retired
+        float4* raw = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(lo_ring + l * STAGE_BYTES);
+#pragma unroll 4
+        for (int i = t; i < STAGE_BYTES / 16; i += 128) {
+          float4 v = raw[i];
+          const float4 w = split_tf32(v);
+          raw[i] = v; lo[i] = w;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(lofull + l)) : "memory");
+        if (++l == TCP_LO_SLOTS) { l = 0; lph ^= 1; }
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -683,26 +754,32 @@ static bool persist_ok(const TcParams& p) {
   return p.C || p.Ct;
 }
 
-template <int BN>
+template <int BN, bool X3>
 static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tct, const CUtensorMap& taux,
                           const TcParamsP& pp, cudaStream_t st) {
-  const int smem = tcp_smem_bytes(BN, pp.stages, pp.has_ct != 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
+  const int smem = tcp_smem_bytes(BN, pp.stages, pp.has_ct != 0, X3);
+  GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persist_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_MAX));   // per device; cheap
   const int units = pp.m_tiles * pp.n_tiles * pp.splits;
-  gemm_tf32_persist_kernel<BN><<<min(units, sm_count()), TCP_THREADS, smem, st>>>(ta, tb, tc, tct, taux, pp);
+  gemm_tf32_persist_kernel<BN, X3><<<min(units, sm_count()), X3 ? TCP_THREADS_X3 : TCP_THREADS, smem, st>>>(ta, tb, tc, tct, taux, pp);
   count_launch();
   return 0;
 }
 
+// multiply precision of the tensor-core GEMMs: 3 = 3xTF32 split (default, fp32-class products), 1 = single tf32 pass (round 1's kernel;
+// GO2_GEMM=tf32 or go2_gemm_set_passes(1))
+static int g_tc_passes = 0;
+static int tc_passes() {
+  if (!g_tc_passes) { const char* e = getenv("GO2_GEMM"); g_tc_passes = (e && !strcmp(e, "tf32")) ? 1 : 3; }
+  return g_tc_passes;
+}
+
 // split-K slices of C sit rows_pad = roundup(M, 128) rows apart so that one 2-D map covers all of them
 static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
-  const int BN = p.Ct ? 128 : persist_bn(p.N);          // the 160-wide tile has no room for the transposed staging buffers
+  const bool x3 = tc_passes() == 3;
+  // the 160-wide tile has no room for the transposed staging buffers; with the lo side ring of 3xTF32 it only keeps 2 stages: used for N <= 160 only
+  const int BN = (p.Ct || (x3 && p.N > 160)) ? 128 : persist_bn(p.N);
   TcParamsP pp{};
-  pp.stages = 4;
+  pp.stages = tcp_stages(BN, p.Ct != nullptr, x3);
   pp.M = p.M; pp.N = p.N; pp.K = p.K;
   pp.m_tiles = (p.M + TC_BM - 1) / TC_BM; pp.n_tiles = (p.N + BN - 1) / BN;
   pp.total_kb = (p.K + TC_BK - 1) / TC_BK;
@@ -721,7 +798,8 @@ static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, c
   if (p.C) { rc = make_map(&tc, p.C, splits > 1 ? (long)splits * pp.rows_pad : p.M, p.N, p.ldc, TC_BM); if (rc) return rc; }
   if (p.Ct) { rc = make_map(&tct, p.Ct, p.N, p.M, p.ldct, 32, TC_BM); if (rc) return rc; }
   if (pp.has_aux) { rc = make_map(&taux, p.aux, p.M, p.N, p.ldaux, TC_BM); if (rc) return rc; }
-  rc = BN == 160 ? launch_persist<160>(ta, tb, tc, tct, taux, pp, st) : launch_persist<128>(ta, tb, tc, tct, taux, pp, st);
+  if (x3) rc = BN == 160 ? launch_persist<160, true>(ta, tb, tc, tct, taux, pp, st) : launch_persist<128, true>(ta, tb, tc, tct, taux, pp, st);
+  else rc = BN == 160 ? launch_persist<160, false>(ta, tb, tc, tct, taux, pp, st) : launch_persist<128, false>(ta, tb, tc, tct, taux, pp, st);
   if (rc) return rc;
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -730,6 +808,11 @@ static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, c
 // C[M,N] = A[M,K] B[N,K]^T with both operands K-major; see TcParams for the epilogue
 static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams p, int splits, cudaStream_t st) {
   if (persist_ok(p)) return gemm_tc_persist(A, lda, B, ldb, p, splits, st);
+  // the one-tile-per-CTA kernel below is the single-pass tf32 kernel of round 1 (debug stamps, GO2_GEMM_LEGACY, operands the TMA store path
+  // cannot take): never a silent precision downgrade of the 3xTF32 default
+  if (tc_passes() == 3 && !legacy_only() && !p.dbg)
+    return set_error(5, "gemm_tc: operands do not meet the persistent kernel's alignment rules (16-byte aligned C / aux, ld % 4 == 0); "
+                        "the single-pass tf32 kernel needs go2_gemm_set_passes(1)");
   const int BN = p.N > 64 ? 128 : 64;
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, p.M, p.K, lda, TC_BM);
@@ -751,6 +834,13 @@ static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams 
 using namespace go2;
 
 extern "C" {
+
+int go2_gemm_set_passes(int passes) {
+  if (passes != 1 && passes != 3) return set_error(1, "go2_gemm_set_passes: 1 (single tf32 pass) or 3 (3xTF32 split)");
+  g_tc_passes = passes;
+  return 0;
+}
+int go2_gemm_get_passes(void) { return tc_passes(); }
 
 // Y[M,N] (and optionally Yt[N,M]) = act(X[M,K] W[N,K]^T + b)
 int go2_linear_forward_tc(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N,

@@ -203,11 +203,16 @@ class LeggedRobot:
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def end_rollout(self):
-        """extras of the rollout's steps (what step() would have returned in infos['episode'] at each of them)."""
+        """extras of the rollout's steps (what step() would have returned in infos['episode'] at each of them): a step without a reset re-serves the
+        previous step's statistics (the kernel copies the row forward) and nothing is served before the first reset ever, like the reference's
+        extras dict, which has no 'episode' key until then (legged_robot.py:229-242, on_policy_runner.py:145-146).  One D2H read per rollout."""
+        assert len(self._rollout_slots) <= EP_SLOTS, "num_steps_per_env must not exceed the episode-statistics ring (GO2_EP_SLOTS)"
+        valid = self._A.tensors["ep_stats"][self._rollout_slots, _abi.NUM_REW + 11].cpu()
         eps = []
-        for slot in self._rollout_slots:
+        for slot, v in zip(self._rollout_slots, valid.tolist()):
             self._fill_extras(slot)
-            eps.append(self.extras["episode"])
+            if v > 0:
+                eps.append(self.extras["episode"])
         return eps
 
     def step_host(self, actions_np, obs_out, priv_out, rew_out, reset_out):

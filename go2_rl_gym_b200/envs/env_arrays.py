@@ -24,7 +24,7 @@ from ..utils.terrain import Terrain, TERRAIN_NAMES
 
 _U8 = ("reset_buf", "time_out_buf", "last_is_limit_vel")
 _I32 = ("episode_length_buf", "terrain_levels", "terrain_types", "terrain_ids")
-EP_SLOTS = 64
+EP_SLOTS = 64          # = GO2_EP_SLOTS (include/go2_b200.h): the finalize kernel copies the previous slot forward on steps without a reset
 
 
 class EnvArrays:

@@ -13,6 +13,7 @@ import torch.distributed as dist
 from .. import _ops, dist_utils
 from .._ops import call, ptr
 from ..storage.rollout_storage_cts import RolloutStorageCTS
+from .ppo import adam_group_template
 
 
 class CTS:
@@ -312,8 +313,17 @@ class CTS:
             n, off = p.numel(), self.model._offsets[k]
             state[i] = {"step": lr_state[1].detach().cpu().clone(), "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
-        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "params": list(range(len(names)))}
-        return {"state": state, "param_groups": [group]}
+        # one param_group per top-level module, in the order the reference hands them to torch.optim.Adam (cts.py:73-80: teacher_encoder, critic,
+        # actor, std for optimizer 1; the student encoder alone for optimizer 2), each with the installed torch's full Adam key set (ppo.adam_group_template), so that the reference's
+        # Optimizer.load_state_dict (which checks the group count and sizes) accepts a checkpoint written here
+        groups, prev = [], None
+        for i, k in enumerate(names):
+            top = k.split(".")[0]
+            if top != prev:
+                groups.append(dict(adam_group_template(), lr=lr, params=[]))
+                prev = top
+            groups[-1]["params"].append(i)
+        return {"state": state, "param_groups": groups}
 
     def optimizer1_state_dict(self):
         return self._opt_state(self.model.seg1_names, self.learning_rate, self._lr1)

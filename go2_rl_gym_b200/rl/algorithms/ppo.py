@@ -15,6 +15,14 @@ from ..modules import ActorCritic
 from ..storage import RolloutStorage
 
 
+def adam_group_template():
+    """The param_group keys (with their defaults) of the installed torch's Adam: the key set differs between torch versions (2.11 adds
+    decoupled_weight_decay; the reference recommends 2.3.1), and the reference's Optimizer.load_state_dict takes the saved group verbatim."""
+    g = dict(torch.optim.Adam([torch.zeros(1)], lr=1e-3).param_groups[0])
+    g.pop("params")
+    return g
+
+
 class PPO:
     actor_critic: ActorCritic
 
@@ -217,8 +225,7 @@ class PPO:
             k, off = p.numel(), offs[name]
             state[i] = {"step": torch.tensor(float(self._opt_step)), "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
-        group = {"lr": self.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
-                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(state)))}
+        group = dict(adam_group_template(), lr=self.learning_rate, params=list(range(len(state))))
         return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):

@@ -72,7 +72,7 @@ class OnPolicyRunnerCTS:
             alg.process_env_step(rewards, dones, infos)
             if log:
                 if not dev and 'episode' in infos:
-                    ep_infos.append(infos['episode'])
+                    ep_infos.append((infos['episode'], infos.get('episode_valid')))
                 self._cur_reward_sum += rewards
                 self._cur_episode_length += 1
                 self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
@@ -93,7 +93,11 @@ class OnPolicyRunnerCTS:
                     alg.end_rollout(T)
                 ep_infos = env.end_rollout()
                 return ep_infos if log else []
-            return self._rollout_steps(log, False)
+            ep_infos = self._rollout_steps(log, False)
+            # eager steps serve extras["episode"] without a host sync; rows from before the env's first reset are dropped here, once per rollout
+            flags = [v for _, v in ep_infos if v is not None]
+            keep = torch.stack(flags).cpu().tolist() if flags else []
+            return [e for (e, v), k in zip(ep_infos, keep or [1.0] * len(ep_infos)) if k > 0]
 
     def run_iteration(self, sync=None):
         """One un-logged iteration (rollout + returns + both update passes) — the timing loop of bench.py / tools."""
@@ -204,6 +208,8 @@ class OnPolicyRunnerCTS:
         if load_optimizer:
             self.alg.load_optimizer_state_dicts(d.get('optimizer1_state_dict'), d.get('optimizer2_state_dict'))
         self.current_learning_iteration = d['iter']
+        # the action-sampling stream is keyed (seed, env, step): continue it where the saved run stood instead of replaying iteration 0's draws
+        self.alg._act_step = self.current_learning_iteration * self.num_steps_per_env
         return d['infos']
 
     def get_inference_policy(self, device=None):

@@ -30,7 +30,10 @@ extern "C" {
 #define GO2_NUM_REW 14       /* active reward terms of GO2Cfg (go2_config.py:178-194) */
 #define GO2_NUM_CMD 4
 #define GO2_INERTIA_STRIDE 10 /* mass, com xyz, Ixx Iyy Izz Ixy Ixz Iyz (about COM, link frame) */
-#define GO2_EP_STATS (GO2_NUM_REW + 12) /* rew means [14], terrain level mean, per-terrain-id means [9], n_reset, spare */
+#define GO2_EP_STATS (GO2_NUM_REW + 12) /* rew means [14], terrain level mean, per-terrain-id means [9], n_reset, valid flag */
+#define GO2_EP_SLOTS 64 /* rows of ep_stats: a ring indexed by Go2StepParams.ep_slot.  A step in which no env reset copies the previous slot's row
+                           forward (the reference re-serves its stale extras["episode"], legged_robot.py:229-242 / on_policy_runner.py:145-146); the
+                           valid flag stays 0 until the first reset, when the reference's extras has no "episode" key yet */
 
 /* order of reward terms everywhere (scales, curriculum scales, episode_sums columns) */
 enum Go2Reward {
@@ -246,6 +249,12 @@ int go2_refresh_weights(int n, const float* const* src, const int* ldin, float* 
                         const int* transpose, void* stream);
 /* out[cols,rows] = in[rows,cols]^T */
 int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, int cols, void* stream);
+/* Multiply precision of the tensor-core GEMMs (process-wide).  3 (default): 3xTF32 — every fp32 operand is split in shared memory into
+   hi = rn_tf32(a) and lo = a - hi and the product accumulates lo_a hi_b + hi_a lo_b + hi_a hi_b in fp32 (TMEM): fp32-class products
+   (relative error ~1e-6) matching the reference's sgemm (rsl_rl/algorithms/ppo.py:120-187 runs torch fp32).  1: one tf32 pass (10-bit
+   mantissa products; round 1's kernel, kept for A/B; also selected by the environment variable GO2_GEMM=tf32). */
+int go2_gemm_set_passes(int passes);
+int go2_gemm_get_passes(void);
 /* db[N] = column sums of dY[M,N] */
 int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */

@@ -893,6 +893,10 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     for (int t = 0; t < 9; ++t) st[GO2_NUM_REW + 1 + t] = lvl_cnt[t] > 0 ? (float)(lvl_sum[t] / lvl_cnt[t]) : 0.0f;
     st[GO2_NUM_REW + 10] = (float)n_reset;
     st[GO2_NUM_REW + 11] = 1.0f;
+  } else if (B.ep_stats) {   // no reset: the previous step's row is served again (include/go2_b200.h: GO2_EP_SLOTS)
+    const float* prev = B.ep_stats + (size_t)((sp.ep_slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_EP_STATS;
+    float* st = B.ep_stats + (size_t)sp.ep_slot * GO2_EP_STATS;
+    for (int k = 0; k < GO2_EP_STATS; ++k) st[k] = prev[k];
   }
   return 0;
 }

@@ -36,6 +36,10 @@ int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* 
     for (int t = 0; t < 9; ++t) st[GO2_NUM_REW + 1 + t] = cnt[t] ? B->ep_accum[GO2_NUM_REW + 1 + t] / cnt[t] : 0.0f;
     st[GO2_NUM_REW + 10] = n_reset;
     st[GO2_NUM_REW + 11] = 1.0f;
+  } else if (B->ep_stats) {
+    const float* prev = B->ep_stats + (size_t)((sp->ep_slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_EP_STATS;
+    float* st = B->ep_stats + (size_t)sp->ep_slot * GO2_EP_STATS;
+    for (int k = 0; k < GO2_EP_STATS; ++k) st[k] = prev[k];
   }
   return 0;
 }

@@ -45,13 +45,29 @@ def _tma(ptr, ld, what):
     _need(int(ptr) % 16 == 0 and int(ld) % 4 == 0, f"{what}: TMA operand must be 16-byte aligned with a 16-byte multiple row pitch")
 
 
-def _tf32(a):
-    """GO2_EMU_TF32=1: operands of the tensor-core entry points lose their low 13 mantissa bits, like tcgen05 kind::tf32 reading fp32 data
-    (used to check on the CPU that the tf32 bars of the GPU tests are realistic for new wirings)."""
-    import os
-    if os.environ.get("GO2_EMU_TF32", "0") != "1":
-        return a
+def _trunc_tf32(a):
     return (np.ascontiguousarray(a, dtype=F).view(np.uint32) & np.uint32(0xFFFFE000)).view(F)
+
+
+def _rna_tf32(a):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) at 10 mantissa bits"""
+    u = np.ascontiguousarray(a, dtype=F).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(F)
+
+
+def _mm_tc(a, b):
+    """a @ b.T as the tensor-core entry points form it (csrc/gemm_tc.cu), selected by GO2_EMU_TF32 (checks on the CPU that the bars of the GPU tests
+    are realistic for new wirings): '0' (default) plain fp32; '1' one tf32 pass: operands lose their low 13 mantissa bits, like tcgen05 kind::tf32
+    reading fp32 data; '3' the library's default 3xTF32 split: hi = rna_tf32(a), lo = a - hi (read truncated), lo_a hi_b + hi_a lo_b + hi_a hi_b."""
+    import os
+    mode = os.environ.get("GO2_EMU_TF32", "0")
+    if mode == "1":
+        return _trunc_tf32(a) @ _trunc_tf32(b).T
+    if mode == "3":
+        ah, bh = _rna_tf32(a), _rna_tf32(b)
+        al, bl = _trunc_tf32(np.asarray(a, F) - ah), _trunc_tf32(np.asarray(b, F) - bh)
+        return ((al @ bh.T).astype(F) + (ah @ bl.T).astype(F)).astype(F) + (ah @ bh.T).astype(F)
+    return a @ b.T
 
 
 def _elu(x):
@@ -84,9 +100,7 @@ def _linear_forward(X, ldx, W, ldw, b, Y, ldy, Yt, ldyt, M, N, K, act, tc):
     if tc:
         _tma(X, ldx, "forward_tc X"); _tma(W, ldw, "forward_tc W")
     x, w = _mat(X, M, K, ldx), _mat(W, N, K, ldw)
-    if tc:
-        x, w = _tf32(x), _tf32(w)
-    y = x @ w.T
+    y = _mm_tc(x, w) if tc else x @ w.T
     if b:
         y = y + _vec(b, N)
     y = y.astype(F)
@@ -119,7 +133,7 @@ def go2_linear_dgrad_simt(dY, lddy, W, ldw, act_in, ldact, dX, lddx, dXt, lddxt,
 
 def go2_linear_dgrad_tc(dZ, lddz, Wt, ldwt, act_in, ldact, act_in_t, ldact_t, dX, lddx, dXt, lddxt, M, N, K, stream):
     _tma(dZ, lddz, "dgrad_tc dZ"); _tma(Wt, ldwt, "dgrad_tc Wt")
-    d = (_tf32(_mat(dZ, M, N, lddz)) @ _tf32(_mat(Wt, K, N, ldwt)).T).astype(F)
+    d = _mm_tc(_mat(dZ, M, N, lddz), _mat(Wt, K, N, ldwt)).astype(F)
     if act_in:
         d = d * _elu_grad_from_out(_mat(act_in, M, K, ldact))
     elif act_in_t:
@@ -144,7 +158,7 @@ def go2_linear_wgrad_tc_rm(dZ, lddz, X, ldx, dW, lddw, db, M, N, K, ws, wsn, str
     ldp, rows_pad = (kk + 3) // 4 * 4, (N + 127) // 128 * 128
     _need(rows_pad * ldp <= wsn, "go2_linear_wgrad_tc_rm: workspace too small")
     _need(ldx >= kk, "go2_linear_wgrad_tc_rm: no room for the ones column")
-    full = (_tf32(_mat(dZ, M, N, lddz)).T @ _tf32(_mat(X, M, kk, ldx))).astype(F)
+    full = _mm_tc(_mat(dZ, M, N, lddz).T, _mat(X, M, kk, ldx).T).astype(F)
     _mat(dW, N, K, lddw)[...] = full[:, :K]
     if db:
         _vec(db, N)[...] = full[:, K]
@@ -154,7 +168,7 @@ def go2_linear_wgrad_tc_rm(dZ, lddz, X, ldx, dW, lddw, db, M, N, K, ws, wsn, str
 def go2_linear_wgrad_tc(dZt, lddzt, Xt, ldxt, dW, lddw, db, M, N, K, ws, wsn, stream):
     _tma(dZt, lddzt, "wgrad_tc dZt"); _tma(Xt, ldxt, "wgrad_tc Xt")
     kk = K + 1 if db else K
-    full = (_tf32(_mat(dZt, N, M, lddzt)) @ _tf32(_mat(Xt, kk, M, ldxt)).T).astype(F)
+    full = _mm_tc(_mat(dZt, N, M, lddzt), _mat(Xt, kk, M, ldxt)).astype(F)
     _mat(dW, N, K, lddw)[...] = full[:, :K]
     if db:
         _vec(db, N)[...] = full[:, K]

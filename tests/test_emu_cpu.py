@@ -391,3 +391,28 @@ def test_emulated_kernel_tracks_oracle_off_the_training_defaults(name, overrides
         n_reset += int(Ac.tensors["reset_buf"].sum())
         copy_state(Ac.tensors, Ae.tensors)
     assert n_reset > 0
+
+
+@pytest.mark.parametrize("kind", ["oracle", "emu"])
+def test_episode_statistics_are_reserved_on_steps_without_a_reset(kind):
+    """extras["episode"] semantics (legged_robot.py:229-242, on_policy_runner.py:145-146): no 'episode' entry before the first reset (valid
+    flag 0), a fresh row on a step with resets, and on later steps WITHOUT a reset the previous step's row served again (copied forward in the ring),
+    not whatever an older rollout left in that slot."""
+    from go2_rl_gym_b200 import _abi
+    cfg = GO2Cfg(); cfg.terrain.mesh_type = "plane"; cfg.env.num_envs = 4; cfg.domain_rand.push_robots = False
+    A = EnvArrays(cfg, "cpu", seed=3)
+    env = OracleEnv(A) if kind == "oracle" else EmuEnv(A)
+    env.reset_all(); T = A.tensors
+    T["ep_stats"].fill_(7.0)                                    # stale garbage in every slot
+    T["ep_stats"][:, _abi.NUM_REW + 11] = 0
+    rows = []
+    for k in range(4):
+        if k == 1:
+            T["episode_length_buf"][0] = 1250                   # env 0 times out in this step
+        sp = env.step(torch.zeros(4, 12))
+        rows.append(T["ep_stats"][sp.ep_slot].clone())
+        assert int(T["reset_buf"].sum()) == (1 if k == 1 else 0)
+    v = _abi.NUM_REW + 11
+    assert float(rows[0][v]) == 0.0                             # nothing to serve yet
+    assert float(rows[1][v]) == 1.0 and float(rows[1][_abi.NUM_REW + 10]) == 1.0 and not torch.equal(rows[1][:14], torch.full((14,), 7.0))
+    assert torch.equal(rows[2], rows[1]) and torch.equal(rows[3], rows[1])

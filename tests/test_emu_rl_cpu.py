@@ -166,10 +166,35 @@ def test_act_inference_host_logic_matches_exported_policy(variant, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", CTS_VARIANTS)
-def test_tf32_operand_noise_stays_within_the_gpu_bars(variant, monkeypatch):
-    """GO2_EMU_TF32=1 truncates the operands of the emulated tensor-core entry points to tf32 (10 mantissa bits), the arithmetic tcgen05 kind::tf32
-    applies to fp32 data: the fixture comparisons must then stay inside the bars the GPU tests use for GO2_GEMM=tc (act 3e-3, losses 3e-3, update 5e-2
-    for the hardware-verified variants, tests/test_gpu_cts.py; TC_UPDATE_BAR for the new ones, tests/test_gpu_x_moe_heads.py)."""
+def test_3xtf32_arithmetic_meets_the_fp32_bars(variant, monkeypatch):
+    """GO2_EMU_TF32=3 gives the emulated tensor-core entry points the arithmetic of the library's DEFAULT GEMM (csrc/gemm_tc.cu: hi = rna_tf32(a),
+    lo = a - hi read at tf32 precision, lo hi + hi lo + hi hi accumulated in fp32): every CTS-family fixture must then meet the STRICT fp32 bars
+    the GPU tests apply to GO2_GEMM=tc (act 2e-5, losses 2e-4, update 2e-3: tests/test_gpu_cts.py, tests/test_gpu_x_moe_heads.py)."""
+    Z = _variant_or_skip(variant)
+    emu_rl.install(monkeypatch)
+    monkeypatch.setenv("GO2_GEMM", "tc")
+    monkeypatch.setenv("GO2_EMU_TF32", "3")
+    t = lambda k: torch.from_numpy(Z[k])
+    model, alg, T, N = make_cts(variant, Z, "cpu")
+    alg.act(t("in_obs")[0], t("in_priv")[0], t("in_hist")[0])
+    st = alg.storage
+    for k in ("mu", "sigma", "values"):
+        assert torch.allclose(getattr(st, k)[0], t("st_" + k)[0], atol=2e-5), k
+    model, alg, T, N = make_cts(variant, Z, "cpu")
+    for k in STORAGE_KEYS:
+        getattr(alg.storage, k).copy_(t("st_" + k))
+    losses = alg.update(t("tperm"), t("sperm"))
+    for a, b in zip(losses, Z["losses"]):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (losses, Z["losses"])
+    assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
+    rel = _check_update(model, Z, strict=False)
+    assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("variant", ["moe_cts", "mcp_cts"])
+def test_single_pass_tf32_noise_is_what_3xtf32_removes(variant, monkeypatch):
+    """GO2_EMU_TF32=1 (one tf32 pass, go2_gemm_set_passes(1) on the GPU): the operands lose 13 mantissa bits and the same comparisons only hold at the
+    loose bars round 1 shipped with (act 3e-3, losses 3e-3, update 5e-2 .. 0.15) — and measurably miss the strict ones."""
     Z = _variant_or_skip(variant)
     emu_rl.install(monkeypatch)
     monkeypatch.setenv("GO2_GEMM", "tc")
@@ -179,17 +204,16 @@ def test_tf32_operand_noise_stays_within_the_gpu_bars(variant, monkeypatch):
     alg.act(t("in_obs")[0], t("in_priv")[0], t("in_hist")[0])
     st = alg.storage
     for k in ("mu", "sigma", "values"):
-        assert torch.allclose(getattr(st, k)[0], t("st_" + k)[0], atol=3e-3), k
-    assert float((st.mu[0] - t("st_mu")[0]).abs().max()) > 1e-6            # the truncation is really applied
+        assert torch.allclose(getattr(st, k)[0], t("st_" + k)[0], atol=1e-2), k
+    assert float((st.mu[0] - t("st_mu")[0]).abs().max()) > 2e-5            # the truncation is really applied: the strict bar is missed
     model, alg, T, N = make_cts(variant, Z, "cpu")
     for k in STORAGE_KEYS:
         getattr(alg.storage, k).copy_(t("st_" + k))
     losses = alg.update(t("tperm"), t("sperm"))
     for a, b in zip(losses, Z["losses"]):
         assert abs(a - b) < 3e-3 * max(1.0, abs(b)), (losses, Z["losses"])
-    assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
     rel = _check_update(model, Z, strict=False)
-    assert rel < (5e-2 if variant in ("moe_cts", "cts", "moe_ng_cts") else 0.15), rel
+    assert 2e-3 < rel < 0.15, rel
 
 
 class _Holder:
@@ -431,6 +455,19 @@ def test_resume_from_a_reference_checkpoint(variant, monkeypatch, tmp_path):
     for (k, v), r in zip(model.state_dict().items(), ref.state_dict().values()):
         num += float(((v - sd0[k]) - (r - sd0[k])).pow(2).sum()); den += float((r - sd0[k]).pow(2).sum())
     assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
+    # ... and the other way round: what this package saves must load into the REFERENCE's optimisers, whose load_state_dict checks the
+    # number and sizes of the param_groups (optimizer 1 of the CTS family has four: teacher encoder, critic, actor, std; cts.py:73-80)
+    if cts:
+        pairs = [(ralg.optimizer1, alg.optimizer1_state_dict()), (ralg.optimizer2, alg.optimizer2_state_dict())]
+    else:
+        pairs = [(ralg.optimizer, alg.optimizer_state_dict())]
+    for opt, sd in pairs:
+        ref_sd = opt.state_dict()
+        assert [len(g["params"]) for g in sd["param_groups"]] == [len(g["params"]) for g in ref_sd["param_groups"]]
+        assert set(sd["param_groups"][0]) == set(ref_sd["param_groups"][0])
+        opt.load_state_dict(sd)                              # raises on a group-count / size mismatch
+        for i, st in opt.state_dict()["state"].items():
+            assert torch.allclose(st["exp_avg"], sd["state"][i]["exp_avg"]) and float(st["step"]) == float(sd["state"][i]["step"])
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_RSL), reason="reference checkout not present (build container only)")

@@ -40,7 +40,7 @@ def _make(gemm, monkeypatch, variant="moe_cts"):
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
 def test_cts_act_matches_reference(gemm, variant, monkeypatch):
     model, alg, T, N = _make(gemm, monkeypatch, variant)
-    tol = 2e-5 if gemm == "simt" else 3e-3
+    tol = 2e-5                 # tc = 3xTF32 (the default, benchmarked path): the strict-fp32 bar
     a = alg.act(_t("in_obs")[0], _t("in_priv")[0], _t("in_hist")[0])
     st = alg.storage
     assert torch.allclose(st.mu[0].cpu(), torch.from_numpy(Z["st_mu"][0]), atol=tol)
@@ -56,8 +56,9 @@ def test_cts_act_matches_reference(gemm, variant, monkeypatch):
 @pytest.mark.parametrize("variant", ["moe_cts", "cts", "moe_ng_cts"])
 @pytest.mark.parametrize("gemm", ["simt", "tc"])
 def test_cts_update_matches_reference(gemm, variant, monkeypatch):
-    """Both passes of MoECTS.update (moe_cts.py:104-234) / CTS.update (cts.py:167-285).  simt: parameters to 1e-3 rel / 3e-5 abs.  tc: relative error of the whole
-    update < 5 %, losses within 3e-3, same learning-rate path."""
+    """Both passes of MoECTS.update (moe_cts.py:104-234) / CTS.update (cts.py:167-285).  The DEFAULT tensor-core path (tc: 3xTF32 tcgen05 GEMMs) and the
+    strict-fp32 CUDA-core path (simt) are held to the same bars: parameters to 1e-3 rel / 3e-5 abs, relative error of the whole update < 2e-3, losses
+    within 2e-4, same learning-rate path."""
     model, alg, T, N = _make(gemm, monkeypatch, variant)
     st = alg.storage
     for k in ("observations", "privileged_observations", "history", "actions", "rewards", "dones", "values", "returns", "advantages",
@@ -65,7 +66,7 @@ def test_cts_update_matches_reference(gemm, variant, monkeypatch):
         getattr(st, k).copy_(_t("st_" + k))
     losses = alg.update(_t("tperm"), _t("sperm"))
     ref = Z["losses"]
-    tol = 2e-4 if gemm == "simt" else 3e-3
+    tol = 2e-4
     for a, b, name in zip(losses, ref, ("value", "surrogate", "entropy", "latent", "load_balance")):
         assert abs(a - b) < tol * max(1.0, abs(b)), (name, a, b)
     assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
@@ -76,11 +77,10 @@ def test_cts_update_matches_reference(gemm, variant, monkeypatch):
         e = float((v.cpu() - r).abs().max())
         worst = (k, e) if e > worst[1] else worst
         num += float(((v.cpu() - o) - (r - o)).pow(2).sum()); den += float((r - o).pow(2).sum())
-        if gemm == "simt":
-            assert torch.allclose(v.cpu(), r, rtol=1e-3, atol=3e-5), (k, e)
+        assert torch.allclose(v.cpu(), r, rtol=1e-3, atol=3e-5), (k, e)
     rel = (num / den) ** 0.5
     print(f"[{gemm}] {variant} update: worst |param - ref| = {worst}, relative error of the update = {rel:.3e}")
-    assert rel < (2e-3 if gemm == "simt" else 5e-2)
+    assert rel < 2e-3
 
 
 @pytest.mark.parametrize("task", ["go2_moe_cts", "go2_cts", "go2_moe_ng_cts"])

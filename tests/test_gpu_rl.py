@@ -17,7 +17,34 @@ def _t(k, dev="cuda"):
 
 
 def _rel(a, b):
-    return float((a - b).norm() / (b.norm() + 1e-30))
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+# Multiply precision of the tensor-core GEMMs (include/go2_b200.h: go2_gemm_set_passes).  3 = 3xTF32 split, the DEFAULT and the path bench.py
+# times: fp32-class products, bars below are fp32 bars against an fp64 reference.  1 = one tf32 pass (10-bit mantissas; round 1's kernel, A/B only).
+REL_BAR = {3: 4e-6, 1: 2e-3}
+
+
+@pytest.fixture(params=[3, 1], ids=["3xtf32", "tf32"])
+def passes(request):
+    from go2_rl_gym_b200.rl import _ops
+    L = _ops.lib()
+    assert L.go2_gemm_get_passes() == 3                      # the default
+    assert L.go2_gemm_set_passes(request.param) == 0
+    yield request.param
+    assert L.go2_gemm_set_passes(3) == 0
+
+
+def _tc_call(passes, persistable, name, *args):
+    """3xTF32 lives in the persistent TMA-store kernel: operands that kernel cannot take (a row pitch that is not a multiple of 16 bytes) must be
+    REFUSED under the default precision, never served by the single-pass kernel silently.  -> False when the call was (rightly) refused."""
+    from go2_rl_gym_b200.rl import _ops
+    if passes == 3 and not persistable:
+        with pytest.raises(RuntimeError, match="alignment rules"):
+            _ops.call(name, *args)
+        return False
+    _ops.call(name, *args)
+    return True
 
 
 @pytest.mark.parametrize("M,N,K,act", [(1000, 512, 45, 1), (4096, 256, 512, 1), (333, 12, 128, 0), (2048, 1, 128, 0), (24576, 512, 263, 1)])
@@ -36,45 +63,54 @@ def test_linear_forward(M, N, K, act):
 
 @pytest.mark.parametrize("M,N,K,act", [(1000, 512, 48, 1), (4096, 256, 512, 1), (333, 12, 128, 0), (2048, 1, 128, 0), (24576, 512, 264, 1),
                                        (24576, 128, 256, 1), (130, 64, 32, 0), (6148, 2048, 256, 1), (49152, 296, 80, 0)])
-def test_linear_forward_tensor_core(M, N, K, act):
-    """tcgen05 tf32 x tf32 -> fp32: operands are truncated to 10 mantissa bits, so the bar is 2e-3 relative (norm-wise) and
-    5e-3 * sqrt(K)-scaled absolute per element."""
+def test_linear_forward_tensor_core(M, N, K, act, passes):
+    """tcgen05 GEMM vs an fp64 reference.  3xTF32 (default): fp32-class, 4e-6 relative (norm-wise) and 2e-5 per element; one tf32 pass: operands
+    rounded to 10 mantissa bits, 2e-3 / 5e-3."""
     from go2_rl_gym_b200.rl import _ops
     g = torch.Generator(device="cpu").manual_seed(M + N)
     X, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
-    ref = torch.nn.functional.linear(X, W, b)
+    ref = torch.nn.functional.linear(X.double(), W.double(), b.double())
     ref = torch.nn.functional.elu(ref) if act else ref
     Xd, Wd, bd = X.cuda(), W.cuda(), b.cuda()
     Y, Yt = torch.zeros(M, N, device="cuda"), torch.zeros(N, M, device="cuda")
-    _ops.call("go2_linear_forward_tc", Xd.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Y.data_ptr(), N, Yt.data_ptr(), M, M, N, K, act)
+    if not _tc_call(passes, N % 4 == 0 and M % 4 == 0, "go2_linear_forward_tc", Xd.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Y.data_ptr(), N,
+                    Yt.data_ptr(), M, M, N, K, act):
+        return
     torch.cuda.synchronize()
-    assert _rel(Y.cpu(), ref) < 2e-3, _rel(Y.cpu(), ref)
-    assert torch.allclose(Y.cpu(), ref, rtol=5e-3, atol=5e-3)
+    assert _rel(Y.cpu(), ref) < REL_BAR[passes], _rel(Y.cpu(), ref)
+    tol = 2e-5 if passes == 3 else 5e-3
+    assert torch.allclose(Y.cpu().double(), ref, rtol=tol, atol=tol)
     assert torch.equal(Yt.t().contiguous(), Y)
+    # the trainer's own call shape: row-major output only
+    Y2 = torch.zeros(M, N, device="cuda")
+    if N % 4 == 0:
+        _ops.call("go2_linear_forward_tc", Xd.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Y2.data_ptr(), N, 0, 0, M, N, K, act)
+        assert torch.equal(Y2, Y)
 
 
 @pytest.mark.parametrize("M,N,K", [(8192, 256, 512), (24576, 128, 256), (777 * 4, 12, 128), (24576, 512, 45), (24576, 1, 128), (6144, 512, 264), (4100, 2048, 256)])
-def test_linear_backward_tensor_core(M, N, K):
+def test_linear_backward_tensor_core(M, N, K, passes):
     from go2_rl_gym_b200.rl import _ops
     g = torch.Generator(device="cpu").manual_seed(M + K)
     Xact = torch.nn.functional.elu(torch.randn(M, K, generator=g))
     W = torch.randn(N, K, generator=g) / math.sqrt(K)
     dY = torch.randn(M, N, generator=g)
-    dX_ref = (dY @ W) * torch.where(Xact > 0, torch.ones_like(Xact), Xact + 1)
-    dW_ref = dY.t() @ Xact
+    dX_ref = (dY.double() @ W.double()) * torch.where(Xact > 0, torch.ones_like(Xact), Xact + 1).double()
+    dW_ref = dY.double().t() @ Xact.double()
+    bar = REL_BAR[passes]
     dYd, Xd = dY.cuda(), Xact.cuda()
     dYt = dYd.t().contiguous()
     Xt = torch.cat([Xd.t(), torch.ones(1, M, device="cuda")], 0).contiguous()      # [K+1, M]: last row of ones -> bias gradient
     dW, db = torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda")
     work = torch.empty(64 * ((N + 127) // 128 * 128 if N > 1 else 1) * ((K + 4) // 4 * 4), device="cuda")    # N = 1: small workspace -> legacy slice layout
-    _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
-    torch.cuda.synchronize()
-    assert _rel(dW.cpu(), dW_ref) < 2e-3, _rel(dW.cpu(), dW_ref)
-    assert _rel(db.cpu(), dY.sum(0)) < 2e-3
-    dW2 = torch.zeros(N, K, device="cuda")
-    _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW2.data_ptr(), K, 0, M, N, K, work.data_ptr(), work.numel())
-    torch.cuda.synchronize()
-    assert _rel(dW2.cpu(), dW_ref) < 2e-3
+    if _tc_call(passes, N > 1, "go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel()):
+        torch.cuda.synchronize()
+        assert _rel(dW.cpu(), dW_ref) < bar, _rel(dW.cpu(), dW_ref)
+        assert _rel(db.cpu(), dY.double().sum(0)) < bar
+        dW2 = torch.zeros(N, K, device="cuda")
+        _ops.call("go2_linear_wgrad_tc", dYt.data_ptr(), M, Xt.data_ptr(), M, dW2.data_ptr(), K, 0, M, N, K, work.data_ptr(), work.numel())
+        torch.cuda.synchronize()
+        assert _rel(dW2.cpu(), dW_ref) < bar
     if N % 4 == 0 and K % 4 == 0:
         Np = N
         Wt = W.t().contiguous().cuda()                        # [K, N]
@@ -85,14 +121,15 @@ def test_linear_backward_tensor_core(M, N, K):
         torch.cuda.synchronize()
         assert torch.equal(dX2, dX)
         torch.cuda.synchronize()
-        assert _rel(dX.cpu(), dX_ref) < 2e-3, _rel(dX.cpu(), dX_ref)
+        assert _rel(dX.cpu(), dX_ref) < bar, _rel(dX.cpu(), dX_ref)
         assert torch.equal(dXt.t().contiguous(), dX)
 
 
 @pytest.mark.parametrize("M,N,K", [(8192, 256, 512), (24576, 128, 256), (777 * 4, 12, 128), (24576, 512, 263), (6148, 2048, 256), (4099, 32, 256), (24576, 1, 128)])
-def test_wgrad_from_row_major_operands(M, N, K):
+def test_wgrad_from_row_major_operands(M, N, K, passes):
     """MN-major tf32 operands (TMA SWIZZLE_128B_ATOM_32B + UMMA 128B_BASE32B descriptors): dW = dZ^T X and db from the ones column,
     no transposed copies.  Same tolerance as the K-major path."""
+    bar = REL_BAR[passes]
     from go2_rl_gym_b200.rl import _ops
     g = torch.Generator(device="cpu").manual_seed(M + K)
     X = torch.nn.functional.elu(torch.randn(M, K, generator=g))
@@ -105,12 +142,13 @@ def test_wgrad_from_row_major_operands(M, N, K):
     work = torch.empty(64 * ((N + 127) // 128 * 128) * ((K + 4) // 4 * 4), device="cuda")
     _ops.call("go2_linear_wgrad_tc_rm", dYp.data_ptr(), ldy, Xp.data_ptr(), ldx, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
     torch.cuda.synchronize()
-    assert _rel(dW.cpu(), dY.t() @ X) < 2e-3, _rel(dW.cpu(), dY.t() @ X)
-    assert _rel(db.cpu(), dY.sum(0)) < 2e-3
+    ref = dY.double().t() @ X.double()
+    assert _rel(dW.cpu(), ref) < bar, _rel(dW.cpu(), ref)
+    assert _rel(db.cpu(), dY.double().sum(0)) < bar
     dW2 = torch.zeros(N, K, device="cuda")
     _ops.call("go2_linear_wgrad_tc_rm", dYp.data_ptr(), ldy, Xp.data_ptr(), ldx, dW2.data_ptr(), K, 0, M, N, K, work.data_ptr(), work.numel())
     torch.cuda.synchronize()
-    assert _rel(dW2.cpu(), dY.t() @ X) < 2e-3
+    assert _rel(dW2.cpu(), ref) < bar
 
 
 @pytest.mark.parametrize("M,N,K", [(24576, 12, 128), (4096, 1, 128), (1001, 16, 100), (5, 8, 32)])
@@ -198,13 +236,23 @@ def test_gae_matches_reference_fixture():
     assert torch.allclose(st.advantages.cpu(), torch.from_numpy(Z["st_advantages"]), atol=2e-5)
 
 
-@pytest.mark.parametrize("gemm", ["simt", "tc"])
+@pytest.mark.parametrize("gemm", ["simt", "tc", "tf32"])
 def test_ppo_update_matches_reference_fixture(gemm, monkeypatch):
     """Whole PPO.update (5 epochs x 4 mini-batches, adaptive LR, clip + Adam) vs the reference's result on the same data.
-    simt = strict fp32 GEMMs: parameters within 1e-3 rel / 2e-5 abs.  tc = tf32 tensor-core GEMMs (10-bit mantissa operands):
-    Adam divides by sqrt(v), which amplifies gradient rounding on near-zero gradients, so the bar is on the UPDATE as a whole:
-    || (new - old) - (ref_new - old) || <= 5 % of || ref_new - old ||, losses within 2e-3, identical learning-rate path."""
-    monkeypatch.setenv("GO2_GEMM", gemm)
+    tc = the DEFAULT and benchmarked path (3xTF32 tcgen05 GEMMs) and simt = strict fp32 CUDA-core GEMMs are held to the SAME fp32 bars:
+    parameters within 1e-3 rel / 2e-5 abs, relative error of the whole update < 1e-3, losses within 2e-4, Adam moments too.
+    tf32 = one tf32 pass (10-bit mantissa operands; A/B only): Adam divides by sqrt(v), which amplifies gradient rounding on near-zero gradients,
+    so its bar is on the UPDATE as a whole: 5 % of || ref_new - old ||, losses within 2e-3, identical learning-rate path."""
+    from go2_rl_gym_b200.rl import _ops
+    monkeypatch.setenv("GO2_GEMM", "simt" if gemm == "simt" else "tc")
+    assert _ops.lib().go2_gemm_set_passes(1 if gemm == "tf32" else 3) == 0
+    try:
+        _ppo_update_case(gemm)
+    finally:
+        _ops.lib().go2_gemm_set_passes(3)
+
+
+def _ppo_update_case(gemm):
     from golden.rl_cfg import CFG
     from go2_rl_gym_b200.rl.algorithms import PPO
     from go2_rl_gym_b200.rl.modules import ActorCritic
@@ -217,7 +265,8 @@ def test_ppo_update_matches_reference_fixture(gemm, monkeypatch):
     for k in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
         getattr(st, k).copy_(_t("st_" + k))
     mvl, msl = alg.update(indices=_t("perm"))
-    tol_l, atol_p = (1e-4, 2e-5) if gemm == "simt" else (2e-3, None)
+    strict = gemm != "tf32"
+    tol_l, atol_p = (2e-4, 2e-5) if strict else (2e-3, None)
     assert abs(mvl - float(Z["mean_value_loss"])) < tol_l and abs(msl - float(Z["mean_surrogate_loss"])) < tol_l
     assert abs(alg.learning_rate - float(Z["lr"])) < 1e-9
     worst, num, den = 0.0, 0.0, 0.0
@@ -229,8 +278,8 @@ def test_ppo_update_matches_reference_fixture(gemm, monkeypatch):
             assert torch.allclose(v.cpu(), ref, rtol=1e-3, atol=atol_p), (k, float((v.cpu() - ref).abs().max()))
     rel = (num / den) ** 0.5
     print(f"[{gemm}] after 20 optimiser steps: max |param - reference| = {worst:.2e}, relative error of the update = {rel:.3e}")
-    assert rel < (1e-3 if gemm == "simt" else 5e-2)
-    if gemm == "simt":
+    assert rel < (1e-3 if strict else 5e-2)
+    if strict:
         osd = alg.optimizer_state_dict()
         assert torch.allclose(osd["state"][1]["exp_avg"].cpu(), torch.from_numpy(Z["adam_exp_avg_1"]), rtol=1e-3, atol=1e-6)
 
@@ -250,11 +299,11 @@ def test_act_and_process_env_step():
     from oracle import rl_oracle as R
     mu = R.mlp_forward(sd, "actor", obs.cpu()); v = R.mlp_forward(sd, "critic", priv.cpu())
     st = alg.storage
-    assert torch.allclose(st.mu[0].cpu(), mu, atol=3e-3) and torch.allclose(st.values[0].cpu(), v, atol=3e-3)   # tf32 forward
+    assert torch.allclose(st.mu[0].cpu(), mu, atol=2e-5) and torch.allclose(st.values[0].cpu(), v, atol=2e-5)   # 3xTF32 forward: fp32-class
     z = (a.cpu() - mu) / sd["std"]
     assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02      # Philox Box-Muller normals
     lp = R.log_prob(st.mu[0].cpu(), sd["std"], a.cpu())
-    assert torch.allclose(st.actions_log_prob[0].cpu().squeeze(-1), lp, atol=1e-3)
+    assert torch.allclose(st.actions_log_prob[0].cpu().squeeze(-1), lp, atol=1e-4)
     rew = torch.randn(N, device="cuda"); dones = torch.rand(N, device="cuda") < 0.1; touts = dones & (torch.rand(N, device="cuda") < 0.5)
     alg.process_env_step(rew, dones, {"time_outs": touts})
     exp = rew + CFG["gamma"] * st.values[0].squeeze(-1) * touts.float()
@@ -337,3 +386,19 @@ def test_play_loop_and_policy_export(task, tmp_path):
         assert torch.allclose(out, ref, atol=5e-3)          # tf32 GEMMs on the CUDA side
     else:
         assert out.shape == (1, 12) and torch.isfinite(out).all()
+
+
+def test_go2_learns_on_the_gpu():
+    """The B200 path TRAINS (missing item 1; the reference logs the same statistics at on_policy_runner.py:203-207): 200 PPO iterations of
+    --task=go2 at 4096 envs through task_registry (tools/train_gpu_curve.py).  The CPU counterpart — the oracle env under the UNMODIFIED reference PPO,
+    1024 envs (profiles/r01n_cpu_oracle_learning_curve_relaxed.txt) — goes from episode length 13 / return -0.9 to ~1200 / +4 within 150 iterations."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from train_gpu_curve import train
+    rows = train("go2", 4096, 200, report=lambda s: None)
+    first, last = rows[0], rows[-1]
+    print(f"first iteration: {first}\nlast iteration:  {last}")
+    assert first["len"] < 100 and first["std"] > 0.95
+    assert last["len"] > 1000 and last["ret"] > 0.0, last                      # robots stay up for (almost) the whole 1250-step episode, positive return
+    assert last["rew_step"] > first["rew_step"] + 0.03 and last["std"] < 0.7   # reward per step up from ~-0.055, action noise annealed
+    assert all(r["lr"] >= 1e-5 - 1e-12 and r["lr"] <= 1e-2 + 1e-12 for r in rows)
