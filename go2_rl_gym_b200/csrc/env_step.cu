@@ -46,19 +46,33 @@ step_kernel_wide(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
   step_env(L, smem, X);
 }
 
+// Leg-warp rotation of the packed maps: CTAs that land on the same SM take consecutive tickets, so their leg warps (ticket % warps) sit on
+// different warp schedulers (warp w of a CTA runs on scheduler w % 4).  Results do not depend on the choice (same per-thread code).
+__device__ unsigned int g_sm_ticket[1024];
+__device__ __forceinline__ int pick_leg_warp(int nwarps, int* slot) {
+  if (threadIdx.x == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    *slot = (int)(atomicAdd(&g_sm_ticket[smid & 1023u], 1u) % (unsigned int)nwarps);
+  }
+  __syncthreads();
+  return *slot;
+}
+
 // PACKED thread map (env_step_core.cuh): a CTA of 8 warps owns 8 envs; the serial leg recursions of all 8 envs run in warp 0 (one
 // (env, leg) item per lane), the base 6x6 factorisations in warps 1-2; every phase ends in a CTA barrier.  The leg code is ~80 % of the
 // step's instructions and used 4 of 32 lanes with the warp-per-env map: here it is issued once per 8 envs.
-template <int MINB>
+template <int MINB, int ROT>
 __global__ void __launch_bounds__(256, MINB)
 step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
                    const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
+  __shared__ int leg_warp_slot;
   const int e0 = blockIdx.x * 8;
   StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
-  init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8);
+  init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8, ROT ? pick_leg_warp(8, &leg_warp_slot) : 0);
 #if defined(GO2_PHASE_TIMING)
   if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { go2_ph_count = 1; go2_ph_clock[0] = clock64(); }
 #endif
@@ -79,10 +93,11 @@ step_kernel_quad(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
                  const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
+  __shared__ int leg_warp_slot;
   const int e0 = blockIdx.x * E;
   StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
-  init_roles(L, threadIdx.x, 1, e0, min(E, cfg->num_envs - e0), E);
+  init_roles(L, threadIdx.x, 1, e0, min(E, cfg->num_envs - e0), E, pick_leg_warp(E, &leg_warp_slot));
   step_env(L, smem, X);
 }
 
@@ -147,40 +162,29 @@ struct Go2Env {
 };
 
 static int parse_step_mode(const char* m) {
-  return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : !strcmp(m, "Q2") ? 5 : -1;
+  return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : !strcmp(m, "Q2") ? 5
+       : !strcmp(m, "P2f") ? 6 : -1;
 }
 
 namespace go2 {
 template <int W, int MINB, int LOCKSTEP>
 static int launch_wide(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
   const int smem = W * (int)sizeof(WarpSmem);
-  static bool attr = false;
-  if (!attr) {
-    GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_wide<W, MINB, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_wide<W, MINB, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   step_kernel_wide<W, MINB, LOCKSTEP><<<(h->cfg.num_envs + W - 1) / W, 32 * W, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   return 0;
 }
-template <int MINB>
+template <int MINB, int ROT>
 static int launch_packed(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
   const int smem = 8 * (int)sizeof(WarpSmem);
-  static bool attr = false;
-  if (!attr) {
-    GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
-  step_kernel_packed<MINB><<<(h->cfg.num_envs + 7) / 8, 256, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
+  GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<MINB, ROT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device, cheap
+  step_kernel_packed<MINB, ROT><<<(h->cfg.num_envs + 7) / 8, 256, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   return 0;
 }
 template <int E, int MINB>
 static int launch_quad(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
   const int smem = E * (int)sizeof(WarpSmem);
-  static bool attr = false;
-  if (!attr) {
-    GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_quad<E, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_quad<E, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   step_kernel_quad<E, MINB><<<(h->cfg.num_envs + E - 1) / E, 32 * E, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   return 0;
 }
@@ -240,12 +244,13 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
 
 // Thread map of the step kernel (same results bit for bit; tuning / A-B aid).  Default "P2"; the GO2_STEP_MODE environment variable
 // presets it at create time.
-//   "P2": packed map, 8 envs per 256-thread CTA, 2 CTAs/SM (128 registers) · "P3": the same with 3 CTAs/SM (80 registers)
+//   "P2": packed map, 8 envs per 256-thread CTA, 2 CTAs/SM (128 registers), leg warp rotated per SM · "P2f": the same with the leg stream fixed on
+//   warp 0 (round 1's kernel) · "P3": 3 CTAs/SM (80 registers)
 //   "Q4" / "Q2": packed map with 4 / 2 envs per 128- / 64-thread CTA, 4 / 8 CTAs/SM (unmeasured: built after round 1's GPU budget was spent)
 //   "8p": warp per env, 8 warps per CTA, CTA barrier at substep boundaries (the previous default: 203 us at 4096 envs)
 //   "4" : warp per env, 4 warps per CTA, no barrier (the first kernel: 239 us)
 int go2_env_set_step_mode(Go2Env* h, const char* mode) {
-  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P3, Q4, Q2, 8p, 4)");
+  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P2f, P3, Q4, Q2, 8p, 4)");
   h->step_mode = parse_step_mode(mode);
   return 0;
 }
@@ -269,9 +274,9 @@ int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, v
   const int mode = h->step_mode;
   if (mode == 0) go2::step_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   else {
-    int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2>(h, actions, sp, st)
-           : mode == 3 ? go2::launch_packed<3>(h, actions, sp, st) : mode == 4 ? go2::launch_quad<4, 4>(h, actions, sp, st)
-           : go2::launch_quad<2, 8>(h, actions, sp, st);
+    int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2, 1>(h, actions, sp, st)
+           : mode == 3 ? go2::launch_packed<3, 1>(h, actions, sp, st) : mode == 4 ? go2::launch_quad<4, 4>(h, actions, sp, st)
+           : mode == 6 ? go2::launch_packed<2, 0>(h, actions, sp, st) : go2::launch_quad<2, 8>(h, actions, sp, st);
     if (rc) return rc;
   }
   go2::count_launch();

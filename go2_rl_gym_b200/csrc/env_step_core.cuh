@@ -322,7 +322,10 @@ __device__ __forceinline__ void go2_phase_sync(const Lane& L) {
 //   packed == 0: warp w owns env e0 + w; its lanes 0..3 are that env's LEGS items.
 //   packed == 1: 8 warps, up to 8 envs; warp w still owns env e0 + w for the WIDE role, but the LEGS items of all envs sit in
 //                warp 0 (lane = 4 * slot + leg).
-GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nwarps) {
+//                the LEGS items of all envs sit in ONE warp `leg_warp` (lane = 4 * slot + leg).  Which warp is free: the hardware maps warp w of a
+//                CTA to scheduler w % 4, so co-resident CTAs that all used warp 0 would queue their serial leg streams on scheduler 0
+//                (measured in round 1: scheduler 0 saturated, the other three a third busy); the kernels rotate it per SM.
+GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nwarps, int leg_warp = 0) {
   const int warp = tid >> 5, lane = tid & 31;
   L.e0 = e0; L.w = warp; L.lane = lane;
   L.own = warp < n_local;
@@ -332,7 +335,7 @@ GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nw
     L.w0 = warp; L.nw = 1;
     L.nsync = 0;
   } else {
-    L.leg = (warp == 0 && (lane >> 2) < n_local) ? (lane & 3) : -1; L.wl = lane >> 2;
+    L.leg = (warp == leg_warp && (lane >> 2) < n_local) ? (lane & 3) : -1; L.wl = lane >> 2;
     L.w0 = 0; L.nw = n_local;
     L.nsync = 32 * nwarps;
   }

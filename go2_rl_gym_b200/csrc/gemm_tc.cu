@@ -305,6 +305,7 @@ struct TcParamsP {
   int rows_pad;            // rows between consecutive split slices in the C map (multiple of 128)
   int stages;              // operand ring depth
   int mn_major;            // wgrad from row-major operands: A = dZ[batch, out], B = X[batch, in] are MN-major (contraction index = rows)
+  int split_rewrite;       // 3xTF32 split: 0 = lo only (hardware truncation is the hi part), 1 = raw stage rewritten with rn_tf32(a) (A/B check)
   const float* bias;
   int epi, has_c, has_ct, has_aux;
 };
@@ -315,12 +316,31 @@ struct TcParamsP {
 // the MMA warp: they rewrite each landed stage in place with hi and write lo into a 2-slot side ring of the same (swizzled) layout, so the
 // descriptors of the lo operands are the raw ones at another base address.  The GEMMs of this path are HBM / L2 bound (33 flop/B), so the two extra
 // MMAs and the shared-memory pass hide behind the operand stream.
-__device__ __forceinline__ float4 split_tf32(float4& v) {
-  float4 lo;
-  uint32_t h;
-#define GO2_SPLIT1(c) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.c)); { const float hf = __uint_as_float(h); lo.c = (fabsf(hf) < INFINITY) ? v.c - hf : 0.0f; v.c = hf; }
-  GO2_SPLIT1(x) GO2_SPLIT1(y) GO2_SPLIT1(z) GO2_SPLIT1(w)
-#undef GO2_SPLIT1
+// Default split (p.split_rewrite == 0): the raw stage is left alone — tcgen05 kind::tf32 reads fp32 words and drops the 13 low mantissa bits, so
+// the hardware's hi is trunc(a) and the splitters only write lo = rn_tf32(a - trunc(a)); the hi hi MMAs of a stage are issued as soon as its TMA
+// bytes land, the two cross terms when the lo slot is ready.  EIGHT splitter warps, every thread loads its 8-9 vectors of the stage before the
+// first store (round 2's first version serialised LDS -> cvt -> STS per vector in four warps: 3 us per 32 KB stage, the whole kernel's pace).
+// lo word of one fp32 operand.  REWRITE = 0: the tensor core reads the raw word and ignores its 13 low mantissa bits, i.e. it multiplies
+// hi = trunc_tf32(a); lo = rn_tf32(a - hi) (a - hi is exact).  REWRITE = 1: hi = rn_tf32(a) replaces the raw word, lo = a - hi.
+template <int REWRITE>
+__device__ __forceinline__ uint32_t split_word(uint32_t& u) {
+  const float a = __uint_as_float(u);
+  uint32_t h, l;
+  if (REWRITE) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
+    const float hf = __uint_as_float(h);
+    l = __float_as_uint((fabsf(hf) < INFINITY) ? a - hf : 0.0f);
+    u = h;
+  } else {
+    h = u & 0xFFFFE000u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(a - __uint_as_float(h)));
+  }
+  return l;
+}
+template <int REWRITE>
+__device__ __forceinline__ uint4 split_tf32(uint4& v) {
+  uint4 lo;
+  lo.x = split_word<REWRITE>(v.x); lo.y = split_word<REWRITE>(v.y); lo.z = split_word<REWRITE>(v.z); lo.w = split_word<REWRITE>(v.w);
   return lo;
 }
 constexpr int TCP_LO_SLOTS = 2;
@@ -331,7 +351,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 
 constexpr int TCP_THREADS = 320;                 // producer warp, MMA warp, 2 x 4 epilogue warps
-constexpr int TCP_THREADS_X3 = 448;              // + 4 splitter warps (3xTF32)
+constexpr int TCP_SPLIT_WARPS = 8;
+constexpr int TCP_THREADS_X3 = 320 + 32 * TCP_SPLIT_WARPS;   // + splitter warps (3xTF32)
 constexpr int TCP_CHUNK_BYTES = TC_BM * 32 * 4;  // one staged 128 x 32 chunk
 constexpr int TCP_MAX_STAGES = 4;
 constexpr int TCP_SMEM_MAX = 232448;             // 227 KB opt-in limit per CTA
@@ -378,7 +399,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int s = 0; s < S; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 8); }
     for (int b = 0; b < 4; ++b) mbar_init(auxb + b, 1);
-    for (int b = 0; b < TCP_LO_SLOTS; ++b) { mbar_init(lofull + b, 4); mbar_init(loempty + b, 1); }
+    for (int b = 0; b < TCP_LO_SLOTS; ++b) { mbar_init(lofull + b, TCP_SPLIT_WARPS); mbar_init(loempty + b, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the whole TMEM: two accumulators of up to 256 columns
@@ -430,31 +451,29 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar + s, ph);
-          if (X3) mbar_wait(lofull + l, lph);                     // the splitter warps have rewritten this stage as hi and filled the lo slot
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sl = smem_u32(lo_ring + l * STAGE_BYTES);
-          if (!p.mn_major) {
-            const uint64_t da = make_desc_kmajor_sw128(sa), db = make_desc_kmajor_sw128(sa + A_BYTES);
-            const uint64_t la = make_desc_kmajor_sw128(sl), lb = make_desc_kmajor_sw128(sl + A_BYTES);
+          const bool kmaj = !p.mn_major;
+          // K-major: +32 bytes of K inside the swizzle atom per instruction; MN-major: 8 contraction rows = 1024 B further into every box
+          const uint64_t da = kmaj ? make_desc_kmajor_sw128(sa) : make_desc_mnmajor_sw128_32b(sa);
+          const uint64_t db = kmaj ? make_desc_kmajor_sw128(sa + A_BYTES) : make_desc_mnmajor_sw128_32b(sa + A_BYTES);
+          const uint64_t kstep = kmaj ? 2 : 64;
+          const uint32_t idesc = kmaj ? IDESC : (IDESC | (1u << 15) | (1u << 16));
+          const bool hi_first = !X3 || !p.split_rewrite;      // the raw stage is (or stays) the hi operand: no need to wait for the splitters
+          if (hi_first) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          if (X3) {
+            mbar_wait(lofull + l, lph);                           // the splitter warps have filled the lo slot (and, rewrite mode, rewritten the stage as hi)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t la = kmaj ? make_desc_kmajor_sw128(sl) : make_desc_mnmajor_sw128_32b(sl);
+            const uint64_t lb = kmaj ? make_desc_kmajor_sw128(sl + A_BYTES) : make_desc_mnmajor_sw128_32b(sl + A_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-              if (X3) {   // small terms first
-                umma_tf32(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
-                umma_tf32(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
-                umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
-              } else umma_tf32(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
-            }
-          } else {   // 8 contraction rows per instruction = 1024 B further into every box
-            const uint64_t da = make_desc_mnmajor_sw128_32b(sa), db = make_desc_mnmajor_sw128_32b(sa + A_BYTES);
-            const uint64_t la = make_desc_mnmajor_sw128_32b(sl), lb = make_desc_mnmajor_sw128_32b(sl + A_BYTES);
-            constexpr uint32_t IDT = IDESC | (1u << 15) | (1u << 16);
-#pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-              if (X3) {
-                umma_tf32(tacc, la + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDT, (kb | k) ? 1u : 0u);
-                umma_tf32(tacc, da + (uint64_t)(64 * k), lb + (uint64_t)(64 * k), IDT, 1u);
-                umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDT, 1u);
-              } else umma_tf32(tacc, da + (uint64_t)(64 * k), db + (uint64_t)(64 * k), IDT, (kb | k) ? 1u : 0u);
+              umma_tf32(tacc, la + kstep * k, db + kstep * k, idesc, (hi_first || (kb | k)) ? 1u : 0u);
+              umma_tf32(tacc, da + kstep * k, lb + kstep * k, idesc, 1u);
+              if (!hi_first) umma_tf32(tacc, da + kstep * k, db + kstep * k, idesc, 1u);
             }
           }
           umma_commit(empty_bar + s);
@@ -467,6 +486,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (X3 && warp >= 10) {
     // ===== splitter warps (3xTF32): stage s landed -> hi in place, lo into slot l; then hand both to the MMA warp
     const int t = threadIdx.x - 320;
+    constexpr int NV = STAGE_BYTES / 16, NT = 32 * TCP_SPLIT_WARPS, PER = (NV + NT - 1) / NT;
     int s = 0, l = 0;
     uint32_t ph = 0, lph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -474,14 +494,18 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar + s, ph);                              // TMA bytes have landed (async proxy -> visible after the wait)
+        uint4* raw = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * STAGE_BYTES);
+        uint4 v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) v[j] = raw[t + NT * j];
         mbar_wait(loempty + l, lph ^ 1);                          // the MMAs that read this lo slot have retired
-        float4* raw = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(lo_ring + l * STAGE_BYTES);
-#pragma unroll 4
-        for (int i = t; i < STAGE_BYTES / 16; i += 128) {
-          float4 v = raw[i];
-          const float4 w = split_tf32(v);
-          raw[i] = v; lo[i] = w;
+        if (p.split_rewrite) {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) { const uint4 w = split_tf32<1>(v[j]); raw[t + NT * j] = v[j]; lo[t + NT * j] = w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) lo[t + NT * j] = split_tf32<0>(v[j]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
@@ -773,6 +797,13 @@ static int tc_passes() {
   return g_tc_passes;
 }
 
+// how the 3xTF32 kernel gets its hi operand: 0 = hardware truncation of the raw word (default), 1 = raw stage rewritten with rn_tf32 (GO2_GEMM_SPLIT=rewrite)
+static int g_tc_split = -1;
+static int tc_split_rewrite() {
+  if (g_tc_split < 0) { const char* e = getenv("GO2_GEMM_SPLIT"); g_tc_split = (e && !strcmp(e, "rewrite")) ? 1 : 0; }
+  return g_tc_split;
+}
+
 // split-K slices of C sit rows_pad = roundup(M, 128) rows apart so that one 2-D map covers all of them
 static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
   const bool x3 = tc_passes() == 3;
@@ -789,7 +820,7 @@ static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, c
   pp.bias = p.bias; pp.epi = p.epi; pp.has_c = p.C != nullptr; pp.has_ct = p.Ct != nullptr; pp.has_aux = p.epi == TC_EPI_MUL_ELU_GRAD;
   if (splits > 1 && p.split_stride != (long)pp.rows_pad * p.ldc) return set_error(5, "gemm_tc_persist: split stride must be roundup(M,128) * ldc");
   CUtensorMap ta, tb, tc, tct, taux;
-  pp.mn_major = p.mn_major;
+  pp.mn_major = p.mn_major; pp.split_rewrite = tc_split_rewrite();
   int rc = p.mn_major ? make_map(&ta, A, p.K, p.M, lda, 32, 32, true) : make_map(&ta, A, p.M, p.K, lda, TC_BM);
   if (rc) return rc;
   rc = p.mn_major ? make_map(&tb, B, p.K, p.N, ldb, 32, 32, true) : make_map(&tb, B, p.N, p.K, ldb, BN);
@@ -841,6 +872,11 @@ int go2_gemm_set_passes(int passes) {
   return 0;
 }
 int go2_gemm_get_passes(void) { return tc_passes(); }
+int go2_gemm_set_split(int rewrite) {
+  if (rewrite != 0 && rewrite != 1) return set_error(1, "go2_gemm_set_split: 0 (lo only, hardware truncation is hi) or 1 (stage rewritten with rn_tf32)");
+  g_tc_split = rewrite;
+  return 0;
+}
 
 // Y[M,N] (and optionally Yt[N,M]) = act(X[M,K] W[N,K]^T + b)
 int go2_linear_forward_tc(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, float* Yt, int ldyt, int M, int N,

@@ -255,6 +255,10 @@ int go2_transpose(const float* in, int ldin, float* out, int ldout, int rows, in
    mantissa products; round 1's kernel, kept for A/B; also selected by the environment variable GO2_GEMM=tf32). */
 int go2_gemm_set_passes(int passes);
 int go2_gemm_get_passes(void);
+/* Where the 3xTF32 kernel takes its hi operand from.  0 (default): the raw fp32 word — tcgen05 kind::tf32 ignores the 13 low mantissa bits, so the
+   hardware's hi is trunc_tf32(a) and the splitter warps only write lo = rn_tf32(a - trunc_tf32(a)).  1: the staged operand is rewritten with
+   rn_tf32(a) and lo = a - hi (A/B check of the assumption; also GO2_GEMM_SPLIT=rewrite). */
+int go2_gemm_set_split(int rewrite);
 /* db[N] = column sums of dY[M,N] */
 int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */

@@ -58,14 +58,19 @@ def _rna_tf32(a):
 def _mm_tc(a, b):
     """a @ b.T as the tensor-core entry points form it (csrc/gemm_tc.cu), selected by GO2_EMU_TF32 (checks on the CPU that the bars of the GPU tests
     are realistic for new wirings): '0' (default) plain fp32; '1' one tf32 pass: operands lose their low 13 mantissa bits, like tcgen05 kind::tf32
-    reading fp32 data; '3' the library's default 3xTF32 split: hi = rna_tf32(a), lo = a - hi (read truncated), lo_a hi_b + hi_a lo_b + hi_a hi_b."""
+    reading fp32 data; '3' the library's default 3xTF32 split: hi = trunc_tf32(a) (what the tensor core reads from the raw word), lo = rna_tf32(a - hi),
+    lo_a hi_b + hi_a lo_b + hi_a hi_b; '3rw' the A/B variant go2_gemm_set_split(1): hi = rna_tf32(a), lo = a - hi (read truncated)."""
     import os
     mode = os.environ.get("GO2_EMU_TF32", "0")
     if mode == "1":
         return _trunc_tf32(a) @ _trunc_tf32(b).T
-    if mode == "3":
-        ah, bh = _rna_tf32(a), _rna_tf32(b)
-        al, bl = _trunc_tf32(np.asarray(a, F) - ah), _trunc_tf32(np.asarray(b, F) - bh)
+    if mode in ("3", "3rw"):
+        if mode == "3":
+            ah, bh = _trunc_tf32(a), _trunc_tf32(b)
+            al, bl = _rna_tf32(np.asarray(a, F) - ah), _rna_tf32(np.asarray(b, F) - bh)
+        else:
+            ah, bh = _rna_tf32(a), _rna_tf32(b)
+            al, bl = _trunc_tf32(np.asarray(a, F) - ah), _trunc_tf32(np.asarray(b, F) - bh)
         return ((al @ bh.T).astype(F) + (ah @ bl.T).astype(F)).astype(F) + (ah @ bh.T).astype(F)
     return a @ b.T
 

@@ -165,15 +165,17 @@ def test_act_inference_host_logic_matches_exported_policy(variant, monkeypatch):
         assert torch.allclose(a[0], b, atol=2e-5), (t, float((a[0] - b).abs().max()))
 
 
+@pytest.mark.parametrize("split", ["3", "3rw"])
 @pytest.mark.parametrize("variant", CTS_VARIANTS)
-def test_3xtf32_arithmetic_meets_the_fp32_bars(variant, monkeypatch):
-    """GO2_EMU_TF32=3 gives the emulated tensor-core entry points the arithmetic of the library's DEFAULT GEMM (csrc/gemm_tc.cu: hi = rna_tf32(a),
-    lo = a - hi read at tf32 precision, lo hi + hi lo + hi hi accumulated in fp32): every CTS-family fixture must then meet the STRICT fp32 bars
+def test_3xtf32_arithmetic_meets_the_fp32_bars(variant, split, monkeypatch):
+    """GO2_EMU_TF32=3 gives the emulated tensor-core entry points the arithmetic of the library's DEFAULT GEMM (csrc/gemm_tc.cu: hi = trunc_tf32(a) as
+    the tensor core reads the raw word, lo = rna_tf32(a - hi), lo hi + hi lo + hi hi accumulated in fp32; "3rw" = the go2_gemm_set_split(1) variant,
+    hi = rna_tf32(a) written back, lo = a - hi read truncated): every CTS-family fixture must then meet the STRICT fp32 bars
     the GPU tests apply to GO2_GEMM=tc (act 2e-5, losses 2e-4, update 2e-3: tests/test_gpu_cts.py, tests/test_gpu_x_moe_heads.py)."""
     Z = _variant_or_skip(variant)
     emu_rl.install(monkeypatch)
     monkeypatch.setenv("GO2_GEMM", "tc")
-    monkeypatch.setenv("GO2_EMU_TF32", "3")
+    monkeypatch.setenv("GO2_EMU_TF32", split)
     t = lambda k: torch.from_numpy(Z[k])
     model, alg, T, N = make_cts(variant, Z, "cpu")
     alg.act(t("in_obs")[0], t("in_priv")[0], t("in_hist")[0])

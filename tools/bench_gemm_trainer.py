@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""The trainer's own GEMM calls (go2 PPO update, M = 24576 rows per mini-batch; rollout inference, M = 4096), per multiply mode:
+   tf32      one tf32 pass (round 1's kernel)
+   3x        3xTF32, lo-only split (hardware truncation of the raw word is the hi part) — the default
+   3x-rw     3xTF32, stage rewritten with rn_tf32 (A/B check)
+Columns: time per call (CUDA events, L2 flushed by the working set of the shape list) and relative error (norm-wise) against fp64."""
+import math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from go2_rl_gym_b200.rl import _ops
+
+L = _ops.lib()
+MODES = (("tf32", 1, 0), ("3x", 3, 0), ("3x-rw", 3, 1))
+
+
+def set_mode(passes, rewrite):
+    assert L.go2_gemm_set_passes(passes) == 0 and L.go2_gemm_set_split(rewrite) == 0
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def rel(a, b):
+    return float((a.double() - b).norm() / b.norm())
+
+
+def main():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rows = []
+    for M in (24576, 4096):
+        for (N, K) in ((512, 48), (512, 264), (256, 512), (128, 256)):
+            X = torch.randn(M, K, device="cuda", generator=g); W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+            b = torch.randn(N, device="cuda", generator=g); Y = torch.empty(M, N + 4, device="cuda")
+            ref = torch.nn.functional.elu(X.double() @ W.double().t() + b.double())
+            out = [f"fwd   M={M:6d} N={N:4d} K={K:4d}"]
+            for name, ps, rw in MODES:
+                set_mode(ps, rw)
+                fn = lambda: _ops.call("go2_linear_forward_tc", X.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N + 4, 0, 0, M, N, K, 1)
+                us = timeit(fn)
+                out.append(f"{name} {us:7.1f} us err {rel(Y[:, :N], ref):.2e}")
+            rows.append("   ".join(out)); print(rows[-1], flush=True)
+    M = 24576
+    for (N, K) in ((256, 512), (128, 256), (512, 256), (256, 128)):      # dZ [M, N] -> dX [M, K]
+        dZ = torch.randn(M, N, device="cuda", generator=g); Wt = torch.randn(K, N, device="cuda", generator=g) / math.sqrt(N)
+        act = torch.nn.functional.elu(torch.randn(M, K + 4, device="cuda", generator=g)); dX = torch.empty(M, K, device="cuda")
+        a = act[:, :K].double()
+        ref = (dZ.double() @ Wt.double().t()) * torch.where(a > 0, torch.ones_like(a), a + 1)
+        out = [f"dgrad M={M:6d} N={N:4d} K={K:4d}"]
+        for name, ps, rw in MODES:
+            set_mode(ps, rw)
+            fn = lambda: _ops.call("go2_linear_dgrad_tc", dZ.data_ptr(), N, Wt.data_ptr(), N, act.data_ptr(), K + 4, 0, 0, dX.data_ptr(), K, 0, 0, M, N, K)
+            us = timeit(fn)
+            out.append(f"{name} {us:7.1f} us err {rel(dX, ref):.2e}")
+        rows.append("   ".join(out)); print(rows[-1], flush=True)
+    for (N, K) in ((512, 48), (512, 264), (256, 512), (128, 256)):       # dW [N, K] = dZ^T X
+        dZ = torch.randn(M, N, device="cuda", generator=g); X = torch.ones(M, K + 4, device="cuda"); X[:, :K] = torch.nn.functional.elu(torch.randn(M, K, device="cuda", generator=g))
+        dW, db = torch.empty(N, K, device="cuda"), torch.empty(N, device="cuda")
+        work = torch.empty(64 * ((N + 127) // 128 * 128) * ((K + 4) // 4 * 4), device="cuda")
+        ref = dZ.double().t() @ X[:, :K].double()
+        r32 = rel(dZ.t() @ X[:, :K], ref)
+        out = [f"wgrad M={M:6d} N={N:4d} K={K:4d}"]
+        for name, ps, rw in MODES:
+            set_mode(ps, rw)
+            fn = lambda: _ops.call("go2_linear_wgrad_tc_rm", dZ.data_ptr(), N, X.data_ptr(), K + 4, dW.data_ptr(), K, db.data_ptr(), M, N, K, work.data_ptr(), work.numel())
+            us = timeit(fn)
+            out.append(f"{name} {us:7.1f} us err {rel(dW, ref):.2e}")
+        out.append(f"(torch fp32 matmul err {r32:.2e})")
+        rows.append("   ".join(out)); print(rows[-1], flush=True)
+    set_mode(3, 0)
+
+
+if __name__ == "__main__":
+    main()
