@@ -305,6 +305,7 @@ struct TcParamsP {
   int rows_pad;            // rows between consecutive split slices in the C map (multiple of 128)
   int stages;              // operand ring depth
   int mn_major;            // wgrad from row-major operands: A = dZ[batch, out], B = X[batch, in] are MN-major (contraction index = rows)
+  long long* dbg;          // optional [gridDim.x][16] cycle counters (go2_gemm_set_debug): where each role of a CTA waited
   int split_rewrite;       // 3xTF32 split: 0 = lo only (hardware truncation is the hi part), 1 = raw stage rewritten with rn_tf32(a) (A/B check)
   const float* bias;
   int epi, has_c, has_ct, has_aux;
@@ -344,6 +345,11 @@ __device__ __forceinline__ uint4 split_tf32(uint4& v) {
   return lo;
 }
 constexpr int TCP_LO_SLOTS = 2;
+// mbarrier wait that adds the cycles it blocked to *acc when profiling (acc == nullptr otherwise)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long* acc) {
+  if (acc) { const long long t0 = clock64(); mbar_wait(bar, parity); *acc += clock64() - t0; }
+  else mbar_wait(bar, parity);
+}
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
@@ -416,11 +422,13 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
+      long long w_empty = 0, *pw = p.dbg ? &w_empty : nullptr;
+      const long long t_start = p.dbg ? clock64() : 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
         const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_wait_t(empty_bar + s, ph ^ 1, pw);
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
           if (!p.mn_major) {
@@ -435,6 +443,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[0] = clock64() - t_start; d[1] = w_empty; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread)
@@ -442,15 +451,19 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int s = 0, ui = 0, l = 0;
       uint32_t ph = 0, lph = 0;
+      long long w_tempty = 0, w_full = 0, w_lofull = 0, nst = 0;
+      long long *pw_tempty = p.dbg ? &w_tempty : nullptr, *pw_full = p.dbg ? &w_full : nullptr, *pw_lofull = p.dbg ? &w_lofull : nullptr;
+      const long long t_start = p.dbg ? clock64() : 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
         const int z = u / (p.n_tiles * p.m_tiles);
         const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
         const int buf = ui & 1;
-        mbar_wait(tempty + buf, ((ui >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
+        nst += nkb;
+        mbar_wait_t(tempty + buf, ((ui >> 1) & 1) ^ 1, pw_tempty);             // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_bar + s, ph);
+          mbar_wait_t(full_bar + s, ph, pw_full);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sl = smem_u32(lo_ring + l * STAGE_BYTES);
           const bool kmaj = !p.mn_major;
@@ -465,7 +478,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32(tacc, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
           }
           if (X3) {
-            mbar_wait(lofull + l, lph);                           // the splitter warps have filled the lo slot (and, rewrite mode, rewritten the stage as hi)
+            mbar_wait_t(lofull + l, lph, pw_lofull);              // the splitter warps have filled the lo slot (and, rewrite mode, rewritten the stage as hi)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t la = kmaj ? make_desc_kmajor_sw128(sl) : make_desc_mnmajor_sw128_32b(sl);
             const uint64_t lb = kmaj ? make_desc_kmajor_sw128(sl + A_BYTES) : make_desc_mnmajor_sw128_32b(sl + A_BYTES);
@@ -482,6 +495,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         umma_commit(tfull + buf);
       }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[2] = clock64() - t_start; d[3] = w_tempty; d[4] = w_full; d[5] = w_lofull; d[6] = nst; }
     }
   } else if (X3 && warp >= 10) {
     // ===== splitter warps (3xTF32): stage s landed -> hi in place, lo into slot l; then hand both to the MMA warp
@@ -489,17 +503,20 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int NV = STAGE_BYTES / 16, NT = 32 * TCP_SPLIT_WARPS, PER = (NV + NT - 1) / NT;
     int s = 0, l = 0;
     uint32_t ph = 0, lph = 0;
+    long long w_full = 0, w_loempty = 0, t_work = 0;
+    long long *pw_full = p.dbg ? &w_full : nullptr, *pw_loempty = p.dbg ? &w_loempty : nullptr;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int z = u / (p.n_tiles * p.m_tiles);
       const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(full_bar + s, ph);                              // TMA bytes have landed (async proxy -> visible after the wait)
+        mbar_wait_t(full_bar + s, ph, pw_full);                   // TMA bytes have landed (async proxy -> visible after the wait)
+        const long long t_w0 = p.dbg ? clock64() : 0;
         uint4* raw = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * STAGE_BYTES);
         uint4 v[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) v[j] = raw[t + NT * j];
-        mbar_wait(loempty + l, lph ^ 1);                          // the MMAs that read this lo slot have retired
+        mbar_wait_t(loempty + l, lph ^ 1, pw_loempty);            // the MMAs that read this lo slot have retired
         if (p.split_rewrite) {
 #pragma unroll
           for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) { const uint4 w = split_tf32<1>(v[j]); raw[t + NT * j] = v[j]; lo[t + NT * j] = w; }
@@ -510,10 +527,12 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(lofull + l)) : "memory");
+        if (p.dbg) t_work += clock64() - t_w0;
         if (++l == TCP_LO_SLOTS) { l = 0; lph ^= 1; }
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
+    if (p.dbg && t == 0) { long long* d = p.dbg + blockIdx.x * 16; d[7] = w_full; d[8] = w_loempty; d[9] = t_work; }   // t_work includes w_loempty
   } else {
     // ===== epilogue: group grp takes chunks grp, grp+2, ... of every unit; warp -> TMEM lane quadrant q; thread = one tile row
     const int grp = (warp - 2) >> 2, q = warp & 3;
@@ -535,6 +554,9 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_expect_tx(auxb_g + slot, TCP_CHUNK_BYTES);
       tma_load_2d(&tmAux, auxb_g + slot, cst_g + slot * TCP_CHUNK_BYTES, nt * BN + c * 32, mt * TC_BM);
     };
+    long long w_tfull = 0, *pw_tfull = (p.dbg && leader) ? &w_tfull : nullptr;
+    long long w_aux = 0, *pw_aux = (p.dbg && leader) ? &w_aux : nullptr;
+    const long long t_start = p.dbg ? clock64() : 0;
     uint32_t g = 0;        // this group's running chunk counter: staging slot = g & 1, aux barrier phase = (g >> 1) & 1
     int ui = 0;
     if (p.has_aux && leader) {
@@ -546,7 +568,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m0 = mt * TC_BM, n0 = nt * BN;
       const int nch = n_chunks(u);
       const int buf = ui & 1;
-      mbar_wait(tfull + buf, (ui >> 1) & 1);
+      mbar_wait_t(tfull + buf, (ui >> 1) & 1, pw_tfull);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int c = grp; c < nch; c += 2, ++g) {
         const int nb = n0 + c * 32;
@@ -577,7 +599,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           v[j] = x;
         }
         if (p.has_aux) {
-          mbar_wait(auxb_g + slot, (g >> 1) & 1);
+          mbar_wait_t(auxb_g + slot, (g >> 1) & 1, pw_aux);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 y = *reinterpret_cast<const float4*>(cs + row * 32 + ((j4 ^ sw) << 2));
@@ -615,6 +637,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + buf)) : "memory");
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.dbg && leader) { long long* d = p.dbg + blockIdx.x * 16 + 10 + 2 * grp; d[0] = clock64() - t_start; d[1] = w_tfull; p.dbg[blockIdx.x * 16 + 14 + grp] = w_aux; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -804,6 +827,8 @@ static int tc_split_rewrite() {
   return g_tc_split;
 }
 
+static long long* g_tc_dbg = nullptr;   // go2_gemm_set_debug
+
 // split-K slices of C sit rows_pad = roundup(M, 128) rows apart so that one 2-D map covers all of them
 static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
   const bool x3 = tc_passes() == 3;
@@ -820,7 +845,7 @@ static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, c
   pp.bias = p.bias; pp.epi = p.epi; pp.has_c = p.C != nullptr; pp.has_ct = p.Ct != nullptr; pp.has_aux = p.epi == TC_EPI_MUL_ELU_GRAD;
   if (splits > 1 && p.split_stride != (long)pp.rows_pad * p.ldc) return set_error(5, "gemm_tc_persist: split stride must be roundup(M,128) * ldc");
   CUtensorMap ta, tb, tc, tct, taux;
-  pp.mn_major = p.mn_major; pp.split_rewrite = tc_split_rewrite();
+  pp.mn_major = p.mn_major; pp.split_rewrite = tc_split_rewrite(); pp.dbg = g_tc_dbg;
   int rc = p.mn_major ? make_map(&ta, A, p.K, p.M, lda, 32, 32, true) : make_map(&ta, A, p.M, p.K, lda, TC_BM);
   if (rc) return rc;
   rc = p.mn_major ? make_map(&tb, B, p.K, p.N, ldb, 32, 32, true) : make_map(&tb, B, p.N, p.K, ldb, BN);
@@ -872,6 +897,7 @@ int go2_gemm_set_passes(int passes) {
   return 0;
 }
 int go2_gemm_get_passes(void) { return tc_passes(); }
+int go2_gemm_set_debug(long long* counters) { g_tc_dbg = counters; return 0; }
 int go2_gemm_set_split(int rewrite) {
   if (rewrite != 0 && rewrite != 1) return set_error(1, "go2_gemm_set_split: 0 (lo only, hardware truncation is hi) or 1 (stage rewritten with rn_tf32)");
   g_tc_split = rewrite;

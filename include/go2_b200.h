@@ -259,6 +259,11 @@ int go2_gemm_get_passes(void);
    hardware's hi is trunc_tf32(a) and the splitter warps only write lo = rn_tf32(a - trunc_tf32(a)).  1: the staged operand is rewritten with
    rn_tf32(a) and lo = a - hi (A/B check of the assumption; also GO2_GEMM_SPLIT=rewrite). */
 int go2_gemm_set_split(int rewrite);
+/* Profiling aid: counters != NULL makes every persistent tensor-core GEMM launch write, per CTA b, 16 int64 cycle counters at counters[16 b ...]
+   (device memory, >= 16 x SM count): 0 producer total, 1 producer waiting for a free stage; 2 MMA thread total, 3 .. waiting for a drained accumulator,
+   4 .. for TMA bytes, 5 .. for the lo slot, 6 stages processed; 7 splitter waiting for TMA bytes, 8 .. for a free lo slot, 9 splitter busy (incl. 8);
+   10/11 and 12/13 epilogue group 0 / 1 total and waiting for an accumulator, 14 / 15 .. for the ELU' operand (dgrad).  NULL (default) disables it. */
+int go2_gemm_set_debug(long long* counters);
 /* db[N] = column sums of dY[M,N] */
 int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */

@@ -9,7 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from go2_rl_gym_b200.rl import _ops
 
+import ctypes
 L = _ops.lib()
+L.go2_gemm_set_debug.argtypes = [ctypes.c_void_p]
 MODES = (("tf32", 1, 0), ("3x", 3, 0), ("3x-rw", 3, 1))
 
 
@@ -27,6 +29,29 @@ def timeit(fn, reps=20):
         fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
+
+
+NAMES = ["prod_total", "prod_w_empty", "mma_total", "mma_w_tempty", "mma_w_full", "mma_w_lofull", "stages", "split_w_full", "split_w_loempty", "split_busy",
+         "epi0_total", "epi0_w_tfull", "epi1_total", "epi1_w_tfull", "epi0_w_aux", "epi1_w_aux"]
+DBG = None
+
+
+def profile(fn, label):
+    """one launch with the per-role cycle counters on (go2_gemm_set_debug): mean over the CTAs that ran, cycles per stage"""
+    global DBG
+    if "--dbg" not in sys.argv:
+        return
+    if DBG is None:
+        DBG = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+    fn(); torch.cuda.synchronize()
+    DBG.zero_()
+    assert L.go2_gemm_set_debug(DBG.data_ptr()) == 0
+    fn(); torch.cuda.synchronize()
+    assert L.go2_gemm_set_debug(None) == 0
+    d = DBG.view(148, 16).double().cpu()
+    d = d[d[:, 6] > 0]
+    m = d.mean(0); st = float(m[6])
+    print(f"    [{label}] {len(d)} CTAs, {st:.1f} stages/CTA; cycles per stage: " + ", ".join(f"{n} {float(m[i]) / st:.0f}" for i, n in enumerate(NAMES) if i != 6 and m[i] > 0), flush=True)
 
 
 def rel(a, b):
@@ -48,6 +73,8 @@ def main():
                 us = timeit(fn)
                 out.append(f"{name} {us:7.1f} us err {rel(Y[:, :N], ref):.2e}")
             rows.append("   ".join(out)); print(rows[-1], flush=True)
+            for name, ps, rw in MODES[:2]:
+                set_mode(ps, rw); profile(fn, name)
     M = 24576
     for (N, K) in ((256, 512), (128, 256), (512, 256), (256, 128)):      # dZ [M, N] -> dX [M, K]
         dZ = torch.randn(M, N, device="cuda", generator=g); Wt = torch.randn(K, N, device="cuda", generator=g) / math.sqrt(N)
@@ -61,6 +88,8 @@ def main():
             us = timeit(fn)
             out.append(f"{name} {us:7.1f} us err {rel(dX, ref):.2e}")
         rows.append("   ".join(out)); print(rows[-1], flush=True)
+        for name, ps, rw in MODES[:2]:
+            set_mode(ps, rw); profile(fn, name)
     for (N, K) in ((512, 48), (512, 264), (256, 512), (128, 256)):       # dW [N, K] = dZ^T X
         dZ = torch.randn(M, N, device="cuda", generator=g); X = torch.ones(M, K + 4, device="cuda"); X[:, :K] = torch.nn.functional.elu(torch.randn(M, K, device="cuda", generator=g))
         dW, db = torch.empty(N, K, device="cuda"), torch.empty(N, device="cuda")
@@ -75,6 +104,8 @@ def main():
             out.append(f"{name} {us:7.1f} us err {rel(dW, ref):.2e}")
         out.append(f"(torch fp32 matmul err {r32:.2e})")
         rows.append("   ".join(out)); print(rows[-1], flush=True)
+        for name, ps, rw in MODES[:2]:
+            set_mode(ps, rw); profile(fn, name)
     set_mode(3, 0)
 
 
