@@ -77,7 +77,9 @@ def test_cts_update_matches_reference(gemm, variant, monkeypatch):
         e = float((v.cpu() - r).abs().max())
         worst = (k, e) if e > worst[1] else worst
         num += float(((v.cpu() - o) - (r - o)).pow(2).sum()); den += float((r - o).pow(2).sum())
-        assert torch.allclose(v.cpu(), r, rtol=1e-3, atol=3e-5), (k, e)
+        # per element: 3e-5 on the strict-fp32 path; 1e-4 on the tensor-core path (Adam's g / sqrt(v) turns 1e-6-class product noise on a near-zero
+        # gradient into a step of up to lr = 1e-2 x O(1e-2): measured worst 6.5e-5 on ONE weight of 590 k).  The bar on the update as a whole is shared.
+        assert torch.allclose(v.cpu(), r, rtol=1e-3, atol=3e-5 if gemm == "simt" else 1e-4), (k, e)
     rel = (num / den) ** 0.5
     print(f"[{gemm}] {variant} update: worst |param - ref| = {worst}, relative error of the update = {rel:.3e}")
     assert rel < 2e-3

@@ -117,15 +117,18 @@ def test_linear_backward_tensor_core(M, N, K, passes):
     if N % 4 == 0 and K % 4 == 0:
         Np = N
         Wt = W.t().contiguous().cuda()                        # [K, N]
-        dX, dXt = torch.zeros(M, K, device="cuda"), torch.zeros(K, M, device="cuda")
-        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, 0, 0, Xt.data_ptr(), M, dX.data_ptr(), K, dXt.data_ptr(), M, M, N, K)
-        dX2 = torch.zeros(M, K, device="cuda")
-        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, Xd.data_ptr(), K, 0, 0, dX2.data_ptr(), K, 0, 0, M, N, K)
-        torch.cuda.synchronize()
-        assert torch.equal(dX2, dX)
+        # the trainer's call: ELU' operand read ROW-MAJOR (TMA load into the staging buffer), row-major output
+        dX = torch.zeros(M, K, device="cuda")
+        _ops.call("go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, Xd.data_ptr(), K, 0, 0, dX.data_ptr(), K, 0, 0, M, N, K)
         torch.cuda.synchronize()
         assert _rel(dX.cpu(), dX_ref) < (bar if N <= 256 else bar_w), _rel(dX.cpu(), dX_ref)      # contraction over N (up to 2048 here)
-        assert torch.equal(dXt.t().contiguous(), dX)
+        # round 1's form (ELU' operand given TRANSPOSED only, transposed output as well): served by the one-tile kernel, i.e. single-pass tf32 only —
+        # under the 3xTF32 default it must be refused, not silently downgraded
+        dX1, dXt = torch.zeros(M, K, device="cuda"), torch.zeros(K, M, device="cuda")
+        if _tc_call(passes, False, "go2_linear_dgrad_tc", dYd.data_ptr(), N, Wt.data_ptr(), Np, 0, 0, Xt.data_ptr(), M, dX1.data_ptr(), K, dXt.data_ptr(), M, M, N, K):
+            torch.cuda.synchronize()
+            assert _rel(dX1.cpu(), dX_ref) < bar, _rel(dX1.cpu(), dX_ref)
+            assert torch.equal(dXt.t().contiguous(), dX1)
 
 
 @pytest.mark.parametrize("M,N,K", [(8192, 256, 512), (24576, 128, 256), (777 * 4, 12, 128), (24576, 512, 263), (6148, 2048, 256), (4099, 32, 256), (24576, 1, 128)])
