@@ -647,6 +647,333 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// The GEMMs of this path are bound by SHARED-MEMORY bandwidth, not by HBM or the tensor pipe (measured with go2_gemm_set_debug, round 2): a
+// 128 x 128 x 8 tf32 MMA reads 8 KB of operands per 64 cycles = the SM's whole 128 B/clk, and the TMA writes and the 3xTF32 split come on top
+// (3xTF32: 48 KB of shared-memory traffic per 192 tensor cycles -> 375 cycles per K step).  Two CTAs on the two SMs of a TPC share one 256 x BN
+// tile: each stages its own 128 rows of A and HALF of B, the leader's one thread issues tcgen05.mma.cta_group::2 over both SMs' operands, and each
+// tensor core reads only its own SM's 4 + BN/64 KB per MMA — at BN = 256 the same 48 KB now cover 384 tensor cycles.
+//   roles per CTA (18 warps): 0 TMA producer (own A rows, own half of B) · 1 MMA issuer in the leader / landing relay in the peer (tells the
+//   leader that the peer's stage has landed) · 2..9 epilogue (own 128 accumulator rows, own TMEM) · 10..17 splitters (own stage -> own lo slot)
+//   barriers: full / loempty / empty / tfull are CTA-local (commits are multicast to both CTAs); the leader's pfull, lofull and tempty also take
+//   the peer's arrivals through the cluster window (mapa + mbarrier.arrive.shared::cluster).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `target` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t target) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// commit of the leader's MMAs, delivered to the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+constexpr int TCQ_THREADS = 320, TCQ_THREADS_X3 = 320 + 32 * TCP_SPLIT_WARPS;
+constexpr int TCQ_BM = 256;                      // rows of a pair tile
+// shared-memory slot of one CTA's half of B: BN/2 rows of 128 B (K-major) or ceil(BN/64) boxes of [32 rows][32 features] (MN-major)
+__host__ __device__ constexpr int tcq_b_bytes(int BN) { return (BN / 2 + 31) / 32 * 4096; }
+static int tcq_smem_bytes(int BN, int stages, bool x3) {
+  return (stages + (x3 ? TCP_LO_SLOTS : 0)) * (TC_BM * TC_BK * 4 + tcq_b_bytes(BN)) + 4 * TCP_CHUNK_BYTES + 512 + 1024;
+}
+static int tcq_stages(int BN, bool x3) {
+  int s = TCP_MAX_STAGES;
+  while (s > 2 && tcq_smem_bytes(BN, s, x3) > TCP_SMEM_MAX) --s;
+  return s;
+}
+
+template <int BN, bool X3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? TCQ_THREADS_X3 : TCQ_THREADS, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                      const __grid_constant__ CUtensorMap tmAux, const TcParamsP p) {
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "pair tile width: multiple of 32 (epilogue chunks), at most 256 (one tcgen05.mma)");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int BH = BN / 2;                                   // rows (features) of B this CTA stages
+  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = tcq_b_bytes(BN), STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int NBOX_B = (BH + 31) / 32;
+  constexpr int NCH = BN / 32;
+  const int S = p.stages;
+  uint8_t* lo_ring = smem + S * STAGE_BYTES;
+  uint8_t* cst = lo_ring + (X3 ? TCP_LO_SLOTS * STAGE_BYTES : 0);   // [group][2] row-major staging chunks [128 rows][128 B], SW128
+  uint64_t* full_bar = (uint64_t*)(cst + 4 * TCP_CHUNK_BYTES);
+  uint64_t* pfull_bar = full_bar + TCP_MAX_STAGES;             // leader: the peer's stage has landed
+  uint64_t* empty_bar = pfull_bar + TCP_MAX_STAGES;
+  uint64_t* tfull = empty_bar + TCP_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;                                // leader: 16 epilogue warps (8 local, 8 of the peer)
+  uint64_t* auxb = tempty + 2;                                 // [group][2]
+  uint64_t* lofull = auxb + 4;                                 // leader: 16 splitter warps
+  uint64_t* loempty = lofull + TCP_LO_SLOTS;
+  uint32_t* tmem_slot = (uint32_t*)(loempty + TCP_LO_SLOTS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;      // cluster index / number of clusters
+  const int units = p.m_tiles * p.n_tiles * p.splits;          // m_tiles = 256-row pair tiles
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    if (p.has_c) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmC) : "memory");
+    if (p.has_aux) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmAux) : "memory");
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar + s, 1); mbar_init(pfull_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 16); }
+    for (int b = 0; b < 4; ++b) mbar_init(auxb + b, 1);
+    for (int b = 0; b < TCP_LO_SLOTS; ++b) { mbar_init(lofull + b, 2 * TCP_SPLIT_WARPS); mbar_init(loempty + b, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();                                          // both CTAs' barriers exist before anything can arrive remotely
+  if (warp == 1) {  // the pair's TMEM: two accumulators of up to 256 columns in each SM (same warp id in both CTAs)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: own 128 rows of A, own half of B
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      long long w_empty = 0, *pw = p.dbg ? &w_empty : nullptr;
+      const long long t_start = p.dbg ? clock64() : 0;
+      for (int u = cid; u < units; u += ncl) {
+        const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
+        const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+        const int arow = mt * TCQ_BM + (int)rank * TC_BM, brow = nt * BN + (int)rank * BH;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_t(empty_bar + s, ph ^ 1, pw);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          if (!p.mn_major) {
+            mbar_expect_tx(full_bar + s, A_BYTES + BH * TC_BK * 4);
+            tma_load_2d(&tmA, full_bar + s, sa, (kb0 + kb) * TC_BK, arow);
+            tma_load_2d(&tmB, full_bar + s, sa + A_BYTES, (kb0 + kb) * TC_BK, brow);
+          } else {   // one [32 rows][32 features] box per 32-wide feature group
+            mbar_expect_tx(full_bar + s, A_BYTES + NBOX_B * 4096);
+#pragma unroll
+            for (int g = 0; g < TC_BM / 32; ++g) tma_load_2d(&tmA, full_bar + s, sa + g * 4096, arow + 32 * g, (kb0 + kb) * TC_BK);
+#pragma unroll
+            for (int g = 0; g < NBOX_B; ++g) tma_load_2d(&tmB, full_bar + s, sa + A_BYTES + g * 4096, brow + 32 * g, (kb0 + kb) * TC_BK);
+          }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+      if (p.dbg && rank == 0) { long long* d = p.dbg + cid * 16; d[0] = clock64() - t_start; d[1] = w_empty; }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===== landing relay (peer): stage s of this CTA has landed -> the leader may multiply it
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = cid; u < units; u += ncl) {
+        const int z = u / (p.n_tiles * p.m_tiles);
+        const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + s, ph);
+          mbar_arrive_cluster(pfull_bar + s, 0);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread of the leader CTA, for both SMs)
+    if (elect_one()) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TCQ_BM >> 4) << 24);
+      int s = 0, ui = 0, l = 0;
+      uint32_t ph = 0, lph = 0;
+      long long w_tempty = 0, w_full = 0, w_lofull = 0, nst = 0;
+      long long *pw_tempty = p.dbg ? &w_tempty : nullptr, *pw_full = p.dbg ? &w_full : nullptr, *pw_lofull = p.dbg ? &w_lofull : nullptr;
+      const long long t_start = p.dbg ? clock64() : 0;
+      for (int u = cid; u < units; u += ncl, ++ui) {
+        const int z = u / (p.n_tiles * p.m_tiles);
+        const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+        const int buf = ui & 1;
+        nst += nkb;
+        mbar_wait_t(tempty + buf, ((ui >> 1) & 1) ^ 1, pw_tempty);            // both CTAs' epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_t(full_bar + s, ph, pw_full);
+          mbar_wait_t(pfull_bar + s, ph, pw_full);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sl = smem_u32(lo_ring + l * STAGE_BYTES);
+          const bool kmaj = !p.mn_major;
+          const uint64_t da = kmaj ? make_desc_kmajor_sw128(sa) : make_desc_mnmajor_sw128_32b(sa);
+          const uint64_t db = kmaj ? make_desc_kmajor_sw128(sa + A_BYTES) : make_desc_mnmajor_sw128_32b(sa + A_BYTES);
+          const uint64_t kstep = kmaj ? 2 : 64;
+          const uint32_t idesc = kmaj ? IDESC : (IDESC | (1u << 15) | (1u << 16));
+          const bool hi_first = !X3 || !p.split_rewrite;
+          if (hi_first) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_tf32_pair(tacc, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          if (X3) {
+            mbar_wait_t(lofull + l, lph, pw_lofull);              // both CTAs' splitters have filled their lo slots
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t la = kmaj ? make_desc_kmajor_sw128(sl) : make_desc_mnmajor_sw128_32b(sl);
+            const uint64_t lb = kmaj ? make_desc_kmajor_sw128(sl + A_BYTES) : make_desc_mnmajor_sw128_32b(sl + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              umma_tf32_pair(tacc, la + kstep * k, db + kstep * k, idesc, (hi_first || (kb | k)) ? 1u : 0u);
+              umma_tf32_pair(tacc, da + kstep * k, lb + kstep * k, idesc, 1u);
+              if (!hi_first) umma_tf32_pair(tacc, da + kstep * k, db + kstep * k, idesc, 1u);
+            }
+          }
+          umma_commit_pair(empty_bar + s);
+          if (X3) { umma_commit_pair(loempty + l); if (++l == TCP_LO_SLOTS) { l = 0; lph ^= 1; } }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(tfull + buf);
+      }
+      if (p.dbg) { long long* d = p.dbg + cid * 16; d[2] = clock64() - t_start; d[3] = w_tempty; d[4] = w_full; d[5] = w_lofull; d[6] = nst; }
+    }
+  } else if (X3 && warp >= 10) {
+    // ===== splitter warps (3xTF32): own stage -> own lo slot; every warp of BOTH CTAs arrives on the leader's lofull
+    const int t = threadIdx.x - 320;
+    constexpr int NV = STAGE_BYTES / 16, NT = 32 * TCP_SPLIT_WARPS, PER = (NV + NT - 1) / NT;
+    int s = 0, l = 0;
+    uint32_t ph = 0, lph = 0;
+    long long w_full = 0, w_loempty = 0, t_work = 0;
+    long long *pw_full = p.dbg ? &w_full : nullptr, *pw_loempty = p.dbg ? &w_loempty : nullptr;
+    for (int u = cid; u < units; u += ncl) {
+      const int z = u / (p.n_tiles * p.m_tiles);
+      const int kb0 = z * p.kb_per_split, nkb = min(p.kb_per_split, p.total_kb - kb0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_t(full_bar + s, ph, pw_full);
+        const long long t_w0 = p.dbg ? clock64() : 0;
+        uint4* raw = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * STAGE_BYTES);
+        uint4 v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) v[j] = raw[t + NT * j];
+        mbar_wait_t(loempty + l, lph ^ 1, pw_loempty);            // the MMAs that read this lo slot (in both SMs) have retired
+        if (p.split_rewrite) {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) { const uint4 w = split_tf32<1>(v[j]); raw[t + NT * j] = v[j]; lo[t + NT * j] = w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) if (NV % NT == 0 || t + NT * j < NV) lo[t + NT * j] = split_tf32<0>(v[j]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lofull + l, 0);
+        if (p.dbg) t_work += clock64() - t_w0;
+        if (++l == TCP_LO_SLOTS) { l = 0; lph ^= 1; }
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+    if (p.dbg && t == 0 && rank == 0) { long long* d = p.dbg + cid * 16; d[7] = w_full; d[8] = w_loempty; d[9] = t_work; }
+  } else if (warp >= 2 && warp < 10) {
+    // ===== epilogue: own 128 accumulator rows; group grp takes chunks grp, grp+2, ...; warp -> TMEM lane quadrant q; thread = one tile row
+    const int grp = (warp - 2) >> 2, q = warp & 3;
+    const int row = 32 * q + lane;
+    const bool leader = (((warp - 2) & 3) == 0) && lane == 0;
+    const int sw = row & 7;
+    uint8_t* cst_g = cst + grp * 2 * TCP_CHUNK_BYTES;
+    uint64_t* auxb_g = auxb + grp * 2;
+    auto n_chunks = [&](int u) { return min(NCH, (p.N - (u % p.n_tiles) * BN + 31) / 32); };
+    auto advance = [&](int& u, int& c) {
+      c += 2;
+      while (u < units && c >= n_chunks(u)) { u += ncl; c = grp; }
+      return u < units;
+    };
+    auto aux_load = [&](int u, int c, int slot) {
+      const int nt = u % p.n_tiles, mt = (u / p.n_tiles) % p.m_tiles;
+      mbar_expect_tx(auxb_g + slot, TCP_CHUNK_BYTES);
+      tma_load_2d(&tmAux, auxb_g + slot, cst_g + slot * TCP_CHUNK_BYTES, nt * BN + c * 32, mt * TCQ_BM + (int)rank * TC_BM);
+    };
+    long long w_tfull = 0, *pw_tfull = (p.dbg && leader && rank == 0) ? &w_tfull : nullptr;
+    long long w_aux = 0, *pw_aux = (p.dbg && leader && rank == 0) ? &w_aux : nullptr;
+    const long long t_start = p.dbg ? clock64() : 0;
+    uint32_t g = 0;
+    int ui = 0;
+    if (p.has_aux && leader) {
+      int u0 = cid, c0 = grp - 2;
+      if (advance(u0, c0)) aux_load(u0, c0, 0);
+    }
+    for (int u = cid; u < units; u += ncl, ++ui) {
+      const int nt = u % p.n_tiles, t = u / p.n_tiles, mt = t % p.m_tiles, z = t / p.m_tiles;
+      const int m0 = mt * TCQ_BM + (int)rank * TC_BM, n0 = nt * BN;
+      const int nch = n_chunks(u);
+      const int buf = ui & 1;
+      mbar_wait_t(tfull + buf, (ui >> 1) & 1, pw_tfull);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = grp; c < nch; c += 2, ++g) {
+        const int nb = n0 + c * 32;
+        const int slot = g & 1;
+        float* cs = reinterpret_cast<float*>(cst_g + slot * TCP_CHUNK_BYTES);
+        if (leader) {
+          if (p.has_aux) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            int nu = u, nc = c;
+            if (advance(nu, nc)) aux_load(nu, nc, slot ^ 1);
+          } else {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 256 + c * 32), r);
+        float v[32];
+        float bias_lane = 0.0f;
+        if ((p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) && nb + lane < p.N) bias_lane = __ldg(p.bias + nb + lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (p.epi == TC_EPI_BIAS || p.epi == TC_EPI_BIAS_ELU) x += __shfl_sync(0xffffffffu, bias_lane, j);
+          if (p.epi == TC_EPI_BIAS_ELU) x = x > 0.0f ? x : (__expf(x) - 1.0f);
+          v[j] = x;
+        }
+        if (p.has_aux) {
+          mbar_wait_t(auxb_g + slot, (g >> 1) & 1, pw_aux);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 y = *reinterpret_cast<const float4*>(cs + row * 32 + ((j4 ^ sw) << 2));
+            v[4 * j4 + 0] *= (y.x > 0.0f ? 1.0f : y.x + 1.0f);
+            v[4 * j4 + 1] *= (y.y > 0.0f ? 1.0f : y.y + 1.0f);
+            v[4 * j4 + 2] *= (y.z > 0.0f ? 1.0f : y.z + 1.0f);
+            v[4 * j4 + 3] *= (y.w > 0.0f ? 1.0f : y.w + 1.0f);
+          }
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(cs + row * 32 + ((j4 ^ sw) << 2)) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (leader) {
+          tma_store_2d(&tmC, cs, nb, z * p.rows_pad + m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      // this warp has read everything it needs from the accumulator: hand it back to the leader's MMA thread
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty + buf, 0);
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.dbg && leader && rank == 0) { long long* d = p.dbg + cid * 16 + 10 + 2 * grp; d[0] = clock64() - t_start; d[1] = w_tfull; p.dbg[cid * 16 + 14 + grp] = w_aux; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  cluster_sync_all();                                          // nobody leaves (or frees TMEM) while the partner may still touch this SM
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // out[i] = sum_z part[z][i] (deterministic split-K reduction); rows x cols with output leading dimension ld_out
 // cols = K (+1 when the bias gradient rides along as an extra "ones" column of X^T: that column goes to db)
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int Z, long ld_part, long split_stride, long ld_out,
@@ -829,6 +1156,70 @@ static int tc_split_rewrite() {
 
 static long long* g_tc_dbg = nullptr;   // go2_gemm_set_debug
 
+// CTA-pair kernel on / off (GO2_GEMM_PAIR=0 or go2_gemm_set_pair(0): the one-CTA persistent kernel everywhere; A/B aid)
+static int g_tc_pair = -1;
+static bool tc_pair() {
+  if (g_tc_pair < 0) { const char* e = getenv("GO2_GEMM_PAIR"); g_tc_pair = (e && !strcmp(e, "0")) ? 0 : 1; }
+  return g_tc_pair == 1;
+}
+// tile width of the pair kernel: the padded width ceil(N / BN) * BN decides, wider tiles win ties (fewer shared-memory bytes per flop)
+static int pair_bn(int N) {
+  if (N <= 64) return 64;
+  const int cand[4] = {256, 192, 160, 128};
+  int best = 256; long cost = -1;
+  for (int i = 0; i < 4; ++i) {
+    const long c = (long)((N + cand[i] - 1) / cand[i]) * cand[i];
+    if (cost < 0 || c < cost) { cost = c; best = cand[i]; }
+  }
+  return best;
+}
+static bool pair_ok(const TcParams& p) { return tc_pair() && tc_passes() == 3 && !p.Ct && p.C && p.M > TC_BM && (sm_count() & 1) == 0; }
+
+template <int BN>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& taux, const TcParamsP& pp, cudaStream_t st) {
+  const int smem = tcq_smem_bytes(BN, pp.stages, true);
+  GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_pair_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_MAX));
+  const int units = pp.m_tiles * pp.n_tiles * pp.splits;
+  gemm_tf32_pair_kernel<BN, true><<<2 * min(units, sm_count() / 2), TCQ_THREADS_X3, smem, st>>>(ta, tb, tc, taux, pp);
+  count_launch();
+  return 0;
+}
+
+// C = A B^T on CTA pairs (3xTF32): 256-row tiles, split-K slices rows_pad = roundup(M, 256) rows apart
+static int gemm_tc_pair(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
+  const int BN = pair_bn(p.N);
+  TcParamsP pp{};
+  pp.stages = tcq_stages(BN, true);
+  pp.M = p.M; pp.N = p.N; pp.K = p.K;
+  pp.m_tiles = (p.M + TCQ_BM - 1) / TCQ_BM; pp.n_tiles = (p.N + BN - 1) / BN;
+  pp.total_kb = (p.K + TC_BK - 1) / TC_BK;
+  pp.kb_per_split = (pp.total_kb + splits - 1) / splits;
+  pp.splits = (pp.total_kb + pp.kb_per_split - 1) / pp.kb_per_split;
+  pp.rows_pad = pp.m_tiles * TCQ_BM;
+  pp.bias = p.bias; pp.epi = p.epi; pp.has_c = 1; pp.has_ct = 0; pp.has_aux = p.epi == TC_EPI_MUL_ELU_GRAD;
+  pp.mn_major = p.mn_major; pp.split_rewrite = tc_split_rewrite(); pp.dbg = g_tc_dbg;
+  if (splits > 1 && p.split_stride != (long)pp.rows_pad * p.ldc) return set_error(5, "gemm_tc_pair: split stride must be roundup(M,256) * ldc");
+  CUtensorMap ta, tb, tc, taux;
+  int rc = p.mn_major ? make_map(&ta, A, p.K, p.M, lda, 32, 32, true) : make_map(&ta, A, p.M, p.K, lda, TC_BM);
+  if (rc) return rc;
+  rc = p.mn_major ? make_map(&tb, B, p.K, p.N, ldb, 32, 32, true) : make_map(&tb, B, p.N, p.K, ldb, BN / 2);
+  if (rc) return rc;
+  rc = make_map(&tc, p.C, splits > 1 ? (long)splits * pp.rows_pad : p.M, p.N, p.ldc, TC_BM);
+  if (rc) return rc;
+  taux = ta;
+  if (pp.has_aux) { rc = make_map(&taux, p.aux, p.M, p.N, p.ldaux, TC_BM); if (rc) return rc; }
+  switch (BN) {
+    case 64: rc = launch_pair<64>(ta, tb, tc, taux, pp, st); break;
+    case 128: rc = launch_pair<128>(ta, tb, tc, taux, pp, st); break;
+    case 160: rc = launch_pair<160>(ta, tb, tc, taux, pp, st); break;
+    case 192: rc = launch_pair<192>(ta, tb, tc, taux, pp, st); break;
+    default: rc = launch_pair<256>(ta, tb, tc, taux, pp, st); break;
+  }
+  if (rc) return rc;
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // split-K slices of C sit rows_pad = roundup(M, 128) rows apart so that one 2-D map covers all of them
 static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, const TcParams& p, int splits, cudaStream_t st) {
   const bool x3 = tc_passes() == 3;
@@ -863,6 +1254,7 @@ static int gemm_tc_persist(const float* A, long lda, const float* B, long ldb, c
 
 // C[M,N] = A[M,K] B[N,K]^T with both operands K-major; see TcParams for the epilogue
 static int gemm_tc(const float* A, long lda, const float* B, long ldb, TcParams p, int splits, cudaStream_t st) {
+  if (persist_ok(p) && pair_ok(p) && splits == 1) return gemm_tc_pair(A, lda, B, ldb, p, 1, st);
   if (persist_ok(p)) return gemm_tc_persist(A, lda, B, ldb, p, splits, st);
   // the one-tile-per-CTA kernel below is the single-pass tf32 kernel of round 1 (debug stamps, GO2_GEMM_LEGACY, operands the TMA store path
   // cannot take): never a silent precision downgrade of the 3xTF32 default
@@ -897,6 +1289,11 @@ int go2_gemm_set_passes(int passes) {
   return 0;
 }
 int go2_gemm_get_passes(void) { return tc_passes(); }
+int go2_gemm_set_pair(int on) {
+  if (on != 0 && on != 1) return set_error(1, "go2_gemm_set_pair: 0 or 1");
+  g_tc_pair = on;
+  return 0;
+}
 int go2_gemm_set_debug(long long* counters) { g_tc_dbg = counters; return 0; }
 int go2_gemm_set_split(int rewrite) {
   if (rewrite != 0 && rewrite != 1) return set_error(1, "go2_gemm_set_split: 0 (lo only, hardware truncation is hi) or 1 (stage rewritten with rn_tf32)");
@@ -968,17 +1365,21 @@ int go2_linear_wgrad_tc_rm(const float* dZ, int lddz, const float* X, int ldx, f
   if (!workspace) return set_error(5, "go2_linear_wgrad_tc_rm: workspace required");
   const long ldp = (K + 3) / 4 * 4;
   const int total_kb = (M + TC_BK - 1) / TC_BK;
-  const int rows_pad = (N + TC_BM - 1) / TC_BM * TC_BM;
-  const int BN = persist_bn(K);
-  const int tiles = ((N + TC_BM - 1) / TC_BM) * ((K + BN - 1) / BN);
-  int splits = max(1, min(min(total_kb / 8, 48), (sm_count() + tiles / 2) / tiles));
+  TcParams p{};
+  p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN; p.mn_major = 1;
+  p.C = workspace; p.ldc = ldp;
+  const bool pair = pair_ok(p) && (long)((N + TCQ_BM - 1) / TCQ_BM * TCQ_BM) * ldp <= workspace_floats;
+  const int tile_m = pair ? TCQ_BM : TC_BM;
+  const int rows_pad = (N + tile_m - 1) / tile_m * tile_m;
+  const int BN = pair ? pair_bn(K) : persist_bn(K);
+  const int tiles = ((N + tile_m - 1) / tile_m) * ((K + BN - 1) / BN);
+  // ~ one unit per SM (one-CTA kernel) / at most one unit per CTA pair
+  int splits = pair ? max(1, min(min(total_kb / 8, 48), (sm_count() / 2) / tiles)) : max(1, min(min(total_kb / 8, 48), (sm_count() + tiles / 2) / tiles));
   while (splits > 1 && (long)splits * rows_pad * ldp > workspace_floats) --splits;
   if ((long)rows_pad * ldp > workspace_floats) return set_error(5, "go2_linear_wgrad_tc_rm: workspace too small");
   splits = (total_kb + (total_kb + splits - 1) / splits - 1) / ((total_kb + splits - 1) / splits);
-  TcParams p{};
-  p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN; p.mn_major = 1;
-  p.C = workspace; p.ldc = ldp; p.split_stride = (long)rows_pad * ldp;
-  int rc = gemm_tc_persist(dZ, lddz, X, ldx, p, splits, st);
+  p.split_stride = (long)rows_pad * ldp;
+  int rc = pair ? gemm_tc_pair(dZ, lddz, X, ldx, p, splits, st) : gemm_tc_persist(dZ, lddz, X, ldx, p, splits, st);
   if (rc) return rc;
   const long n = (long)N * (ldp / 4);
   tc_splitk_reduce_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 8), 0, st>>>(workspace, dW, N, splits, ldp, p.split_stride, lddw, K, k_real, db);
