@@ -665,7 +665,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t target) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  // default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the .release.cluster form compiles to
+  // MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrival (measured: +900 cycles per 32 KB stage in the splitter warps).  What the arrival
+  // publishes is shared memory of THIS SM for the tensor core of THIS SM (made visible to the async proxy by the fence.proxy.async before it).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -1173,7 +1176,13 @@ static int pair_bn(int N) {
   }
   return best;
 }
-static bool pair_ok(const TcParams& p) { return tc_pair() && tc_passes() == 3 && !p.Ct && p.C && p.M > TC_BM && (sm_count() & 1) == 0; }
+// Pairs pay off when there are enough 256-row tiles to go round: with a handful of units (rollout inference, 4096 rows = 16 pair tiles) the one-CTA
+// kernel spreads the same work over four times as many SMs (measured: 17 us vs 22 us for 4096 x 512 x 264).  `units` = pair tiles x splits.
+static bool pair_ok(const TcParams& p, int splits = 1) {
+  if (!(tc_pair() && tc_passes() == 3 && !p.Ct && p.C && p.M > TC_BM && (sm_count() & 1) == 0)) return false;
+  const long units = (long)((p.M + TCQ_BM - 1) / TCQ_BM) * ((p.N + pair_bn(p.N) - 1) / pair_bn(p.N)) * splits;
+  return units >= sm_count() / 4;
+}
 
 template <int BN>
 static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& taux, const TcParamsP& pp, cudaStream_t st) {
@@ -1368,7 +1377,7 @@ int go2_linear_wgrad_tc_rm(const float* dZ, int lddz, const float* X, int ldx, f
   TcParams p{};
   p.M = N; p.N = K; p.K = M; p.epi = TC_EPI_PLAIN; p.mn_major = 1;
   p.C = workspace; p.ldc = ldp;
-  const bool pair = pair_ok(p) && (long)((N + TCQ_BM - 1) / TCQ_BM * TCQ_BM) * ldp <= workspace_floats;
+  const bool pair = pair_ok(p, 64) && (long)((N + TCQ_BM - 1) / TCQ_BM * TCQ_BM) * ldp <= workspace_floats;
   const int tile_m = pair ? TCQ_BM : TC_BM;
   const int rows_pad = (N + tile_m - 1) / tile_m * tile_m;
   const int BN = pair ? pair_bn(K) : persist_bn(K);
