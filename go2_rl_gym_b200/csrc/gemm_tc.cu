@@ -395,6 +395,9 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = p.m_tiles * p.n_tiles * p.splits;
+  // programmatic dependent launch: the next GEMM of the stream may take over this SM as soon as this CTA exits and run its prologue (barriers, TMEM,
+  // tensor-map prefetch) under the tail of this grid; it blocks in griddepcontrol.wait below until this grid has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -416,6 +419,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // everything before this line touched no global memory (no-op without the launch attribute)
 
   if (warp == 0) {
     // ===== TMA producer: the stage ring runs straight through the unit list
@@ -724,6 +728,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;      // cluster index / number of clusters
   const int units = p.m_tiles * p.n_tiles * p.splits;          // m_tiles = 256-row pair tiles
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see gemm_tf32_persist_kernel
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -745,6 +750,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer: own 128 rows of A, own half of B
@@ -1131,13 +1137,32 @@ static bool persist_ok(const TcParams& p) {
   return p.C || p.Ct;
 }
 
+// GO2_GEMM_PDL=0 / go2_gemm_set_pdl(0): plain stream-ordered launches of the persistent GEMMs (A/B aid)
+static int g_tc_pdl = -1;
+static bool tc_pdl() {
+  if (g_tc_pdl < 0) { const char* e = getenv("GO2_GEMM_PDL"); g_tc_pdl = (e && !strcmp(e, "0")) ? 0 : 1; }
+  return g_tc_pdl == 1;
+}
+// launch with programmatic stream serialization: the grid may start while the previous kernel of the stream drains (its griddepcontrol.wait orders
+// the memory traffic); captured into CUDA graphs as a programmatic dependency edge
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = tc_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int BN, bool X3>
 static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tct, const CUtensorMap& taux,
                           const TcParamsP& pp, cudaStream_t st) {
   const int smem = tcp_smem_bytes(BN, pp.stages, pp.has_ct != 0, X3);
   GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persist_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_MAX));   // per device; cheap
   const int units = pp.m_tiles * pp.n_tiles * pp.splits;
-  gemm_tf32_persist_kernel<BN, X3><<<min(units, sm_count()), X3 ? TCP_THREADS_X3 : TCP_THREADS, smem, st>>>(ta, tb, tc, tct, taux, pp);
+  GO2_CUDA_OK(launch_pdl(gemm_tf32_persist_kernel<BN, X3>, min(units, sm_count()), X3 ? TCP_THREADS_X3 : TCP_THREADS, smem, st, ta, tb, tc, tct, taux, pp));
   count_launch();
   return 0;
 }
@@ -1189,7 +1214,7 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int smem = tcq_smem_bytes(BN, pp.stages, true);
   GO2_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_pair_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_MAX));
   const int units = pp.m_tiles * pp.n_tiles * pp.splits;
-  gemm_tf32_pair_kernel<BN, true><<<2 * min(units, sm_count() / 2), TCQ_THREADS_X3, smem, st>>>(ta, tb, tc, taux, pp);
+  GO2_CUDA_OK(launch_pdl(gemm_tf32_pair_kernel<BN, true>, 2 * min(units, sm_count() / 2), TCQ_THREADS_X3, smem, st, ta, tb, tc, taux, pp));
   count_launch();
   return 0;
 }
@@ -1298,6 +1323,11 @@ int go2_gemm_set_passes(int passes) {
   return 0;
 }
 int go2_gemm_get_passes(void) { return tc_passes(); }
+int go2_gemm_set_pdl(int on) {
+  if (on != 0 && on != 1) return set_error(1, "go2_gemm_set_pdl: 0 or 1");
+  g_tc_pdl = on;
+  return 0;
+}
 int go2_gemm_set_pair(int on) {
   if (on != 0 && on != 1) return set_error(1, "go2_gemm_set_pair: 0 or 1");
   g_tc_pair = on;

@@ -129,6 +129,42 @@ class GraphSet:
         g.replay()
 
 
+class SideStream:
+    """Second CUDA stream for work that is independent of the main chain (the critic next to the actor): fork() makes it wait for everything issued
+    so far on the current stream, `with side:` issues on it, join() makes the current stream wait for it.  The GEMM kernels are persistent
+    one-CTA-per-SM grids whose tails leave SMs idle (static tile lists, 1.3 - 2.6 waves of tiles): two independent chains fill each other's tails.
+    Inside a CUDA-graph capture the events become graph edges.  Disabled (everything on the current stream) on the CPU and with GO2_TWO_STREAMS=0."""
+
+    def __init__(self, device):
+        self.enabled = torch.device(device).type == "cuda" and os.environ.get("GO2_TWO_STREAMS", "1") != "0"
+        if self.enabled:
+            self.stream = torch.cuda.Stream(device=device)
+            self._e0, self._e1 = torch.cuda.Event(), torch.cuda.Event()
+        self._ctx = None
+
+    def fork(self):
+        if self.enabled:
+            self._e0.record()
+            self.stream.wait_event(self._e0)
+
+    def join(self):
+        if self.enabled:
+            self._e1.record(self.stream)
+            torch.cuda.current_stream().wait_event(self._e1)
+
+    def __enter__(self):
+        if self.enabled:
+            self._ctx = torch.cuda.stream(self.stream)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            ctx, self._ctx = self._ctx, None
+            return ctx.__exit__(*exc)
+        return False
+
+
 def _pad4(n):
     return (n + 3) // 4 * 4
 

@@ -70,6 +70,8 @@ class PPO:
         self._lr = torch.zeros(4, device=dev)      # {lr, optimiser step, Adam bias corrections} — device resident
         self._lr[0] = float(self.learning_rate)
         self._graphs = _ops.GraphSet()
+        self._side = _ops.SideStream(dev)          # the critic's chain runs next to the actor's (see _ops.SideStream)
+        self._join_pending = False
         self._scal = torch.zeros(20, device=dev)
         self._log = torch.zeros(5, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
@@ -105,9 +107,15 @@ class PPO:
             raise AssertionError("Rollout buffer overflow")
         N, A = st.num_envs, st.actions.shape[-1]
         st.observations[t].copy_(obs)
-        (st.privileged_observations if st.privileged_observations is not None else st.observations)[t].copy_(critic_obs)
+        cobs = (st.privileged_observations if st.privileged_observations is not None else st.observations)[t]
+        cobs.copy_(critic_obs)
+        # the value is first needed by process_env_step: the critic reads the STORED row (the env overwrites its own buffer during step()) on the
+        # side stream, next to the actor, the sampling and — inside a rollout opened by begin_rollout() — the env step itself
+        sd = self._side
+        sd.fork()
+        with sd:
+            ac.evaluate(cobs, out=st.values[t])
         mu = ac._actor_forward(st.observations[t])
-        ac.evaluate(critic_obs, out=st.values[t])
         if self._dev_steps is not None:      # rollout opened by begin_rollout(): the Philox step counter comes from device memory
             _ops.call("go2_sample_actions_dev", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
                       _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._dev_steps.data_ptr() + 4 * t, self.env_offset)
@@ -115,12 +123,18 @@ class PPO:
             self._act_step += 1
             _ops.call("go2_sample_actions", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
                       _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._act_step, self.env_offset)
+        if self._dev_steps is not None:
+            self._join_pending = True        # joined in process_env_step
+        else:
+            sd.join()
         self.transition.actions = st.actions[t]
         self.transition.values = st.values[t]
         return st.actions[t]
 
     def process_env_step(self, rewards, dones, infos):
         st, t = self.storage, self.storage.step
+        if self._join_pending:
+            self._side.join(); self._join_pending = False
         tout = infos.get('time_outs') if isinstance(infos, dict) else None
         d8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8)
         t8 = None if tout is None else (tout.view(torch.uint8) if tout.dtype == torch.bool else tout.to(torch.uint8))
@@ -193,16 +207,23 @@ class PPO:
         s = slice(i * mb, (i + 1) * mb)
         obs_b, cobs_b = sh["obs"][s], sh["critic_obs"][s]
         # padded gathers carry a 1 in their first padding column (the bias-gradient column of the row-major wgrad)
+        sd = self._side
+        sd.fork()
+        with sd:
+            ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, x_ones=tc)
         ac.actor_engine.forward(obs_b, obs_b.shape[1], mb, self._mu_b, A, train=True, x_ones=tc)
-        ac.critic_engine.forward(cobs_b, cobs_b.shape[1], mb, self._val_b, 1, train=True, x_ones=tc)
+        sd.join()
         _ops.call("go2_ppo_loss", _ops.ptr(self._mu_b), _ops.ptr(ac.std.data), _ops.ptr(self._val_b), _ops.ptr(sh["actions"][s]),
                   _ops.ptr(sh["old_logp"][s]), _ops.ptr(sh["adv"][s]), _ops.ptr(sh["values"][s]), _ops.ptr(sh["returns"][s]),
                   _ops.ptr(sh["old_mu"][s]), _ops.ptr(sh["old_sigma"][s]), _ops.ptr(self._dmu), 0,
                   _ops.ptr(self._dval), _ops.ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
                   int(self.use_clipped_value_loss), inv_count, mb, inv_count, inv_count)
+        sd.fork()
+        with sd:
+            ac.critic_engine.backward(self._dval, 1)
         ac.actor_engine.backward(self._dmu, A)
-        ac.critic_engine.backward(self._dval, 1)
         ac._gviews["std"].copy_(self._scal[4:4 + A])
+        sd.join()
 
     def _step_part(self):
         """KL-adaptive learning rate (ppo.py:139-151) + clip + Adam on the (all-reduced) flat gradient."""

@@ -262,6 +262,9 @@ int go2_gemm_set_split(int rewrite);
 /* 1 (default): 3xTF32 GEMMs with more than 128 rows run on CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles, each SM stages half of B);
    0: the one-CTA persistent kernel everywhere (A/B aid; also GO2_GEMM_PAIR=0).  Same arithmetic, same results up to the summation split. */
 int go2_gemm_set_pair(int on);
+/* 1 (default): the persistent GEMMs are launched with programmatic stream serialization (their prologue runs under the tail of the previous kernel,
+   griddepcontrol.wait orders the memory traffic); 0: plain stream order (A/B aid; also GO2_GEMM_PDL=0). */
+int go2_gemm_set_pdl(int on);
 /* Profiling aid: counters != NULL makes every persistent tensor-core GEMM launch write, per CTA b, 16 int64 cycle counters at counters[16 b ...]
    (device memory, >= 16 x SM count): 0 producer total, 1 producer waiting for a free stage; 2 MMA thread total, 3 .. waiting for a drained accumulator,
    4 .. for TMA bytes, 5 .. for the lo slot, 6 stages processed; 7 splitter waiting for TMA bytes, 8 .. for a free lo slot, 9 splitter busy (incl. 8);
