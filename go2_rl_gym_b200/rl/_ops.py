@@ -165,6 +165,28 @@ class SideStream:
         return False
 
 
+class StreamPool:
+    """n side streams for loops of independent small launches (the E block-diagonal experts of a mixture layer: each is a GEMM of a few dozen tiles that
+    cannot fill 148 SMs on its own).  fork() -> `with pool.lane(i):` ... -> join().  Lane i is a SideStream; all lanes fork from / join into the
+    current stream."""
+
+    def __init__(self, device, n=4):
+        self.lanes = [SideStream(device) for _ in range(n)]
+        self.n = n
+        self.enabled = self.lanes[0].enabled
+
+    def fork(self):
+        for l in self.lanes:
+            l.fork()
+
+    def lane(self, i):
+        return self.lanes[i % self.n]
+
+    def join(self):
+        for l in self.lanes:
+            l.join()
+
+
 def _pad4(n):
     return (n + 3) // 4 * 4
 
@@ -197,7 +219,9 @@ class MlpEngine:
         hidden = dims[1:] if last_act else dims[1:-1]
         self.acts = [torch.ones(max_rows, d + 4, device=dev) for d in hidden]       # column d stays 1
         hmax = max(dims[1:-1]) if self.L > 1 else dims[-1]
-        self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(2)]
+        # one gradient buffer per layer boundary: the weight gradient of layer l (side stream) may still read dZ_l while the chain moves on
+        self.dbuf = [torch.empty(max(train_rows, 1), hmax, device=dev) for _ in range(max(self.L - 1, 1) if train_rows else 1)]
+        self.wside = SideStream(dev if train_rows else "cpu")        # weight gradients run next to the dgrad chain (disabled for inference-only engines)
         self.work = torch.empty(64 * max(_pad4(dims[l] + 1) * ((dims[l + 1] + 127) // 128 * 128) for l in range(self.L)), device=dev)
         self.kpad0 = pad_in(dims[0]) if self.tc else dims[0]               # room for the ones column
         self.W0p = torch.zeros(dims[1], self.kpad0, device=dev) if self.tc else None
@@ -276,25 +300,30 @@ class MlpEngine:
         With need_dx the gradient w.r.t. the input lands in self.dx [M, kpad0]."""
         M = self._M
         d, ldd = dY, lddy
+        ws = self.wside
         for l in range(self.L - 1, -1, -1):
             n_out, n_in = self.dims[l + 1], self.dims[l]
             xin, ldx = (self._Xin, self._ldxin) if l == 0 else (self.acts[l - 1], n_in + 4)
             ones = self._x_ones if l == 0 else True
             small = n_out <= 16 and n_in <= 128 and l > 0
-            if small:       # narrow heads: streaming fp32 kernels (weights + bias in one pass)
-                call("go2_linear_wgrad_smalln", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]), M, n_out, n_in, ptr(self.work), self.work.numel())
-            elif self.tc and ldd % 4 == 0 and d.data_ptr() % 16 == 0:
-                if not ones:
+            # weight gradient of layer l: needs dZ_l (ready on the current stream) and the stored activations; nothing of the dgrad chain needs it.
+            # All weight gradients of this engine share `work`, so they stay in order on ONE side stream.
+            ws.fork()
+            with ws:
+                if small:       # narrow heads: streaming fp32 kernels (weights + bias in one pass)
+                    call("go2_linear_wgrad_smalln", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]), M, n_out, n_in, ptr(self.work), self.work.numel())
+                elif self.tc and ldd % 4 == 0 and d.data_ptr() % 16 == 0:
+                    if not ones:
+                        call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
+                    call("go2_linear_wgrad_tc_rm", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]) if ones else 0, M, n_out, n_in,
+                         ptr(self.work), self.work.numel())
+                elif n_out == 1 and n_in <= 512:      # the critic's scalar head: one streaming pass (weights + bias)
+                    call("go2_linear_wgrad_rank1", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), ptr(self.gb[l]), M, n_in, ptr(self.work), self.work.numel())
+                else:
                     call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
-                call("go2_linear_wgrad_tc_rm", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, ptr(self.gb[l]) if ones else 0, M, n_out, n_in,
-                     ptr(self.work), self.work.numel())
-            elif n_out == 1 and n_in <= 512:      # the critic's scalar head: one streaming pass (weights + bias)
-                call("go2_linear_wgrad_rank1", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), ptr(self.gb[l]), M, n_in, ptr(self.work), self.work.numel())
-            else:
-                call("go2_colsum", ptr(d), ldd, ptr(self.gb[l]), M, n_out, ptr(self.work))
-                call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())
+                    call("go2_linear_wgrad_simt", ptr(d), ldd, ptr(xin), ldx, ptr(self.gW[l]), n_in, 0, M, n_out, n_in, ptr(self.work), self.work.numel())
             if l > 0:
-                nxt = self.dbuf[l % 2]
+                nxt = self.dbuf[l - 1]
                 if small:
                     call("go2_linear_dgrad_smalln", ptr(d), ldd, ptr(self.W[l]), n_in, ptr(self.acts[l - 1]), n_in + 4, ptr(nxt), n_in, M, n_out, n_in)
                 elif self.tc and n_out % 4 == 0:
@@ -308,3 +337,4 @@ class MlpEngine:
                     call("go2_linear_dgrad_tc", ptr(d), ldd, ptr(self.Wt[0]), self.Wt[0].shape[1], 0, 0, 0, 0, ptr(self.dx), self.kpad0, 0, 0, M, n_out, n_in)
                 else:
                     call("go2_linear_dgrad_simt", ptr(d), ldd, ptr(self.W[0]), n_in, 0, 0, ptr(self.dx), self.kpad0, 0, 0, M, n_out, n_in)
+        ws.join()

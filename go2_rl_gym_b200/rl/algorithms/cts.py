@@ -84,6 +84,7 @@ class CTS:
         self._hist_p = z(N, self.history_length * actor_obs_shape[0])
         self._rew_p, self._actions_env = z(N), z(N, A)
         self._graphs = _ops.GraphSet()
+        self._side = _ops.SideStream(dev)          # independent chains (teacher / student, actor / critic) run side by side: _ops.SideStream
 
     def test_mode(self):
         self.model.eval()
@@ -95,10 +96,14 @@ class CTS:
     def _latents(self, priv, hist, n_t, n_s, train_teacher=False):
         """self._lat[0:n_t] = teacher latent of the first n_t rows, self._lat[n_t:n_t+n_s] = student latent of the rest (no grad)."""
         m = self.model
-        if n_t:
-            m.teacher_latent(priv[:n_t], n_t, self._lat[:n_t], train=train_teacher, x_ones=train_teacher and _ops.use_tc())
+        sd = self._side
+        sd.fork()
+        with sd:         # the teacher's rows next to the student's
+            if n_t:
+                m.teacher_latent(priv[:n_t], n_t, self._lat[:n_t], train=train_teacher, x_ones=train_teacher and _ops.use_tc())
         if n_s:
             m.student.forward(hist[n_t:n_t + n_s], n_s, self._lat[n_t:n_t + n_s])
+        sd.join()
 
     def _heads(self, obs, priv, M, train=False):
         m, D = self.model, self.model.latent_dim
@@ -107,8 +112,12 @@ class CTS:
         call("go2_concat2", ptr(self._lat), D, D, ptr(obs), m.num_obs, obs.stride(0), ptr(self._xa), self._xa.shape[1], 0, M)
         call("go2_concat2", ptr(self._lat), D, D, ptr(priv), m.num_critic_obs, priv.stride(0), ptr(self._xc), self._xc.shape[1], 0, M)
         ones = self._xa.shape[1] > D + m.num_obs
+        sd = self._side
+        sd.fork()
+        with sd:         # the critic next to the actor
+            m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, x_ones=self._xc.shape[1] > D + m.num_critic_obs)
         m.actor_engine.forward(self._xa, self._xa.shape[1], M, self._mu[:M], m.num_actions, train=train, x_ones=ones)
-        m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, x_ones=self._xc.shape[1] > D + m.num_critic_obs)
+        sd.join()
 
     # ---- rollout -------------------------------------------------------------------------------------------------------
     def begin_rollout(self, T):
@@ -267,11 +276,15 @@ class CTS:
              ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
              0, ptr(self._dval), ptr(self._scal), mb, A, self.clip_param, self.value_loss_coef, self.entropy_coef,
              int(self.use_clipped_value_loss), 1.0 / (mb * ws), tm, 1.0 / (tm * ws), 1.0 / (max(sm, 1) * ws))
+        sd = self._side
+        sd.fork()
+        with sd:
+            m.critic_engine.backward(self._dval, 1)
         m.actor_engine.backward(self._dmu, A)
-        m.critic_engine.backward(self._dval, 1)
         # d loss / d latent = first D columns of the actor's input gradient, teacher rows only (student latents carry no grad)
         m.teacher_backward(m.actor_engine.dx, m.actor_engine.kpad0, self._lat, D, tm)
         m._gviews["std"].copy_(self._scal[4:4 + A])
+        sd.join()
 
     def _step1(self):
         m, ws = self.model, self.world_size
@@ -289,8 +302,12 @@ class CTS:
         tc = _ops.use_tc()
         s = slice(i * mb + tm, (i + 1) * mb)
         priv_b, hist_b = sh["critic_obs"][s], sh["history"][s]
-        m.teacher_latent(priv_b, sm, self._lat_t)
+        sd = self._side
+        sd.fork()
+        with sd:
+            m.teacher_latent(priv_b, sm, self._lat_t)
         m.student.forward(hist_b, sm, self._lat[:sm], train=True, x_ones=tc)
+        sd.join()
         call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t), ptr(self._dls), ptr(self._acc), sm, D)
         m.student.backward(self._dls, self.load_balance_coef)
         call("go2_cts_log", ptr(self._acc), ptr(m.student.usage) if self._moe else 0, ptr(self._log2), sm * D, m.student.E if self._moe else 1)

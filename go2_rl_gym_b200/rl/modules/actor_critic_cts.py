@@ -301,7 +301,10 @@ class _StudentMoE:
         self.dfeat = z(tr, E * self.H)
         self.usage = torch.zeros(E, device=dev)
         self.Wet = torch.zeros(E * self.H, D, device=dev)   # per expert W_e^T [H, D], stacked
+        self.pool = _ops.StreamPool(dev, 4)                 # the E experts are independent small GEMMs: four lanes, one split-K workspace each
+        self.side = _ops.SideStream(dev)                    # the gate runs next to backbone + experts
         self.work = torch.empty(64 * 128 * (self.H + 4), device=dev)
+        self.works = [self.work] + [torch.empty_like(self.work) for _ in range(self.pool.n - 1)]
         self._dirty = True
         self.train_rows = train_rows
 
@@ -313,17 +316,23 @@ class _StudentMoE:
 
     def forward(self, hist, M, out, train=False, x_ones=False):
         E, D, H = self.E, self.D, self.H
+        self.side.fork()
+        with self.side:
+            self.gate.forward(hist, hist.shape[1], M, self.logits[:M], E, train=train, x_ones=x_ones)
         if self.expert_cols is None:
             self.backbone.forward(hist, hist.shape[1], M, train=train, x_ones=x_ones)
         else:   # the experts see the history without its command columns (gather into a dense buffer; the engine pads it itself)
             torch.index_select(hist[:M], 1, self.expert_cols, out=self._hsel[:M])
             self.backbone.forward(self._hsel, self._hsel.shape[1], M, train=train, x_ones=False)
         feat, ldf = self.backbone.out, self.backbone.ld_out
+        self.pool.fork()
         for e in range(E):  # block-diagonal expert layer = Conv1d(groups=E, kernel 1)
             fn = "go2_linear_forward_tc" if _ops.use_tc() else "go2_linear_forward_simt"
-            call(fn, ptr(feat) + 4 * e * H, ldf, ptr(self.We) + 4 * e * D * H, H, ptr(self.be) + 4 * e * D, ptr(self.eo) + 4 * e * D, E * D, 0, 0,
-                 M, D, H, 0)
-        self.gate.forward(hist, hist.shape[1], M, self.logits[:M], E, train=train, x_ones=x_ones)
+            with self.pool.lane(e):
+                call(fn, ptr(feat) + 4 * e * H, ldf, ptr(self.We) + 4 * e * D * H, H, ptr(self.be) + 4 * e * D, ptr(self.eo) + 4 * e * D, E * D, 0, 0,
+                     M, D, H, 0)
+        self.pool.join()
+        self.side.join()
         call("go2_moe_combine_forward", ptr(self.logits), ptr(self.eo), ptr(self.gates), ptr(self.pre), M, E, D)
         call("go2_l2norm_forward", ptr(self.pre), D, ptr(out), out.stride(0), ptr(self.norm), M, D)
         self._out, self._M = out, M
@@ -342,19 +351,26 @@ class _StudentMoE:
             self._dirty = False
         call("go2_colsum", ptr(self.deo), E * D, ptr(self.gbe), M, E * D, ptr(self.work))
         feat, ldf = self.backbone.out, self.backbone.ld_out
+        self.side.fork()
+        with self.side:
+            self.gate.backward(self.dlogits, E)
+        self.pool.fork()
         for e in range(E):
-            if tc:
-                call("go2_linear_wgrad_tc_rm", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, ldf, ptr(self.gWe) + 4 * e * D * H, H, 0,
-                     M, D, H, ptr(self.work), self.work.numel())
-                call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, ptr(feat) + 4 * e * H, ldf, 0, 0,
-                     ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
-            else:
-                call("go2_linear_wgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, ldf, ptr(self.gWe) + 4 * e * D * H, H, 0,
-                     M, D, H, ptr(self.work), self.work.numel())
-                call("go2_linear_dgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(self.We) + 4 * e * D * H, H, ptr(feat) + 4 * e * H, ldf,
-                     ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
+            work = self.works[e % self.pool.n]
+            with self.pool.lane(e):
+                if tc:
+                    call("go2_linear_wgrad_tc_rm", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, ldf, ptr(self.gWe) + 4 * e * D * H, H, 0,
+                         M, D, H, ptr(work), work.numel())
+                    call("go2_linear_dgrad_tc", ptr(self.deo) + 4 * e * D, E * D, ptr(self.Wet) + 4 * e * H * D, D, ptr(feat) + 4 * e * H, ldf, 0, 0,
+                         ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
+                else:
+                    call("go2_linear_wgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(feat) + 4 * e * H, ldf, ptr(self.gWe) + 4 * e * D * H, H, 0,
+                         M, D, H, ptr(work), work.numel())
+                    call("go2_linear_dgrad_simt", ptr(self.deo) + 4 * e * D, E * D, ptr(self.We) + 4 * e * D * H, H, ptr(feat) + 4 * e * H, ldf,
+                         ptr(self.dfeat) + 4 * e * H, E * H, 0, 0, M, D, H)
+        self.pool.join()
         self.backbone.backward(self.dfeat, E * H)
-        self.gate.backward(self.dlogits, E)
+        self.side.join()
 
 
 class ActorCriticMoECTS(_CTSBase):
