@@ -69,7 +69,9 @@ class CTS:
         self.exp_avg, self.exp_avg_sq = z(m.flat_params.numel()), z(m.flat_params.numel())
         self._lr1, self._lr2 = z(4), z(4)
         self._lr1[0], self._lr2[0] = float(self.learning_rate), float(self.student_encoder_learning_rate)
-        self._scal, self._log, self._log2 = z(20), z(5), z(2)
+        # env-sharded over GPUs: symmetric gradient buffer + the library's NVLink all-reduce kernel (see PPO.init_storage)
+        self._red = dist_utils.reducer_for(m.flat_grads) if self.world_size > 1 else None
+        self._scal, self._log, self._log2 = (self._red.tail if self._red is not None else z(20)), z(5), z(2)
         self._scratch, self._acc = z(1025), z(1)
         rows = max(N, self.mb)
         self._lat = z(rows, D)
@@ -198,8 +200,8 @@ class CTS:
         self._log.zero_(); self._log2.zero_()
         if self.world_size == 1:
             self._graphs.run("update", self._update_body)
-        elif self._dist_graph and "update_dist" not in self._graphs._failed:
-            self._graphs.run("update_dist", self._update_body_dist)       # both passes with their NCCL all-reduces as one CUDA graph
+        elif (self._red is not None or self._dist_graph) and "update_dist" not in self._graphs._failed:
+            self._graphs.run("update_dist", self._update_body_dist)       # both passes with their gradient exchanges as one CUDA graph
         else:
             ws, n1, G = self.world_size, m.n1, m.flat_grads
             for epoch in range(self.num_learning_epochs):
@@ -254,14 +256,20 @@ class CTS:
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self._grad1(i)
-                self._comm1 = dist_utils.allreduce_grads_and_tail(G[:n1], self._scal, getattr(self, "_comm1", None))
+                if self._red is not None:
+                    self._red.allreduce(0, dist_utils.TAIL + n1)          # [scalar tail | pass-1 gradient] in one launch
+                else:
+                    self._comm1 = dist_utils.allreduce_grads_and_tail(G[:n1], self._scal, getattr(self, "_comm1", None))
                 self._step1()
         if self.sm == 0:
             return
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self._grad2(i)
-                dist.all_reduce(G[n1:])
+                if self._red is not None:
+                    self._red.allreduce(dist_utils.TAIL + n1, m.n2)
+                else:
+                    dist.all_reduce(G[n1:])
                 self._step2()
 
     def _grad1(self, i):
@@ -289,9 +297,11 @@ class CTS:
     def _step1(self):
         m, ws = self.model, self.world_size
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
-        call("go2_kl_adaptive_lr", ptr(self._scal), float(self.mb * ws), float(self.desired_kl) if adaptive else -1.0, ptr(self._lr1), ptr(self._log),
+        red = self._red      # the exchanged sums (same layout) when the gradient went through the NVLink all-reduce kernel
+        scal, grads = (red.out_tail, red.out_grads) if red is not None else (self._scal, m.flat_grads)
+        call("go2_kl_adaptive_lr", ptr(scal), float(self.mb * ws), float(self.desired_kl) if adaptive else -1.0, ptr(self._lr1), ptr(self._log),
              float(self.tm * ws), float(max(self.sm, 1) * ws))
-        call("go2_adam_clip_step", ptr(m.flat_params), ptr(m.flat_grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), m.n1, self.max_grad_norm, ptr(self._lr1),
+        call("go2_adam_clip_step", ptr(m.flat_params), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), m.n1, self.max_grad_norm, ptr(self._lr1),
              1.0, ptr(self._scratch))
         for e in m.pass1_engines():
             e.mark_dirty()
@@ -315,7 +325,8 @@ class CTS:
     def _step2(self):
         m, n1 = self.model, self.model.n1
         # with world_size > 1 the gradient arrives SUM-reduced: fold the 1/world_size of the mean loss into the step
-        call("go2_adam_clip_step", ptr(m.flat_params) + 4 * n1, ptr(m.flat_grads) + 4 * n1, ptr(self.exp_avg) + 4 * n1, ptr(self.exp_avg_sq) + 4 * n1, m.n2,
+        grads = self._red.out_grads if self._red is not None else m.flat_grads
+        call("go2_adam_clip_step", ptr(m.flat_params) + 4 * n1, ptr(grads) + 4 * n1, ptr(self.exp_avg) + 4 * n1, ptr(self.exp_avg_sq) + 4 * n1, m.n2,
              self.max_grad_norm, ptr(self._lr2), 1.0 / self.world_size, ptr(self._scratch))
         for e in m.student.engines():
             e.mark_dirty()

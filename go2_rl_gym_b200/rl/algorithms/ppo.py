@@ -69,10 +69,14 @@ class PPO:
         self.exp_avg_sq = torch.zeros(n, device=dev)
         self._lr = torch.zeros(4, device=dev)      # {lr, optimiser step, Adam bias corrections} — device resident
         self._lr[0] = float(self.learning_rate)
+        # env-sharded over GPUs: the flat gradient lives in a symmetric buffer and the per-step exchange is the library's own NVLink kernel
+        # (dist_utils.P2PReducer), so the 20 optimiser steps and their exchanges replay as ONE graph; otherwise (gloo, no peer access) NCCL / gloo
+        # all-reduces between graph segments
+        self._red = dist_utils.reducer_for(ac.flat_grads) if self.world_size > 1 else None
         self._graphs = _ops.GraphSet()
         self._side = _ops.SideStream(dev)          # the critic's chain runs next to the actor's (see _ops.SideStream)
         self._join_pending = False
-        self._scal = torch.zeros(20, device=dev)
+        self._scal = self._red.tail if self._red is not None else torch.zeros(20, device=dev)
         self._log = torch.zeros(5, device=dev)
         self._scratch = torch.zeros(1025, device=dev)
         self._dmu = torch.empty(self.mini_batch_size, action_shape[0], device=dev)
@@ -166,7 +170,7 @@ class PPO:
         self._sh, self._total, self._tc = sh, total, tc
         if self.world_size == 1:
             self._graphs.run("update", self._update_body)
-        elif self._dist_graph and "update_dist" not in self._graphs._failed:
+        elif (self._red is not None or self._dist_graph) and "update_dist" not in self._graphs._failed:
             # the 20 optimiser steps INCLUDING their NCCL all-reduces as one CUDA graph (NCCL collectives are capturable); a failed capture
             # falls back to the segmented path below for the rest of the run
             self._graphs.run("update_dist", self._update_body_dist)
@@ -230,14 +234,19 @@ class PPO:
         ac = self.actor_critic
         mb = self.mini_batch_size
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
-        _ops.call("go2_kl_adaptive_lr", _ops.ptr(self._scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
+        red = self._red         # the exchanged sums (same layout) when the gradient went through the NVLink all-reduce kernel
+        scal, grads = (red.out_tail, red.out_grads) if red is not None else (self._scal, ac.flat_grads)
+        _ops.call("go2_kl_adaptive_lr", _ops.ptr(scal), float(mb * self.world_size), float(self.desired_kl) if adaptive else -1.0,
                   _ops.ptr(self._lr), _ops.ptr(self._log), float(mb * self.world_size), 1.0)
-        _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(ac.flat_grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
+        _ops.call("go2_adam_clip_step", _ops.ptr(ac.flat_params), _ops.ptr(grads), _ops.ptr(self.exp_avg), _ops.ptr(self.exp_avg_sq),
                   ac.flat_params.numel(), self.max_grad_norm, _ops.ptr(self._lr), 1.0, _ops.ptr(self._scratch))
         ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
 
     def _allreduce_grads(self):
-        self._comm = dist_utils.allreduce_grads_and_tail(self.actor_critic.flat_grads, self._scal[:4], getattr(self, "_comm", None))
+        if self._red is not None:
+            self._red.allreduce(0, dist_utils.TAIL + self._red.n)       # [scalar tail | flat gradient] in one launch
+        else:
+            self._comm = dist_utils.allreduce_grads_and_tail(self.actor_critic.flat_grads, self._scal[:4], getattr(self, "_comm", None))
 
     # ---- checkpoint interop (torch.optim.Adam layout, ppo.py:67) ---------------------------------------------
     def optimizer_state_dict(self):

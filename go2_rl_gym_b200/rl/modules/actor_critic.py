@@ -7,7 +7,7 @@ autograd: gradients land in a second flat vector that the fused clip+Adam kernel
 import torch
 import torch.nn as nn
 
-from .. import _ops
+from .. import _ops, dist_utils
 
 
 def _mlp(dims):
@@ -45,7 +45,7 @@ class ActorCritic(nn.Module):
         """Move to `device`, re-home every parameter inside one flat vector (parameters() order: std, actor.*, critic.*)."""
         n = sum((p.numel() + 3) // 4 * 4 for p in self.parameters())     # every parameter starts 16-byte aligned (TMA operand rule)
         flat = torch.zeros(n, device=device, dtype=torch.float32)
-        grad = torch.zeros(n, device=device, dtype=torch.float32)
+        grad = dist_utils.new_flat_grad(n, device)        # a symmetric (peer-mapped) buffer when the envs are sharded over GPUs
         off = 0
         self._views, self._gviews, self._offsets = {}, {}, {}
         for name, p in self.named_parameters():

@@ -8,7 +8,7 @@ and every forward / backward evaluated by the library's kernels (GEMMs on tcgen0
 import torch
 import torch.nn as nn
 
-from .. import _ops
+from .. import _ops, dist_utils
 from .._ops import call, ptr
 
 
@@ -81,7 +81,7 @@ class _CTSBase(nn.Module):
         n1 = sum((named[k].numel() + 3) // 4 * 4 for k in seg1)     # every parameter starts 16-byte aligned (TMA operand rule);
         n2 = sum((named[k].numel() + 3) // 4 * 4 for k in seg2)     # the padding stays zero (zero gradient -> Adam leaves it at zero)
         flat = torch.zeros(n1 + n2, device=device)
-        grad = torch.zeros(n1 + n2, device=device)
+        grad = dist_utils.new_flat_grad(n1 + n2, device)    # a symmetric (peer-mapped) buffer when the envs are sharded over GPUs
         self._views, self._gviews, self._offsets, off = {}, {}, {}, 0
         for k in seg1 + seg2:
             p = named[k]

@@ -270,6 +270,13 @@ int go2_gemm_set_pdl(int on);
    4 .. for TMA bytes, 5 .. for the lo slot, 6 stages processed; 7 splitter waiting for TMA bytes, 8 .. for a free lo slot, 9 splitter busy (incl. 8);
    10/11 and 12/13 epilogue group 0 / 1 total and waiting for an accumulator, 14 / 15 .. for the ELU' operand (dgrad).  NULL (default) disables it. */
 int go2_gemm_set_debug(long long* counters);
+/* One-shot SUM all-reduce over NVLink peer memory (csrc/dist_kernels.cu), the data-parallel trainer's per-optimiser-step exchange — replaces the
+   reference's single-process optimizer.step() boundary (rsl_rl/algorithms/ppo.py:183-185) when the envs are sharded over GPUs:
+   out[off .. off+n) = sum_r peer_data[r][off .. off+n), same summation order on every rank.  peer_data / peer_flags are HOST arrays of `world`
+   device pointers (this process's mappings of every rank's symmetric buffer / 16-word zeroed flag block, index = rank); ctr = 2 zeroed uint32
+   words of this rank.  off, n multiples of 4 floats.  Collective: every rank calls it with the same arguments in the same order; capturable. */
+int go2_allreduce_p2p(const float* const* peer_data, uint32_t* const* peer_flags, float* out, long off, long n, int rank, int world, uint32_t* ctr,
+                      void* stream);
 /* db[N] = column sums of dY[M,N] */
 int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */

@@ -39,6 +39,6 @@ dist.all_gather(allc, chk)
 same = all(torch.equal(allc[0], c) for c in allc)
 if rank == 0:
     g = runner.alg._graphs
-    print(f"task {a.task} world {world} dist_graph {os.environ.get('GO2_DIST_GRAPH', '1')} graphs {sorted(map(str, g._g))} failed {sorted(map(str, g._failed))} "
+    print(f"task {a.task} world {world} p2p {getattr(runner.alg, '_red', None) is not None} dist_graph {os.environ.get('GO2_DIST_GRAPH', '0')} graphs {sorted(map(str, g._g))} failed {sorted(map(str, g._failed))} "
           f"ms/iter {1e3 * sum(t[2:]) / len(t[2:]):.2f} checksum {[f'{float(x):.9e}' for x in chk]} ranks_identical {same} losses {[round(float(x), 5) for x in losses]} lr {runner.alg.learning_rate:.3e}", flush=True)
 dist.destroy_process_group()
