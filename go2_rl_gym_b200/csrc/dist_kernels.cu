@@ -52,14 +52,30 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const P2PPeers peers
     while ((int32_t)(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {}           // every peer's gradient is complete
   }
   __syncthreads();
+  // four vectors per thread and trip: 4 x W independent peer loads in flight before the first add (a peer load is a ~2 us NVLink round trip)
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 acc = ld_peer(peers.data[0] + off + 4 * i);
-    for (int r = 1; r < W; ++r) {
-      const float4 v = ld_peer(peers.data[r] + off + 4 * i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long i = i0 + u * stride;
+      acc[u] = i < n4 ? ld_peer(peers.data[0] + off + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<float4*>(out + off + 4 * i) = acc;
+    for (int r = 1; r < W; ++r) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long i = i0 + u * stride;
+        v[u] = i < n4 ? ld_peer(peers.data[r] + off + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long i = i0 + u * stride;
+      if (i < n4) *reinterpret_cast<float4*>(out + off + 4 * i) = acc[u];
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -50,10 +50,6 @@ class P2PReducer:
         assert n % 4 == 0
         self.n = n
         group = dist.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:      # noqa: BLE001 - newer torch enables it implicitly
-            pass
         self.buf = symm.empty(TAIL + n + _FLAGS, dtype=torch.float32, device=device)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group.group_name)
