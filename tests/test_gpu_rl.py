@@ -410,3 +410,40 @@ def test_go2_learns_on_the_gpu():
     assert last["len"] > 850 and last["ret"] > 2.0, last
     assert last["rew_step"] > first["rew_step"] + 0.03 and last["std"] < 0.7   # reward per step up from ~-0.055, action noise annealed
     assert all(r["lr"] >= 1e-5 - 1e-12 and r["lr"] <= 1e-2 + 1e-12 for r in rows)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_p2p_allreduce_kernel_protocol(world):
+    """csrc/dist_kernels.cu on ONE GPU: `world` buffers play the ranks' symmetric buffers (every 'peer' pointer is local), each rank's kernel runs on its
+    own stream, all co-resident, so the ready / done flag protocol, the epoch counter and the rank-ordered sums are exercised for several exchanges in
+    a row — including a slice exchange (CTS pass 2) and a rank that arrives late.  Every rank must hold the bit-identical sum."""
+    import ctypes as C
+    from go2_rl_gym_b200.rl import _ops
+    n, TAIL, FL = 4096 * 12 + 8, 32, 32
+    g = torch.Generator(device="cuda").manual_seed(world)
+    bufs = [torch.zeros(TAIL + n + FL, device="cuda") for _ in range(world)]
+    outs = [torch.zeros(TAIL + n, device="cuda") for _ in range(world)]
+    ctrs = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(world)]
+    data = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    flags = (C.c_void_p * world)(*[b.data_ptr() + 4 * (TAIL + n) for b in bufs])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for it, (off, cnt) in enumerate([(0, TAIL + n), (0, TAIL + n), (TAIL + 1024, n - 1024), (0, TAIL + 4096)]):
+        for b in bufs:
+            b[:TAIL + n].copy_(torch.randn(TAIL + n, device="cuda", generator=g))
+        for o in outs:
+            o.fill_(-7.0)
+        torch.cuda.synchronize()
+        for r in reversed(range(world)):          # the last rank launches first, rank 0 after a delay
+            with torch.cuda.stream(streams[r]):
+                if r == 0:
+                    torch.cuda._sleep(2_000_000)
+                _ops.call("go2_allreduce_p2p", data, flags, outs[r].data_ptr(), off, cnt, r, world, ctrs[r].data_ptr())
+        torch.cuda.synchronize()
+        ref = bufs[0][off:off + cnt].clone()
+        for b in bufs[1:]:
+            ref += b[off:off + cnt]               # same order as the kernel: rank 0, 1, ...
+        for r in range(world):
+            assert torch.equal(outs[r][off:off + cnt], ref), (it, r)
+            assert (outs[r][:off] == -7.0).all() and (outs[r][off + cnt:] == -7.0).all()      # nothing outside the slice was touched
+            assert ctrs[r].tolist() == [it + 1, 0]
