@@ -45,7 +45,7 @@ def workload_config(task, num_envs, world):
     return {"workload": f"{task} rough-terrain heightfield, num_envs={num_envs} per GPU, PPO iteration (24 steps + {upd})",
             "task": task, "num_envs_per_gpu": num_envs, "n_gpus": world,
             "l2": "per-iteration working set ~300 MB > 126 MB L2",
-            "parallelism": f"env-sharded dp{world}, NCCL all-reduce per optimiser step"}
+            "parallelism": f"env-sharded dp{world}, one gradient all-reduce per optimiser step (own NVLink peer-memory kernel inside the update graph)"}
 
 
 def _peaks():
@@ -382,9 +382,10 @@ def _main(out):
         Yg = torch.empty(Mg, Ng, device=dev)
         flush = torch.empty(64 * 1024 * 1024, device=dev)                    # 256 MB > 126 MB L2, rewritten between launches
         run = lambda: _ops.call("go2_linear_forward_tc", Xg.data_ptr(), Kg, Wg.data_ptr(), Kg, bg.data_ptr(), Yg.data_ptr(), Ng, 0, 0, Mg, Ng, Kg, 1)
-        us_by_passes = {}
-        for pz in (1, 3):
-            _ops.lib().go2_gemm_set_passes(pz)
+        us_by_mode = {}
+        L_ = _ops.lib()
+        for mode, pz, pair in (("tf32", 1, 0), ("3xtf32_pair", 3, 1), ("3xtf32_1cta", 3, 0)):
+            L_.go2_gemm_set_passes(pz); L_.go2_gemm_set_pair(pair)
             for _ in range(3):
                 run()
             tot = 0.0
@@ -394,19 +395,21 @@ def _main(out):
                 g0.record(); run(); g1.record()
                 torch.cuda.synchronize()
                 tot += g0.elapsed_time(g1)
-            us_by_passes[pz] = tot / 10 * 1e3
-        _ops.lib().go2_gemm_set_passes(passes)
-        us = us_by_passes[passes]
+            us_by_mode[mode] = tot / 10 * 1e3
+        L_.go2_gemm_set_passes(passes); L_.go2_gemm_set_pair(1)
+        us = us_by_mode["3xtf32_pair" if passes == 3 else "tf32"]
         gbytes = 4.0 * (Mg * Kg + Ng * Kg + Mg * Ng)                 # ALGORITHMIC bytes: operands read once, ONE output written once
         tfl = 2.0 * Mg * Ng * Kg / us / 1e6
-        tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-        gemm = {"kernel": f"go2::gemm_tf32_persist_kernel<128,{'true' if passes == 3 else 'false'}> (Y = ELU(X W^T + b), critic layer 0 forward)",
-                "shape": [Mg, Ng, Kg], "passes": passes, "bound": "hbm", "achieved": gbytes / us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbytes / us / 1e3 / peaks["hbm_gbs"], "kernel_us": us, "kernel_us_single_tf32_pass": us_by_passes[1],
-                "tflops": tfl, "tflops_frac_of_bf16_sustained": tfl / tpeak if tpeak else None,
-                "tensor_flops_issued": tfl * passes,
-                "note": "algorithmic bytes = operands once + one output (76.8 MB at 4096 envs); fp32 activations make every MLP GEMM of the update "
-                        "HBM / L2 bound (33 flop/B); L2 flushed between launches; tflops = useful fp32-class flops, x passes issued on the tensor cores"}
+        tpeak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained"))      # a kernel timed alone: the burst figure
+        kname = "go2::gemm_tf32_pair_kernel<256,true> (tcgen05.mma.cta_group::2, 3xTF32)" if passes == 3 else "go2::gemm_tf32_persist_kernel<128,false>"
+        gemm = {"kernel": f"{kname} (Y = ELU(X W^T + b), critic layer 0 forward)",
+                "shape": [Mg, Ng, Kg], "passes": passes, "bound": "tensor", "achieved": tfl * passes, "peak": tpeak / 2 if tpeak else None, "unit": "TFLOP/s",
+                "frac": (tfl * passes) / (tpeak / 2) if tpeak else None, "kernel_us": us, "kernel_us_by_mode": us_by_mode,
+                "useful_tflops": tfl, "hbm_gbs": gbytes / us / 1e3, "hbm_frac": gbytes / us / 1e3 / peaks["hbm_gbs"],
+                "note": "tf32 runs at half the bf16 tensor rate: peak = MEASURED_PEAKS bf16_tflops (burst, kernel timed alone) / 2; achieved = tensor flops ISSUED (3 MMAs per operand pair), "
+                        "useful_tflops = fp32-class product flops.  Measured bound (profiles/r02*_gemm_*): shared-memory bandwidth of the operand stream "
+                        "(128 B/clk/SM) — a 128x128x8 tf32 MMA reads 8 KB per 64 cycles; CTA pairs halve it.  hbm_* = algorithmic bytes (operands once + "
+                        "one output, 76.8 MB at 4096 envs); L2 flushed between launches"}
         del Xg, Wg, bg, Yg, flush
     traffic, issue_active = None, None
     try:   # ncu --set full capture of the step kernel of this build at this size (profiles/): dram bytes per launch, issue-slot utilisation
