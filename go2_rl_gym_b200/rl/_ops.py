@@ -45,6 +45,7 @@ _SIGS = {
     "go2_mcp_compose_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _i, _vp],
     "go2_sample_actions_sigma": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_uint64, C.c_uint32, _vp, _i, _vp],
     "go2_allreduce_p2p": [_vp, _vp, _vp, _l, _l, _i, _i, _vp, _vp],
+    "go2_allreduce_p2p2": [_vp, _vp, _vp, _vp, _l, _l, _i, _i, _vp, _vp],
     "go2_ppo_loss_sigma": [_vp] * 14 + [_i, _i, _f, _f, _f, _i, _f, _i, _f, _f, _vp],
 }
 _lib = None

@@ -50,24 +50,26 @@ class P2PReducer:
         assert n % 4 == 0
         self.n = n
         group = dist.group.WORLD
-        self.buf = symm.empty(TAIL + n + _FLAGS, dtype=torch.float32, device=device)
+        m = TAIL + n
+        self.buf = symm.empty(2 * m + _FLAGS, dtype=torch.float32, device=device)      # [tail | gradient] [result, same layout] [flags]
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group.group_name)
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self._data = (C.c_void_p * self.world)(*ptrs)
-        self._flags = (C.c_void_p * self.world)(*[p + 4 * (TAIL + n) for p in ptrs])
-        self.out = torch.zeros(TAIL + n, device=device)
+        self._out = (C.c_void_p * self.world)(*[p + 4 * m for p in ptrs])
+        self._flags = (C.c_void_p * self.world)(*[p + 8 * m for p in ptrs])
+        self.out = self.buf[m:2 * m]                    # symmetric too: with >= 4 ranks every rank sums one slice and stores it into all results
         self.ctr = torch.zeros(2, dtype=torch.int32, device=device)
-        self.tail, self.grads = self.buf[:TAIL], self.buf[TAIL:TAIL + n]
-        self.out_tail, self.out_grads = self.out[:TAIL], self.out[TAIL:TAIL + n]
+        self.tail, self.grads = self.buf[:TAIL], self.buf[TAIL:m]
+        self.out_tail, self.out_grads = self.out[:TAIL], self.out[TAIL:m]
         torch.cuda.synchronize(device)
         dist.barrier()          # every rank's flag words are zero before any peer can write them
 
     def allreduce(self, off, n):
         """out[off : off + n] = sum over ranks of buf[off : off + n] (float offsets into [tail | gradient]); collective, capturable."""
         from . import _ops
-        _ops.call("go2_allreduce_p2p", self._data, self._flags, self.out.data_ptr(), off, n, self.rank, self.world, self.ctr.data_ptr())
+        _ops.call("go2_allreduce_p2p2", self._data, self._flags, self._out, self.out.data_ptr(), off, n, self.rank, self.world, self.ctr.data_ptr())
 
 
 def new_flat_grad(n, device):

@@ -277,6 +277,10 @@ int go2_gemm_set_debug(long long* counters);
    words of this rank.  off, n multiples of 4 floats.  Collective: every rank calls it with the same arguments in the same order; capturable. */
 int go2_allreduce_p2p(const float* const* peer_data, uint32_t* const* peer_flags, float* out, long off, long n, int rank, int world, uint32_t* ctr,
                       void* stream);
+/* The same exchange with the result buffers symmetric as well (peer_out: HOST array of `world` device pointers, peer_out[rank] == out): with
+   world >= 4 it runs two-shot — rank r sums slice r only (1/world of the peer reads) and stores it into every rank's result. */
+int go2_allreduce_p2p2(const float* const* peer_data, uint32_t* const* peer_flags, float* const* peer_out, float* out, long off, long n, int rank,
+                       int world, uint32_t* ctr, void* stream);
 /* db[N] = column sums of dY[M,N] */
 int go2_colsum(const float* dY, int lddy, float* db, int M, int N, float* scratch /* >= 64*N floats */, void* stream);
 /* PPO.act tail (ppo.py:94-101): actions = mu + std z (Philox normal), log-prob, mu/sigma rows of the transition */

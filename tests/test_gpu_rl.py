@@ -412,11 +412,12 @@ def test_go2_learns_on_the_gpu():
     assert all(r["lr"] >= 1e-5 - 1e-12 and r["lr"] <= 1e-2 + 1e-12 for r in rows)
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_p2p_allreduce_kernel_protocol(world):
+@pytest.mark.parametrize("world,two_shot", [(1, False), (2, False), (4, False), (4, True), (8, True)])
+def test_p2p_allreduce_kernel_protocol(world, two_shot):
     """csrc/dist_kernels.cu on ONE GPU: `world` buffers play the ranks' symmetric buffers (every 'peer' pointer is local), each rank's kernel runs on its
     own stream, all co-resident, so the ready / done flag protocol, the epoch counter and the rank-ordered sums are exercised for several exchanges in
-    a row — including a slice exchange (CTS pass 2) and a rank that arrives late.  Every rank must hold the bit-identical sum."""
+    a row — including a slice exchange (CTS pass 2) and a rank that arrives late.  Every rank must hold the bit-identical sum.  two_shot: the
+    result buffers are handed over as well, so each rank sums one slice and stores it into every rank's result (the >= 4 rank schedule)."""
     import ctypes as C
     from go2_rl_gym_b200.rl import _ops
     n, TAIL, FL = 4096 * 12 + 8, 32, 32
@@ -426,6 +427,7 @@ def test_p2p_allreduce_kernel_protocol(world):
     ctrs = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(world)]
     data = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
     flags = (C.c_void_p * world)(*[b.data_ptr() + 4 * (TAIL + n) for b in bufs])
+    peer_out = (C.c_void_p * world)(*[o.data_ptr() for o in outs]) if two_shot else None
     streams = [torch.cuda.Stream() for _ in range(world)]
     torch.cuda.synchronize()
     for it, (off, cnt) in enumerate([(0, TAIL + n), (0, TAIL + n), (TAIL + 1024, n - 1024), (0, TAIL + 4096)]):
@@ -438,7 +440,7 @@ def test_p2p_allreduce_kernel_protocol(world):
             with torch.cuda.stream(streams[r]):
                 if r == 0:
                     torch.cuda._sleep(2_000_000)
-                _ops.call("go2_allreduce_p2p", data, flags, outs[r].data_ptr(), off, cnt, r, world, ctrs[r].data_ptr())
+                _ops.call("go2_allreduce_p2p2", data, flags, peer_out, outs[r].data_ptr(), off, cnt, r, world, ctrs[r].data_ptr())
         torch.cuda.synchronize()
         ref = bufs[0][off:off + cnt].clone()
         for b in bufs[1:]:
