@@ -82,7 +82,7 @@ __global__ void moe_combine_fwd_kernel(const float* __restrict__ logits, const f
   }
 }
 // column means of the gates (mean usage, moe_cts.py:211) : one block per expert
-__global__ void __launch_bounds__(256) gate_usage_kernel(const float* __restrict__ gates, float* __restrict__ usage, long n, int E) {
+__global__ void __launch_bounds__(256) gate_usage_kernel(const float* __restrict__ gates, float* __restrict__ usage, long n, int E, float scale = 1.0f) {
   __shared__ float red[256];
   const int e = blockIdx.x;
   float s = 0;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) gate_usage_kernel(const float* __restrict
   red[threadIdx.x] = s;
   __syncthreads();
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
-  if (threadIdx.x == 0) usage[e] = red[0] / (float)n;
+  if (threadIdx.x == 0) usage[e] = red[0] / (float)n * scale;
 }
 // backward of the combine + softmax + load-balance term.  dpre [n,D] -> deo [n,E*D] (+ transposed), dlogits [n,E] (+ transposed)
 __global__ void moe_combine_bwd_kernel(const float* __restrict__ dpre, const float* __restrict__ gates, const float* __restrict__ eo,
@@ -205,6 +205,25 @@ int go2_moe_combine_backward(const float* dpre, const float* gates, const float*
   gate_usage_kernel<<<E, 256, 0, st>>>(gates, usage, n, E);
   count_launch();
   moe_combine_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dpre, gates, expert_out, usage, lb_coef, dexpert_out, dexpert_out_t, dlogits, dlogits_t, n, E, D);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// The two halves of go2_moe_combine_backward for the env-sharded trainer: the mean gate usage of THIS rank's rows times `scale` (1 / world_size),
+// summed over the ranks by the caller (go2_allreduce_p2p2), then the backward with the GLOBAL usage — the load-balance term of moe_cts.py:211-214
+// is a function of the whole mini-batch's mean usage, not of one shard's.
+int go2_gate_usage(const float* gates, float* usage, long n, int E, float scale, void* stream) {
+  if (E > 16) return set_error(1, "go2_gate_usage: at most 16 experts");
+  gate_usage_kernel<<<E, 256, 0, (cudaStream_t)stream>>>(gates, usage, n, E, scale);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int go2_moe_combine_backward_given_usage(const float* dpre, const float* gates, const float* expert_out, const float* usage, float lb_coef,
+                                         float* dexpert_out, float* dexpert_out_t, float* dlogits, float* dlogits_t, long n, int E, int D, void* stream) {
+  if (E > 16) return set_error(1, "go2_moe_combine_backward_given_usage: at most 16 experts");
+  moe_combine_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dpre, gates, expert_out, usage, lb_coef, dexpert_out, dexpert_out_t,
+                                                                                     dlogits, dlogits_t, n, E, D);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -36,6 +36,8 @@ _SIGS = {
     "go2_l2norm_backward": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _l, _i, _vp],
     "go2_moe_combine_forward": [_vp, _vp, _vp, _vp, _l, _i, _i, _vp],
     "go2_moe_combine_backward": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _l, _i, _i, _vp],
+    "go2_gate_usage": [_vp, _vp, _l, _i, _f, _vp],
+    "go2_moe_combine_backward_given_usage": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _l, _i, _i, _vp],
     "go2_latent_loss": [_vp, _vp, _vp, _vp, _l, _i, _vp],
     "go2_cts_log": [_vp, _vp, _vp, _l, _i, _vp],
     "go2_history_update": [_vp, _vp, _vp, _l, _i, _i, _vp],

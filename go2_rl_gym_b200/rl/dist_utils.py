@@ -89,3 +89,36 @@ def new_flat_grad(n, device):
 
 def reducer_for(flat_grads):
     return _reducers.get(flat_grads.data_ptr())
+
+
+class SmallSum:
+    """SUM of a short vector over the ranks in the middle of a backward pass (the mixture layers' mean gate usage): the NVLink kernel over its own
+    tiny symmetric buffer when the gradient exchange uses it too (capturable), a plain dist.all_reduce with gloo (CPU tests).  `inp` is written by
+    the caller, reduce() returns the tensor that holds the sums.  make_small_sum() -> None when there is nothing to sum (one process) or when the
+    only collective available is NCCL between graph segments (each rank then keeps its own shard's usage, as before)."""
+
+    def __init__(self, n, device, red):
+        self.n, self.red = n, red
+        self.inp = red.grads[:n] if red is not None else torch.zeros(n, device=device)
+
+    def reduce(self):
+        if self.red is not None:
+            self.red.allreduce(TAIL, (self.n + 3) // 4 * 4)
+            return self.red.out_grads[:self.n]
+        dist.all_reduce(self.inp)
+        return self.inp
+
+
+def make_small_sum(n, device):
+    if world_size() == 1:
+        return None
+    dev = torch.device(device)
+    if dev.type == "cuda" and dist.get_backend() == "nccl":
+        if os.environ.get("GO2_DIST_P2P", "1") == "0":
+            return None
+        try:
+            return SmallSum(n, dev, P2PReducer((n + 3) // 4 * 4, dev))
+        except Exception as e:      # noqa: BLE001
+            warnings.warn(f"symmetric-memory exchange unavailable for the gate usage ({type(e).__name__}: {e}); per-rank usage")
+            return None
+    return SmallSum(n, dev, None)

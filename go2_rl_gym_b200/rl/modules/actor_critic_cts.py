@@ -240,6 +240,17 @@ class _CTSBase(nn.Module):
         return out.clone()
 
 
+def combine_backward(mod, dpre, gates, eo, lb_coef, deo, dlogits, M, E, D):
+    """go2_moe_combine_backward with the mean gate usage taken over ALL ranks' rows when the envs are sharded (mod.usage_sum: dist_utils.SmallSum)."""
+    us = getattr(mod, "usage_sum", None)
+    if us is None or lb_coef == 0.0:
+        call("go2_moe_combine_backward", ptr(dpre), ptr(gates), ptr(eo), ptr(mod.usage), float(lb_coef), ptr(deo), 0, ptr(dlogits), 0, M, E, D)
+        return
+    call("go2_gate_usage", ptr(gates), ptr(us.inp), M, E, 1.0 / dist_utils.world_size())
+    mod.usage.copy_(us.reduce())
+    call("go2_moe_combine_backward_given_usage", ptr(dpre), ptr(gates), ptr(eo), ptr(mod.usage), float(lb_coef), ptr(deo), 0, ptr(dlogits), 0, M, E, D)
+
+
 class _StudentMLP:
     """Plain student encoder: MLP + L2Norm (actor_critic_cts.py:73-89)."""
 
@@ -300,6 +311,7 @@ class _StudentMoE:
         self.dlogits = z(tr, E)
         self.dfeat = z(tr, E * self.H)
         self.usage = torch.zeros(E, device=dev)
+        self.usage_sum = dist_utils.make_small_sum(E, dev) if train_rows else None      # env-sharded: the load-balance term sees the global mean usage
         self.Wet = torch.zeros(E * self.H, D, device=dev)   # per expert W_e^T [H, D], stacked
         self.pool = _ops.StreamPool(dev, 4)                 # the E experts are independent small GEMMs: four lanes, one split-K workspace each
         self.side = _ops.SideStream(dev)                    # the gate runs next to backbone + experts
@@ -341,8 +353,7 @@ class _StudentMoE:
         E, D, H, M, tr = self.E, self.D, self.H, self._M, self.train_rows
         tc = _ops.use_tc()
         call("go2_l2norm_backward", ptr(dlatent), D, ptr(self._out), self._out.stride(0), ptr(self.norm), ptr(self.dpre), D, 0, M, D)
-        call("go2_moe_combine_backward", ptr(self.dpre), ptr(self.gates), ptr(self.eo), ptr(self.usage), float(lb_coef), ptr(self.deo), 0,
-             ptr(self.dlogits), 0, M, E, D)
+        combine_backward(self, self.dpre, self.gates, self.eo, lb_coef, self.deo, self.dlogits, M, E, D)
         if self._dirty and tc:      # W_e^T of the 8 experts in one launch
             import ctypes as C
             vp, ia = (C.c_void_p * E), (C.c_int * E)
@@ -599,6 +610,7 @@ class _MoEHead:
         self.logits, self.gates = torch.empty(max_rows, E, device=dev), torch.empty(max_rows, E, device=dev)
         self.dlogits, self.deo = torch.empty(tr, E, device=dev), torch.empty(tr, E * D, device=dev)
         self.usage = torch.zeros(E, device=dev)
+        self.usage_sum = dist_utils.make_small_sum(E, dev) if train_rows else None      # env-sharded: the load-balance term sees the global mean usage
 
     def engines(self):
         """Everything that keeps operand copies derived from the weights (refreshed after an optimiser step)."""
@@ -619,8 +631,7 @@ class _MoEHead:
         """dout [M, D] dense.  lb_coef: load-balance term on the mean gate usage of these M rows (ac_moe_cts.py:226-228).  extra_dlogits: the
         gate's gradient from another consumer of the same gates (the critic's weighted value), already through the softmax."""
         M, E, D = self._M, self.E, self.D
-        call("go2_moe_combine_backward", ptr(dout), ptr(self.gates), ptr(self.layer.out), ptr(self.usage), float(lb_coef), ptr(self.deo), 0,
-             ptr(self.dlogits), 0, M, E, D)
+        combine_backward(self, dout, self.gates, self.layer.out, lb_coef, self.deo, self.dlogits, M, E, D)
         if extra_dlogits is not None:
             self.dlogits[:M].add_(extra_dlogits[:M])
         self.layer.backward(self.deo, self.backbone.out, self.backbone.ld_out, M)

@@ -319,6 +319,12 @@ int go2_l2norm_backward(const float* dy, int lddy, const float* y, int ldy, cons
 int go2_moe_combine_forward(const float* logits, const float* expert_out, float* gates, float* pre, long n, int E, int D, void* stream);
 int go2_moe_combine_backward(const float* dpre, const float* gates, const float* expert_out, float* usage, float lb_coef, float* dexpert_out,
                              float* dexpert_out_t, float* dlogits, float* dlogits_t, long n, int E, int D, void* stream);
+/* go2_moe_combine_backward in two halves for the env-sharded trainer (the load-balance term of moe_cts.py:211-214 is a function of the WHOLE
+   mini-batch's mean gate usage): usage[e] = scale * mean over this rank's n rows (scale = 1 / world_size; the caller sums it over the ranks),
+   then the backward with the given (global) usage. */
+int go2_gate_usage(const float* gates, float* usage, long n, int E, float scale, void* stream);
+int go2_moe_combine_backward_given_usage(const float* dpre, const float* gates, const float* expert_out, const float* usage, float lb_coef,
+                                         float* dexpert_out, float* dexpert_out_t, float* dlogits, float* dlogits_t, long n, int E, int D, void* stream);
 /* latent reconstruction loss mean((teacher - student)^2) and its gradient (moe_cts.py:205-207); acc[1] receives the sum of squares */
 int go2_latent_loss(const float* student, const float* teacher, float* dstudent, float* acc, long n, int d, void* stream);
 /* log[0] += latent loss, log[1] += load-balance loss from usage[E] (NULL -> 0) */

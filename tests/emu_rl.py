@@ -455,11 +455,21 @@ def go2_moe_combine_forward(logits, expert_out, gates, pre, n, E, D, stream):
     return 0
 
 
+def go2_gate_usage(gates, usage, n, E, scale, stream):
+    _need(E <= 16, "go2_gate_usage: at most 16 experts")
+    _vec(usage, E)[...] = _mat(gates, n, E, E).sum(0, dtype=F) / F(n) * F(scale)
+    return 0
+
+
 def go2_moe_combine_backward(dpre, gates, expert_out, usage, lb_coef, dexpert_out, dexpert_out_t, dlogits, dlogits_t, n, E, D, stream):
     _need(E <= 16, "go2_moe_combine_backward: at most 16 experts")
+    _vec(usage, E)[...] = _mat(gates, n, E, E).sum(0, dtype=F) / F(n)
+    return go2_moe_combine_backward_given_usage(dpre, gates, expert_out, usage, lb_coef, dexpert_out, dexpert_out_t, dlogits, dlogits_t, n, E, D, stream)
+
+
+def go2_moe_combine_backward_given_usage(dpre, gates, expert_out, usage, lb_coef, dexpert_out, dexpert_out_t, dlogits, dlogits_t, n, E, D, stream):
     g, eo, dp = _mat(gates, n, E, E), _mat(expert_out, n, E * D, E * D).reshape(n, E, D), _mat(dpre, n, D, D)
     us = _vec(usage, E)
-    us[...] = g.sum(0, dtype=F) / F(n)
     dg = F(lb_coef) * (F(2) / F(E)) * (us - F(1) / F(E)) / F(n) + (dp[:, None, :] * eo).sum(2, dtype=F)
     deo = (g[:, :, None] * dp[:, None, :]).astype(F).reshape(n, E * D)
     _mat(dexpert_out, n, E * D, E * D)[...] = deo

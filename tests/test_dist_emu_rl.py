@@ -1,6 +1,7 @@
 """The multi-GPU trainer path on CPU: two gloo ranks, each with HALF of a reference-made fixture's envs, run the real
 compute_returns() + update() of the algorithm classes (C ABI emulated by tests/emu_rl.py) — the per-optimiser-step all-reduce of the flat
-gradient + scalar tail, the all-reduced advantage statistics, the 1 / world_size scaling of the student pass — and must end (a) bit-identical on
+gradient + scalar tail, the all-reduced advantage statistics, the 1 / world_size scaling of the student pass, the mean gate usage of the
+load-balance terms summed over the ranks — and must end (a) bit-identical on
 both ranks and (b) equal, to summation-order tolerance, to ONE process that runs the whole batch with the mini-batches composed of the same samples."""
 import os
 
@@ -38,7 +39,7 @@ def _build(variant, Z, device, N, env_offset, lb0):
                                     "mcp_cts": (Mo.ActorCriticMCPCTS, A.MCPCTS, cc.POLICY_MCP, cc.ALG_CTS)}[variant]
             akw = dict(akw)
             if lb0 and "load_balance_coef" in akw:
-                akw["load_balance_coef"] = 0.0       # the load-balance terms use each rank's own mean usage: excluded from the equality
+                akw["load_balance_coef"] = 0.0       # (unused since round 2: the mean gate usage is summed over the ranks, dist_utils.SmallSum)
             model = mcls(45, 263, 12, N, 5, **pol)
             model.load_state_dict({k[4:]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith("sd0_")})
             alg = acls(model, N, 5, device=device, env_offset=env_offset, **akw)
@@ -96,7 +97,7 @@ def _worker(rank, world, port, variant, q):
     NG = Z["st_rewards"].shape[1]
     Nl = NG // world
     sl = slice(rank * Nl, (rank + 1) * Nl)
-    model, alg = _build(variant, Z, "cpu", Nl, rank * Nl, lb0=True)
+    model, alg = _build(variant, Z, "cpu", Nl, rank * Nl, lb0=False)
     assert alg.world_size == world
     _fill(alg, _env_major(variant, Z, NG), sl, variant)
     with torch.inference_mode():
@@ -134,7 +135,7 @@ def test_two_rank_update_equals_the_single_process_update(variant, monkeypatch):
     Z = np.load(os.path.join(G, f"rl_{variant}.npz"))
     T, NG = Z["st_rewards"].shape[:2]
     Nl = NG // world
-    model, alg = _build(variant, Z, "cpu", NG, 0, lb0=True)
+    model, alg = _build(variant, Z, "cpu", NG, 0, lb0=False)
     _fill(alg, _env_major(variant, Z, NG), slice(0, NG), variant)
     with torch.inference_mode():
         alg.compute_returns(*_last_args(variant, Z, slice(0, NG)))
@@ -145,7 +146,7 @@ def test_two_rank_update_equals_the_single_process_update(variant, monkeypatch):
         adv_env[:, r * Nl + order] = res[r][4]
     g_order = np.arange(NG) if variant == "ppo" else alg.perm.numpy()
     assert np.allclose(adv_env[:, g_order], alg.storage.advantages.numpy(), atol=2e-6)
-    shards = [_build(variant, Z, "cpu", Nl, r * Nl, lb0=True)[1] for r in range(world)]
+    shards = [_build(variant, Z, "cpu", Nl, r * Nl, lb0=False)[1] for r in range(world)]
     lperms = [_local_perms(variant, shards[r], r, 11) for r in range(world)]
     if variant == "ppo":
         mbl = Nl * T // NB
