@@ -76,6 +76,10 @@ class CTS:
         rows = max(N, self.mb)
         self._lat = z(rows, D)
         self._lat_t = z(max(self.sm, 1), D)          # teacher latents of the student rows (pass 2 target)
+        # Neither the student encoder (pass 1) nor the teacher encoder (pass 2) changes during the pass that only READS it, and every epoch walks the
+        # same mini-batches (rollout_storage_cts.py:168-216): the no-grad latents are computed once per mini-batch and update(), not once per epoch
+        self._lat_s_cache = z(nb, max(self.sm, 1), D)
+        self._lat_t_cache = z(nb, max(self.sm, 1), D)
         self._xa = z(rows, _ops.pad_in(D + actor_obs_shape[0]))
         self._xc = z(rows, _ops.pad_in(D + critic_obs_shape[0]))
         self._mu, self._val = z(rows, A), z(rows, 1)
@@ -95,15 +99,18 @@ class CTS:
         self.model.train()
 
     # ---- shared forward pieces -----------------------------------------------------------------------------------------
-    def _latents(self, priv, hist, n_t, n_s, train_teacher=False):
-        """self._lat[0:n_t] = teacher latent of the first n_t rows, self._lat[n_t:n_t+n_s] = student latent of the rest (no grad)."""
+    def _latents(self, priv, hist, n_t, n_s, train_teacher=False, cache=None):
+        """self._lat[0:n_t] = teacher latent of the first n_t rows, self._lat[n_t:n_t+n_s] = student latent of the rest (no grad).
+        cache = i: the student latents of mini-batch i were computed by _pre1() (same weights, same rows, every epoch)."""
         m = self.model
         sd = self._side
         sd.fork()
         with sd:         # the teacher's rows next to the student's
             if n_t:
                 m.teacher_latent(priv[:n_t], n_t, self._lat[:n_t], train=train_teacher, x_ones=train_teacher and _ops.use_tc())
-        if n_s:
+        if n_s and cache is not None:
+            self._lat[n_t:n_t + n_s].copy_(self._lat_s_cache[cache, :n_s])
+        elif n_s:
             m.student.forward(hist[n_t:n_t + n_s], n_s, self._lat[n_t:n_t + n_s])
         sd.join()
 
@@ -204,6 +211,7 @@ class CTS:
             self._graphs.run("update_dist", self._update_body_dist)       # both passes with their gradient exchanges as one CUDA graph
         else:
             ws, n1, G = self.world_size, m.n1, m.flat_grads
+            self._graphs.run("pre1", self._pre1)
             for epoch in range(self.num_learning_epochs):
                 for i in range(self.num_mini_batches):
                     self._graphs.run(("grad1", i), lambda: self._grad1(i))
@@ -211,6 +219,7 @@ class CTS:
                     self._graphs.run("step1", self._step1)
                     m.mark_dirty()                    # replays skip the Python side of the step
             if self.sm > 0:
+                self._graphs.run("pre2", self._pre2)
                 for epoch in range(self.num_learning_epochs):
                     for i in range(self.num_mini_batches):
                         self._graphs.run(("grad2", i), lambda: self._grad2(i))
@@ -237,8 +246,21 @@ class CTS:
         out = (log[0] / n, log[1] / n, log[4] / n, log2[0] / n)
         return out + (log2[1] / n,) if self._moe else out
 
+    def _pre1(self):
+        """student latents (no grad) of every mini-batch's student rows, once per update()"""
+        sh, tm, sm, mb = self._sh, self.tm, self.sm, self.mb
+        for i in range(self.num_mini_batches if sm > 0 else 0):
+            self.model.student.forward(sh["history"][i * mb + tm:(i + 1) * mb], sm, self._lat_s_cache[i, :sm])
+
+    def _pre2(self):
+        """teacher latents (the target of pass 2, no grad) of every mini-batch's student rows, once per update(), after pass 1 has moved the teacher"""
+        sh, tm, sm, mb = self._sh, self.tm, self.sm, self.mb
+        for i in range(self.num_mini_batches):
+            self.model.teacher_latent(sh["critic_obs"][i * mb + tm:(i + 1) * mb], sm, self._lat_t_cache[i, :sm])
+
     def _update_body(self):
         # pass 1: PPO on teacher + student rows, optimizer 1 (moe_cts.py:114-195)
+        self._pre1()
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self._grad1(i)
@@ -246,6 +268,7 @@ class CTS:
         # pass 2: student encoder towards the (updated) teacher latent, optimizer 2 (moe_cts.py:197-224)
         if self.sm == 0:
             return
+        self._pre2()
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self._grad2(i)
@@ -253,6 +276,7 @@ class CTS:
 
     def _update_body_dist(self):
         m, n1, G = self.model, self.model.n1, self.model.flat_grads
+        self._pre1()
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self._grad1(i)
@@ -263,6 +287,7 @@ class CTS:
                 self._step1()
         if self.sm == 0:
             return
+        self._pre2()
         for epoch in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 self._grad2(i)
@@ -278,7 +303,7 @@ class CTS:
         tc, ws = _ops.use_tc(), self.world_size
         s = slice(i * mb, (i + 1) * mb)
         obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
-        self._latents(priv_b, hist_b, tm, sm, train_teacher=True)
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True, cache=i)
         self._heads(obs_b, priv_b, mb, train=True)
         call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
              ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
@@ -312,13 +337,8 @@ class CTS:
         tc = _ops.use_tc()
         s = slice(i * mb + tm, (i + 1) * mb)
         priv_b, hist_b = sh["critic_obs"][s], sh["history"][s]
-        sd = self._side
-        sd.fork()
-        with sd:
-            m.teacher_latent(priv_b, sm, self._lat_t)
         m.student.forward(hist_b, sm, self._lat[:sm], train=True, x_ones=tc)
-        sd.join()
-        call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t), ptr(self._dls), ptr(self._acc), sm, D)
+        call("go2_latent_loss", ptr(self._lat), ptr(self._lat_t_cache[i]), ptr(self._dls), ptr(self._acc), sm, D)      # target: _pre2()
         m.student.backward(self._dls, self.load_balance_coef)
         call("go2_cts_log", ptr(self._acc), ptr(m.student.usage) if self._moe else 0, ptr(self._log2), sm * D, m.student.E if self._moe else 1)
 
@@ -433,7 +453,7 @@ class ACMoECTS(CTS):
         ws = self.world_size
         s = slice(i * mb, (i + 1) * mb)
         obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
-        self._latents(priv_b, hist_b, tm, sm, train_teacher=True)
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True, cache=i)
         self._heads(obs_b, priv_b, mb, train=True)
         call("go2_ppo_loss", ptr(self._mu), ptr(m.std.data), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
              ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
@@ -502,7 +522,7 @@ class MCPCTS(CTS):
         ws = self.world_size
         s = slice(i * mb, (i + 1) * mb)
         obs_b, priv_b, hist_b = sh["obs"][s], sh["critic_obs"][s], sh["history"][s]
-        self._latents(priv_b, hist_b, tm, sm, train_teacher=True)
+        self._latents(priv_b, hist_b, tm, sm, train_teacher=True, cache=i)
         self._heads(obs_b, priv_b, mb, train=True)
         call("go2_ppo_loss_sigma", ptr(self._mu), ptr(self._sigma), ptr(self._val), ptr(sh["actions"][s]), ptr(sh["old_logp"][s]), ptr(sh["adv"][s]),
              ptr(sh["values"][s]), ptr(sh["returns"][s]), ptr(sh["old_mu"][s]), ptr(sh["old_sigma"][s]), ptr(self._dmu),
