@@ -346,6 +346,7 @@ __device__ __forceinline__ uint4 split_tf32(uint4& v) {
 }
 constexpr int TCP_LO_SLOTS = 2;
 // mbarrier wait that adds the cycles it blocked to *acc when profiling (acc == nullptr otherwise)
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long* acc) {
   if (acc) { const long long t0 = clock64(); mbar_wait(bar, parity); *acc += clock64() - t0; }
   else mbar_wait(bar, parity);
@@ -395,6 +396,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = p.m_tiles * p.n_tiles * p.splits;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 24 + 16] = globaltimer_ns();
   // programmatic dependent launch: the next GEMM of the stream may take over this SM as soon as this CTA exits and run its prologue (barriers, TMEM,
   // tensor-map prefetch) under the tail of this grid; it blocks in griddepcontrol.wait below until this grid has completed and flushed
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -419,7 +421,9 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 24 + 17] = globaltimer_ns();
   asm volatile("griddepcontrol.wait;" ::: "memory");          // everything before this line touched no global memory (no-op without the launch attribute)
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 24 + 18] = globaltimer_ns();
 
   if (warp == 0) {
     // ===== TMA producer: the stage ring runs straight through the unit list
@@ -447,7 +451,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
-      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[0] = clock64() - t_start; d[1] = w_empty; }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 24; d[0] = clock64() - t_start; d[1] = w_empty; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread)
@@ -499,7 +503,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         umma_commit(tfull + buf);
       }
-      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[2] = clock64() - t_start; d[3] = w_tempty; d[4] = w_full; d[5] = w_lofull; d[6] = nst; }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 24; d[2] = clock64() - t_start; d[3] = w_tempty; d[4] = w_full; d[5] = w_lofull; d[6] = nst; }
     }
   } else if (X3 && warp >= 10) {
     // ===== splitter warps (3xTF32): stage s landed -> hi in place, lo into slot l; then hand both to the MMA warp
@@ -536,7 +540,7 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-    if (p.dbg && t == 0) { long long* d = p.dbg + blockIdx.x * 16; d[7] = w_full; d[8] = w_loempty; d[9] = t_work; }   // t_work includes w_loempty
+    if (p.dbg && t == 0) { long long* d = p.dbg + blockIdx.x * 24; d[7] = w_full; d[8] = w_loempty; d[9] = t_work; }   // t_work includes w_loempty
   } else {
     // ===== epilogue: group grp takes chunks grp, grp+2, ... of every unit; warp -> TMEM lane quadrant q; thread = one tile row
     const int grp = (warp - 2) >> 2, q = warp & 3;
@@ -641,10 +645,11 @@ gemm_tf32_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + buf)) : "memory");
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (p.dbg && leader) { long long* d = p.dbg + blockIdx.x * 16 + 10 + 2 * grp; d[0] = clock64() - t_start; d[1] = w_tfull; p.dbg[blockIdx.x * 16 + 14 + grp] = w_aux; }
+    if (p.dbg && leader) { long long* d = p.dbg + blockIdx.x * 24 + 10 + 2 * grp; d[0] = clock64() - t_start; d[1] = w_tfull; p.dbg[blockIdx.x * 24 + 14 + grp] = w_aux; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 24 + 19] = globaltimer_ns();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -728,6 +733,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;      // cluster index / number of clusters
   const int units = p.m_tiles * p.n_tiles * p.splits;          // m_tiles = 256-row pair tiles
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cid * 24 + 16] = globaltimer_ns();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see gemm_tf32_persist_kernel
 
   if (warp == 0 && lane == 0) {
@@ -750,7 +756,9 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cid * 24 + 17] = globaltimer_ns();
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cid * 24 + 18] = globaltimer_ns();
 
   if (warp == 0) {
     // ===== TMA producer: own 128 rows of A, own half of B
@@ -780,7 +788,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
-      if (p.dbg && rank == 0) { long long* d = p.dbg + cid * 16; d[0] = clock64() - t_start; d[1] = w_empty; }
+      if (p.dbg && rank == 0) { long long* d = p.dbg + cid * 24; d[0] = clock64() - t_start; d[1] = w_empty; }
     }
   } else if (warp == 1 && rank != 0) {
     // ===== landing relay (peer): stage s of this CTA has landed -> the leader may multiply it
@@ -847,7 +855,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         umma_commit_pair(tfull + buf);
       }
-      if (p.dbg) { long long* d = p.dbg + cid * 16; d[2] = clock64() - t_start; d[3] = w_tempty; d[4] = w_full; d[5] = w_lofull; d[6] = nst; }
+      if (p.dbg) { long long* d = p.dbg + cid * 24; d[2] = clock64() - t_start; d[3] = w_tempty; d[4] = w_full; d[5] = w_lofull; d[6] = nst; }
     }
   } else if (X3 && warp >= 10) {
     // ===== splitter warps (3xTF32): own stage -> own lo slot; every warp of BOTH CTAs arrives on the leader's lofull
@@ -884,7 +892,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-    if (p.dbg && t == 0 && rank == 0) { long long* d = p.dbg + cid * 16; d[7] = w_full; d[8] = w_loempty; d[9] = t_work; }
+    if (p.dbg && t == 0 && rank == 0) { long long* d = p.dbg + cid * 24; d[7] = w_full; d[8] = w_loempty; d[9] = t_work; }
   } else if (warp >= 2 && warp < 10) {
     // ===== epilogue: own 128 accumulator rows; group grp takes chunks grp, grp+2, ...; warp -> TMEM lane quadrant q; thread = one tile row
     const int grp = (warp - 2) >> 2, q = warp & 3;
@@ -973,10 +981,11 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) mbar_arrive_cluster(tempty + buf, 0);
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (p.dbg && leader && rank == 0) { long long* d = p.dbg + cid * 16 + 10 + 2 * grp; d[0] = clock64() - t_start; d[1] = w_tfull; p.dbg[cid * 16 + 14 + grp] = w_aux; }
+    if (p.dbg && leader && rank == 0) { long long* d = p.dbg + cid * 24 + 10 + 2 * grp; d[0] = clock64() - t_start; d[1] = w_tfull; p.dbg[cid * 24 + 14 + grp] = w_aux; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   cluster_sync_all();                                          // nobody leaves (or frees TMEM) while the partner may still touch this SM
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cid * 24 + 19] = globaltimer_ns();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

@@ -265,8 +265,8 @@ int go2_gemm_set_pair(int on);
 /* 1 (default): the persistent GEMMs are launched with programmatic stream serialization (their prologue runs under the tail of the previous kernel,
    griddepcontrol.wait orders the memory traffic); 0: plain stream order (A/B aid; also GO2_GEMM_PDL=0). */
 int go2_gemm_set_pdl(int on);
-/* Profiling aid: counters != NULL makes every persistent tensor-core GEMM launch write, per CTA b, 16 int64 cycle counters at counters[16 b ...]
-   (device memory, >= 16 x SM count): 0 producer total, 1 producer waiting for a free stage; 2 MMA thread total, 3 .. waiting for a drained accumulator,
+/* Profiling aid: counters != NULL makes every persistent tensor-core GEMM launch write, per CTA b, 24 int64 counters at counters[24 b ...]
+   (device memory, >= 24 x SM count; 16..19: %globaltimer ns at kernel entry, after the prologue, after griddepcontrol.wait, at exit): 0 producer total, 1 producer waiting for a free stage; 2 MMA thread total, 3 .. waiting for a drained accumulator,
    4 .. for TMA bytes, 5 .. for the lo slot, 6 stages processed; 7 splitter waiting for TMA bytes, 8 .. for a free lo slot, 9 splitter busy (incl. 8);
    10/11 and 12/13 epilogue group 0 / 1 total and waiting for an accumulator, 14 / 15 .. for the ELU' operand (dgrad).  NULL (default) disables it. */
 int go2_gemm_set_debug(long long* counters);

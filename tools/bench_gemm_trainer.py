@@ -43,16 +43,19 @@ def profile(fn, label):
     if "--dbg" not in sys.argv:
         return
     if DBG is None:
-        DBG = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+        DBG = torch.zeros(148 * 24, dtype=torch.int64, device="cuda")
     fn(); torch.cuda.synchronize()
     DBG.zero_()
     assert L.go2_gemm_set_debug(DBG.data_ptr()) == 0
     fn(); torch.cuda.synchronize()
     assert L.go2_gemm_set_debug(None) == 0
-    d = DBG.view(148, 16).double().cpu()
+    d = DBG.view(148, 24).double().cpu()
     d = d[d[:, 6] > 0]
+    g = d[:, 16:20]
+    t0 = g[:, 0].min()
+    span = f"; ns from first CTA entry: prologue done {float((g[:, 1] - t0).mean()):.0f} (mean), dependency wait done {float((g[:, 2] - t0).mean()):.0f}, exit mean {float((g[:, 3] - t0).mean()):.0f} / max {float((g[:, 3] - t0).max()):.0f}, entry spread {float((g[:, 0] - t0).max()):.0f}"
     m = d.mean(0); st = float(m[6])
-    print(f"    [{label}] {len(d)} CTAs, {st:.1f} stages/CTA; cycles per stage: " + ", ".join(f"{n} {float(m[i]) / st:.0f}" for i, n in enumerate(NAMES) if i != 6 and m[i] > 0), flush=True)
+    print(f"    [{label}] {len(d)} CTAs, {st:.1f} stages/CTA; cycles per stage: " + ", ".join(f"{n} {float(m[i]) / st:.0f}" for i, n in enumerate(NAMES) if i != 6 and m[i] > 0) + span, flush=True)
 
 
 def rel(a, b):
