@@ -449,3 +449,56 @@ def test_p2p_allreduce_kernel_protocol(world, two_shot):
             assert torch.equal(outs[r][off:off + cnt], ref), (it, r)
             assert (outs[r][:off] == -7.0).all() and (outs[r][off + cnt:] == -7.0).all()      # nothing outside the slice was touched
             assert ctrs[r].tolist() == [it + 1, 0]
+
+
+@pytest.mark.parametrize("M,N,K,act", [(24576, 512, 264, 1), (24576, 256, 512, 1), (8192, 128, 256, 0), (3000, 268, 64, 0), (24576, 516, 48, 1)])
+def test_pair_kernel_equals_one_cta_kernel(M, N, K, act):
+    """The CTA-pair GEMM (tcgen05.mma.cta_group::2, 256-row tiles, half of B per SM) and the one-CTA persistent kernel run the same 3xTF32 arithmetic in
+    the same K order per output element: bit-identical outputs, for every pair tile width (256 / 192 / 160 / 128), ragged M and N included."""
+    from go2_rl_gym_b200.rl import _ops
+    L = _ops.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    X, W, b = torch.randn(M, K, device="cuda", generator=g), torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K), torch.randn(N, device="cuda", generator=g)
+    outs = []
+    try:
+        for pair in (1, 0):
+            assert L.go2_gemm_set_pair(pair) == 0
+            Y = torch.zeros(M, N, device="cuda")
+            _ops.call("go2_linear_forward_tc", X.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), Y.data_ptr(), N, 0, 0, M, N, K, act)
+            torch.cuda.synchronize()
+            outs.append(Y)
+    finally:
+        L.go2_gemm_set_pair(1)
+    assert torch.equal(outs[0], outs[1])
+    ref = torch.nn.functional.linear(X.double(), W.double(), b.double())
+    ref = torch.nn.functional.elu(ref) if act else ref
+    assert _rel(outs[0].cpu(), ref.cpu()) < REL_BAR[3]
+
+
+def test_side_streams_do_not_change_the_update(monkeypatch):
+    """Actor / critic chains and the weight gradients run on side streams joined as graph edges (rl/_ops.py: SideStream).  Concurrency must not change a
+    bit: PPO.update over the reference-made fixture with GO2_TWO_STREAMS=0 (everything on one stream) and =1, three times each (a race would show
+    as run-to-run differences), must leave identical parameters and losses."""
+    from golden.rl_cfg import CFG
+    from go2_rl_gym_b200.rl.algorithms import PPO
+    from go2_rl_gym_b200.rl.modules import ActorCritic
+    T, N = Z["st_rewards"].shape[:2]
+    results = []
+    for ts in ("0", "1", "1", "1"):
+        monkeypatch.setenv("GO2_TWO_STREAMS", ts)
+        ac = ActorCritic(45, 263, 12, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128])
+        torch.manual_seed(3)
+        for p in ac.parameters():
+            p.data.copy_(torch.randn(p.shape) * 0.05)
+        alg = PPO(ac, device="cuda", **CFG)
+        alg.init_storage(N, T, [45], [263], [12])
+        st = alg.storage
+        for k in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
+            getattr(st, k).copy_(_t("st_" + k))
+        for _ in range(2):       # second call = the captured graph
+            st.step = T
+            losses = alg.update(indices=_t("perm"))
+        assert alg._side.enabled == (ts == "1")
+        results.append((ac.flat_params.clone(), losses))
+    for r in results[1:]:
+        assert torch.equal(r[0], results[0][0]) and r[1] == results[0][1]
