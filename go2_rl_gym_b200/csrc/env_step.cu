@@ -72,7 +72,7 @@ step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restr
   const int e0 = blockIdx.x * 8;
   StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
-  init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8, ROT ? pick_leg_warp(8, &leg_warp_slot) : 0);
+  init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8, ROT == 1 ? pick_leg_warp(8, &leg_warp_slot) : ROT == 2 ? (int)((blockIdx.x / 148u) & 3u) : 0);
 #if defined(GO2_PHASE_TIMING)
   if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { go2_ph_count = 1; go2_ph_clock[0] = clock64(); }
 #endif
@@ -163,7 +163,7 @@ struct Go2Env {
 
 static int parse_step_mode(const char* m) {
   return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : !strcmp(m, "Q2") ? 5
-       : !strcmp(m, "P2r") ? 6 : -1;
+       : !strcmp(m, "P2r") ? 6 : !strcmp(m, "P2b") ? 7 : -1;
 }
 
 namespace go2 {
@@ -245,12 +245,12 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
 // Thread map of the step kernel (same results bit for bit; tuning / A-B aid).  Default "P2"; the GO2_STEP_MODE environment variable
 // presets it at create time.
 //   "P2": packed map, 8 envs per 256-thread CTA, 2 CTAs/SM (128 registers) · "P2r": the same with the leg warp rotated per SM through an atomic ticket
-//   (measured round 2: 167 us vs 162 us — the ticket costs more than spreading the leg streams over the schedulers gains) · "P3": 3 CTAs/SM (80 registers)
+//   (measured round 2: 167 us vs 162 us — the ticket costs more than spreading the leg streams over the schedulers gains) · "P2b": leg warp = (block index / 148) mod 4, no ticket (co-resident CTAs of the first waves get different schedulers) · "P3": 3 CTAs/SM (80 registers)
 //   "Q4" / "Q2": packed map with 4 / 2 envs per 128- / 64-thread CTA, 4 / 8 CTAs/SM (unmeasured: built after round 1's GPU budget was spent)
 //   "8p": warp per env, 8 warps per CTA, CTA barrier at substep boundaries (the previous default: 203 us at 4096 envs)
 //   "4" : warp per env, 4 warps per CTA, no barrier (the first kernel: 239 us)
 int go2_env_set_step_mode(Go2Env* h, const char* mode) {
-  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P2r, P3, Q4, Q2, 8p, 4)");
+  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P2r, P2b, P3, Q4, Q2, 8p, 4)");
   h->step_mode = parse_step_mode(mode);
   return 0;
 }
@@ -276,7 +276,7 @@ int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, v
   else {
     int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2, 0>(h, actions, sp, st)
            : mode == 3 ? go2::launch_packed<3, 0>(h, actions, sp, st) : mode == 4 ? go2::launch_quad<4, 4>(h, actions, sp, st)
-           : mode == 6 ? go2::launch_packed<2, 1>(h, actions, sp, st) : go2::launch_quad<2, 8>(h, actions, sp, st);
+           : mode == 6 ? go2::launch_packed<2, 1>(h, actions, sp, st) : mode == 7 ? go2::launch_packed<2, 2>(h, actions, sp, st) : go2::launch_quad<2, 8>(h, actions, sp, st);
     if (rc) return rc;
   }
   go2::count_launch();
