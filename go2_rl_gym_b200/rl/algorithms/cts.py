@@ -91,6 +91,7 @@ class CTS:
         self._rew_p, self._actions_env = z(N), z(N, A)
         self._graphs = _ops.GraphSet()
         self._side = _ops.SideStream(dev)          # independent chains (teacher / student, actor / critic) run side by side: _ops.SideStream
+        self._join_pending = False
 
     def test_mode(self):
         self.model.eval()
@@ -114,7 +115,7 @@ class CTS:
             m.student.forward(hist[n_t:n_t + n_s], n_s, self._lat[n_t:n_t + n_s])
         sd.join()
 
-    def _heads(self, obs, priv, M, train=False):
+    def _heads(self, obs, priv, M, train=False, values_out=None):
         m, D = self.model, self.model.latent_dim
         tc = _ops.use_tc()
         # go2_concat2 writes a 1 into the first padding column of its output (bias-gradient column of the row-major wgrad)
@@ -125,8 +126,13 @@ class CTS:
         sd.fork()
         with sd:         # the critic next to the actor
             m.critic_engine.forward(self._xc, self._xc.shape[1], M, self._val[:M], 1, train=train, x_ones=self._xc.shape[1] > D + m.num_critic_obs)
+            if values_out is not None:       # rollout: the value is first needed by process_env_step — the critic also runs next to the env step
+                values_out.copy_(self._val[:M])
         m.actor_engine.forward(self._xa, self._xa.shape[1], M, self._mu[:M], m.num_actions, train=train, x_ones=ones)
-        sd.join()
+        if values_out is not None:
+            self._join_pending = True
+        else:
+            sd.join()
 
     # ---- rollout -------------------------------------------------------------------------------------------------------
     def begin_rollout(self, T):
@@ -151,8 +157,11 @@ class CTS:
         gather(history, history.shape[1], st.history[t])
         nt, ns = self.teacher_num_envs, self.student_num_envs
         self._latents(st.privileged_observations[t], st.history[t], nt, ns)
-        self._heads(st.observations[t], st.privileged_observations[t], N)
-        st.values[t].copy_(self._val[:N])
+        if type(self)._heads is CTS._heads and self._dev_steps is not None:      # graph-replayed rollout: critic + value copy on the side stream, joined
+            self._heads(st.observations[t], st.privileged_observations[t], N, values_out=st.values[t])      # in process_env_step
+        else:
+            self._heads(st.observations[t], st.privileged_observations[t], N)
+            st.values[t].copy_(self._val[:N])
         self._sample(t, N, A)
         call("go2_gather_rows", ptr(st.actions[t]), A, ptr(self.inv_perm), ptr(self._actions_env), A, 0, N)   # back to env order
         return self._actions_env
@@ -170,6 +179,8 @@ class CTS:
 
     def process_env_step(self, rewards, dones, infos):
         st, t = self.storage, self.storage.step
+        if self._join_pending:
+            self._side.join(); self._join_pending = False
         tout = infos.get('time_outs') if isinstance(infos, dict) else None
         d8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8)
         t8 = None if tout is None else (tout.view(torch.uint8) if tout.dtype == torch.bool else tout.to(torch.uint8))
