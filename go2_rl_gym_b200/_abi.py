@@ -10,6 +10,8 @@ NUM_DOF, NUM_DYN, NUM_REPORT, NUM_COL = 12, 13, 19, 32
 NUM_OBS, NUM_PRIV, NUM_HEIGHT, NUM_REW, NUM_CMD = 45, 263, 187, 14, 4
 INERTIA_STRIDE = 10
 EP_STATS = NUM_REW + 12
+EP_ACC_FIXED_OFF = (EP_STATS + 2 + 1) // 2 * 2       # include/go2_b200.h: GO2_EP_ACC_FIXED_OFF / GO2_EP_ACCUM_FLOATS
+EP_ACCUM_FLOATS = EP_ACC_FIXED_OFF + 2 * NUM_REW
 
 REWARD_NAMES = ["tracking_lin_vel", "tracking_ang_vel", "lin_vel_z", "ang_vel_xy", "dof_acc", "dof_power", "torques",
                 "correct_base_height", "action_rate", "action_smoothness", "collision", "dof_pos_limits",

@@ -133,7 +133,7 @@ __global__ void finalize_kernel(const Go2EnvConfig* __restrict__ cfg, float* __r
   __syncthreads();
   if (n_reset > 0.0f && ep_stats != nullptr) {
     float* st = ep_stats + (size_t)slot * GO2_EP_STATS;
-    if (k < GO2_NUM_REW) st[k] = ep_accum[k] / n_reset / cfg->max_episode_length_s;
+    if (k < GO2_NUM_REW) st[k] = (float)((double)reinterpret_cast<const long long*>(ep_accum + GO2_EP_ACC_FIXED_OFF)[k] / (double)GO2_EP_FIXED_ONE) / n_reset / cfg->max_episode_length_s;
     else if (k == GO2_NUM_REW) st[k] = cfg->mesh_type == 0 ? 0.0f : ep_accum[k] / (float)cfg->num_envs;
     else if (k < GO2_NUM_REW + 10) st[k] = id_counts[k - GO2_NUM_REW - 1] > 0 ? ep_accum[k] / id_counts[k - GO2_NUM_REW - 1] : 0.0f;
     else if (k == GO2_NUM_REW + 10) st[k] = n_reset;
@@ -143,6 +143,7 @@ __global__ void finalize_kernel(const Go2EnvConfig* __restrict__ cfg, float* __r
   }
   __syncthreads();
   if (k < GO2_EP_STATS + 2) ep_accum[k] = 0.0f;
+  if (k < GO2_NUM_REW) reinterpret_cast<long long*>(ep_accum + GO2_EP_ACC_FIXED_OFF)[k] = 0;
 }
 
 }  // namespace go2
@@ -233,7 +234,7 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
   float counts[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int e = 0; e < cfg->num_envs; ++e) if (ids[e] >= 0 && ids[e] < 9) counts[ids[e]] += 1.0f;
   GO2_CUDA_OK(cudaMemcpy(h->d_id_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
-  GO2_CUDA_OK(cudaMemset(bufs->ep_accum, 0, sizeof(float) * (GO2_EP_STATS + 2)));
+  GO2_CUDA_OK(cudaMemset(bufs->ep_accum, 0, sizeof(float) * GO2_EP_ACCUM_FLOATS));
   if (const char* m = getenv("GO2_STEP_MODE")) {
     if (parse_step_mode(m) < 0) { go2_env_destroy(h); return go2::set_error(1, "go2_env_create: unknown GO2_STEP_MODE"); }
     h->step_mode = parse_step_mode(m);
@@ -308,7 +309,7 @@ int go2_env_reset_all(Go2Env* h, const Go2StepParams* sp, void* stream) {
   GO2_CUDA_OK(cudaMemcpyAsync(h->d_sp, sp, sizeof(Go2StepParams), cudaMemcpyHostToDevice, st));
   go2::reset_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, h->d_sp);
   go2::count_launch();
-  GO2_CUDA_OK(cudaMemsetAsync(h->buf.ep_accum, 0, sizeof(float) * (GO2_EP_STATS + 2), st));
+  GO2_CUDA_OK(cudaMemsetAsync(h->buf.ep_accum, 0, sizeof(float) * GO2_EP_ACCUM_FLOATS, st));
   GO2_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -972,8 +972,10 @@ GO2_HD void heading_to_yaw(WarpSmem& S) {
 
 #if defined(__CUDACC__)
 #define GO2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define GO2_ATOMIC_ADD_FIXED(acc, k, v) atomicAdd(reinterpret_cast<unsigned long long*>((acc) + GO2_EP_ACC_FIXED_OFF) + (k), (unsigned long long)__float2ll_rn((v) * GO2_EP_FIXED_ONE))
 #else
 #define GO2_ATOMIC_ADD(p, v) (*(p) += (v))
+#define GO2_ATOMIC_ADD_FIXED(acc, k, v) (reinterpret_cast<long long*>((acc) + GO2_EP_ACC_FIXED_OFF)[k] += llrintf((v) * GO2_EP_FIXED_ONE))
 #endif
 
 // reset_idx for this env (legged_robot.py:180-245, :620-707, :1143-1169); `initial` = the reset at construction
@@ -999,7 +1001,7 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool ini
     if (lane >= 16 && lane < 16 + GO2_NUM_REW) {
       const int k = lane - 16;
       float* es = B->episode_sums + (size_t)e * GO2_NUM_REW + k;
-      if (!initial) GO2_ATOMIC_ADD(B->ep_accum + k, *es);
+      if (!initial) GO2_ATOMIC_ADD_FIXED(B->ep_accum, k, *es);      // 2^-20 fixed point, integer atomics: the sum does not depend on the order
       *es = 0;
     }
     if (lane == 30 && !initial) GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW + 10, 1.0f);

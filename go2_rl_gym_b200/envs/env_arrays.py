@@ -144,7 +144,7 @@ class EnvArrays:
         T["restitutions"] = torch.from_numpy(rest[sl].astype(np.float32)).to(dev)
         T["body_inertia"] = torch.from_numpy(inertia).to(dev)
         z("ep_stats", EP_SLOTS, _abi.EP_STATS)
-        z("ep_accum", _abi.EP_STATS + 2)
+        z("ep_accum", _abi.EP_ACCUM_FLOATS)
         T["projected_gravity"][:, 2] = -1.0
         self.tensors = T
         self.terrain_ids_np = ids

@@ -31,6 +31,9 @@ extern "C" {
 #define GO2_NUM_CMD 4
 #define GO2_INERTIA_STRIDE 10 /* mass, com xyz, Ixx Iyy Izz Ixy Ixz Iyz (about COM, link frame) */
 #define GO2_EP_STATS (GO2_NUM_REW + 12) /* rew means [14], terrain level mean, per-terrain-id means [9], n_reset, valid flag */
+#define GO2_EP_ACC_FIXED_OFF ((GO2_EP_STATS + 2 + 1) / 2 * 2)
+#define GO2_EP_ACCUM_FLOATS (GO2_EP_ACC_FIXED_OFF + 2 * GO2_NUM_REW)
+#define GO2_EP_FIXED_ONE 1048576.0f /* 2^20 */
 #define GO2_EP_SLOTS 64 /* rows of ep_stats: a ring indexed by Go2StepParams.ep_slot.  A step in which no env reset copies the previous slot's row
                            forward (the reference re-serves its stale extras["episode"], legged_robot.py:229-242 / on_policy_runner.py:145-146); the
                            valid flag stays 0 until the first reset, when the reference's extras has no "episode" key yet */
@@ -182,7 +185,10 @@ typedef struct Go2EnvBuffers {
   /* logging */
   float* episode_sums;     /* [N,14] */
   float* ep_stats;         /* [ep_slots, GO2_EP_STATS] */
-  float* ep_accum;         /* [GO2_EP_STATS + 2] scratch for the cross-env sums (zeroed by the step) */
+  float* ep_accum;         /* [GO2_EP_ACCUM_FLOATS] scratch for the cross-env sums (zeroed by the step): GO2_EP_STATS + 2 floats (terrain-level sums and
+                              counters: integer-valued, so their float atomics are order-independent), then, 8-byte aligned at float index
+                              GO2_EP_ACC_FIXED_OFF, GO2_NUM_REW int64 accumulators of the finished episodes' reward sums in 2^-20 fixed point —
+                              integer atomics, so the logged means are bit-reproducible run to run whatever order the CTAs finish in */
 } Go2EnvBuffers;
 
 /* ---- environment (CUDA library: libgo2b200.so) ------------------------------------------------ */

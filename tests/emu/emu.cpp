@@ -22,14 +22,15 @@ template <class F> static void for_groups(const Go2EnvConfig* C, F&& f) {
 extern "C" {
 void go2_emu_set_packed(int packed) { g_packed = packed; }
 int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const float* actions, const Go2StepParams* sp) {
-  for (int k = 0; k < GO2_EP_STATS + 2; ++k) B->ep_accum[k] = 0;
+  for (int k = 0; k < GO2_EP_ACCUM_FLOATS; ++k) B->ep_accum[k] = 0;
   StepCtx X{C, M, B, sp, actions};
   for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { step_env(lanes, NT, SM, X); });
   // finalize extras["episode"] (mirrors the tiny finalize kernel)
   float n_reset = B->ep_accum[GO2_NUM_REW + 10];
   if (n_reset > 0 && B->ep_stats) {
     float* st = B->ep_stats + (size_t)sp->ep_slot * GO2_EP_STATS;
-    for (int k = 0; k < GO2_NUM_REW; ++k) st[k] = B->ep_accum[k] / n_reset / C->max_episode_length_s;
+    for (int k = 0; k < GO2_NUM_REW; ++k)
+      st[k] = (float)((double)reinterpret_cast<const long long*>(B->ep_accum + GO2_EP_ACC_FIXED_OFF)[k] / (double)GO2_EP_FIXED_ONE) / n_reset / C->max_episode_length_s;
     std::vector<int> cnt(9, 0);
     for (int e = 0; e < C->num_envs; ++e) cnt[B->terrain_ids[e]]++;
     st[GO2_NUM_REW] = C->mesh_type == 0 ? 0.0f : B->ep_accum[GO2_NUM_REW] / C->num_envs;

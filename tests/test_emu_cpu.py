@@ -89,8 +89,8 @@ def test_packed_map_is_bit_identical_to_warp_per_env(packed):
         e0.step(a); e1.step(a)
         n_reset += int(A0.tensors["reset_buf"].sum())
         for k, v in A0.tensors.items():
-            if k == "ep_accum":
-                continue        # scratch of the cross-env logging sums (summation order differs)
+            # incl. "ep_accum" / "ep_stats": the finished episodes' reward sums are accumulated with integer atomics in 2^-20 fixed point, so the
+            # logged means do not depend on the order in which the groups run
             assert torch.equal(v, A1.tensors[k]) or (torch.isnan(v) == torch.isnan(A1.tensors[k])).all() and torch.equal(torch.nan_to_num(v), torch.nan_to_num(A1.tensors[k])), (step, k)
     assert n_reset > 5
 

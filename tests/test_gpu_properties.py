@@ -66,17 +66,26 @@ def test_invariants_at_full_size():
 
 
 def test_same_seed_same_bits():
+    """Two runs from the same seed leave the same bits — including the LOGGED episode statistics (extras["episode"]: `ep_stats`): the finished
+    episodes' reward sums are accumulated across CTAs with integer atomics in 2^-20 fixed point, so they do not depend on the order in which
+    the CTAs finish (float atomicAdd made the logged means run-to-run non-deterministic)."""
     N = 8192
     outs = []
+    keys = KEYS + ("ep_stats",)
     for _ in range(2):
         cfg, A, e = _env(N, seed=11)
+        A.tensors["episode_length_buf"].copy_(torch.randint(1000, 1250, (N,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)))
         g = torch.Generator(device="cuda").manual_seed(5)
+        n_reset = 0
         for _ in range(12):
             e.step(torch.randn(N, 12, device="cuda", generator=g))
-        outs.append({k: A.tensors[k].clone() for k in KEYS})
+            n_reset += int(A.tensors["reset_buf"].sum())
+        outs.append({k: A.tensors[k].clone() for k in keys})
         del e
-    for k in KEYS:
+    assert n_reset > 100                                   # many envs finished episodes: the cross-CTA sums were exercised
+    for k in keys:
         assert torch.equal(outs[0][k], outs[1][k]), k
+    assert float(outs[0]["ep_stats"][:, :14].abs().sum()) > 0
 
 
 def test_shards_equal_slices_of_the_whole():
