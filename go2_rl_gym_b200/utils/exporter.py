@@ -9,8 +9,8 @@ actor, with the call signatures the deployment loops expect (deploy/deploy_mujoc
 The CTS variants keep the rolling observation history ([1, H, 45], shift-append) inside the module and expose `reset()`.
 The exported module is plain PyTorch built from the policy's state_dict (inference on the robot / in MuJoCo has no B200);
 it is rebuilt from weights rather than deep-copied because this package's modules evaluate through the CUDA library.
-The three remaining ablation variants (MCP / AC-MoE / Dual-MoE) are exported from any module or checkpoint with the reference's key layout
-(their training path is not on the CUDA kernels yet); ONNX export and the recurrent policy are out of scope."""
+The three remaining ablation variants (MCP / AC-MoE / Dual-MoE; all seven registered tasks train on the CUDA kernels) are exported from any
+module or checkpoint with the reference's key layout; ONNX export and the recurrent policy are out of scope."""
 import os
 from typing import Optional, Tuple
 

@@ -58,3 +58,24 @@ def test_registered_tasks_equal_the_reference():
     from go2_rl_gym_b200.envs import task_registry
     mine = set(task_registry.task_classes)
     assert mine == ref_tasks and len(mine) == 7, (mine, ref_tasks)       # legged_gym/envs/__init__.py:9-15
+
+
+def test_command_range_curriculum_after_a_late_resume():
+    """A run resumed past BOTH command-range boundaries (go2_config.py:112-124) trains on the ranges of the LAST boundary — what an uninterrupted run
+    would be using — whereas the reference's backward walk inside `_resample_commands` (legged_robot.py:433-446) ends on the earliest entry
+    (DESIGN.md section 6).  An uninterrupted run crosses the boundaries one at a time and agrees with the reference at each."""
+    from go2_rl_gym_b200.envs.env_arrays import EnvArrays
+    from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+    cfg = GO2Cfg(); cfg.env.num_envs = 8; cfg.terrain.mesh_type = "plane"
+    entries = sorted(cfg.commands.command_range_curriculum, key=lambda e: e["iter"])
+    assert len(entries) >= 2
+    late = EnvArrays(cfg, "cpu", seed=1)
+    late.step_params(24 * (entries[-1]["iter"] + 5))                          # resumed after the last boundary
+    for key in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw"):
+        assert list(late.command_ranges[key]) == list(entries[-1][key]), key
+    walk = EnvArrays(cfg, "cpu", seed=1)
+    for e in entries:                                                           # uninterrupted: one boundary at a time
+        walk.step_params(24 * e["iter"])
+        for key in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw"):
+            assert list(walk.command_ranges[key]) == list(e[key]), (e["iter"], key)
+    assert late.tensors["env_command_ranges"].equal(walk.tensors["env_command_ranges"])
