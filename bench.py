@@ -339,35 +339,9 @@ def _main(out):
     h_obs, h_priv, h_rew = torch.empty(N, 45).pin_memory(), torch.empty(N, 263).pin_memory(), torch.empty(N).pin_memory()
     h_reset = torch.empty(N, dtype=torch.uint8).pin_memory()
 
-    host_graphs = _ops.GraphSet()       # the per-step policy / bookkeeping launches of the host-buffer loop, replayed (the env call itself is the C-ABI entry point)
-
     def iteration_host():
-        alg.storage.step = 0
-        with torch.inference_mode():
-            alg.begin_rollout(STEPS_PER_ENV)                                  # device-resident sampling counters, as in runner.collect()
-            for t in range(STEPS_PER_ENV):
-                alg.storage.step = t
-
-                def act_body():
-                    act(env.obs_buf, env.privileged_obs_buf)
-                    if getattr(alg, "_join_pending", False):                  # the critic's side stream rejoins before the actions leave the device
-                        alg._side.join(); alg._join_pending = False
-                host_graphs.run(("act", t), act_body)
-                a = alg._actions_env if is_cts else alg.storage.actions[t]
-                h_act.copy_(a)                                                # D2H of the policy output (synchronises)
-                env.step_host(h_act.numpy(), h_obs.numpy(), h_priv.numpy(), h_rew.numpy(), h_reset.numpy())
-                alg.storage.step = t
-
-                def proc_body():
-                    after_step(env.obs_buf, env.reset_buf)
-                    alg.process_env_step(env.rew_buf, env.reset_buf, {"time_outs": env.time_out_buf})
-                host_graphs.run(("proc", t), proc_body)
-            alg.end_rollout(STEPS_PER_ENV)
-            if is_cts:
-                runner._compute_returns(env.obs_buf, env.privileged_obs_buf)
-            else:
-                alg.compute_returns(env.privileged_obs_buf)
-        return alg.update()                                                   # ends with the D2H read of the losses
+        """the runner's own host-buffer iteration (rl/runners: run_iteration_host -> collect_host -> env.step_host = go2_env_step_host)"""
+        return runner.run_iteration_host(h_act, h_obs, h_priv, h_rew, h_reset)
 
     for _ in range(2):                                                        # eager pass, then the pass that captures the per-step graphs
         iteration_host()

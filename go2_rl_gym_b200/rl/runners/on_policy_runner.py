@@ -104,6 +104,46 @@ class OnPolicyRunner:
             keep = torch.stack(flags).cpu().tolist() if flags else []
             return [e for (e, v), k in zip(ep_infos, keep or [1.0] * len(ep_infos)) if k > 0]
 
+    def collect_host(self, h_actions, h_obs, h_priv, h_rew, h_reset):
+        """One rollout with the env reached through its HOST-buffer entry point (`go2_env_step_host`, the call an external simulator loop or a
+        logging host would make): every step copies the sampled actions into the pinned host tensor `h_actions`, the C call uploads them, steps and
+        downloads observations / privileged observations / rewards / resets into the other four host tensors.  The policy inference + sampling in
+        front of the call and the transition bookkeeping behind it are replayed as per-step CUDA graphs."""
+        env, alg, T = self.env, self.alg, self.num_steps_per_env
+        if not hasattr(self, "_host_graphs"):
+            self._host_graphs = _ops.GraphSet()
+        with torch.inference_mode():
+            alg.begin_rollout(T)                      # device-resident sampling counters, as in collect()
+            for t in range(T):
+                alg.storage.step = t
+                self._host_graphs.run(("act", t), lambda: self._host_act(t))
+                h_actions.copy_(self._host_actions(t))            # D2H of the policy output (synchronises)
+                env.step_host(h_actions.numpy(), h_obs.numpy(), h_priv.numpy(), h_rew.numpy(), h_reset.numpy())
+                alg.storage.step = t
+                self._host_graphs.run(("proc", t), self._host_proc)
+            alg.end_rollout(T)
+
+    def _host_act(self, t):
+        env, alg = self.env, self.alg
+        alg.act(env.obs_buf, env.privileged_obs_buf)
+        if getattr(alg, "_join_pending", False):      # the critic's side stream rejoins before the actions leave the device
+            alg._side.join(); alg._join_pending = False
+
+    def _host_actions(self, t):
+        return self.alg.storage.actions[t]
+
+    def _host_proc(self):
+        env = self.env
+        self.alg.process_env_step(env.rew_buf, env.reset_buf, {"time_outs": env.time_out_buf})
+
+    def run_iteration_host(self, h_actions, h_obs, h_priv, h_rew, h_reset):
+        """collect_host() + returns + update: one iteration end to end through host buffers (bench.py `e2e`)."""
+        self.collect_host(h_actions, h_obs, h_priv, h_rew, h_reset)
+        env = self.env
+        with torch.inference_mode():
+            self.alg.compute_returns(env.privileged_obs_buf)
+        return self.alg.update()                      # ends with the D2H read of the losses
+
     def run_iteration(self, sync=None):
         """One un-logged iteration (rollout + returns + update) — the timing loop of bench.py / tools."""
         self.collect(False)

@@ -11,6 +11,7 @@ import torch
 import yaml
 
 from .. import _ops
+from .on_policy_runner import OnPolicyRunner
 from ..algorithms import CTS, MoECTS, MoENGCTS, ACMoECTS, DualMoECTS, MCPCTS
 from ..modules import (ActorCriticCTS, ActorCriticMoECTS, ActorCriticMoENGCTS, ActorCriticACMoECTS, ActorCriticDualMoECTS,
                        ActorCriticMCPCTS)
@@ -98,6 +99,33 @@ class OnPolicyRunnerCTS:
             flags = [v for _, v in ep_infos if v is not None]
             keep = torch.stack(flags).cpu().tolist() if flags else []
             return [e for (e, v), k in zip(ep_infos, keep or [1.0] * len(ep_infos)) if k > 0]
+
+    # host-buffer rollout: same loop as OnPolicyRunner.collect_host (history in the policy input, history roll before the bookkeeping)
+    collect_host = OnPolicyRunner.collect_host
+
+    def _host_act(self, t):
+        env, alg = self.env, self.alg
+        alg.act(env.obs_buf, env.privileged_obs_buf, self.history.flatten(1))
+        if getattr(alg, "_join_pending", False):
+            alg._side.join(); alg._join_pending = False
+
+    def _host_actions(self, t):
+        return self.alg._actions_env
+
+    def _host_proc(self):
+        env = self.env
+        self._roll_history(env.obs_buf, env.reset_buf)
+        self.alg.process_env_step(env.rew_buf, env.reset_buf, {"time_outs": env.time_out_buf})
+
+    def run_iteration_host(self, h_actions, h_obs, h_priv, h_rew, h_reset):
+        env = self.env
+        if not getattr(self, "_hist_primed", False):
+            self._roll_history(env.get_observations(), None)
+            self._hist_primed = True
+        self.collect_host(h_actions, h_obs, h_priv, h_rew, h_reset)
+        with torch.inference_mode():
+            self._compute_returns(env.obs_buf, env.privileged_obs_buf)
+        return self.alg.update()
 
     def run_iteration(self, sync=None):
         """One un-logged iteration (rollout + returns + both update passes) — the timing loop of bench.py / tools."""

@@ -333,11 +333,13 @@ def test_runner_learns_two_iterations(tmp_path):
 @pytest.mark.parametrize("log", [False, True])
 def test_graph_rollout_equals_eager_rollout(task, log):
     """The rollout replayed as ONE CUDA graph over device-resident step parameters (runner.collect) must leave exactly the bits the
-    per-step launches leave: env state, counters and every row of the rollout storage, over 3 rollouts (eager, capture + replay, replay)."""
+    per-step launches leave: env state, counters and every row of the rollout storage, over 3 rollouts (eager, capture + replay, replay) — and
+    so must the host-buffer rollout (runner.collect_host, the path bench.py's `e2e` times)."""
     from go2_rl_gym_b200.envs import task_registry
     from go2_rl_gym_b200.utils import get_args
     outs = []
-    for graphs in (True, False):
+    for mode in ("graph", "eager") + (() if log else ("host",)):
+        graphs = mode == "graph"
         args = get_args(["--task", task, "--num_envs", "512", "--headless"])
         env, _ = task_registry.make_env(task, args)
         runner, _ = task_registry.make_alg_runner(env, task, args, log_root=None)
@@ -346,12 +348,23 @@ def test_graph_rollout_equals_eager_rollout(task, log):
             runner._roll_history(env.get_observations(), None)
         env.episode_length_buf = torch.randint(1100, 1250, (512,), generator=torch.Generator().manual_seed(1)).cuda()     # time-outs inside the rollouts
         infos = []
-        for _ in range(3):
-            infos = runner.collect(log)
-        torch.cuda.synchronize()
+        if mode == "host":
+            # the same three rollouts through the HOST-buffer entry point (runner.collect_host -> env.step_host -> go2_env_step_host): actions up,
+            # observations / rewards / resets down every step, the policy launches replayed as per-step graphs — and what came down is the device state
+            h = [torch.empty(512, 12).pin_memory(), torch.empty(512, 45).pin_memory(), torch.empty(512, 263).pin_memory(), torch.empty(512).pin_memory(),
+                 torch.empty(512, dtype=torch.uint8).pin_memory()]
+            for _ in range(3):
+                runner.collect_host(*h)
+            torch.cuda.synchronize()
+            assert torch.equal(h[1], env.obs_buf.cpu()) and torch.equal(h[2], env.privileged_obs_buf.cpu()) and torch.equal(h[3], env.rew_buf.cpu())
+            assert ("act", 23) in runner._host_graphs._g and not runner._host_graphs._failed
+        else:
+            for _ in range(3):
+                infos = runner.collect(log)
+            torch.cuda.synchronize()
+            assert len(infos) == (24 if log else 0)
         if graphs:
             assert ("rollout", log) in runner._rollout_graphs._g and not runner._rollout_graphs._failed      # the graph path really ran
-        assert len(infos) == (24 if log else 0)
         st = runner.alg.storage
         out = {k: getattr(st, k).clone() for k in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "mu", "actions_log_prob")}
         out.update(root=env.root_states.clone(), q=env.dof_pos.clone(), ep_len=env.episode_length_buf.clone(), levels=env.terrain_levels.clone(),
@@ -361,9 +374,10 @@ def test_graph_rollout_equals_eager_rollout(task, log):
         outs.append(out)
         assert int(st.dones.sum()) > 50
         del runner, env
-    for k in outs[0]:
-        a, b = outs[0][k], outs[1][k]
-        assert (torch.equal(a, b) if torch.is_tensor(a) else a == b), k
+    for o in outs[1:]:
+        for k in outs[0]:
+            a, b = outs[0][k], o[k]
+            assert (torch.equal(a, b) if torch.is_tensor(a) else a == b), k
 
 
 @pytest.mark.parametrize("task", ["go2", "go2_moe_cts"])
