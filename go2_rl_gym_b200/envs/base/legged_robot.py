@@ -202,11 +202,14 @@ class LeggedRobot:
             self.extras["time_outs"] = self.time_out_buf
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
-    def end_rollout(self):
+    def end_rollout(self, fetch=True):
         """extras of the rollout's steps (what step() would have returned in infos['episode'] at each of them): a step without a reset re-serves the
         previous step's statistics (the kernel copies the row forward) and nothing is served before the first reset ever, like the reference's
         extras dict, which has no 'episode' key until then (legged_robot.py:229-242, on_policy_runner.py:145-146).  One D2H read per rollout."""
         assert len(self._rollout_slots) <= EP_SLOTS, "num_steps_per_env must not exceed the episode-statistics ring (GO2_EP_SLOTS)"
+        if not fetch:        # un-logged rollout: no host read, the host runs ahead of the device (the statistics stay in the device ring)
+            self._fill_extras(self._rollout_slots[-1])
+            return []
         valid = self._A.tensors["ep_stats"][self._rollout_slots, _abi.NUM_REW + 11].cpu()
         eps = []
         for slot, v in zip(self._rollout_slots, valid.tolist()):

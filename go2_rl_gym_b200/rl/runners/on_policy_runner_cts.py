@@ -92,8 +92,7 @@ class OnPolicyRunnerCTS:
                     self._rollout_graphs.run(("rollout", bool(log)), lambda: self._rollout_steps(log, True))
                 finally:
                     alg.end_rollout(T)
-                ep_infos = env.end_rollout()
-                return ep_infos if log else []
+                return env.end_rollout(fetch=bool(log))      # un-logged: no device -> host read at the end of the rollout
             ep_infos = self._rollout_steps(log, False)
             # eager steps serve extras["episode"] without a host sync; rows from before the env's first reset are dropped here, once per rollout
             flags = [v for _, v in ep_infos if v is not None]
