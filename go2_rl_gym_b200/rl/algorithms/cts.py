@@ -208,7 +208,8 @@ class CTS:
         return self._priv_p
 
     # ---- update --------------------------------------------------------------------------------------------------------
-    def update(self, teacher_perm=None, student_perm=None):
+    def update(self, teacher_perm=None, student_perm=None, fetch=True):
+        """fetch=False: no host read of the logged means at the end (see PPO.update)."""
         st, m = self.storage, self.model
         idx, tm, sm = st.batch_indices(self.num_mini_batches, teacher_perm, student_perm)
         tc = _ops.use_tc()
@@ -239,6 +240,9 @@ class CTS:
                         m.mark_dirty()
         m.mark_dirty()
         n = self.num_learning_epochs * self.num_mini_batches
+        if not fetch:
+            st.clear()
+            return None
         if self.world_size > 1:      # pass 2's logged means are per-rank sums (pass 1's travel in the gradient's scalar tail): one small collective per iteration
             self._reduce_logs()
         log, log2 = self._log.tolist(), self._log2.tolist()      # the single host sync of update()
@@ -454,9 +458,9 @@ class ACMoECTS(CTS):
         self.storage.compute_returns(self._last_values, self.gamma, self.lam,
                                      reduce_stats=(lambda s: dist_utils.allreduce_adv_stats(s, N * self.storage.num_transitions_per_env)) if self.world_size > 1 else None)
 
-    def update(self, teacher_perm=None, student_perm=None):
+    def update(self, teacher_perm=None, student_perm=None, fetch=True):
         self._log3.zero_()
-        return super().update(teacher_perm, student_perm)
+        return super().update(teacher_perm, student_perm, fetch=fetch)
 
     def _grad1(self, i):
         st, m, sh = self.storage, self.model, self._sh

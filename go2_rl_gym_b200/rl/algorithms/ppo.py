@@ -156,7 +156,9 @@ class PPO:
         return dist_utils.allreduce_adv_stats(stats, self.storage.num_envs * self.storage.num_transitions_per_env)
 
     # ---- update ----------------------------------------------------------------------------------------------
-    def update(self, indices=None):
+    def update(self, indices=None, fetch=True):
+        """fetch=False: no host read of the logged means at the end (an un-logged iteration; the host runs ahead of the device, the learning rate
+        lives on the device anyway) -> returns None and leaves `learning_rate` at its last fetched value."""
         st, ac = self.storage, self.actor_critic
         mb, A = self.mini_batch_size, st.actions.shape[-1]
         sh_w = (st.privileged_observations if st.privileged_observations is not None else st.observations).shape[-1]
@@ -184,6 +186,9 @@ class PPO:
         ac.actor_engine.mark_dirty(); ac.critic_engine.mark_dirty()
         self._opt_step += self.num_learning_epochs * self.num_mini_batches
         num_updates = self.num_learning_epochs * self.num_mini_batches
+        if not fetch:
+            st.clear()
+            return None
         log = self._log.tolist()          # the single host sync of update()
         self.learning_rate = log[3]
         st.clear()

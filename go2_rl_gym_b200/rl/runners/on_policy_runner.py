@@ -143,7 +143,7 @@ class OnPolicyRunner:
             self.alg.compute_returns(env.privileged_obs_buf)
         return self.alg.update()                      # ends with the D2H read of the losses
 
-    def run_iteration(self, sync=None):
+    def run_iteration(self, sync=None, fetch_losses=True):
         """One un-logged iteration (rollout + returns + update) — the timing loop of bench.py / tools."""
         self.collect(False)
         priv = self.env.get_privileged_observations()
@@ -152,7 +152,7 @@ class OnPolicyRunner:
             if sync is not None:
                 sync()
             self.alg.compute_returns(cobs)
-        return self.alg.update()
+        return self.alg.update(fetch=fetch_losses)
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         if self.log_dir is not None and self.writer is None and SummaryWriter is not None:

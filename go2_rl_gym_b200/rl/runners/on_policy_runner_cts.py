@@ -126,7 +126,7 @@ class OnPolicyRunnerCTS:
             self._compute_returns(env.obs_buf, env.privileged_obs_buf)
         return self.alg.update()
 
-    def run_iteration(self, sync=None):
+    def run_iteration(self, sync=None, fetch_losses=True):
         """One un-logged iteration (rollout + returns + both update passes) — the timing loop of bench.py / tools."""
         env, alg = self.env, self.alg
         if not getattr(self, "_hist_primed", False):
@@ -137,7 +137,7 @@ class OnPolicyRunnerCTS:
             if sync is not None:
                 sync()
             self._compute_returns(env.get_observations(), env.get_privileged_observations())
-        return alg.update()
+        return alg.update(fetch=fetch_losses)
 
     def _compute_returns(self, obs, privileged_obs):
         if self._returns_need_obs:
