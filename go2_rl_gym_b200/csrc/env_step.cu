@@ -14,6 +14,7 @@
 namespace go2 {
 
 constexpr int WARPS_PER_CTA = 4;
+typedef StepT<1, 0, 6> T1;   // one virtual lane per WIDE thread, both roles in every thread, scratch stride 1 mod 32 words
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 4)
 step_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
@@ -24,7 +25,7 @@ step_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ m
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
   if (!L.own) return;
-  step_env(L, smem, X);
+  step_env<T1>(L, smem, X);
 }
 
 // Same step, W warps per CTA with dynamic shared memory; LOCKSTEP: phases end in a CTA-wide named barrier, so all warps of the CTA
@@ -43,7 +44,7 @@ step_kernel_wide(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
   L.nsync = LOCKSTEP == 1 ? 32 * n_local : 0;
   L.ncoarse = LOCKSTEP >= 2 ? 32 * n_local : 0;
   L.nmid = LOCKSTEP == 3 ? L.ncoarse : 0;
-  step_env(L, smem, X);
+  step_env<T1>(L, smem, X);
 }
 
 // Leg-warp rotation of the packed maps: CTAs that land on the same SM take consecutive tickets, so their leg warps (ticket % warps) sit on
@@ -76,7 +77,7 @@ step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restr
 #if defined(GO2_PHASE_TIMING)
   if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { go2_ph_count = 1; go2_ph_clock[0] = clock64(); }
 #endif
-  step_env(L, smem, X);
+  step_env<T1>(L, smem, X);
 #if defined(GO2_PHASE_TIMING)
   __syncthreads();
   if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { const int k = go2_ph_count; if (k < 512) go2_ph_clock[k] = clock64(); go2_ph_count = k + 1; }
@@ -98,7 +99,26 @@ step_kernel_quad(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
   StepCtx X{cfg, mdl, &buf, sp, actions};
   Lane L;
   init_roles(L, threadIdx.x, 1, e0, min(E, cfg->num_envs - e0), E, pick_leg_warp(E, &leg_warp_slot));
-  step_env(L, smem, X);
+  step_env<T1>(L, smem, X);
+}
+
+// HALF-WARP map "H14" (env_step_core.cuh: init_roles, packed == 2): a CTA of 9 warps owns 14 envs — 7 WIDE warps (16 threads per env, two items per
+// thread) and 2 dedicated LEGS warps — at 112 registers, so that TWO such CTAs (28 envs) are resident per SM and 4096 envs are ONE wave on the 148
+// SMs (the packed map holds 16 envs per SM: 1.73 waves, i.e. two CTA-steps back to back).  The warps are specialised at compile time: each role's
+// instantiation carries only its own per-thread state and instruction stream.
+constexpr int HALF_WARPS = GO2_HALF_ENVS / 2 + 2;
+typedef WarpSmemT<7> HalfSmem;
+__global__ void __launch_bounds__(32 * HALF_WARPS, 2)
+step_kernel_half(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
+                 const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  HalfSmem* smem = reinterpret_cast<HalfSmem*>(smem_dyn);
+  const int e0 = blockIdx.x * GO2_HALF_ENVS;
+  StepCtx X{cfg, mdl, &buf, sp, actions};
+  Lane L;
+  init_roles(L, threadIdx.x, 2, e0, min(GO2_HALF_ENVS, cfg->num_envs - e0), HALF_WARPS);
+  if (threadIdx.x < 32 * (GO2_HALF_ENVS / 2)) step_env<StepT<2, 1, 7>>(L, smem, X);
+  else step_env<StepT<2, 2, 7>>(L, smem, X);
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
@@ -110,7 +130,7 @@ reset_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ 
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
   if (!L.own) return;
-  reset_env_initial(L, smem, X);
+  reset_env_initial<T1>(L, smem, X);
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
@@ -122,7 +142,7 @@ substeps_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
   if (!L.own) return;
-  substeps_env(L, smem, X, tau, n);
+  substeps_env<T1>(L, smem, X, tau, n);
 }
 
 // extras["episode"] (legged_robot.py:229-242): refreshed only when at least one env reset this step; then clear the sums
@@ -164,7 +184,7 @@ struct Go2Env {
 
 static int parse_step_mode(const char* m) {
   return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : !strcmp(m, "Q2") ? 5
-       : !strcmp(m, "P2r") ? 6 : !strcmp(m, "P2b") ? 7 : -1;
+       : !strcmp(m, "P2r") ? 6 : !strcmp(m, "P2b") ? 7 : !strcmp(m, "H14") ? 8 : -1;
 }
 
 namespace go2 {
@@ -187,6 +207,12 @@ static int launch_quad(Go2Env* h, const float* actions, const Go2StepParams* sp,
   const int smem = E * (int)sizeof(WarpSmem);
   GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_quad<E, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   step_kernel_quad<E, MINB><<<(h->cfg.num_envs + E - 1) / E, 32 * E, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
+  return 0;
+}
+static int launch_half(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
+  const int smem = GO2_HALF_ENVS * (int)sizeof(HalfSmem);
+  GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_half, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  step_kernel_half<<<(h->cfg.num_envs + GO2_HALF_ENVS - 1) / GO2_HALF_ENVS, 32 * HALF_WARPS, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
   return 0;
 }
 }  // namespace go2
@@ -251,7 +277,7 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
 //   "8p": warp per env, 8 warps per CTA, CTA barrier at substep boundaries (the previous default: 203 us at 4096 envs)
 //   "4" : warp per env, 4 warps per CTA, no barrier (the first kernel: 239 us)
 int go2_env_set_step_mode(Go2Env* h, const char* mode) {
-  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P2r, P2b, P3, Q4, Q2, 8p, 4)");
+  if (!h || !mode || parse_step_mode(mode) < 0) return go2::set_error(1, "go2_env_set_step_mode: unknown mode (P2, P2r, P2b, P3, Q4, Q2, H14, 8p, 4)");
   h->step_mode = parse_step_mode(mode);
   return 0;
 }
@@ -277,7 +303,7 @@ int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, v
   else {
     int rc = mode == 1 ? go2::launch_wide<8, 2, 2>(h, actions, sp, st) : mode == 2 ? go2::launch_packed<2, 0>(h, actions, sp, st)
            : mode == 3 ? go2::launch_packed<3, 0>(h, actions, sp, st) : mode == 4 ? go2::launch_quad<4, 4>(h, actions, sp, st)
-           : mode == 6 ? go2::launch_packed<2, 1>(h, actions, sp, st) : mode == 7 ? go2::launch_packed<2, 2>(h, actions, sp, st) : go2::launch_quad<2, 8>(h, actions, sp, st);
+           : mode == 8 ? go2::launch_half(h, actions, sp, st) : mode == 6 ? go2::launch_packed<2, 1>(h, actions, sp, st) : mode == 7 ? go2::launch_packed<2, 2>(h, actions, sp, st) : go2::launch_quad<2, 8>(h, actions, sp, st);
     if (rc) return rc;
   }
   go2::count_launch();

@@ -37,6 +37,7 @@
 #define GO2_FMUL(a, b) __fmul_rn((a), (b))
 #define GO2_FADD(a, b) __fadd_rn((a), (b))
 #define GO2_LDG(p) __ldg(p)
+#define GO2_UNROLL _Pragma("unroll")
 #else
 #define GO2_EACH for (int tid_ = 0; tid_ < NT; ++tid_) if (Lane& L = lanes[tid_]; true)
 #define GO2_SYNC() do { } while (0)
@@ -44,11 +45,22 @@
 #define GO2_FMUL(a, b) ((a) * (b))
 #define GO2_FADD(a, b) ((a) + (b))
 #define GO2_LDG(p) (*(p))
+#define GO2_UNROLL
 #endif
 // bind S (the item's env scratch), e (its env id) and lane (the item index within the role) for the block that follows
-#define GO2_BIND(slot, idx) if (WarpSmem& S = SM[slot]; true) if (const int e = L.e0 + (slot), lane = (idx); (void)e, (void)lane, true)
-#define GO2_WIDE GO2_EACH if (L.own) GO2_BIND(L.w, L.lane)
-#define GO2_LEGS GO2_EACH if (L.leg >= 0) GO2_BIND(L.wl, L.leg)
+#define GO2_BIND(slot, idx) if (auto& S = SM[slot]; true) if (const int e = L.e0 + (slot), lane = (idx); (void)e, (void)lane, true)
+// WIDE: a thread owns T::NV "virtual lanes" of its env (NV = 1: lane = the thread's lane in the env's warp; NV = 2, the half-warp maps: an env
+// is served by 16 threads, thread k runs the block for item k and then for item k + 16).  vh is visible inside the block (per-collider state).
+// T::ROLE prunes the other role's code at compile time in kernels whose warps are specialised (0 = both roles, 1 = WIDE only, 2 = LEGS only).
+#if defined(__CUDACC__)   /* the kernel's map is a compile-time property */
+#define GO2_VLANE(vh) ((T::NV == 2 ? (L.lane & 15) : L.lane) + 16 * (vh))
+#define GO2_NV_OK(vh) true
+#else                     /* the emulation is compiled once (T::NV = 2) and takes the map from init_roles */
+#define GO2_VLANE(vh) ((L.nv == 2 ? (L.lane & 15) : L.lane) + 16 * (vh))
+#define GO2_NV_OK(vh) ((vh) < L.nv)
+#endif
+#define GO2_WIDE GO2_EACH if (T::ROLE != 2 && L.own) GO2_UNROLL for (int vh = 0; vh < T::NV; ++vh) if (GO2_NV_OK(vh)) GO2_BIND(L.w, GO2_VLANE(vh))
+#define GO2_LEGS GO2_EACH if (T::ROLE != 1 && L.leg >= 0) GO2_BIND(L.wl, L.leg)
 
 namespace go2 {
 
@@ -237,7 +249,8 @@ GO2_HD void base_inverse(const Sym6& I, M3& P, M3& Q, M3& R) {
 }
 
 // ------------------------------------------------------------------------------------------------ per-warp scratch
-struct WarpSmem {
+template <int PAD>
+struct WarpSmemT {
   float inertia[GO2_NUM_DYN * GO2_INERTIA_STRIDE];
   float Rw[GO2_NUM_DYN][9];
   float pw[GO2_NUM_DYN][3];
@@ -247,7 +260,10 @@ struct WarpSmem {
   float Lam[GO2_NUM_DYN][27];  // mobility blocks P, Q, R of bodies 1..12 (index 0 unused, base uses Lam0)
   float Lam0[36];              // (I^A_0)^-1, full 6x6
   float legIA[4][27], legpA[4][6], legp[4][6];
-  float fcol[GO2_NUM_COL][6];  // spatial impulse of each collider on its body (body coords)
+  union {                      // the contact phases of the substeps / the post-physics phases
+    float fcol[GO2_NUM_COL][6];    // spatial impulse of each collider on its body (body coords)
+    float heights[GO2_NUM_HEIGHT]; // height scan (written after the last substep)
+  };
   float pcol[GO2_NUM_COL][3];  // world impulse of each collider
   float tgt[12][2];            // joint-limit target velocities (lower, upper row)
   float Dje[12];               // limit-row step limit_relax / (M^-1)_jj (limit_relax > 0)
@@ -261,7 +277,6 @@ struct WarpSmem {
   float root[13];
   float cf[GO2_NUM_REPORT][3];
   float feet[4][6];
-  float heights[GO2_NUM_HEIGHT];
   float obsrow[76];            // proprioceptive columns of the privileged observation (go2_env.py:36-47), before clipping
   float part[32];
   float jterm[7][12];
@@ -274,10 +289,16 @@ struct WarpSmem {
   float env_origin[3];
   int active[GO2_NUM_COL];
   int ep_len, reset, tout, last_lim, level, ttype, tid, delay_start;
-  int pad_[11];   // stride = 1 mod 32 words: consecutive envs start one bank apart (the packed map reads 8 envs' scratch from one warp)
+  int pad_[PAD];  // PAD = 6: stride = 1 mod 32 words, consecutive envs start one bank apart (the packed maps read 8 envs' scratch from one warp);
+                  // PAD = 7: stride = 2 mod 32 words (half-warp maps: the two envs of a warp are 8 slots = 16 banks apart)
 };
-static_assert((sizeof(WarpSmem) / 4) % 32 == 1, "WarpSmem stride must be 1 mod 32 words");
+typedef WarpSmemT<6> WarpSmem;
+static_assert((sizeof(WarpSmemT<6>) / 4) % 32 == 1, "WarpSmemT<6> stride must be 1 mod 32 words");
+static_assert((sizeof(WarpSmemT<7>) / 4) % 32 == 2, "WarpSmemT<7> stride must be 2 mod 32 words");
+// compile-time description of a kernel's thread map: virtual lanes per WIDE thread, role pruning, shared-memory stride
+template <int NV_, int ROLE_, int PAD_> struct StepT { static constexpr int NV = NV_, ROLE = ROLE_; typedef WarpSmemT<PAD_> Smem; };
 
+#define GO2_HALF_ENVS 14   /* envs per barrier group of the half-warp map */
 struct Lane {
   // joint lanes (0..11)
   float kp, kd, mzo, mstr;
@@ -285,11 +306,10 @@ struct Lane {
   float c[3], s[3], Dinv[3], u[3], uI[3];
   float U[3][6], cb[3][6];
   float lam_lo[3], lam_hi[3];   // accumulated joint-limit impulses of the leg's joints
-  // collider lanes (0..31)
-  float n[3], Winv[6], vt, r[3], p[3], gsplit;
-  int body, act;
+  // collider items (one per virtual lane)
+  struct Col { float n[3], Winv[6], vt, r[3], gsplit; int body, act; } col[2];
   // thread map (init_roles): own env slot / lane, leg item, base-column item, first env id of the group, slots of the group
-  int own, w, lane;
+  int own, w, lane, nv;
   int leg, wl;
   int e0, w0, nw;
   // phase barrier: 0 = warp-level (__syncwarp); otherwise the number of threads of the CTA-wide named barrier every phase ends in
@@ -327,25 +347,56 @@ __device__ __forceinline__ void go2_phase_sync(const Lane& L) {
 //                (measured in round 1: scheduler 0 saturated, the other three a third busy); the kernels rotate it per SM.
 GO2_HD void init_roles(Lane& L, int tid, int packed, int e0, int n_local, int nwarps, int leg_warp = 0) {
   const int warp = tid >> 5, lane = tid & 31;
-  L.e0 = e0; L.w = warp; L.lane = lane;
+  L.e0 = e0; L.w = warp; L.lane = lane; L.nv = 1;
   L.own = warp < n_local;
   L.ncoarse = 0; L.nmid = 0;
   if (!packed) {
     L.leg = (L.own && lane < 4) ? lane : -1; L.wl = warp;
     L.w0 = warp; L.nw = 1;
     L.nsync = 0;
-  } else {
+  } else if (packed == 1) {
     L.leg = (warp == leg_warp && (lane >> 2) < n_local) ? (lane & 3) : -1; L.wl = lane >> 2;
+    L.w0 = 0; L.nw = n_local;
+    L.nsync = 32 * nwarps;
+  } else {
+    // packed == 2, the HALF-WARP map ("H14"): a group of 14 envs = 7 WIDE warps (16 threads per env, two virtual lanes each) + 2 dedicated
+    // LEGS warps (56 (env, leg) items).  Warp w < 6 serves slots w and w + 8, warp 6 slots 6 and 7: with a scratch stride of 2 mod 32 words the
+    // two halves of warps 0..5 sit 16 banks apart.  28 envs are resident per SM (two groups): 4096 envs are ONE wave on 148 SMs.
+    const int nwide = GO2_HALF_ENVS / 2;
+    if (warp < nwide) {
+      const int h = lane >> 4;
+      L.w = warp < nwide - 1 ? warp + 8 * h : nwide - 1 + h;
+      L.lane = lane & 15; L.nv = 2;
+      L.own = L.w < n_local;
+      L.leg = -1; L.wl = 0;
+    } else {
+      const int it = (warp - nwide) * 32 + lane;
+      L.w = 0; L.own = 0;
+      L.wl = it >> 2;
+      L.leg = (L.wl < n_local && L.wl < GO2_HALF_ENVS) ? (it & 3) : -1;
+      if (L.leg < 0) L.wl = 0;
+    }
     L.w0 = 0; L.nw = n_local;
     L.nsync = 32 * nwarps;
   }
 }
 // does any env of the thread's group reset this step?  (uniform over the threads that share phase barriers)
-GO2_HD bool group_any_reset(const Lane& L, const WarpSmem* SM) {
+template <class SMT>
+GO2_HD bool group_any_reset(const Lane& L, const SMT* SM) {
   bool any = false;
   for (int k = 0; k < L.nw; ++k) any = any || (SM[L.w0 + k].reset != 0);
   return any;
 }
+
+#if defined(__CUDACC__)
+template <class T> __device__ __forceinline__ bool own_warp_any_reset(const Lane& L, const typename T::Smem* SM) {
+  if (T::NV == 1) return SM[L.w].reset != 0;
+  // the two slots of the thread's warp: its own and its partner's (slot pairs of init_roles, packed == 2)
+  const int nwide = GO2_HALF_ENVS / 2, warp = threadIdx.x >> 5;
+  const int s0 = warp < nwide - 1 ? warp : nwide - 1, s1 = warp < nwide - 1 ? warp + 8 : nwide;
+  return (s0 < L.nw && SM[s0].reset != 0) || (s1 < L.nw && SM[s1].reset != 0);
+}
+#endif
 
 struct StepCtx {
   const Go2EnvConfig* cfg; const Go2Model* mdl; const Go2EnvBuffers* buf; const Go2StepParams* sp;
@@ -381,8 +432,8 @@ GO2_HD void terrain_query(const Go2EnvConfig* C, const int16_t* hs, float x, flo
 // Pass 1 + 2 of the articulated-body algorithm for the three links of leg l (hip, thigh, calf), leaves to root.
 // Leaves U, Dinv, u, c (bias accel), (c,s) in the Lane; writes world transforms, start velocities and the leg's
 // contribution to the base's articulated inertia / bias force into shared memory.
-template <int I>
-GO2_HD void leg_pass1(int l, Lane& L, WarpSmem& S, const Go2Model* M, V6& vpar, M3& Rwp, V3& pwp, V6 (&vl)[3], V6 (&pA)[3]) {
+template <int I, class SMT>
+GO2_HD void leg_pass1(int l, Lane& L, SMT& S, const Go2Model* M, V6& vpar, M3& Rwp, V3& pwp, V6 (&vl)[3], V6 (&pA)[3]) {
   constexpr int AX = LinkAxis<I>::ax;
   const int j = 3 * l + I, b = j + 1;
   float c = S.cs[j][0], s = S.cs[j][1];
@@ -421,8 +472,8 @@ GO2_HD void leg_pass1(int l, Lane& L, WarpSmem& S, const Go2Model* M, V6& vpar, 
 }
 
 // one backward step: consumes the articulated inertia IA / bias pA of link I, returns their contribution to the parent
-template <int I>
-GO2_HD void leg_pass2(int l, Lane& L, WarpSmem& S, const Go2Model* M, Sym6& IA, V6& pA, Sym6& IAout, V6& pAout) {
+template <int I, class SMT>
+GO2_HD void leg_pass2(int l, Lane& L, SMT& S, const Go2Model* M, Sym6& IA, V6& pA, Sym6& IAout, V6& pAout) {
   constexpr int AX = LinkAxis<I>::ax;
   const int j = 3 * l + I;
   float c = L.c[I], s = L.s[I];
@@ -465,8 +516,8 @@ GO2_HD void leg_pass2(int l, Lane& L, WarpSmem& S, const Go2Model* M, Sym6& IA, 
 }
 
 // impulse response, inward: p (force-space, body coords) of link I -> contribution to the parent; stores uI
-template <int I>
-GO2_HD void leg_imp_in(int l, Lane& L, const WarpSmem& S, const Go2Model* M, const V6& p, V6& pout) {
+template <int I, class SMT>
+GO2_HD void leg_imp_in(int l, Lane& L, const SMT& S, const Go2Model* M, const V6& p, V6& pout) {
   constexpr int AX = LinkAxis<I>::ax;
   const int j = 3 * l + I;
   float uI = S.tauimp[j] - comp(p.a, AX);
@@ -480,8 +531,8 @@ GO2_HD void leg_imp_in(int l, Lane& L, const WarpSmem& S, const Go2Model* M, con
   pout.l = fb; pout.a = nb + cross(r, fb);
 }
 // outward: parent's dv -> this link's dv and joint velocity change
-template <int I>
-GO2_HD void leg_imp_out(int l, Lane& L, WarpSmem& S, const Go2Model* M, V6& dvpar) {
+template <int I, class SMT>
+GO2_HD void leg_imp_out(int l, Lane& L, SMT& S, const Go2Model* M, V6& dvpar) {
   constexpr int AX = LinkAxis<I>::ax;
   const int j = 3 * l + I, b = j + 1;
   V3 r = ld3(M->joint_origin[j]);
@@ -496,8 +547,8 @@ GO2_HD void leg_imp_out(int l, Lane& L, WarpSmem& S, const Go2Model* M, V6& dvpa
   dvpar = dp;
 }
 // pass 3 + unconstrained velocity + mobility, outward for link I
-template <int I>
-GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, float limit_relax, V6& apar, V6& vmpar, M3& Pp, M3& Qp, M3& Rp) {
+template <int I, class SMT>
+GO2_HD void leg_pass3(int l, Lane& L, SMT& S, const Go2Model* M, float dt, float limit_relax, V6& apar, V6& vmpar, M3& Pp, M3& Qp, M3& Rp) {
   constexpr int AX = LinkAxis<I>::ax;
   const int j = 3 * l + I, b = j + 1;
   float c = L.c[I], s = L.s[I];
@@ -550,14 +601,16 @@ GO2_HD void leg_pass3(int l, Lane& L, WarpSmem& S, const Go2Model* M, float dt, 
 #if defined(__CUDACC__)
 #define GO2_LANE_ARGS Lane& L
 #define GO2_LANE_PASS L
-#define GO2_ANY_RESET(SM) (SM[L.w].reset != 0)          /* the env's own warp decides alone: reset_phases holds WIDE phases only */
+/* the env's own warp decides alone: reset_phases holds WIDE phases only (half-warp maps: either env of the warp, read through the warp's first thread's view) */
+#define GO2_ANY_RESET(SM) (T::ROLE != 2 && own_warp_any_reset<T>(L, SM))
 #else
 #define GO2_LANE_ARGS Lane* lanes, int NT
 #define GO2_LANE_PASS lanes, NT
 #define GO2_ANY_RESET(SM) group_any_reset(lanes[0], SM)   /* the emulated group walks reset_phases when any of its envs resets */
 #endif
 
-GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool last) {
+template <class T>
+GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, bool last) {
   const Go2EnvConfig* C = X.cfg;
   const Go2Model* M = X.mdl;
   const float dt = C->sim_dt;
@@ -655,12 +708,12 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
   // ---- S6: collider lanes: narrow phase + per-contact 3x3 mobility
   GO2_WIDE {
     {
+      Lane::Col& K = L.col[vh];
       const int ci = lane;
       const int b = M->col_dyn[ci];
-      L.body = b;
+      K.body = b;
       V3 r = ld3(M->col_pos[ci]);
-      L.r[0] = r.x; L.r[1] = r.y; L.r[2] = r.z;
-      L.p[0] = L.p[1] = L.p[2] = 0;
+      K.r[0] = r.x; K.r[1] = r.y; K.r[2] = r.z;
       M3 Rw = ldm(S.Rw[b]);
       V3 cw = ld3(S.pw[b]) + mul(Rw, r);
       float h, dhx, dhy;
@@ -669,8 +722,8 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
       V3 n = mk(-dhx * inv, -dhy * inv, inv);
       float gap = (cw.z - h) * n.z - M->col_radius[ci];
       int act = gap < C->contact_offset;
-      L.act = act; S.active[ci] = act;
-      L.n[0] = n.x; L.n[1] = n.y; L.n[2] = n.z;
+      K.act = act; S.active[ci] = act;
+      K.n[0] = n.x; K.n[1] = n.y; K.n[2] = n.z;
       for (int k = 0; k < 6; ++k) S.fcol[ci][k] = 0;
       S.pcol[ci][0] = S.pcol[ci][1] = S.pcol[ci][2] = 0;
       if (act) {
@@ -686,23 +739,24 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
         float a = W.m[0], bq = W.m[1], c2 = W.m[2], d = W.m[4], e2 = W.m[5], f = W.m[8];
         float c00 = d * f - e2 * e2, c01 = c2 * e2 - bq * f, c02 = bq * e2 - c2 * d;
         float id = 1.0f / (a * c00 + bq * c01 + c2 * c02);
-        L.Winv[0] = c00 * id; L.Winv[1] = c01 * id; L.Winv[2] = c02 * id;
-        L.Winv[3] = (a * f - c2 * c2) * id; L.Winv[4] = (bq * c2 - a * e2) * id; L.Winv[5] = (a * d - bq * bq) * id;
+        K.Winv[0] = c00 * id; K.Winv[1] = c01 * id; K.Winv[2] = c02 * id;
+        K.Winv[3] = (a * f - c2 * c2) * id; K.Winv[4] = (bq * c2 - a * e2) * id; K.Winv[5] = (a * d - bq * bq) * id;
         // normal velocity target; restitution looks at the approach speed at the START of the step
         V6 vsb; ld6(S.vs[b], vsb);
         float vn0 = dot(mul(Rw, vsb.l + cross(vsb.a, r)), n);
         float vt = (gap >= 0) ? -gap / dt : fminf(fmaxf(-gap - C->penetration_slop, 0.0f) * C->erp / dt, C->max_depen_vel);
         if (vn0 < -C->bounce_threshold) vt = fmaxf(vt, -S.rest_env * vn0);
-        L.vt = vt;
+        K.vt = vt;
       }
     }
   } GO2_SYNC_WARP();
   // ---- S7: mass-splitting factor of the collider's group (base = colliders 0..7, leg l = 8+6l .. 13+6l)
   GO2_WIDE {
     {
+      Lane::Col& K = L.col[vh];
       int g0 = lane < 8 ? 0 : 8 + 6 * ((lane - 8) / 6), gn = lane < 8 ? 8 : 6, cnt = 0;
       for (int k = 0; k < gn; ++k) cnt += S.active[g0 + k];
-      L.gsplit = C->contact_relax / (float)cnt;      // block step of the contact rows; only read by active colliders: cnt >= 1
+      K.gsplit = C->contact_relax / (float)cnt;      // block step of the contact rows; only read by active colliders: cnt >= 1
     }
   }
   // ---- Jacobi sweeps with exact propagation through the tree: [collider lanes: block-solve every contact] | CTA barrier |
@@ -710,25 +764,25 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
   GO2_MID_SYNC();
   for (int it = 0; it < C->solver_iters; ++it) {
     GO2_WIDE {
-      if (L.act) {
-        const int b = L.body;
-        V3 r = mk(L.r[0], L.r[1], L.r[2]), n = mk(L.n[0], L.n[1], L.n[2]);
+      Lane::Col& K = L.col[vh];
+      if (K.act) {
+        const int b = K.body;
+        V3 r = mk(K.r[0], K.r[1], K.r[2]), n = mk(K.n[0], K.n[1], K.n[2]);
         M3 Rw = ldm(S.Rw[b]);
         V6 vb, db; ld6(S.v[b], vb); ld6(S.dv[b], db);
         vb.a = vb.a + db.a; vb.l = vb.l + db.l;
         V3 vp = mul(Rw, vb.l + cross(vb.a, r));
-        V3 err = vp - L.vt * n;
-        float is = L.gsplit;
-        V3 we = mk(L.Winv[0] * err.x + L.Winv[1] * err.y + L.Winv[2] * err.z, L.Winv[1] * err.x + L.Winv[3] * err.y + L.Winv[4] * err.z,
-                   L.Winv[2] * err.x + L.Winv[4] * err.y + L.Winv[5] * err.z);
-        V3 pc = mk(L.p[0], L.p[1], L.p[2]) - is * we;
+        V3 err = vp - K.vt * n;
+        float is = K.gsplit;
+        V3 we = mk(K.Winv[0] * err.x + K.Winv[1] * err.y + K.Winv[2] * err.z, K.Winv[1] * err.x + K.Winv[3] * err.y + K.Winv[4] * err.z,
+                   K.Winv[2] * err.x + K.Winv[4] * err.y + K.Winv[5] * err.z);
+        V3 pc = ld3(S.pcol[lane]) - is * we;   // the accumulated impulse lives in pcol (zeroed by the narrow phase)
         float pcn = dot(pc, n);
         float pn = fmaxf(0.0f, pcn);
         V3 pt = pc - pcn * n;
         float ptn = sqrtf(dot(pt, pt)), lim = S.mu_env * pn;
         if (ptn > lim) pt = (ptn > 0 ? lim / ptn : 0.0f) * pt;
         V3 p = pn * n + pt;
-        L.p[0] = p.x; L.p[1] = p.y; L.p[2] = p.z;
         V3 fl = mulT(Rw, p), fn = cross(r, fl);
         st3(S.fcol[lane], fn); st3(S.fcol[lane] + 3, fl);
         st3(S.pcol[lane], p);
@@ -828,7 +882,8 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool 
 
 // State guard (Go2EnvConfig.state_guard): an env whose state is non-finite after the substeps restarts from its initial pose at its origin and
 // resets in this step, so that nothing non-finite reaches the observations / rewards the shared networks train on.  One WIDE phase, lane 0.
-GO2_HD void state_guard(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+template <class T>
+GO2_HD void state_guard(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cfg;
   GO2_WIDE {
     if (lane == 0) {
@@ -850,7 +905,8 @@ GO2_HD void state_guard(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
 }
 
 // feet position / velocity at the current configuration (rigid_body_states refresh, legged_robot.py:109)
-GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+template <class T>
+GO2_HD void feet_kinematics(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2Model* M = X.mdl;
   GO2_WIDE {   // lanes 0..3 of the env's own warp: once per step, between WIDE phases (no CTA barrier on either side)
     if (lane < 4) {
@@ -884,7 +940,8 @@ GO2_HD void feet_kinematics(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
 
 // ================================================================================================ commands / reset (lane 0)
 // legged_robot.py:423-592 for GO2Cfg (dynamic_resample_commands, no heading command); isaacgym_utils.py:32-55
-GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) {
+template <class SMT>
+GO2_HD void resample_commands(SMT& S, const StepCtx& X, int e, int stream) {
   const Go2EnvConfig* C = X.cfg;
   const Go2StepParams* sp = X.sp;
   const uint32_t ge = (uint32_t)(C->env_offset + e);
@@ -957,7 +1014,8 @@ GO2_HD void resample_commands(WarpSmem& S, const StepCtx& X, int e, int stream) 
 }
 
 // yaw-rate command from the heading target (legged_robot.py:411-419; quat_apply and wrap_to_pi in torch's operation order)
-GO2_HD void heading_to_yaw(WarpSmem& S) {
+template <class SMT>
+GO2_HD void heading_to_yaw(SMT& S) {
   const float qx = S.root[3], qy = S.root[4], qz = S.root[5], qw = S.root[6];
   // t = 2 (q_xyz x [1,0,0]) = 2 (0, qz, -qy);  forward = [1,0,0] + qw t + q_xyz x t
   const float ty = GO2_FMUL(qz, 2.0f), tz = GO2_FMUL(-qy, 2.0f);
@@ -979,7 +1037,8 @@ GO2_HD void heading_to_yaw(WarpSmem& S) {
 #endif
 
 // reset_idx for this env (legged_robot.py:180-245, :620-707, :1143-1169); `initial` = the reset at construction
-GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool initial) {
+template <class T>
+GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, bool initial) {
   const Go2EnvConfig* C = X.cfg;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
@@ -1042,7 +1101,8 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, bool ini
 }
 
 // ================================================================================================ load / store
-GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+template <class T>
+GO2_HD void load_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cfg;
   const Go2EnvBuffers* B = X.buf;
   GO2_WIDE {
@@ -1085,7 +1145,8 @@ GO2_HD void load_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   } GO2_SYNC_WARP();
 }
 
-GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+template <class T>
+GO2_HD void store_state(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvBuffers* B = X.buf;
   GO2_WIDE {
     if (lane < 13) B->root_states[(size_t)e * 13 + lane] = S.root[lane];
@@ -1113,7 +1174,8 @@ GO2_HD void store_state(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
 }
 
 // torques for the current substep (legged_robot.py:74-81, :594-618, control_type 'P')
-GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, int sub) {
+template <class T>
+GO2_HD void compute_torques(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, int sub) {
   const Go2EnvConfig* C = X.cfg;
   const Go2Model* M = X.mdl;
   GO2_WIDE {
@@ -1132,20 +1194,21 @@ GO2_HD void compute_torques(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, int s
 }
 
 // ================================================================================================ the full step
-GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
+template <class T>
+GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cfg;
   const Go2Model* M = X.mdl;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
-  load_env(GO2_LANE_PASS, SM, X);
+  load_env<T>(GO2_LANE_PASS, SM, X);
   for (int sub = 0; sub < C->decimation; ++sub) {
     GO2_COARSE_SYNC();
-    compute_torques(GO2_LANE_PASS, SM, X, sub);
-    physics_substep(GO2_LANE_PASS, SM, X, sub == C->decimation - 1);
+    compute_torques<T>(GO2_LANE_PASS, SM, X, sub);
+    physics_substep<T>(GO2_LANE_PASS, SM, X, sub == C->decimation - 1);
   }
   GO2_COARSE_SYNC();
-  state_guard(GO2_LANE_PASS, SM, X);
-  feet_kinematics(GO2_LANE_PASS, SM, X);
+  state_guard<T>(GO2_LANE_PASS, SM, X);
+  feet_kinematics<T>(GO2_LANE_PASS, SM, X);
   // ---- post_physics_step (legged_robot.py:102-142)
   GO2_WIDE {
     // height scan (legged_robot.py:1188-1224, math.py:8-12): yaw-only rotation of the body-frame grid
@@ -1272,7 +1335,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
     if (lane < GO2_NUM_REW) B->episode_sums[(size_t)e * GO2_NUM_REW + lane] += S.termv[lane];
     if (lane == 31) B->rew_buf[e] = S.rew;
   } GO2_SYNC_WARP();
-  if (GO2_ANY_RESET(SM)) reset_phases(GO2_LANE_PASS, SM, X, false);   // warp-uniform (WIDE phases only); items are predicated by their env
+  if (GO2_ANY_RESET(SM)) reset_phases<T>(GO2_LANE_PASS, SM, X, false);   // warp-uniform (WIDE phases only); items are predicated by their env
   GO2_WIDE {
     if (lane == 0) {
       if (C->push_robots && (S.ep_len % C->push_interval == 0)) {  // _push_robots, legged_robot.py:709-724
@@ -1333,36 +1396,38 @@ GO2_HD void step_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) { S.lact[lane] = S.act[lane]; S.lqd[lane] = S.qd[lane]; }
   } GO2_SYNC_WARP();
-  store_state(GO2_LANE_PASS, SM, X);
+  store_state<T>(GO2_LANE_PASS, SM, X);
 }
 
 // reset_idx(all envs) at construction (base_task.py:82-86; the zero-action step that follows is issued by the caller)
-GO2_HD void reset_env_initial(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X) {
-  load_env(GO2_LANE_PASS, SM, X);
+template <class T>
+GO2_HD void reset_env_initial(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
+  load_env<T>(GO2_LANE_PASS, SM, X);
   GO2_WIDE {
     if (lane == 0) { S.tout = 0; }
     if (lane < 4) for (int k = 0; k < 6; ++k) S.feet[lane][k] = 0;
   } GO2_SYNC_WARP();
-  reset_phases(GO2_LANE_PASS, SM, X, true);
-  feet_kinematics(GO2_LANE_PASS, SM, X);
-  store_state(GO2_LANE_PASS, SM, X);
+  reset_phases<T>(GO2_LANE_PASS, SM, X, true);
+  feet_kinematics<T>(GO2_LANE_PASS, SM, X);
+  store_state<T>(GO2_LANE_PASS, SM, X);
 }
 
 // n physics substeps with given joint torques (dynamics parity in isolation)
-GO2_HD void substeps_env(GO2_LANE_ARGS, WarpSmem* SM, const StepCtx& X, const float* tau_in, int n) {
+template <class T>
+GO2_HD void substeps_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, const float* tau_in, int n) {
   const Go2Model* M = X.mdl;
-  load_env(GO2_LANE_PASS, SM, X);
+  load_env<T>(GO2_LANE_PASS, SM, X);
   for (int s = 0; s < n; ++s) {
     GO2_WIDE {
       if (lane < GO2_NUM_DOF) { float lim = M->effort[lane]; S.tau[lane] = fminf(fmaxf(tau_in[(size_t)e * GO2_NUM_DOF + lane], -lim), lim); }
     } GO2_SYNC_WARP();
-    physics_substep(GO2_LANE_PASS, SM, X, s == n - 1);
+    physics_substep<T>(GO2_LANE_PASS, SM, X, s == n - 1);
   }
-  feet_kinematics(GO2_LANE_PASS, SM, X);
+  feet_kinematics<T>(GO2_LANE_PASS, SM, X);
   GO2_WIDE {
     if (lane == 0) { S.reset = X.buf->reset_buf[e]; S.tout = X.buf->time_out_buf[e]; }
   } GO2_SYNC_WARP();
-  store_state(GO2_LANE_PASS, SM, X);
+  store_state<T>(GO2_LANE_PASS, SM, X);
 }
 
 }  // namespace go2

@@ -70,9 +70,10 @@ def test_emulated_kernel_tracks_oracle(packed, N):
     assert n_reset > 0
 
 
-@pytest.mark.parametrize("packed", [True, 4, 2])
+@pytest.mark.parametrize("packed", [True, 4, 2, 14])
 def test_packed_map_is_bit_identical_to_warp_per_env(packed):
-    """The thread maps (warp per env; 8 envs packed per CTA = "P2"; 4 envs packed per CTA = "Q4") run the same arithmetic in the same order:
+    """The thread maps (warp per env; 8 envs packed per CTA = "P2"; 4 envs packed per CTA = "Q4"; 14 envs per group on half-warps with dedicated
+    leg warps = "H14") run the same arithmetic in the same order:
     every buffer must be bit-identical over a rollout with resets."""
     N = 29   # partial last group
     cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.terrain.mesh_type = "heightfield"; cfg.seed = 4

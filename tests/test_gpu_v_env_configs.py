@@ -45,7 +45,7 @@ def test_cuda_tracks_oracle_off_the_training_defaults(name, overrides):
     assert n_reset > 0
 
 
-@pytest.mark.parametrize("mode", ["Q4", "Q2"])
+@pytest.mark.parametrize("mode", ["Q4", "Q2", "H14"])
 def test_q_thread_maps_agree_with_the_default(mode):
     """"Q4" / "Q2" (4 / 2 envs packed per 128- / 64-thread CTA, 4 / 8 CTAs per SM; go2_env_set_step_mode) against the default "P2" map: the
     comparison of tests/test_gpu_properties.py::test_thread_maps_agree, incl. a partially filled last CTA and envs that time out."""
