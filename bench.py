@@ -35,7 +35,7 @@ NUM_ENVS_PER_GPU = 4096
 STEPS_PER_ENV = 24
 ALGO_BYTES_PER_ENV_STEP = 2350          # algorithmic HBM bytes of the fused step kernel per env-step
 OTHER_CONFIGS = [("go2_cts", 8192), ("go2_moe_cts", 4096), ("go2_moe_cts", 8192)]      # BASELINE.json configs[2], [3] (per-GPU share), [4]
-STEP_KERNELS = {"P2": "go2::step_kernel_packed<2>", "P3": "go2::step_kernel_packed<3>", "Q4": "go2::step_kernel_quad<4,4>",
+STEP_KERNELS = {"H14": "go2::step_kernel_half", "P2": "go2::step_kernel_packed<2>", "P3": "go2::step_kernel_packed<3>", "Q4": "go2::step_kernel_quad<4,4>",
                 "Q2": "go2::step_kernel_quad<2,8>", "8p": "go2::step_kernel_wide<8,2,2>", "4": "go2::step_kernel"}
 
 
@@ -360,7 +360,7 @@ def _main(out):
     e2e_value = world * N * STEPS_PER_ENV / (float(ms2) / n_e2e * 1e-3)
     h2d = STEPS_PER_ENV * N * 12 * 4
     d2h = STEPS_PER_ENV * (N * 12 * 4 + N * (45 + 263 + 1) * 4 + N) + 16
-    step_mode = os.environ.get("GO2_STEP_MODE", getattr(env, "step_mode", "P2"))
+    step_mode = os.environ.get("GO2_STEP_MODE", getattr(env, "step_mode", "H14"))
     drop(runner)
     del env, runner, alg
     gc.collect(); torch.cuda.empty_cache()

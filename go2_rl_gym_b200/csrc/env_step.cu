@@ -21,7 +21,7 @@ step_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ m
             const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
   const int e0 = blockIdx.x * WARPS_PER_CTA;
-  StepCtx X{cfg, mdl, &buf, sp, actions};
+  StepCtx X{cfg, mdl, &buf, sp, actions, cfg};
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
   if (!L.own) return;
@@ -37,7 +37,7 @@ step_kernel_wide(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
   const int e0 = blockIdx.x * W, n_local = min(W, cfg->num_envs - e0);
-  StepCtx X{cfg, mdl, &buf, sp, actions};
+  StepCtx X{cfg, mdl, &buf, sp, actions, cfg};
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, n_local, W);
   if (!L.own) return;
@@ -71,7 +71,7 @@ step_kernel_packed(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restr
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
   __shared__ int leg_warp_slot;
   const int e0 = blockIdx.x * 8;
-  StepCtx X{cfg, mdl, &buf, sp, actions};
+  StepCtx X{cfg, mdl, &buf, sp, actions, cfg};
   Lane L;
   init_roles(L, threadIdx.x, 1, e0, min(8, cfg->num_envs - e0), 8, ROT == 1 ? pick_leg_warp(8, &leg_warp_slot) : ROT == 2 ? (int)((blockIdx.x / 148u) & 3u) : 0);
 #if defined(GO2_PHASE_TIMING)
@@ -96,7 +96,7 @@ step_kernel_quad(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
   WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
   __shared__ int leg_warp_slot;
   const int e0 = blockIdx.x * E;
-  StepCtx X{cfg, mdl, &buf, sp, actions};
+  StepCtx X{cfg, mdl, &buf, sp, actions, cfg};
   Lane L;
   init_roles(L, threadIdx.x, 1, e0, min(E, cfg->num_envs - e0), E, pick_leg_warp(E, &leg_warp_slot));
   step_env<T1>(L, smem, X);
@@ -110,15 +110,22 @@ constexpr int HALF_WARPS = GO2_HALF_ENVS / 2 + 2;
 typedef WarpSmemT<7> HalfSmem;
 __global__ void __launch_bounds__(32 * HALF_WARPS, 2)
 step_kernel_half(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
-                 const Go2StepParams* __restrict__ sp, const float* __restrict__ actions) {
+                 const Go2StepParams* __restrict__ sp, const float* __restrict__ actions, const __grid_constant__ Go2EnvConfig cfgv) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   HalfSmem* smem = reinterpret_cast<HalfSmem*>(smem_dyn);
   const int e0 = blockIdx.x * GO2_HALF_ENVS;
-  StepCtx X{cfg, mdl, &buf, sp, actions};
+  StepCtx X{cfg, mdl, &buf, sp, actions, &cfgv};
   Lane L;
-  init_roles(L, threadIdx.x, 2, e0, min(GO2_HALF_ENVS, cfg->num_envs - e0), HALF_WARPS);
+  init_roles(L, threadIdx.x, 2, e0, min(GO2_HALF_ENVS, cfgv.num_envs - e0), HALF_WARPS);
+#if defined(GO2_PHASE_TIMING)
+  if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { go2_ph_count = 1; go2_ph_clock[0] = clock64(); }
+#endif
   if (threadIdx.x < 32 * (GO2_HALF_ENVS / 2)) step_env<StepT<2, 1, 7>>(L, smem, X);
   else step_env<StepT<2, 2, 7>>(L, smem, X);
+#if defined(GO2_PHASE_TIMING)
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { const int k = go2_ph_count; if (k < 512) go2_ph_clock[k] = clock64(); go2_ph_count = k + 1; }
+#endif
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
@@ -126,7 +133,7 @@ reset_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ 
              const Go2StepParams* __restrict__ sp) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
   const int e0 = blockIdx.x * WARPS_PER_CTA;
-  StepCtx X{cfg, mdl, &buf, sp, nullptr};
+  StepCtx X{cfg, mdl, &buf, sp, nullptr, cfg};
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
   if (!L.own) return;
@@ -138,7 +145,7 @@ substeps_kernel(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict
                 const float* __restrict__ tau, int n) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
   const int e0 = blockIdx.x * WARPS_PER_CTA;
-  StepCtx X{cfg, mdl, &buf, nullptr, nullptr};
+  StepCtx X{cfg, mdl, &buf, nullptr, nullptr, cfg};
   Lane L;
   init_roles(L, threadIdx.x, 0, e0, min(WARPS_PER_CTA, cfg->num_envs - e0), WARPS_PER_CTA);
   if (!L.own) return;
@@ -179,11 +186,11 @@ struct Go2Env {
   float* d_id_counts = nullptr;
   Go2StepParams* d_sp = nullptr;  // staging slot of the host-parameter entry points (the kernels read the step parameters from device memory)
   int grid = 0;
-  int step_mode = 2;              // thread map of the step kernel, see go2_env_set_step_mode
+  int step_mode = 8;              // thread map of the step kernel, see go2_env_set_step_mode
 };
 
 static int parse_step_mode(const char* m) {
-  return !m ? 2 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : !strcmp(m, "Q2") ? 5
+  return !m ? 8 : !strcmp(m, "4") ? 0 : !strcmp(m, "8p") ? 1 : !strcmp(m, "P2") ? 2 : !strcmp(m, "P3") ? 3 : !strcmp(m, "Q4") ? 4 : !strcmp(m, "Q2") ? 5
        : !strcmp(m, "P2r") ? 6 : !strcmp(m, "P2b") ? 7 : !strcmp(m, "H14") ? 8 : -1;
 }
 
@@ -212,7 +219,7 @@ static int launch_quad(Go2Env* h, const float* actions, const Go2StepParams* sp,
 static int launch_half(Go2Env* h, const float* actions, const Go2StepParams* sp, cudaStream_t st) {
   const int smem = GO2_HALF_ENVS * (int)sizeof(HalfSmem);
   GO2_CUDA_OK(cudaFuncSetAttribute(step_kernel_half, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  step_kernel_half<<<(h->cfg.num_envs + GO2_HALF_ENVS - 1) / GO2_HALF_ENVS, 32 * HALF_WARPS, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
+  step_kernel_half<<<(h->cfg.num_envs + GO2_HALF_ENVS - 1) / GO2_HALF_ENVS, 32 * HALF_WARPS, smem, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions, h->cfg);
   return 0;
 }
 }  // namespace go2
@@ -269,8 +276,10 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
   return 0;
 }
 
-// Thread map of the step kernel (same results bit for bit; tuning / A-B aid).  Default "P2"; the GO2_STEP_MODE environment variable
+// Thread map of the step kernel (same results bit for bit; tuning / A-B aid).  Default "H14"; the GO2_STEP_MODE environment variable
 // presets it at create time.
+//   "H14": half-warp map, 14 envs per 288-thread CTA (7 WIDE warps, 16 threads per env + 2 dedicated LEGS warps), 2 CTAs/SM at 96 registers: 28 envs
+//   resident per SM, 4096 envs in one wave (measured round 2: 114 us vs 162 us for "P2")
 //   "P2": packed map, 8 envs per 256-thread CTA, 2 CTAs/SM (128 registers) · "P2r": the same with the leg warp rotated per SM through an atomic ticket
 //   (measured round 2: 167 us vs 162 us — the ticket costs more than spreading the leg streams over the schedulers gains) · "P2b": leg warp = (block index / 148) mod 4, no ticket (co-resident CTAs of the first waves get different schedulers) · "P3": 3 CTAs/SM (80 registers)
 //   "Q4" / "Q2": packed map with 4 / 2 envs per 128- / 64-thread CTA, 4 / 8 CTAs/SM (unmeasured: built after round 1's GPU budget was spent)

@@ -401,6 +401,8 @@ template <class T> __device__ __forceinline__ bool own_warp_any_reset(const Lane
 struct StepCtx {
   const Go2EnvConfig* cfg; const Go2Model* mdl; const Go2EnvBuffers* buf; const Go2StepParams* sp;
   const float* actions_in;  // [N,12] or nullptr (reset_all / substeps entry points)
+  const Go2EnvConfig* cs;   // where the SCALAR fields of the config are read from: the H14 kernel passes a by-value copy (kernel parameter space = constant
+                            // bank operands, no load latency); the lane-indexed tables (kp, default_dof_pos, height_points ...) stay behind `cfg` (L1)
 };
 
 // joint axis of link index i within a leg: hip = x, thigh = calf = y (asserted on the host at create time)
@@ -611,7 +613,8 @@ GO2_HD void leg_pass3(int l, Lane& L, SMT& S, const Go2Model* M, float dt, float
 
 template <class T>
 GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, bool last) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2Model* M = X.mdl;
   const float dt = C->sim_dt;
   // ---- S1: joint lanes: sin/cos, limit targets; lane 12: base kinematics
@@ -884,7 +887,8 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
 // resets in this step, so that nothing non-finite reaches the observations / rewards the shared networks train on.  One WIDE phase, lane 0.
 template <class T>
 GO2_HD void state_guard(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   GO2_WIDE {
     if (lane == 0) {
       int bad = 0;
@@ -942,7 +946,8 @@ GO2_HD void feet_kinematics(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
 // legged_robot.py:423-592 for GO2Cfg (dynamic_resample_commands, no heading command); isaacgym_utils.py:32-55
 template <class SMT>
 GO2_HD void resample_commands(SMT& S, const StepCtx& X, int e, int stream) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2StepParams* sp = X.sp;
   const uint32_t ge = (uint32_t)(C->env_offset + e);
   U4 r0 = philox(ge, sp->common_step_counter, (uint32_t)stream, 0, C->seed_lo, C->seed_hi);
@@ -1039,7 +1044,8 @@ GO2_HD void heading_to_yaw(SMT& S) {
 // reset_idx for this env (legged_robot.py:180-245, :620-707, :1143-1169); `initial` = the reset at construction
 template <class T>
 GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, bool initial) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
   GO2_WIDE if (initial || S.reset) {   // only the envs of the group that reset
@@ -1054,7 +1060,7 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, 
         B->d_gains_multiplier[o] = affine(C->kd_mult_range[1], u01(r.w), C->kd_mult_range[0]);
       }
       U4 rq = philox(ge, sp->common_step_counter, ST_RESET_STATE, (uint32_t)(lane / 4), C->seed_lo, C->seed_hi);
-      S.q[lane] = GO2_FMUL(C->default_dof_pos[lane], GO2_FADD(u01(pick(rq, lane % 4)), 0.5f));
+      S.q[lane] = GO2_FMUL(CT->default_dof_pos[lane], GO2_FADD(u01(pick(rq, lane % 4)), 0.5f));
       S.qd[lane] = 0; S.act[lane] = 0; S.lact[lane] = 0; S.lqd[lane] = 0;
     }
     if (lane >= 16 && lane < 16 + GO2_NUM_REW) {
@@ -1103,7 +1109,8 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, 
 // ================================================================================================ load / store
 template <class T>
 GO2_HD void load_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2EnvBuffers* B = X.buf;
   GO2_WIDE {
     for (int i = lane; i < GO2_NUM_DYN * GO2_INERTIA_STRIDE; i += 32) S.inertia[i] = GO2_LDG(B->body_inertia + (size_t)e * GO2_NUM_DYN * GO2_INERTIA_STRIDE + i);
@@ -1115,7 +1122,7 @@ GO2_HD void load_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.tq[lane] = B->torques[o];
       float a = X.actions_in ? X.actions_in[o] : B->actions[o];
       S.act[lane] = fminf(fmaxf(a, -C->clip_actions), C->clip_actions);
-      L.kp = C->kp[lane] * B->p_gains_multiplier[o]; L.kd = C->kd[lane] * B->d_gains_multiplier[o];
+      L.kp = CT->kp[lane] * B->p_gains_multiplier[o]; L.kd = CT->kd[lane] * B->d_gains_multiplier[o];
       L.mzo = B->motor_zero_offsets[o]; L.mstr = B->motor_strengths[o];
     }
     if (lane >= 12 && lane < 16) S.cmd[lane - 12] = B->commands[(size_t)e * GO2_NUM_CMD + lane - 12];
@@ -1161,7 +1168,7 @@ GO2_HD void store_state(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
     if (lane == 25) { B->episode_length_buf[e] = S.ep_len; B->commands_resampling_step[e] = S.resamp_step; }
     if (lane == 26) { B->commands_xy_accumulation[(size_t)e * 2] = S.acc_xy[0]; B->commands_xy_accumulation[(size_t)e * 2 + 1] = S.acc_xy[1]; }
     if (lane == 27) { B->max_move_distance[e] = S.max_move; B->last_is_limit_vel[e] = (uint8_t)S.last_lim; }
-    if (lane == 30 && X.cfg->heading_command) GO2_EXT_PTR(uint8_t*, X.cfg, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
+    if (lane == 30 && X.cs->heading_command) GO2_EXT_PTR(uint8_t*, X.cs, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
     if (lane == 28) B->terrain_levels[e] = S.level;
     if (lane == 29) { B->reset_buf[e] = (uint8_t)S.reset; B->time_out_buf[e] = (uint8_t)S.tout; }
     for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = S.cf[i / 3][i % 3];
@@ -1176,12 +1183,13 @@ GO2_HD void store_state(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
 // torques for the current substep (legged_robot.py:74-81, :594-618, control_type 'P')
 template <class T>
 GO2_HD void compute_torques(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, int sub) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2Model* M = X.mdl;
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
       float a_in = (C->randomize_action_delay && sub < S.delay_start) ? S.lact[lane] : S.act[lane];
-      float t = L.kp * (a_in * C->action_scale + C->default_dof_pos[lane] - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
+      float t = L.kp * (a_in * C->action_scale + CT->default_dof_pos[lane] - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
       if (C->control_type == 1) t = L.kp * (a_in * C->action_scale - S.qd[lane]) - L.kd * (S.qd[lane] - S.lqd[lane]) / C->sim_dt;   // 'V', legged_robot.py:612-613
       else if (C->control_type == 2) t = a_in * C->action_scale;                                                                  // 'T', :614-615
       float lim = M->effort[lane];
@@ -1196,7 +1204,8 @@ GO2_HD void compute_torques(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
 // ================================================================================================ the full step
 template <class T>
 GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
-  const Go2EnvConfig* C = X.cfg;
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2Model* M = X.mdl;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
@@ -1222,7 +1231,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       for (int k6 = 0; k6 < (GO2_NUM_HEIGHT + 31) / 32; ++k6) {      // unrolled: the 3 x 6 heightfield loads of a lane are all in flight together
         const int i = lane + 32 * k6;
         if (i >= GO2_NUM_HEIGHT) break;
-        float bx = C->height_points[i][0], by = C->height_points[i][1];
+        float bx = CT->height_points[i][0], by = CT->height_points[i][1];
         float tx = GO2_FMUL(2.0f, -GO2_FMUL(qz, by)), ty = GO2_FMUL(2.0f, GO2_FMUL(qz, bx));
         float px = GO2_FADD(GO2_FADD(bx, GO2_FMUL(qw, tx)), -GO2_FMUL(qz, ty)), py = GO2_FADD(GO2_FADD(by, GO2_FMUL(qw, ty)), GO2_FMUL(qz, tx));
         px = GO2_FADD(GO2_FADD(px, S.root[0]), C->border); py = GO2_FADD(GO2_FADD(py, S.root[1]), C->border);
@@ -1249,7 +1258,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   GO2_WIDE {
     {
       float sh = 0;
-      for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) sh += S.heights[i] * C->base_height_mask[i];
+      for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) sh += S.heights[i] * CT->base_height_mask[i];
       S.part[lane] = sh;
     }
     if (lane < GO2_NUM_DOF) {  // per-joint reward terms
@@ -1261,8 +1270,8 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.jterm[3][lane] = (la - a) * (la - a);
       float sm = a - 2 * la + lla;
       S.jterm[4][lane] = sm * sm;
-      S.jterm[5][lane] = -fminf(q - C->soft_dof_limit_lo[lane], 0.0f) + fmaxf(q - C->soft_dof_limit_hi[lane], 0.0f);
-      S.jterm[6][lane] = (lane % 3 == 0) ? fabsf(q - C->default_dof_pos[lane]) : 0.0f;
+      S.jterm[5][lane] = -fminf(q - CT->soft_dof_limit_lo[lane], 0.0f) + fmaxf(q - CT->soft_dof_limit_hi[lane], 0.0f);
+      S.jterm[6][lane] = (lane % 3 == 0) ? fabsf(q - CT->default_dof_pos[lane]) : 0.0f;
       S.llact[lane] = la;  // legged_robot.py:1378
     }
     if (lane >= 16 && lane < 24) {  // collision flags: thigh, calf of each leg (reported bodies 4+4l, 5+4l)
@@ -1356,7 +1365,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   // shared memory by the lanes that own their sources (no divergent 12-way branch per column), then rows leave coalesced.
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
-      S.obsrow[12 + lane] = (S.q[lane] - C->default_dof_pos[lane]) * C->obs_scale_dof_pos;
+      S.obsrow[12 + lane] = (S.q[lane] - CT->default_dof_pos[lane]) * C->obs_scale_dof_pos;
       S.obsrow[24 + lane] = S.qd[lane] * C->obs_scale_dof_vel;
       S.obsrow[36 + lane] = S.act[lane];
       S.obsrow[52 + lane] = S.tq[lane] / M->effort[lane];
@@ -1384,7 +1393,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
           if (C->add_noise) {
             const uint32_t ge = (uint32_t)(C->env_offset + e);
             U4 r = philox(ge, sp->common_step_counter, ST_NOISE, (uint32_t)(o / 4), C->seed_lo, C->seed_hi);
-            x = GO2_FADD(x, GO2_FMUL(GO2_FADD(GO2_FMUL(2.0f, u01(pick(r, o % 4))), -1.0f), C->noise_scale_vec[o]));
+            x = GO2_FADD(x, GO2_FMUL(GO2_FADD(GO2_FMUL(2.0f, u01(pick(r, o % 4))), -1.0f), CT->noise_scale_vec[o]));
           }
           B->obs_buf[(size_t)e * GO2_NUM_OBS + o] = fminf(fmaxf(x, -C->clip_obs), C->clip_obs);
         }

@@ -255,7 +255,7 @@ class LeggedRobot:
         """No viewer (legged_robot.py:283-288); kept so that scripts written for the reference run unchanged."""
 
     def set_step_mode(self, mode):
-        """Thread map of the step kernel: "P2" (default), "P3", "Q4", "8p", "4" — identical results, different speed (tuning / tests)."""
+        """Thread map of the step kernel: "H14" (default), "P2", "P3", "Q4", "8p", "4" — identical results, different speed (tuning / tests)."""
         _abi.check(self._lib.go2_env_set_step_mode(self._h, str(mode).encode()), self._lib)
 
     def substeps(self, tau, n):

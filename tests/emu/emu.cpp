@@ -26,7 +26,7 @@ extern "C" {
 void go2_emu_set_packed(int packed) { g_packed = packed; }
 int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const float* actions, const Go2StepParams* sp) {
   for (int k = 0; k < GO2_EP_ACCUM_FLOATS; ++k) B->ep_accum[k] = 0;
-  StepCtx X{C, M, B, sp, actions};
+  StepCtx X{C, M, B, sp, actions, C};
   for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { step_env<EmuT>(lanes, NT, SM, X); });
   // finalize extras["episode"] (mirrors the tiny finalize kernel)
   float n_reset = B->ep_accum[GO2_NUM_REW + 10];
@@ -48,12 +48,12 @@ int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* 
   return 0;
 }
 int go2_emu_reset_all(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const Go2StepParams* sp) {
-  StepCtx X{C, M, B, sp, nullptr};
+  StepCtx X{C, M, B, sp, nullptr, C};
   for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { reset_env_initial<EmuT>(lanes, NT, SM, X); });
   return 0;
 }
 int go2_emu_substeps(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const float* tau, int n) {
-  StepCtx X{C, M, B, nullptr, nullptr};
+  StepCtx X{C, M, B, nullptr, nullptr, C};
   for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { substeps_env<EmuT>(lanes, NT, SM, X, tau, n); });
   return 0;
 }

@@ -16,9 +16,11 @@ from go2_rl_gym_b200.envs.go2.go2_env import Go2Robot
 ap = argparse.ArgumentParser()
 ap.add_argument("--num_envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--mode", default="H14")
 args = ap.parse_args()
 cfg = GO2Cfg(); cfg.env.num_envs = args.num_envs; cfg.terrain.mesh_type = "heightfield"
 env = Go2Robot(cfg, None, None, "cuda:0", True)
+env.set_step_mode(args.mode)
 env.reset()
 lib = _abi.load_library()
 lib.go2_debug_phase_clocks.argtypes = [ctypes.c_void_p, ctypes.c_int]
