@@ -60,6 +60,9 @@
 #define GO2_NV_OK(vh) ((vh) < L.nv)
 #endif
 #define GO2_WIDE GO2_EACH if (T::ROLE != 2 && L.own) GO2_UNROLL for (int vh = 0; vh < T::NV; ++vh) if (GO2_NV_OK(vh)) GO2_BIND(L.w, GO2_VLANE(vh))
+// items i = lane, lane + 32, ... < n of a WIDE block as a FIXED-trip unrolled loop with a predicate: the loads of all trips are in flight together
+// (a `for (i = lane; i < n; i += 32)` loop has a lane-dependent trip count, is not unrolled, and serialises one memory round trip per trip)
+#define GO2_STRIDED(i, n) GO2_UNROLL for (int k_ = 0; k_ < ((n) + 31) / 32; ++k_) if (const int i = lane + 32 * k_; i < (n))
 #define GO2_LEGS GO2_EACH if (T::ROLE != 1 && L.leg >= 0) GO2_BIND(L.wl, L.leg)
 
 namespace go2 {
@@ -302,12 +305,14 @@ template <int NV_, int ROLE_, int PAD_> struct StepT { static constexpr int NV =
 struct Lane {
   // joint lanes (0..11)
   float kp, kd, mzo, mstr;
+  float ddp, eff, qlo, qhi, vlim;   // default_dof_pos, effort / position / velocity limits of the joint (read once per step)
   // leg lanes (0..3): per link i of the leg
   float c[3], s[3], Dinv[3], u[3], uI[3];
   float U[3][6], cb[3][6];
+  float pA[3][6];               // bias forces of pass 1, consumed by pass 2
   float lam_lo[3], lam_hi[3];   // accumulated joint-limit impulses of the leg's joints
   // collider items (one per virtual lane)
-  struct Col { float n[3], Winv[6], vt, r[3], gsplit; int body, act; } col[2];
+  struct Col { float n[3], Winv[6], vt, r[3], gsplit, gap; int body, act; } col[2];
   // thread map (init_roles): own env slot / lane, leg item, base-column item, first env id of the group, slots of the group
   int own, w, lane, nv;
   int leg, wl;
@@ -331,11 +336,23 @@ __device__ __forceinline__ void go2_phase_sync(const Lane& L) {
   if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { const int k = go2_ph_count; if (k < 512) go2_ph_clock[k] = clock64(); go2_ph_count = k + 1; }
 #endif
 }
+// role-specialised kernels: the leg warps signal "kinematics done" without waiting (bar.arrive), the WIDE warps wait for it (bar.sync on the same
+// named barrier); every thread of the leg warps arrives, also the ones without an item
+#define GO2_KIN_ARRIVE() do { if (T::ROLE == 2) { __threadfence_block(); asm volatile("bar.arrive 4, %0;" ::"r"(L.nsync) : "memory"); } } while (0)
+#define GO2_KIN_WAIT() do { asm volatile("bar.sync 4, %0;" ::"r"(L.nsync) : "memory"); } while (0)
+#if defined(GO2_PHASE_TIMING)
+#define GO2_TICK() do { if (threadIdx.x == 0 && blockIdx.x == GO2_PHASE_TIMING) { const int k = go2_ph_count; if (k < 512) go2_ph_clock[k] = clock64(); go2_ph_count = k + 1; } } while (0)
+#else
+#define GO2_TICK() do { } while (0)
+#endif
 #define GO2_COARSE_SYNC() do { if (L.ncoarse) asm volatile("bar.sync 2, %0;" ::"r"(L.ncoarse) : "memory"); } while (0)
 #define GO2_MID_SYNC() do { if (L.nmid) asm volatile("bar.sync 3, %0;" ::"r"(L.nmid) : "memory"); } while (0)
 #else
 #define GO2_COARSE_SYNC() do { } while (0)
 #define GO2_MID_SYNC() do { } while (0)
+#define GO2_KIN_ARRIVE() do { } while (0)
+#define GO2_KIN_WAIT() do { } while (0)
+#define GO2_TICK() do { } while (0)
 #endif
 
 // Thread map of thread `tid` of a group of `nwarps` warps whose first env is e0 and which holds n_local (>= 1) envs.
@@ -413,20 +430,31 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 #endif
 
-// bilinear heightfield query (plane: h = 0)
+// bilinear heightfield query (plane: every sample reads as 0, h = 0).  Branch-free: the loads are predicated, so the queries of a thread's two
+// virtual lanes overlap
+#if defined(__CUDACC__)
+__device__ __forceinline__ float ldg_h_if(bool p, const int16_t* a) {
+  int v = 0;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.nc.s16 %0, [%1];\n}" : "+r"(v) : "l"(a), "r"((int)p));
+  return (float)v;
+}
+#else
+static inline float ldg_h_if(bool p, const int16_t* a) { return p ? (float)*a : 0.0f; }
+#endif
 GO2_HD void terrain_query(const Go2EnvConfig* C, const int16_t* hs, float x, float y, float& h, float& dhx, float& dhy) {
-  if (C->mesh_type == 0) { h = 0; dhx = 0; dhy = 0; return; }
+  const bool hf = C->mesh_type != 0;
   float gx = (x + C->border) / C->hscale, gy = (y + C->border) / C->hscale;
   int ix = (int)floorf(gx), iy = (int)floorf(gy);
   ix = min(max(ix, 0), C->hf_rows - 2);
   iy = min(max(iy, 0), C->hf_cols - 2);
   float fx = fminf(fmaxf(gx - (float)ix, 0.0f), 1.0f), fy = fminf(fmaxf(gy - (float)iy, 0.0f), 1.0f);
   const int16_t* p = hs + (size_t)ix * C->hf_cols + iy;
-  float h00 = (float)GO2_LDG(p), h01 = (float)GO2_LDG(p + 1), h10 = (float)GO2_LDG(p + C->hf_cols), h11 = (float)GO2_LDG(p + C->hf_cols + 1);
+  float h00 = ldg_h_if(hf, p), h01 = ldg_h_if(hf, p + 1), h10 = ldg_h_if(hf, p + C->hf_cols), h11 = ldg_h_if(hf, p + C->hf_cols + 1);
   float vs = C->vscale, k = vs / C->hscale;
   h = vs * ((1 - fx) * (1 - fy) * h00 + fx * (1 - fy) * h10 + (1 - fx) * fy * h01 + fx * fy * h11);
   dhx = k * ((1 - fy) * (h10 - h00) + fy * (h11 - h01));
   dhy = k * ((1 - fx) * (h01 - h00) + fx * (h11 - h10));
+  if (!hf) { h = 0; dhx = 0; dhy = 0; }
 }
 
 
@@ -611,6 +639,37 @@ GO2_HD void leg_pass3(int l, Lane& L, SMT& S, const Go2Model* M, float dt, float
 #define GO2_ANY_RESET(SM) group_any_reset(lanes[0], SM)   /* the emulated group walks reset_phases when any of its envs resets */
 #endif
 
+// ---- S6a: collider lanes: narrow phase against the terrain (needs the world transforms of ABA pass 1 only).  Branch-free, so that the two
+// virtual lanes of a half-warp thread overlap their heightfield loads.  In the role-specialised kernels the WIDE warps run it WHILE the leg warps
+// are in ABA passes 2-3 (GO2_KIN_ARRIVE / GO2_KIN_WAIT below).
+template <class T>
+GO2_HD void narrow_phase(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
+  const Go2EnvConfig* C = X.cs;
+  const Go2Model* M = X.mdl;
+  GO2_WIDE {
+    {
+      Lane::Col& K = L.col[vh];
+      const int ci = lane;
+      const int b = M->col_dyn[ci];
+      K.body = b;
+      V3 r = ld3(M->col_pos[ci]);
+      K.r[0] = r.x; K.r[1] = r.y; K.r[2] = r.z;
+      M3 Rw = ldm(S.Rw[b]);
+      V3 cw = ld3(S.pw[b]) + mul(Rw, r);
+      float h, dhx, dhy;
+      terrain_query(C, X.buf->height_samples, cw.x, cw.y, h, dhx, dhy);
+      float inv = 1.0f / sqrtf(dhx * dhx + dhy * dhy + 1.0f);
+      V3 n = mk(-dhx * inv, -dhy * inv, inv);
+      float gap = (cw.z - h) * n.z - M->col_radius[ci];
+      int act = gap < C->contact_offset;
+      K.act = act; S.active[ci] = act; K.gap = gap;
+      K.n[0] = n.x; K.n[1] = n.y; K.n[2] = n.z;
+      for (int k = 0; k < 6; ++k) S.fcol[ci][k] = 0;
+      S.pcol[ci][0] = S.pcol[ci][1] = S.pcol[ci][2] = 0;
+    }
+  } GO2_SYNC_WARP();
+}
+
 template <class T>
 GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, bool last) {
   const Go2EnvConfig* C = X.cs;
@@ -628,7 +687,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
       sn = sinf(q); cn = cosf(q);
 #endif
       S.cs[lane][0] = cn; S.cs[lane][1] = sn;
-      float glo = q - M->q_lower[lane], ghi = M->q_upper[lane] - q;
+      float glo = q - L.qlo, ghi = L.qhi - q;
       S.tgt[lane][0] = (glo >= 0) ? -glo / dt : -glo * C->limit_erp / dt;
       S.tgt[lane][1] = (ghi >= 0) ? ghi / dt : ghi * C->limit_erp / dt;
       S.dqd[lane] = 0; S.tauimp[lane] = 0;
@@ -642,7 +701,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
     }
     if (lane >= 13 && lane < 13 + GO2_NUM_DYN) { for (int k = 0; k < 6; ++k) S.dv[lane - 13][k] = 0; }
   } GO2_SYNC();
-  // ---- S2: leg lanes: ABA pass 1 and 2
+  // ---- S2: leg lanes: ABA pass 1 (kinematics, bias forces) ...
   GO2_LEGS {
     if (lane < 4) {
       V6 vpar; ld6(S.vs[0], vpar);
@@ -651,6 +710,15 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
       leg_pass1<0>(lane, L, S, M, vpar, Rwp, pwp, vl, pA);
       leg_pass1<1>(lane, L, S, M, vpar, Rwp, pwp, vl, pA);
       leg_pass1<2>(lane, L, S, M, vpar, Rwp, pwp, vl, pA);
+      for (int i = 0; i < 3; ++i) st6(L.pA[i], pA[i]);
+    }
+  }
+  GO2_KIN_ARRIVE();   // the world transforms are in shared memory: the WIDE warps of a role-specialised kernel start the narrow phase (every thread of the leg warps arrives)
+  // ---- ... and pass 2 (articulated inertias, leaves to root)
+  GO2_LEGS {
+    if (lane < 4) {
+      V6 pA[3];
+      for (int i = 0; i < 3; ++i) ld6(L.pA[i], pA[i]);
       Sym6 IA = rigid_inertia(S.inertia + (3 * lane + 3) * GO2_INERTIA_STRIDE), Iout;
       V6 pout;
       leg_pass2<2>(lane, L, S, M, IA, pA[2], Iout, pout);
@@ -670,6 +738,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
   // cross-lane traffic), then runs pass 3 / unconstrained velocities / the mobility recursion for its own leg.  The only dependency on
   // the other legs is their legIA / legpA: a warp-level sync (the 4 leg lanes of an env always share a warp).
   GO2_SYNC_WARP();
+  if (T::ROLE == 1) { GO2_KIN_WAIT(); narrow_phase<T>(GO2_LANE_PASS, SM, X); }
   GO2_LEGS {
     if (lane < 4) {
       Sym6 I0 = rigid_inertia(S.inertia);
@@ -708,28 +777,16 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
       for (int i = 0; i < 3; ++i) { L.lam_lo[i] = 0; L.lam_hi[i] = 0; }
     }
   } GO2_SYNC();
-  // ---- S6: collider lanes: narrow phase + per-contact 3x3 mobility
+  // ---- S6a (narrow phase) for the thread maps whose threads carry both roles; the role-specialised kernels ran it above, under the leg warps
+  if (T::ROLE != 1) narrow_phase<T>(GO2_LANE_PASS, SM, X);
+  // ---- S6b: collider lanes: per-contact 3x3 mobility and velocity target of the active colliders
   GO2_WIDE {
     {
       Lane::Col& K = L.col[vh];
-      const int ci = lane;
-      const int b = M->col_dyn[ci];
-      K.body = b;
-      V3 r = ld3(M->col_pos[ci]);
-      K.r[0] = r.x; K.r[1] = r.y; K.r[2] = r.z;
-      M3 Rw = ldm(S.Rw[b]);
-      V3 cw = ld3(S.pw[b]) + mul(Rw, r);
-      float h, dhx, dhy;
-      terrain_query(C, X.buf->height_samples, cw.x, cw.y, h, dhx, dhy);
-      float inv = 1.0f / sqrtf(dhx * dhx + dhy * dhy + 1.0f);
-      V3 n = mk(-dhx * inv, -dhy * inv, inv);
-      float gap = (cw.z - h) * n.z - M->col_radius[ci];
-      int act = gap < C->contact_offset;
-      K.act = act; S.active[ci] = act;
-      K.n[0] = n.x; K.n[1] = n.y; K.n[2] = n.z;
-      for (int k = 0; k < 6; ++k) S.fcol[ci][k] = 0;
-      S.pcol[ci][0] = S.pcol[ci][1] = S.pcol[ci][2] = 0;
-      if (act) {
+      const int ci = lane, b = K.body;
+      if (K.act) {
+        V3 r = mk(K.r[0], K.r[1], K.r[2]), n = mk(K.n[0], K.n[1], K.n[2]);
+        M3 Rw = ldm(S.Rw[b]);
         M3 P, Q, R;
         if (b == 0) {
           for (int i = 0; i < 3; ++i)
@@ -747,10 +804,12 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
         // normal velocity target; restitution looks at the approach speed at the START of the step
         V6 vsb; ld6(S.vs[b], vsb);
         float vn0 = dot(mul(Rw, vsb.l + cross(vsb.a, r)), n);
+        const float gap = K.gap;
         float vt = (gap >= 0) ? -gap / dt : fminf(fmaxf(-gap - C->penetration_slop, 0.0f) * C->erp / dt, C->max_depen_vel);
         if (vn0 < -C->bounce_threshold) vt = fmaxf(vt, -S.rest_env * vn0);
         K.vt = vt;
       }
+      (void)ci;
     }
   } GO2_SYNC_WARP();
   // ---- S7: mass-splitting factor of the collider's group (base = colliders 0..7, leg l = 8+6l .. 13+6l)
@@ -837,7 +896,7 @@ GO2_HD void physics_substep(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& 
   GO2_MID_SYNC();
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
-      float x = S.qdm[lane] + S.dqd[lane], vl = M->vel_limit[lane];
+      float x = S.qdm[lane] + S.dqd[lane], vl = L.vlim;
       x = fminf(fmaxf(x, -vl), vl);
       S.qd[lane] = x;
       S.q[lane] += dt * x;
@@ -1107,48 +1166,99 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, 
 }
 
 // ================================================================================================ load / store
+// predicated global loads: every lane issues the same load instructions (no branch between them), so all of a thread's loads are in flight
+// together and load_env costs ONE memory round trip instead of one per `if (lane == ...)` block
+#if defined(__CUDACC__)
+__device__ __forceinline__ float ldg_if(bool p, const float* a) {
+  float v = 0.0f;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.f32 %0, [%1];\n}" : "+f"(v) : "l"(a), "r"((int)p));
+  return v;
+}
+__device__ __forceinline__ int ldg_if(bool p, const int32_t* a) {
+  int v = 0;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.b32 %0, [%1];\n}" : "+r"(v) : "l"(a), "r"((int)p));
+  return v;
+}
+__device__ __forceinline__ int ldg_if(bool p, const uint8_t* a) {
+  int v = 0;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.global.u8 %0, [%1];\n}" : "+r"(v) : "l"(a), "r"((int)p));
+  return v;
+}
+#else
+static inline float ldg_if(bool p, const float* a) { return p ? *a : 0.0f; }
+static inline int ldg_if(bool p, const int32_t* a) { return p ? *a : 0; }
+static inline int ldg_if(bool p, const uint8_t* a) { return p ? (int)*a : 0; }
+#endif
+
 template <class T>
 GO2_HD void load_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cs;
   const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2EnvBuffers* B = X.buf;
   GO2_WIDE {
-    for (int i = lane; i < GO2_NUM_DYN * GO2_INERTIA_STRIDE; i += 32) S.inertia[i] = GO2_LDG(B->body_inertia + (size_t)e * GO2_NUM_DYN * GO2_INERTIA_STRIDE + i);
-    if (lane < 13) S.root[lane] = B->root_states[(size_t)e * 13 + lane];
-    if (lane < GO2_NUM_DOF) {
-      const size_t o = (size_t)e * GO2_NUM_DOF + lane;
-      S.q[lane] = B->dof_pos[o]; S.qd[lane] = B->dof_vel[o];
-      S.lact[lane] = B->last_actions[o]; S.llact[lane] = B->last_last_actions[o]; S.lqd[lane] = B->last_dof_vel[o];
-      S.tq[lane] = B->torques[o];
-      float a = X.actions_in ? X.actions_in[o] : B->actions[o];
-      S.act[lane] = fminf(fmaxf(a, -C->clip_actions), C->clip_actions);
-      L.kp = CT->kp[lane] * B->p_gains_multiplier[o]; L.kd = CT->kd[lane] * B->d_gains_multiplier[o];
-      L.mzo = B->motor_zero_offsets[o]; L.mstr = B->motor_strengths[o];
+    // ---- every global load of the lane, issued back to back (the buffers are read-only for the duration of the loads: the kernel writes
+    // them in store_state / the post-physics phases only)
+    constexpr int NI = GO2_NUM_DYN * GO2_INERTIA_STRIDE, NCF = GO2_NUM_REPORT * 3;
+    const bool pj = lane < GO2_NUM_DOF;
+    const size_t o = (size_t)e * GO2_NUM_DOF + (pj ? lane : 0);
+    float vin[(NI + 31) / 32], vcf[(NCF + 31) / 32];
+    GO2_UNROLL for (int k = 0; k < (NI + 31) / 32; ++k) vin[k] = ldg_if(lane + 32 * k < NI, B->body_inertia + (size_t)e * NI + min(lane + 32 * k, NI - 1));
+    GO2_UNROLL for (int k = 0; k < (NCF + 31) / 32; ++k) vcf[k] = ldg_if(lane + 32 * k < NCF, B->contact_forces + (size_t)e * NCF + min(lane + 32 * k, NCF - 1));
+    const float v_root = ldg_if(lane < 13, B->root_states + (size_t)e * 13 + min(lane, 12));
+    const float v_q = ldg_if(pj, B->dof_pos + o), v_qd = ldg_if(pj, B->dof_vel + o), v_la = ldg_if(pj, B->last_actions + o);
+    const float v_lla = ldg_if(pj, B->last_last_actions + o), v_lqd = ldg_if(pj, B->last_dof_vel + o), v_tq = ldg_if(pj, B->torques + o);
+    const float v_a = ldg_if(pj, (X.actions_in ? X.actions_in : B->actions) + o);
+    const float v_pg = ldg_if(pj, B->p_gains_multiplier + o), v_dg = ldg_if(pj, B->d_gains_multiplier + o);
+    const float v_mzo = ldg_if(pj, B->motor_zero_offsets + o), v_ms = ldg_if(pj, B->motor_strengths + o);
+    const float v_kp = ldg_if(pj, CT->kp + (pj ? lane : 0)), v_kd = ldg_if(pj, CT->kd + (pj ? lane : 0));
+    const float v_ddp = ldg_if(pj, CT->default_dof_pos + (pj ? lane : 0)), v_eff = ldg_if(pj, X.mdl->effort + (pj ? lane : 0));
+    const float v_qlo = ldg_if(pj, X.mdl->q_lower + (pj ? lane : 0)), v_qhi = ldg_if(pj, X.mdl->q_upper + (pj ? lane : 0));
+    const float v_vl = ldg_if(pj, X.mdl->vel_limit + (pj ? lane : 0));
+    const bool p_cmd = lane >= 12 && lane < 16, p_rng = lane >= 16 && lane < 22, p_org = lane >= 22 && lane < 25;
+    const float v_cmd = ldg_if(p_cmd, B->commands + (size_t)e * GO2_NUM_CMD + (p_cmd ? lane - 12 : 0));
+    const float v_rng = ldg_if(p_rng, B->env_command_ranges + (size_t)e * 6 + (p_rng ? lane - 16 : 0));
+    const float v_org = ldg_if(p_org, B->env_origins + (size_t)e * 3 + (p_org ? lane - 22 : 0));
+    const int v_eplen = ldg_if(lane == 25, B->episode_length_buf + e);
+    const float v_rs = ldg_if(lane == 25, B->commands_resampling_step + e);
+    const float v_ax = ldg_if(lane == 26, B->commands_xy_accumulation + (size_t)e * 2), v_ay = ldg_if(lane == 26, B->commands_xy_accumulation + (size_t)e * 2 + 1);
+    const float v_mm = ldg_if(lane == 27, B->max_move_distance + e);
+    const int v_ll = ldg_if(lane == 27, B->last_is_limit_vel + e);
+    const int v_lvl = ldg_if(lane == 28, B->terrain_levels + e), v_tt = ldg_if(lane == 28, B->terrain_types + e), v_tid = ldg_if(lane == 28, B->terrain_ids + e);
+    const float v_fr = ldg_if(lane == 30, B->friction_coeffs + e), v_re = ldg_if(lane == 30, B->restitutions + e);
+    // ---- shared-memory writes
+    GO2_UNROLL for (int k = 0; k < (NI + 31) / 32; ++k) if (lane + 32 * k < NI) S.inertia[lane + 32 * k] = vin[k];
+    GO2_UNROLL for (int k = 0; k < (NCF + 31) / 32; ++k) if (lane + 32 * k < NCF) S.cf[(lane + 32 * k) / 3][(lane + 32 * k) % 3] = vcf[k];
+    if (lane < 13) S.root[lane] = v_root;
+    if (pj) {
+      S.q[lane] = v_q; S.qd[lane] = v_qd;
+      S.lact[lane] = v_la; S.llact[lane] = v_lla; S.lqd[lane] = v_lqd;
+      S.tq[lane] = v_tq;
+      S.act[lane] = fminf(fmaxf(v_a, -C->clip_actions), C->clip_actions);
+      L.kp = v_kp * v_pg; L.kd = v_kd * v_dg;
+      L.mzo = v_mzo; L.mstr = v_ms;
+      L.ddp = v_ddp; L.eff = v_eff; L.qlo = v_qlo; L.qhi = v_qhi; L.vlim = v_vl;
     }
-    if (lane >= 12 && lane < 16) S.cmd[lane - 12] = B->commands[(size_t)e * GO2_NUM_CMD + lane - 12];
-    if (lane >= 16 && lane < 22) S.cmd_rng[lane - 16] = B->env_command_ranges[(size_t)e * 6 + lane - 16];
-    if (lane >= 22 && lane < 25) S.env_origin[lane - 22] = B->env_origins[(size_t)e * 3 + lane - 22];
-    if (lane == 25) { S.ep_len = B->episode_length_buf[e]; S.resamp_step = B->commands_resampling_step[e]; }
-    if (lane == 26) { S.acc_xy[0] = B->commands_xy_accumulation[(size_t)e * 2]; S.acc_xy[1] = B->commands_xy_accumulation[(size_t)e * 2 + 1]; }
-    if (lane == 27) { S.max_move = B->max_move_distance[e]; S.last_lim = B->last_is_limit_vel[e]; }
+    if (p_cmd) S.cmd[lane - 12] = v_cmd;
+    if (p_rng) S.cmd_rng[lane - 16] = v_rng;
+    if (p_org) S.env_origin[lane - 22] = v_org;
+    if (lane == 25) { S.ep_len = v_eplen; S.resamp_step = v_rs; }
+    if (lane == 26) { S.acc_xy[0] = v_ax; S.acc_xy[1] = v_ay; }
+    if (lane == 27) { S.max_move = v_mm; S.last_lim = v_ll; }
+    if (lane == 28) { S.level = v_lvl; S.ttype = v_tt; S.tid = v_tid; }
     if (lane == 30) {
       S.stop_heading = 0; S.hrng[0] = 0.0f; S.hrng[1] = 0.0f;
       if (C->heading_command) {
         const float* hr = GO2_EXT_PTR(const float*, C, ext_heading_ranges);
         S.stop_heading = GO2_EXT_PTR(const uint8_t*, C, ext_stop_heading)[e]; S.hrng[0] = hr[(size_t)e * 2]; S.hrng[1] = hr[(size_t)e * 2 + 1];
       }
-    }
-    if (lane == 28) { S.level = B->terrain_levels[e]; S.ttype = B->terrain_types[e]; S.tid = B->terrain_ids[e]; }
-    if (lane == 30) {
-      S.mu_env = 0.5f * (C->terrain_friction + GO2_LDG(B->friction_coeffs + e));
-      S.rest_env = 0.5f * (C->terrain_restitution + GO2_LDG(B->restitutions + e));
+      S.mu_env = 0.5f * (C->terrain_friction + v_fr);
+      S.rest_env = 0.5f * (C->terrain_restitution + v_re);
     }
     if (lane == 29) {
       S.delay_start = 0;
       if (C->randomize_action_delay && X.sp)
         S.delay_start = (int)(philox((uint32_t)(C->env_offset + e), X.sp->common_step_counter, ST_DELAY, 0, C->seed_lo, C->seed_hi).x % (uint32_t)(C->decimation + 1));
     }
-    for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) S.cf[i / 3][i % 3] = B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i];
   } GO2_SYNC_WARP();
 }
 
@@ -1171,7 +1281,7 @@ GO2_HD void store_state(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
     if (lane == 30 && X.cs->heading_command) GO2_EXT_PTR(uint8_t*, X.cs, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
     if (lane == 28) B->terrain_levels[e] = S.level;
     if (lane == 29) { B->reset_buf[e] = (uint8_t)S.reset; B->time_out_buf[e] = (uint8_t)S.tout; }
-    for (int i = lane; i < GO2_NUM_REPORT * 3; i += 32) B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = S.cf[i / 3][i % 3];
+    GO2_STRIDED(i, GO2_NUM_REPORT * 3) B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = S.cf[i / 3][i % 3];
     if (lane < 24) {
       const int l = lane / 6, k = lane % 6;
       if (k < 3) B->feet_pos[(size_t)e * 12 + l * 3 + k] = S.feet[l][k];
@@ -1185,14 +1295,14 @@ template <class T>
 GO2_HD void compute_torques(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, int sub) {
   const Go2EnvConfig* C = X.cs;
   const Go2EnvConfig* CT = X.cfg; (void)CT;
-  const Go2Model* M = X.mdl;
+  const Go2Model* M = X.mdl; (void)M;
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
       float a_in = (C->randomize_action_delay && sub < S.delay_start) ? S.lact[lane] : S.act[lane];
-      float t = L.kp * (a_in * C->action_scale + CT->default_dof_pos[lane] - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
+      float t = L.kp * (a_in * C->action_scale + L.ddp - S.q[lane] + L.mzo) - L.kd * S.qd[lane];
       if (C->control_type == 1) t = L.kp * (a_in * C->action_scale - S.qd[lane]) - L.kd * (S.qd[lane] - S.lqd[lane]) / C->sim_dt;   // 'V', legged_robot.py:612-613
       else if (C->control_type == 2) t = a_in * C->action_scale;                                                                  // 'T', :614-615
-      float lim = M->effort[lane];
+      float lim = L.eff;
       t = fminf(fmaxf(t, -lim), lim);
       if (C->randomize_motor_strength) t *= L.mstr;
       S.tq[lane] = t;                               // what the reference reports (legged_robot.py:79-81)
@@ -1206,7 +1316,7 @@ template <class T>
 GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cs;
   const Go2EnvConfig* CT = X.cfg; (void)CT;
-  const Go2Model* M = X.mdl;
+  const Go2Model* M = X.mdl; (void)M;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
   load_env<T>(GO2_LANE_PASS, SM, X);
@@ -1216,21 +1326,21 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
     physics_substep<T>(GO2_LANE_PASS, SM, X, sub == C->decimation - 1);
   }
   GO2_COARSE_SYNC();
-  state_guard<T>(GO2_LANE_PASS, SM, X);
-  feet_kinematics<T>(GO2_LANE_PASS, SM, X);
+  GO2_TICK();
+  state_guard<T>(GO2_LANE_PASS, SM, X); GO2_TICK();
+  feet_kinematics<T>(GO2_LANE_PASS, SM, X); GO2_TICK();
   // ---- post_physics_step (legged_robot.py:102-142)
   GO2_WIDE {
     // height scan (legged_robot.py:1188-1224, math.py:8-12): yaw-only rotation of the body-frame grid
     if (C->mesh_type == 0) {
-      for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) S.heights[i] = 0;
+      GO2_STRIDED(i, GO2_NUM_HEIGHT) S.heights[i] = 0;
     } else {
       float qz = S.root[5], qw = S.root[6];
       float nrm = fmaxf(sqrtf(qz * qz + qw * qw), 1e-9f);
       qz /= nrm; qw /= nrm;
 #pragma unroll
-      for (int k6 = 0; k6 < (GO2_NUM_HEIGHT + 31) / 32; ++k6) {      // unrolled: the 3 x 6 heightfield loads of a lane are all in flight together
-        const int i = lane + 32 * k6;
-        if (i >= GO2_NUM_HEIGHT) break;
+      for (int k6 = 0; k6 < (GO2_NUM_HEIGHT + 31) / 32; ++k6) {      // unrolled and branch-free: the 3 x 6 heightfield loads of a lane are all in flight together
+        const int i0 = lane + 32 * k6, i = min(i0, GO2_NUM_HEIGHT - 1);  // lanes past the end recompute the last sample and do not store
         float bx = CT->height_points[i][0], by = CT->height_points[i][1];
         float tx = GO2_FMUL(2.0f, -GO2_FMUL(qz, by)), ty = GO2_FMUL(2.0f, GO2_FMUL(qz, bx));
         float px = GO2_FADD(GO2_FADD(bx, GO2_FMUL(qw, tx)), -GO2_FMUL(qz, ty)), py = GO2_FADD(GO2_FADD(by, GO2_FMUL(qw, ty)), GO2_FMUL(qz, tx));
@@ -1240,7 +1350,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
         const int16_t* p = B->height_samples + (size_t)ix * C->hf_cols + iy;
         int16_t h1 = GO2_LDG(p), h2 = GO2_LDG(p + C->hf_cols), h3 = GO2_LDG(p + 1);
         int16_t hm = h1 < h2 ? h1 : h2; hm = hm < h3 ? hm : h3;
-        S.heights[i] = (float)hm * C->vscale;
+        if (i0 < GO2_NUM_HEIGHT) S.heights[i] = (float)hm * C->vscale;
       }
     }
     if (lane == 0) {
@@ -1254,11 +1364,11 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       if (S.resamp_step <= 0.0f && S.ep_len < C->max_episode_length - 1) resample_commands(S, X, e, ST_CMD_CB);
       if (C->heading_command && !S.stop_heading) heading_to_yaw(S);
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
     {
       float sh = 0;
-      for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) sh += S.heights[i] * CT->base_height_mask[i];
+      GO2_STRIDED(i, GO2_NUM_HEIGHT) sh += S.heights[i] * CT->base_height_mask[i];
       S.part[lane] = sh;
     }
     if (lane < GO2_NUM_DOF) {  // per-joint reward terms
@@ -1271,7 +1381,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       float sm = a - 2 * la + lla;
       S.jterm[4][lane] = sm * sm;
       S.jterm[5][lane] = -fminf(q - CT->soft_dof_limit_lo[lane], 0.0f) + fmaxf(q - CT->soft_dof_limit_hi[lane], 0.0f);
-      S.jterm[6][lane] = (lane % 3 == 0) ? fabsf(q - CT->default_dof_pos[lane]) : 0.0f;
+      S.jterm[6][lane] = (lane % 3 == 0) ? fabsf(q - L.ddp) : 0.0f;
       S.llact[lane] = la;  // legged_robot.py:1378
     }
     if (lane >= 16 && lane < 24) {  // collision flags: thigh, calf of each leg (reported bodies 4+4l, 5+4l)
@@ -1279,7 +1389,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       const float* f = S.cf[3 + 4 * l + k];
       S.coll[lane - 16] = (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
     if (lane == 0) {
       float sh = 0;
@@ -1291,7 +1401,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.reset = term || S.tout;
       S.reset |= S.bad;
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
     if (lane < 4) {  // feet_regulation per foot, legged_robot.py:1404-1414
       const float* fp = S.feet[lane];
@@ -1299,7 +1409,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       float fh = fmaxf(S.base_height - f2b, 0.0f);
       S.fterm[lane] = (fp[3] * fp[3] + fp[4] * fp[4]) * expf(-fh / (0.025f * C->base_height_target));
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
     if (lane == 0) {
       float tv[GO2_NUM_REW];
@@ -1339,12 +1449,13 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       if (C->only_positive_rewards) rew = fmaxf(rew, 0.0f);     // the episode sums keep the unclipped terms (legged_robot.py:263-267)
       S.rew = rew;
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
     if (lane < GO2_NUM_REW) B->episode_sums[(size_t)e * GO2_NUM_REW + lane] += S.termv[lane];
     if (lane == 31) B->rew_buf[e] = S.rew;
-  } GO2_SYNC_WARP();
-  if (GO2_ANY_RESET(SM)) reset_phases<T>(GO2_LANE_PASS, SM, X, false);   // warp-uniform (WIDE phases only); items are predicated by their env
+  } GO2_SYNC_WARP(); GO2_TICK();
+  if (GO2_ANY_RESET(SM)) reset_phases<T>(GO2_LANE_PASS, SM, X, false);
+  GO2_TICK();   // warp-uniform (WIDE phases only); items are predicated by their env
   GO2_WIDE {
     if (lane == 0) {
       if (C->push_robots && (S.ep_len % C->push_interval == 0)) {  // _push_robots, legged_robot.py:709-724
@@ -1360,15 +1471,15 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW, (float)S.level);
       GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW + 1 + S.tid, (float)S.level);
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   // ---- compute_observations (go2_env.py:23-53) + clip (legged_robot.py:96-99).  The 76 proprioceptive columns are first written to
   // shared memory by the lanes that own their sources (no divergent 12-way branch per column), then rows leave coalesced.
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) {
-      S.obsrow[12 + lane] = (S.q[lane] - CT->default_dof_pos[lane]) * C->obs_scale_dof_pos;
+      S.obsrow[12 + lane] = (S.q[lane] - L.ddp) * C->obs_scale_dof_pos;
       S.obsrow[24 + lane] = S.qd[lane] * C->obs_scale_dof_vel;
       S.obsrow[36 + lane] = S.act[lane];
-      S.obsrow[52 + lane] = S.tq[lane] / M->effort[lane];
+      S.obsrow[52 + lane] = S.tq[lane] / L.eff;
       S.obsrow[64 + lane] = (S.lqd[lane] - S.qd[lane]) / C->dt * 1e-4f;
     } else if (lane < 15) {
       const int k = lane - 12;
@@ -1380,7 +1491,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       const float* f = S.cf[6 + 4 * (lane - 18)];
       S.obsrow[48 + lane - 18] = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) * 1e-3f;
     }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
 #pragma unroll
     for (int k = 0; k < (GO2_NUM_PRIV + 31) / 32; ++k) {
@@ -1399,13 +1510,13 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
         }
       }
     }
-    for (int i = lane; i < GO2_NUM_HEIGHT; i += 32) B->measured_heights[(size_t)e * GO2_NUM_HEIGHT + i] = S.heights[i];
+    GO2_STRIDED(i, GO2_NUM_HEIGHT) B->measured_heights[(size_t)e * GO2_NUM_HEIGHT + i] = S.heights[i];
     if (lane < 3) { B->base_lin_vel[(size_t)e * 3 + lane] = S.blv[lane]; B->base_ang_vel[(size_t)e * 3 + lane] = S.bav[lane]; B->projected_gravity[(size_t)e * 3 + lane] = S.pg[lane]; }
-  } GO2_SYNC_WARP();
+  } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {
     if (lane < GO2_NUM_DOF) { S.lact[lane] = S.act[lane]; S.lqd[lane] = S.qd[lane]; }
-  } GO2_SYNC_WARP();
-  store_state<T>(GO2_LANE_PASS, SM, X);
+  } GO2_SYNC_WARP(); GO2_TICK();
+  store_state<T>(GO2_LANE_PASS, SM, X); GO2_TICK();
 }
 
 // reset_idx(all envs) at construction (base_task.py:82-86; the zero-action step that follows is issued by the caller)

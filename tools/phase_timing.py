@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--num_envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--mode", default="H14")
+ap.add_argument("--raw", action="store_true", help="print every interval between CTA barriers")
 args = ap.parse_args()
 cfg = GO2Cfg(); cfg.env.num_envs = args.num_envs; cfg.terrain.mesh_type = "heightfield"
 env = Go2Robot(cfg, None, None, "cuda:0", True)
@@ -42,12 +43,17 @@ for sb in range(4):
     names += [f"s{sb}.wide_pre", f"s{sb}.legs_aba", f"s{sb}.narrow_contact0", f"s{sb}.legs_sweep"]
     for it in range(3):
         names += [f"s{sb}.contact", f"s{sb}.legs_sweep"]
-names += [f"post{k}" for k in range(len(d) - len(names))]
+post = ["post.S12_last", "post.state_guard", "post.feet_kin", "post.heights_prelude", "post.partials_jterm", "post.termination", "post.fterm", "post.reward",
+        "post.episode_sums", "post.reset", "post.push_atomics", "post.obsrow", "post.obs_out", "post.lact", "post.store_state", "post.cta_exit"]
+names += [post[k] if k < len(post) else f"post{k}" for k in range(len(d) - len(names))]
 tot = sum(d)
+if args.raw:
+    for nm, v in zip(names, d):
+        print(f"  {nm:20s} {v:9.0f}")
 print(f"phases {len(d)}  total {tot:.0f} cycles per CTA-step")
 agg = {}
 for nm, v in zip(names, d):
-    key = nm.split(".")[-1] if nm.startswith("s") else nm
+    key = nm.split(".")[-1] if nm.startswith("s") else "post"
     agg[key] = agg.get(key, 0.0) + v
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
     print(f"{k:12s} {v:10.0f} cycles  {100 * v / tot:5.1f} %")
