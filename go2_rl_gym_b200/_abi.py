@@ -17,6 +17,13 @@ REWARD_NAMES = ["tracking_lin_vel", "tracking_ang_vel", "lin_vel_z", "ang_vel_xy
                 "correct_base_height", "action_rate", "action_smoothness", "collision", "dof_pos_limits",
                 "feet_regulation", "hip_to_default"]
 
+# the reward functions that are inactive in every registered go2 task (include/go2_b200.h: enum Go2XReward; legged_robot.py:1236-1441, go2_env.py:62-68)
+XREWARD_NAMES = ["orientation", "base_height", "dof_vel", "termination", "dof_vel_limits", "torque_limits", "feet_air_time", "stumble",
+                 "stand_still", "feet_contact_forces", "similar_to_default", "upright", "legs_distance", "x_command_hip_regular"]
+NUM_XREW = len(XREWARD_NAMES)
+EP_SLOTS = 64
+XREW_LOG_BYTES = NUM_XREW * 8 + EP_SLOTS * NUM_XREW * 4
+
 f32, i32, u32 = C.c_float, C.c_int32, C.c_uint32
 
 
@@ -59,12 +66,20 @@ class Go2EnvConfig(C.Structure):
         ("control_type", i32), ("only_positive_rewards", i32),
         ("heading_command", i32), ("stop_heading_at_limit", i32), ("ext_stop_heading_lo", u32), ("ext_stop_heading_hi", u32),
         ("ext_heading_ranges_lo", u32), ("ext_heading_ranges_hi", u32),
+        ("num_xrew", i32), ("xrew_scales", f32 * NUM_XREW),
+        ("soft_dof_vel_limit", f32), ("soft_torque_limit", f32), ("max_contact_force", f32), ("min_legs_distance", f32),
+        ("ext_xrew_sums_lo", u32), ("ext_xrew_sums_hi", u32), ("ext_xrew_state_lo", u32), ("ext_xrew_state_hi", u32),
+        ("ext_xrew_log_lo", u32), ("ext_xrew_log_hi", u32),
+        ("turn_over", i32), ("turn_over_proportions", f32 * 3), ("turn_over_back_height", f32 * 2), ("turn_over_side_height", f32 * 2),
+        ("turn_over_zero_time_back", f32), ("turn_over_zero_time_side", f32), ("turn_over_roll_threshold", f32),
+        ("to_scales", f32 * NUM_REW), ("to_xscales", f32 * NUM_XREW),
+        ("ext_turn_over_timer_lo", u32), ("ext_turn_over_timer_hi", u32),
     ]
 
 
 class Go2StepParams(C.Structure):
     _fields_ = [("common_step_counter", u32), ("reward_curriculum", f32 * NUM_REW), ("zero_command_proba", f32),
-                ("max_lin_vel", f32), ("ep_slot", i32)]
+                ("max_lin_vel", f32), ("ep_slot", i32), ("xrew_curriculum", f32 * NUM_XREW)]
 
 
 _PTR_FIELDS = [

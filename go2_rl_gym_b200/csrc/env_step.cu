@@ -168,6 +168,13 @@ __global__ void finalize_kernel(const Go2EnvConfig* __restrict__ cfg, float* __r
   } else if (ep_stats != nullptr && k < GO2_EP_STATS) {   // no reset in this step: the previous step's row is served again (header: GO2_EP_SLOTS)
     ep_stats[(size_t)slot * GO2_EP_STATS + k] = ep_stats[(size_t)((slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_EP_STATS + k];
   }
+  if (cfg->num_xrew > 0 && k < GO2_NUM_XREW) {   // the extra reward terms' episode means: same rules, their own accumulators / rows (Go2EnvConfig.ext_xrew_log)
+    long long* xacc = GO2_EXT_PTR(long long*, cfg, ext_xrew_log);
+    float* xst = reinterpret_cast<float*>(xacc + GO2_NUM_XREW);
+    if (n_reset > 0.0f) xst[(size_t)slot * GO2_NUM_XREW + k] = (float)((double)xacc[k] / (double)GO2_EP_FIXED_ONE) / n_reset / cfg->max_episode_length_s;
+    else xst[(size_t)slot * GO2_NUM_XREW + k] = xst[(size_t)((slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_NUM_XREW + k];
+    xacc[k] = 0;
+  }
   __syncthreads();
   if (k < GO2_EP_STATS + 2) ep_accum[k] = 0.0f;
   if (k < GO2_NUM_REW) reinterpret_cast<long long*>(ep_accum + GO2_EP_ACC_FIXED_OFF)[k] = 0;
@@ -242,6 +249,8 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
   if (cfg->num_envs <= 0) return go2::set_error(1, "go2_env_create: num_envs must be positive");
   if (cfg->heading_command && (!GO2_EXT_PTR(const void*, cfg, ext_stop_heading) || !GO2_EXT_PTR(const void*, cfg, ext_heading_ranges)))
     return go2::set_error(1, "go2_env_create: heading_command needs ext_stop_heading and ext_heading_ranges");
+  if (cfg->num_xrew > 0 && (!GO2_EXT_PTR(const void*, cfg, ext_xrew_sums) || !GO2_EXT_PTR(const void*, cfg, ext_xrew_state) || !GO2_EXT_PTR(const void*, cfg, ext_xrew_log)))
+    return go2::set_error(1, "go2_env_create: extra reward terms need ext_xrew_sums, ext_xrew_state and ext_xrew_log");
   if (cfg->control_type < 0 || cfg->control_type > 2) return go2::set_error(2, "go2_env_create: control_type must be 0 (P), 1 (V) or 2 (T)");
   // the kernel bakes the Go2 topology: hip = x axis, thigh/calf = y axis, collider lanes grouped per body
   for (int j = 0; j < GO2_NUM_DOF; ++j)

@@ -1092,12 +1092,97 @@ GO2_HD void heading_to_yaw(SMT& S) {
   S.cmd[2] = fminf(fmaxf(GO2_FMUL(0.5f, a), S.cmd_rng[4]), S.cmd_rng[5]);
 }
 
+// The reward functions that are inactive in every registered go2 task (legged_robot.py:1236-1441, go2_env.py:62-68; enum Go2XReward), evaluated on
+// lane 0 when the config gives one of them a non-zero scale (Go2EnvConfig.num_xrew > 0).  A function the reference does not call (zero scale) does
+// not advance its state (feet_air_time / last_contacts, last_contacts2).  rew receives the scaled terms; the termination term is returned
+// separately: the reference adds it after the only_positive_rewards clip (legged_robot.py:268-272).
+template <class SMT>
+GO2_HD void extra_rewards(SMT& S, const StepCtx& X, int e, float& rew, float& term_rew) {
+  const Go2EnvConfig* C = X.cs;
+  const Go2EnvConfig* CT = X.cfg;
+  const Go2Model* M = X.mdl;
+  float* sums = GO2_EXT_PTR(float*, C, ext_xrew_sums) + (size_t)e * GO2_NUM_XREW;
+  float* st = GO2_EXT_PTR(float*, C, ext_xrew_state) + (size_t)e * 12;
+  const float* sc = C->xrew_scales;
+  float tv[GO2_NUM_XREW];
+  for (int k = 0; k < GO2_NUM_XREW; ++k) tv[k] = 0.0f;
+  const float cmd_xy = sqrtf(S.cmd[0] * S.cmd[0] + S.cmd[1] * S.cmd[1]);
+  bool contact[4];
+  for (int l = 0; l < 4; ++l) contact[l] = S.cf[6 + 4 * l][2] > 1.0f;                       // feet_indices = reported bodies 6 + 4 l
+  tv[GO2_XREW_ORIENTATION] = S.pg[0] * S.pg[0] + S.pg[1] * S.pg[1];                          // :1236-1238
+  if (sc[GO2_XREW_BASE_HEIGHT] != 0.0f) {                                                    // :1245-1259
+    float nfc = 0.0f, fcp[3] = {0.0f, 0.0f, 0.0f};
+    for (int l = 0; l < 4; ++l) {
+      const bool filt = contact[l] || st[8 + l] != 0.0f;
+      st[8 + l] = contact[l] ? 1.0f : 0.0f;
+      if (filt) { nfc += 1.0f; for (int k = 0; k < 3; ++k) fcp[k] += S.feet[l][k]; }
+    }
+    const float den = fmaxf(nfc, 1.0f);
+    float bh = 0.0f;
+    for (int k = 0; k < 3; ++k) bh += (fcp[k] / den - S.root[k]) * S.pg[k];
+    tv[GO2_XREW_BASE_HEIGHT] = (bh - C->base_height_target) * (bh - C->base_height_target) * (nfc > 0.0f ? 1.0f : 0.0f);
+  }
+  float s_qd = 0.0f, s_vl = 0.0f, s_tl = 0.0f, s_def = 0.0f;
+  for (int j = 0; j < GO2_NUM_DOF; ++j) {
+    s_qd += S.qd[j] * S.qd[j];                                                               // dof_vel :1265-1267
+    s_vl += fminf(fmaxf(fabsf(S.qd[j]) - M->vel_limit[j] * C->soft_dof_vel_limit, 0.0f), 1.0f);   // dof_vel_limits :1291-1294
+    s_tl += fmaxf(fabsf(S.tq[j]) - M->effort[j] * C->soft_torque_limit, 0.0f);              // torque_limits :1296-1298
+    s_def += fabsf(S.q[j] - CT->default_dof_pos[j]);                                         // similar_to_default :1416-1418
+  }
+  tv[GO2_XREW_DOF_VEL] = s_qd; tv[GO2_XREW_DOF_VEL_LIMITS] = s_vl; tv[GO2_XREW_TORQUE_LIMITS] = s_tl; tv[GO2_XREW_SIMILAR_TO_DEFAULT] = s_def;
+  tv[GO2_XREW_TERMINATION] = (S.reset && !S.tout) ? 1.0f : 0.0f;                             // :1281-1283
+  if (sc[GO2_XREW_FEET_AIR_TIME] != 0.0f) {                                                  // :1347-1358
+    float r = 0.0f;
+    for (int l = 0; l < 4; ++l) {
+      const bool filt = contact[l] || st[4 + l] != 0.0f;
+      st[4 + l] = contact[l] ? 1.0f : 0.0f;
+      const bool first = st[l] > 0.0f && filt;
+      st[l] += C->dt;
+      r += (st[l] - 0.5f) * (first ? 1.0f : 0.0f);
+      if (filt) st[l] = 0.0f;
+    }
+    tv[GO2_XREW_FEET_AIR_TIME] = r * (cmd_xy > 0.1f ? 1.0f : 0.0f);
+  }
+  {
+    bool stumble = false;                                                                    // :1360-1363
+    float s_fc = 0.0f;                                                                       // feet_contact_forces :1369-1371
+    for (int l = 0; l < 4; ++l) {
+      const float* f = S.cf[6 + 4 * l];
+      stumble = stumble || (sqrtf(f[0] * f[0] + f[1] * f[1]) > 5.0f * fabsf(f[2]));
+      s_fc += fmaxf(sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) - C->max_contact_force, 0.0f);
+    }
+    tv[GO2_XREW_STUMBLE] = stumble ? 1.0f : 0.0f;
+    tv[GO2_XREW_FEET_CONTACT_FORCES] = s_fc;
+  }
+  tv[GO2_XREW_STAND_STILL] = s_def * (cmd_xy < 0.1f ? 1.0f : 0.0f);                          // :1365-1367
+  tv[GO2_XREW_UPRIGHT] = (-1.0f - S.pg[2]) / 2.0f;                                           // :1420-1421
+  {                                                                                          // legs_distance :1423-1441
+    float ly[4];
+    for (int l = 0; l < 4; ++l) ly[l] = quat_rotate_inverse(S.root + 3, mk(S.feet[l][0] - S.root[0], S.feet[l][1] - S.root[1], S.feet[l][2] - S.root[2])).y;
+    const float df = fmaxf(C->min_legs_distance - (ly[0] - ly[1]), 0.0f), dr = fmaxf(C->min_legs_distance - (ly[2] - ly[3]), 0.0f);
+    tv[GO2_XREW_LEGS_DISTANCE] = df * df + dr * dr;
+  }
+  if (sc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0.0f) {                                          // go2_env.py:62-68 (0 / 0 at an all-zero command, like the reference)
+    const float ratio = fabsf(S.cmd[0]) / sqrtf(S.cmd[0] * S.cmd[0] + S.cmd[1] * S.cmd[1] + S.cmd[2] * S.cmd[2]);
+    tv[GO2_XREW_X_COMMAND_HIP_REGULAR] = (fabsf(S.q[0] + S.q[3]) + fabsf(S.q[6] + S.q[9])) * ratio;
+  }
+  term_rew = 0.0f;
+  for (int k = 0; k < GO2_NUM_XREW; ++k) {
+    if (sc[k] == 0.0f) continue;
+    const float rk = tv[k] * sc[k] * X.sp->xrew_curriculum[k];
+    if (k == GO2_XREW_TERMINATION) term_rew = rk; else rew += rk;
+    sums[k] += rk;
+  }
+}
+
 #if defined(__CUDACC__)
 #define GO2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define GO2_ATOMIC_ADD_FIXED(acc, k, v) atomicAdd(reinterpret_cast<unsigned long long*>((acc) + GO2_EP_ACC_FIXED_OFF) + (k), (unsigned long long)__float2ll_rn((v) * GO2_EP_FIXED_ONE))
+#define GO2_ATOMIC_ADD_FIXED64(acc64, k, v) atomicAdd(reinterpret_cast<unsigned long long*>(acc64) + (k), (unsigned long long)__float2ll_rn((v) * GO2_EP_FIXED_ONE))
 #else
 #define GO2_ATOMIC_ADD(p, v) (*(p) += (v))
 #define GO2_ATOMIC_ADD_FIXED(acc, k, v) (reinterpret_cast<long long*>((acc) + GO2_EP_ACC_FIXED_OFF)[k] += llrintf((v) * GO2_EP_FIXED_ONE))
+#define GO2_ATOMIC_ADD_FIXED64(acc64, k, v) ((acc64)[k] += llrintf((v) * GO2_EP_FIXED_ONE))
 #endif
 
 // reset_idx for this env (legged_robot.py:180-245, :620-707, :1143-1169); `initial` = the reset at construction
@@ -1129,6 +1214,13 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, 
       *es = 0;
     }
     if (lane == 30 && !initial) GO2_ATOMIC_ADD(B->ep_accum + GO2_NUM_REW + 10, 1.0f);
+    if (C->num_xrew > 0 && lane >= 16 && lane < 16 + GO2_NUM_XREW) {     // the extra terms' episode sums (legged_robot.py:229-233), feet_air_time (:220)
+      const int k = lane - 16;
+      float* xs = GO2_EXT_PTR(float*, C, ext_xrew_sums) + (size_t)e * GO2_NUM_XREW + k;
+      if (!initial) GO2_ATOMIC_ADD_FIXED64(GO2_EXT_PTR(long long*, C, ext_xrew_log), k, *xs);
+      *xs = 0;
+      if (k < 4) GO2_EXT_PTR(float*, C, ext_xrew_state)[(size_t)e * 12 + k] = 0;
+    }
     if (lane == 0) {
       U4 s3 = philox(ge, sp->common_step_counter, ST_RESET_STATE, 3, C->seed_lo, C->seed_hi);
       U4 s4 = philox(ge, sp->common_step_counter, ST_RESET_STATE, 4, C->seed_lo, C->seed_hi);
@@ -1446,8 +1538,10 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
         rew += rk;
         S.termv[k] = rk;
       }
+      float term_rew = 0.0f;
+      if (C->num_xrew > 0) extra_rewards(S, X, e, rew, term_rew);
       if (C->only_positive_rewards) rew = fmaxf(rew, 0.0f);     // the episode sums keep the unclipped terms (legged_robot.py:263-267)
-      S.rew = rew;
+      S.rew = rew + term_rew;                                   // termination reward after the clip (legged_robot.py:268-272)
     }
   } GO2_SYNC_WARP(); GO2_TICK();
   GO2_WIDE {

@@ -63,6 +63,9 @@ class LeggedRobot:
         self.base_pos = self.root_states[:, 0:3]
         self.friction_coeffs = T["friction_coeffs"]
         self.episode_sums = {n: T["episode_sums"][:, k] for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales}
+        self.episode_sums.update({n: T["xrew_sums"][:, k] for k, n in enumerate(_abi.XREWARD_NAMES) if n in A.reward_scales})
+        self.feet_air_time = T["xrew_state"][:, 0:4]            # state of the feet_air_time / base_height reward terms (legged_robot.py:817-818,1248-1251)
+        self.last_contacts, self.last_contacts2 = T["xrew_state"][:, 4:8], T["xrew_state"][:, 8:12]
         self.env_command_ranges = {"lin_vel_x": T["env_command_ranges"][:, 0:2], "lin_vel_y": T["env_command_ranges"][:, 2:4],
                                    "ang_vel_yaw": T["env_command_ranges"][:, 4:6], "heading": T["heading_ranges"]}
         self.stop_heading = T["stop_heading"].view(torch.bool)
@@ -98,6 +101,8 @@ class LeggedRobot:
         self.zero_command_proba = 0.0
         self._ep_names = ["rew_" + n for n in _abi.REWARD_NAMES if n in A.reward_scales]
         self._ep_cols = [k for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales]
+        self._xep = [("rew_" + n, k) for k, n in enumerate(_abi.XREWARD_NAMES) if n in A.reward_scales]
+        self._xrew_stats = T["xrew_log"][_abi.NUM_XREW:].view(torch.float32).view(EP_SLOTS, _abi.NUM_XREW)   # rows behind the 14 int64 accumulators
         # ---- library handle
         h = ctypes.c_void_p()
         _abi.check(self._lib.go2_env_create(ctypes.byref(A.config), ctypes.byref(A.model), ctypes.byref(A.buffers), ctypes.byref(h)), self._lib)
@@ -235,6 +240,8 @@ class LeggedRobot:
         ep = {}
         for name, col in zip(self._ep_names, self._ep_cols):
             ep[name] = row[col]
+        for name, col in self._xep:
+            ep[name] = self._xrew_stats[slot, col]
         ep["terrain_level_all"] = row[_abi.NUM_REW]
         if not self._A.plane:
             for name, cols in self._A.terrain.name2cols.items():

@@ -56,10 +56,12 @@ class EnvArrays:
         # ---- rewards (scales * dt, zero scales dropped)
         scales = class_to_dict(cfg.rewards.scales)
         active = {k: v for k, v in scales.items() if v != 0}
-        unknown = sorted(set(active) - set(_abi.REWARD_NAMES))
-        if unknown:
-            raise NotImplementedError(f"reward terms {unknown} are outside the fused kernel's set {_abi.REWARD_NAMES}")
+        unknown = sorted(set(active) - set(_abi.REWARD_NAMES) - set(_abi.XREWARD_NAMES))
+        if unknown:      # the reference fails the same way: getattr(self, '_reward_' + name), legged_robot.py:936
+            raise AttributeError(f"no reward function for {unknown}: the kernel holds {_abi.REWARD_NAMES + _abi.XREWARD_NAMES}")
         self.reward_scales = {k: v * self.dt for k, v in active.items()}
+        # the terms outside the 14 every registered go2 task uses (legged_robot.py:1236-1441, go2_env.py:62-68): evaluated only when switched on
+        self.xreward_names = [n for n in _abi.XREWARD_NAMES if n in active]
         self.reward_curriculum_configs = list(cfg.rewards.curriculum_rewards or [])
 
         # ---- terrain
@@ -143,6 +145,8 @@ class EnvArrays:
         T["friction_coeffs"] = torch.from_numpy(friction[sl].astype(np.float32)).to(dev)
         T["restitutions"] = torch.from_numpy(rest[sl].astype(np.float32)).to(dev)
         T["body_inertia"] = torch.from_numpy(inertia).to(dev)
+        z("xrew_sums", N, _abi.NUM_XREW); z("xrew_state", N, 12)               # extra reward terms (Go2EnvConfig.ext_xrew_*)
+        z("xrew_log", _abi.XREW_LOG_BYTES // 8, dtype=torch.int64)
         z("ep_stats", EP_SLOTS, _abi.EP_STATS)
         z("ep_accum", _abi.EP_ACCUM_FLOATS)
         T["projected_gravity"][:, 2] = -1.0
@@ -213,6 +217,14 @@ class EnvArrays:
         c.max_episode_length, c.max_episode_length_s, c.dt = self.max_episode_length, self.max_episode_length_s, self.dt
         for k, name in enumerate(_abi.REWARD_NAMES):
             c.reward_scales[k] = self.reward_scales.get(name, 0.0)
+        c.num_xrew = len(self.xreward_names)
+        for k, name in enumerate(_abi.XREWARD_NAMES):
+            c.xrew_scales[k] = self.reward_scales.get(name, 0.0)
+        rw = cfg.rewards
+        c.soft_dof_vel_limit, c.soft_torque_limit = getattr(rw, "soft_dof_vel_limit", 1.0), getattr(rw, "soft_torque_limit", 1.0)
+        c.max_contact_force, c.min_legs_distance = getattr(rw, "max_contact_force", 100.0), getattr(rw, "min_legs_distance", 0.1)
+        for name, key in (("ext_xrew_sums", "xrew_sums"), ("ext_xrew_state", "xrew_state"), ("ext_xrew_log", "xrew_log")):
+            setattr(c, name + "_lo", T[key].data_ptr() & 0xFFFFFFFF); setattr(c, name + "_hi", T[key].data_ptr() >> 32)
         c.only_positive_rewards = int(bool(cfg.rewards.only_positive_rewards))     # off for every go2 task (go2_config.py:159)
         c.tracking_sigma, c.base_height_target = cfg.rewards.tracking_sigma, cfg.rewards.base_height_target
         for j in range(12):
@@ -314,6 +326,8 @@ class EnvArrays:
         rc = reward_curriculum if reward_curriculum is not None else self.reward_curriculum_scales(common_step_counter)
         for k, name in enumerate(_abi.REWARD_NAMES):
             sp.reward_curriculum[k] = rc.get(name, 1.0)
+        for k, name in enumerate(_abi.XREWARD_NAMES):
+            sp.xrew_curriculum[k] = rc.get(name, 1.0)
         zc = self.cfg.commands.zero_command_curriculum
         sp.zero_command_proba = self._scale(zc, it) if zc is not None else 0.0
         sp.max_lin_vel = self.max_lin_vel

@@ -122,8 +122,35 @@ typedef struct Go2EnvConfig {
      kernel argument nor this struct's 4-byte alignment changes (a pointer member raises it to 8 and alters the default build's code). */
   int32_t heading_command, stop_heading_at_limit;
   uint32_t ext_stop_heading_lo, ext_stop_heading_hi, ext_heading_ranges_lo, ext_heading_ranges_hi;
+  /* the reward functions that are INACTIVE in every registered go2 task (13 in legged_robot.py:1236-1441 + go2_env.py:62-68; enum Go2XReward):
+     evaluated only when num_xrew > 0, i.e. when cfg.rewards.scales gives one of them a non-zero scale.  xrew_scales are multiplied by dt like
+     reward_scales (0 = this term is off: its function is not called, so a stateful term does not advance its state — legged_robot.py:920-938).
+     Caller-owned device arrays (addresses as 32-bit halves, see above): xrew_sums [N, GO2_NUM_XREW] episode sums; xrew_state [N, 12]
+     (feet_air_time[4], last_contacts[4], last_contacts2[4] as 0 / 1); xrew_log = GO2_NUM_XREW int64 accumulators of the finished episodes'
+     sums in 2^-20 fixed point followed by GO2_EP_SLOTS rows of GO2_NUM_XREW float means (the counterpart of ep_accum / ep_stats). */
+  int32_t num_xrew;
+  float xrew_scales[14];
+  float soft_dof_vel_limit, soft_torque_limit, max_contact_force, min_legs_distance;
+  uint32_t ext_xrew_sums_lo, ext_xrew_sums_hi, ext_xrew_state_lo, ext_xrew_state_hi, ext_xrew_log_lo, ext_xrew_log_hi;
+  /* init_state.turn_over (legged_robot.py:114-115,174-175,257-265,586-590,642-691): robots are reset on their back / side with the given
+     proportions (back, side, no flip), contact termination is off, while |roll| > turn_over_roll_threshold every reward term uses its
+     turn_over scale instead of its normal one (to_scales / to_xscales, already x dt; terms of turn_over_scales need not be in scales), and
+     commands stay zero until the per-env timer [N] (caller-owned, ext_turn_over_timer) has run down. */
+  int32_t turn_over;
+  float turn_over_proportions[3], turn_over_back_height[2], turn_over_side_height[2];   /* heights as {lower, span} like the other uniform ranges */
+  float turn_over_zero_time_back, turn_over_zero_time_side, turn_over_roll_threshold;
+  float to_scales[GO2_NUM_REW], to_xscales[14];
+  uint32_t ext_turn_over_timer_lo, ext_turn_over_timer_hi;
 } Go2EnvConfig;
 #define GO2_EXT_PTR(type, cfg, name) ((type)(uintptr_t)(((uint64_t)(cfg)->name##_hi << 32) | (uint64_t)(cfg)->name##_lo))
+
+#define GO2_NUM_XREW 14
+enum Go2XReward {
+  GO2_XREW_ORIENTATION = 0, GO2_XREW_BASE_HEIGHT, GO2_XREW_DOF_VEL, GO2_XREW_TERMINATION, GO2_XREW_DOF_VEL_LIMITS, GO2_XREW_TORQUE_LIMITS,
+  GO2_XREW_FEET_AIR_TIME, GO2_XREW_STUMBLE, GO2_XREW_STAND_STILL, GO2_XREW_FEET_CONTACT_FORCES, GO2_XREW_SIMILAR_TO_DEFAULT, GO2_XREW_UPRIGHT,
+  GO2_XREW_LEGS_DISTANCE, GO2_XREW_X_COMMAND_HIP_REGULAR
+};
+#define GO2_XREW_LOG_BYTES (GO2_NUM_XREW * 8 + GO2_EP_SLOTS * GO2_NUM_XREW * 4)
 
 /* Per-step scalars the host derives from common_step_counter (curricula), no device sync involved. */
 typedef struct Go2StepParams {
@@ -132,6 +159,7 @@ typedef struct Go2StepParams {
   float zero_command_proba;       /* legged_robot.py:556-557 */
   float max_lin_vel;              /* legged_robot.py:442 */
   int32_t ep_slot;                /* row of ep_stats this step writes */
+  float xrew_curriculum[14];      /* reward_curriculum of the extra terms (enum Go2XReward), 1.0 where no curriculum */
 } Go2StepParams;
 
 /* Caller-owned arrays (device pointers for the CUDA library, host pointers for the oracle). */

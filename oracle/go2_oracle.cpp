@@ -680,7 +680,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
   const Go2EnvConfig& C = *Cp; const Go2Model& M = *Mp; const Go2EnvBuffers& B = *Bp; const Go2StepParams& sp = *spp;
   const int N = C.num_envs;
   Terrain T{Cp, B.height_samples};
-  std::vector<double> acc(GO2_EP_STATS, 0.0);
+  std::vector<double> acc(GO2_EP_STATS, 0.0), xacc(GO2_NUM_XREW, 0.0);
   std::vector<double> lvl_sum(9, 0.0), lvl_cnt(9, 0.0);
   int n_reset = 0;
   std::vector<char> bad(N, 0);
@@ -840,10 +840,86 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
       rew += rk;
       B.episode_sums[(size_t)e * GO2_NUM_REW + k] += rk;
     }
+    float term_rew = 0;
+    if (C.num_xrew > 0) {
+      // the reward functions no registered go2 task switches on (legged_robot.py:1236-1441, go2_env.py:62-68); a function with a zero scale is not
+      // called by the reference (:920-938), so the stateful ones only advance when active
+      float* xs = GO2_EXT_PTR(float*, &C, ext_xrew_sums) + (size_t)e * GO2_NUM_XREW;
+      float* st = GO2_EXT_PTR(float*, &C, ext_xrew_state) + (size_t)e * 12;   // feet_air_time[4], last_contacts[4], last_contacts2[4]
+      const float* sc = C.xrew_scales;
+      float xv[GO2_NUM_XREW] = {0};
+      const float* feet_f[4]; const float* feet_p[4]; bool contact[4];
+      for (int l = 0; l < 4; ++l) { feet_f[l] = cf + (6 + 4 * l) * 3; feet_p[l] = B.feet_pos + ((size_t)e * 4 + l) * 3; contact[l] = feet_f[l][2] > 1.0f; }
+      const float cmd_xy = std::sqrt(cmd[0] * cmd[0] + cmd[1] * cmd[1]);
+      xv[GO2_XREW_ORIENTATION] = pg[0] * pg[0] + pg[1] * pg[1];                                    // :1236-1238
+      if (sc[GO2_XREW_BASE_HEIGHT] != 0) {                                                           // :1245-1259
+        float nfc = 0, fcp[3] = {0, 0, 0};
+        for (int l = 0; l < 4; ++l) {
+          bool filt = contact[l] || st[8 + l] != 0;
+          st[8 + l] = contact[l];
+          if (filt) { nfc += 1; for (int k = 0; k < 3; ++k) fcp[k] += feet_p[l][k]; }
+        }
+        float den = std::max(nfc, 1.0f), bh = 0;
+        for (int k = 0; k < 3; ++k) bh += (fcp[k] / den - rs[k]) * pg[k];
+        xv[GO2_XREW_BASE_HEIGHT] = (bh - C.base_height_target) * (bh - C.base_height_target) * (nfc > 0 ? 1.0f : 0.0f);
+      }
+      float s_qd = 0, s_vl = 0, s_tl = 0, s_def = 0;
+      for (int j = 0; j < GO2_NUM_DOF; ++j) {
+        s_qd += qd[j] * qd[j];                                                                                             // dof_vel :1265-1267
+        s_vl += std::min(std::max(std::fabs(qd[j]) - M.vel_limit[j] * C.soft_dof_vel_limit, 0.0f), 1.0f);                   // dof_vel_limits :1291-1294
+        s_tl += std::max(std::fabs(tq[j]) - M.effort[j] * C.soft_torque_limit, 0.0f);                                      // torque_limits :1296-1298
+        s_def += std::fabs(q[j] - C.default_dof_pos[j]);                                                                   // similar_to_default :1416-1418
+      }
+      xv[GO2_XREW_DOF_VEL] = s_qd; xv[GO2_XREW_DOF_VEL_LIMITS] = s_vl; xv[GO2_XREW_TORQUE_LIMITS] = s_tl; xv[GO2_XREW_SIMILAR_TO_DEFAULT] = s_def;
+      xv[GO2_XREW_TERMINATION] = (B.reset_buf[e] && !B.time_out_buf[e]) ? 1.0f : 0.0f;               // :1281-1283
+      if (sc[GO2_XREW_FEET_AIR_TIME] != 0) {                                                          // :1347-1358
+        float r = 0;
+        for (int l = 0; l < 4; ++l) {
+          bool filt = contact[l] || st[4 + l] != 0;
+          st[4 + l] = contact[l];
+          bool first = st[l] > 0 && filt;
+          st[l] += C.dt;
+          r += (st[l] - 0.5f) * (first ? 1.0f : 0.0f);
+          if (filt) st[l] = 0;
+        }
+        xv[GO2_XREW_FEET_AIR_TIME] = r * (cmd_xy > 0.1f ? 1.0f : 0.0f);
+      }
+      bool stumble = false; float s_fc = 0;
+      for (int l = 0; l < 4; ++l) {
+        const float* f = feet_f[l];
+        stumble = stumble || (std::sqrt(f[0] * f[0] + f[1] * f[1]) > 5 * std::fabs(f[2]));           // :1360-1363
+        s_fc += std::max(std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) - C.max_contact_force, 0.0f);   // :1369-1371
+      }
+      xv[GO2_XREW_STUMBLE] = stumble; xv[GO2_XREW_FEET_CONTACT_FORCES] = s_fc;
+      xv[GO2_XREW_STAND_STILL] = s_def * (cmd_xy < 0.1f ? 1.0f : 0.0f);                              // :1365-1367
+      xv[GO2_XREW_UPRIGHT] = (-1 - pg[2]) / 2;                                                       // :1420-1421
+      {                                                                                              // legs_distance :1423-1441
+        float ly[4];
+        for (int l = 0; l < 4; ++l) {
+          real d[3] = {feet_p[l][0] - rs[0], feet_p[l][1] - rs[1], feet_p[l][2] - rs[2]}, o[3];
+          quat_rotate_inverse(qr, d, o); ly[l] = (float)o[1];
+        }
+        float df = std::max(C.min_legs_distance - (ly[0] - ly[1]), 0.0f), dr = std::max(C.min_legs_distance - (ly[2] - ly[3]), 0.0f);
+        xv[GO2_XREW_LEGS_DISTANCE] = df * df + dr * dr;
+      }
+      if (sc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0)                                                  // go2_env.py:62-68
+        xv[GO2_XREW_X_COMMAND_HIP_REGULAR] = (std::fabs(q[0] + q[3]) + std::fabs(q[6] + q[9])) * (std::fabs(cmd[0]) / std::sqrt(cmd[0] * cmd[0] + cmd[1] * cmd[1] + cmd[2] * cmd[2]));
+      for (int k = 0; k < GO2_NUM_XREW; ++k) {
+        if (sc[k] == 0) continue;
+        float rk = xv[k] * sc[k] * sp.xrew_curriculum[k];
+        if (k == GO2_XREW_TERMINATION) term_rew = rk; else rew += rk;
+        xs[k] += rk;
+      }
+    }
     if (C.only_positive_rewards) rew = std::max(rew, 0.0f);   // legged_robot.py:266-267 (episode sums keep the unclipped terms)
-    B.rew_buf[e] = rew;
+    B.rew_buf[e] = rew + term_rew;                            // termination reward after the clip (:268-272)
     if (B.reset_buf[e]) {
       n_reset++;
+      if (C.num_xrew > 0) {
+        float* xs = GO2_EXT_PTR(float*, &C, ext_xrew_sums) + (size_t)e * GO2_NUM_XREW;
+        for (int k = 0; k < GO2_NUM_XREW; ++k) { xacc[k] += xs[k]; xs[k] = 0; }
+        for (int l = 0; l < 4; ++l) GO2_EXT_PTR(float*, &C, ext_xrew_state)[(size_t)e * 12 + l] = 0;    // feet_air_time, legged_robot.py:220
+      }
       for (int k = 0; k < GO2_NUM_REW; ++k) { acc[k] += B.episode_sums[(size_t)e * GO2_NUM_REW + k]; B.episode_sums[(size_t)e * GO2_NUM_REW + k] = 0; }
       reset_env(C, M, B, sp, e, false);
     }
@@ -883,6 +959,12 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     for (int i = 0; i < GO2_NUM_PRIV; ++i) pv[i] = std::min(std::max(pv[i], -C.clip_obs), C.clip_obs);
     for (int j = 0; j < GO2_NUM_DOF; ++j) { lact[j] = act[j]; lqd[j] = qd[j]; }
   }
+  if (C.num_xrew > 0) {   // the extra terms' episode means (rows behind the 14 int64 accumulators the kernel uses; the oracle sums in double)
+    float* xst = reinterpret_cast<float*>(GO2_EXT_PTR(long long*, &C, ext_xrew_log) + GO2_NUM_XREW);
+    for (int k = 0; k < GO2_NUM_XREW; ++k)
+      xst[(size_t)sp.ep_slot * GO2_NUM_XREW + k] = n_reset > 0 ? (float)(xacc[k] / n_reset) / C.max_episode_length_s
+                                                               : xst[(size_t)((sp.ep_slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_NUM_XREW + k];
+  }
   // extras["episode"], legged_robot.py:229-242 — only refreshed when at least one env reset
   if (n_reset > 0 && B.ep_stats) {
     float* st = B.ep_stats + (size_t)sp.ep_slot * GO2_EP_STATS;
@@ -905,6 +987,10 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
 int go2_oracle_reset_all(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* B, const Go2StepParams* sp) {
   for (int e = 0; e < C->num_envs; ++e) {
     for (int k = 0; k < GO2_NUM_REW; ++k) B->episode_sums[(size_t)e * GO2_NUM_REW + k] = 0;
+    if (C->num_xrew > 0) {
+      for (int k = 0; k < GO2_NUM_XREW; ++k) GO2_EXT_PTR(float*, C, ext_xrew_sums)[(size_t)e * GO2_NUM_XREW + k] = 0;
+      for (int l = 0; l < 4; ++l) GO2_EXT_PTR(float*, C, ext_xrew_state)[(size_t)e * 12 + l] = 0;
+    }
     reset_env(*C, *M, *B, *sp, e, true);
   }
   return 0;

@@ -30,6 +30,15 @@ int go2_emu_step(const Go2EnvConfig* C, const Go2Model* M, const Go2EnvBuffers* 
   for_groups(C, [&](Lane* lanes, int NT, WarpSmem* SM) { step_env<EmuT>(lanes, NT, SM, X); });
   // finalize extras["episode"] (mirrors the tiny finalize kernel)
   float n_reset = B->ep_accum[GO2_NUM_REW + 10];
+  if (C->num_xrew > 0) {
+    long long* xacc = GO2_EXT_PTR(long long*, C, ext_xrew_log);
+    float* xst = reinterpret_cast<float*>(xacc + GO2_NUM_XREW);
+    for (int k = 0; k < GO2_NUM_XREW; ++k) {
+      if (n_reset > 0) xst[(size_t)sp->ep_slot * GO2_NUM_XREW + k] = (float)((double)xacc[k] / (double)GO2_EP_FIXED_ONE) / n_reset / C->max_episode_length_s;
+      else xst[(size_t)sp->ep_slot * GO2_NUM_XREW + k] = xst[(size_t)((sp->ep_slot + GO2_EP_SLOTS - 1) % GO2_EP_SLOTS) * GO2_NUM_XREW + k];
+      xacc[k] = 0;
+    }
+  }
   if (n_reset > 0 && B->ep_stats) {
     float* st = B->ep_stats + (size_t)sp->ep_slot * GO2_EP_STATS;
     for (int k = 0; k < GO2_NUM_REW; ++k)

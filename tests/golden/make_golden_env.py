@@ -313,7 +313,7 @@ STATE_KEYS = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "l
               "commands", "commands_resampling_step", "commands_xy_accumulation", "last_is_limit_vel", "episode_length_buf",
               "terrain_levels", "env_origins", "max_move_distance", "motor_strengths", "motor_zero_offsets",
               "p_gains_multiplier", "d_gains_multiplier", "episode_sums", "friction_coeffs", "restitutions", "body_inertia",
-              "contact_forces"]
+              "contact_forces", "xrew_sums", "xrew_state"]
 OUT_KEYS = ["obs_buf", "privileged_obs_buf", "rew_buf", "reset_buf", "time_out_buf", "root_states", "dof_pos", "dof_vel", "torques",
             "commands", "commands_resampling_step", "commands_xy_accumulation", "last_is_limit_vel", "episode_length_buf",
             "terrain_levels", "env_origins", "max_move_distance", "motor_strengths", "motor_zero_offsets", "p_gains_multiplier",
@@ -342,6 +342,12 @@ def load_state_into_reference(r, A):
     for k, name in enumerate(_abi.REWARD_NAMES):
         r.episode_sums[name].copy_(T["episode_sums"][:, k])
     r.contact_forces.copy_(T["contact_forces"])
+    for k, name in enumerate(_abi.XREWARD_NAMES):      # the reward terms outside the GO2 defaults, when the case switches them on
+        if name in r.episode_sums:
+            r.episode_sums[name].copy_(T["xrew_sums"][:, k])
+    r.feet_air_time.copy_(T["xrew_state"][:, 0:4])
+    r.last_contacts.copy_(T["xrew_state"][:, 4:8].bool())
+    r.last_contacts2 = T["xrew_state"][:, 8:12].bool().clone()        # created lazily by _reward_base_height (legged_robot.py:1248-1249)
 
 
 def _apply(cfg, overrides):
@@ -351,7 +357,7 @@ def _apply(cfg, overrides):
         parts = path.split(".")
         for p in parts[:-1]:
             node = getattr(node, p)
-        assert hasattr(node, parts[-1]), path
+        assert hasattr(node, parts[-1]) or parts[:-1] == ["rewards", "scales"], path      # reward scales may be added (the reference looks the function up by name)
         setattr(node, parts[-1], val)
 
 
@@ -432,6 +438,8 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
                "motor_zero_offsets": r.motor_zero_offsets, "p_gains_multiplier": r.p_gains_multiplier,
                "d_gains_multiplier": r.d_gains_multiplier,
                "episode_sums": torch.stack([r.episode_sums[n] for n in _abi.REWARD_NAMES], 1),
+               "xrew_sums": torch.stack([r.episode_sums[n] if n in r.episode_sums else torch.zeros(N) for n in _abi.XREWARD_NAMES], 1),
+               "xrew_state": torch.cat([r.feet_air_time, r.last_contacts.float(), getattr(r, "last_contacts2", torch.zeros(N, 4)).float()], 1),
                "base_lin_vel": r.base_lin_vel, "base_ang_vel": r.base_ang_vel, "projected_gravity": r.projected_gravity,
                "measured_heights": r.measured_heights if not plane else torch.zeros(N, 187),
                "last_actions": r.last_actions, "last_last_actions": r.last_last_actions, "last_dof_vel": r.last_dof_vel,
@@ -439,6 +447,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
                "terrain_levels": (r.terrain_levels.int() if not plane else torch.zeros(N, dtype=torch.int32))}
         ep = extras.get("episode", {})
         rec["ep_rew"] = torch.tensor([float(ep.get("rew_" + n, float("nan"))) for n in _abi.REWARD_NAMES])
+        rec["ep_xrew"] = torch.tensor([float(ep.get("rew_" + n, float("nan"))) for n in _abi.XREWARD_NAMES])
         rec["ep_terrain_level_all"] = torch.tensor(float(ep.get("terrain_level_all", float("nan"))))
         outs.append({kk: vv.clone().numpy() for kk, vv in rec.items()})
     save = {"meta_N": N, "meta_K": K, "meta_seed": seed, "meta_plane": int(plane), "meta_start_counter": start_counter + 30,
@@ -460,6 +469,16 @@ if __name__ == "__main__":
         make_case("ctrl_v_pos", plane=False, N=32, K=4, seed=13, control_type="V", only_positive=True)
         make_case("ctrl_t", plane=True, N=32, K=3, seed=14, control_type="T")
         make_case("heading", plane=False, N=48, K=6, seed=15, heading=True)
+        sys.exit(0)
+    if "--xrew" in sys.argv:          # every reward function the registered go2 tasks leave off (legged_robot.py:1236-1441, go2_env.py:62-68), switched on
+        xr = {"orientation": -0.2, "base_height": -1.0, "dof_vel": -1e-4, "termination": -2.0, "dof_vel_limits": -0.5, "torque_limits": -0.01,
+              "feet_air_time": 1.0, "stumble": -0.5, "stand_still": -0.1, "feet_contact_forces": -0.01, "similar_to_default": -0.02, "upright": 0.3,
+              "legs_distance": -1.5, "x_command_hip_regular": -0.05}
+        ov = {"rewards.scales." + k: v for k, v in xr.items()}
+        ov.update({"rewards.max_contact_force": 20.0, "rewards.soft_dof_vel_limit": 0.1, "rewards.soft_torque_limit": 0.3, "rewards.min_legs_distance": 0.25,
+                   "rewards.base_height_target": 0.3})
+        make_case("xrew", plane=False, N=48, K=8, seed=21, overrides=ov)
+        make_case("xrew_pos", plane=True, N=32, K=5, seed=22, only_positive=True, overrides={k: v for k, v in ov.items() if "hip_regular" not in k})
         sys.exit(0)
     make_case("rough", plane=False)
     make_case("plane", plane=True, N=32, K=4)

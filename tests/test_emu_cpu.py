@@ -23,10 +23,10 @@ def test_emulated_kernel_matches_reference_golden(name, packed):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "cmdcur"])
+@pytest.mark.parametrize("packed", [False, True, 14])
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "cmdcur", "xrew", "xrew_pos"])
 def test_emulated_kernel_matches_reference_golden_with_env_switches(name, packed):
-    """control_type 'V' / 'T', only_positive_rewards, heading commands and the command-range curriculum boundary:
+    """control_type 'V' / 'T', only_positive_rewards, heading commands, the 14 reward functions no registered task switches on and the command-range curriculum boundary:
     every recorded step of the reference-made fixture, state re-synchronised to the fixture between steps."""
     z, A = load_case(name)
     env = EmuEnv(A, packed=packed)

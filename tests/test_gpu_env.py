@@ -42,11 +42,12 @@ def _cmp(Tg, Tc, loose=1.0):
 TOL_V = dict(TOL, dof_vel=(1e-3, 0.1), last_dof_vel=(1e-3, 0.1), torques=(1e-3, 0.1), privileged_obs_buf=(1e-3, 1e-2), obs_buf=(1e-3, 1e-2))
 
 
-@pytest.mark.parametrize("name", ["rough", "plane", "cmdcur", "ctrl_v_pos", "ctrl_t", "heading"])
+@pytest.mark.parametrize("name", ["rough", "plane", "cmdcur", "ctrl_v_pos", "ctrl_t", "heading", "xrew", "xrew_pos"])
 def test_cuda_replays_reference_golden(name):
     """EVERY recorded step of each fixture made by the REFERENCE's own Python (run over the oracle physics): GO2 defaults on rough terrain and on the
     plane, the command-range curriculum boundary at learning iteration 20 000 (legged_robot.py:433-446), control types 'V' / 'T' with
-    only_positive_rewards (legged_robot.py:605-618,266-267) and heading commands (:411-419).  State re-synchronised to the fixture between steps."""
+    only_positive_rewards (legged_robot.py:605-618,266-267), heading commands (:411-419) and the 14 reward functions the registered tasks leave off
+    (:1236-1441, go2_env.py:62-68; xrew_sums / xrew_state = their episode sums and feet_air_time / last_contacts state).  State re-synchronised to the fixture between steps."""
     from cuda_util import CudaEnv
     z, A = load_case(name, device="cuda")
     env = CudaEnv(A)
