@@ -251,6 +251,8 @@ int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvB
     return go2::set_error(1, "go2_env_create: heading_command needs ext_stop_heading and ext_heading_ranges");
   if (cfg->num_xrew > 0 && (!GO2_EXT_PTR(const void*, cfg, ext_xrew_sums) || !GO2_EXT_PTR(const void*, cfg, ext_xrew_state) || !GO2_EXT_PTR(const void*, cfg, ext_xrew_log)))
     return go2::set_error(1, "go2_env_create: extra reward terms need ext_xrew_sums, ext_xrew_state and ext_xrew_log");
+  if (cfg->turn_over && (!GO2_EXT_PTR(const void*, cfg, ext_turn_over_timer) || !GO2_EXT_PTR(const void*, cfg, ext_stop_heading)))
+    return go2::set_error(1, "go2_env_create: turn_over needs ext_turn_over_timer and ext_stop_heading");
   if (cfg->control_type < 0 || cfg->control_type > 2) return go2::set_error(2, "go2_env_create: control_type must be 0 (P), 1 (V) or 2 (T)");
   // the kernel bakes the Go2 topology: hip = x axis, thigh/calf = y axis, collider lanes grouped per body
   for (int j = 0; j < GO2_NUM_DOF; ++j)

@@ -1074,6 +1074,10 @@ GO2_HD void resample_commands(SMT& S, const StepCtx& X, int e, int stream) {
       }
     }
   }
+  if (C->turn_over && GO2_EXT_PTR(const float*, C, ext_turn_over_timer)[e] > 0.0f) {      // turn-over zero-command time (legged_robot.py:585-590)
+    S.cmd[0] = 0; S.cmd[1] = 0; S.cmd[2] = 0;
+    S.stop_heading = 1;
+  }
   S.acc_xy[0] += S.cmd[0]; S.acc_xy[1] += S.cmd[1];
 }
 
@@ -1097,20 +1101,21 @@ GO2_HD void heading_to_yaw(SMT& S) {
 // not advance its state (feet_air_time / last_contacts, last_contacts2).  rew receives the scaled terms; the termination term is returned
 // separately: the reference adds it after the only_positive_rewards clip (legged_robot.py:268-272).
 template <class SMT>
-GO2_HD void extra_rewards(SMT& S, const StepCtx& X, int e, float& rew, float& term_rew) {
+GO2_HD void extra_rewards(SMT& S, const StepCtx& X, int e, bool need_to, float& rew, float& term_rew) {
   const Go2EnvConfig* C = X.cs;
   const Go2EnvConfig* CT = X.cfg;
   const Go2Model* M = X.mdl;
   float* sums = GO2_EXT_PTR(float*, C, ext_xrew_sums) + (size_t)e * GO2_NUM_XREW;
   float* st = GO2_EXT_PTR(float*, C, ext_xrew_state) + (size_t)e * 12;
   const float* sc = C->xrew_scales;
+  const float* tsc = C->to_xscales;      // turn_over scales: a term is evaluated when either scale is set (legged_robot.py:925-930)
   float tv[GO2_NUM_XREW];
   for (int k = 0; k < GO2_NUM_XREW; ++k) tv[k] = 0.0f;
   const float cmd_xy = sqrtf(S.cmd[0] * S.cmd[0] + S.cmd[1] * S.cmd[1]);
   bool contact[4];
   for (int l = 0; l < 4; ++l) contact[l] = S.cf[6 + 4 * l][2] > 1.0f;                       // feet_indices = reported bodies 6 + 4 l
   tv[GO2_XREW_ORIENTATION] = S.pg[0] * S.pg[0] + S.pg[1] * S.pg[1];                          // :1236-1238
-  if (sc[GO2_XREW_BASE_HEIGHT] != 0.0f) {                                                    // :1245-1259
+  if (sc[GO2_XREW_BASE_HEIGHT] != 0.0f || tsc[GO2_XREW_BASE_HEIGHT] != 0.0f) {                                                    // :1245-1259
     float nfc = 0.0f, fcp[3] = {0.0f, 0.0f, 0.0f};
     for (int l = 0; l < 4; ++l) {
       const bool filt = contact[l] || st[8 + l] != 0.0f;
@@ -1131,7 +1136,7 @@ GO2_HD void extra_rewards(SMT& S, const StepCtx& X, int e, float& rew, float& te
   }
   tv[GO2_XREW_DOF_VEL] = s_qd; tv[GO2_XREW_DOF_VEL_LIMITS] = s_vl; tv[GO2_XREW_TORQUE_LIMITS] = s_tl; tv[GO2_XREW_SIMILAR_TO_DEFAULT] = s_def;
   tv[GO2_XREW_TERMINATION] = (S.reset && !S.tout) ? 1.0f : 0.0f;                             // :1281-1283
-  if (sc[GO2_XREW_FEET_AIR_TIME] != 0.0f) {                                                  // :1347-1358
+  if (sc[GO2_XREW_FEET_AIR_TIME] != 0.0f || tsc[GO2_XREW_FEET_AIR_TIME] != 0.0f) {                                                  // :1347-1358
     float r = 0.0f;
     for (int l = 0; l < 4; ++l) {
       const bool filt = contact[l] || st[4 + l] != 0.0f;
@@ -1162,14 +1167,14 @@ GO2_HD void extra_rewards(SMT& S, const StepCtx& X, int e, float& rew, float& te
     const float df = fmaxf(C->min_legs_distance - (ly[0] - ly[1]), 0.0f), dr = fmaxf(C->min_legs_distance - (ly[2] - ly[3]), 0.0f);
     tv[GO2_XREW_LEGS_DISTANCE] = df * df + dr * dr;
   }
-  if (sc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0.0f) {                                          // go2_env.py:62-68 (0 / 0 at an all-zero command, like the reference)
+  if (sc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0.0f || tsc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0.0f) {                                          // go2_env.py:62-68 (0 / 0 at an all-zero command, like the reference)
     const float ratio = fabsf(S.cmd[0]) / sqrtf(S.cmd[0] * S.cmd[0] + S.cmd[1] * S.cmd[1] + S.cmd[2] * S.cmd[2]);
     tv[GO2_XREW_X_COMMAND_HIP_REGULAR] = (fabsf(S.q[0] + S.q[3]) + fabsf(S.q[6] + S.q[9])) * ratio;
   }
   term_rew = 0.0f;
   for (int k = 0; k < GO2_NUM_XREW; ++k) {
-    if (sc[k] == 0.0f) continue;
-    const float rk = tv[k] * sc[k] * X.sp->xrew_curriculum[k];
+    if (sc[k] == 0.0f && tsc[k] == 0.0f) continue;
+    const float rk = tv[k] * ((need_to && k != GO2_XREW_TERMINATION) ? tsc[k] : sc[k]) * X.sp->xrew_curriculum[k];
     if (k == GO2_XREW_TERMINATION) term_rew = rk; else rew += rk;
     sums[k] += rk;
   }
@@ -1245,6 +1250,27 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, 
       float yaw = affine(2 * PI_F, u01(s3.x), -PI_F);
       for (int i = 0; i < 13; ++i) S.root[i] = C->base_init_state[i];
       S.root[3] = 0; S.root[4] = 0; S.root[5] = sinf(GO2_FMUL(yaw, 0.5f)); S.root[6] = cosf(GO2_FMUL(yaw, 0.5f));
+      if (C->turn_over) {       // flipped initial poses (legged_robot.py:642-691): on the back (roll pi), on a side (roll +- pi / 2) or upright
+        float* tt = GO2_EXT_PTR(float*, C, ext_turn_over_timer) + e;
+        *tt = 0.0f;
+        const float rp = u01(s5.z);
+        const float* pr = C->turn_over_proportions;       // cumulative: [back, back + side, back + side + none]
+        const bool back = rp >= 0.0f && rp < pr[0], side = rp >= pr[0] && rp < pr[1], none = rp >= pr[1] && rp < pr[2];
+        if (back || side) {
+          U4 s6 = philox(ge, sp->common_step_counter, ST_RESET_STATE, 6, C->seed_lo, C->seed_hi);
+          float roll;
+          if (back) { S.root[2] = affine(C->turn_over_back_height[1], u01(s6.x), C->turn_over_back_height[0]); roll = PI_F; *tt = C->turn_over_zero_time_back; }
+          else { S.root[2] = affine(C->turn_over_side_height[1], u01(s6.y), C->turn_over_side_height[0]); roll = (u01(s5.w) < 0.5f) ? 0.5f * PI_F : -0.5f * PI_F; *tt = C->turn_over_zero_time_side; }
+          // quat_from_euler_xyz(roll, 0, yaw) in torch's operation order (cp = 1, sp = 0)
+          const float cy = cosf(GO2_FMUL(yaw, 0.5f)), sy = sinf(GO2_FMUL(yaw, 0.5f)), cr = cosf(GO2_FMUL(roll, 0.5f)), sr = sinf(GO2_FMUL(roll, 0.5f));
+          S.root[6] = GO2_FADD(GO2_FMUL(GO2_FMUL(cy, cr), 1.0f), GO2_FMUL(GO2_FMUL(sy, sr), 0.0f));
+          S.root[3] = GO2_FADD(GO2_FMUL(GO2_FMUL(cy, sr), 1.0f), -GO2_FMUL(GO2_FMUL(sy, cr), 0.0f));
+          S.root[4] = GO2_FADD(GO2_FMUL(GO2_FMUL(cy, cr), 0.0f), GO2_FMUL(GO2_FMUL(sy, sr), 1.0f));
+          S.root[5] = GO2_FADD(GO2_FMUL(GO2_FMUL(sy, cr), 1.0f), -GO2_FMUL(GO2_FMUL(cy, sr), 0.0f));
+        } else if (!none) {     // proportions that do not add up to one leave the configured orientation (base_init_state) for the remainder
+          for (int i = 3; i < 7; ++i) S.root[i] = C->base_init_state[i];
+        }
+      }
       for (int i = 0; i < 3; ++i) S.root[i] = GO2_FADD(S.root[i], S.env_origin[i]);
       if (C->custom_origins) { S.root[0] = GO2_FADD(S.root[0], affine(2.0f, u01(s3.y), -1.0f)); S.root[1] = GO2_FADD(S.root[1], affine(2.0f, u01(s3.z), -1.0f)); }
       S.root[7] = u01(s4.x) - 0.5f; S.root[8] = u01(s4.y) - 0.5f; S.root[9] = u01(s4.z) - 0.5f;
@@ -1342,7 +1368,7 @@ GO2_HD void load_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       if (C->heading_command) {
         const float* hr = GO2_EXT_PTR(const float*, C, ext_heading_ranges);
         S.stop_heading = GO2_EXT_PTR(const uint8_t*, C, ext_stop_heading)[e]; S.hrng[0] = hr[(size_t)e * 2]; S.hrng[1] = hr[(size_t)e * 2 + 1];
-      }
+      } else if (C->turn_over) S.stop_heading = GO2_EXT_PTR(const uint8_t*, C, ext_stop_heading)[e];    // the flag is also set by the turn-over zero-command time
       S.mu_env = 0.5f * (C->terrain_friction + v_fr);
       S.rest_env = 0.5f * (C->terrain_restitution + v_re);
     }
@@ -1370,7 +1396,7 @@ GO2_HD void store_state(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
     if (lane == 25) { B->episode_length_buf[e] = S.ep_len; B->commands_resampling_step[e] = S.resamp_step; }
     if (lane == 26) { B->commands_xy_accumulation[(size_t)e * 2] = S.acc_xy[0]; B->commands_xy_accumulation[(size_t)e * 2 + 1] = S.acc_xy[1]; }
     if (lane == 27) { B->max_move_distance[e] = S.max_move; B->last_is_limit_vel[e] = (uint8_t)S.last_lim; }
-    if (lane == 30 && X.cs->heading_command) GO2_EXT_PTR(uint8_t*, X.cs, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
+    if (lane == 30 && (X.cs->heading_command || X.cs->turn_over)) GO2_EXT_PTR(uint8_t*, X.cs, ext_stop_heading)[e] = (uint8_t)S.stop_heading;
     if (lane == 28) B->terrain_levels[e] = S.level;
     if (lane == 29) { B->reset_buf[e] = (uint8_t)S.reset; B->time_out_buf[e] = (uint8_t)S.tout; }
     GO2_STRIDED(i, GO2_NUM_REPORT * 3) B->contact_forces[(size_t)e * GO2_NUM_REPORT * 3 + i] = S.cf[i / 3][i % 3];
@@ -1448,6 +1474,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
     if (lane == 0) {
       S.ep_len += 1;
       S.resamp_step -= 1.0f;
+      if (C->turn_over) { float* tt = GO2_EXT_PTR(float*, C, ext_turn_over_timer) + e; *tt = fmaxf(*tt - C->dt, 0.0f); }   // legged_robot.py:114-115
       V3 blv = quat_rotate_inverse(S.root + 3, ld3(S.root + 7)), bav = quat_rotate_inverse(S.root + 3, ld3(S.root + 10));
       V3 pg = quat_rotate_inverse(S.root + 3, mk(0.0f, 0.0f, -1.0f));
       st3(S.blv, blv); st3(S.bav, bav); st3(S.pg, pg);
@@ -1488,7 +1515,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       for (int k = 0; k < 32; ++k) sh += S.part[k];
       S.base_height = S.root[2] - sh / C->num_base_height_points;
       const float* f = S.cf[0];
-      int term = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
+      int term = !C->turn_over && sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;     // no contact termination with turn_over (legged_robot.py:174-175)
       S.tout = S.ep_len > C->max_episode_length;
       S.reset = term || S.tout;
       S.reset |= S.bad;
@@ -1533,13 +1560,18 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       tv[GO2_REW_COLLISION] = cs;
       tv[GO2_REW_FEET_REGULATION] = S.fterm[0] + S.fterm[1] + S.fterm[2] + S.fterm[3];
       float rew = 0;
+      bool need_to = false;     // turn_over: while |roll| exceeds the threshold every term uses its turn_over scale (legged_robot.py:257-265; get_euler_xyz, isaacgym_utils.py:11-17)
+      if (C->turn_over) {
+        const float qx = S.root[3], qy = S.root[4], qz = S.root[5], qw = S.root[6];
+        need_to = fabsf(atan2f(2.0f * (qw * qx + qy * qz), qw * qw - qx * qx - qy * qy + qz * qz)) > C->turn_over_roll_threshold;
+      }
       for (int k = 0; k < GO2_NUM_REW; ++k) {
-        float rk = tv[k] * C->reward_scales[k] * sp->reward_curriculum[k];
+        float rk = tv[k] * (need_to ? C->to_scales[k] : C->reward_scales[k]) * sp->reward_curriculum[k];
         rew += rk;
         S.termv[k] = rk;
       }
       float term_rew = 0.0f;
-      if (C->num_xrew > 0) extra_rewards(S, X, e, rew, term_rew);
+      if (C->num_xrew > 0) extra_rewards(S, X, e, need_to, rew, term_rew);
       if (C->only_positive_rewards) rew = fmaxf(rew, 0.0f);     // the episode sums keep the unclipped terms (legged_robot.py:263-267)
       S.rew = rew + term_rew;                                   // termination reward after the clip (legged_robot.py:268-272)
     }

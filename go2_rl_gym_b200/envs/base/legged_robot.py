@@ -62,8 +62,10 @@ class LeggedRobot:
         self.base_quat = self.root_states[:, 3:7]
         self.base_pos = self.root_states[:, 0:3]
         self.friction_coeffs = T["friction_coeffs"]
-        self.episode_sums = {n: T["episode_sums"][:, k] for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales}
-        self.episode_sums.update({n: T["xrew_sums"][:, k] for k, n in enumerate(_abi.XREWARD_NAMES) if n in A.reward_scales})
+        self.episode_sums = {n: T["episode_sums"][:, k] for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_names}
+        self.episode_sums.update({n: T["xrew_sums"][:, k] for k, n in enumerate(_abi.XREWARD_NAMES) if n in A.reward_names})
+        self.turn_over_timer = T["turn_over_timer"]          # legged_robot.py:833
+        self.reward_turn_over_scales = A.reward_turn_over_scales
         self.feet_air_time = T["xrew_state"][:, 0:4]            # state of the feet_air_time / base_height reward terms (legged_robot.py:817-818,1248-1251)
         self.last_contacts, self.last_contacts2 = T["xrew_state"][:, 4:8], T["xrew_state"][:, 8:12]
         self.env_command_ranges = {"lin_vel_x": T["env_command_ranges"][:, 0:2], "lin_vel_y": T["env_command_ranges"][:, 2:4],
@@ -99,9 +101,9 @@ class LeggedRobot:
         self.reward_curriculum_configs = list(cfg.rewards.curriculum_rewards or [])
         self.reward_curriculum_scales = {c["reward_name"]: c["start_value"] for c in self.reward_curriculum_configs}
         self.zero_command_proba = 0.0
-        self._ep_names = ["rew_" + n for n in _abi.REWARD_NAMES if n in A.reward_scales]
-        self._ep_cols = [k for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_scales]
-        self._xep = [("rew_" + n, k) for k, n in enumerate(_abi.XREWARD_NAMES) if n in A.reward_scales]
+        self._ep_names = ["rew_" + n for n in _abi.REWARD_NAMES if n in A.reward_names]
+        self._ep_cols = [k for k, n in enumerate(_abi.REWARD_NAMES) if n in A.reward_names]
+        self._xep = [("rew_" + n, k) for k, n in enumerate(_abi.XREWARD_NAMES) if n in A.reward_names]
         self._xrew_stats = T["xrew_log"][_abi.NUM_XREW:].view(torch.float32).view(EP_SLOTS, _abi.NUM_XREW)   # rows behind the 14 int64 accumulators
         # ---- library handle
         h = ctypes.c_void_p()

@@ -60,8 +60,16 @@ class EnvArrays:
         if unknown:      # the reference fails the same way: getattr(self, '_reward_' + name), legged_robot.py:936
             raise AttributeError(f"no reward function for {unknown}: the kernel holds {_abi.REWARD_NAMES + _abi.XREWARD_NAMES}")
         self.reward_scales = {k: v * self.dt for k, v in active.items()}
+        # init_state.turn_over: a second scale set used while the robot lies flipped (legged_robot.py:257-265,922-930)
+        self.turn_over = bool(cfg.init_state.turn_over)
+        to = {k: v for k, v in class_to_dict(cfg.rewards.turn_over_scales).items() if v != 0} if self.turn_over else {}
+        unknown = sorted(set(to) - set(_abi.REWARD_NAMES) - set(_abi.XREWARD_NAMES))
+        if unknown:
+            raise AttributeError(f"no reward function for {unknown} (rewards.turn_over_scales)")
+        self.reward_turn_over_scales = {k: v * self.dt for k, v in to.items()}
         # the terms outside the 14 every registered go2 task uses (legged_robot.py:1236-1441, go2_env.py:62-68): evaluated only when switched on
-        self.xreward_names = [n for n in _abi.XREWARD_NAMES if n in active]
+        self.xreward_names = [n for n in _abi.XREWARD_NAMES if n in active or n in to]
+        self.reward_names = [n for n in _abi.REWARD_NAMES + _abi.XREWARD_NAMES if n in active or n in to]
         self.reward_curriculum_configs = list(cfg.rewards.curriculum_rewards or [])
 
         # ---- terrain
@@ -147,6 +155,7 @@ class EnvArrays:
         T["body_inertia"] = torch.from_numpy(inertia).to(dev)
         z("xrew_sums", N, _abi.NUM_XREW); z("xrew_state", N, 12)               # extra reward terms (Go2EnvConfig.ext_xrew_*)
         z("xrew_log", _abi.XREW_LOG_BYTES // 8, dtype=torch.int64)
+        z("turn_over_timer", N)                                                  # init_state.turn_over (Go2EnvConfig.ext_turn_over_timer)
         z("ep_stats", EP_SLOTS, _abi.EP_STATS)
         z("ep_accum", _abi.EP_ACCUM_FLOATS)
         T["projected_gravity"][:, 2] = -1.0
@@ -202,8 +211,23 @@ class EnvArrays:
         c.move_down_by_accumulated_xy_command = int(cfg.terrain.move_down_by_accumulated_xy_command)
         c.custom_origins = int(self.custom_origins)
         cm = cfg.commands
-        if cfg.init_state.turn_over or cm.curriculum:
-            raise NotImplementedError("turn_over / commands.curriculum are outside the hot path (SURVEY 8f-3)")
+        if cm.curriculum:      # vestigial in this fork: it rewrites command_ranges["lin_vel_x"], which the sampler no longer reads
+            raise NotImplementedError("commands.curriculum is not built (SURVEY 8f-3, DESIGN.md section 6)")
+        c.turn_over = int(self.turn_over)
+        if self.turn_over:     # legged_robot.py:642-691,585-590; go2_config.py:23-30,125-128
+            ini = cfg.init_state
+            pr = [float(x) for x in ini.turn_over_proportions]
+            c.turn_over_proportions[0], c.turn_over_proportions[1], c.turn_over_proportions[2] = pr[0], pr[0] + pr[1], pr[0] + pr[1] + pr[2]   # cumulative, formed in double
+            for dst, key in ((c.turn_over_back_height, "backflip"), (c.turn_over_side_height, "sideflip")):
+                lo, hi = ini.turn_over_init_heights[key]
+                dst[0], dst[1] = lo, hi - lo                                       # {lower, span in double} like torch_rand_float
+            c.turn_over_zero_time_back, c.turn_over_zero_time_side = cm.turn_over_zero_time["backflip"], cm.turn_over_zero_time["sideflip"]
+            c.turn_over_roll_threshold = cfg.rewards.turn_over_roll_threshold
+            for k, name in enumerate(_abi.REWARD_NAMES):
+                c.to_scales[k] = self.reward_turn_over_scales.get(name, 0.0)
+            for k, name in enumerate(_abi.XREWARD_NAMES):
+                c.to_xscales[k] = self.reward_turn_over_scales.get(name, 0.0)
+        c.ext_turn_over_timer_lo, c.ext_turn_over_timer_hi = T["turn_over_timer"].data_ptr() & 0xFFFFFFFF, T["turn_over_timer"].data_ptr() >> 32
         # heading commands (legged_robot.py:411-419)
         c.heading_command, c.stop_heading_at_limit = int(bool(cm.heading_command)), int(bool(getattr(cm, "stop_heading_at_limit", False)))
         for name, key in (("ext_stop_heading", "stop_heading"), ("ext_heading_ranges", "heading_ranges")):       # addresses as 32-bit halves (go2_b200.h)

@@ -497,8 +497,8 @@ static void resample_commands(const Go2EnvConfig& C, const Go2EnvBuffers& B, con
   B.commands_resampling_step[e] = C.resampling_time / C.dt;
   const bool heading = C.heading_command != 0;
   const float* hr = heading ? GO2_EXT_PTR(const float*, &C, ext_heading_ranges) + (size_t)e * 2 : nullptr;
-  uint8_t* stop_heading = heading ? GO2_EXT_PTR(uint8_t*, &C, ext_stop_heading) : nullptr;
-  if (heading) stop_heading[e] = 0;                               // legged_robot.py:431
+  uint8_t* stop_heading = (heading || C.turn_over) ? GO2_EXT_PTR(uint8_t*, &C, ext_stop_heading) : nullptr;
+  if (stop_heading) stop_heading[e] = 0;                          // legged_robot.py:431
   if (C.dynamic_resample_commands) {
     float vlow = std::max(remaining / ((max_len - ep_len + 1e-9f) * C.dt), 0.0f);
     for (int a = 0; a < 2; ++a) {  // sample_disjoint_intervals, isaacgym_utils.py:32-47
@@ -552,6 +552,10 @@ static void resample_commands(const Go2EnvConfig& C, const Go2EnvBuffers& B, con
         if (heading) stop_heading[e] = 1;                          // :581-582
       }
     }
+  }
+  if (C.turn_over && GO2_EXT_PTR(const float*, &C, ext_turn_over_timer)[e] > 0) {   // turn-over zero-command time, legged_robot.py:585-590
+    cmd[0] = 0; cmd[1] = 0; cmd[2] = 0;
+    if (stop_heading) stop_heading[e] = 1;
   }
   acc[0] += cmd[0]; acc[1] += cmd[1];
 }
@@ -617,6 +621,24 @@ static void reset_env(const Go2EnvConfig& C, const Go2Model& M, const Go2EnvBuff
   float yaw = (2 * 3.14159265358979323846f) * u01(s3.x) - 3.14159265358979323846f;
   for (int i = 0; i < 13; ++i) rs[i] = C.base_init_state[i];
   rs[3] = 0; rs[4] = 0; rs[5] = std::sin(yaw * 0.5f); rs[6] = std::cos(yaw * 0.5f);
+  if (C.turn_over) {   // legged_robot.py:642-691: flipped initial poses; the masks compare a float32 draw with cumulative proportions
+    float* tt = GO2_EXT_PTR(float*, &C, ext_turn_over_timer) + e;
+    *tt = 0;
+    float rp = u01(s5.z);
+    bool back = rp >= 0 && rp < C.turn_over_proportions[0], side = rp >= C.turn_over_proportions[0] && rp < C.turn_over_proportions[1];
+    bool none = rp >= C.turn_over_proportions[1] && rp < C.turn_over_proportions[2];
+    if (back || side) {
+      U4 s6 = philox4x32_10(ge, sp.common_step_counter, ST_RESET_STATE, 6, C.seed_lo, C.seed_hi);
+      const float PI_F = 3.14159265358979323846f;
+      float roll;
+      if (back) { rs[2] = C.turn_over_back_height[1] * u01(s6.x) + C.turn_over_back_height[0]; roll = PI_F; *tt = C.turn_over_zero_time_back; }
+      else { rs[2] = C.turn_over_side_height[1] * u01(s6.y) + C.turn_over_side_height[0]; roll = (u01(s5.w) < 0.5f) ? 0.5f * PI_F : -0.5f * PI_F; *tt = C.turn_over_zero_time_side; }
+      float cy = std::cos(yaw * 0.5f), sy = std::sin(yaw * 0.5f), cr = std::cos(roll * 0.5f), sr = std::sin(roll * 0.5f);   // quat_from_euler_xyz(roll, 0, yaw)
+      rs[6] = cy * cr; rs[3] = cy * sr; rs[4] = sy * sr; rs[5] = sy * cr;
+    } else if (!none) {
+      for (int i = 3; i < 7; ++i) rs[i] = C.base_init_state[i];
+    }
+  }
   for (int i = 0; i < 3; ++i) rs[i] += B.env_origins[(size_t)e * 3 + i];
   if (C.custom_origins) { rs[0] += 2 * u01(s3.y) - 1; rs[1] += 2 * u01(s3.z) - 1; }
   rs[7] = u01(s4.x) - 0.5f; rs[8] = u01(s4.y) - 0.5f; rs[9] = u01(s4.z) - 0.5f;
@@ -759,6 +781,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     float* rs = B.root_states + (size_t)e * 13;
     B.episode_length_buf[e] += 1;
     B.commands_resampling_step[e] -= 1;
+    if (C.turn_over) { float* tt = GO2_EXT_PTR(float*, &C, ext_turn_over_timer) + e; *tt = std::max(*tt - C.dt, 0.0f); }   // legged_robot.py:114-115
     real qr[4] = {rs[3], rs[4], rs[5], rs[6]}, o3[3];
     real lv[3] = {rs[7], rs[8], rs[9]}, av[3] = {rs[10], rs[11], rs[12]}, gv[3] = {0, 0, -1};
     float* blv = B.base_lin_vel + (size_t)e * 3; float* bav = B.base_ang_vel + (size_t)e * 3; float* pg = B.projected_gravity + (size_t)e * 3;
@@ -774,7 +797,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
     measure_heights(C, B, e);
     // check_termination, legged_robot.py:170-178
     const float* cf = B.contact_forces + (size_t)e * GO2_NUM_REPORT * 3;
-    bool term = std::sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.0f;
+    bool term = !C.turn_over && std::sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.0f;   // legged_robot.py:174-175
     bool tout = B.episode_length_buf[e] > C.max_episode_length;
     B.time_out_buf[e] = tout; B.reset_buf[e] = term || tout || bad[e];
     // compute_reward, legged_robot.py:247-274, terms in enum order
@@ -835,8 +858,13 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
       term_v[GO2_REW_FEET_REGULATION] = r;
     }
     float rew = 0;
+    bool need_to = false;   // legged_robot.py:257-265; roll of get_euler_xyz (isaacgym_utils.py:11-17)
+    if (C.turn_over) {
+      float qx = rs[3], qy = rs[4], qz = rs[5], qw = rs[6];
+      need_to = std::fabs(std::atan2(2.0f * (qw * qx + qy * qz), qw * qw - qx * qx - qy * qy + qz * qz)) > C.turn_over_roll_threshold;
+    }
     for (int k = 0; k < GO2_NUM_REW; ++k) {
-      float rk = term_v[k] * C.reward_scales[k] * sp.reward_curriculum[k];
+      float rk = term_v[k] * (need_to ? C.to_scales[k] : C.reward_scales[k]) * sp.reward_curriculum[k];
       rew += rk;
       B.episode_sums[(size_t)e * GO2_NUM_REW + k] += rk;
     }
@@ -846,13 +874,13 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
       // called by the reference (:920-938), so the stateful ones only advance when active
       float* xs = GO2_EXT_PTR(float*, &C, ext_xrew_sums) + (size_t)e * GO2_NUM_XREW;
       float* st = GO2_EXT_PTR(float*, &C, ext_xrew_state) + (size_t)e * 12;   // feet_air_time[4], last_contacts[4], last_contacts2[4]
-      const float* sc = C.xrew_scales;
+      const float* sc = C.xrew_scales; const float* tsc = C.to_xscales;
       float xv[GO2_NUM_XREW] = {0};
       const float* feet_f[4]; const float* feet_p[4]; bool contact[4];
       for (int l = 0; l < 4; ++l) { feet_f[l] = cf + (6 + 4 * l) * 3; feet_p[l] = B.feet_pos + ((size_t)e * 4 + l) * 3; contact[l] = feet_f[l][2] > 1.0f; }
       const float cmd_xy = std::sqrt(cmd[0] * cmd[0] + cmd[1] * cmd[1]);
       xv[GO2_XREW_ORIENTATION] = pg[0] * pg[0] + pg[1] * pg[1];                                    // :1236-1238
-      if (sc[GO2_XREW_BASE_HEIGHT] != 0) {                                                           // :1245-1259
+      if (sc[GO2_XREW_BASE_HEIGHT] != 0 || tsc[GO2_XREW_BASE_HEIGHT] != 0) {                                                           // :1245-1259
         float nfc = 0, fcp[3] = {0, 0, 0};
         for (int l = 0; l < 4; ++l) {
           bool filt = contact[l] || st[8 + l] != 0;
@@ -872,7 +900,7 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
       }
       xv[GO2_XREW_DOF_VEL] = s_qd; xv[GO2_XREW_DOF_VEL_LIMITS] = s_vl; xv[GO2_XREW_TORQUE_LIMITS] = s_tl; xv[GO2_XREW_SIMILAR_TO_DEFAULT] = s_def;
       xv[GO2_XREW_TERMINATION] = (B.reset_buf[e] && !B.time_out_buf[e]) ? 1.0f : 0.0f;               // :1281-1283
-      if (sc[GO2_XREW_FEET_AIR_TIME] != 0) {                                                          // :1347-1358
+      if (sc[GO2_XREW_FEET_AIR_TIME] != 0 || tsc[GO2_XREW_FEET_AIR_TIME] != 0) {                                                          // :1347-1358
         float r = 0;
         for (int l = 0; l < 4; ++l) {
           bool filt = contact[l] || st[4 + l] != 0;
@@ -902,11 +930,11 @@ int go2_oracle_step(const Go2EnvConfig* Cp, const Go2Model* Mp, const Go2EnvBuff
         float df = std::max(C.min_legs_distance - (ly[0] - ly[1]), 0.0f), dr = std::max(C.min_legs_distance - (ly[2] - ly[3]), 0.0f);
         xv[GO2_XREW_LEGS_DISTANCE] = df * df + dr * dr;
       }
-      if (sc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0)                                                  // go2_env.py:62-68
+      if (sc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0 || tsc[GO2_XREW_X_COMMAND_HIP_REGULAR] != 0)                                                  // go2_env.py:62-68
         xv[GO2_XREW_X_COMMAND_HIP_REGULAR] = (std::fabs(q[0] + q[3]) + std::fabs(q[6] + q[9])) * (std::fabs(cmd[0]) / std::sqrt(cmd[0] * cmd[0] + cmd[1] * cmd[1] + cmd[2] * cmd[2]));
       for (int k = 0; k < GO2_NUM_XREW; ++k) {
-        if (sc[k] == 0) continue;
-        float rk = xv[k] * sc[k] * sp.xrew_curriculum[k];
+        if (sc[k] == 0 && tsc[k] == 0) continue;
+        float rk = xv[k] * ((need_to && k != GO2_XREW_TERMINATION) ? tsc[k] : sc[k]) * sp.xrew_curriculum[k];
         if (k == GO2_XREW_TERMINATION) term_rew = rk; else rew += rk;
         xs[k] += rk;
       }

@@ -8,7 +8,8 @@ from go2_rl_gym_b200 import _abi
 STATE = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "last_last_actions", "last_dof_vel", "torques",
          "commands", "commands_resampling_step", "commands_xy_accumulation", "last_is_limit_vel", "episode_length_buf",
          "terrain_levels", "env_origins", "max_move_distance", "motor_strengths", "motor_zero_offsets",
-         "p_gains_multiplier", "d_gains_multiplier", "episode_sums", "contact_forces", "reset_buf", "time_out_buf"]
+         "p_gains_multiplier", "d_gains_multiplier", "episode_sums", "contact_forces", "reset_buf", "time_out_buf",
+         "stop_heading", "xrew_sums", "xrew_state", "turn_over_timer"]
 
 
 class CudaEnv:

@@ -106,6 +106,9 @@ def install_rng(draws, num_envs):
         elif line == 645:
             ids = _ids(fr.f_locals["env_ids"])
             u = draws.u(ids, ST_RESET_STATE, 3, 0).unsqueeze(1)
+        elif line in (661, 672):    # init_state.turn_over: initial heights of the robots reset on their back / side (draws of the flipped envs only)
+            ids = _ids(fr.f_locals["env_ids"][fr.f_locals["back_mask" if line == 661 else "side_mask"]])
+            u = draws.u(ids, ST_RESET_STATE, 6, 0 if line == 661 else 1).unsqueeze(1)
         elif line == 698:
             ids = _ids(fr.f_locals["env_ids"])
             u = torch.stack([draws.u(ids, ST_RESET_STATE, 3, 1), draws.u(ids, ST_RESET_STATE, 3, 2)], 1)
@@ -146,6 +149,10 @@ def install_rng(draws, num_envs):
                 return draws.u(_ids(fr.f_locals["env_ids"]), stream, 0, 2)
             if line == 509:
                 return draws.u(_ids(fr.f_locals["env_ids"]), stream, 0, 3)
+            if line == 654:     # turn_over: which flip (legged_robot.py:654)
+                return draws.u(_ids(fr.f_locals["env_ids"]), ST_RESET_STATE, 5, 2)
+            if line == 674:     # turn_over: which side (:674)
+                return draws.u(_ids(fr.f_locals["env_ids"][fr.f_locals["side_ids"]]), ST_RESET_STATE, 5, 3)
             if line == 571:
                 return draws.u(_ids(fr.f_locals["zero_env_ids"]), stream, 1, 1)
             if line == 575:
@@ -313,7 +320,7 @@ STATE_KEYS = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "l
               "commands", "commands_resampling_step", "commands_xy_accumulation", "last_is_limit_vel", "episode_length_buf",
               "terrain_levels", "env_origins", "max_move_distance", "motor_strengths", "motor_zero_offsets",
               "p_gains_multiplier", "d_gains_multiplier", "episode_sums", "friction_coeffs", "restitutions", "body_inertia",
-              "contact_forces", "xrew_sums", "xrew_state"]
+              "contact_forces", "xrew_sums", "xrew_state", "turn_over_timer"]
 OUT_KEYS = ["obs_buf", "privileged_obs_buf", "rew_buf", "reset_buf", "time_out_buf", "root_states", "dof_pos", "dof_vel", "torques",
             "commands", "commands_resampling_step", "commands_xy_accumulation", "last_is_limit_vel", "episode_length_buf",
             "terrain_levels", "env_origins", "max_move_distance", "motor_strengths", "motor_zero_offsets", "p_gains_multiplier",
@@ -345,6 +352,7 @@ def load_state_into_reference(r, A):
     for k, name in enumerate(_abi.XREWARD_NAMES):      # the reward terms outside the GO2 defaults, when the case switches them on
         if name in r.episode_sums:
             r.episode_sums[name].copy_(T["xrew_sums"][:, k])
+    r.turn_over_timer.copy_(T["turn_over_timer"])
     r.feet_air_time.copy_(T["xrew_state"][:, 0:4])
     r.last_contacts.copy_(T["xrew_state"][:, 4:8].bool())
     r.last_contacts2 = T["xrew_state"][:, 8:12].bool().clone()        # created lazily by _reward_base_height (legged_robot.py:1248-1249)
@@ -357,7 +365,7 @@ def _apply(cfg, overrides):
         parts = path.split(".")
         for p in parts[:-1]:
             node = getattr(node, p)
-        assert hasattr(node, parts[-1]) or parts[:-1] == ["rewards", "scales"], path      # reward scales may be added (the reference looks the function up by name)
+        assert hasattr(node, parts[-1]) or parts[:-1] in (["rewards", "scales"], ["rewards", "turn_over_scales"]), path      # reward scales may be added (the reference looks the function up by name)
         setattr(node, parts[-1], val)
 
 
@@ -438,6 +446,7 @@ def make_case(name, plane, N=48, K=6, seed=7, start_counter=24 * 700, control_ty
                "motor_zero_offsets": r.motor_zero_offsets, "p_gains_multiplier": r.p_gains_multiplier,
                "d_gains_multiplier": r.d_gains_multiplier,
                "episode_sums": torch.stack([r.episode_sums[n] for n in _abi.REWARD_NAMES], 1),
+               "turn_over_timer": r.turn_over_timer,
                "xrew_sums": torch.stack([r.episode_sums[n] if n in r.episode_sums else torch.zeros(N) for n in _abi.XREWARD_NAMES], 1),
                "xrew_state": torch.cat([r.feet_air_time, r.last_contacts.float(), getattr(r, "last_contacts2", torch.zeros(N, 4)).float()], 1),
                "base_lin_vel": r.base_lin_vel, "base_ang_vel": r.base_ang_vel, "projected_gravity": r.projected_gravity,
@@ -478,6 +487,11 @@ if __name__ == "__main__":
         ov.update({"rewards.max_contact_force": 20.0, "rewards.soft_dof_vel_limit": 0.1, "rewards.soft_torque_limit": 0.3, "rewards.min_legs_distance": 0.25,
                    "rewards.base_height_target": 0.3})
         make_case("xrew", plane=False, N=48, K=8, seed=21, overrides=ov)
+        # init_state.turn_over (legged_robot.py:114-115,174-175,257-265,585-590,642-691): flipped resets, no contact termination, the turn_over reward scales
+        # (an extra term, a default term and the default upright = 1) while |roll| > pi / 4, zero commands while the timer runs
+        to = {"init_state.turn_over": True, "init_state.turn_over_proportions": [0.3, 0.4, 0.3], "rewards.turn_over_scales.torques": -2e-4,
+              "rewards.turn_over_scales.dof_vel": -1e-3, "rewards.scales.orientation": -0.2, "env.episode_length_s": 0.3}
+        make_case("turn_over", plane=False, N=48, K=8, seed=23, overrides=to)
         make_case("xrew_pos", plane=True, N=32, K=5, seed=22, only_positive=True, overrides={k: v for k, v in ov.items() if "hip_regular" not in k})
         sys.exit(0)
     make_case("rough", plane=False)

@@ -83,3 +83,10 @@ ODD = {"domain_rand.randomize_action_delay": False, "domain_rand.randomize_motor
        "commands.dynamic_resample_commands": False, "env.episode_length_s": 2, "normalization.clip_observations": 5.0, "control.action_scale": 0.5}
 BARE = {"commands.zero_command_curriculum": None, "commands.limit_vel_prob": 0.0, "domain_rand.push_interval_s": 0.3, "rewards.soft_dof_pos_limit": 0.5,
         "rewards.base_height_target": 0.3, "rewards.tracking_sigma": 0.5, "normalization.clip_actions": 1.0}
+# the f-3 switches together (tests/test_emu_cpu.py, tests/test_gpu_v_env_configs.py): turn_over with short episodes (flipped resets every few steps, zero-command timers,
+# turn_over reward scales) and every reward function the registered tasks leave off (x_command_hip_regular excepted: 0 / 0 at zero commands)
+FLIP = {"init_state.turn_over": True, "init_state.turn_over_proportions": [0.3, 0.3, 0.4], "env.episode_length_s": 0.4, "rewards.turn_over_scales.torques": -2e-4,
+        "rewards.turn_over_scales.feet_air_time": 0.5, "rewards.scales.orientation": -0.2, "rewards.scales.base_height": -1.0, "rewards.scales.dof_vel": -1e-4,
+        "rewards.scales.termination": -2.0, "rewards.scales.dof_vel_limits": -0.5, "rewards.scales.torque_limits": -0.01, "rewards.scales.feet_air_time": 1.0,
+        "rewards.scales.stumble": -0.5, "rewards.scales.stand_still": -0.1, "rewards.scales.feet_contact_forces": -0.01, "rewards.scales.similar_to_default": -0.02,
+        "rewards.scales.legs_distance": -1.5, "rewards.soft_dof_vel_limit": 0.1, "rewards.soft_torque_limit": 0.3, "rewards.max_contact_force": 20.0}

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import load_case, compare_step, TOL, PLAY, ODD, BARE
+from golden_util import load_case, compare_step, TOL, PLAY, ODD, BARE, FLIP
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays
 from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
 from emu.emu import EmuEnv
@@ -24,7 +24,7 @@ def test_emulated_kernel_matches_reference_golden(name, packed):
 
 
 @pytest.mark.parametrize("packed", [False, True, 14])
-@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "cmdcur", "xrew", "xrew_pos"])
+@pytest.mark.parametrize("name", ["ctrl_v_pos", "ctrl_t", "heading", "cmdcur", "xrew", "xrew_pos", "turn_over"])
 def test_emulated_kernel_matches_reference_golden_with_env_switches(name, packed):
     """control_type 'V' / 'T', only_positive_rewards, heading commands, the 14 reward functions no registered task switches on and the command-range curriculum boundary:
     every recorded step of the reference-made fixture, state re-synchronised to the fixture between steps."""
@@ -359,7 +359,7 @@ def test_heading_mode_with_stop_flags_kernel_source_equals_oracle(packed):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("name,overrides", [("play", PLAY), ("odd", ODD), ("bare", BARE)])
+@pytest.mark.parametrize("name,overrides", [("play", PLAY), ("odd", ODD), ("bare", BARE), ("flip", FLIP)])
 def test_emulated_kernel_tracks_oracle_off_the_training_defaults(name, overrides, packed):
     """The kernel's branches for configurations other than GO2 training: legged_gym/scripts/play.py's evaluation set-up (7 x 7 terrain without
     curriculum, noise / pushes / most randomisation off) and two mixes of the remaining switches (single-interval command sampling, no dynamic
@@ -371,7 +371,7 @@ def test_emulated_kernel_tracks_oracle_off_the_training_defaults(name, overrides
         node, parts = cfg, path.split(".")
         for p in parts[:-1]:
             node = getattr(node, p)
-        assert hasattr(node, parts[-1]), path
+        assert hasattr(node, parts[-1]) or parts[1] in ("scales", "turn_over_scales"), path
         setattr(node, parts[-1], val)
     Ac, Ae = EnvArrays(cfg, "cpu", seed=17), EnvArrays(cfg, "cpu", seed=17)
     orc, env = OracleEnv(Ac), EmuEnv(Ae, packed=packed)
@@ -386,12 +386,14 @@ def test_emulated_kernel_tracks_oracle_off_the_training_defaults(name, overrides
         orc.step(a); env.step(a)
         for k in ("reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel"):
             assert torch.equal(Ac.tensors[k], Ae.tensors[k]), (name, step, k)
-        for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums"):
+        for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums", "xrew_sums", "xrew_state", "turn_over_timer"):
             rtol, atol = TOL.get(k, TOL["default"])
             assert np.allclose(Ae.tensors[k].numpy(), Ac.tensors[k].numpy(), rtol=rtol, atol=atol), (name, step, k)
         n_reset += int(Ac.tensors["reset_buf"].sum())
         copy_state(Ac.tensors, Ae.tensors)
     assert n_reset > 0
+    if name == "flip":
+        assert float(Ac.tensors["turn_over_timer"].max()) > 0 and float(Ac.tensors["xrew_sums"].abs().max()) > 0
 
 
 @pytest.mark.parametrize("kind", ["oracle", "emu"])

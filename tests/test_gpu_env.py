@@ -42,7 +42,7 @@ def _cmp(Tg, Tc, loose=1.0):
 TOL_V = dict(TOL, dof_vel=(1e-3, 0.1), last_dof_vel=(1e-3, 0.1), torques=(1e-3, 0.1), privileged_obs_buf=(1e-3, 1e-2), obs_buf=(1e-3, 1e-2))
 
 
-@pytest.mark.parametrize("name", ["rough", "plane", "cmdcur", "ctrl_v_pos", "ctrl_t", "heading", "xrew", "xrew_pos"])
+@pytest.mark.parametrize("name", ["rough", "plane", "cmdcur", "ctrl_v_pos", "ctrl_t", "heading", "xrew", "xrew_pos", "turn_over"])
 def test_cuda_replays_reference_golden(name):
     """EVERY recorded step of each fixture made by the REFERENCE's own Python (run over the oracle physics): GO2 defaults on rough terrain and on the
     plane, the command-range curriculum boundary at learning iteration 20 000 (legged_robot.py:433-446), control types 'V' / 'T' with

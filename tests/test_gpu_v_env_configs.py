@@ -8,12 +8,12 @@ import torch
 
 from go2_rl_gym_b200.envs.env_arrays import EnvArrays
 from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
-from golden_util import BARE, ODD, PLAY, TOL
+from golden_util import BARE, FLIP, ODD, PLAY, TOL
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,overrides", [("play", PLAY), ("odd", ODD), ("bare", BARE)])
+@pytest.mark.parametrize("name,overrides", [("play", PLAY), ("odd", ODD), ("bare", BARE), ("flip", FLIP)])
 def test_cuda_tracks_oracle_off_the_training_defaults(name, overrides):
     from cuda_util import CudaEnv, copy_state
     from oracle.oracle import OracleEnv
@@ -37,7 +37,7 @@ def test_cuda_tracks_oracle_off_the_training_defaults(name, overrides):
         orc.step(a); env.step(a)
         for k in ("reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel"):
             assert torch.equal(Ac.tensors[k], Ag.tensors[k].cpu()), (name, step, k)
-        for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums"):
+        for k in ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums", "xrew_sums", "turn_over_timer"):
             rtol, atol = TOL.get(k, TOL["default"])
             assert np.allclose(Ag.tensors[k].cpu().numpy(), Ac.tensors[k].numpy(), rtol=rtol, atol=atol), (name, step, k)
         n_reset += int(Ac.tensors["reset_buf"].sum())
