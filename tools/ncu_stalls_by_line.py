@@ -38,7 +38,7 @@ for r in body:       # join on the offset inside the kernel; instructions nvdisa
 ins = joined
 ci = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "(Not Issued)" not in h]
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "go2_rl_gym_b200", "csrc", "env_step_core.cuh")).read().splitlines()
+src = open(os.environ.get("GO2_STALL_SRC") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "go2_rl_gym_b200", "csrc", "env_step_core.cuh")).read().splitlines()   # GO2_STALL_SRC: the source of the build the report was taken from
 def region(line):
     for k in range(line - 1, -1, -1):
         s = src[k]
