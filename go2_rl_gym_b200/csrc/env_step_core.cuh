@@ -60,6 +60,18 @@
 #define GO2_NV_OK(vh) ((vh) < L.nv)
 #endif
 #define GO2_WIDE GO2_EACH if (T::ROLE != 2 && L.own) GO2_UNROLL for (int vh = 0; vh < T::NV; ++vh) if (GO2_NV_OK(vh)) GO2_BIND(L.w, GO2_VLANE(vh))
+// the same for the phases that run ONCE per step (post-physics, store, reset) with the loop over the virtual lanes kept ROLLED (-DGO2_COLD_ROLLED=1).
+// That code is cold in the instruction cache every time it runs, so one copy instead of two looked attractive; measured on the B200 (round 2,
+// 4096 envs): 13.3 k instead of 14.1 k SASS instructions (most second-lane copies are pruned anyway: the lane ranges are compile-time), 107.3 us
+// against 106.6 us unrolled — the rolled loop serialises the two lanes' loads.  Default: unrolled.
+#if !defined(GO2_COLD_ROLLED)
+#define GO2_COLD_ROLLED 0
+#endif
+#if defined(__CUDACC__) && GO2_COLD_ROLLED
+#define GO2_WIDE_COLD GO2_EACH if (T::ROLE != 2 && L.own) _Pragma("unroll 1") for (int vh = 0; vh < T::NV; ++vh) GO2_BIND(L.w, GO2_VLANE(vh))
+#else
+#define GO2_WIDE_COLD GO2_WIDE
+#endif
 // items i = lane, lane + 32, ... < n of a WIDE block as a FIXED-trip unrolled loop with a predicate: the loads of all trips are in flight together
 // (a `for (i = lane; i < n; i += 32)` loop has a lane-dependent trip count, is not unrolled, and serialises one memory round trip per trip)
 #define GO2_STRIDED(i, n) GO2_UNROLL for (int k_ = 0; k_ < ((n) + 31) / 32; ++k_) if (const int i = lane + 32 * k_; i < (n))
@@ -948,7 +960,7 @@ template <class T>
 GO2_HD void state_guard(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvConfig* C = X.cs;
   const Go2EnvConfig* CT = X.cfg; (void)CT;
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane == 0) {
       int bad = 0;
       if (C->state_guard) {
@@ -971,7 +983,7 @@ GO2_HD void state_guard(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
 template <class T>
 GO2_HD void feet_kinematics(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2Model* M = X.mdl;
-  GO2_WIDE {   // lanes 0..3 of the env's own warp: once per step, between WIDE phases (no CTA barrier on either side)
+  GO2_WIDE_COLD {   // lanes 0..3 of the env's own warp: once per step, between WIDE phases (no CTA barrier on either side)
     if (lane < 4) {
       M3 Rw = quat_to_mat(S.root[3], S.root[4], S.root[5], S.root[6]);
       V3 pw = ld3(S.root);
@@ -1197,7 +1209,7 @@ GO2_HD void reset_phases(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X, 
   const Go2EnvConfig* CT = X.cfg; (void)CT;
   const Go2EnvBuffers* B = X.buf;
   const Go2StepParams* sp = X.sp;
-  GO2_WIDE if (initial || S.reset) {   // only the envs of the group that reset
+  GO2_WIDE_COLD if (initial || S.reset) {   // only the envs of the group that reset
     const uint32_t ge = (uint32_t)(C->env_offset + e);
     if (lane < GO2_NUM_DOF) {
       const size_t o = (size_t)e * GO2_NUM_DOF + lane;
@@ -1383,7 +1395,7 @@ GO2_HD void load_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
 template <class T>
 GO2_HD void store_state(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   const Go2EnvBuffers* B = X.buf;
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane < 13) B->root_states[(size_t)e * 13 + lane] = S.root[lane];
     if (lane < GO2_NUM_DOF) {
       const size_t o = (size_t)e * GO2_NUM_DOF + lane;
@@ -1448,7 +1460,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   state_guard<T>(GO2_LANE_PASS, SM, X); GO2_TICK();
   feet_kinematics<T>(GO2_LANE_PASS, SM, X); GO2_TICK();
   // ---- post_physics_step (legged_robot.py:102-142)
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     // height scan (legged_robot.py:1188-1224, math.py:8-12): yaw-only rotation of the body-frame grid
     if (C->mesh_type == 0) {
       GO2_STRIDED(i, GO2_NUM_HEIGHT) S.heights[i] = 0;
@@ -1484,7 +1496,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       if (C->heading_command && !S.stop_heading) heading_to_yaw(S);
     }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     {
       float sh = 0;
       GO2_STRIDED(i, GO2_NUM_HEIGHT) sh += S.heights[i] * CT->base_height_mask[i];
@@ -1509,7 +1521,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.coll[lane - 16] = (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
     }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane == 0) {
       float sh = 0;
       for (int k = 0; k < 32; ++k) sh += S.part[k];
@@ -1521,7 +1533,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.reset |= S.bad;
     }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane < 4) {  // feet_regulation per foot, legged_robot.py:1404-1414
       const float* fp = S.feet[lane];
       float f2b = (fp[0] - S.root[0]) * S.pg[0] + (fp[1] - S.root[1]) * S.pg[1] + (fp[2] - S.root[2]) * S.pg[2];
@@ -1529,7 +1541,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.fterm[lane] = (fp[3] * fp[3] + fp[4] * fp[4]) * expf(-fh / (0.025f * C->base_height_target));
     }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane == 0) {
       float tv[GO2_NUM_REW];
       float ds_on = (C->terrain_curriculum && C->dynamic_sigma && C->mesh_type != 0) ? 1.0f : 0.0f;
@@ -1576,13 +1588,13 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.rew = rew + term_rew;                                   // termination reward after the clip (legged_robot.py:268-272)
     }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane < GO2_NUM_REW) B->episode_sums[(size_t)e * GO2_NUM_REW + lane] += S.termv[lane];
     if (lane == 31) B->rew_buf[e] = S.rew;
   } GO2_SYNC_WARP(); GO2_TICK();
   if (GO2_ANY_RESET(SM)) reset_phases<T>(GO2_LANE_PASS, SM, X, false);
   GO2_TICK();   // warp-uniform (WIDE phases only); items are predicated by their env
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane == 0) {
       if (C->push_robots && (S.ep_len % C->push_interval == 0)) {  // _push_robots, legged_robot.py:709-724
         const uint32_t ge = (uint32_t)(C->env_offset + e);
@@ -1600,7 +1612,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
   } GO2_SYNC_WARP(); GO2_TICK();
   // ---- compute_observations (go2_env.py:23-53) + clip (legged_robot.py:96-99).  The 76 proprioceptive columns are first written to
   // shared memory by the lanes that own their sources (no divergent 12-way branch per column), then rows leave coalesced.
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane < GO2_NUM_DOF) {
       S.obsrow[12 + lane] = (S.q[lane] - L.ddp) * C->obs_scale_dof_pos;
       S.obsrow[24 + lane] = S.qd[lane] * C->obs_scale_dof_vel;
@@ -1618,7 +1630,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
       S.obsrow[48 + lane - 18] = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) * 1e-3f;
     }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
 #pragma unroll
     for (int k = 0; k < (GO2_NUM_PRIV + 31) / 32; ++k) {
       const int i = lane + 32 * k;
@@ -1639,7 +1651,7 @@ GO2_HD void step_env(GO2_LANE_ARGS, typename T::Smem* SM, const StepCtx& X) {
     GO2_STRIDED(i, GO2_NUM_HEIGHT) B->measured_heights[(size_t)e * GO2_NUM_HEIGHT + i] = S.heights[i];
     if (lane < 3) { B->base_lin_vel[(size_t)e * 3 + lane] = S.blv[lane]; B->base_ang_vel[(size_t)e * 3 + lane] = S.bav[lane]; B->projected_gravity[(size_t)e * 3 + lane] = S.pg[lane]; }
   } GO2_SYNC_WARP(); GO2_TICK();
-  GO2_WIDE {
+  GO2_WIDE_COLD {
     if (lane < GO2_NUM_DOF) { S.lact[lane] = S.act[lane]; S.lqd[lane] = S.qd[lane]; }
   } GO2_SYNC_WARP(); GO2_TICK();
   store_state<T>(GO2_LANE_PASS, SM, X); GO2_TICK();

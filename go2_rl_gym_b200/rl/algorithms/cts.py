@@ -16,6 +16,8 @@ from ..storage.rollout_storage_cts import RolloutStorageCTS
 from .ppo import adam_group_template
 
 
+_CRITIC_JOIN_EARLY = os.environ.get("GO2_CRITIC_JOIN", "late") == "early"
+
 class CTS:
     def __init__(self, model, num_envs, history_length, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
                  value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, student_encoder_learning_rate=1e-3, max_grad_norm=1.0,
@@ -130,7 +132,10 @@ class CTS:
                 values_out.copy_(self._val[:M])
         m.actor_engine.forward(self._xa, self._xa.shape[1], M, self._mu[:M], m.num_actions, train=train, x_ones=ones)
         if values_out is not None:
-            self._join_pending = True
+            if _CRITIC_JOIN_EARLY:           # A/B: the critic rejoins before the env step (it then only runs beside the actor and the sampling)
+                sd.join()
+            else:
+                self._join_pending = True
         else:
             sd.join()
 

@@ -23,6 +23,8 @@ def adam_group_template():
     return g
 
 
+_CRITIC_JOIN_EARLY = os.environ.get("GO2_CRITIC_JOIN", "late") == "early"
+
 class PPO:
     actor_critic: ActorCritic
 
@@ -128,7 +130,10 @@ class PPO:
             _ops.call("go2_sample_actions", _ops.ptr(mu), _ops.ptr(ac.std.data), _ops.ptr(st.actions[t]), _ops.ptr(st.actions_log_prob[t]),
                       _ops.ptr(st.mu[t]), _ops.ptr(st.sigma[t]), N, A, self.seed, self._act_step, self.env_offset)
         if self._dev_steps is not None:
-            self._join_pending = True        # joined in process_env_step
+            if _CRITIC_JOIN_EARLY:           # A/B: the critic rejoins before the env step (it then only runs beside the actor and the sampling)
+                sd.join()
+            else:
+                self._join_pending = True        # joined in process_env_step
         else:
             sd.join()
         self.transition.actions = st.actions[t]
