@@ -23,26 +23,31 @@ from oracle.oracle import OracleEnv  # noqa: E402
 from fuzz_reference_parity import SWITCHES  # noqa: E402
 
 EXACT = ("reset_buf", "time_out_buf", "episode_length_buf", "terrain_levels", "last_is_limit_vel", "stop_heading")
-FLOATS = ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums", "torques")
+FLOATS = ("obs_buf", "privileged_obs_buf", "rew_buf", "root_states", "dof_pos", "dof_vel", "commands", "episode_sums", "torques", "xrew_sums", "xrew_state",
+          "turn_over_timer")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="0:40")
     ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--f3", action="store_true", help="also draw the reward functions outside the GO2 defaults and init_state.turn_over (fuzz_reference_parity.f3_overrides)")
     args = ap.parse_args()
     lo, hi = (int(x) for x in args.seeds.split(":"))
     n_bad = 0
     for seed in range(lo, hi):
         rng = np.random.default_rng(seed)
         N = int(rng.integers(9, 90))
-        packed = [False, True, 4][int(rng.integers(0, 3))]
+        packed = [False, True, 4, 14][int(rng.integers(0, 4))]
         cfg = GO2Cfg(); cfg.env.num_envs = N; cfg.seed = seed
         cfg.terrain.mesh_type = "plane" if rng.integers(0, 4) == 0 else "heightfield"
         ov = {}
         for path, vals in SWITCHES.items():
             if rng.integers(0, 3) == 0:
                 ov[path] = vals[int(rng.integers(0, len(vals)))]
+        if args.f3:
+            from fuzz_reference_parity import f3_overrides
+            ov.update(f3_overrides(rng))
         for path, val in ov.items():
             node, parts = cfg, path.split(".")
             for p in parts[:-1]:

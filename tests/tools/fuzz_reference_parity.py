@@ -30,12 +30,37 @@ SWITCHES = {
 }
 
 
+# SURVEY 8f-3 switches of round 2: the reward functions the registered tasks leave off (random subsets, random signs / sizes) and init_state.turn_over
+XREW = {"orientation": -0.2, "base_height": -1.0, "dof_vel": -1e-4, "termination": -2.0, "dof_vel_limits": -0.5, "torque_limits": -0.01, "feet_air_time": 1.0,
+        "stumble": -0.5, "stand_still": -0.1, "feet_contact_forces": -0.01, "similar_to_default": -0.02, "upright": 0.3, "legs_distance": -1.5}
+
+
+def f3_overrides(rng):
+    ov = {}
+    for k, v in XREW.items():
+        if rng.integers(0, 2):
+            ov["rewards.scales." + k] = float(v * rng.uniform(0.3, 3.0))
+    ov.update({"rewards.max_contact_force": float(rng.uniform(5, 150)), "rewards.soft_dof_vel_limit": float(rng.uniform(0.05, 1.0)),
+               "rewards.soft_torque_limit": float(rng.uniform(0.1, 1.0)), "rewards.min_legs_distance": float(rng.uniform(0.05, 0.4))})
+    if rng.integers(0, 2):
+        p = rng.dirichlet([1, 1, 1])
+        ov.update({"init_state.turn_over": True, "init_state.turn_over_proportions": [float(p[0]), float(p[1]), float(1.0 - p[0] - p[1])],
+                   "env.episode_length_s": float(rng.choice([0.2, 0.5, 20])), "rewards.turn_over_roll_threshold": float(rng.uniform(0.3, 1.5))})
+        for k in ("torques", "dof_vel", "feet_air_time", "orientation", "action_rate"):
+            if rng.integers(0, 3) == 0:
+                ov["rewards.turn_over_scales." + k] = float(rng.uniform(-1, 1) * 1e-2)
+    if rng.integers(0, 3) == 0:
+        ov["rewards.only_positive_rewards"] = True
+    return ov
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="20:30")
     ap.add_argument("--N", type=int, default=64)
     ap.add_argument("--K", type=int, default=8)
     ap.add_argument("--switches", action="store_true", help="also flip config switches away from the GO2 defaults on both sides")
+    ap.add_argument("--f3", action="store_true", help="random subsets of the 13 extra reward functions (x_command_hip_regular excepted: 0 / 0) and init_state.turn_over")
     ap.add_argument("--relaxed", action="store_true", help="oracle physics with the relaxed contact solver + state guard (the second library build's settings)")
     ap.add_argument("--control_types", action="store_true", help="also draw control_type V / T (violent: the first contact solver can diverge to NaN there, and V control amplifies rounding; expect tolerance-level mismatches)")
     args = ap.parse_args()
@@ -61,7 +86,18 @@ def main():
             for path, vals in SWITCHES.items():
                 if rng.integers(0, 3) == 0:
                     ov[path] = vals[int(rng.integers(0, len(vals)))]
-        H.make_case(name, plane=plane, N=N, K=args.K, seed=seed, start_counter=start, control_type=ctrl, heading=heading, overrides=ov,
+        if args.f3:
+            ov.update(f3_overrides(rng))
+            if ov.get("init_state.turn_over"):   # the reference's heading clip raises as soon as one env holds its heading (legged_robot.py:415-419),
+                heading = False                  # which the turn-over zero-command time does at once
+            if ov.pop("rewards.only_positive_rewards", False):
+                ctrl = ctrl                      # (the positive clip is a make_case argument)
+                only_pos = True
+            else:
+                only_pos = False
+        else:
+            only_pos = False
+        H.make_case(name, plane=plane, N=N, K=args.K, seed=seed, start_counter=start, control_type=ctrl, only_positive=only_pos, heading=heading, overrides=ov,
                     b200=dict(limit_relax=0.5, contact_relax=0.7, limit_erp=0.8, state_guard=1) if args.relaxed else None)
         z, A = GU.load_case(name)
         O = OracleEnv(A)
