@@ -108,7 +108,10 @@ step_kernel_quad(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restric
 // instantiation carries only its own per-thread state and instruction stream.
 constexpr int HALF_WARPS = GO2_HALF_ENVS / 2 + 2;
 typedef WarpSmemT<7> HalfSmem;
-__global__ void __launch_bounds__(32 * HALF_WARPS, 2)
+#if !defined(GO2_HALF_MINB)
+#define GO2_HALF_MINB 2      /* CTAs per SM the register allocation aims at (1: tuning experiment, up to 224 registers) */
+#endif
+__global__ void __launch_bounds__(32 * HALF_WARPS, GO2_HALF_MINB)
 step_kernel_half(const Go2EnvConfig* __restrict__ cfg, const Go2Model* __restrict__ mdl, const __grid_constant__ Go2EnvBuffers buf,
                  const Go2StepParams* __restrict__ sp, const float* __restrict__ actions, const __grid_constant__ Go2EnvConfig cfgv) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
