@@ -59,20 +59,27 @@ class OnPolicyRunner:
         self._done_len = torch.full((self.num_steps_per_env, N), float("nan"), device=self.device)
         self._rollout_graphs = _ops.GraphSet()
 
-    # ---- rollout (on_policy_runner.py:136-153) -----------------------------------------------------------------------------
+    # ---- rollout (on_policy_runner.py:136-153; on_policy_runner_cts.py:147-170) ----------------------------------------------
+    # The loop is shared with OnPolicyRunnerCTS, which overrides the two hooks: how the policy is fed and what happens between the env step and the
+    # transition bookkeeping (the observation history of the CTS family).
+    def _policy_act(self, obs, priv):
+        return self.alg.act(obs, priv if priv is not None else obs)
+
+    def _after_env_step(self, obs, dones):
+        pass
+
     def _rollout_steps(self, log, dev):
         """The num_steps_per_env act -> step -> process_env_step loop.  dev: step parameters / sampling counters are device-resident
         (begin_rollout), so the launch sequence depends on nothing the host computes per step and can be captured in one CUDA graph."""
         env, alg = self.env, self.alg
         obs, priv = env.get_observations(), env.get_privileged_observations()
-        cobs = priv if priv is not None else obs
         nan = float("nan")
         ep_infos = []
         alg.storage.step = 0
         for i in range(self.num_steps_per_env):
-            actions = alg.act(obs, cobs)
+            actions = self._policy_act(obs, priv)
             obs, priv, rewards, dones, infos = env.step_dev(actions, i) if dev else env.step(actions)
-            cobs = priv if priv is not None else obs
+            self._after_env_step(obs, dones)
             alg.process_env_step(rewards, dones, infos)
             if log:
                 if not dev and 'episode' in infos:

@@ -57,47 +57,16 @@ class OnPolicyRunnerCTS:
         d8 = None if dones is None else (dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8))
         _ops.call("go2_history_update", _ops.ptr(self.history), _ops.ptr(obs), _ops.ptr(d8), self.env.num_envs, self.history_length, self.env.num_obs)
 
-    # ---- rollout (on_policy_runner_cts.py:147-170) -------------------------------------------------------------------------
-    def _rollout_steps(self, log, dev):
-        """act -> step -> history roll -> process_env_step, num_steps_per_env times.  dev: device-resident step parameters / sampling
-        counters (begin_rollout), i.e. a launch sequence that can be captured in one CUDA graph."""
-        env, alg = self.env, self.alg
-        obs, priv = env.get_observations(), env.get_privileged_observations()
-        nan = float("nan")
-        ep_infos = []
-        alg.storage.step = 0
-        for i in range(self.num_steps_per_env):
-            actions = alg.act(obs, priv, self.history.flatten(1))
-            obs, priv, rewards, dones, infos = env.step_dev(actions, i) if dev else env.step(actions)
-            self._roll_history(obs, dones)
-            alg.process_env_step(rewards, dones, infos)
-            if log:
-                if not dev and 'episode' in infos:
-                    ep_infos.append((infos['episode'], infos.get('episode_valid')))
-                self._cur_reward_sum += rewards
-                self._cur_episode_length += 1
-                self._done_rew[i] = torch.where(dones, self._cur_reward_sum, nan)
-                self._done_len[i] = torch.where(dones, self._cur_episode_length, nan)
-                self._cur_reward_sum *= ~dones
-                self._cur_episode_length *= ~dones
-        return ep_infos
+    # ---- rollout (on_policy_runner_cts.py:147-170): OnPolicyRunner's loop with the history in the policy input and the history roll between the env
+    # step and the transition bookkeeping; replayed as one CUDA graph by the shared collect()
+    def _policy_act(self, obs, priv):
+        return self.alg.act(obs, priv, self.history.flatten(1))
 
-    def collect(self, log=False):
-        """One rollout, replayed as a single CUDA graph when possible (see OnPolicyRunner.collect)."""
-        env, alg, T = self.env, self.alg, self.num_steps_per_env
-        with torch.inference_mode():
-            if self._rollout_graphs.enabled and hasattr(env, "begin_rollout") and env.begin_rollout(T):
-                alg.begin_rollout(T)
-                try:
-                    self._rollout_graphs.run(("rollout", bool(log)), lambda: self._rollout_steps(log, True))
-                finally:
-                    alg.end_rollout(T)
-                return env.end_rollout(fetch=bool(log))      # un-logged: no device -> host read at the end of the rollout
-            ep_infos = self._rollout_steps(log, False)
-            # eager steps serve extras["episode"] without a host sync; rows from before the env's first reset are dropped here, once per rollout
-            flags = [v for _, v in ep_infos if v is not None]
-            keep = torch.stack(flags).cpu().tolist() if flags else []
-            return [e for (e, v), k in zip(ep_infos, keep or [1.0] * len(ep_infos)) if k > 0]
+    def _after_env_step(self, obs, dones):
+        self._roll_history(obs, dones)
+
+    _rollout_steps = OnPolicyRunner._rollout_steps
+    collect = OnPolicyRunner.collect
 
     # host-buffer rollout: same loop as OnPolicyRunner.collect_host (history in the policy input, history roll before the bookkeeping)
     collect_host = OnPolicyRunner.collect_host
