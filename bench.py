@@ -314,18 +314,26 @@ def _main(out):
             runner._roll_history(obs, dones)
 
     def rollout_eager_timed():
+        """the rollout launched step by step (no graph) through the device-parameter entry point the graph replays (go2_env_step_dev): the events
+        bracket exactly the step kernel + its finalize kernel, no host -> device parameter copy in between"""
         obs, priv = env.get_observations(), env.get_privileged_observations()
         alg.storage.step = 0
         with torch.inference_mode():
-            for _ in range(STEPS_PER_ENV):
+            dev_params = env.begin_rollout(STEPS_PER_ENV)
+            if dev_params:
+                alg.begin_rollout(STEPS_PER_ENV)
+            for i in range(STEPS_PER_ENV):
                 a = act(obs, priv)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                obs, priv, rew, dones, infos = env.step(a)
+                obs, priv, rew, dones, infos = env.step_dev(a, i) if dev_params else env.step(a)
                 e1.record()
                 step_ev.append((e0, e1))
                 after_step(obs, dones)
                 alg.process_env_step(rew, dones, infos)
+            if dev_params:
+                alg.end_rollout(STEPS_PER_ENV)
+                env.end_rollout(fetch=False)
     for _ in range(2):
         rollout_eager_timed()
     sync()
