@@ -139,6 +139,10 @@ def load_library(path=None):
     lib.go2_env_step_dev.restype = C.c_int
     lib.go2_env_step_host.argtypes = [vp, vp, C.POINTER(Go2StepParams), vp, vp, vp, vp, vp]
     lib.go2_env_step_host.restype = C.c_int
+    lib.go2_env_step_host_begin.argtypes = [vp, vp, C.POINTER(Go2StepParams), vp, vp, vp, vp, vp]
+    lib.go2_env_step_host_begin.restype = C.c_int
+    lib.go2_env_step_host_end.argtypes = [vp]
+    lib.go2_env_step_host_end.restype = C.c_int
     lib.go2_env_reset_all.argtypes = [vp, C.POINTER(Go2StepParams), vp]
     lib.go2_env_reset_all.restype = C.c_int
     lib.go2_env_substeps.argtypes = [vp, vp, C.c_int, vp]

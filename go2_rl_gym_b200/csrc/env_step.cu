@@ -195,6 +195,9 @@ struct Go2Env {
   float* d_actions = nullptr;     // staging for the host-buffer entry point
   float* d_id_counts = nullptr;
   Go2StepParams* d_sp = nullptr;  // staging slot of the host-parameter entry points (the kernels read the step parameters from device memory)
+  cudaStream_t copy_stream = nullptr;   // device -> host copies of go2_env_step_host_begin
+  cudaEvent_t ev_step = nullptr, ev_copied = nullptr;
+  bool host_pending = false;
   int grid = 0;
   int step_mode = 8;              // thread map of the step kernel, see go2_env_set_step_mode
 };
@@ -308,6 +311,9 @@ int go2_env_set_step_mode(Go2Env* h, const char* mode) {
 void go2_env_destroy(Go2Env* h) {
   if (!h) return;
   cudaFree(h->d_cfg); cudaFree(h->d_mdl); cudaFree(h->d_actions); cudaFree(h->d_id_counts); cudaFree(h->d_sp);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_step) cudaEventDestroy(h->ev_step);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
   delete h;
 }
 
@@ -320,6 +326,7 @@ int go2_env_step(Go2Env* h, const float* actions, const Go2StepParams* sp, void*
 
 int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, void* stream) {
   if (!h || !actions || !sp) return go2::set_error(1, "go2_env_step_dev: null argument");
+  if (h->host_pending) return go2::set_error(1, "go2_env_step: a host step opened by go2_env_step_host_begin is still pending (go2_env_step_host_end)");
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = h->step_mode;
   if (mode == 0) go2::step_kernel<<<h->grid, 32 * go2::WARPS_PER_CTA, 0, st>>>(h->d_cfg, h->d_mdl, h->buf, sp, actions);
@@ -336,20 +343,44 @@ int go2_env_step_dev(Go2Env* h, const float* actions, const Go2StepParams* sp, v
   return 0;
 }
 
-int go2_env_step_host(Go2Env* h, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv, float* h_rew,
-                      uint8_t* h_reset, void* stream) {
+int go2_env_step_host_begin(Go2Env* h, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv, float* h_rew,
+                            uint8_t* h_reset, void* stream) {
   if (!h || !h_actions || !sp) return go2::set_error(1, "go2_env_step_host: null argument");
+  if (h->host_pending) return go2::set_error(1, "go2_env_step_host_begin: the previous host step has not been closed by go2_env_step_host_end");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t N = (size_t)h->cfg.num_envs;
+  if (!h->copy_stream) {
+    GO2_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    GO2_CUDA_OK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
+    GO2_CUDA_OK(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+  }
   GO2_CUDA_OK(cudaMemcpyAsync(h->d_actions, h_actions, sizeof(float) * GO2_NUM_DOF * N, cudaMemcpyHostToDevice, st));
   int rc = go2_env_step(h, h->d_actions, sp, stream);
   if (rc) return rc;
-  if (h_obs) GO2_CUDA_OK(cudaMemcpyAsync(h_obs, h->buf.obs_buf, sizeof(float) * GO2_NUM_OBS * N, cudaMemcpyDeviceToHost, st));
-  if (h_priv) GO2_CUDA_OK(cudaMemcpyAsync(h_priv, h->buf.privileged_obs_buf, sizeof(float) * GO2_NUM_PRIV * N, cudaMemcpyDeviceToHost, st));
-  if (h_rew) GO2_CUDA_OK(cudaMemcpyAsync(h_rew, h->buf.rew_buf, sizeof(float) * N, cudaMemcpyDeviceToHost, st));
-  if (h_reset) GO2_CUDA_OK(cudaMemcpyAsync(h_reset, h->buf.reset_buf, N, cudaMemcpyDeviceToHost, st));
-  GO2_CUDA_OK(cudaStreamSynchronize(st));
+  // the copies leave on the library's copy stream once the step has run: work the caller enqueues on `stream` after this call overlaps them
+  GO2_CUDA_OK(cudaEventRecord(h->ev_step, st));
+  GO2_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_step, 0));
+  if (h_rew) GO2_CUDA_OK(cudaMemcpyAsync(h_rew, h->buf.rew_buf, sizeof(float) * N, cudaMemcpyDeviceToHost, h->copy_stream));
+  if (h_reset) GO2_CUDA_OK(cudaMemcpyAsync(h_reset, h->buf.reset_buf, N, cudaMemcpyDeviceToHost, h->copy_stream));
+  if (h_obs) GO2_CUDA_OK(cudaMemcpyAsync(h_obs, h->buf.obs_buf, sizeof(float) * GO2_NUM_OBS * N, cudaMemcpyDeviceToHost, h->copy_stream));
+  if (h_priv) GO2_CUDA_OK(cudaMemcpyAsync(h_priv, h->buf.privileged_obs_buf, sizeof(float) * GO2_NUM_PRIV * N, cudaMemcpyDeviceToHost, h->copy_stream));
+  GO2_CUDA_OK(cudaEventRecord(h->ev_copied, h->copy_stream));
+  h->host_pending = true;
   return 0;
+}
+
+int go2_env_step_host_end(Go2Env* h) {
+  if (!h) return go2::set_error(1, "go2_env_step_host_end: null argument");
+  if (!h->host_pending) return 0;
+  h->host_pending = false;
+  GO2_CUDA_OK(cudaEventSynchronize(h->ev_copied));
+  return 0;
+}
+
+int go2_env_step_host(Go2Env* h, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv, float* h_rew,
+                      uint8_t* h_reset, void* stream) {
+  int rc = go2_env_step_host_begin(h, h_actions, sp, h_obs, h_priv, h_rew, h_reset, stream);
+  return rc ? rc : go2_env_step_host_end(h);
 }
 
 int go2_env_reset_all(Go2Env* h, const Go2StepParams* sp, void* stream) {

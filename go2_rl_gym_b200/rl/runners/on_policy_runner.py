@@ -111,10 +111,12 @@ class OnPolicyRunner:
             return [e for (e, v), k in zip(ep_infos, keep or [1.0] * len(ep_infos)) if k > 0]
 
     def collect_host(self, h_actions, h_obs, h_priv, h_rew, h_reset):
-        """One rollout with the env reached through its HOST-buffer entry point (`go2_env_step_host`, the call an external simulator loop or a
-        logging host would make): every step copies the sampled actions into the pinned host tensor `h_actions`, the C call uploads them, steps and
-        downloads observations / privileged observations / rewards / resets into the other four host tensors.  The policy inference + sampling in
-        front of the call and the transition bookkeeping behind it are replayed as per-step CUDA graphs."""
+        """One rollout with the env reached through its HOST-buffer entry point (`go2_env_step_host_begin / _end`, the calls an external simulator loop
+        or a logging host would make): every step copies the sampled actions into the pinned host tensor `h_actions`, the C call uploads them, steps
+        and downloads observations / privileged observations / rewards / resets into the other four host tensors.  The policy inference + sampling in
+        front of the call and the transition bookkeeping behind it are replayed as per-step CUDA graphs; the download of step t (5 MB at 4096 envs)
+        runs on the library's copy stream beside that bookkeeping and the next inference, and is complete — the host buffers hold step t — before
+        the actions of step t + 1 go up."""
         env, alg, T = self.env, self.alg, self.num_steps_per_env
         if not hasattr(self, "_host_graphs"):
             self._host_graphs = _ops.GraphSet()
@@ -124,9 +126,11 @@ class OnPolicyRunner:
                 alg.storage.step = t
                 self._host_graphs.run(("act", t), lambda: self._host_act(t))
                 h_actions.copy_(self._host_actions(t))            # D2H of the policy output (synchronises)
-                env.step_host(h_actions.numpy(), h_obs.numpy(), h_priv.numpy(), h_rew.numpy(), h_reset.numpy())
+                env.step_host_end()                               # step t - 1 is on the host (no-op at t = 0)
+                env.step_host_begin(h_actions.numpy(), h_obs.numpy(), h_priv.numpy(), h_rew.numpy(), h_reset.numpy())
                 alg.storage.step = t
                 self._host_graphs.run(("proc", t), self._host_proc)
+            env.step_host_end()
             alg.end_rollout(T)
 
     def _host_act(self, t):

@@ -225,7 +225,7 @@ typedef struct Go2Env Go2Env;
 /* Replaces gym.create_sim/prepare_sim + acquire_*_tensor (legged_robot.py:292-310,769-787). 0 on success. */
 int go2_env_create(const Go2EnvConfig* cfg, const Go2Model* model, const Go2EnvBuffers* bufs, Go2Env** out);
 void go2_env_destroy(Go2Env* env);
-/* Thread map of the fused step kernel: "P2" (default; 8 envs packed per CTA), "P3", "Q4" (4 envs packed per CTA), "8p", "4" (warp per env).
+/* Thread map of the fused step kernel: "H14" (default; 14 envs per 9-warp CTA on half-warps, dedicated leg warps), "P2" (8 envs packed per CTA), "P3", "Q4" (4 envs packed per CTA), "8p", "4" (warp per env).
  * Same results (bit for bit in the host emulation; each map is its own kernel instantiation on the GPU). */
 int go2_env_set_step_mode(Go2Env* env, const char* mode);
 /* Replaces LeggedRobot.step (legged_robot.py:60-100): the fused kernel. actions: device [N,12]. */
@@ -236,6 +236,15 @@ int go2_env_step_dev(Go2Env* env, const float* actions, const Go2StepParams* d_s
 /* Same, HOST buffers: H2D of actions, kernel, D2H of obs/priv/rew/reset inside the call (bench e2e). */
 int go2_env_step_host(Go2Env* env, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv,
                       float* h_rew, uint8_t* h_reset, void* cuda_stream);
+
+/* The host-buffer step in two halves, for a caller that has device work of its own to enqueue between a step and the next one (the runner's transition
+   bookkeeping and the next policy inference): _begin uploads the actions, launches the step on `stream` and starts the device -> host copies on the
+   library's own copy stream; it returns without waiting.  _end blocks until the four host buffers of that step are filled.  Every _begin must be closed
+   by one _end before the next _begin / any other step call on the handle (the next step overwrites the device buffers the copies read); between the two
+   calls work enqueued on `stream` may READ the env's device buffers.  go2_env_step_host == _begin + _end. */
+int go2_env_step_host_begin(Go2Env* env, const float* h_actions, const Go2StepParams* sp, float* h_obs, float* h_priv,
+                            float* h_rew, uint8_t* h_reset, void* stream);
+int go2_env_step_host_end(Go2Env* env);
 /* Replaces reset_idx(arange(N)) at construction (base_task.py:82-86 calls reset_idx then a zero-action step). */
 int go2_env_reset_all(Go2Env* env, const Go2StepParams* sp, void* cuda_stream);
 /* n bare physics substeps under given joint torques tau [N,12] (parity tests of the dynamics in isolation). */

@@ -197,6 +197,20 @@ def test_step_host_entry_point_equals_device_entry_point():
     sp = A1.step_params(e1.common_step_counter + 1)
     _abi.check(e1.lib.go2_env_step_host(e1.h, a.data_ptr(), C.byref(sp), None, None, h_rew.data_ptr(), None, None), e1.lib)
     assert e1.lib.go2_env_step_host(e1.h, None, C.byref(sp), None, None, None, None, None) != 0
+    # the split form: _begin returns without waiting, device work enqueued meanwhile may read the env buffers, _end delivers the host buffers;
+    # a second _begin (or any other step) before _end is refused
+    hp = [t.pin_memory() for t in (h_obs, h_priv, h_rew, h_reset)]
+    ap = a.pin_memory()
+    sp = A1.step_params(e1.common_step_counter + 2)
+    _abi.check(e1.lib.go2_env_step_host_begin(e1.h, ap.data_ptr(), C.byref(sp), hp[0].data_ptr(), hp[1].data_ptr(), hp[2].data_ptr(), hp[3].data_ptr(), None), e1.lib)
+    busy = A1.tensors["privileged_obs_buf"].clone() * 2.0            # reads the env's buffers beside the copies
+    assert e1.lib.go2_env_step_host_begin(e1.h, ap.data_ptr(), C.byref(sp), None, None, None, None, None) != 0
+    assert e1.lib.go2_env_step(e1.h, A1.tensors["actions"].data_ptr(), C.byref(sp), None) != 0
+    _abi.check(e1.lib.go2_env_step_host_end(e1.h), e1.lib)
+    for host, key in zip(hp, ("obs_buf", "privileged_obs_buf", "rew_buf", "reset_buf")):
+        assert torch.equal(host, A1.tensors[key].cpu()), key
+    assert torch.equal(busy.cpu(), 2.0 * hp[1])
+    _abi.check(e1.lib.go2_env_step_host_end(e1.h), e1.lib)          # idempotent
 
 
 def test_state_guard_contains_a_diverged_env_on_the_gpu():
