@@ -341,14 +341,14 @@ def _main(out):
     peaks, peak_kind = _peaks()
     achieved = ALGO_BYTES_PER_ENV_STEP * N / (kern_ms * 1e-3) / 1e9
 
-    # ---- e2e: the same iteration with the env reached through its HOST-buffer C-ABI call (go2_env_step_host): every step uploads the
+    # ---- e2e: the same iteration with the env reached through its HOST-buffer C-ABI calls (go2_env_step_host_begin / _end): every step uploads the
     # actions from pinned host memory and reads observations / privileged observations / rewards / resets back
     h_act = torch.empty(N, 12).pin_memory()
     h_obs, h_priv, h_rew = torch.empty(N, 45).pin_memory(), torch.empty(N, 263).pin_memory(), torch.empty(N).pin_memory()
     h_reset = torch.empty(N, dtype=torch.uint8).pin_memory()
 
     def iteration_host():
-        """the runner's own host-buffer iteration (rl/runners: run_iteration_host -> collect_host -> env.step_host = go2_env_step_host)"""
+        """the runner's own host-buffer iteration (rl/runners: run_iteration_host -> collect_host -> env.step_host_begin / _end = go2_env_step_host_begin / _end)"""
         return runner.run_iteration_host(h_act, h_obs, h_priv, h_rew, h_reset)
 
     for _ in range(2):                                                        # eager pass, then the pass that captures the per-step graphs
