@@ -166,6 +166,148 @@ __global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const int64_t*
   if (i < n) out[i] = src[perm[i]];
 }
 
+// ================================================================================================ grouped expert layer (fp32, CUDA cores)
+// Conv1d(E*H -> E*D, kernel 1, groups = E) (rsl_rl/modules/utils.py:83-88) = E block-diagonal Linear(H -> D) over the feature blocks of the backbone.
+// Each expert is a [M, H] x [H, D] product with D ~ 32: eight tensor-core launches of a few tiles each were pure launch latency (12 us apiece in the
+// rollout).  ONE launch per direction for all experts, exact fp32 FMAs (sequential over the contraction index inside a thread):
+//   forward  Y[m, e D + d]  = b[e D + d] + sum_h X[m, e H + h] W[e D + d, h]
+//   dgrad    dX[m, e H + h] = ELU'(act[m, e H + h]) sum_d dY[m, e D + d] W[e D + d, h]          (act = the backbone's last activation, may be null)
+//   wgrad    dW[e D + d, h] = sum_m dY[m, e D + d] X[m, e H + h]     partials over row chunks, summed in chunk order by a second kernel (deterministic)
+constexpr int GX_BM = 64, GX_BK = 32, GX_BD = 32;
+
+__global__ void __launch_bounds__(256) grouped_fwd_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ W, const float* __restrict__ b,
+                                                          float* __restrict__ Y, long ldy, long M, int E, int D, int H) {
+  __shared__ float Xs[GX_BM][GX_BK + 1], Ws[GX_BD][GX_BK + 1];
+  const int e = blockIdx.y / ((D + GX_BD - 1) / GX_BD), d0 = (blockIdx.y % ((D + GX_BD - 1) / GX_BD)) * GX_BD;
+  const long m0 = (long)blockIdx.x * GX_BM;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // thread -> rows ty * 4 .. + 3, columns tx * 2, tx * 2 + 1
+  float acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  for (int k0 = 0; k0 < H; k0 += GX_BK) {
+    for (int i = threadIdx.x; i < GX_BM * GX_BK; i += 256) {
+      const int r = i / GX_BK, k = i % GX_BK;
+      Xs[r][k] = (m0 + r < M && k0 + k < H) ? X[(m0 + r) * ldx + (long)e * H + k0 + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < GX_BD * GX_BK; i += 256) {
+      const int d = i / GX_BK, k = i % GX_BK;
+      Ws[d][k] = (d0 + d < D && k0 + k < H) ? W[((long)e * D + d0 + d) * H + k0 + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < GX_BK; ++k) {
+      const float w0 = Ws[tx * 2][k], w1 = Ws[tx * 2 + 1][k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float x = Xs[ty * 4 + r][k];
+        acc[r][0] = fmaf(x, w0, acc[r][0]); acc[r][1] = fmaf(x, w1, acc[r][1]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const long m = m0 + ty * 4 + r; const int d = d0 + tx * 2 + c;
+      if (m < M && d < D) Y[m * ldy + (long)e * D + d] = acc[r][c] + b[e * D + d];
+    }
+}
+
+// dX tile: 64 rows x 64 feature columns of one expert; contraction over D in chunks of 32
+__global__ void __launch_bounds__(256) grouped_dgrad_kernel(const float* __restrict__ dY, long lddy, const float* __restrict__ W, const float* __restrict__ act,
+                                                            long ldact, float* __restrict__ dX, long lddx, long M, int E, int D, int H) {
+  __shared__ float Gs[GX_BM][GX_BD + 1], Ws[GX_BD][64 + 1];
+  const int hb = (H + 63) / 64, e = blockIdx.y / hb, h0 = (blockIdx.y % hb) * 64;
+  const long m0 = (long)blockIdx.x * GX_BM;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // rows ty * 4 .. + 3, columns tx + 16 c (c = 0..3)
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+  for (int d0 = 0; d0 < D; d0 += GX_BD) {
+    for (int i = threadIdx.x; i < GX_BM * GX_BD; i += 256) {
+      const int r = i / GX_BD, d = i % GX_BD;
+      Gs[r][d] = (m0 + r < M && d0 + d < D) ? dY[(m0 + r) * lddy + (long)e * D + d0 + d] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < GX_BD * 64; i += 256) {
+      const int d = i / 64, h = i % 64;
+      Ws[d][h] = (d0 + d < D && h0 + h < H) ? W[((long)e * D + d0 + d) * H + h0 + h] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int d = 0; d < GX_BD; ++d) {
+      float w[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) w[c] = Ws[d][tx + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float g = Gs[ty * 4 + r][d];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(g, w[c], acc[r][c]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long m = m0 + ty * 4 + r; const int h = h0 + tx + 16 * c;
+      if (m < M && h < H) {
+        float v = acc[r][c];
+        if (act) { const float y = act[m * ldact + (long)e * H + h]; v *= (y > 0.0f ? 1.0f : y + 1.0f); }
+        dX[m * lddx + (long)e * H + h] = v;
+      }
+    }
+}
+
+// partial weight gradients: block (chunk, e, h-block of 64): part[chunk][e D + d][h] = sum over the chunk's rows; D <= 32 per pass (grid z = d-block)
+constexpr int GX_ROWS = 256;     // rows per chunk
+__global__ void __launch_bounds__(256) grouped_wgrad_partial_kernel(const float* __restrict__ dY, long lddy, const float* __restrict__ X, long ldx,
+                                                                    float* __restrict__ part, long M, int E, int D, int H) {
+  __shared__ float Gs[32][GX_BD + 1], Xs[32][64 + 1];
+  const int hb = (H + 63) / 64, e = blockIdx.y / hb, h0 = (blockIdx.y % hb) * 64, d0 = blockIdx.z * GX_BD;
+  const long r0 = (long)blockIdx.x * GX_ROWS, r1 = min(M, r0 + GX_ROWS);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // outputs d = ty * 2 + {0, 1}, h = tx + 16 c
+  float acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (long m0 = r0; m0 < r1; m0 += 32) {
+    for (int i = threadIdx.x; i < 32 * GX_BD; i += 256) {
+      const int r = i / GX_BD, d = i % GX_BD;
+      Gs[r][d] = (m0 + r < r1 && d0 + d < D) ? dY[(m0 + r) * lddy + (long)e * D + d0 + d] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int r = i / 64, h = i % 64;
+      Xs[r][h] = (m0 + r < r1 && h0 + h < H) ? X[(m0 + r) * ldx + (long)e * H + h0 + h] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float g0 = Gs[r][ty * 2], g1 = Gs[r][ty * 2 + 1];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float x = Xs[r][tx + 16 * c];
+        acc[0][c] = fmaf(g0, x, acc[0][c]); acc[1][c] = fmaf(g1, x, acc[1][c]);
+      }
+    }
+    __syncthreads();
+  }
+  float* P = part + (long)blockIdx.x * E * D * H;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int d = d0 + ty * 2 + j, h = h0 + tx + 16 * c;
+      if (d < D && h < H) P[((long)e * D + d) * H + h] = acc[j][c];
+    }
+}
+__global__ void grouped_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int chunks, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int c = 0; c < chunks; ++c) s += part[(long)c * n + i];      // chunk order: deterministic
+  dW[i] = s;
+}
+
 }  // namespace go2
 
 using namespace go2;
@@ -250,6 +392,40 @@ int go2_history_update(float* history, const float* obs, const uint8_t* dones, l
 }
 int go2_gather_u8(const uint8_t* src, const int64_t* perm, uint8_t* out, long n, void* stream) {
   gather_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, perm, out, n);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int go2_grouped_linear_forward(const float* X, long ldx, const float* W, const float* b, float* Y, long ldy, long M, int E, int D, int H, void* stream) {
+  if (!X || !W || !b || !Y || M <= 0 || E <= 0 || D <= 0 || H <= 0) return set_error(1, "go2_grouped_linear_forward: bad argument");
+  dim3 grid((unsigned)((M + GX_BM - 1) / GX_BM), (unsigned)(E * ((D + GX_BD - 1) / GX_BD)));
+  grouped_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, W, b, Y, ldy, M, E, D, H);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int go2_grouped_linear_dgrad(const float* dY, long lddy, const float* W, const float* act, long ldact, float* dX, long lddx, long M, int E, int D, int H,
+                             void* stream) {
+  if (!dY || !W || !dX || M <= 0 || E <= 0 || D <= 0 || H <= 0) return set_error(1, "go2_grouped_linear_dgrad: bad argument");
+  dim3 grid((unsigned)((M + GX_BM - 1) / GX_BM), (unsigned)(E * ((H + 63) / 64)));
+  grouped_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, lddy, W, act, ldact, dX, lddx, M, E, D, H);
+  count_launch();
+  GO2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+long go2_grouped_linear_wgrad_workspace(long M, int E, int D, int H) { return ((M + GX_ROWS - 1) / GX_ROWS) * (long)E * D * H; }
+int go2_grouped_linear_wgrad(const float* dY, long lddy, const float* X, long ldx, float* dW, long M, int E, int D, int H, float* workspace,
+                             long workspace_floats, void* stream) {
+  if (!dY || !X || !dW || !workspace || M <= 0 || E <= 0 || D <= 0 || H <= 0) return set_error(1, "go2_grouped_linear_wgrad: bad argument");
+  const int chunks = (int)((M + GX_ROWS - 1) / GX_ROWS);
+  const long n = (long)E * D * H;
+  if (workspace_floats < chunks * n) return set_error(1, "go2_grouped_linear_wgrad: workspace too small (go2_grouped_linear_wgrad_workspace)");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)chunks, (unsigned)(E * ((H + 63) / 64)), (unsigned)((D + GX_BD - 1) / GX_BD));
+  grouped_wgrad_partial_kernel<<<grid, 256, 0, st>>>(dY, lddy, X, ldx, workspace, M, E, D, H);
+  count_launch();
+  grouped_wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, dW, chunks, n);
   count_launch();
   GO2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -34,6 +34,9 @@ _SIGS = {
     "go2_concat2": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _l, _vp],
     "go2_l2norm_forward": [_vp, _i, _vp, _i, _vp, _l, _i, _vp],
     "go2_l2norm_backward": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _l, _i, _vp],
+    "go2_grouped_linear_forward": [_vp, _l, _vp, _vp, _vp, _l, _l, _i, _i, _i, _vp],
+    "go2_grouped_linear_dgrad": [_vp, _l, _vp, _vp, _l, _vp, _l, _l, _i, _i, _i, _vp],
+    "go2_grouped_linear_wgrad": [_vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _vp, _l, _vp],
     "go2_moe_combine_forward": [_vp, _vp, _vp, _vp, _l, _i, _i, _vp],
     "go2_moe_combine_backward": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _l, _i, _i, _vp],
     "go2_gate_usage": [_vp, _vp, _l, _i, _f, _vp],

@@ -5,6 +5,8 @@ Same constructor arguments and `state_dict` keys (teacher_encoder.*, student_enc
 actor.*, critic.*, std), parameters re-homed in ONE flat vector split into two contiguous optimiser segments:
   segment 1 (optimizer1, cts.py:72-79): teacher_encoder, critic, actor, std        segment 2 (optimizer2): the student encoder
 and every forward / backward evaluated by the library's kernels (GEMMs on tcgen05, the small pieces in csrc/cts_kernels.cu)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -549,11 +551,15 @@ class _ExpertLayer:
         self.gW = model._gviews[pname + ".weight"].view(E * D, H)
         self.gb = model._gviews[pname + ".bias"]
         self.small = D <= 16 and H <= 128
-        self.tc = _ops.use_tc() and not self.small and D % 4 == 0
+        # wider experts (the student encoder's 8 x (256 -> 32)): ONE grouped fp32 launch per direction for all experts (go2_grouped_linear_*);
+        # GO2_EXPERTS=tc keeps the earlier one-tensor-core-GEMM-per-expert path for A / B
+        self.grouped = not self.small and os.environ.get("GO2_EXPERTS", "grouped") == "grouped"
+        self.tc = _ops.use_tc() and not self.small and not self.grouped and D % 4 == 0
         self.out = torch.empty(max_rows, E * D, device=dev)
         self.dfeat = torch.empty(max(train_rows, 1), E * H, device=dev)
         self.Wt = torch.zeros(E * H, D, device=dev) if self.tc else None
         self.work = torch.empty(max(296 * (D * H + D), 64 * 128 * (H + 4), 64 * E * D), device=dev)
+        self.gwork = torch.empty(((max(train_rows, 1) + 255) // 256) * E * D * H, device=dev) if self.grouped else None   # go2_grouped_linear_wgrad_workspace
         self._dirty = True
 
     def mark_dirty(self):
@@ -561,6 +567,9 @@ class _ExpertLayer:
 
     def forward(self, feat, ldf, M):
         E, D, H = self.E, self.D, self.H
+        if self.grouped:
+            call("go2_grouped_linear_forward", ptr(feat), ldf, ptr(self.W), ptr(self.b), ptr(self.out), E * D, M, E, D, H)
+            return
         for e in range(E):
             x, w, b, y = ptr(feat) + 4 * e * H, ptr(self.W) + 4 * e * D * H, ptr(self.b) + 4 * e * D, ptr(self.out) + 4 * e * D
             if self.small:
@@ -579,6 +588,10 @@ class _ExpertLayer:
             self._dirty = False
         if not self.small:
             call("go2_colsum", ptr(dout), E * D, ptr(self.gb), M, E * D, ptr(self.work))
+        if self.grouped:
+            call("go2_grouped_linear_wgrad", ptr(dout), E * D, ptr(feat), ldf, ptr(self.gW), M, E, D, H, ptr(self.gwork), self.gwork.numel())
+            call("go2_grouped_linear_dgrad", ptr(dout), E * D, ptr(self.W), ptr(feat), ldf, ptr(self.dfeat), E * H, M, E, D, H)
+            return
         for e in range(E):
             d, x, gw = ptr(dout) + 4 * e * D, ptr(feat) + 4 * e * H, ptr(self.gW) + 4 * e * D * H
             df = ptr(self.dfeat) + 4 * e * H

@@ -359,6 +359,16 @@ int go2_concat2(const float* a, int wa, int lda, const float* b, int wb, int ldb
 int go2_l2norm_forward(const float* x, int ldx, float* y, int ldy, float* norm, long n, int d, void* stream);
 int go2_l2norm_backward(const float* dy, int lddy, const float* y, int ldy, const float* norm, float* dx, int lddx, float* dx_t, long n, int d, void* stream);
 /* softmax gate + weighted sum of the expert outputs (modules/utils.py:122-126) and its backward incl. the load-balance term (moe_cts.py:210-216) */
+/* Expert layer of the mixture modules = Conv1d(E*H -> E*D, kernel 1, groups = E) (rsl_rl/modules/utils.py:83-88): E block-diagonal Linear(H -> D) over the
+   backbone's feature blocks, all experts in ONE launch per direction (fp32 FMAs on the CUDA cores; W is [E*D, H] row-major, b [E*D]):
+   forward Y[m, eD+d] = b + sum_h X[m, eH+h] W[eD+d, h]; dgrad dX[m, eH+h] = ELU'(act[m, eH+h]) sum_d dY[m, eD+d] W[eD+d, h] (act may be null);
+   wgrad dW[eD+d, h] = sum_m dY[m, eD+d] X[m, eH+h], row chunks summed in a fixed order (workspace: go2_grouped_linear_wgrad_workspace floats). */
+int go2_grouped_linear_forward(const float* X, long ldx, const float* W, const float* b, float* Y, long ldy, long M, int E, int D, int H, void* stream);
+int go2_grouped_linear_dgrad(const float* dY, long lddy, const float* W, const float* act, long ldact, float* dX, long lddx, long M, int E, int D, int H,
+                             void* stream);
+long go2_grouped_linear_wgrad_workspace(long M, int E, int D, int H);
+int go2_grouped_linear_wgrad(const float* dY, long lddy, const float* X, long ldx, float* dW, long M, int E, int D, int H, float* workspace,
+                             long workspace_floats, void* stream);
 int go2_moe_combine_forward(const float* logits, const float* expert_out, float* gates, float* pre, long n, int E, int D, void* stream);
 int go2_moe_combine_backward(const float* dpre, const float* gates, const float* expert_out, float* usage, float lb_coef, float* dexpert_out,
                              float* dexpert_out_t, float* dlogits, float* dlogits_t, long n, int E, int D, void* stream);

@@ -444,6 +444,35 @@ def go2_l2norm_backward(dy, lddy, y, ldy, norm, dx, lddx, dx_t, n, d, stream):
     return 0
 
 
+def go2_grouped_linear_forward(X, ldx, W, b, Y, ldy, M, E, D, H, stream):
+    _need(X and W and b and Y and M > 0 and E > 0 and D > 0 and H > 0, "go2_grouped_linear_forward: bad argument")
+    x, y = _mat(X, M, E * H, ldx), _mat(Y, M, E * D, ldy)
+    w, bias = _mat(W, E * D, H, H), _vec(b, E * D)
+    for e in range(E):
+        y[:, e * D:(e + 1) * D] = (x[:, e * H:(e + 1) * H] @ w[e * D:(e + 1) * D].T + bias[e * D:(e + 1) * D]).astype(F)
+    return 0
+
+
+def go2_grouped_linear_dgrad(dY, lddy, W, act, ldact, dX, lddx, M, E, D, H, stream):
+    _need(dY and W and dX and M > 0 and E > 0 and D > 0 and H > 0, "go2_grouped_linear_dgrad: bad argument")
+    g, dx, w = _mat(dY, M, E * D, lddy), _mat(dX, M, E * H, lddx), _mat(W, E * D, H, H)
+    for e in range(E):
+        d = (g[:, e * D:(e + 1) * D] @ w[e * D:(e + 1) * D]).astype(F)
+        if act:
+            d = d * _elu_grad_from_out(_mat(act, M, E * H, ldact)[:, e * H:(e + 1) * H])
+        dx[:, e * H:(e + 1) * H] = d
+    return 0
+
+
+def go2_grouped_linear_wgrad(dY, lddy, X, ldx, dW, M, E, D, H, ws, wsn, stream):
+    _need(dY and X and dW and ws and M > 0 and E > 0 and D > 0 and H > 0, "go2_grouped_linear_wgrad: bad argument")
+    _need(wsn >= ((M + 255) // 256) * E * D * H, "go2_grouped_linear_wgrad: workspace too small (go2_grouped_linear_wgrad_workspace)")
+    g, x, dw = _mat(dY, M, E * D, lddy), _mat(X, M, E * H, ldx), _mat(dW, E * D, H, H)
+    for e in range(E):
+        dw[e * D:(e + 1) * D] = (g[:, e * D:(e + 1) * D].T @ x[:, e * H:(e + 1) * H]).astype(F)
+    return 0
+
+
 def go2_moe_combine_forward(logits, expert_out, gates, pre, n, E, D, stream):
     _need(E <= 16, "go2_moe_combine_forward: at most 16 experts")
     lg = _mat(logits, n, E, E)

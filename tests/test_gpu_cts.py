@@ -107,3 +107,43 @@ def test_cts_runner_two_iterations(task, tmp_path):
     policy = runner.get_inference_policy()
     a = policy(env.get_observations())
     assert a.shape == (256, 12) and torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("M,E,D,H", [(2048, 8, 32, 256), (12288, 8, 32, 256), (1000, 3, 20, 100), (77, 2, 40, 72)])
+def test_grouped_expert_layer_kernels_match_fp32_torch(M, E, D, H):
+    """go2_grouped_linear_forward / _dgrad / _wgrad (the expert layer = Conv1d(E*H -> E*D, groups = E), modules/utils.py:83-88, all experts in one launch)
+    against the grouped convolution itself in fp64 -> the kernels' fp32 FMAs agree to fp32 rounding; ragged sizes exercise every tile edge."""
+    import torch.nn.functional as Fn
+    from go2_rl_gym_b200.rl._ops import call, ptr
+    g = torch.Generator(device="cuda").manual_seed(M + E)
+    ldx, ldy = E * H + 4, E * D
+    X = torch.randn(M, ldx, device="cuda", generator=g)
+    W = torch.randn(E * D, H, device="cuda", generator=g) / H ** 0.5
+    b = torch.randn(E * D, device="cuda", generator=g)
+    Y = torch.full((M, ldy), float("nan"), device="cuda")
+    call("go2_grouped_linear_forward", ptr(X), ldx, ptr(W), ptr(b), ptr(Y), ldy, M, E, D, H)
+    ref = Fn.conv1d(X[:, :E * H].double().unsqueeze(-1), W.double().unsqueeze(-1), b.double(), groups=E).squeeze(-1)
+    assert torch.allclose(Y.double(), ref, rtol=1e-5, atol=1e-5), float((Y.double() - ref).abs().max())
+    # backward: dX = ELU'(act) * conv_transpose, dW = sum over rows
+    act = torch.nn.functional.elu(torch.randn(M, ldx, device="cuda", generator=g))
+    dY = torch.randn(M, ldy, device="cuda", generator=g)
+    dX = torch.full((M, E * H), float("nan"), device="cuda")
+    call("go2_grouped_linear_dgrad", ptr(dY), ldy, ptr(W), ptr(act), ldx, ptr(dX), E * H, M, E, D, H)
+    Wd = W.double().view(E, D, H)
+    dref = torch.einsum("med,edh->meh", dY.double().view(M, E, D), Wd).reshape(M, E * H)
+    a = act[:, :E * H].double()
+    dref = dref * torch.where(a > 0, torch.ones_like(a), a + 1.0)
+    assert torch.allclose(dX.double(), dref, rtol=1e-5, atol=1e-5), float((dX.double() - dref).abs().max())
+    dX2 = torch.empty_like(dX)
+    call("go2_grouped_linear_dgrad", ptr(dY), ldy, ptr(W), 0, 0, ptr(dX2), E * H, M, E, D, H)       # no activation
+    assert torch.allclose(dX2.double(), torch.einsum("med,edh->meh", dY.double().view(M, E, D), Wd).reshape(M, E * H), rtol=1e-5, atol=1e-5)
+    ws = torch.empty(((M + 255) // 256) * E * D * H, device="cuda")
+    dW = torch.full((E * D, H), float("nan"), device="cuda")
+    call("go2_grouped_linear_wgrad", ptr(dY), ldy, ptr(X), ldx, ptr(dW), M, E, D, H, ptr(ws), ws.numel())
+    wref = torch.einsum("med,meh->edh", dY.double().view(M, E, D), X[:, :E * H].double().view(M, E, H)).reshape(E * D, H)
+    assert torch.allclose(dW.double(), wref, rtol=1e-4, atol=1e-4 * M ** 0.5), float((dW.double() - wref).abs().max())
+    dW2 = torch.empty_like(dW)
+    call("go2_grouped_linear_wgrad", ptr(dY), ldy, ptr(X), ldx, ptr(dW2), M, E, D, H, ptr(ws), ws.numel())
+    assert torch.equal(dW, dW2)                                                                     # fixed summation order
+    with pytest.raises(RuntimeError):
+        call("go2_grouped_linear_wgrad", ptr(dY), ldy, ptr(X), ldx, ptr(dW2), M, E, D, H, ptr(ws), 16)
