@@ -231,15 +231,16 @@ class LeggedRobot:
         self.step_host_end()
 
     def step_host_begin(self, actions_np, obs_out, priv_out, rew_out, reset_out):
-        """First half of step_host: uploads the actions, launches the step and starts the device -> host copies on the library's copy stream, without
+        """(arguments: host torch tensors — pinned for asynchronous copies — or numpy arrays.)  First half of step_host: uploads the actions, launches the step and starts the device -> host copies on the library's copy stream, without
         waiting.  Device work enqueued before step_host_end() (the transition bookkeeping, the next policy inference) overlaps the copies; it may
         read the env's device buffers.  The host arrays are valid after step_host_end()."""
         self.common_step_counter += 1
         self.update_reward_curriculum()
         sp = self._A.step_params(self.common_step_counter, ep_slot=self.common_step_counter % EP_SLOTS,
                                  reward_curriculum=self.reward_curriculum_scales)
-        _abi.check(self._lib.go2_env_step_host_begin(self._h, actions_np.ctypes.data, ctypes.byref(sp), obs_out.ctypes.data,
-                                                     priv_out.ctypes.data, rew_out.ctypes.data, reset_out.ctypes.data, self._stream), self._lib)
+        p = lambda x: x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data      # host tensors (pinned) or numpy arrays
+        _abi.check(self._lib.go2_env_step_host_begin(self._h, p(actions_np), ctypes.byref(sp), p(obs_out), p(priv_out), p(rew_out), p(reset_out),
+                                                     self._stream), self._lib)
 
     def step_host_end(self):
         _abi.check(self._lib.go2_env_step_host_end(self._h), self._lib)

@@ -345,15 +345,23 @@ class EnvArrays:
         if changed:
             self.max_lin_vel = self._max_lin_vel()
             self._update_env_command_ranges()
-        sp = _abi.Go2StepParams()
-        sp.common_step_counter = int(common_step_counter) & 0xFFFFFFFF
         rc = reward_curriculum if reward_curriculum is not None else self.reward_curriculum_scales(common_step_counter)
-        for k, name in enumerate(_abi.REWARD_NAMES):
-            sp.reward_curriculum[k] = rc.get(name, 1.0)
-        for k, name in enumerate(_abi.XREWARD_NAMES):
-            sp.xrew_curriculum[k] = rc.get(name, 1.0)
-        zc = self.cfg.commands.zero_command_curriculum
-        sp.zero_command_proba = self._scale(zc, it) if zc is not None else 0.0
-        sp.max_lin_vel = self.max_lin_vel
+        # everything but the two counters depends on the iteration and the curriculum scales only: the block of the previous call is reused while they
+        # stand (the per-step host loops call this 24 times per iteration)
+        key = (it, tuple(rc.values()), self.max_lin_vel)
+        memo = getattr(self, "_sp_memo", None)
+        if memo is not None and memo[0] == key:
+            sp = _abi.Go2StepParams.from_buffer_copy(memo[1])
+        else:
+            sp = _abi.Go2StepParams()
+            for k, name in enumerate(_abi.REWARD_NAMES):
+                sp.reward_curriculum[k] = rc.get(name, 1.0)
+            for k, name in enumerate(_abi.XREWARD_NAMES):
+                sp.xrew_curriculum[k] = rc.get(name, 1.0)
+            zc = self.cfg.commands.zero_command_curriculum
+            sp.zero_command_proba = self._scale(zc, it) if zc is not None else 0.0
+            sp.max_lin_vel = self.max_lin_vel
+            self._sp_memo = (key, bytes(sp))
+        sp.common_step_counter = int(common_step_counter) & 0xFFFFFFFF
         sp.ep_slot = int(ep_slot)
         return sp

@@ -125,9 +125,10 @@ class OnPolicyRunner:
             for t in range(T):
                 alg.storage.step = t
                 self._host_graphs.run(("act", t), lambda: self._host_act(t))
-                h_actions.copy_(self._host_actions(t))            # D2H of the policy output (synchronises)
+                # the policy output goes to the pinned host tensor on the same stream the C call uploads it from: stream order, no host wait in between
+                h_actions.copy_(self._host_actions(t), non_blocking=True)
                 env.step_host_end()                               # step t - 1 is on the host (no-op at t = 0)
-                env.step_host_begin(h_actions.numpy(), h_obs.numpy(), h_priv.numpy(), h_rew.numpy(), h_reset.numpy())
+                env.step_host_begin(h_actions, h_obs, h_priv, h_rew, h_reset)
                 alg.storage.step = t
                 self._host_graphs.run(("proc", t), self._host_proc)
             env.step_host_end()
