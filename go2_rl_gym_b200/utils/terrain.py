@@ -147,6 +147,40 @@ def pit_terrain(t, depth, platform_size=1.0):  # terrain.py:190-197
     t.height_field_raw[x1:x2, y1:y2] = -d
 
 
+def convert_heightfield_to_trimesh(height_field_raw, horizontal_scale, vertical_scale, slope_threshold=None):
+    """isaacgym.terrain_utils.convert_heightfield_to_trimesh restated (Isaac Gym is absent: UNPINNED, written from its published algorithm): one vertex per
+    heightfield sample, two triangles per cell; where the slope between neighbouring samples exceeds slope_threshold the LOWER vertex is moved onto its
+    higher neighbour's xy, so that steep ramps become vertical walls (legged_gym/utils/terrain.py:45-49, `slope_treshold`).
+    Returns (vertices [rows * cols, 3] float32, triangles [2 (rows - 1) (cols - 1), 3] uint32).  The physics of this package collides against the sampled
+    heightfield; the mesh is provided for exporters / viewers, as `Terrain.vertices / .triangles` like the reference."""
+    hf = height_field_raw
+    num_rows, num_cols = hf.shape
+    y = np.linspace(0, (num_cols - 1) * horizontal_scale, num_cols)
+    x = np.linspace(0, (num_rows - 1) * horizontal_scale, num_rows)
+    yy, xx = np.meshgrid(y, x)
+    if slope_threshold is not None:
+        thr = slope_threshold * horizontal_scale / vertical_scale
+        move_x, move_y, move_c = (np.zeros((num_rows, num_cols)) for _ in range(3))
+        move_x[:num_rows - 1, :] += (hf[1:num_rows, :] - hf[:num_rows - 1, :] > thr)
+        move_x[1:num_rows, :] -= (hf[:num_rows - 1, :] - hf[1:num_rows, :] > thr)
+        move_y[:, :num_cols - 1] += (hf[:, 1:num_cols] - hf[:, :num_cols - 1] > thr)
+        move_y[:, 1:num_cols] -= (hf[:, :num_cols - 1] - hf[:, 1:num_cols] > thr)
+        move_c[:num_rows - 1, :num_cols - 1] += (hf[1:num_rows, 1:num_cols] - hf[:num_rows - 1, :num_cols - 1] > thr)
+        move_c[1:num_rows, 1:num_cols] -= (hf[:num_rows - 1, :num_cols - 1] - hf[1:num_rows, 1:num_cols] > thr)
+        xx = xx + (move_x + move_c * (move_x == 0)) * horizontal_scale
+        yy = yy + (move_y + move_c * (move_y == 0)) * horizontal_scale
+    vertices = np.zeros((num_rows * num_cols, 3), dtype=np.float32)
+    vertices[:, 0], vertices[:, 1], vertices[:, 2] = xx.flatten(), yy.flatten(), hf.flatten() * vertical_scale
+    triangles = -np.ones((2 * (num_rows - 1) * (num_cols - 1), 3), dtype=np.uint32)
+    for i in range(num_rows - 1):
+        ind0 = np.arange(0, num_cols - 1) + i * num_cols
+        ind1, ind2, ind3 = ind0 + 1, ind0 + num_cols, ind0 + num_cols + 1
+        start, stop = 2 * i * (num_cols - 1), 2 * i * (num_cols - 1) + 2 * (num_cols - 1)
+        triangles[start:stop:2, 0], triangles[start:stop:2, 1], triangles[start:stop:2, 2] = ind0, ind3, ind1
+        triangles[start + 1:stop:2, 0], triangles[start + 1:stop:2, 1], triangles[start + 1:stop:2, 2] = ind0, ind2, ind3
+    return vertices, triangles
+
+
 # ---- the grid -------------------------------------------------------------------------------------------
 class Terrain:
     def __init__(self, cfg, num_robots, seed=0):
@@ -177,6 +211,24 @@ class Terrain:
         else:
             self.randomized_terrain()
         self.heightsamples = self.height_field_raw
+        self._mesh = None
+
+    def _trimesh(self):      # terrain.py:45-49; built on first use (3 M vertices at the GO2 grid): the simulation itself never reads it
+        if self._mesh is None:
+            self._mesh = convert_heightfield_to_trimesh(self.height_field_raw, self.cfg.horizontal_scale, self.cfg.vertical_scale, self.cfg.slope_treshold)
+        return self._mesh
+
+    @property
+    def vertices(self):
+        if self.type != "trimesh":
+            raise AttributeError("Terrain.vertices exists for mesh_type == 'trimesh' only (terrain.py:44-49)")
+        return self._trimesh()[0]
+
+    @property
+    def triangles(self):
+        if self.type != "trimesh":
+            raise AttributeError("Terrain.triangles exists for mesh_type == 'trimesh' only (terrain.py:44-49)")
+        return self._trimesh()[1]
 
     def randomized_terrain(self):  # terrain.py:51-59
         for k in range(self.cfg.num_sub_terrains):

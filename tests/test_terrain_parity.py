@@ -84,3 +84,33 @@ def test_round_robin_terrain_assignment_uses_torch_float32_semantics(N):
         A = EnvArrays(cfg, "cpu", num_envs=Ns, env_offset=off, num_envs_global=N, seed=1)
         assert torch.equal(A.tensors["terrain_types"].long(), ref_types[off:off + Ns])
         assert int(A.tensors["terrain_types"][0]) == int(ref_types[off]) == (5 if N == 100 else 4)   # the float32 boundary case itself (100 / 20 is exact)
+
+
+def test_trimesh_conversion_makes_steep_edges_vertical():
+    """convert_heightfield_to_trimesh (restated from isaacgym.terrain_utils, unpinned): vertex / triangle counts, heights untouched, and the wall
+    correction of terrain.py:45-49 — across every cell edge steeper than slope_treshold the lower vertex sits on its higher neighbour's xy."""
+    import numpy as np
+    from go2_rl_gym_b200.utils.terrain import convert_heightfield_to_trimesh
+    hf = np.zeros((12, 9), dtype=np.int16)
+    hf[5:, :] = 40                      # a 0.2 m step along x at vertical_scale 0.005: slope 2 > 0.75
+    hf[:, 6:] += 6                      # a 0.03 m step along y: slope 0.3, left alone
+    v, t = convert_heightfield_to_trimesh(hf, 0.1, 0.005, 0.75)
+    assert v.shape == (12 * 9, 3) and t.shape == (2 * 11 * 8, 3) and t.max() == 12 * 9 - 1 and v.dtype == np.float32
+    V = v.reshape(12, 9, 3)
+    assert np.allclose(V[..., 2], hf * 0.005)
+    assert np.allclose(V[4, :, 0], V[5, :, 0]) and np.allclose(V[5, :, 0], 0.5)        # row 4 (low side) moved onto row 5's x
+    assert np.allclose(V[3, :, 0], 0.3) and np.allclose(V[6, :, 0], 0.6)                # the other rows stay on the grid
+    keep = [r for r in range(12) if r != 4]
+    assert np.allclose(V[keep, :, 1], np.arange(9) * 0.1)                               # the shallow step along y moves nothing (row 4 also takes the corner rule)
+    v0, _ = convert_heightfield_to_trimesh(hf, 0.1, 0.005, None)
+    assert np.allclose(v0.reshape(12, 9, 3)[..., 0], (np.arange(12) * 0.1)[:, None])
+    # Terrain exposes the mesh for mesh_type == 'trimesh' (terrain.py:44-49) and only then
+    from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+    from go2_rl_gym_b200.utils.terrain import Terrain
+    cfg = GO2Cfg().terrain
+    cfg.num_rows, cfg.num_cols, cfg.mesh_type = 2, 2, "trimesh"
+    T = Terrain(cfg, 16, seed=1)
+    assert T.vertices.shape[0] == T.tot_rows * T.tot_cols and T.triangles.shape[0] == 2 * (T.tot_rows - 1) * (T.tot_cols - 1)
+    cfg.mesh_type = "heightfield"
+    with pytest.raises(AttributeError):
+        Terrain(cfg, 16, seed=1).vertices
