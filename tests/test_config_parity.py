@@ -79,3 +79,20 @@ def test_command_range_curriculum_after_a_late_resume():
         for key in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw"):
             assert list(walk.command_ranges[key]) == list(e[key]), (e["iter"], key)
     assert late.tensors["env_command_ranges"].equal(walk.tensors["env_command_ranges"])
+
+
+def test_step_params_memo_equals_a_fresh_block():
+    """EnvArrays.step_params reuses the previous call's block while the iteration and the curriculum scales stand (the host-buffer loop calls it every
+    step): the memoised block must equal a freshly built one byte for byte, across iteration boundaries, reward-curriculum changes and the
+    command-range curriculum boundary at learning iteration 20 000."""
+    from go2_rl_gym_b200.envs.env_arrays import EnvArrays
+    from go2_rl_gym_b200.envs.go2.go2_config import GO2Cfg
+    cfg = GO2Cfg(); cfg.env.num_envs = 16; cfg.terrain.mesh_type = "plane"
+    A, B = EnvArrays(cfg, "cpu", seed=1), EnvArrays(cfg, "cpu", seed=1)
+    for c in list(range(24 * 99, 24 * 101 + 3)) + list(range(24 * 19999, 24 * 20001 + 2)):
+        rc = {"lin_vel_z": 1.0 - (c // 24 % 7) / 7.0}
+        a = A.step_params(c, ep_slot=c % 64, reward_curriculum=rc)
+        B._sp_memo = None
+        b = B.step_params(c, ep_slot=c % 64, reward_curriculum=rc)
+        assert bytes(a) == bytes(b), c
+        assert a.common_step_counter == c and a.ep_slot == c % 64
