@@ -1,6 +1,7 @@
 // env_step.cu — sm_100a kernels of the fused Go2 environment step and their C ABI (include/go2_b200.h).
-// One warp per env (lane roles in env_step_core.cuh), 4 envs per CTA, per-env rows read/written coalesced,
-// per-link inertias and all solver state staged in shared memory.
+// The step body (phases, roles) is env_step_core.cuh; this file holds one kernel per thread map — default "H14" = step_kernel_half: 14 envs per 9-warp
+// CTA, half a warp per env + dedicated leg warps, 28 envs resident per SM — the per-env rows read / written coalesced, per-link inertias and all solver
+// state staged in shared memory.
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdio>

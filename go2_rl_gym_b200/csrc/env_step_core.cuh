@@ -16,9 +16,11 @@
 //         i = lane + 32 k · observation columns i = lane + 32 k · the scalar per-env bookkeeping on lane 0.
 //   LEGS  one thread per (env, leg): the serial 6x6 articulated-body recursions along hip -> thigh -> calf, and (redundantly on the 4
 //         leg threads of an env) the base's 6x6 inverse and impulse response, so that consecutive LEGS phases only need a warp sync.
-// Two thread maps exist.  "warp per env": LEGS = lanes 0..3 of the env's own warp (28 lanes idle in the heaviest phases).
+// Three families of thread maps exist (init_roles).  "warp per env": LEGS = lanes 0..3 of the env's own warp (28 lanes idle in the heaviest phases).
 // "packed": a CTA of 8 warps owns 8 envs and the 32 (env, leg) items fill warp 0, so the long serial leg code is issued once per
 // 8 envs instead of once per env; WIDE <-> LEGS transitions are CTA barriers, LEGS -> LEGS transitions stay inside warp 0.
+// "half-warp" (H14, the default): 16 threads per env, each running a WIDE block for two "virtual lanes" (T::NV = 2), and dedicated LEGS warps
+// compiled as their own instantiation (T::ROLE): 14 envs per 9-warp CTA at 96 registers, 28 envs resident per SM.
 #pragma once
 #include <stdint.h>
 #include <math.h>
